@@ -1,0 +1,259 @@
+"""ctypes binding of libgaml_b200.so (include/gaml_b200.h) + a thin `ProbCalculator` mirror.
+
+This module is plumbing for tests and bench.py: the product is the C ABI. It never touches oracle/.
+`ProbCalculator.calc_prob(paths)` has the meaning of the reference's
+`ProbCalculator::CalcProb(paths, zeros, total_len)` (prob_calculator.h:63-109): same statefulness, same
+outputs. The library has no CPU fallback; creating a context without a B200 raises GamlError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .workload import ALN_DTYPE, KIND_PACBIO, KIND_PAIRED, PB_DTYPE, ReadSetSpec, Workload
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgaml_b200.so")
+
+INT32_MIN = -(2 ** 31)
+
+
+class GamlError(RuntimeError):
+    pass
+
+
+class ReadsetConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("mismatch_prob", C.c_double),
+                ("match_prob", C.c_double), ("insert_mean", C.c_double), ("insert_std", C.c_double),
+                ("min_prob_per_base", C.c_double), ("min_prob_start", C.c_double), ("weight", C.c_double),
+                ("penalty_constant", C.c_double), ("step", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("prob", C.c_double), ("total_len", C.c_int32), ("n_sets", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("evals", C.c_int64), ("last_records_gathered", C.c_int64),
+                ("last_reads_scanned", C.c_int64), ("last_algorithmic_bytes", C.c_int64),
+                ("last_h2d_bytes", C.c_int64), ("last_d2h_bytes", C.c_int64), ("last_device_ms", C.c_double),
+                ("last_score_kernel_ms", C.c_double), ("last_was_full", C.c_int32),
+                ("last_overflow_reads", C.c_int32)]
+
+
+EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream", "gaml_set_graph",
+           "gaml_add_readset", "gaml_cache_insert", "gaml_cache_insert_pacbio", "gaml_cache_contains",
+           "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials",
+           "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
+           "gaml_get_stats"]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the in-tree CUDA library; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GamlError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, i64p, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    lib.gaml_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.gaml_ctx_destroy.argtypes = [vp]
+    lib.gaml_ctx_destroy.restype = None
+    lib.gaml_last_error.argtypes = [vp]
+    lib.gaml_last_error.restype = C.c_char_p
+    lib.gaml_ctx_stream.argtypes = [vp]
+    lib.gaml_ctx_stream.restype = vp
+    lib.gaml_set_graph.argtypes = [vp, C.c_int32, i32p, i32p]
+    lib.gaml_add_readset.argtypes = [vp, C.POINTER(ReadsetConfig), C.c_int64, C.c_int64, C.c_int64, i32p, i32p,
+                                     C.c_int32, C.c_int32]
+    lib.gaml_cache_insert.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int32, vp, C.c_int64, C.c_int32]
+    lib.gaml_cache_insert_pacbio.argtypes = [vp, C.c_int, i32p, C.c_int32, vp, C.c_int64]
+    lib.gaml_cache_contains.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int32]
+    lib.gaml_cache_commit.argtypes = [vp]
+    lib.gaml_calc_prob.argtypes = [vp, i32p, i64p, C.c_int32, C.POINTER(Result), i32p]
+    lib.gaml_calc_prob_partial.argtypes = [vp, i32p, i64p, C.c_int32, dp, i32p]
+    lib.gaml_combine_partials.argtypes = [vp, dp, C.c_int32, C.c_int32, C.POINTER(Result), i32p]
+    lib.gaml_eval_prepare.argtypes = [vp, i32p, i64p, C.c_int32]
+    lib.gaml_eval_launch.argtypes = [vp]
+    lib.gaml_eval_finish.argtypes = [vp, dp, i32p]
+    lib.gaml_reset_state.argtypes = [vp]
+    lib.gaml_read_values.argtypes = [vp, C.c_int, dp, C.c_int64]
+    lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    for name in EXPORTS:
+        if name not in ("gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p32(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def flatten_walks(walks: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    offs = np.zeros(len(walks) + 1, dtype=np.int64)
+    for i, w in enumerate(walks):
+        offs[i + 1] = offs[i] + len(w)
+    nodes = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
+    for i, w in enumerate(walks):
+        nodes[offs[i]:offs[i + 1]] = w
+    return nodes, offs
+
+
+class ProbCalculator:
+    """Mirror of the reference's `ProbCalculator` over the C ABI (one context, one CUDA stream)."""
+
+    def __init__(self, node_len, normalize_map=None, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.gaml_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise GamlError(f"gaml_ctx_create failed ({rc}): {self.lib.gaml_last_error(None).decode()}")
+        self.h = h
+        nl = _i32(node_len)
+        nm = _i32(normalize_map) if normalize_map is not None else None
+        self._check(self.lib.gaml_set_graph(self.h, len(nl), _p32(nl), _p32(nm) if nm is not None else None))
+        self.sets: List[dict] = []
+
+    # -- plumbing --
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise GamlError(f"gaml_b200 error {rc}: {self.lib.gaml_last_error(self.h).decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gaml_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.gaml_ctx_stream(self.h) or 0)
+
+    # -- read sets / cache --
+    def add_readset(self, spec: ReadSetSpec, shard: Optional[Tuple[int, int]] = None,
+                    max_read_len: Optional[Sequence[int]] = None, lens_are_local: bool = False) -> int:
+        lo, hi = shard if shard is not None else (0, spec.n_reads)
+        cfg = ReadsetConfig(kind=spec.kind, mismatch_prob=spec.mismatch_prob, match_prob=spec.match_prob,
+                            insert_mean=spec.insert_mean, insert_std=spec.insert_std,
+                            min_prob_per_base=spec.min_prob_per_base, min_prob_start=spec.min_prob_start,
+                            weight=spec.weight, penalty_constant=spec.penalty_constant, step=spec.step)
+        lens = [_i32(rl if lens_are_local else rl[lo:hi]) for rl in spec.read_len]
+        if max_read_len is None:
+            max_read_len = [int(rl.max()) if len(rl) else 0 for rl in spec.read_len]
+        l2 = _p32(lens[1]) if spec.kind == KIND_PAIRED else None
+        m2 = int(max_read_len[1]) if spec.kind == KIND_PAIRED else -1
+        sid = self._check(self.lib.gaml_add_readset(self.h, C.byref(cfg), spec.n_reads, lo, hi, _p32(lens[0]), l2,
+                                                    int(max_read_len[0]), m2))
+        self.sets.append({"spec": spec, "lo": lo, "hi": hi})
+        return sid
+
+    def cache_insert(self, set_id: int, mate: int, key: Sequence[int], records: np.ndarray,
+                     key_max_position: int = INT32_MIN) -> None:
+        k = _i32(key)
+        spec = self.sets[set_id]["spec"]
+        if spec.kind == KIND_PACBIO:
+            r = np.ascontiguousarray(records, dtype=PB_DTYPE)
+            self._check(self.lib.gaml_cache_insert_pacbio(self.h, set_id, _p32(k), len(k), r.ctypes.data, len(r)))
+        else:
+            r = np.ascontiguousarray(records, dtype=ALN_DTYPE)
+            self._check(self.lib.gaml_cache_insert(self.h, set_id, mate, _p32(k), len(k), r.ctypes.data, len(r),
+                                                   key_max_position))
+
+    def cache_contains(self, set_id: int, mate: int, key: Sequence[int]) -> bool:
+        k = _i32(key)
+        return bool(self._check(self.lib.gaml_cache_contains(self.h, set_id, mate, _p32(k), len(k))))
+
+    def commit(self) -> None:
+        self._check(self.lib.gaml_cache_commit(self.h))
+
+    @classmethod
+    def from_workload(cls, wl: Workload, device: int = 0, shard_of=None) -> "ProbCalculator":
+        """Loads every read set and injected cache of a workload. shard_of=(rank, world) keeps the
+        contiguous read-id block of that rank for each set."""
+        pc = cls(wl.node_len, wl.normalize_map, device)
+        for spec in wl.sets:
+            shard = None
+            if shard_of is not None:
+                rank, world = shard_of
+                per = (spec.n_reads + world - 1) // world
+                shard = (min(rank * per, spec.n_reads), min((rank + 1) * per, spec.n_reads))
+            sid = pc.add_readset(spec, shard)
+            for mate, cache in enumerate(spec.caches):
+                for key, recs in cache.items():
+                    pc.cache_insert(sid, mate, key, recs)
+        pc.commit()
+        return pc
+
+    # -- scoring --
+    def calc_prob(self, paths: Sequence[Sequence[int]]):
+        """-> (prob, zeros [(floored, n_reads)] per set, total_len)."""
+        nodes, offs = flatten_walks(paths)
+        res = Result()
+        zeros = np.zeros(2 * max(len(self.sets), 1), dtype=np.int32)
+        self._check(self.lib.gaml_calc_prob(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                            len(paths), C.byref(res), _p32(zeros)))
+        z = [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(self.sets))]
+        return res.prob, z, res.total_len
+
+    def calc_prob_partial(self, paths: Sequence[Sequence[int]]):
+        nodes, offs = flatten_walks(paths)
+        part = np.zeros(3 * max(len(self.sets), 1), dtype=np.float64)
+        tl = C.c_int32()
+        self._check(self.lib.gaml_calc_prob_partial(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    len(paths), part.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    C.byref(tl)))
+        return part, tl.value
+
+    def combine(self, gathered: np.ndarray, n_shards: int, total_len: int):
+        g = np.ascontiguousarray(gathered, dtype=np.float64)
+        res = Result()
+        zeros = np.zeros(2 * max(len(self.sets), 1), dtype=np.int32)
+        self._check(self.lib.gaml_combine_partials(self.h, g.ctypes.data_as(C.POINTER(C.c_double)), n_shards,
+                                                   total_len, C.byref(res), _p32(zeros)))
+        z = [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(self.sets))]
+        return res.prob, z, res.total_len
+
+    def prepare(self, paths):
+        nodes, offs = flatten_walks(paths)
+        self._check(self.lib.gaml_eval_prepare(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               len(paths)))
+
+    def launch(self):
+        self._check(self.lib.gaml_eval_launch(self.h))
+
+    def finish(self):
+        part = np.zeros(3 * max(len(self.sets), 1), dtype=np.float64)
+        tl = C.c_int32()
+        self._check(self.lib.gaml_eval_finish(self.h, part.ctypes.data_as(C.POINTER(C.c_double)), C.byref(tl)))
+        return part, tl.value
+
+    def reset_state(self):
+        self._check(self.lib.gaml_reset_state(self.h))
+
+    def read_values(self, set_id: int) -> np.ndarray:
+        n = self.sets[set_id]["hi"] - self.sets[set_id]["lo"]
+        out = np.zeros(max(n, 1), dtype=np.float64)
+        self._check(self.lib.gaml_read_values(self.h, set_id, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return out[:n]
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.gaml_get_stats(self.h, C.byref(s)))
+        return s

@@ -1,0 +1,102 @@
+// Plain structs shared by the host engine and the sm_100a kernels. Layout in HBM is documented in
+// DESIGN.md §3; every struct is 16 or 32 bytes so one record is one (or two) 128-bit transactions.
+#pragma once
+#include <cstdint>
+
+namespace gaml {
+
+// One occurrence of a cache key in the walks of the current evaluation ("segment"): produced on the
+// host by walking the reference's lookup loops (graph.cc:547-597 paired, 613-646 single,
+// 2438-2500 pacbio) without touching any record.
+struct Occ {
+  int32_t walk;        // ordinal of the walk in this evaluation (erased walks first, then added)
+  int32_t seg;         // global enumeration index of the lookup (walk-major) — the reference's order
+  int32_t cur_pos;     // offset added to every record position (graph.cc:575, 636, 2497)
+  int32_t skip_below;  // records with position+cur_pos below this are skipped (max_pos-5, graph.cc:577)
+};
+
+// Device-resident table indexed by key id. A slot is live iff epoch == the evaluation's epoch, so an
+// evaluation only writes the slots of the keys it touches. The first occurrence is inline.
+struct KeySlot {
+  uint32_t epoch;
+  int32_t n_occ;
+  int32_t occ_begin;   // into the evaluation's Occ array (all n_occ occurrences, first included)
+  int32_t pad;
+  Occ first;
+};
+static_assert(sizeof(KeySlot) == 32, "KeySlot is two 128-bit words");
+
+struct SlotUpdate {    // host -> device, scattered into KeySlot[key] by apply_slots_kernel
+  int32_t key;
+  int32_t n_occ;
+  int32_t occ_begin;
+  int32_t store;       // which mate store's slot table
+  Occ first;
+};
+static_assert(sizeof(SlotUpdate) == 32, "");
+
+// Key-major arena (mirror of aligment_cache_: keys in insertion order, records in list order).
+struct ArenaShort { int32_t read; int32_t pos; int32_t edor; int32_t key; };   // edor = edit_dist | orientation<<30
+struct ArenaLong { int32_t read; int32_t key; double logprob; };
+// Read-major CSR rows built from the arena on the device; seq = arena index = reference list order.
+struct RowShort { int32_t key; int32_t pos; int32_t edor; uint32_t seq; };
+struct RowLong { int32_t key; uint32_t seq; double logprob; };
+static_assert(sizeof(ArenaShort) == 16 && sizeof(ArenaLong) == 16 && sizeof(RowShort) == 16 && sizeof(RowLong) == 16, "");
+
+// A record placed on a walk of the current evaluation.
+struct Plc {
+  unsigned long long ord;   // (seg << 32) | seq : the reference's enumeration order
+  int32_t walk;
+  int32_t pos;
+  int32_t edor;
+  int32_t pad;
+};
+struct PlcLong {
+  unsigned long long ord;
+  double logprob;
+};
+
+struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one touched mate-1 key
+
+constexpr int kPartialStride = 4;   // per block: sum_hi, sum_lo, floored, spare
+
+struct MateView {
+  const void* rows;          // RowShort* / RowLong*
+  const uint32_t* rowptr;    // n_reads + 1
+  const KeySlot* slots;
+  const Occ* occ;
+  const double* pow_match;   // match^k     (graph.cc:1451)
+  const double* pow_mismatch;// mismatch^k  (graph.cc:1452)
+};
+
+struct ScoreParams {
+  MateView m[2];
+  const uint32_t* lens;      // single/pacbio: read length; paired: len1 | len2<<16
+  const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)
+  int32_t ins_n;
+  const double* thr_tab;     // single/paired: exp(mps + mppb*len) indexed by len (paired: len1+len2)
+  double floor_a, floor_b;   // pacbio: log(exp(mps)), log(exp(mppb)) (graph.cc:3075-3076)
+  double* values;            // paired: ScoringState::probs; single: sum p1; pacbio: LSE
+  uint32_t epoch;
+  int32_t n_erased;          // walks with ordinal < n_erased are subtracted (paired)
+  int32_t n_reads;           // reads in this shard
+  int32_t two_len;           // 2*total_len as the reference's int expression (total_len==0 -> 1)
+  // many-placement reads
+  uint32_t* ovf_count;
+  uint32_t* ovf_list;
+  uint32_t ovf_cap;
+  Plc* scratch;              // also used as PlcLong (same size)
+  unsigned long long* scratch_cursor;
+  unsigned long long scratch_cap;
+  uint32_t* error_flag;
+  // reduction
+  double* partials;          // [n_partial_blocks][kPartialStride]
+  // delta discovery
+  const ArenaShort* arena1;
+  const TouchRange* touch;
+  const uint32_t* touch_prefix;   // n_touch + 1
+  int32_t n_touch;
+  uint32_t* stamp;           // per read: epoch of the evaluation that last claimed it
+};
+
+}  // namespace gaml

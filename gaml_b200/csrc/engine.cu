@@ -1,0 +1,1090 @@
+// Host engine + C ABI (include/gaml_b200.h) of the B200 GAML likelihood path.
+//
+// Host side responsibilities, all O(#nodes in the touched walks), never O(records):
+//   * mirror of aligment_cache_ (graph.h:427, 587): key -> id map, per-key arena range / max position;
+//   * GetChanges (graph.cc:1745-1764) on the same container + hash as the reference so erased walks
+//     come out in the same order;
+//   * flattening of walks into per-key occurrence tables following the reference's three lookup
+//     rules (graph.cc:547-597, 613-646, 2438-2500) — see flatten_*();
+//   * host-computed constant tables (pow tables graph.cc:1448-1453, insert pdf graph.cc:1593-1598,
+//     floor thresholds graph.cc:1506-1507/1528) so that those values are bit-identical to the
+//     reference's on the same host.
+// Everything that touches an alignment record runs in kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/gaml_b200.h"
+#include "kernels.h"
+
+namespace gaml {
+namespace {
+
+using Walk = std::vector<int>;
+constexpr int kWindowLen = 300;   // kMinSubpathLength, graph.cc:27
+
+// graph.h:21-45: the reference's hash for vector<int>; it fixes the iteration order of the
+// unordered_multiset in GetChanges, hence the order in which erased walks are subtracted.
+struct WalkHash {
+  size_t operator()(const Walk& v) const {
+    size_t seed = 0;
+    for (size_t i = 0; i < v.size(); i++) seed ^= std::hash<int>()(v[i]) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+    return seed;
+  }
+};
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  // grows (contents preserved when keep > 0); new space zeroed when zero_new
+  cudaError_t reserve(size_t bytes, size_t keep, bool zero_new, cudaStream_t st) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap + cap / 2);
+    ncap = (ncap + 255) & ~size_t(255);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (zero_new) {
+      e = cudaMemsetAsync(np, 0, ncap, st);
+      if (e != cudaSuccess) return e;
+    }
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    if (p) {
+      cudaStreamSynchronize(st);
+      cudaFree(p);
+    }
+    p = np;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct KeyMeta {
+  uint32_t arena_off = 0;   // into the store's arena (shard-local records)
+  uint32_t count = 0;       // shard-local records
+  int32_t max_pos = 0;      // over ALL reads' records
+  bool any = false;         // the key has at least one record (any read)
+};
+
+struct MateStore {
+  bool is_long = false;
+  std::unordered_map<Walk, int, WalkHash> key_ids;
+  std::vector<KeyMeta> keys;
+  std::vector<int4> pending;          // staged arena records (ArenaShort / ArenaLong bit patterns)
+  size_t arena_n = 0;                 // records on the device
+  DevBuf arena, rows, rowptr, cursor, slots;
+  bool dirty = true;
+  std::vector<double> pow_match, pow_mismatch;
+  DevBuf d_pow_match, d_pow_mismatch;
+  int table_index = -1;               // position in ctx->d_tables
+  size_t total_records() const { return arena_n + pending.size(); }
+};
+
+struct ReadSetState {
+  gaml_readset_config cfg{};
+  int64_t n_total = 0, lo = 0, hi = 0;
+  int n_local = 0;
+  int n_mates = 1;
+  int max_len[2] = {0, 0};
+  std::vector<int32_t> len[2];
+  MateStore mate[2];
+  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list;
+  int ins_n = 0;
+  double floor_a = 0, floor_b = 0;
+  // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
+  std::vector<Walk> old_walks;
+  bool has_state = false;
+};
+
+struct SetPlan {
+  bool full = true;
+  int n_erased = 0;
+  int total_len = 0;
+  int64_t records = 0;          // A: live (record, occurrence) pairs in this shard
+  int64_t touch_records = 0;
+  int grid = 0;                 // blocks of the reducing kernel
+  int n_partials = 0;
+  int partial_begin = 0;
+  size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
+  size_t touch_off = 0, prefix_off = 0;
+  int n_touch = 0;
+};
+
+}  // namespace
+}  // namespace gaml
+
+using namespace gaml;
+
+struct gaml_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string error;
+  std::vector<int32_t> node_len, nmap;
+  std::vector<std::unique_ptr<ReadSetState>> sets;
+  std::vector<MateStore*> stores;
+  DevBuf d_tables;                // KeySlot* per store
+  bool tables_dirty = true;
+  DevBuf d_blob;                  // per-evaluation staging (updates, occurrences, touch ranges, set_begin)
+  void* h_blob = nullptr;         // pinned
+  size_t h_blob_cap = 0;
+  DevBuf d_partials, d_out, d_flags, d_scratch, d_csr_temp;
+  double* h_out = nullptr;        // pinned, 4 doubles per set
+  size_t h_out_cap = 0;
+  unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
+  uint32_t ovf_cap = 1u << 20;
+  uint32_t epoch = 0;
+  // pending evaluation
+  bool prepared = false, launched = false;
+  std::vector<SetPlan> plan;
+  std::vector<Walk> plan_walks;
+  int n_updates = 0;
+  size_t upd_off = 0, setbegin_off = 0, blob_bytes = 0;
+  int n_partials_total = 0;
+  gaml_stats stats{};
+};
+
+namespace gaml {
+namespace {
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      ctx->error = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+      return GAML_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+int fail(gaml_ctx* ctx, int code, const std::string& msg) {
+  ctx->error = msg;
+  return code;
+}
+
+double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, same expression order
+  double z = (d - mean) / sd;
+  double e = exp(-z * z / 2.0);
+  double c = sqrt(2 * M_PI) * sd;
+  return e / c;
+}
+
+// ---- walk helpers -------------------------------------------------------------------------
+int walk_length(const gaml_ctx* ctx, const Walk& w) {   // graph.cc:1766-1773
+  int t = 0;
+  for (int x : w) t += x < 0 ? -x : ctx->node_len[x];
+  return t;
+}
+
+void split_at_gaps(const Walk& w, std::vector<Walk>& ctgs, std::vector<int>& gaps) {   // graph.cc:1813-1824
+  ctgs.assign(1, Walk());
+  gaps.clear();
+  for (int x : w) {
+    if (x < 0) {
+      gaps.push_back(-x);
+      ctgs.emplace_back();
+    } else {
+      ctgs.back().push_back(x);
+    }
+  }
+}
+
+void window_key(const gaml_ctx* ctx, const Walk& ctg, size_t i, Walk& key) {   // graph.cc:552-561, 618-627
+  key.assign(1, ctg[i]);
+  int beyond = 0;
+  for (size_t j = i + 1; j < ctg.size(); j++) {
+    beyond += ctx->node_len[ctg[j]];
+    key.push_back(ctg[j]);
+    if (beyond > kWindowLen) break;
+  }
+}
+
+int find_key(const MateStore& st, const Walk& key) {
+  auto it = st.key_ids.find(key);
+  return it == st.key_ids.end() ? -1 : it->second;
+}
+
+// Per-store accumulation of the occurrences of one evaluation.
+struct OccBuilder {
+  std::vector<std::pair<int, Occ>> items;   // (key id, occurrence) in enumeration order
+  int next_seg = 0;
+  void add(int key, int walk, int cur_pos, int skip_below) {
+    items.push_back({key, Occ{walk, next_seg++, cur_pos, skip_below}});
+  }
+};
+
+// Paired lookup rule (ReadSet::GetPositionsOnlyPath, graph.cc:535-598) for one walk, both mates.
+void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, int ord, OccBuilder ob[2],
+                         SetPlan& sp, std::vector<TouchRange>* touch) {
+  std::vector<Walk> ctgs;
+  std::vector<int> gaps;
+  split_at_gaps(walk, ctgs, gaps);
+  Walk key;
+  int cur_len = 0;
+  for (size_t c = 0; c < ctgs.size(); c++) {
+    if (c > 0) cur_len += gaps[c - 1];
+    const Walk& ctg = ctgs[c];
+    int ctg_len = 0;
+    for (int m = 0; m < 2; m++) {
+      MateStore& st = rs.mate[m];
+      int cur = cur_len, seen_max = 0;
+      for (size_t i = 0; i < ctg.size(); i++) {
+        int node_max = 0;
+        window_key(ctx, ctg, i, key);
+        int kid[2] = {find_key(st, key), -1};
+        if (ctx->node_len[ctg[i]] > kWindowLen) {
+          if (key.size() == 1) kid[1] = -1;   // window key IS the single-node key: the second lookup re-visits
+                                              // the same list at the same offset, a no-op under the de-dup rule
+          else { Walk one(1, ctg[i]); kid[1] = find_key(st, one); }
+        }
+        for (int t = 0; t < 2; t++) {
+          if (kid[t] < 0) continue;
+          const KeyMeta& km = st.keys[kid[t]];
+          const int skip = seen_max - 5;   // graph.cc:577
+          if (km.count) {
+            ob[m].add(kid[t], ord, cur, skip);
+            sp.records += km.count;
+            if (m == 0 && touch) touch->push_back(TouchRange{km.arena_off, km.count});
+          }
+          if (km.any) {
+            const int gp = (int)((unsigned)km.max_pos + (unsigned)cur);
+            if (gp >= skip) node_max = std::max(node_max, gp);   // graph.cc:580
+          }
+        }
+        cur += ctx->node_len[ctg[i]];
+        seen_max = std::max(seen_max, node_max);   // graph.cc:596
+      }
+      ctg_len = cur - cur_len;
+    }
+    cur_len += ctg_len;
+  }
+}
+
+// Single lookup rule (CalcScoreForPaths + ReadSet::AddPositions, graph.cc:1665-1686, 600-649).
+void flatten_single(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Walk>& walks, OccBuilder& ob, SetPlan& sp) {
+  std::vector<Walk> ctgs;
+  std::vector<int> gaps;
+  Walk key;
+  unsigned stride = 0, tl = 0;
+  for (const Walk& w : walks) {
+    split_at_gaps(w, ctgs, gaps);
+    for (size_t c = 0; c < ctgs.size(); c++) {
+      if (c > 0) tl += (unsigned)gaps[c - 1];
+      unsigned cur = stride + tl;
+      for (size_t i = 0; i < ctgs[c].size(); i++) {
+        tl += (unsigned)ctx->node_len[ctgs[c][i]];
+        window_key(ctx, ctgs[c], i, key);
+        int kid = find_key(rs.mate[0], key);
+        if (kid >= 0 && rs.mate[0].keys[kid].count) {
+          ob.add(kid, 0, (int)cur, INT_MIN);
+          sp.records += rs.mate[0].keys[kid].count;
+        }
+        cur += (unsigned)ctx->node_len[ctgs[c][i]];
+      }
+    }
+    stride += 1000000u;   // graph.cc:1685
+  }
+  sp.total_len = (int)tl;
+}
+
+// PacBio lookup rule (PacbioReadSet::GetReadProbabilities, graph.cc:2410-2503) on normalised walks.
+void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Walk>& walks, OccBuilder& ob, SetPlan& sp) {
+  unsigned tl = 0;
+  Walk key;
+  std::vector<int> begin, end;
+  for (Walk w : walks) {
+    for (int& x : w)
+      if (x >= 0) x = ctx->nmap[x];   // graph.h:268-273
+    const size_t n = w.size();
+    begin.resize(n);
+    end.resize(n);
+    int off = 0;
+    for (size_t i = 0; i < n; i++) {
+      begin[i] = off;
+      off += w[i] < 0 ? -w[i] : ctx->node_len[w[i]];
+      end[i] = off;
+    }
+    tl += (unsigned)off;
+    for (size_t i = 0; i < n; i++) {
+      key.clear();
+      for (size_t j = i; j < n; j++) {
+        key.push_back(w[j]);
+        int kid = find_key(rs.mate[0], key);
+        if (kid >= 0 && rs.mate[0].keys[kid].count) {
+          ob.add(kid, 0, begin[i], INT_MIN);
+          sp.records += rs.mate[0].keys[kid].count;
+        }
+        if ((end[j] - begin[i]) - (end[i] - begin[i]) > rs.max_len[0]) break;   // graph.cc:2450
+      }
+    }
+  }
+  sp.total_len = (int)tl;
+}
+
+// Groups a store's occurrences by key: emits one SlotUpdate per key and the Occ array (occurrences of a
+// key contiguous, in enumeration order).
+void group_occurrences(OccBuilder& ob, int table_index, std::vector<SlotUpdate>& updates, std::vector<Occ>& occ) {
+  std::stable_sort(ob.items.begin(), ob.items.end(),
+                   [](const std::pair<int, Occ>& a, const std::pair<int, Occ>& b) { return a.first < b.first; });
+  occ.clear();
+  occ.reserve(ob.items.size());
+  size_t i = 0;
+  while (i < ob.items.size()) {
+    size_t j = i;
+    while (j < ob.items.size() && ob.items[j].first == ob.items[i].first) j++;
+    SlotUpdate u;
+    u.key = ob.items[i].first;
+    u.n_occ = (int)(j - i);
+    u.occ_begin = (int)occ.size();
+    u.store = table_index;
+    u.first = ob.items[i].second;
+    updates.push_back(u);
+    for (size_t t = i; t < j; t++) occ.push_back(ob.items[t].second);
+    i = j;
+  }
+}
+
+int ensure_pinned(gaml_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_blob_cap) return GAML_OK;
+  if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
+  ctx->h_blob = nullptr;
+  size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+  CU(cudaMallocHost(&ctx->h_blob, cap));
+  ctx->h_blob_cap = cap;
+  return GAML_OK;
+}
+
+// Upload staged cache inserts and rebuild the read-major CSR of every dirty store.
+int commit(gaml_ctx* ctx) {
+  for (auto& rsp : ctx->sets) {
+    ReadSetState& rs = *rsp;
+    for (int m = 0; m < rs.n_mates; m++) {
+      MateStore& st = rs.mate[m];
+      if (!st.dirty) continue;
+      const size_t total = st.total_records();
+      if (total > 0xfffffff0ull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 alignment records in one mate store");
+      CU(st.arena.reserve(std::max<size_t>(total, 1) * 16, st.arena_n * 16, false, ctx->stream));
+      if (!st.pending.empty()) {
+        CU(cudaMemcpyAsync(st.arena.as<char>() + st.arena_n * 16, st.pending.data(), st.pending.size() * 16,
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        st.arena_n = total;
+        st.pending.clear();
+        st.pending.shrink_to_fit();
+      }
+      CU(st.rows.reserve(std::max<size_t>(total, 1) * 16, 0, false, ctx->stream));
+      CU(st.rowptr.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
+      CU(st.cursor.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
+      const size_t old_slots = st.slots.cap;
+      CU(st.slots.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(KeySlot), 0, true, ctx->stream));
+      if (st.slots.cap != old_slots) ctx->tables_dirty = true;
+      const size_t temp = csr_temp_bytes(rs.n_local);
+      CU(ctx->d_csr_temp.reserve(std::max<size_t>(temp, 256), 0, false, ctx->stream));
+      int launches = 0;
+      CU(build_csr(st.arena.p, st.arena_n, rs.n_local, st.is_long, st.rowptr.as<uint32_t>(), st.cursor.as<uint32_t>(),
+                   st.rows.p, ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->sm_count, ctx->stream, &launches));
+      ctx->stats.kernel_launches += launches;
+      st.dirty = false;
+    }
+  }
+  if (ctx->tables_dirty) {
+    std::vector<KeySlot*> tabs;
+    for (MateStore* s : ctx->stores) tabs.push_back(s->slots.as<KeySlot>());
+    CU(ctx->d_tables.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(KeySlot*), 0, false, ctx->stream));
+    if (!tabs.empty())
+      CU(cudaMemcpyAsync(ctx->d_tables.p, tabs.data(), tabs.size() * sizeof(KeySlot*), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tables_dirty = false;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAML_OK;
+}
+
+int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walks) {
+  if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
+  if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
+  std::vector<Walk> walks(n_walks);
+  for (int w = 0; w < n_walks; w++) {
+    walks[w].assign(nodes + offs[w], nodes + offs[w + 1]);
+    for (int x : walks[w])
+      if (x >= (int)ctx->node_len.size()) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
+  }
+  int rc = commit(ctx);
+  if (rc != GAML_OK) return rc;
+  ctx->epoch++;
+  if (ctx->epoch == 0) return fail(ctx, GAML_ERR_STATE, "epoch counter wrapped");
+
+  const size_t n_sets = ctx->sets.size();
+  ctx->plan.assign(n_sets, SetPlan());
+  std::vector<SlotUpdate> updates;
+  std::vector<std::vector<Occ>> occs(ctx->stores.size());
+  std::vector<std::vector<TouchRange>> touches(n_sets);
+  int partial_cursor = 0;
+
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    SetPlan& sp = ctx->plan[s];
+    sp.grid = score_grid(rs.n_local, ctx->sm_count);
+    if (rs.cfg.kind == GAML_KIND_PAIRED) {
+      OccBuilder ob[2];
+      std::vector<Walk> erased, added;
+      if (!rs.has_state) {
+        sp.full = true;
+        added = walks;
+      } else {
+        sp.full = false;
+        // GetChanges, graph.cc:1745-1764 — same container, same hash, same insertion order.
+        std::unordered_multiset<Walk, WalkHash> idx(rs.old_walks.begin(), rs.old_walks.end());
+        for (const Walk& w : walks) {
+          auto f = idx.find(w);
+          if (f == idx.end()) added.push_back(w);
+          else idx.erase(f);
+        }
+        erased.insert(erased.end(), idx.begin(), idx.end());
+      }
+      sp.n_erased = (int)erased.size();
+      int ord = 0;
+      std::vector<TouchRange>* tp = sp.full ? nullptr : &touches[s];
+      for (const Walk& w : erased) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp);
+      for (const Walk& w : added) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp);
+      int tl = 0;
+      for (const Walk& w : walks) tl += walk_length(ctx, w);   // GetTotalLen, graph.cc:1966
+      sp.total_len = tl;
+      for (int m = 0; m < 2; m++) group_occurrences(ob[m], rs.mate[m].table_index, updates, occs[rs.mate[m].table_index]);
+      for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
+      sp.n_touch = (int)touches[s].size();
+      sp.n_partials = sp.grid + (sp.full ? 1 : 0);
+    } else {
+      OccBuilder ob;
+      sp.full = true;
+      if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, walks, ob, sp);
+      else flatten_pacbio(ctx, rs, walks, ob, sp);
+      group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
+      sp.n_partials = sp.grid + 1;
+    }
+    sp.partial_begin = partial_cursor;
+    partial_cursor += sp.n_partials;
+  }
+  ctx->n_partials_total = partial_cursor;
+
+  // ---- pack the staging blob: [updates][occ per store][touch + prefix per set][set_begin] -----
+  auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  size_t off = 0;
+  ctx->upd_off = off;
+  off = align16(off + updates.size() * sizeof(SlotUpdate));
+  std::vector<size_t> occ_off(ctx->stores.size());
+  for (size_t i = 0; i < ctx->stores.size(); i++) {
+    occ_off[i] = off;
+    off = align16(off + occs[i].size() * sizeof(Occ));
+  }
+  for (size_t s = 0; s < n_sets; s++) {
+    SetPlan& sp = ctx->plan[s];
+    ReadSetState& rs = *ctx->sets[s];
+    for (int m = 0; m < rs.n_mates; m++) sp.occ_off[m] = occ_off[rs.mate[m].table_index];
+    sp.touch_off = off;
+    off = align16(off + touches[s].size() * sizeof(TouchRange));
+    sp.prefix_off = off;
+    off = align16(off + (touches[s].size() + 1) * sizeof(uint32_t));
+  }
+  ctx->setbegin_off = off;
+  off = align16(off + (n_sets + 1) * sizeof(int));
+  ctx->blob_bytes = off;
+  rc = ensure_pinned(ctx, off);
+  if (rc != GAML_OK) return rc;
+  char* hb = static_cast<char*>(ctx->h_blob);
+  if (!updates.empty()) memcpy(hb + ctx->upd_off, updates.data(), updates.size() * sizeof(SlotUpdate));
+  for (size_t i = 0; i < ctx->stores.size(); i++)
+    if (!occs[i].empty()) memcpy(hb + occ_off[i], occs[i].data(), occs[i].size() * sizeof(Occ));
+  for (size_t s = 0; s < n_sets; s++) {
+    SetPlan& sp = ctx->plan[s];
+    if (!touches[s].empty()) memcpy(hb + sp.touch_off, touches[s].data(), touches[s].size() * sizeof(TouchRange));
+    uint32_t* pre = reinterpret_cast<uint32_t*>(hb + sp.prefix_off);
+    uint64_t acc = 0;
+    for (size_t t = 0; t < touches[s].size(); t++) {
+      pre[t] = (uint32_t)acc;
+      acc += touches[s][t].count;
+    }
+    if (acc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one evaluation");
+    pre[touches[s].size()] = (uint32_t)acc;
+  }
+  int* sb = reinterpret_cast<int*>(hb + ctx->setbegin_off);
+  for (size_t s = 0; s < n_sets; s++) sb[s] = ctx->plan[s].partial_begin;
+  sb[n_sets] = partial_cursor;
+  ctx->n_updates = (int)updates.size();
+
+  CU(ctx->d_blob.reserve(std::max<size_t>(off, 256), 0, false, ctx->stream));
+  CU(ctx->d_partials.reserve(std::max<size_t>((size_t)partial_cursor, 1) * kPartialStride * sizeof(double), 0, false, ctx->stream));
+  CU(ctx->d_out.reserve(std::max<size_t>(n_sets, 1) * 4 * sizeof(double), 0, false, ctx->stream));
+  CU(ctx->d_flags.reserve((2 + 2 * std::max<size_t>(n_sets, 1)) * sizeof(unsigned long long), 0, true, ctx->stream));
+  CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
+  if (ctx->h_out_cap < n_sets * 4 + 4) {
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    ctx->h_out = nullptr;
+    CU(cudaMallocHost(&ctx->h_out, (n_sets * 4 + 4) * sizeof(double)));
+    ctx->h_out_cap = n_sets * 4 + 4;
+  }
+  CU(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.last_h2d_bytes = (int64_t)off;
+  ctx->plan_walks.swap(walks);
+  ctx->prepared = true;
+  ctx->launched = false;
+  return GAML_OK;
+}
+
+// d_flags layout: [0] scratch cursor (u64) | [1] error flag (u32) | then per set one u32 overflow counter (in u64 slots)
+ScoreParams make_params(gaml_ctx* ctx, size_t s) {
+  ReadSetState& rs = *ctx->sets[s];
+  const SetPlan& sp = ctx->plan[s];
+  char* blob = ctx->d_blob.as<char>();
+  ScoreParams P{};
+  for (int m = 0; m < rs.n_mates; m++) {
+    MateStore& st = rs.mate[m];
+    P.m[m].rows = st.rows.p;
+    P.m[m].rowptr = st.rowptr.as<uint32_t>();
+    P.m[m].slots = st.slots.as<KeySlot>();
+    P.m[m].occ = reinterpret_cast<const Occ*>(blob + sp.occ_off[m]);
+    P.m[m].pow_match = st.d_pow_match.as<double>();
+    P.m[m].pow_mismatch = st.d_pow_mismatch.as<double>();
+  }
+  P.lens = rs.d_lens.as<uint32_t>();
+  P.ins_tab = rs.d_ins.as<double>();
+  P.ins_n = rs.ins_n;
+  P.thr_tab = rs.d_thr.as<double>();
+  P.floor_a = rs.floor_a;
+  P.floor_b = rs.floor_b;
+  P.values = rs.d_values.as<double>();
+  P.epoch = ctx->epoch;
+  P.n_erased = sp.n_erased;
+  P.n_reads = rs.n_local;
+  const int tl = sp.total_len == 0 ? 1 : sp.total_len;   // graph.cc:1500-1502
+  P.two_len = (int)(2u * (unsigned)tl);                   // the reference's int expression 2*total_len
+  unsigned long long* fl = ctx->d_flags.as<unsigned long long>();
+  P.scratch_cursor = fl;
+  P.error_flag = reinterpret_cast<uint32_t*>(fl + 1);
+  P.ovf_count = reinterpret_cast<uint32_t*>(fl + 2 + s);
+  P.ovf_list = rs.d_ovf_list.as<uint32_t>();
+  P.ovf_cap = ctx->ovf_cap;
+  P.scratch = ctx->d_scratch.as<Plc>();
+  P.scratch_cap = ctx->scratch_entries;
+  P.partials = ctx->d_partials.as<double>() + (size_t)sp.partial_begin * kPartialStride;
+  P.arena1 = rs.mate[0].arena.as<ArenaShort>();
+  P.touch = reinterpret_cast<const TouchRange*>(blob + sp.touch_off);
+  P.touch_prefix = reinterpret_cast<const uint32_t*>(blob + sp.prefix_off);
+  P.n_touch = sp.n_touch;
+  P.stamp = rs.d_stamp.as<uint32_t>();
+  return P;
+}
+
+int launch(gaml_ctx* ctx) {
+  if (!ctx->prepared) return fail(ctx, GAML_ERR_STATE, "gaml_eval_launch without gaml_eval_prepare");
+  cudaStream_t st = ctx->stream;
+  const size_t n_sets = ctx->sets.size();
+  CU(cudaEventRecord(ctx->ev[0], st));
+  CU(cudaMemsetAsync(ctx->d_flags.p, 0, (2 + 2 * std::max<size_t>(n_sets, 1)) * sizeof(unsigned long long), st));
+  char* blob = ctx->d_blob.as<char>();
+  int launches = 0;
+  if (ctx->n_updates > 0) {
+    launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates,
+                       ctx->d_tables.as<KeySlot*>(), ctx->epoch, st);
+    launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[1], st));
+  int64_t records = 0, reads = 0, bytes = 0;
+  bool any_full = false;
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    const SetPlan& sp = ctx->plan[s];
+    ScoreParams P = make_params(ctx, s);
+    records += sp.records;
+    reads += rs.n_local;
+    if (rs.cfg.kind == GAML_KIND_PAIRED) {
+      if (sp.full) {
+        launch_paired_full(P, sp.grid, sp.grid, st);
+        launches += 2;
+        any_full = true;
+        // rowptr (4+4) + lens (4) + probs write (8) per pair, 16 per record
+        bytes += 16 * sp.records + 20 * (int64_t)rs.n_local;
+      } else {
+        launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, ctx->sm_count, st);
+        launches += sp.touch_records > 0 ? 3 : 1;
+        bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
+      }
+    } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
+      launch_single_full(P, sp.grid, sp.grid, st);
+      launches += 2;
+      bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
+    } else {
+      launch_pacbio_full(P, sp.grid, sp.grid, st);
+      launches += 2;
+      bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
+    }
+  }
+  CU(cudaEventRecord(ctx->ev[2], st));
+  if (n_sets > 0) {
+    unsigned long long* fl = ctx->d_flags.as<unsigned long long>();
+    launch_finalize(ctx->d_partials.as<double>(), reinterpret_cast<const int*>(blob + ctx->setbegin_off), (int)n_sets,
+                    ctx->d_out.as<double>(), reinterpret_cast<const uint32_t*>(fl + 1),
+                    reinterpret_cast<const uint32_t*>(fl + 2), st);
+    launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[3], st));
+  CU(cudaGetLastError());
+  ctx->stats.kernel_launches += launches;
+  ctx->stats.last_records_gathered = records;
+  ctx->stats.last_reads_scanned = reads;
+  ctx->stats.last_algorithmic_bytes = bytes;
+  ctx->stats.last_was_full = any_full ? 1 : 0;
+  ctx->launched = true;
+  return GAML_OK;
+}
+
+int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
+  if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
+  const size_t n_sets = ctx->sets.size();
+  if (n_sets > 0) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out.p, n_sets * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.last_d2h_bytes = (int64_t)(n_sets * 4 * sizeof(double));
+  float ms = 0, ms2 = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  cudaEventElapsedTime(&ms2, ctx->ev[1], ctx->ev[2]);
+  ctx->stats.last_device_ms = ms;
+  ctx->stats.last_score_kernel_ms = ms2;
+  ctx->stats.evals++;
+  ctx->prepared = ctx->launched = false;
+  int tl = 0;
+  uint32_t flags = 0, ovf = 0;
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    const double* o = ctx->h_out + s * 4;
+    if (partials) {
+      partials[s * GAML_PARTIAL_DOUBLES + 0] = o[0];
+      partials[s * GAML_PARTIAL_DOUBLES + 1] = o[1];
+      partials[s * GAML_PARTIAL_DOUBLES + 2] = o[2];
+    }
+    const uint64_t f = (uint64_t)o[3];
+    flags |= (uint32_t)(f & 15);
+    ovf += (uint32_t)(f >> 4);
+    if (rs.cfg.kind == GAML_KIND_PAIRED) {
+      rs.old_walks = ctx->plan_walks;   // graph.cc:1986: state follows the last EVALUATED walks
+      rs.has_state = true;
+    }
+  }
+  // CalcProb leaves the value of the last set it ran: single sets, then paired, then pacbio (prob_calculator.h:70-107)
+  for (int kind = 0; kind < 3; kind++)
+    for (size_t s = 0; s < n_sets; s++)
+      if (ctx->sets[s]->cfg.kind == kind) tl = ctx->plan[s].total_len;
+  if (total_len) *total_len = tl;
+  ctx->stats.last_overflow_reads = (int32_t)ovf;
+  if (flags & 1) return fail(ctx, GAML_ERR_CAPACITY, "too many many-placement reads for the overflow list");
+  if (flags & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
+  return GAML_OK;
+}
+
+int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, gaml_result* result, int32_t* zeros) {
+  const size_t n_sets = ctx->sets.size();
+  if (!gathered || n_shards < 1 || !result) return fail(ctx, GAML_ERR_ARG, "bad combine arguments");
+  std::vector<double> score(n_sets);
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    // shard totals arrive as (hi, lo) pairs; add them in rank order with an error-free transformation
+    double hi = 0, lo = 0, fl = 0;
+    for (int k = 0; k < n_shards; k++) {
+      const double* p = gathered + ((size_t)k * n_sets + s) * GAML_PARTIAL_DOUBLES;
+      double sum = hi + p[0];
+      double bb = sum - hi;
+      double err = (hi - (sum - bb)) + (p[0] - bb);
+      hi = sum;
+      lo += err + p[1];
+      fl += p[2];
+    }
+    const double total = hi + lo;
+    double sc = total / (double)rs.n_total;   // total_prob / total_c, graph.cc:1515, 1536, 3087
+    if (rs.cfg.kind == GAML_KIND_PACBIO) {
+      const int tl = total_len == 0 ? 1 : total_len;
+      sc -= log((double)(int)(2u * (unsigned)tl));   // graph.cc:3087
+    }
+    score[s] = sc;
+    if (zeros) {
+      zeros[2 * s] = (int32_t)fl;
+      zeros[2 * s + 1] = (int32_t)rs.n_total;
+    }
+  }
+  double prob = 0;
+  for (int kind = 0; kind < 3; kind++)   // prob_calculator.h:70-107: single, paired, pacbio
+    for (size_t s = 0; s < n_sets; s++)
+      if (ctx->sets[s]->cfg.kind == kind) prob += score[s] * ctx->sets[s]->cfg.weight;
+  result->prob = prob;
+  result->total_len = total_len;
+  result->n_sets = (int32_t)n_sets;
+  return GAML_OK;
+}
+
+int check_ctx(gaml_ctx* ctx) { return ctx ? GAML_OK : GAML_ERR_ARG; }
+
+}  // namespace
+}  // namespace gaml
+
+// ===========================================================================================
+// C ABI
+// ===========================================================================================
+extern "C" {
+
+int gaml_ctx_create(int device, gaml_ctx** out) {
+  if (!out) return GAML_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return GAML_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return GAML_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return GAML_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "gaml_b200 is built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return GAML_ERR_CUDA;
+  }
+  gaml_ctx* ctx = new gaml_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return GAML_ERR_CUDA;
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return GAML_OK;
+}
+
+void gaml_ctx_destroy(gaml_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->sets.clear();
+  if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  cudaStream_t st = ctx->stream;
+  delete ctx;
+  if (st) cudaStreamDestroy(st);
+}
+
+const char* gaml_last_error(gaml_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+void* gaml_ctx_stream(gaml_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int gaml_set_graph(gaml_ctx* ctx, int32_t n_nodes, const int32_t* node_len, const int32_t* normalize_map) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (n_nodes <= 0 || !node_len) return fail(ctx, GAML_ERR_ARG, "bad graph");
+  ctx->node_len.assign(node_len, node_len + n_nodes);
+  ctx->nmap.resize(n_nodes);
+  for (int i = 0; i < n_nodes; i++) {
+    ctx->nmap[i] = normalize_map ? normalize_map[i] : i;
+    if (ctx->nmap[i] < 0 || ctx->nmap[i] >= n_nodes) return fail(ctx, GAML_ERR_ARG, "normalize_map out of range");
+    if (node_len[i] < 0) return fail(ctx, GAML_ERR_ARG, "negative node length");
+  }
+  return GAML_OK;
+}
+
+int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_reads_total, int64_t shard_lo,
+                     int64_t shard_hi, const int32_t* read_len1, const int32_t* read_len2, int32_t max_read_len1,
+                     int32_t max_read_len2) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (!cfg || n_reads_total < 0 || shard_lo < 0 || shard_hi < shard_lo || shard_hi > n_reads_total)
+    return fail(ctx, GAML_ERR_ARG, "bad read set shape");
+  if (cfg->kind < 0 || cfg->kind > 2) return fail(ctx, GAML_ERR_ARG, "bad read set kind");
+  if (cfg->penalty_constant != 0.0)
+    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0: the coverage-gap penalty (graph.cc:1700-1742, 1893-1919, "
+                                           "3197-3250) is not on the device yet");
+  const int64_t n_local = shard_hi - shard_lo;
+  if (n_local > 0x7fffffff) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^31 reads in one shard");
+  if (n_local > 0 && !read_len1) return fail(ctx, GAML_ERR_ARG, "read_len1 is NULL");
+  const bool paired = cfg->kind == GAML_KIND_PAIRED;
+  if (paired && n_local > 0 && !read_len2) return fail(ctx, GAML_ERR_ARG, "read_len2 is NULL");
+  if (paired && !(cfg->insert_std > 0)) return fail(ctx, GAML_ERR_ARG, "insert_std must be positive");
+  cudaSetDevice(ctx->device);
+  std::unique_ptr<ReadSetState> rsp(new ReadSetState());
+  ReadSetState& rs = *rsp;
+  rs.cfg = *cfg;
+  rs.n_total = n_reads_total;
+  rs.lo = shard_lo;
+  rs.hi = shard_hi;
+  rs.n_local = (int)n_local;
+  rs.n_mates = paired ? 2 : 1;
+  const int32_t* lens[2] = {read_len1, read_len2};
+  const int32_t maxes[2] = {max_read_len1, max_read_len2};
+  for (int m = 0; m < rs.n_mates; m++) {
+    rs.len[m].assign(lens[m], lens[m] + n_local);
+    int mx = 0;
+    for (int v : rs.len[m]) {
+      if (v < 0) return fail(ctx, GAML_ERR_ARG, "negative read length");
+      mx = std::max(mx, v);
+    }
+    if (maxes[m] >= 0) {
+      if (maxes[m] < mx) return fail(ctx, GAML_ERR_ARG, "max_read_len smaller than a given read length");
+      mx = maxes[m];
+    }
+    rs.max_len[m] = mx;
+    if (paired && mx > 0xffff) return fail(ctx, GAML_ERR_CAPACITY, "paired read longer than 65535");
+    MateStore& st = rs.mate[m];
+    st.is_long = cfg->kind == GAML_KIND_PACBIO;
+    if (!st.is_long) {   // ReadSet::CalcMaxReadLen, graph.cc:1448-1453
+      st.pow_match.resize(mx + 7);
+      st.pow_mismatch.resize(mx + 7);
+      for (size_t i = 0; i < st.pow_match.size(); i++) {
+        st.pow_match[i] = pow(cfg->match_prob, (double)i);
+        st.pow_mismatch[i] = pow(cfg->mismatch_prob, (double)i);
+      }
+      CU(st.d_pow_match.reserve(st.pow_match.size() * 8, 0, false, ctx->stream));
+      CU(st.d_pow_mismatch.reserve(st.pow_match.size() * 8, 0, false, ctx->stream));
+      CU(cudaMemcpyAsync(st.d_pow_match.p, st.pow_match.data(), st.pow_match.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(st.d_pow_mismatch.p, st.pow_mismatch.data(), st.pow_match.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  // lengths
+  std::vector<uint32_t> packed(std::max<int64_t>(n_local, 1));
+  for (int64_t i = 0; i < n_local; i++)
+    packed[i] = paired ? ((uint32_t)rs.len[0][i] | ((uint32_t)rs.len[1][i] << 16)) : (uint32_t)rs.len[0][i];
+  CU(rs.d_lens.reserve(packed.size() * 4, 0, false, ctx->stream));
+  CU(cudaMemcpyAsync(rs.d_lens.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(rs.d_values.reserve(std::max<int64_t>(n_local, 1) * 8, 0, true, ctx->stream));
+  CU(rs.d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));
+  if (paired) CU(rs.d_stamp.reserve(std::max<int64_t>(n_local, 1) * 4, 0, true, ctx->stream));
+  // floor thresholds
+  std::vector<double> thr;
+  if (cfg->kind != GAML_KIND_PACBIO) {
+    const int top = rs.max_len[0] + (paired ? rs.max_len[1] : 0);
+    thr.resize(top + 1);
+    for (int l = 0; l <= top; l++) thr[l] = exp(cfg->min_prob_start + cfg->min_prob_per_base * (l));   // graph.cc:1506-1507, 1528
+    CU(rs.d_thr.reserve(thr.size() * 8, 0, false, ctx->stream));
+    CU(cudaMemcpyAsync(rs.d_thr.p, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    rs.floor_a = log(exp(cfg->min_prob_start));      // logdouble(exp(mps)), graph.cc:3075
+    rs.floor_b = log(exp(cfg->min_prob_per_base));   // logdouble(exp(mppb)), graph.cc:3076
+  }
+  // insert-size pdf: the reference tabulates [0,(int)(mean+5 std)) and evaluates the closed form beyond
+  // (graph.cc:1801-1804, 1877-1882). The same closed form is tabulated here on the HOST out to mean+40 std,
+  // where exp(-z*z/2) has underflowed to exactly 0, so the device never evaluates exp for a pair term.
+  std::vector<double> ins;
+  if (paired) {
+    const double top = cfg->insert_mean + 40.0 * cfg->insert_std + 2.0;
+    if (!(top < 64.0 * 1024 * 1024)) return fail(ctx, GAML_ERR_CAPACITY, "insert distribution too wide for the pdf table");
+    rs.ins_n = std::max((int)top, (int)(cfg->insert_mean + 5 * cfg->insert_std));
+    ins.resize(std::max(rs.ins_n, 1));
+    for (int d = 0; d < rs.ins_n; d++) ins[d] = insert_pdf((double)d, cfg->insert_mean, cfg->insert_std);
+    CU(rs.d_ins.reserve(ins.size() * 8, 0, false, ctx->stream));
+    CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int m = 0; m < rs.n_mates; m++) {
+    rs.mate[m].table_index = (int)ctx->stores.size();
+    ctx->stores.push_back(&rs.mate[m]);
+  }
+  ctx->tables_dirty = true;
+  ctx->sets.push_back(std::move(rsp));
+  return (int)ctx->sets.size() - 1;
+}
+
+static int insert_common(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len, MateStore** out_store,
+                         ReadSetState** out_rs) {
+  if (set < 0 || set >= (int)ctx->sets.size()) return fail(ctx, GAML_ERR_ARG, "bad read set index");
+  ReadSetState& rs = *ctx->sets[set];
+  if (mate < 0 || mate >= rs.n_mates) return fail(ctx, GAML_ERR_ARG, "bad mate index");
+  if (!key || key_len <= 0) return fail(ctx, GAML_ERR_ARG, "empty key");
+  *out_store = &rs.mate[mate];
+  *out_rs = &rs;
+  return GAML_OK;
+}
+
+int gaml_cache_insert(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len,
+                      const gaml_alignment* records, int64_t n_records, int32_t key_max_position) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  MateStore* st;
+  ReadSetState* rs;
+  int rc = insert_common(ctx, set, mate, key, key_len, &st, &rs);
+  if (rc) return rc;
+  if (st->is_long) return fail(ctx, GAML_ERR_ARG, "use gaml_cache_insert_pacbio for pacbio sets");
+  if (n_records < 0 || (n_records > 0 && !records)) return fail(ctx, GAML_ERR_ARG, "bad records");
+  Walk k(key, key + key_len);
+  if (st->key_ids.count(k)) return fail(ctx, GAML_ERR_KEY_EXISTS, "cache key inserted twice");
+  KeyMeta km;
+  km.arena_off = (uint32_t)st->total_records();
+  int mx = INT_MIN;
+  const int max_ed = rs->max_len[mate] + 6;
+  for (int64_t i = 0; i < n_records; i++) {
+    const gaml_alignment& a = records[i];
+    if (a.read_id < 0 || a.read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
+    if (a.orientation != 0 && a.orientation != 1) return fail(ctx, GAML_ERR_ARG, "record orientation must be 0 or 1");
+    if (a.edit_dist < 0 || a.edit_dist > max_ed) return fail(ctx, GAML_ERR_ARG, "record edit_dist outside the pow tables");
+    mx = std::max(mx, a.position);
+    if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
+    const int local = (int)(a.read_id - rs->lo);
+    if (rs->len[mate][local] - a.edit_dist < 0) return fail(ctx, GAML_ERR_ARG, "edit_dist larger than the read length");
+    int4 v;
+    v.x = local;
+    v.y = a.position;
+    v.z = a.edit_dist | (a.orientation << 30);
+    v.w = (int)st->keys.size();
+    st->pending.push_back(v);
+    km.count++;
+  }
+  if (key_max_position != INT_MIN) {
+    km.any = true;
+    km.max_pos = key_max_position;
+  } else {
+    km.any = n_records > 0;
+    km.max_pos = n_records > 0 ? mx : 0;
+  }
+  st->key_ids.emplace(std::move(k), (int)st->keys.size());
+  st->keys.push_back(km);
+  st->dirty = true;
+  return GAML_OK;
+}
+
+int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t key_len,
+                             const gaml_pacbio_alignment* records, int64_t n_records) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  MateStore* st;
+  ReadSetState* rs;
+  int rc = insert_common(ctx, set, 0, key, key_len, &st, &rs);
+  if (rc) return rc;
+  if (!st->is_long) return fail(ctx, GAML_ERR_ARG, "not a pacbio set");
+  if (n_records < 0 || (n_records > 0 && !records)) return fail(ctx, GAML_ERR_ARG, "bad records");
+  Walk k(key, key + key_len);
+  if (st->key_ids.count(k)) return fail(ctx, GAML_ERR_KEY_EXISTS, "cache key inserted twice");
+  KeyMeta km;
+  km.arena_off = (uint32_t)st->total_records();
+  for (int64_t i = 0; i < n_records; i++) {
+    const gaml_pacbio_alignment& a = records[i];
+    if (a.read_id < 0 || a.read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
+    if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
+    ArenaLong al;
+    al.read = (int)(a.read_id - rs->lo);
+    al.key = (int)st->keys.size();
+    al.logprob = a.logprob;
+    int4 v;
+    memcpy(&v, &al, 16);
+    st->pending.push_back(v);
+    km.count++;
+  }
+  km.any = n_records > 0;
+  st->key_ids.emplace(std::move(k), (int)st->keys.size());
+  st->keys.push_back(km);
+  st->dirty = true;
+  return GAML_OK;
+}
+
+int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  MateStore* st;
+  ReadSetState* rs;
+  int rc = insert_common(ctx, set, mate, key, key_len, &st, &rs);
+  if (rc) return rc;
+  return st->key_ids.count(Walk(key, key + key_len)) ? 1 : 0;
+}
+
+int gaml_cache_commit(gaml_ctx* ctx) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return commit(ctx);
+}
+
+int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return prepare(ctx, walk_nodes, walk_offsets, n_walks);
+}
+
+int gaml_eval_launch(gaml_ctx* ctx) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return launch(ctx);
+}
+
+int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return finish(ctx, partials, total_len);
+}
+
+int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
+                           double* partials, int32_t* total_len) {
+  int rc = gaml_eval_prepare(ctx, walk_nodes, walk_offsets, n_walks);
+  if (rc) return rc;
+  rc = gaml_eval_launch(ctx);
+  if (rc) return rc;
+  return gaml_eval_finish(ctx, partials, total_len);
+}
+
+int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shards, int32_t total_len, gaml_result* result,
+                          int32_t* zeros) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  return combine(ctx, gathered, n_shards, total_len, result, zeros);
+}
+
+int gaml_calc_prob(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
+                   gaml_result* result, int32_t* zeros) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (!result) return fail(ctx, GAML_ERR_ARG, "result is NULL");
+  for (auto& rs : ctx->sets)
+    if (rs->lo != 0 || rs->hi != rs->n_total)
+      return fail(ctx, GAML_ERR_STATE, "gaml_calc_prob on a sharded context: use gaml_calc_prob_partial + gaml_combine_partials");
+  std::vector<double> partials(std::max<size_t>(ctx->sets.size(), 1) * GAML_PARTIAL_DOUBLES);
+  int32_t tl = 0;
+  int rc = gaml_calc_prob_partial(ctx, walk_nodes, walk_offsets, n_walks, partials.data(), &tl);
+  if (rc) return rc;
+  return combine(ctx, partials.data(), 1, tl, result, zeros);
+}
+
+int gaml_reset_state(gaml_ctx* ctx) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  for (auto& rs : ctx->sets) {
+    rs->has_state = false;
+    rs->old_walks.clear();
+  }
+  return GAML_OK;
+}
+
+int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (set < 0 || set >= (int)ctx->sets.size() || !out) return fail(ctx, GAML_ERR_ARG, "bad arguments");
+  ReadSetState& rs = *ctx->sets[set];
+  if (n != rs.n_local) return fail(ctx, GAML_ERR_ARG, "n must equal the shard's read count");
+  cudaSetDevice(ctx->device);
+  if (n > 0) CU(cudaMemcpyAsync(out, rs.d_values.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GAML_OK;
+}
+
+int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out) {
+  if (check_ctx(ctx) || !out) return GAML_ERR_ARG;
+  *out = ctx->stats;
+  return GAML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,697 @@
+// sm_100a kernels of the GAML assembly-likelihood path. Nothing here is a dense contraction: the work
+// is an integer gather over 16-byte alignment records plus a handful of fp64 operations per record, so
+// the bound is HBM bandwidth and tensor cores are not used.
+//
+// Exactness contract: every product/sum that the reference performs in fp64 is issued
+// with __dmul_rn/__dadd_rn so no FMA contraction can change a bit; the paired state therefore replays
+// ScoringState::probs (graph.cc:1936-1950) bit for bit. Only log/exp/log1p differ from glibc (<= 1-2 ulp).
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.h"
+
+namespace gaml {
+
+namespace {
+
+constexpr int kCap = 8;            // placements per mate handled in registers/local memory
+constexpr int kBlock = 256;
+
+// ---- small helpers ------------------------------------------------------------------------
+__device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+
+__device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+
+// double-double accumulation (error-free TwoSum) so the shard total does not depend on grouping.
+struct DD { double hi, lo; };
+__device__ __forceinline__ void dd_add(DD& a, double b) {
+  double s = __dadd_rn(a.hi, b);
+  double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+  a.hi = s;
+  a.lo = __dadd_rn(a.lo, e);
+}
+__device__ __forceinline__ void dd_merge(DD& a, const DD& b) {
+  dd_add(a, b.hi);
+  a.lo = __dadd_rn(a.lo, b.lo);
+}
+
+// Block reduction of (dd sum, floored count) -> partials[blockIdx.x]; warp shuffles then one smem hop.
+__device__ void block_reduce_store(DD acc, unsigned floored, double* partials) {
+  __shared__ double s_hi[kBlock / 32], s_lo[kBlock / 32];
+  __shared__ unsigned s_fl[kBlock / 32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    DD o;
+    o.hi = __shfl_down_sync(0xffffffffu, acc.hi, off);
+    o.lo = __shfl_down_sync(0xffffffffu, acc.lo, off);
+    dd_merge(acc, o);
+    floored += __shfl_down_sync(0xffffffffu, floored, off);
+  }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_hi[warp] = acc.hi; s_lo[warp] = acc.lo; s_fl[warp] = floored; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DD t{0.0, 0.0};
+    unsigned f = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      dd_merge(t, DD{s_hi[w], s_lo[w]});
+      f += s_fl[w];
+    }
+    double* p = partials + (size_t)blockIdx.x * kPartialStride;
+    p[0] = t.hi;
+    p[1] = t.lo;
+    p[2] = (double)f;
+    p[3] = 0.0;
+  }
+}
+
+// ---- placement enumeration ----------------------------------------------------------------
+// Visits every (record, live occurrence) of one read in one mate store. F(seg, cur-shifted pos, row).
+template <class Row, class F>
+__device__ __forceinline__ void for_each_placement(const MateView& mv, uint32_t epoch, int r, F&& f) {
+  const uint32_t b = __ldg(mv.rowptr + r), e = __ldg(mv.rowptr + r + 1);
+  const Row* rows = static_cast<const Row*>(mv.rows);
+  for (uint32_t i = b; i < e; i++) {
+    const int4 rw = ldg4(rows + i);
+    const int key = rw.x;
+    const int4 hdr = ldg4(mv.slots + key);
+    if ((uint32_t)hdr.x != epoch) continue;
+    const int4 o0 = ldg4(reinterpret_cast<const int4*>(mv.slots + key) + 1);
+    f(o0, rw);
+    for (int t = 1; t < hdr.y; t++) {
+      const int4 ot = ldg4(mv.occ + hdr.z + t);
+      f(ot, rw);
+    }
+  }
+}
+
+__device__ __forceinline__ void sort_by_ord(Plc* p, int n) {
+  for (int i = 1; i < n; i++) {
+    Plc v = p[i];
+    int j = i - 1;
+    while (j >= 0 && p[j].ord > v.ord) { p[j + 1] = p[j]; j--; }
+    p[j + 1] = v;
+  }
+}
+__device__ __forceinline__ void sort_by_ord(PlcLong* p, int n) {
+  for (int i = 1; i < n; i++) {
+    PlcLong v = p[i];
+    int j = i - 1;
+    while (j >= 0 && p[j].ord > v.ord) { p[j + 1] = p[j]; j--; }
+    p[j + 1] = v;
+  }
+}
+
+// De-duplicate [b,e) in place by position: first occurrence keeps the slot, a later record with the
+// same position overwrites its payload (graph.cc:583-592, 635-641). Returns the new end.
+__device__ __forceinline__ int dedup_positions(Plc* p, int b, int e) {
+  int out = b;
+  for (int k = b; k < e; k++) {
+    int t = b;
+    for (; t < out; t++)
+      if (p[t].pos == p[k].pos) break;
+    if (t < out) p[t].edor = p[k].edor;
+    else p[out++] = p[k];
+  }
+  return out;
+}
+
+// ---- paired -------------------------------------------------------------------------------
+__device__ __forceinline__ double align_prob(const MateView& mv, int edor, int len) {
+  const int ed = edor & 0x3fffffff;
+  return __dmul_rn(__ldg(mv.pow_mismatch + ed), __ldg(mv.pow_match + (len - ed)));   // graph.cc:1859-1863
+}
+
+// One (x, y) combination of graph.cc:1861-1889; returns false when the orientation/order filter drops it.
+__device__ __forceinline__ bool pair_term(const ScoreParams& P, int xpos, int xedor, int ypos, int yedor, int l1,
+                                          int l2, double p1, double& term) {
+  const int xo = (xedor >> 30) & 1, yo = (yedor >> 30) & 1;
+  if (xo == yo) return false;
+  int d;
+  if (xpos < ypos) {
+    if (xo != 0) return false;
+    d = ypos - xpos + l2;
+  } else {
+    if (xo != 1) return false;
+    d = xpos - ypos + l1;
+  }
+  const double p2 = align_prob(P.m[1], yedor, l2);
+  const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
+  term = __dmul_rn(__dmul_rn(p1, p2), ins);
+  return true;
+}
+
+// Replays the reference's per-read update for sorted placement lists: walks in ordinal order (erased
+// first: subtract, then added: add), x-major / y-minor inside a walk.
+__device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int n2, int l1, int l2, double acc) {
+  sort_by_ord(a, n1);
+  sort_by_ord(b, n2);
+  int i = 0, j = 0;
+  while (i < n1 && j < n2) {
+    const int w = min(a[i].walk, b[j].walk);
+    int e1 = i, e2 = j;
+    while (e1 < n1 && a[e1].walk == w) e1++;
+    while (e2 < n2 && b[e2].walk == w) e2++;
+    if (e1 > i && e2 > j) {
+      const int m1 = dedup_positions(a, i, e1), m2 = dedup_positions(b, j, e2);
+      const bool sub = w < P.n_erased;
+      for (int x = i; x < m1; x++) {
+        const double p1 = align_prob(P.m[0], a[x].edor, l1);
+        for (int y = j; y < m2; y++) {
+          double t;
+          if (pair_term(P, a[x].pos, a[x].edor, b[y].pos, b[y].edor, l1, l2, p1, t))
+            acc = sub ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+        }
+      }
+    }
+    i = e1;
+    j = e2;
+  }
+  return acc;
+}
+
+struct FirstPlc { int walk, pos, edor; };
+
+// Counts the placements of one mate and remembers the first one (the common case is exactly one).
+__device__ __forceinline__ int scan_short(const MateView& mv, uint32_t epoch, int r, FirstPlc& first) {
+  int n = 0;
+  for_each_placement<RowShort>(mv, epoch, r, [&](const int4& o, const int4& rw) {
+    const int pos = wrap_add(rw.y, o.z);
+    if (pos < o.w) return;
+    if (n == 0) { first.walk = o.x; first.pos = pos; first.edor = rw.z; }
+    n++;
+  });
+  return n;
+}
+
+__device__ __forceinline__ int gather_short(const MateView& mv, uint32_t epoch, int r, Plc* out, int cap) {
+  int n = 0;
+  for_each_placement<RowShort>(mv, epoch, r, [&](const int4& o, const int4& rw) {
+    const int pos = wrap_add(rw.y, o.z);
+    if (pos < o.w) return;
+    if (n < cap) {
+      Plc p;
+      p.ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)rw.w;
+      p.walk = o.x;
+      p.pos = pos;
+      p.edor = rw.z;
+      p.pad = 0;
+      out[n] = p;
+    }
+    n++;
+  });
+  return n;
+}
+
+// Per-read paired update. Returns false if the read needs the scratch path (more than kCap placements).
+__device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
+  FirstPlc f1, f2;
+  const int n1 = scan_short(P.m[0], P.epoch, r, f1);
+  if (n1 == 0) return true;
+  const int n2 = scan_short(P.m[1], P.epoch, r, f2);
+  if (n2 == 0) return true;
+  const uint32_t ll = __ldg(P.lens + r);
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  if (n1 == 1 && n2 == 1) {
+    if (f1.walk == f2.walk) {
+      double t;
+      const double p1 = align_prob(P.m[0], f1.edor, l1);
+      if (pair_term(P, f1.pos, f1.edor, f2.pos, f2.edor, l1, l2, p1, t))
+        acc = (f1.walk < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+    }
+    return true;
+  }
+  if (n1 > kCap || n2 > kCap) return false;
+  Plc a[kCap], b[kCap];
+  gather_short(P.m[0], P.epoch, r, a, kCap);
+  gather_short(P.m[1], P.epoch, r, b, kCap);
+  acc = apply_pairs(P, a, n1, b, n2, l1, l2, acc);
+  return true;
+}
+
+// log max(p/(2L), thr) and the floored flag: GetTotalProb, graph.cc:1505-1512.
+__device__ __forceinline__ double floored_log(double p, int two_len, double thr, unsigned& floored) {
+  double v = __ddiv_rn(p, (double)two_len);
+  if (v < thr) { floored++; v = thr; }
+  return log(v);
+}
+
+__device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
+  const uint32_t slot = atomicAdd(P.ovf_count, 1u);
+  if (slot < P.ovf_cap) P.ovf_list[slot] = (uint32_t)r;
+  else atomicOr(P.error_flag, 1u);
+}
+
+// FULL: every read of the shard is re-scored from an empty state and the total is reduced in the same
+// pass (CalcScoreForPathsNew on a fresh ScoringState + GetTotalProb).
+__global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (paired_read(P, r, acc)) {
+      P.values[r] = acc;
+      const uint32_t ll = __ldg(P.lens + r);
+      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    } else {
+      push_overflow(P, r);
+    }
+  }
+  block_reduce_store(sum, floored, P.partials);
+}
+
+// DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
+// thread to stamp a read owns it and replays that read's subtract/add sequence.
+__global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams P) {
+  const uint32_t total = __ldg(P.touch_prefix + P.n_touch);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = P.n_touch;   // largest t with prefix[t] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.touch_prefix + mid) <= i) lo = mid; else hi = mid;
+    }
+    const TouchRange tr = P.touch[lo];
+    const int r = ldg4(P.arena1 + tr.begin + (i - __ldg(P.touch_prefix + lo))).x;
+    if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;
+    double acc = P.values[r];
+    if (paired_read(P, r, acc)) P.values[r] = acc;
+    else push_overflow(P, r);
+  }
+}
+
+// Reads with more than kCap placements on a mate: exact counts, scratch from a bump allocator, same replay.
+__global__ void __launch_bounds__(128) paired_overflow_kernel(const ScoreParams P, int full_mode, int partial_slot) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  const uint32_t n = min(*P.ovf_count, P.ovf_cap);
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const int r = (int)P.ovf_list[k];
+    FirstPlc f;
+    const int n1 = scan_short(P.m[0], P.epoch, r, f), n2 = scan_short(P.m[1], P.epoch, r, f);
+    const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
+    double acc = full_mode ? 0.0 : P.values[r];
+    if (base + n1 + n2 > P.scratch_cap) {
+      atomicOr(P.error_flag, 2u);
+    } else {
+      Plc* a = P.scratch + base;
+      Plc* b = a + n1;
+      gather_short(P.m[0], P.epoch, r, a, n1);
+      gather_short(P.m[1], P.epoch, r, b, n2);
+      const uint32_t ll = __ldg(P.lens + r);
+      acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
+      P.values[r] = acc;
+    }
+    if (full_mode) {
+      const uint32_t ll = __ldg(P.lens + r);
+      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    }
+  }
+  if (full_mode) {
+    // single block: reuse the block reduction with an explicit slot
+    __shared__ double s_hi[4], s_lo[4];
+    __shared__ unsigned s_fl[4];
+    for (int off = 16; off > 0; off >>= 1) {
+      DD o;
+      o.hi = __shfl_down_sync(0xffffffffu, sum.hi, off);
+      o.lo = __shfl_down_sync(0xffffffffu, sum.lo, off);
+      dd_merge(sum, o);
+      floored += __shfl_down_sync(0xffffffffu, floored, off);
+    }
+    if ((threadIdx.x & 31) == 0) { s_hi[threadIdx.x >> 5] = sum.hi; s_lo[threadIdx.x >> 5] = sum.lo; s_fl[threadIdx.x >> 5] = floored; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      DD t{0.0, 0.0};
+      unsigned fl = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
+      double* p = P.partials + (size_t)partial_slot * kPartialStride;
+      p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
+    }
+  }
+}
+
+// O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
+__global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams P) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+    const uint32_t ll = __ldg(P.lens + r);
+    dd_add(sum, floored_log(P.values[r], P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+  }
+  block_reduce_store(sum, floored, P.partials);
+}
+
+// ---- single -------------------------------------------------------------------------------
+// CalcScoreForPaths (graph.cc:1650-1743): placements of all walks pooled per read, de-duplicated on the
+// global position, summed in enumeration order.
+__device__ __forceinline__ double single_sum(const ScoreParams& P, Plc* a, int n, int len) {
+  sort_by_ord(a, n);
+  const int m = dedup_positions(a, 0, n);
+  double acc = 0.0;
+  for (int x = 0; x < m; x++) acc = __dadd_rn(acc, align_prob(P.m[0], a[x].edor, len));
+  return acc;
+}
+
+__global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+    FirstPlc f;
+    const int n = scan_short(P.m[0], P.epoch, r, f);
+    const int len = (int)__ldg(P.lens + r);
+    double acc = 0.0;
+    bool ok = true;
+    if (n == 1) {
+      acc = __dadd_rn(0.0, align_prob(P.m[0], f.edor, len));
+    } else if (n > 1) {
+      if (n <= kCap) {
+        Plc a[kCap];
+        gather_short(P.m[0], P.epoch, r, a, kCap);
+        acc = single_sum(P, a, n, len);
+      } else {
+        ok = false;
+      }
+    }
+    if (ok) {
+      P.values[r] = acc;
+      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+    } else {
+      push_overflow(P, r);
+    }
+  }
+  block_reduce_store(sum, floored, P.partials);
+}
+
+__global__ void __launch_bounds__(128) single_overflow_kernel(const ScoreParams P, int partial_slot) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  const uint32_t n = min(*P.ovf_count, P.ovf_cap);
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const int r = (int)P.ovf_list[k];
+    FirstPlc f;
+    const int n1 = scan_short(P.m[0], P.epoch, r, f);
+    const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)n1);
+    const int len = (int)__ldg(P.lens + r);
+    double acc = 0.0;
+    if (base + n1 > P.scratch_cap) {
+      atomicOr(P.error_flag, 2u);
+    } else {
+      Plc* a = P.scratch + base;
+      gather_short(P.m[0], P.epoch, r, a, n1);
+      acc = single_sum(P, a, n1, len);
+    }
+    P.values[r] = acc;
+    dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+  }
+  __shared__ double s_hi[4], s_lo[4];
+  __shared__ unsigned s_fl[4];
+  for (int off = 16; off > 0; off >>= 1) {
+    DD o;
+    o.hi = __shfl_down_sync(0xffffffffu, sum.hi, off);
+    o.lo = __shfl_down_sync(0xffffffffu, sum.lo, off);
+    dd_merge(sum, o);
+    floored += __shfl_down_sync(0xffffffffu, floored, off);
+  }
+  if ((threadIdx.x & 31) == 0) { s_hi[threadIdx.x >> 5] = sum.hi; s_lo[threadIdx.x >> 5] = sum.lo; s_fl[threadIdx.x >> 5] = floored; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DD t{0.0, 0.0};
+    unsigned fl = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
+    double* p = P.partials + (size_t)partial_slot * kPartialStride;
+    p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
+  }
+}
+
+// ---- pacbio (log space; logdouble.hpp) -----------------------------------------------------
+// logdouble::operator+= (logdouble.hpp:21-31): -inf is the additive identity, otherwise
+// max + log1p(exp(min - max)).
+__device__ __forceinline__ double lse_add(double acc, double v) {
+  if (isinf(acc) && acc < 0) return v;
+  if (isinf(v) && v < 0) return acc;
+  const double hi = fmax(acc, v), lo = fmin(acc, v);
+  return __dadd_rn(hi, log1p(exp(__dsub_rn(lo, hi))));
+}
+
+// Warp-shuffle log-sum-exp (order-free variant used for very long placement lists): max-reduce, then
+// sum of exp(v - max) in the warp, then one log.
+__device__ __forceinline__ double warp_lse(double v) {
+  double m = v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (isinf(m) && m < 0) return m;
+  double s = exp(__dsub_rn(v, m));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, off));
+  return __dadd_rn(m, log(s));
+}
+
+__device__ __forceinline__ int scan_long(const MateView& mv, uint32_t epoch, int r, double& first) {
+  int n = 0;
+  for_each_placement<RowLong>(mv, epoch, r, [&](const int4&, const int4& rw) {
+    if (n == 0) first = __hiloint2double(rw.w, rw.z);
+    n++;
+  });
+  return n;
+}
+
+__device__ __forceinline__ int gather_long(const MateView& mv, uint32_t epoch, int r, PlcLong* out, int cap) {
+  int n = 0;
+  for_each_placement<RowLong>(mv, epoch, r, [&](const int4& o, const int4& rw) {
+    if (n < cap) {
+      out[n].ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)rw.y;
+      out[n].logprob = __hiloint2double(rw.w, rw.z);
+    }
+    n++;
+  });
+  return n;
+}
+
+__device__ __forceinline__ double pacbio_floor(const ScoreParams& P, double v, int len, unsigned& floored) {
+  const double fl = __dadd_rn(P.floor_a, __dmul_rn(P.floor_b, (double)len));   // graph.cc:3075-3076
+  if (v < fl) { floored++; v = fl; }
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+    double first = 0.0;
+    const int n = scan_long(P.m[0], P.epoch, r, first);
+    double acc = -INFINITY;
+    bool ok = true;
+    if (n == 1) {
+      acc = first;
+    } else if (n > 1) {
+      if (n <= kCap) {
+        PlcLong a[kCap];
+        gather_long(P.m[0], P.epoch, r, a, kCap);
+        sort_by_ord(a, n);
+        for (int x = 0; x < n; x++) acc = lse_add(acc, a[x].logprob);
+      } else {
+        ok = false;
+      }
+    }
+    if (ok) {
+      P.values[r] = acc;
+      dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+    } else {
+      push_overflow(P, r);
+    }
+  }
+  block_reduce_store(sum, floored, P.partials);
+}
+
+// One WARP per many-placement read: lanes gather a strided share, each folds its share sequentially,
+// and the 32 partial log-sums are combined with the warp-shuffle LSE.
+__global__ void __launch_bounds__(128) pacbio_overflow_kernel(const ScoreParams P, int partial_slot) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  const uint32_t n = min(*P.ovf_count, P.ovf_cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (uint32_t k = warp; k < n; k += n_warps) {
+    const int r = (int)P.ovf_list[k];
+    const MateView& mv = P.m[0];
+    const uint32_t b = __ldg(mv.rowptr + r), e = __ldg(mv.rowptr + r + 1);
+    const RowLong* rows = static_cast<const RowLong*>(mv.rows);
+    double part = -INFINITY;
+    for (uint32_t i = b + lane; i < e; i += 32) {
+      const int4 rw = ldg4(rows + i);
+      const int4 hdr = ldg4(mv.slots + rw.x);
+      if ((uint32_t)hdr.x != P.epoch) continue;
+      const double lp = __hiloint2double(rw.w, rw.z);
+      for (int t = 0; t < hdr.y; t++) part = lse_add(part, lp);   // same record under n_occ live lookups
+    }
+    const double acc = warp_lse(part);
+    if (lane == 0) {
+      P.values[r] = acc;
+      dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+    }
+  }
+  __shared__ double s_hi[4], s_lo[4];
+  __shared__ unsigned s_fl[4];
+  if (lane == 0) { s_hi[warp] = sum.hi; s_lo[warp] = sum.lo; s_fl[warp] = floored; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DD t{0.0, 0.0};
+    unsigned fl = 0;
+    for (int w = 0; w < n_warps; w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
+    double* p = P.partials + (size_t)partial_slot * kPartialStride;
+    p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
+  }
+}
+
+// ---- per-evaluation tables, reduction of partials -------------------------------------------
+__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SlotUpdate u = upd[i];
+  KeySlot s;
+  s.epoch = epoch;
+  s.n_occ = u.n_occ;
+  s.occ_begin = u.occ_begin;
+  s.pad = 0;
+  s.first = u.first;
+  tables[u.store][u.key] = s;
+}
+
+// out[set] = {sum_hi, sum_lo, floored, flags}: fixed-order double-double sum of the block partials.
+__global__ void finalize_kernel(const double* partials, const int* set_begin, int n_sets, double* out,
+                                const uint32_t* error_flag, const uint32_t* ovf_counts) {
+  const int s = threadIdx.x;
+  if (s >= n_sets) return;
+  DD t{0.0, 0.0};
+  double fl = 0.0;
+  for (int b = set_begin[s]; b < set_begin[s + 1]; b++) {
+    const double* p = partials + (size_t)b * kPartialStride;
+    dd_merge(t, DD{p[0], p[1]});
+    fl += p[2];
+  }
+  // renormalise so hi carries the rounded total
+  const double hi = __dadd_rn(t.hi, t.lo);
+  const double lo = __dsub_rn(t.lo, __dsub_rn(hi, t.hi));
+  out[s * 4 + 0] = hi;
+  out[s * 4 + 1] = lo;
+  out[s * 4 + 2] = fl;
+  out[s * 4 + 3] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
+}
+
+// ---- CSR build: arena (key-major) -> rows (read-major) --------------------------------------
+__global__ void count_reads_kernel(const int4* arena, size_t n, uint32_t* counts) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    atomicAdd(counts + arena[i].x, 1u);
+}
+
+template <bool kLong>
+__global__ void fill_rows_kernel(const int4* arena, size_t n, const uint32_t* rowptr, uint32_t* cursor, int4* rows) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int4 a = arena[i];
+    const uint32_t slot = rowptr[a.x] + atomicAdd(cursor + a.x, 1u);
+    int4 r;
+    if (kLong) { r.x = a.y; r.y = (int)(uint32_t)i; r.z = a.z; r.w = a.w; }   // {key, seq, logprob}
+    else { r.x = a.w; r.y = a.y; r.z = a.z; r.w = (int)(uint32_t)i; }          // {key, pos, edor, seq}
+    rows[slot] = r;
+  }
+}
+
+// Atomics scatter in arbitrary order; restore arena (= reference list) order inside every read's row.
+template <bool kLong>
+__global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t b = rowptr[r], e = rowptr[r + 1];
+  for (uint32_t i = b + 1; i < e; i++) {
+    const int4 v = rows[i];
+    const uint32_t sv = kLong ? (uint32_t)v.y : (uint32_t)v.w;
+    uint32_t j = i;
+    while (j > b) {
+      const int4 u = rows[j - 1];
+      const uint32_t su = kLong ? (uint32_t)u.y : (uint32_t)u.w;
+      if (su <= sv) break;
+      rows[j] = u;
+      j--;
+    }
+    rows[j] = v;
+  }
+}
+
+int grid_for(size_t n, int block, int sm_count, int per_sm) {
+  size_t need = (n + block - 1) / block;
+  size_t cap = (size_t)sm_count * per_sm;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace
+
+// ---- launch wrappers ------------------------------------------------------------------------
+int score_grid(int n_reads, int sm_count) { return grid_for((size_t)n_reads, kBlock, sm_count, 8); }
+
+void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st) {
+  if (n <= 0) return;
+  apply_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(upd, n, tables, epoch);
+}
+
+void launch_paired_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+  paired_full_kernel<<<grid, kBlock, 0, st>>>(P);
+  paired_overflow_kernel<<<1, 128, 0, st>>>(P, 1, ovf_slot);
+}
+
+void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int sm_count, cudaStream_t st) {
+  if (n_touch_records > 0) {
+    paired_delta_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P);
+    paired_overflow_kernel<<<1, 128, 0, st>>>(P, 0, 0);
+  }
+  paired_total_kernel<<<grid_total, kBlock, 0, st>>>(P);
+}
+
+void launch_single_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+  single_full_kernel<<<grid, kBlock, 0, st>>>(P);
+  single_overflow_kernel<<<1, 128, 0, st>>>(P, ovf_slot);
+}
+
+void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+  pacbio_full_kernel<<<grid, kBlock, 0, st>>>(P);
+  pacbio_overflow_kernel<<<1, 128, 0, st>>>(P, ovf_slot);
+}
+
+void launch_finalize(const double* partials, const int* set_begin, int n_sets, double* out, const uint32_t* error_flag,
+                     const uint32_t* ovf_counts, cudaStream_t st) {
+  finalize_kernel<<<1, 32 * ((n_sets + 31) / 32), 0, st>>>(partials, set_begin, n_sets, out, error_flag, ovf_counts);
+}
+
+cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
+                      void* rows, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches) {
+  // rowptr doubles as the count array (n_reads + 1 entries, zeroed here)
+  cudaError_t err = cudaMemsetAsync(rowptr, 0, sizeof(uint32_t) * ((size_t)n_reads + 1), st);
+  if (err != cudaSuccess) return err;
+  err = cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * ((size_t)n_reads + 1), st);
+  if (err != cudaSuccess) return err;
+  if (n_records > 0) {
+    count_reads_kernel<<<grid_for(n_records, 256, sm_count, 16), 256, 0, st>>>(static_cast<const int4*>(arena), n_records, rowptr);
+    (*launches)++;
+  }
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, rowptr, rowptr, n_reads + 1, st);
+  if (need > temp_bytes) return cudaErrorMemoryAllocation;
+  err = cub::DeviceScan::ExclusiveSum(temp, need, rowptr, rowptr, n_reads + 1, st);
+  if (err != cudaSuccess) return err;
+  (*launches)++;
+  if (n_records > 0) {
+    const int g = grid_for(n_records, 256, sm_count, 16);
+    if (is_long) fill_rows_kernel<true><<<g, 256, 0, st>>>(static_cast<const int4*>(arena), n_records, rowptr, cursor, static_cast<int4*>(rows));
+    else fill_rows_kernel<false><<<g, 256, 0, st>>>(static_cast<const int4*>(arena), n_records, rowptr, cursor, static_cast<int4*>(rows));
+    const int gs = (n_reads + 255) / 256;
+    if (is_long) sort_rows_kernel<true><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows));
+    else sort_rows_kernel<false><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows));
+    (*launches) += 2;
+  }
+  return cudaGetLastError();
+}
+
+size_t csr_temp_bytes(int n_reads) {
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, n_reads + 1);
+  return need;
+}
+
+}  // namespace gaml

@@ -1,0 +1,165 @@
+/* gaml_b200 — C ABI of the B200-native GAML assembly-likelihood path.
+ *
+ * This is the drop-in boundary: everything the reference's
+ * `ProbCalculator::CalcProb` (prob_calculator.h:63-118) and the three per-read-set scorers it
+ * forwards to (`CalcScoreForPaths` graph.cc:1650, `CalcScoreForPathsNew` graph.cc:1952,
+ * `CalcScoreForPacbio` graph.cc:3171) need, as plain C: opaque context, plain pointers and sizes,
+ * int return codes (0 = ok, <0 = error, text via gaml_last_error), never an exception.
+ * Host buffers are borrowed for the duration of a call only. One context per host thread.
+ * All device work is ordered on one context-owned CUDA stream; results are valid on return.
+ * There is NO CPU fallback: every scoring entry point fails with GAML_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef GAML_B200_H_
+#define GAML_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gaml_ctx gaml_ctx;
+
+enum {
+  GAML_OK = 0,
+  GAML_ERR_CUDA = -1,          /* CUDA runtime / no device */
+  GAML_ERR_ARG = -2,           /* bad argument */
+  GAML_ERR_KEY_EXISTS = -3,    /* cache key inserted twice */
+  GAML_ERR_UNSUPPORTED = -4,   /* e.g. penalty_constant != 0 (coverage penalty, SURVEY §8 A8, not on device yet) */
+  GAML_ERR_CAPACITY = -5,      /* a read needs more placement scratch than configured */
+  GAML_ERR_STATE = -6          /* call order (e.g. finalize without a pending evaluation) */
+};
+
+enum { GAML_KIND_SINGLE = 0, GAML_KIND_PAIRED = 1, GAML_KIND_PACBIO = 2 };
+
+/* Per-read-set scoring parameters: SingleReadConfig / PairedReadConfig (prob_calculator.h:7-35)
+ * plus the ReadSet constructor's probabilities (graph.h:347-351, 446-449; match = 1 - 4*mismatch is the
+ * caller's business, gaml.cc:813,854). insert_* are ignored for single / pacbio sets. */
+typedef struct {
+  int32_t kind;                /* GAML_KIND_* */
+  int32_t reserved;
+  double mismatch_prob;
+  double match_prob;
+  double insert_mean;
+  double insert_std;
+  double min_prob_per_base;
+  double min_prob_start;
+  double weight;
+  double penalty_constant;     /* must be 0 for now (GAML_ERR_UNSUPPORTED otherwise) */
+  double step;
+} gaml_readset_config;
+
+/* `Aligment` (graph.h:211-215): one cached short-read alignment under a subpath key. */
+typedef struct {
+  int32_t position;
+  int32_t edit_dist;
+  int32_t read_id;             /* GLOBAL read id; records outside this context's shard are dropped */
+  int32_t orientation;
+} gaml_alignment;
+
+/* `PacbioReadSet::PacbioAligment` (graph.h:516-520). */
+typedef struct {
+  int32_t position;
+  int32_t position_end;
+  int32_t read_id;
+  int32_t pad;
+  double logprob;
+} gaml_pacbio_alignment;
+
+/* Result of one CalcProb (prob_calculator.h:63): zeros[i] = (floored reads, n_reads) per read set in
+ * the order the sets were added; total_len as the reference leaves it (last set's value). */
+typedef struct {
+  double prob;
+  int32_t total_len;
+  int32_t n_sets;
+} gaml_result;
+
+/* Partial sums of one read-id shard: per set {sum_hi, sum_lo, floored}; combine across shards with
+ * gaml_combine_partials after an all-gather. */
+#define GAML_PARTIAL_DOUBLES 3
+
+typedef struct {
+  int64_t kernel_launches;         /* kernels of THIS library launched since context creation */
+  int64_t evals;                   /* CalcProb evaluations */
+  int64_t last_records_gathered;   /* alignment records whose key was live in the last evaluation (A) */
+  int64_t last_reads_scanned;      /* reads streamed by the last evaluation (R of the shard, all sets) */
+  int64_t last_algorithmic_bytes;  /* 16*A + per-read bytes of the pass that ran */
+  int64_t last_h2d_bytes;          /* bytes copied host->device by the last evaluation */
+  int64_t last_d2h_bytes;
+  double last_device_ms;           /* CUDA-event time of the last evaluation's kernels on the ctx stream */
+  double last_score_kernel_ms;     /* CUDA-event time of the dominant scoring kernel(s) only */
+  int32_t last_was_full;           /* 1 if the paired sets were re-scored from scratch */
+  int32_t last_overflow_reads;     /* reads that took the scratch (many-placement) path */
+} gaml_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int gaml_ctx_create(int device, gaml_ctx** out);
+void gaml_ctx_destroy(gaml_ctx* ctx);
+const char* gaml_last_error(gaml_ctx* ctx);          /* ctx may be NULL: last creation error */
+void* gaml_ctx_stream(gaml_ctx* ctx);                /* the cudaStream_t all work is ordered on */
+
+/* Graph (graph.h:74-77, 233-273): the path only needs Node::s.length() per node id (2k forward,
+ * 2k+1 twin) and normalize_map (NULL = identity). */
+int gaml_set_graph(gaml_ctx* ctx, int32_t n_nodes, const int32_t* node_len, const int32_t* normalize_map);
+
+/* ---- read sets -------------------------------------------------------------------------- */
+/* Adds a read set; returns its index (>= 0) or an error. The context holds reads
+ * [shard_lo, shard_hi) of n_reads_total (read-id sharding); read_len1/2 point at the
+ * SHARD's lengths (shard_hi - shard_lo entries; read_len2 only for paired sets). max_read_len1/2 are
+ * the maxima over ALL reads (ReadSet::max_read_len_, graph.cc:1443-1447); pass -1 to take them from
+ * the given arrays (correct when the shard is the whole set). */
+int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_reads_total, int64_t shard_lo,
+                     int64_t shard_hi, const int32_t* read_len1, const int32_t* read_len2, int32_t max_read_len1,
+                     int32_t max_read_len2);
+
+/* ---- alignment cache mirror (aligment_cache_, graph.h:427 / 587) -------------------------- */
+/* aligment_cache_[key] = records. mate is 0/1 (paired: ReadSet 1 / 2), 0 otherwise.
+ * key_max_position: largest `position` over the key's records of ALL reads (it drives the
+ * `max_pos - 5` skip rule, graph.cc:577-596); pass INT32_MIN to compute it from `records`
+ * (correct whenever `records` holds the whole list, not just this shard's). */
+int gaml_cache_insert(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len,
+                      const gaml_alignment* records, int64_t n_records, int32_t key_max_position);
+int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t key_len,
+                             const gaml_pacbio_alignment* records, int64_t n_records);
+/* 1 if the key is present (aligment_cache_.count(key)), 0 if not, <0 on error. */
+int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len);
+/* Uploads staged inserts and rebuilds the per-read CSR on the device (also done lazily by CalcProb). */
+int gaml_cache_commit(gaml_ctx* ctx);
+
+/* ---- scoring ---------------------------------------------------------------------------- */
+/* ProbCalculator::CalcProb(paths, zeros, total_len) (prob_calculator.h:63-109). Walks are concatenated
+ * node ids (negative = gap of that many N's) with n_walks+1 offsets. STATEFUL exactly like the
+ * reference: every call commits old_paths := paths for the paired sets (graph.cc:1986).
+ * zeros: 2*n_sets int32 (floored, n_reads) pairs; may be NULL. */
+int gaml_calc_prob(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
+                   gaml_result* result, int32_t* zeros);
+
+/* Same evaluation split for sharded (one process per GPU) use: `partials` receives
+ * GAML_PARTIAL_DOUBLES doubles per set for THIS shard; all-gather them over ranks, then every rank calls
+ * gaml_combine_partials with the n_shards x n_sets x 3 array (rank-major) to get the identical result. */
+int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets,
+                           int32_t n_walks, double* partials, int32_t* total_len);
+int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shards, int32_t total_len,
+                          gaml_result* result, int32_t* zeros);
+
+/* Three-phase form of gaml_calc_prob_partial for measurement: prepare = host flattening + H2D of the
+ * per-evaluation tables; launch = the kernels (asynchronous, on gaml_ctx_stream); finish = D2H + sync. */
+int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks);
+int gaml_eval_launch(gaml_ctx* ctx);
+int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len);
+
+/* Forget the paired ScoringState (== constructing a fresh ProbCalculator, prob_calculator.h:45-47): the
+ * next evaluation re-scores every read from scratch ("full logL"). */
+int gaml_reset_state(gaml_ctx* ctx);
+
+/* Per-read values of the last evaluation for parity dumps, shard-local order: single = sum of p1
+ * (graph.cc:1697), paired = ScoringState::probs (graph.h:615), pacbio = log-sum-exp (graph.cc:3057). */
+int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n);
+
+int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAML_B200_H_ */
