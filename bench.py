@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — alignments scored/s of the GAML assembly-likelihood path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path (oracle/_ref)
+
+A step = one full log-likelihood evaluation (`ProbCalculator::CalcProb` on a fresh ScoringState,
+prob_calculator.h:63-109) of BASELINE config 2: synthetic 4.6 Mbp genome, 2 M innie read pairs 2x100 bp,
+insert 300+-30, injected alignment cache. With N GPUs every rank holds a config-2-sized read-id shard of an
+N-times larger genome/read set (weak scaling); partial log-likelihoods are all-gathered over NCCL.
+
+One JSON line on stdout (rank 0). `value` is device time with all inputs resident in HBM (CUDA events on the
+library's stream, L2 flushed between steps); `e2e` is the same metric through gaml_calc_prob with host
+buffers in and out, wall clock. `roofline` is the dominant kernel against the measured HBM copy peak.
+The incremental (delta) evaluations of the annealing loop are reported beside it as `sa_iters_per_s`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+C2 = dict(n_unique=460, unique_len=10000, n_pairs=2_000_000)
+WORKLOAD_NAME = ("C2: synthetic 4.6 Mbp genome (460 x ~10 kbp nodes + 3 repeat nodes x2), 2M innie read pairs 2x100 bp, "
+                 "insert 300+-30, edit distance 0-2, 10% of mates with a second alignment; one walk per long node")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(world: int, rank: int, n_evals: int, scale: float = 1.0):
+    """Config 2 per GPU: the genome and read set grow with `world`, each rank generates only its shard."""
+    from gaml_b200 import synth
+    n_pairs_total = int(C2["n_pairs"] * scale) * world
+    per = (n_pairs_total + world - 1) // world
+    lo, hi = rank * per, min((rank + 1) * per, n_pairs_total)
+    wl = synth.paired_workload(int(C2["n_unique"] * scale) * world, C2["unique_len"], n_pairs_total, n_evals=n_evals,
+                               seed=42, read_lo=lo, read_hi=hi)
+    return wl, (lo, hi)
+
+
+def load_calculator(wl, shard, device, world=1, torch_dev=None):
+    """Builds the context from a (possibly shard-only) workload. The skip rule (graph.cc:577-596) needs each
+    key's largest position over ALL reads, so with several ranks the per-key maxima of the shards are
+    MAX-all-reduced first (keys are enumerated identically on every rank)."""
+    from gaml_b200 import api
+    pc = api.ProbCalculator(wl.node_len, wl.normalize_map, device)
+    spec = wl.sets[0]
+    lo, hi = shard
+    sid = pc.add_readset(spec, shard=(lo, hi), max_read_len=[int(spec.read_len[0].max()), int(spec.read_len[1].max())],
+                         lens_are_local=True)
+    key_max = {}
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        flat = [int(recs["position"].max()) if len(recs) else api.INT32_MIN for cache in spec.caches for recs in cache.values()]
+        t = torch.tensor(flat, dtype=torch.int64, device=torch_dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it = iter(t.cpu().tolist())
+        for mate, cache in enumerate(spec.caches):
+            for key in cache:
+                key_max[(mate, key)] = int(next(it))
+    t0 = time.perf_counter()
+    nbytes = 0
+    for mate, cache in enumerate(spec.caches):
+        for key, recs in cache.items():
+            pc.cache_insert(sid, mate, key, recs, key_max.get((mate, key), api.INT32_MIN))
+            nbytes += recs.nbytes
+    pc.commit()
+    return pc, time.perf_counter() - t0, nbytes
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("paired_full_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def shard_workload(wl, lo, hi):
+    """Workload restricted to reads [lo,hi) with ids shifted to 0 — what one CPU process scores."""
+    from gaml_b200.workload import ReadSetSpec, Workload
+    spec = wl.sets[0]
+    caches = []
+    for cache in spec.caches:
+        c = {}
+        for k, recs in cache.items():
+            m = (recs["read_id"] >= lo) & (recs["read_id"] < hi)
+            r = recs[m].copy()
+            r["read_id"] -= lo
+            c[k] = r
+        caches.append(c)
+    s2 = ReadSetSpec(kind=spec.kind, n_reads=hi - lo, read_len=[rl[lo:hi] for rl in spec.read_len], caches=caches,
+                     mismatch_prob=spec.mismatch_prob, match_prob=spec.match_prob, insert_mean=spec.insert_mean,
+                     insert_std=spec.insert_std, min_prob_per_base=spec.min_prob_per_base,
+                     min_prob_start=spec.min_prob_start, weight=spec.weight, step=spec.step)
+    return Workload(node_len=wl.node_len, normalize_map=wl.normalize_map, sets=[s2], evals=[wl.evals[0]])
+
+
+def cpu_binary():
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if os.path.exists(ref):
+        return ref, "reference"
+    import __graft_entry__ as entry
+    entry.build()
+    return os.path.join(ROOT, "oracle", "gaml_oracle"), "port"
+
+
+def run_cpu(wl, n_procs: int, repeats: int, tmp: str):
+    """n_procs independent processes of the reference's single-threaded scorer, each on a contiguous
+    read-id block; returns per-repeat wall (max over processes) and the alignments scored per repeat."""
+    from gaml_b200 import workload
+    binary, kind = cpu_binary()
+    n = wl.sets[0].n_reads
+    per = (n + n_procs - 1) // n_procs
+    procs, outs, aligns = [], [], 0
+    for p in range(n_procs):
+        lo, hi = p * per, min((p + 1) * per, n)
+        if hi <= lo:
+            continue
+        sw = shard_workload(wl, lo, hi)
+        aligns += sw.sets[0].n_records()
+        wp, rp = os.path.join(tmp, f"cpu{p}.wl"), os.path.join(tmp, f"cpu{p}.res")
+        workload.write_workload(wp, sw)
+        outs.append(rp)
+        procs.append((binary, wp, rp))
+    running = [subprocess.Popen([b, wp, rp, "0", str(repeats)], cwd=tmp, stdout=subprocess.DEVNULL,
+                                stderr=subprocess.DEVNULL) for b, wp, rp in procs]
+    for r in running:
+        if r.wait() != 0:
+            raise RuntimeError("CPU scorer failed")
+    secs = np.array([[e.seconds for e in workload.read_results(rp)] for rp in outs])   # [procs, repeats]
+    return secs.max(axis=0), aligns, kind
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores, 64))
+    wl, _ = make_workload(1, 0, 1, scale=args.scale)
+    with tempfile.TemporaryDirectory() as tmp:
+        per_step, aligns, kind = run_cpu(wl, n_procs, args.steps + args.warmup, tmp)
+    timed = per_step[args.warmup:]
+    total = float(timed.sum())
+    value = aligns * len(timed) / total
+    line = {
+        "impl": "reference", "metric": "alignments_scored_per_s", "value": value, "unit": "alignments/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
+                   "alignments_per_step": aligns},
+        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": n_procs, "kind": kind,
+                         "sample": f"whole C2 workload split into {n_procs} contiguous read-id blocks, one single-threaded "
+                                   f"reference process per block, {len(timed)} timed full evaluations each; step time = slowest process"},
+        "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gaml_b200", choices=["gaml_b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = config 2)")
+    ap.add_argument("--delta-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gaml_b200" else args.warmup
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from gaml_b200 import api
+    from gaml_b200.dist import allgather_partials
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the scoring path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t_gen = time.perf_counter()
+    n_evals = 2 + args.delta_steps
+    wl, shard = make_workload(world, rank, n_evals, scale=args.scale)
+    t_gen = time.perf_counter() - t_gen
+    pc, t_upload, cache_bytes = load_calculator(wl, shard, local_rank, world, dev)
+    log(f"[rank {rank}] workload generated in {t_gen:.1f}s; cache of {cache_bytes / 1e6:.1f} MB inserted+CSR built in {t_upload:.2f}s")
+    walks0 = wl.evals[0]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def full_step_device():
+        """One full evaluation; returns (device ms of the evaluation's kernels, ms of the dominant kernel)."""
+        pc.reset_state()
+        pc.prepare(walks0)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        pc.launch()
+        part, tl = pc.finish()
+        st = pc.stats()
+        return st.last_device_ms, st.last_score_kernel_ms, part, tl
+
+    def full_step_e2e():
+        pc.reset_state()
+        part, tl = pc.calc_prob_partial(walks0)
+        g = allgather_partials(part, dev) if world > 1 else part[None, :]
+        return pc.combine(g, g.shape[0], tl)
+
+    # ---- value: device-resident inputs, CUDA events, L2 flushed between steps ----
+    for _ in range(args.warmup):
+        full_step_device()
+    sampler = ClockSampler(local_rank)
+    launches0 = pc.stats().kernel_launches
+    barrier()
+    sampler.start()
+    dev_ms, ker_ms = 0.0, 0.0
+    for _ in range(args.steps):
+        d, k, part, tl = full_step_device()
+        dev_ms += d
+        ker_ms += k
+    barrier()
+    st = pc.stats()
+    launches = st.kernel_launches - launches0
+    a_local, bytes_local = st.last_records_gathered, st.last_algorithmic_bytes
+    dev_ms_max = max_over_ranks(dev_ms)
+    a_total = sum_over_ranks(float(a_local))
+
+    # ---- e2e: host walks in, host result out, wall clock, collective included ----
+    for _ in range(args.warmup):
+        full_step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        prob, zeros, tl_full = full_step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    st = pc.stats()
+    h2d, d2h = st.last_h2d_bytes, st.last_d2h_bytes
+
+    # ---- incremental evaluations of the annealing loop (delta kernel + O(R) pass) ----
+    pc.reset_state()
+    full_step_e2e()
+    seq = wl.evals[1:1 + args.delta_steps]
+    barrier()
+    t0 = time.perf_counter()
+    delta_dev_ms, touched = 0.0, 0
+    for walks in seq:
+        part, tl = pc.calc_prob_partial(walks)
+        if world > 1:
+            allgather_partials(part, dev)
+        s2 = pc.stats()
+        delta_dev_ms += s2.last_device_ms
+        touched += s2.last_records_gathered
+    barrier()
+    delta_s = max_over_ranks(time.perf_counter() - t0)
+    delta_bytes = pc.stats().last_algorithmic_bytes
+
+    peak, peak_src = measured_peak()
+    achieved = bytes_local / (ker_ms / args.steps * 1e-3) / 1e9
+    line = {
+        "metric": "alignments_scored_per_s", "value": a_total * args.steps / (dev_ms_max * 1e-3), "unit": "alignments/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
+                   "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
+                   "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
+                   "l2": "flushed between steps (256 MiB write)", "timing": "CUDA events on the library stream, max over ranks",
+                   "parallelism": f"read-id shards x{world}, all-gather of 24 B partials per read set"},
+        "roofline": {"bound": "hbm", "kernel": "paired_full_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps},
+        "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "note": "gaml_calc_prob_partial (+ all-gather at N>1) with host walks in / host partials out; the alignment "
+                        "cache is resident state like the reference's aligment_cache_"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "sa_iters_per_s": len(seq) / delta_s,
+        "incremental": {"evals": len(seq), "e2e_ms_per_eval": 1e3 * delta_s / max(len(seq), 1),
+                        "device_ms_per_eval": delta_dev_ms / max(len(seq), 1), "touched_alignments_per_eval": touched / max(len(seq), 1),
+                        "algorithmic_bytes_last_eval": int(delta_bytes)},
+        "cache_upload": {"seconds": t_upload, "bytes": int(cache_bytes)},
+        "result": {"prob": prob, "total_len": tl_full, "floored": zeros[0][0]},
+    }
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        # bounded CPU sample on the box's host: the reference's own scorer, 1 core, whole C2, a few full evaluations
+        with tempfile.TemporaryDirectory() as tmp:
+            t0 = time.perf_counter()
+            per_step, aligns, kind = run_cpu(wl, 1, 5, tmp)
+            log(f"cpu baseline ({kind}) took {time.perf_counter() - t0:.1f}s")
+        line["cpu_baseline"] = {"value": aligns * len(per_step) / float(per_step.sum()), "unit": "alignments/s", "cores": 1,
+                                "kind": kind, "sample": "whole C2 workload, 5 full evaluations on one core (the reference is single-threaded)"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    pc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

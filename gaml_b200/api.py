@@ -46,7 +46,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream", "gaml_set_graph",
            "gaml_add_readset", "gaml_cache_insert", "gaml_cache_insert_pacbio", "gaml_cache_contains",
-           "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials",
+           "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials", "gaml_combine_partials_raw",
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_get_stats"]
 
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
     lib.gaml_calc_prob.argtypes = [vp, i32p, i64p, C.c_int32, C.POINTER(Result), i32p]
     lib.gaml_calc_prob_partial.argtypes = [vp, i32p, i64p, C.c_int32, dp, i32p]
     lib.gaml_combine_partials.argtypes = [vp, dp, C.c_int32, C.c_int32, C.POINTER(Result), i32p]
+    lib.gaml_combine_partials_raw.argtypes = [dp, C.c_int32, C.c_int32, i32p, i64p, dp, C.c_int32, C.POINTER(Result), i32p]
     lib.gaml_eval_prepare.argtypes = [vp, i32p, i64p, C.c_int32]
     lib.gaml_eval_launch.argtypes = [vp]
     lib.gaml_eval_finish.argtypes = [vp, dp, i32p]
@@ -257,3 +258,21 @@ class ProbCalculator:
         s = Stats()
         self._check(self.lib.gaml_get_stats(self.h, C.byref(s)))
         return s
+
+
+def combine_partials_raw(gathered: np.ndarray, kinds: Sequence[int], n_reads_total: Sequence[int],
+                         weights: Sequence[float], total_len: int):
+    """Context-free combine of all-gathered shard partials ([n_shards, n_sets, 3]) -> (prob, zeros, total_len)."""
+    lib = load_library()
+    g = np.ascontiguousarray(gathered, dtype=np.float64).reshape(-1, len(kinds), 3)
+    k = _i32(kinds)
+    n = np.ascontiguousarray(n_reads_total, dtype=np.int64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    res = Result()
+    zeros = np.zeros(2 * max(len(kinds), 1), dtype=np.int32)
+    rc = lib.gaml_combine_partials_raw(g.ctypes.data_as(C.POINTER(C.c_double)), g.shape[0], len(kinds), _p32(k),
+                                       n.ctypes.data_as(C.POINTER(C.c_int64)), w.ctypes.data_as(C.POINTER(C.c_double)),
+                                       total_len, C.byref(res), _p32(zeros))
+    if rc != 0:
+        raise GamlError(f"gaml_combine_partials_raw failed ({rc})")
+    return res.prob, [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(kinds))], res.total_len

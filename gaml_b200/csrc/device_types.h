@@ -61,7 +61,8 @@ struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one t
 constexpr int kPartialStride = 4;   // per block: sum_hi, sum_lo, floored, spare
 
 struct MateView {
-  const void* rows;          // RowShort* / RowLong*
+  const void* first;         // short stores: dense int4 per read {key, pos, edor | count<<16, row offset}; key<0 = none
+  const void* rows;          // RowShort* / RowLong* (read-major CSR; a read's rows in reference list order)
   const uint32_t* rowptr;    // n_reads + 1
   const KeySlot* slots;
   const Occ* occ;

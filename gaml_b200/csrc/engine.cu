@@ -88,7 +88,7 @@ struct MateStore {
   std::vector<KeyMeta> keys;
   std::vector<int4> pending;          // staged arena records (ArenaShort / ArenaLong bit patterns)
   size_t arena_n = 0;                 // records on the device
-  DevBuf arena, rows, rowptr, cursor, slots;
+  DevBuf arena, rows, first, rowptr, cursor, slots;
   bool dirty = true;
   std::vector<double> pow_match, pow_mismatch;
   DevBuf d_pow_match, d_pow_mismatch;
@@ -110,6 +110,11 @@ struct ReadSetState {
   // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
   std::vector<Walk> old_walks;
   bool has_state = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this set's streaming kernel(s)
+  ~ReadSetState() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
 };
 
 struct SetPlan {
@@ -389,6 +394,7 @@ int commit(gaml_ctx* ctx) {
         st.pending.shrink_to_fit();
       }
       CU(st.rows.reserve(std::max<size_t>(total, 1) * 16, 0, false, ctx->stream));
+      if (!st.is_long) CU(st.first.reserve(std::max<size_t>(rs.n_local, 1) * 16, 0, false, ctx->stream));
       CU(st.rowptr.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
       CU(st.cursor.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
       const size_t old_slots = st.slots.cap;
@@ -398,7 +404,7 @@ int commit(gaml_ctx* ctx) {
       CU(ctx->d_csr_temp.reserve(std::max<size_t>(temp, 256), 0, false, ctx->stream));
       int launches = 0;
       CU(build_csr(st.arena.p, st.arena_n, rs.n_local, st.is_long, st.rowptr.as<uint32_t>(), st.cursor.as<uint32_t>(),
-                   st.rows.p, ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->sm_count, ctx->stream, &launches));
+                   st.rows.p, st.first.p, ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->sm_count, ctx->stream, &launches));
       ctx->stats.kernel_launches += launches;
       st.dirty = false;
     }
@@ -468,14 +474,14 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       for (int m = 0; m < 2; m++) group_occurrences(ob[m], rs.mate[m].table_index, updates, occs[rs.mate[m].table_index]);
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
-      sp.n_partials = sp.grid + (sp.full ? 1 : 0);
+      sp.n_partials = sp.grid + (sp.full ? overflow_grid(ctx->sm_count) : 0);
     } else {
       OccBuilder ob;
       sp.full = true;
       if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, walks, ob, sp);
       else flatten_pacbio(ctx, rs, walks, ob, sp);
       group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
-      sp.n_partials = sp.grid + 1;
+      sp.n_partials = sp.grid + overflow_grid(ctx->sm_count);
     }
     sp.partial_begin = partial_cursor;
     partial_cursor += sp.n_partials;
@@ -554,6 +560,7 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   ScoreParams P{};
   for (int m = 0; m < rs.n_mates; m++) {
     MateStore& st = rs.mate[m];
+    P.m[m].first = st.first.p;
     P.m[m].rows = st.rows.p;
     P.m[m].rowptr = st.rowptr.as<uint32_t>();
     P.m[m].slots = st.slots.as<KeySlot>();
@@ -610,26 +617,27 @@ int launch(gaml_ctx* ctx) {
     ReadSetState& rs = *ctx->sets[s];
     const SetPlan& sp = ctx->plan[s];
     ScoreParams P = make_params(ctx, s);
+    const int og = overflow_grid(ctx->sm_count);
     records += sp.records;
     reads += rs.n_local;
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
-        launch_paired_full(P, sp.grid, sp.grid, st);
+        launch_paired_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
         launches += 2;
         any_full = true;
         // rowptr (4+4) + lens (4) + probs write (8) per pair, 16 per record
         bytes += 16 * sp.records + 20 * (int64_t)rs.n_local;
       } else {
-        launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, ctx->sm_count, st);
+        launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, og, ctx->sm_count, st, rs.ev0, rs.ev1);
         launches += sp.touch_records > 0 ? 3 : 1;
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       }
     } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
-      launch_single_full(P, sp.grid, sp.grid, st);
+      launch_single_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
       launches += 2;
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     } else {
-      launch_pacbio_full(P, sp.grid, sp.grid, st);
+      launch_pacbio_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
       launches += 2;
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     }
@@ -661,7 +669,10 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   ctx->stats.last_d2h_bytes = (int64_t)(n_sets * 4 * sizeof(double));
   float ms = 0, ms2 = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
-  cudaEventElapsedTime(&ms2, ctx->ev[1], ctx->ev[2]);
+  for (auto& rs : ctx->sets) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, rs->ev0, rs->ev1) == cudaSuccess) ms2 += t;
+  }
   ctx->stats.last_device_ms = ms;
   ctx->stats.last_score_kernel_ms = ms2;
   ctx->stats.evals++;
@@ -695,12 +706,12 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   return GAML_OK;
 }
 
-int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, gaml_result* result, int32_t* zeros) {
-  const size_t n_sets = ctx->sets.size();
-  if (!gathered || n_shards < 1 || !result) return fail(ctx, GAML_ERR_ARG, "bad combine arguments");
+int combine_raw(const double* gathered, int n_shards, int n_sets, const int32_t* kinds, const int64_t* n_reads_total,
+                const double* weights, int total_len, gaml_result* result, int32_t* zeros) {
+  if (!gathered || n_shards < 1 || n_sets < 0 || !result || (n_sets > 0 && (!kinds || !n_reads_total || !weights)))
+    return GAML_ERR_ARG;
   std::vector<double> score(n_sets);
-  for (size_t s = 0; s < n_sets; s++) {
-    ReadSetState& rs = *ctx->sets[s];
+  for (int s = 0; s < n_sets; s++) {
     // shard totals arrive as (hi, lo) pairs; add them in rank order with an error-free transformation
     double hi = 0, lo = 0, fl = 0;
     for (int k = 0; k < n_shards; k++) {
@@ -713,24 +724,39 @@ int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, 
       fl += p[2];
     }
     const double total = hi + lo;
-    double sc = total / (double)rs.n_total;   // total_prob / total_c, graph.cc:1515, 1536, 3087
-    if (rs.cfg.kind == GAML_KIND_PACBIO) {
+    double sc = total / (double)n_reads_total[s];   // total_prob / total_c, graph.cc:1515, 1536, 3087
+    if (kinds[s] == GAML_KIND_PACBIO) {
       const int tl = total_len == 0 ? 1 : total_len;
       sc -= log((double)(int)(2u * (unsigned)tl));   // graph.cc:3087
     }
     score[s] = sc;
     if (zeros) {
       zeros[2 * s] = (int32_t)fl;
-      zeros[2 * s + 1] = (int32_t)rs.n_total;
+      zeros[2 * s + 1] = (int32_t)n_reads_total[s];
     }
   }
   double prob = 0;
   for (int kind = 0; kind < 3; kind++)   // prob_calculator.h:70-107: single, paired, pacbio
-    for (size_t s = 0; s < n_sets; s++)
-      if (ctx->sets[s]->cfg.kind == kind) prob += score[s] * ctx->sets[s]->cfg.weight;
+    for (int s = 0; s < n_sets; s++)
+      if (kinds[s] == kind) prob += score[s] * weights[s];
   result->prob = prob;
   result->total_len = total_len;
-  result->n_sets = (int32_t)n_sets;
+  result->n_sets = n_sets;
+  return GAML_OK;
+}
+
+int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, gaml_result* result, int32_t* zeros) {
+  const size_t n_sets = ctx->sets.size();
+  std::vector<int32_t> kinds(n_sets);
+  std::vector<int64_t> counts(n_sets);
+  std::vector<double> weights(n_sets);
+  for (size_t s = 0; s < n_sets; s++) {
+    kinds[s] = ctx->sets[s]->cfg.kind;
+    counts[s] = ctx->sets[s]->n_total;
+    weights[s] = ctx->sets[s]->cfg.weight;
+  }
+  int rc = combine_raw(gathered, n_shards, (int)n_sets, kinds.data(), counts.data(), weights.data(), total_len, result, zeros);
+  if (rc) return fail(ctx, rc, "bad combine arguments");
   return GAML_OK;
 }
 
@@ -901,6 +927,8 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaEventCreate(&rs.ev0));
+  CU(cudaEventCreate(&rs.ev1));
   for (int m = 0; m < rs.n_mates; m++) {
     rs.mate[m].table_index = (int)ctx->stores.size();
     ctx->stores.push_back(&rs.mate[m]);
@@ -940,7 +968,8 @@ int gaml_cache_insert(gaml_ctx* ctx, int set, int mate, const int32_t* key, int3
     const gaml_alignment& a = records[i];
     if (a.read_id < 0 || a.read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
     if (a.orientation != 0 && a.orientation != 1) return fail(ctx, GAML_ERR_ARG, "record orientation must be 0 or 1");
-    if (a.edit_dist < 0 || a.edit_dist > max_ed) return fail(ctx, GAML_ERR_ARG, "record edit_dist outside the pow tables");
+    if (a.edit_dist < 0 || a.edit_dist > max_ed || a.edit_dist > 0xffff)
+      return fail(ctx, GAML_ERR_ARG, "record edit_dist outside the pow tables");
     mx = std::max(mx, a.position);
     if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
     const int local = (int)(a.read_id - rs->lo);
@@ -1045,6 +1074,12 @@ int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shard
                           int32_t* zeros) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   return combine(ctx, gathered, n_shards, total_len, result, zeros);
+}
+
+int gaml_combine_partials_raw(const double* gathered, int32_t n_shards, int32_t n_sets, const int32_t* kinds,
+                              const int64_t* n_reads_total, const double* weights, int32_t total_len,
+                              gaml_result* result, int32_t* zeros) {
+  return combine_raw(gathered, n_shards, n_sets, kinds, n_reads_total, weights, total_len, result, zeros);
 }
 
 int gaml_calc_prob(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,

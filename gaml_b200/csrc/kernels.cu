@@ -5,6 +5,12 @@
 // Exactness contract: every product/sum that the reference performs in fp64 is issued
 // with __dmul_rn/__dadd_rn so no FMA contraction can change a bit; the paired state therefore replays
 // ScoringState::probs (graph.cc:1936-1950) bit for bit. Only log/exp/log1p differ from glibc (<= 1-2 ulp).
+//
+// Execution shape: one thread per read, reads in id order, so a warp streams 32
+// consecutive 16-byte "first" records per mate with one coalesced 512-byte request. Reads with at most
+// two live placements per mate (virtually all) are finished in registers; the rest are appended to a
+// per-set list and replayed by a second, dense kernel from a scratch arena, so the streaming kernel
+// never carries the general sort/de-dup code through its warps.
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.h"
@@ -13,8 +19,9 @@ namespace gaml {
 
 namespace {
 
-constexpr int kCap = 8;            // placements per mate handled in registers/local memory
+constexpr int kCapLong = 8;        // pacbio placements handled in local memory before the scratch path
 constexpr int kBlock = 256;
+constexpr int kOvfBlock = 128;
 
 // ---- small helpers ------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
@@ -35,8 +42,9 @@ __device__ __forceinline__ void dd_merge(DD& a, const DD& b) {
   a.lo = __dadd_rn(a.lo, b.lo);
 }
 
-// Block reduction of (dd sum, floored count) -> partials[blockIdx.x]; warp shuffles then one smem hop.
-__device__ void block_reduce_store(DD acc, unsigned floored, double* partials) {
+// Block reduction of (dd sum, floored count) -> partials[slot]; warp shuffles then one smem hop.
+// Fixed shape, so the result is a pure function of the inputs (run-to-run deterministic).
+__device__ void block_reduce_store(DD acc, unsigned floored, double* partials, int slot) {
   __shared__ double s_hi[kBlock / 32], s_lo[kBlock / 32];
   __shared__ unsigned s_fl[kBlock / 32];
 #pragma unroll
@@ -47,7 +55,7 @@ __device__ void block_reduce_store(DD acc, unsigned floored, double* partials) {
     dd_merge(acc, o);
     floored += __shfl_down_sync(0xffffffffu, floored, off);
   }
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { s_hi[warp] = acc.hi; s_lo[warp] = acc.lo; s_fl[warp] = floored; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -57,7 +65,7 @@ __device__ void block_reduce_store(DD acc, unsigned floored, double* partials) {
       dd_merge(t, DD{s_hi[w], s_lo[w]});
       f += s_fl[w];
     }
-    double* p = partials + (size_t)blockIdx.x * kPartialStride;
+    double* p = partials + (size_t)slot * kPartialStride;
     p[0] = t.hi;
     p[1] = t.lo;
     p[2] = (double)f;
@@ -66,36 +74,43 @@ __device__ void block_reduce_store(DD acc, unsigned floored, double* partials) {
 }
 
 // ---- placement enumeration ----------------------------------------------------------------
-// Visits every (record, live occurrence) of one read in one mate store. F(seg, cur-shifted pos, row).
-template <class Row, class F>
-__device__ __forceinline__ void for_each_placement(const MateView& mv, uint32_t epoch, int r, F&& f) {
-  const uint32_t b = __ldg(mv.rowptr + r), e = __ldg(mv.rowptr + r + 1);
-  const Row* rows = static_cast<const Row*>(mv.rows);
-  for (uint32_t i = b; i < e; i++) {
-    const int4 rw = ldg4(rows + i);
-    const int key = rw.x;
-    const int4 hdr = ldg4(mv.slots + key);
-    if ((uint32_t)hdr.x != epoch) continue;
-    const int4 o0 = ldg4(reinterpret_cast<const int4*>(mv.slots + key) + 1);
-    f(o0, rw);
-    for (int t = 1; t < hdr.y; t++) {
-      const int4 ot = ldg4(mv.occ + hdr.z + t);
-      f(ot, rw);
-    }
-  }
+// One live key occurrence applied to one record: F(occurrence int4 {walk, seg, cur_pos, skip_below}, row, row index).
+template <class F>
+__device__ __forceinline__ void visit_row(const MateView& mv, uint32_t epoch, const int4& rw, int idx, F&& f) {
+  const int4 hdr = ldg4(mv.slots + rw.x);
+  if ((uint32_t)hdr.x != epoch) return;
+  const int4 o0 = ldg4(reinterpret_cast<const int4*>(mv.slots + rw.x) + 1);
+  f(o0, rw, idx);
+  for (int t = 1; t < hdr.y; t++) f(ldg4(mv.occ + hdr.z + t), rw, idx);
 }
 
-__device__ __forceinline__ void sort_by_ord(Plc* p, int n) {
-  for (int i = 1; i < n; i++) {
-    Plc v = p[i];
-    int j = i - 1;
-    while (j >= 0 && p[j].ord > v.ord) { p[j + 1] = p[j]; j--; }
-    p[j + 1] = v;
-  }
+// Short-read stores (hybrid layout): first[r] = {key, pos, edor | count<<16, row offset}; the read's
+// other records follow at rows[offset+1 ..]. key < 0 = the read has no record at all.
+template <class F>
+__device__ __forceinline__ void for_each_short(const MateView& mv, uint32_t epoch, int r, F&& f) {
+  int4 rw = ldg4(static_cast<const int4*>(mv.first) + r);
+  if (rw.x < 0) return;
+  int cnt = (rw.z >> 16) & 0x3fff;
+  const uint32_t base = (uint32_t)rw.w;
+  if (cnt == 0x3fff) cnt = (int)(__ldg(mv.rowptr + r + 1) - base);
+  rw.z &= 0x4000ffff;
+  visit_row(mv, epoch, rw, 0, f);
+  const RowShort* rows = static_cast<const RowShort*>(mv.rows);
+  for (int i = 1; i < cnt; i++) visit_row(mv, epoch, ldg4(rows + base + i), i, f);
 }
-__device__ __forceinline__ void sort_by_ord(PlcLong* p, int n) {
+
+// PacBio stores: plain CSR.
+template <class F>
+__device__ __forceinline__ void for_each_long(const MateView& mv, uint32_t epoch, int r, F&& f) {
+  const uint32_t b = __ldg(mv.rowptr + r), e = __ldg(mv.rowptr + r + 1);
+  const RowLong* rows = static_cast<const RowLong*>(mv.rows);
+  for (uint32_t i = b; i < e; i++) visit_row(mv, epoch, ldg4(rows + i), (int)(i - b), f);
+}
+
+template <class T>
+__device__ __forceinline__ void sort_by_ord(T* p, int n) {
   for (int i = 1; i < n; i++) {
-    PlcLong v = p[i];
+    T v = p[i];
     int j = i - 1;
     while (j >= 0 && p[j].ord > v.ord) { p[j + 1] = p[j]; j--; }
     p[j + 1] = v;
@@ -118,7 +133,7 @@ __device__ __forceinline__ int dedup_positions(Plc* p, int b, int e) {
 
 // ---- paired -------------------------------------------------------------------------------
 __device__ __forceinline__ double align_prob(const MateView& mv, int edor, int len) {
-  const int ed = edor & 0x3fffffff;
+  const int ed = edor & 0xffff;
   return __dmul_rn(__ldg(mv.pow_mismatch + ed), __ldg(mv.pow_match + (len - ed)));   // graph.cc:1859-1863
 }
 
@@ -141,57 +156,84 @@ __device__ __forceinline__ bool pair_term(const ScoreParams& P, int xpos, int xe
   return true;
 }
 
-// Replays the reference's per-read update for sorted placement lists: walks in ordinal order (erased
-// first: subtract, then added: add), x-major / y-minor inside a walk.
-__device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int n2, int l1, int l2, double acc) {
-  sort_by_ord(a, n1);
-  sort_by_ord(b, n2);
-  int i = 0, j = 0;
-  while (i < n1 && j < n2) {
-    const int w = min(a[i].walk, b[j].walk);
-    int e1 = i, e2 = j;
-    while (e1 < n1 && a[e1].walk == w) e1++;
-    while (e2 < n2 && b[e2].walk == w) e2++;
-    if (e1 > i && e2 > j) {
-      const int m1 = dedup_positions(a, i, e1), m2 = dedup_positions(b, j, e2);
-      const bool sub = w < P.n_erased;
-      for (int x = i; x < m1; x++) {
-        const double p1 = align_prob(P.m[0], a[x].edor, l1);
-        for (int y = j; y < m2; y++) {
-          double t;
-          if (pair_term(P, a[x].pos, a[x].edor, b[y].pos, b[y].edor, l1, l2, p1, t))
-            acc = sub ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
-        }
-      }
-    }
-    i = e1;
-    j = e2;
-  }
-  return acc;
-}
+// Up to two placements of one mate, in registers.
+struct Two {
+  int n;
+  unsigned long long ord0, ord1;
+  int walk0, pos0, edor0, walk1, pos1, edor1;
+};
 
-struct FirstPlc { int walk, pos, edor; };
-
-// Counts the placements of one mate and remembers the first one (the common case is exactly one).
-__device__ __forceinline__ int scan_short(const MateView& mv, uint32_t epoch, int r, FirstPlc& first) {
-  int n = 0;
-  for_each_placement<RowShort>(mv, epoch, r, [&](const int4& o, const int4& rw) {
+__device__ __forceinline__ void scan_two(const MateView& mv, uint32_t epoch, int r, Two& t) {
+  t.n = 0;
+  for_each_short(mv, epoch, r, [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
-    if (pos < o.w) return;
-    if (n == 0) { first.walk = o.x; first.pos = pos; first.edor = rw.z; }
-    n++;
+    if (pos < o.w) return;   // graph.cc:577
+    const unsigned long long ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)idx;
+    if (t.n == 0) { t.ord0 = ord; t.walk0 = o.x; t.pos0 = pos; t.edor0 = rw.z; }
+    else if (t.n == 1) { t.ord1 = ord; t.walk1 = o.x; t.pos1 = pos; t.edor1 = rw.z; }
+    t.n++;
   });
-  return n;
 }
 
-__device__ __forceinline__ int gather_short(const MateView& mv, uint32_t epoch, int r, Plc* out, int cap) {
+// Enumeration order + per-walk de-dup for at most two entries.
+__device__ __forceinline__ void order_two(Two& t) {
+  if (t.n != 2) return;
+  if (t.ord1 < t.ord0) {
+    unsigned long long o = t.ord0; t.ord0 = t.ord1; t.ord1 = o;
+    int x;
+    x = t.walk0; t.walk0 = t.walk1; t.walk1 = x;
+    x = t.pos0; t.pos0 = t.pos1; t.pos1 = x;
+    x = t.edor0; t.edor0 = t.edor1; t.edor1 = x;
+  }
+  if (t.walk0 == t.walk1 && t.pos0 == t.pos1) {   // graph.cc:583-590: later record replaces the payload
+    t.edor0 = t.edor1;
+    t.n = 1;
+  }
+}
+
+__device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, int xe, int yw, int yp, int ye, int l1,
+                                         int l2, double p1, double& acc) {
+  if (xw != yw) return;
+  double t;
+  if (pair_term(P, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+}
+
+// Per-read paired update for reads with <= 2 live placements per mate. For lists sorted in enumeration
+// order the plain x-major / y-minor loop with a same-walk filter IS the reference's order: walks ascend with
+// x, erased walks (subtract) precede added ones (add). Returns false if the read needs the scratch path.
+__device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
+  Two a, b;
+  scan_two(P.m[0], P.epoch, r, a);
+  if (a.n == 0) return true;
+  scan_two(P.m[1], P.epoch, r, b);
+  if (b.n == 0) return true;
+  if (a.n > 2 || b.n > 2) return false;
+  const uint32_t ll = __ldg(P.lens + r);
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  order_two(a);
+  order_two(b);
+  {
+    const double p1 = align_prob(P.m[0], a.edor0, l1);
+    one_pair(P, a.walk0, a.pos0, a.edor0, b.walk0, b.pos0, b.edor0, l1, l2, p1, acc);
+    if (b.n == 2) one_pair(P, a.walk0, a.pos0, a.edor0, b.walk1, b.pos1, b.edor1, l1, l2, p1, acc);
+  }
+  if (a.n == 2) {
+    const double p1 = align_prob(P.m[0], a.edor1, l1);
+    one_pair(P, a.walk1, a.pos1, a.edor1, b.walk0, b.pos0, b.edor0, l1, l2, p1, acc);
+    if (b.n == 2) one_pair(P, a.walk1, a.pos1, a.edor1, b.walk1, b.pos1, b.edor1, l1, l2, p1, acc);
+  }
+  return true;
+}
+
+// General replay from placement lists in memory (scratch path).
+__device__ int gather_short(const MateView& mv, uint32_t epoch, int r, Plc* out) {
   int n = 0;
-  for_each_placement<RowShort>(mv, epoch, r, [&](const int4& o, const int4& rw) {
+  for_each_short(mv, epoch, r, [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
     if (pos < o.w) return;
-    if (n < cap) {
+    if (out) {
       Plc p;
-      p.ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)rw.w;
+      p.ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)idx;
       p.walk = o.x;
       p.pos = pos;
       p.edor = rw.z;
@@ -203,30 +245,30 @@ __device__ __forceinline__ int gather_short(const MateView& mv, uint32_t epoch, 
   return n;
 }
 
-// Per-read paired update. Returns false if the read needs the scratch path (more than kCap placements).
-__device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
-  FirstPlc f1, f2;
-  const int n1 = scan_short(P.m[0], P.epoch, r, f1);
-  if (n1 == 0) return true;
-  const int n2 = scan_short(P.m[1], P.epoch, r, f2);
-  if (n2 == 0) return true;
-  const uint32_t ll = __ldg(P.lens + r);
-  const int l1 = ll & 0xffff, l2 = ll >> 16;
-  if (n1 == 1 && n2 == 1) {
-    if (f1.walk == f2.walk) {
-      double t;
-      const double p1 = align_prob(P.m[0], f1.edor, l1);
-      if (pair_term(P, f1.pos, f1.edor, f2.pos, f2.edor, l1, l2, p1, t))
-        acc = (f1.walk < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
-    }
-    return true;
+__device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int n2, int l1, int l2, double acc) {
+  sort_by_ord(a, n1);
+  sort_by_ord(b, n2);
+  // per-walk de-dup (lists are walk-major after the sort)
+  int m1 = 0, m2 = 0;
+  for (int i = 0; i < n1;) {
+    int e = i;
+    while (e < n1 && a[e].walk == a[i].walk) e++;
+    const int end = dedup_positions(a, i, e);
+    for (int k = i; k < end; k++) a[m1++] = a[k];
+    i = e;
   }
-  if (n1 > kCap || n2 > kCap) return false;
-  Plc a[kCap], b[kCap];
-  gather_short(P.m[0], P.epoch, r, a, kCap);
-  gather_short(P.m[1], P.epoch, r, b, kCap);
-  acc = apply_pairs(P, a, n1, b, n2, l1, l2, acc);
-  return true;
+  for (int i = 0; i < n2;) {
+    int e = i;
+    while (e < n2 && b[e].walk == b[i].walk) e++;
+    const int end = dedup_positions(b, i, e);
+    for (int k = i; k < end; k++) b[m2++] = b[k];
+    i = e;
+  }
+  for (int x = 0; x < m1; x++) {
+    const double p1 = align_prob(P.m[0], a[x].edor, l1);
+    for (int y = 0; y < m2; y++) one_pair(P, a[x].walk, a[x].pos, a[x].edor, b[y].walk, b[y].pos, b[y].edor, l1, l2, p1, acc);
+  }
+  return acc;
 }
 
 // log max(p/(2L), thr) and the floored flag: GetTotalProb, graph.cc:1505-1512.
@@ -257,7 +299,7 @@ __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P
       push_overflow(P, r);
     }
   }
-  block_reduce_store(sum, floored, P.partials);
+  block_reduce_store(sum, floored, P.partials, blockIdx.x);
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
@@ -279,54 +321,30 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
   }
 }
 
-// Reads with more than kCap placements on a mate: exact counts, scratch from a bump allocator, same replay.
-__global__ void __launch_bounds__(128) paired_overflow_kernel(const ScoreParams P, int full_mode, int partial_slot) {
+// Reads with more than two placements on a mate: exact counts, scratch from a bump allocator, same replay.
+__global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode, int slot0) {
   DD sum{0.0, 0.0};
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
-  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int r = (int)P.ovf_list[k];
-    FirstPlc f;
-    const int n1 = scan_short(P.m[0], P.epoch, r, f), n2 = scan_short(P.m[1], P.epoch, r, f);
+    const int n1 = gather_short(P.m[0], P.epoch, r, nullptr), n2 = gather_short(P.m[1], P.epoch, r, nullptr);
     const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
     double acc = full_mode ? 0.0 : P.values[r];
+    const uint32_t ll = __ldg(P.lens + r);
     if (base + n1 + n2 > P.scratch_cap) {
       atomicOr(P.error_flag, 2u);
     } else {
       Plc* a = P.scratch + base;
       Plc* b = a + n1;
-      gather_short(P.m[0], P.epoch, r, a, n1);
-      gather_short(P.m[1], P.epoch, r, b, n2);
-      const uint32_t ll = __ldg(P.lens + r);
+      gather_short(P.m[0], P.epoch, r, a);
+      gather_short(P.m[1], P.epoch, r, b);
       acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
       P.values[r] = acc;
     }
-    if (full_mode) {
-      const uint32_t ll = __ldg(P.lens + r);
-      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
-    }
+    if (full_mode) dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
   }
-  if (full_mode) {
-    // single block: reuse the block reduction with an explicit slot
-    __shared__ double s_hi[4], s_lo[4];
-    __shared__ unsigned s_fl[4];
-    for (int off = 16; off > 0; off >>= 1) {
-      DD o;
-      o.hi = __shfl_down_sync(0xffffffffu, sum.hi, off);
-      o.lo = __shfl_down_sync(0xffffffffu, sum.lo, off);
-      dd_merge(sum, o);
-      floored += __shfl_down_sync(0xffffffffu, floored, off);
-    }
-    if ((threadIdx.x & 31) == 0) { s_hi[threadIdx.x >> 5] = sum.hi; s_lo[threadIdx.x >> 5] = sum.lo; s_fl[threadIdx.x >> 5] = floored; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      DD t{0.0, 0.0};
-      unsigned fl = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
-      double* p = P.partials + (size_t)partial_slot * kPartialStride;
-      p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
-    }
-  }
+  if (full_mode) block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
 }
 
 // O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
@@ -337,13 +355,13 @@ __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams 
     const uint32_t ll = __ldg(P.lens + r);
     dd_add(sum, floored_log(P.values[r], P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
   }
-  block_reduce_store(sum, floored, P.partials);
+  block_reduce_store(sum, floored, P.partials, blockIdx.x);
 }
 
 // ---- single -------------------------------------------------------------------------------
 // CalcScoreForPaths (graph.cc:1650-1743): placements of all walks pooled per read, de-duplicated on the
 // global position, summed in enumeration order.
-__device__ __forceinline__ double single_sum(const ScoreParams& P, Plc* a, int n, int len) {
+__device__ double single_sum(const ScoreParams& P, Plc* a, int n, int len) {
   sort_by_ord(a, n);
   const int m = dedup_positions(a, 0, n);
   double acc = 0.0;
@@ -355,40 +373,34 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
   DD sum{0.0, 0.0};
   unsigned floored = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
-    FirstPlc f;
-    const int n = scan_short(P.m[0], P.epoch, r, f);
+    Two a;
+    scan_two(P.m[0], P.epoch, r, a);
     const int len = (int)__ldg(P.lens + r);
-    double acc = 0.0;
-    bool ok = true;
-    if (n == 1) {
-      acc = __dadd_rn(0.0, align_prob(P.m[0], f.edor, len));
-    } else if (n > 1) {
-      if (n <= kCap) {
-        Plc a[kCap];
-        gather_short(P.m[0], P.epoch, r, a, kCap);
-        acc = single_sum(P, a, n, len);
-      } else {
-        ok = false;
-      }
-    }
-    if (ok) {
-      P.values[r] = acc;
-      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
-    } else {
+    if (a.n > 2) {
       push_overflow(P, r);
+      continue;
     }
+    double acc = 0.0;
+    if (a.n >= 1) {
+      if (a.n == 2) {   // all walks are one group here (walk ordinal 0), so order_two de-duplicates on the global position
+        order_two(a);
+      }
+      acc = __dadd_rn(acc, align_prob(P.m[0], a.edor0, len));
+      if (a.n == 2) acc = __dadd_rn(acc, align_prob(P.m[0], a.edor1, len));
+    }
+    P.values[r] = acc;
+    dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
   }
-  block_reduce_store(sum, floored, P.partials);
+  block_reduce_store(sum, floored, P.partials, blockIdx.x);
 }
 
-__global__ void __launch_bounds__(128) single_overflow_kernel(const ScoreParams P, int partial_slot) {
+__global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreParams P, int slot0) {
   DD sum{0.0, 0.0};
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
-  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int r = (int)P.ovf_list[k];
-    FirstPlc f;
-    const int n1 = scan_short(P.m[0], P.epoch, r, f);
+    const int n1 = gather_short(P.m[0], P.epoch, r, nullptr);
     const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)n1);
     const int len = (int)__ldg(P.lens + r);
     double acc = 0.0;
@@ -396,30 +408,13 @@ __global__ void __launch_bounds__(128) single_overflow_kernel(const ScoreParams 
       atomicOr(P.error_flag, 2u);
     } else {
       Plc* a = P.scratch + base;
-      gather_short(P.m[0], P.epoch, r, a, n1);
+      gather_short(P.m[0], P.epoch, r, a);
       acc = single_sum(P, a, n1, len);
     }
     P.values[r] = acc;
     dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
   }
-  __shared__ double s_hi[4], s_lo[4];
-  __shared__ unsigned s_fl[4];
-  for (int off = 16; off > 0; off >>= 1) {
-    DD o;
-    o.hi = __shfl_down_sync(0xffffffffu, sum.hi, off);
-    o.lo = __shfl_down_sync(0xffffffffu, sum.lo, off);
-    dd_merge(sum, o);
-    floored += __shfl_down_sync(0xffffffffu, floored, off);
-  }
-  if ((threadIdx.x & 31) == 0) { s_hi[threadIdx.x >> 5] = sum.hi; s_lo[threadIdx.x >> 5] = sum.lo; s_fl[threadIdx.x >> 5] = floored; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    DD t{0.0, 0.0};
-    unsigned fl = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
-    double* p = P.partials + (size_t)partial_slot * kPartialStride;
-    p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
-  }
+  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
 }
 
 // ---- pacbio (log space; logdouble.hpp) -----------------------------------------------------
@@ -445,27 +440,6 @@ __device__ __forceinline__ double warp_lse(double v) {
   return __dadd_rn(m, log(s));
 }
 
-__device__ __forceinline__ int scan_long(const MateView& mv, uint32_t epoch, int r, double& first) {
-  int n = 0;
-  for_each_placement<RowLong>(mv, epoch, r, [&](const int4&, const int4& rw) {
-    if (n == 0) first = __hiloint2double(rw.w, rw.z);
-    n++;
-  });
-  return n;
-}
-
-__device__ __forceinline__ int gather_long(const MateView& mv, uint32_t epoch, int r, PlcLong* out, int cap) {
-  int n = 0;
-  for_each_placement<RowLong>(mv, epoch, r, [&](const int4& o, const int4& rw) {
-    if (n < cap) {
-      out[n].ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)rw.y;
-      out[n].logprob = __hiloint2double(rw.w, rw.z);
-    }
-    n++;
-  });
-  return n;
-}
-
 __device__ __forceinline__ double pacbio_floor(const ScoreParams& P, double v, int len, unsigned& floored) {
   const double fl = __dadd_rn(P.floor_a, __dmul_rn(P.floor_b, (double)len));   // graph.cc:3075-3076
   if (v < fl) { floored++; v = fl; }
@@ -476,40 +450,40 @@ __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P
   DD sum{0.0, 0.0};
   unsigned floored = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
-    double first = 0.0;
-    const int n = scan_long(P.m[0], P.epoch, r, first);
-    double acc = -INFINITY;
-    bool ok = true;
-    if (n == 1) {
-      acc = first;
-    } else if (n > 1) {
-      if (n <= kCap) {
-        PlcLong a[kCap];
-        gather_long(P.m[0], P.epoch, r, a, kCap);
-        sort_by_ord(a, n);
-        for (int x = 0; x < n; x++) acc = lse_add(acc, a[x].logprob);
-      } else {
-        ok = false;
+    PlcLong a[kCapLong];
+    int n = 0;
+    for_each_long(P.m[0], P.epoch, r, [&](const int4& o, const int4& rw, int idx) {
+      if (n < kCapLong) {
+        a[n].ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)idx;
+        a[n].logprob = __hiloint2double(rw.w, rw.z);
       }
-    }
-    if (ok) {
-      P.values[r] = acc;
-      dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
-    } else {
+      n++;
+    });
+    if (n > kCapLong) {
       push_overflow(P, r);
+      continue;
     }
+    double acc = -INFINITY;
+    if (n == 1) {
+      acc = a[0].logprob;
+    } else if (n > 1) {
+      sort_by_ord(a, n);
+      for (int x = 0; x < n; x++) acc = lse_add(acc, a[x].logprob);
+    }
+    P.values[r] = acc;
+    dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
   }
-  block_reduce_store(sum, floored, P.partials);
+  block_reduce_store(sum, floored, P.partials, blockIdx.x);
 }
 
-// One WARP per many-placement read: lanes gather a strided share, each folds its share sequentially,
-// and the 32 partial log-sums are combined with the warp-shuffle LSE.
-__global__ void __launch_bounds__(128) pacbio_overflow_kernel(const ScoreParams P, int partial_slot) {
+// One WARP per many-placement read: lanes fold a strided share of the read's records sequentially and the 32
+// partial log-sums are combined with the warp-shuffle LSE (order-free; within the 1e-12 per-read budget).
+__global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreParams P, int slot0) {
   DD sum{0.0, 0.0};
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  for (uint32_t k = warp; k < n; k += n_warps) {
+  const int lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += n_warps) {
     const int r = (int)P.ovf_list[k];
     const MateView& mv = P.m[0];
     const uint32_t b = __ldg(mv.rowptr + r), e = __ldg(mv.rowptr + r + 1);
@@ -528,17 +502,7 @@ __global__ void __launch_bounds__(128) pacbio_overflow_kernel(const ScoreParams 
       dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
     }
   }
-  __shared__ double s_hi[4], s_lo[4];
-  __shared__ unsigned s_fl[4];
-  if (lane == 0) { s_hi[warp] = sum.hi; s_lo[warp] = sum.lo; s_fl[warp] = floored; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    DD t{0.0, 0.0};
-    unsigned fl = 0;
-    for (int w = 0; w < n_warps; w++) { dd_merge(t, DD{s_hi[w], s_lo[w]}); fl += s_fl[w]; }
-    double* p = P.partials + (size_t)partial_slot * kPartialStride;
-    p[0] = t.hi; p[1] = t.lo; p[2] = (double)fl; p[3] = 0.0;
-  }
+  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
 }
 
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
@@ -555,25 +519,42 @@ __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, KeySlot* const*
   tables[u.store][u.key] = s;
 }
 
-// out[set] = {sum_hi, sum_lo, floored, flags}: fixed-order double-double sum of the block partials.
-__global__ void finalize_kernel(const double* partials, const int* set_begin, int n_sets, double* out,
-                                const uint32_t* error_flag, const uint32_t* ovf_counts) {
-  const int s = threadIdx.x;
-  if (s >= n_sets) return;
+// out[set] = {sum_hi, sum_lo, floored, flags}: one block per set; thread t folds partials t, t+256, ... and the
+// 256 thread sums are folded in index order by thread 0 — a fixed association, independent of timing.
+__global__ void __launch_bounds__(kBlock) finalize_kernel(const double* partials, const int* set_begin, double* out,
+                                                          const uint32_t* error_flag, const uint32_t* ovf_counts) {
+  __shared__ double s_hi[kBlock], s_lo[kBlock], s_fl[kBlock];
+  const int s = blockIdx.x;
   DD t{0.0, 0.0};
   double fl = 0.0;
-  for (int b = set_begin[s]; b < set_begin[s + 1]; b++) {
+  for (int b = set_begin[s] + threadIdx.x; b < set_begin[s + 1]; b += kBlock) {
     const double* p = partials + (size_t)b * kPartialStride;
     dd_merge(t, DD{p[0], p[1]});
     fl += p[2];
   }
-  // renormalise so hi carries the rounded total
-  const double hi = __dadd_rn(t.hi, t.lo);
-  const double lo = __dsub_rn(t.lo, __dsub_rn(hi, t.hi));
-  out[s * 4 + 0] = hi;
-  out[s * 4 + 1] = lo;
-  out[s * 4 + 2] = fl;
-  out[s * 4 + 3] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
+  s_hi[threadIdx.x] = t.hi;
+  s_lo[threadIdx.x] = t.lo;
+  s_fl[threadIdx.x] = fl;
+  __syncthreads();
+  for (int w = kBlock / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      DD a{s_hi[threadIdx.x], s_lo[threadIdx.x]};
+      dd_merge(a, DD{s_hi[threadIdx.x + w], s_lo[threadIdx.x + w]});
+      s_hi[threadIdx.x] = a.hi;
+      s_lo[threadIdx.x] = a.lo;
+      s_fl[threadIdx.x] += s_fl[threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // renormalise so hi carries the rounded total
+    const double hi = __dadd_rn(s_hi[0], s_lo[0]);
+    const double lo = __dsub_rn(s_lo[0], __dsub_rn(hi, s_hi[0]));
+    out[s * 4 + 0] = hi;
+    out[s * 4 + 1] = lo;
+    out[s * 4 + 2] = s_fl[0];
+    out[s * 4 + 3] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
+  }
 }
 
 // ---- CSR build: arena (key-major) -> rows (read-major) --------------------------------------
@@ -594,9 +575,10 @@ __global__ void fill_rows_kernel(const int4* arena, size_t n, const uint32_t* ro
   }
 }
 
-// Atomics scatter in arbitrary order; restore arena (= reference list) order inside every read's row.
+// Atomics scatter in arbitrary order; restore arena (= reference list) order inside every read's row, then
+// (short stores) publish the dense first-record array of the hybrid layout.
 template <bool kLong>
-__global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows) {
+__global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows, int4* first) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = rowptr[r], e = rowptr[r + 1];
@@ -613,6 +595,18 @@ __global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows
     }
     rows[j] = v;
   }
+  if (!kLong) {
+    int4 f;
+    if (e > b) {
+      f = rows[b];
+      const uint32_t cnt = e - b;
+      f.z |= (int)((cnt < 0x3fffu ? cnt : 0x3fffu) << 16);
+      f.w = (int)b;
+    } else {
+      f.x = -1; f.y = 0; f.z = 0; f.w = 0;
+    }
+    first[r] = f;
+  }
 }
 
 int grid_for(size_t n, int block, int sm_count, int per_sm) {
@@ -625,42 +619,53 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 
 // ---- launch wrappers ------------------------------------------------------------------------
 int score_grid(int n_reads, int sm_count) { return grid_for((size_t)n_reads, kBlock, sm_count, 8); }
+int overflow_grid(int sm_count) { return sm_count; }
 
 void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st) {
   if (n <= 0) return;
   apply_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(upd, n, tables, epoch);
 }
 
-void launch_paired_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+// e0/e1 bracket the streaming kernel(s) of the set on the launching stream (roofline timing).
+void launch_paired_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaEventRecord(e0, st);
   paired_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  paired_overflow_kernel<<<1, 128, 0, st>>>(P, 1, ovf_slot);
+  cudaEventRecord(e1, st);
+  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1, grid);
 }
 
-void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int sm_count, cudaStream_t st) {
+void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count,
+                         cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaEventRecord(e0, st);
   if (n_touch_records > 0) {
     paired_delta_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P);
-    paired_overflow_kernel<<<1, 128, 0, st>>>(P, 0, 0);
+    paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 0, 0);
   }
   paired_total_kernel<<<grid_total, kBlock, 0, st>>>(P);
+  cudaEventRecord(e1, st);
 }
 
-void launch_single_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+void launch_single_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaEventRecord(e0, st);
   single_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  single_overflow_kernel<<<1, 128, 0, st>>>(P, ovf_slot);
+  cudaEventRecord(e1, st);
+  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid);
 }
 
-void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_slot, cudaStream_t st) {
+void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+  cudaEventRecord(e0, st);
   pacbio_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  pacbio_overflow_kernel<<<1, 128, 0, st>>>(P, ovf_slot);
+  cudaEventRecord(e1, st);
+  pacbio_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid);
 }
 
 void launch_finalize(const double* partials, const int* set_begin, int n_sets, double* out, const uint32_t* error_flag,
                      const uint32_t* ovf_counts, cudaStream_t st) {
-  finalize_kernel<<<1, 32 * ((n_sets + 31) / 32), 0, st>>>(partials, set_begin, n_sets, out, error_flag, ovf_counts);
+  finalize_kernel<<<n_sets, kBlock, 0, st>>>(partials, set_begin, out, error_flag, ovf_counts);
 }
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
-                      void* rows, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches) {
+                      void* rows, void* first, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches) {
   // rowptr doubles as the count array (n_reads + 1 entries, zeroed here)
   cudaError_t err = cudaMemsetAsync(rowptr, 0, sizeof(uint32_t) * ((size_t)n_reads + 1), st);
   if (err != cudaSuccess) return err;
@@ -680,10 +685,13 @@ cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_
     const int g = grid_for(n_records, 256, sm_count, 16);
     if (is_long) fill_rows_kernel<true><<<g, 256, 0, st>>>(static_cast<const int4*>(arena), n_records, rowptr, cursor, static_cast<int4*>(rows));
     else fill_rows_kernel<false><<<g, 256, 0, st>>>(static_cast<const int4*>(arena), n_records, rowptr, cursor, static_cast<int4*>(rows));
+    (*launches)++;
+  }
+  if (n_reads > 0) {
     const int gs = (n_reads + 255) / 256;
-    if (is_long) sort_rows_kernel<true><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows));
-    else sort_rows_kernel<false><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows));
-    (*launches) += 2;
+    if (is_long) sort_rows_kernel<true><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows), nullptr);
+    else sort_rows_kernel<false><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows), static_cast<int4*>(first));
+    (*launches)++;
   }
   return cudaGetLastError();
 }

@@ -143,6 +143,12 @@ int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64
 int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shards, int32_t total_len,
                           gaml_result* result, int32_t* zeros);
 
+/* Context-free form of the combine step (pure host arithmetic, usable on ranks that only reduce):
+ * kinds / n_reads_total / weights describe the n_sets read sets in the order they were added. */
+int gaml_combine_partials_raw(const double* gathered, int32_t n_shards, int32_t n_sets, const int32_t* kinds,
+                              const int64_t* n_reads_total, const double* weights, int32_t total_len,
+                              gaml_result* result, int32_t* zeros);
+
 /* Three-phase form of gaml_calc_prob_partial for measurement: prepare = host flattening + H2D of the
  * per-evaluation tables; launch = the kernels (asynchronous, on gaml_ctx_stream); finish = D2H + sync. */
 int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks);

