@@ -288,12 +288,15 @@ def main():
     log(f"[rank {rank}] workload generated in {t_gen:.1f}s; cache of {cache_bytes / 1e6:.1f} MB inserted+CSR built in {t_upload:.2f}s")
     walks0 = wl.evals[0]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    flush_view = flush.view(torch.int32)
+    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
 
     def full_step_device():
         """One full evaluation; returns (device ms of the evaluation's kernels, ms of the dominant kernel)."""
         pc.reset_state()
         pc.prepare(walks0)
-        flush.fill_(1)
+        flush.fill_(1)            # write > L2 ...
+        flush_sink.copy_(flush_view.sum())   # ... then read it back so L2 is left holding CLEAN foreign lines
         torch.cuda.synchronize()
         pc.launch()
         part, tl = pc.finish()
@@ -365,7 +368,7 @@ def main():
         "config": {"workload": WORKLOAD_NAME + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
                    "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
                    "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
-                   "l2": "flushed between steps (256 MiB write)", "timing": "CUDA events on the library stream, max over ranks",
+                   "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events on the library stream, max over ranks",
                    "parallelism": f"read-id shards x{world}, all-gather of 24 B partials per read set"},
         "roofline": {"bound": "hbm", "kernel": "paired_full_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,

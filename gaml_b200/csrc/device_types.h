@@ -64,6 +64,8 @@ struct MateView {
   const void* first;         // short stores: dense int4 per read {key, pos, edor | count<<16, row offset}; key<0 = none
   const void* rows;          // RowShort* / RowLong* (read-major CSR; a read's rows in reference list order)
   const uint32_t* rowptr;    // n_reads + 1
+  const void* crows;         // compact copy of the rows of the tier-2 reads (list order), RowShort*
+  const uint32_t* cptr;      // n_complex + 1 offsets into crows
   const KeySlot* slots;
   const Occ* occ;
   const double* pow_match;   // match^k     (graph.cc:1451)
@@ -90,6 +92,10 @@ struct ScoreParams {
   unsigned long long* scratch_cursor;
   unsigned long long scratch_cap;
   uint32_t* error_flag;
+  // static tier-2 list (reads owning several records on a mate), built at cache commit
+  const uint32_t* complex_list;
+  const uint32_t* clens;     // lens[] gathered in list order
+  int32_t n_complex;
   // reduction
   double* partials;          // [n_partial_blocks][kPartialStride]
   // delta discovery

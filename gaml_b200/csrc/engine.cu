@@ -88,7 +88,7 @@ struct MateStore {
   std::vector<KeyMeta> keys;
   std::vector<int4> pending;          // staged arena records (ArenaShort / ArenaLong bit patterns)
   size_t arena_n = 0;                 // records on the device
-  DevBuf arena, rows, first, rowptr, cursor, slots;
+  DevBuf arena, rows, first, rowptr, cursor, slots, crows, cptr;
   bool dirty = true;
   std::vector<double> pow_match, pow_mismatch;
   DevBuf d_pow_match, d_pow_mismatch;
@@ -104,7 +104,9 @@ struct ReadSetState {
   int max_len[2] = {0, 0};
   std::vector<int32_t> len[2];
   MateStore mate[2];
-  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list;
+  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens;
+  int n_complex = 0;
+  bool complex_dirty = true;
   int ins_n = 0;
   double floor_a = 0, floor_b = 0;
   // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
@@ -124,6 +126,7 @@ struct SetPlan {
   int64_t records = 0;          // A: live (record, occurrence) pairs in this shard
   int64_t touch_records = 0;
   int grid = 0;                 // blocks of the reducing kernel
+  int cgrid = 0;                // blocks of the tier-2 (several records per read) kernel
   int n_partials = 0;
   int partial_begin = 0;
   size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
@@ -407,6 +410,38 @@ int commit(gaml_ctx* ctx) {
                    st.rows.p, st.first.p, ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->sm_count, ctx->stream, &launches));
       ctx->stats.kernel_launches += launches;
       st.dirty = false;
+      rs.complex_dirty = true;
+    }
+    if (rs.complex_dirty && rs.cfg.kind != GAML_KIND_PACBIO) {
+      // static tier-2 list: reads that own more than one record on some mate
+      CU(rs.d_complex.reserve(std::max<size_t>(rs.n_local, 1) * 4, 0, false, ctx->stream));
+      uint32_t* flags = rs.mate[0].cursor.as<uint32_t>();   // scratch, free after build_csr
+      int launches = 0;
+      CU(build_complex_list(rs.mate[0].first.p, rs.n_mates == 2 ? rs.mate[1].first.p : nullptr, rs.n_local, flags,
+                            rs.d_complex.as<uint32_t>(), ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->stream, &launches));
+      ctx->stats.kernel_launches += launches;
+      launches = 0;
+      uint32_t n_complex = 0;
+      CU(cudaMemcpyAsync(&n_complex, flags + rs.n_local, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      rs.n_complex = (int)n_complex;
+      // compact copy of the listed reads' rows, per mate, + their packed lengths
+      CU(rs.d_clens.reserve(std::max<size_t>(n_complex, 1) * 4, 0, false, ctx->stream));
+      for (int m = 0; m < rs.n_mates; m++) {
+        MateStore& st = rs.mate[m];
+        CU(st.cptr.reserve(((size_t)n_complex + 1) * 4, 0, false, ctx->stream));
+        CU(compact_offsets(rs.d_complex.as<uint32_t>(), rs.n_complex, st.rowptr.as<uint32_t>(), st.cptr.as<uint32_t>(),
+                           rs.d_lens.as<uint32_t>(), m == 0 ? rs.d_clens.as<uint32_t>() : nullptr, ctx->d_csr_temp.p,
+                           ctx->d_csr_temp.cap, ctx->stream, &launches));
+        uint32_t total_rows = 0;
+        CU(cudaMemcpyAsync(&total_rows, st.cptr.as<uint32_t>() + n_complex, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(st.crows.reserve(std::max<size_t>(total_rows, 1) * 16, 0, false, ctx->stream));
+        CU(compact_copy(rs.d_complex.as<uint32_t>(), rs.n_complex, st.rowptr.as<uint32_t>(), st.cptr.as<uint32_t>(), st.rows.p,
+                        st.crows.p, ctx->stream, &launches));
+      }
+      ctx->stats.kernel_launches += launches;
+      rs.complex_dirty = false;
     }
   }
   if (ctx->tables_dirty) {
@@ -474,14 +509,16 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       for (int m = 0; m < 2; m++) group_occurrences(ob[m], rs.mate[m].table_index, updates, occs[rs.mate[m].table_index]);
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
-      sp.n_partials = sp.grid + (sp.full ? overflow_grid(ctx->sm_count) : 0);
+      sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(rs.n_complex, ctx->sm_count) : 0;
+      sp.n_partials = sp.grid + (sp.full ? sp.cgrid + overflow_grid(ctx->sm_count) : 0);
     } else {
       OccBuilder ob;
       sp.full = true;
       if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, walks, ob, sp);
       else flatten_pacbio(ctx, rs, walks, ob, sp);
       group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
-      sp.n_partials = sp.grid + overflow_grid(ctx->sm_count);
+      sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(rs.n_complex, ctx->sm_count) : 0;
+      sp.n_partials = sp.grid + sp.cgrid + overflow_grid(ctx->sm_count);
     }
     sp.partial_begin = partial_cursor;
     partial_cursor += sp.n_partials;
@@ -563,6 +600,8 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
     P.m[m].first = st.first.p;
     P.m[m].rows = st.rows.p;
     P.m[m].rowptr = st.rowptr.as<uint32_t>();
+    P.m[m].crows = st.crows.p;
+    P.m[m].cptr = st.cptr.as<uint32_t>();
     P.m[m].slots = st.slots.as<KeySlot>();
     P.m[m].occ = reinterpret_cast<const Occ*>(blob + sp.occ_off[m]);
     P.m[m].pow_match = st.d_pow_match.as<double>();
@@ -588,6 +627,9 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.ovf_cap = ctx->ovf_cap;
   P.scratch = ctx->d_scratch.as<Plc>();
   P.scratch_cap = ctx->scratch_entries;
+  P.complex_list = rs.d_complex.as<uint32_t>();
+  P.clens = rs.d_clens.as<uint32_t>();
+  P.n_complex = rs.n_complex;
   P.partials = ctx->d_partials.as<double>() + (size_t)sp.partial_begin * kPartialStride;
   P.arena1 = rs.mate[0].arena.as<ArenaShort>();
   P.touch = reinterpret_cast<const TouchRange*>(blob + sp.touch_off);
@@ -622,20 +664,21 @@ int launch(gaml_ctx* ctx) {
     reads += rs.n_local;
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
-        launch_paired_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
-        launches += 2;
+        launch_paired_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1);
+        launches += 2 + (sp.cgrid > 0);
         any_full = true;
-        // rowptr (4+4) + lens (4) + probs write (8) per pair, 16 per record
-        bytes += 16 * sp.records + 20 * (int64_t)rs.n_local;
+        // 16 B per live record + packed lengths (4) + probs write (8) per pair (no probs read: fused)
+        bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       } else {
         launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, og, ctx->sm_count, st, rs.ev0, rs.ev1);
         launches += sp.touch_records > 0 ? 3 : 1;
+        // touched records + the O(R) pass: probs read (8) + packed lengths (4) per pair
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       }
     } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
-      launch_single_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
-      launches += 2;
-      bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
+      launch_single_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1);
+      launches += 2 + (sp.cgrid > 0);
+      bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
     } else {
       launch_pacbio_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
       launches += 2;

@@ -99,6 +99,15 @@ __device__ __forceinline__ void for_each_short(const MateView& mv, uint32_t epoc
   for (int i = 1; i < cnt; i++) visit_row(mv, epoch, ldg4(rows + base + i), i, f);
 }
 
+// Compact copy of the records of the tier-2 reads (those owning several records on a mate): read k of the
+// static list owns crows[cptr[k] .. cptr[k+1]) — contiguous across neighbouring threads, so tier 2 streams.
+template <class F>
+__device__ __forceinline__ void for_each_compact(const MateView& mv, uint32_t epoch, int k, F&& f) {
+  const uint32_t b = __ldg(mv.cptr + k), e = __ldg(mv.cptr + k + 1);
+  const RowShort* rows = static_cast<const RowShort*>(mv.crows);
+  for (uint32_t i = b; i < e; i++) visit_row(mv, epoch, ldg4(rows + i), (int)(i - b), f);
+}
+
 // PacBio stores: plain CSR.
 template <class F>
 __device__ __forceinline__ void for_each_long(const MateView& mv, uint32_t epoch, int r, F&& f) {
@@ -163,16 +172,19 @@ struct Two {
   int walk0, pos0, edor0, walk1, pos1, edor1;
 };
 
+template <bool kCompact = false>
 __device__ __forceinline__ void scan_two(const MateView& mv, uint32_t epoch, int r, Two& t) {
   t.n = 0;
-  for_each_short(mv, epoch, r, [&](const int4& o, const int4& rw, int idx) {
+  auto visit = [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
     if (pos < o.w) return;   // graph.cc:577
     const unsigned long long ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)idx;
     if (t.n == 0) { t.ord0 = ord; t.walk0 = o.x; t.pos0 = pos; t.edor0 = rw.z; }
     else if (t.n == 1) { t.ord1 = ord; t.walk1 = o.x; t.pos1 = pos; t.edor1 = rw.z; }
     t.n++;
-  });
+  };
+  if (kCompact) for_each_compact(mv, epoch, r, visit);
+  else for_each_short(mv, epoch, r, visit);
 }
 
 // Enumeration order + per-walk de-dup for at most two entries.
@@ -201,14 +213,15 @@ __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, i
 // Per-read paired update for reads with <= 2 live placements per mate. For lists sorted in enumeration
 // order the plain x-major / y-minor loop with a same-walk filter IS the reference's order: walks ascend with
 // x, erased walks (subtract) precede added ones (add). Returns false if the read needs the scratch path.
+template <bool kCompact = false>
 __device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
   Two a, b;
-  scan_two(P.m[0], P.epoch, r, a);
+  const uint32_t ll = __ldg((kCompact ? P.clens : P.lens) + r);   // r is the list index k in the compact variant
+  scan_two<kCompact>(P.m[0], P.epoch, r, a);
   if (a.n == 0) return true;
-  scan_two(P.m[1], P.epoch, r, b);
+  scan_two<kCompact>(P.m[1], P.epoch, r, b);
   if (b.n == 0) return true;
   if (a.n > 2 || b.n > 2) return false;
-  const uint32_t ll = __ldg(P.lens + r);
   const int l1 = ll & 0xffff, l2 = ll >> 16;
   order_two(a);
   order_two(b);
@@ -284,22 +297,76 @@ __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
   else atomicOr(P.error_flag, 1u);
 }
 
-// FULL: every read of the shard is re-scored from an empty state and the total is reduced in the same
-// pass (CalcScoreForPathsNew on a fresh ScoringState + GetTotalProb).
+// FULL, tier 1 (the streaming kernel): every read of the shard is re-scored from an empty state and the total
+// is reduced in the same pass (CalcScoreForPathsNew on a fresh ScoringState + GetTotalProb).
+// A warp reads 32 consecutive first-records of each mate (two coalesced 512-byte requests) plus the packed
+// lengths; all three loads are issued before anything depends on them, then the two key slots. Reads that
+// own more than one record on a mate are a STATIC property of the cache: they are skipped here (idle lanes,
+// no divergent code) and handled densely by tier 2 from a list built at commit time. A key that occurs
+// several times in this evaluation (repeat node) sends the read to the scratch path.
+__device__ __forceinline__ void paired_simple_read(const ScoreParams& P, int r, const int4& rw1, const int4& rw2,
+                                                   uint32_t ll, DD& sum, unsigned& floored) {
+  if ((((rw1.z | rw2.z) >> 17) & 0x1fff) != 0) return;   // count >= 2 on a mate: tier 2
+  double acc = 0.0;
+  if (rw1.x >= 0 && rw2.x >= 0) {
+    const int4 h1 = ldg4(P.m[0].slots + rw1.x);
+    const int4 h2 = ldg4(P.m[1].slots + rw2.x);
+    if ((uint32_t)h1.x == P.epoch && (uint32_t)h2.x == P.epoch) {
+      if (h1.y > 1 || h2.y > 1) {
+        push_overflow(P, r);
+        return;
+      }
+      const int4 o1 = ldg4(reinterpret_cast<const int4*>(P.m[0].slots + rw1.x) + 1);
+      const int4 o2 = ldg4(reinterpret_cast<const int4*>(P.m[1].slots + rw2.x) + 1);
+      const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
+      if (p1 >= o1.w && p2 >= o2.w && o1.x == o2.x) {   // skip rule (graph.cc:577) and same walk
+        const int l1 = ll & 0xffff, l2 = ll >> 16;
+        double t;
+        if (pair_term(P, p1, rw1.z & 0x4000ffff, p2, rw2.z & 0x4000ffff, l1, l2, align_prob(P.m[0], rw1.z, l1), t))
+          acc = (o1.x < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+      }
+    }
+  }
+  P.values[r] = acc;
+  dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+}
+
 __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P) {
   DD sum{0.0, 0.0};
   unsigned floored = 0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+  const int4* first1 = static_cast<const int4*>(P.m[0].first);
+  const int4* first2 = static_cast<const int4*>(P.m[1].first);
+  const int stride = gridDim.x * blockDim.x;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // two reads per iteration: six independent coalesced loads in flight per thread before any use
+  for (; r + stride < P.n_reads; r += 2 * stride) {
+    const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
+    const int4 b1 = __ldg(first1 + r + stride), b2 = __ldg(first2 + r + stride);
+    const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + stride);
+    paired_simple_read(P, r, a1, a2, la, sum, floored);
+    paired_simple_read(P, r + stride, b1, b2, lb, sum, floored);
+  }
+  if (r < P.n_reads) paired_simple_read(P, r, __ldg(first1 + r), __ldg(first2 + r), __ldg(P.lens + r), sum, floored);
+  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+}
+
+// FULL, tier 2: the reads that own several records on a mate (list built once per cache commit), one thread
+// each, at most two live placements per mate in registers; anything bigger goes to the scratch path.
+__global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P, int slot0) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
+    const int r = (int)__ldg(P.complex_list + k);
+    const uint32_t ll = __ldg(P.clens + k);
     double acc = 0.0;
-    if (paired_read(P, r, acc)) {
+    if (paired_read<true>(P, k, acc)) {
       P.values[r] = acc;
-      const uint32_t ll = __ldg(P.lens + r);
       dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
     } else {
       push_overflow(P, r);
     }
   }
-  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
@@ -369,29 +436,62 @@ __device__ double single_sum(const ScoreParams& P, Plc* a, int n, int len) {
   return acc;
 }
 
+// One read through the register path (<= 2 live placements); false = needs the scratch path.
+template <bool kCompact = false>
+__device__ __forceinline__ bool single_read(const ScoreParams& P, int r, int len, double& acc) {
+  Two a;
+  scan_two<kCompact>(P.m[0], P.epoch, r, a);
+  if (a.n > 2) return false;
+  acc = 0.0;
+  if (a.n >= 1) {
+    order_two(a);   // all walks are one group here (walk ordinal 0): de-duplicates on the global position
+    acc = __dadd_rn(acc, align_prob(P.m[0], a.edor0, len));
+    if (a.n == 2) acc = __dadd_rn(acc, align_prob(P.m[0], a.edor1, len));
+  }
+  return true;
+}
+
+// Tier 1: reads with at most one record (static) whose key occurs at most once in this evaluation.
 __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P) {
   DD sum{0.0, 0.0};
   unsigned floored = 0;
+  const int4* first = static_cast<const int4*>(P.m[0].first);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
-    Two a;
-    scan_two(P.m[0], P.epoch, r, a);
+    const int4 rw = __ldg(first + r);
     const int len = (int)__ldg(P.lens + r);
-    if (a.n > 2) {
-      push_overflow(P, r);
-      continue;
-    }
+    if (((rw.z >> 17) & 0x1fff) != 0) continue;   // several records: tier 2
     double acc = 0.0;
-    if (a.n >= 1) {
-      if (a.n == 2) {   // all walks are one group here (walk ordinal 0), so order_two de-duplicates on the global position
-        order_two(a);
+    if (rw.x >= 0) {
+      const int4 h = ldg4(P.m[0].slots + rw.x);
+      if ((uint32_t)h.x == P.epoch) {
+        if (h.y > 1) {
+          push_overflow(P, r);
+          continue;
+        }
+        acc = __dadd_rn(acc, align_prob(P.m[0], rw.z, len));   // no skip rule for single reads (graph.cc:632-645)
       }
-      acc = __dadd_rn(acc, align_prob(P.m[0], a.edor0, len));
-      if (a.n == 2) acc = __dadd_rn(acc, align_prob(P.m[0], a.edor1, len));
     }
     P.values[r] = acc;
     dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
   }
   block_reduce_store(sum, floored, P.partials, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParams P, int slot0) {
+  DD sum{0.0, 0.0};
+  unsigned floored = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
+    const int r = (int)__ldg(P.complex_list + k);
+    const int len = (int)__ldg(P.clens + k);
+    double acc;
+    if (single_read<true>(P, k, len, acc)) {
+      P.values[r] = acc;
+      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+    } else {
+      push_overflow(P, r);
+    }
+  }
+  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreParams P, int slot0) {
@@ -609,6 +709,51 @@ __global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows
   }
 }
 
+// Static tier-2 list: reads owning more than one record on some mate, in read-id order (scan, not atomics,
+// so the list — and with it the association of the partial sums — is the same on every run).
+__global__ void complex_flags_kernel(const int4* first1, const int4* first2, int n_reads, uint32_t* flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_reads) return;
+  uint32_t f = 0;
+  if (r < n_reads) {
+    int z = first1[r].z;
+    if (first2) z |= first2[r].z;
+    f = ((z >> 17) & 0x1fff) != 0;
+  }
+  flags[r] = f;
+}
+
+__global__ void complex_scatter_kernel(const int4* first1, const int4* first2, int n_reads, const uint32_t* offs,
+                                       uint32_t* list) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  int z = first1[r].z;
+  if (first2) z |= first2[r].z;
+  if (((z >> 17) & 0x1fff) != 0) list[offs[r]] = (uint32_t)r;
+}
+
+__global__ void compact_count_kernel(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr,
+                                     const uint32_t* lens, uint32_t* clens) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_complex) return;
+  uint32_t c = 0;
+  if (k < n_complex) {
+    const uint32_t r = list[k];
+    c = rowptr[r + 1] - rowptr[r];
+    if (clens) clens[k] = lens[r];
+  }
+  cptr[k] = c;
+}
+
+__global__ void compact_copy_kernel(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr,
+                                    const int4* rows, int4* crows) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_complex) return;
+  const uint32_t r = list[k];
+  const uint32_t b = rowptr[r], n = rowptr[r + 1] - b, d = cptr[k];
+  for (uint32_t i = 0; i < n; i++) crows[d + i] = rows[b + i];
+}
+
 int grid_for(size_t n, int block, int sm_count, int per_sm) {
   size_t need = (n + block - 1) / block;
   size_t cap = (size_t)sm_count * per_sm;
@@ -627,11 +772,12 @@ void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, ui
 }
 
 // e0/e1 bracket the streaming kernel(s) of the set on the launching stream (roofline timing).
-void launch_paired_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   cudaEventRecord(e0, st);
   paired_full_kernel<<<grid, kBlock, 0, st>>>(P);
+  if (cgrid > 0) paired_complex_kernel<<<cgrid, kBlock, 0, st>>>(P, grid);
   cudaEventRecord(e1, st);
-  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1, grid);
+  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1, grid + cgrid);
 }
 
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count,
@@ -645,11 +791,12 @@ void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int gri
   cudaEventRecord(e1, st);
 }
 
-void launch_single_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   cudaEventRecord(e0, st);
   single_full_kernel<<<grid, kBlock, 0, st>>>(P);
+  if (cgrid > 0) single_complex_kernel<<<cgrid, kBlock, 0, st>>>(P, grid);
   cudaEventRecord(e1, st);
-  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid);
+  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid + cgrid);
 }
 
 void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
@@ -691,6 +838,48 @@ cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_
     const int gs = (n_reads + 255) / 256;
     if (is_long) sort_rows_kernel<true><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows), nullptr);
     else sort_rows_kernel<false><<<gs, 256, 0, st>>>(rowptr, n_reads, static_cast<int4*>(rows), static_cast<int4*>(first));
+    (*launches)++;
+  }
+  return cudaGetLastError();
+}
+
+// Builds the static tier-2 list; flags must hold n_reads + 1 uint32 (scratch), list n_reads uint32. The number
+// of listed reads is left in flags[n_reads] (exclusive scan total).
+cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
+                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches) {
+  const int g = (n_reads + 1 + 255) / 256;
+  complex_flags_kernel<<<g, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2), n_reads, flags);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, flags, flags, n_reads + 1, st);
+  if (need > temp_bytes) return cudaErrorMemoryAllocation;
+  cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, flags, flags, n_reads + 1, st);
+  if (err != cudaSuccess) return err;
+  if (n_reads > 0)
+    complex_scatter_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2),
+                                                                 n_reads, flags, list);
+  (*launches) += 3;
+  return cudaGetLastError();
+}
+
+// Compact tier-2 store of one mate, step 1: per-list-entry record counts -> exclusive scan into cptr (n_complex+1
+// entries; the total is left in cptr[n_complex]); clens (optional) receives the packed lengths of the listed reads.
+cudaError_t compact_offsets(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr, const uint32_t* lens,
+                            uint32_t* clens, void* temp, size_t temp_bytes, cudaStream_t st, int* launches) {
+  compact_count_kernel<<<(n_complex + 1 + 255) / 256, 256, 0, st>>>(list, n_complex, rowptr, cptr, lens, clens);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, cptr, cptr, n_complex + 1, st);
+  if (need > temp_bytes) return cudaErrorMemoryAllocation;
+  cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, cptr, cptr, n_complex + 1, st);
+  (*launches) += 2;
+  return err != cudaSuccess ? err : cudaGetLastError();
+}
+
+// step 2: copy the listed reads' rows (already in reference list order) next to each other.
+cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr, const void* rows,
+                         void* crows, cudaStream_t st, int* launches) {
+  if (n_complex > 0) {
+    compact_copy_kernel<<<(n_complex + 255) / 256, 256, 0, st>>>(list, n_complex, rowptr, cptr, static_cast<const int4*>(rows),
+                                                               static_cast<int4*>(crows));
     (*launches)++;
   }
   return cudaGetLastError();
