@@ -480,7 +480,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
     SetPlan& sp = ctx->plan[s];
-    sp.grid = score_grid(rs.n_local, ctx->sm_count);
+    sp.grid = 0;
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       OccBuilder ob[2];
       std::vector<Walk> erased, added;
@@ -498,6 +498,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
         }
         erased.insert(erased.end(), idx.begin(), idx.end());
       }
+      sp.grid = score_grid(sp.full ? kGridPairedFull : kGridPairedTotal, rs.n_local, ctx->sm_count);
       sp.n_erased = (int)erased.size();
       int ord = 0;
       std::vector<TouchRange>* tp = sp.full ? nullptr : &touches[s];
@@ -509,7 +510,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       for (int m = 0; m < 2; m++) group_occurrences(ob[m], rs.mate[m].table_index, updates, occs[rs.mate[m].table_index]);
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
-      sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(rs.n_complex, ctx->sm_count) : 0;
+      sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(kGridPairedComplex, rs.n_complex, ctx->sm_count) : 0;
       sp.n_partials = sp.grid + (sp.full ? sp.cgrid + overflow_grid(ctx->sm_count) : 0);
     } else {
       OccBuilder ob;
@@ -517,7 +518,8 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, walks, ob, sp);
       else flatten_pacbio(ctx, rs, walks, ob, sp);
       group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
-      sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(rs.n_complex, ctx->sm_count) : 0;
+      sp.grid = score_grid(rs.cfg.kind == GAML_KIND_SINGLE ? kGridSingleFull : kGridPacbioFull, rs.n_local, ctx->sm_count);
+      sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
       sp.n_partials = sp.grid + sp.cgrid + overflow_grid(ctx->sm_count);
     }
     sp.partial_begin = partial_cursor;

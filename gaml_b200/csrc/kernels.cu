@@ -304,31 +304,43 @@ __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
 // own more than one record on a mate are a STATIC property of the cache: they are skipped here (idle lanes,
 // no divergent code) and handled densely by tier 2 from a list built at commit time. A key that occurs
 // several times in this evaluation (repeat node) sends the read to the scratch path.
-__device__ __forceinline__ void paired_simple_read(const ScoreParams& P, int r, const int4& rw1, const int4& rw2,
-                                                   uint32_t ll, DD& sum, unsigned& floored) {
-  if ((((rw1.z | rw2.z) >> 17) & 0x1fff) != 0) return;   // count >= 2 on a mate: tier 2
-  double acc = 0.0;
-  if (rw1.x >= 0 && rw2.x >= 0) {
-    const int4 h1 = ldg4(P.m[0].slots + rw1.x);
-    const int4 h2 = ldg4(P.m[1].slots + rw2.x);
-    if ((uint32_t)h1.x == P.epoch && (uint32_t)h2.x == P.epoch) {
-      if (h1.y > 1 || h2.y > 1) {
-        push_overflow(P, r);
-        return;
-      }
-      const int4 o1 = ldg4(reinterpret_cast<const int4*>(P.m[0].slots + rw1.x) + 1);
-      const int4 o2 = ldg4(reinterpret_cast<const int4*>(P.m[1].slots + rw2.x) + 1);
-      const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
-      if (p1 >= o1.w && p2 >= o2.w && o1.x == o2.x) {   // skip rule (graph.cc:577) and same walk
-        const int l1 = ll & 0xffff, l2 = ll >> 16;
-        double t;
-        if (pair_term(P, p1, rw1.z & 0x4000ffff, p2, rw2.z & 0x4000ffff, l1, l2, align_prob(P.m[0], rw1.z, l1), t))
-          acc = (o1.x < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
-      }
-    }
+// Pair term of a tier-1 read (one record per mate). Every table access that does not depend on another table is
+// issued up front (both key slots, the four pow-table entries), so a read costs three memory round trips: the
+// coalesced first-records, the slot/pow batch (L1/L2 resident), the insert-pdf entry. Returns false when the
+// read is not tier 1's to score (tier-2 read, or a key with several occurrences -> scratch path).
+__device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, int r, const int4& rw1, const int4& rw2,
+                                                  uint32_t ll, double& acc) {
+  acc = 0.0;
+  if ((((rw1.z | rw2.z) >> 17) & 0x1fff) != 0) return false;   // count >= 2 on a mate: tier 2
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  const int k1 = max(rw1.x, 0), k2 = max(rw2.x, 0);            // key -1 (no record) reads slot 0 and is ignored below
+  const int4* s1 = reinterpret_cast<const int4*>(P.m[0].slots + k1);
+  const int4* s2 = reinterpret_cast<const int4*>(P.m[1].slots + k2);
+  const int4 h1 = __ldg(s1), o1 = __ldg(s1 + 1), h2 = __ldg(s2), o2 = __ldg(s2 + 1);
+  const int e1 = rw1.z & 0xffff, e2 = rw2.z & 0xffff;
+  const double a1 = __ldg(P.m[0].pow_mismatch + e1), b1 = __ldg(P.m[0].pow_match + (l1 - e1));
+  const double a2 = __ldg(P.m[1].pow_mismatch + e2), b2 = __ldg(P.m[1].pow_match + (l2 - e2));
+  if (rw1.x < 0 || rw2.x < 0 || (uint32_t)h1.x != P.epoch || (uint32_t)h2.x != P.epoch) return true;
+  if (h1.y > 1 || h2.y > 1) {
+    push_overflow(P, r);
+    return false;
   }
-  P.values[r] = acc;
-  dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+  const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
+  if (p1 < o1.w || p2 < o2.w || o1.x != o2.x) return true;   // skip rule (graph.cc:577); pairs only inside one walk
+  const int xo = (rw1.z >> 30) & 1, yo = (rw2.z >> 30) & 1;
+  if (xo == yo) return true;                                   // graph.cc:1864
+  int d;
+  if (p1 < p2) {
+    if (xo != 0) return true;
+    d = p2 - p1 + l2;                                          // graph.cc:1866-1870
+  } else {
+    if (xo != 1) return true;
+    d = p1 - p2 + l1;                                          // graph.cc:1871-1875
+  }
+  const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
+  const double t = __dmul_rn(__dmul_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2)), ins);   // (p1*p2)*ins, graph.cc:1889
+  acc = (o1.x < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  return true;
 }
 
 __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P) {
@@ -337,16 +349,31 @@ __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P
   const int4* first1 = static_cast<const int4*>(P.m[0].first);
   const int4* first2 = static_cast<const int4*>(P.m[1].first);
   const int stride = gridDim.x * blockDim.x;
+  const int two_len = P.two_len;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  // two reads per iteration: six independent coalesced loads in flight per thread before any use
+  // Two reads per iteration: six independent coalesced loads in flight per thread before any use, and the two
+  // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
   for (; r + stride < P.n_reads; r += 2 * stride) {
     const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
     const int4 b1 = __ldg(first1 + r + stride), b2 = __ldg(first2 + r + stride);
     const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + stride);
-    paired_simple_read(P, r, a1, a2, la, sum, floored);
-    paired_simple_read(P, r + stride, b1, b2, lb, sum, floored);
+    double acc_a, acc_b;
+    const bool ok_a = paired_simple_acc(P, r, a1, a2, la, acc_a);
+    const bool ok_b = paired_simple_acc(P, r + stride, b1, b2, lb, acc_b);
+    const double thr_a = __ldg(P.thr_tab + (la & 0xffff) + (la >> 16)), thr_b = __ldg(P.thr_tab + (lb & 0xffff) + (lb >> 16));
+    unsigned fa = 0, fb = 0;
+    const double ta = floored_log(acc_a, two_len, thr_a, fa), tb = floored_log(acc_b, two_len, thr_b, fb);
+    if (ok_a) { P.values[r] = acc_a; dd_add(sum, ta); floored += fa; }
+    if (ok_b) { P.values[r + stride] = acc_b; dd_add(sum, tb); floored += fb; }
   }
-  if (r < P.n_reads) paired_simple_read(P, r, __ldg(first1 + r), __ldg(first2 + r), __ldg(P.lens + r), sum, floored);
+  if (r < P.n_reads) {
+    const uint32_t ll = __ldg(P.lens + r);
+    double acc;
+    if (paired_simple_acc(P, r, __ldg(first1 + r), __ldg(first2 + r), ll, acc)) {
+      P.values[r] = acc;
+      dd_add(sum, floored_log(acc, two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    }
+  }
   block_reduce_store(sum, floored, P.partials, blockIdx.x);
 }
 
@@ -763,7 +790,30 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 }  // namespace
 
 // ---- launch wrappers ------------------------------------------------------------------------
-int score_grid(int n_reads, int sm_count) { return grid_for((size_t)n_reads, kBlock, sm_count, 8); }
+// Grids are sized to exactly one resident wave (SM count x blocks that fit per SM for that kernel) so the
+// grid-stride loops have no partial second wave.
+template <class K>
+int resident_blocks(K kernel, int block) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
+int score_grid(int which, int n_items, int sm_count) {
+  static int per_sm[6] = {0, 0, 0, 0, 0, 0};
+  if (which < 0 || which > 5) which = 0;
+  if (per_sm[which] == 0) {
+    switch (which) {
+      case kGridPairedFull: per_sm[which] = resident_blocks(paired_full_kernel, kBlock); break;
+      case kGridPairedComplex: per_sm[which] = resident_blocks(paired_complex_kernel, kBlock); break;
+      case kGridPairedTotal: per_sm[which] = resident_blocks(paired_total_kernel, kBlock); break;
+      case kGridSingleFull: per_sm[which] = resident_blocks(single_full_kernel, kBlock); break;
+      case kGridSingleComplex: per_sm[which] = resident_blocks(single_complex_kernel, kBlock); break;
+      default: per_sm[which] = resident_blocks(pacbio_full_kernel, kBlock); break;
+    }
+  }
+  return grid_for((size_t)n_items, kBlock, sm_count, per_sm[which]);
+}
 int overflow_grid(int sm_count) { return sm_count; }
 
 void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st) {

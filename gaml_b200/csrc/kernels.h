@@ -6,7 +6,8 @@
 
 namespace gaml {
 
-int score_grid(int n_reads, int sm_count);
+enum { kGridPairedFull = 0, kGridPairedComplex, kGridPairedTotal, kGridSingleFull, kGridSingleComplex, kGridPacbioFull };
+int score_grid(int which, int n_items, int sm_count);
 int overflow_grid(int sm_count);
 
 void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st);

@@ -31,4 +31,23 @@ g++ "${FLAGS[@]}" -c "$HERE/ref_harness.cc" -o ref_harness.o &
 wait
 g++ -o gaml_ref gaml.o graph.o moves.o input_output.o graph_from_assembly.o 2>/dev/null
 g++ -o ref_harness ref_harness.o graph.o
+# gaml_gpu: the reference's OWN gaml.cc / moves.cc (annealing loop + moves, unchanged) compiled against the
+# drop-in integration/prob_calculator.h and linked with the CUDA library. -Dprivate=public lets the adapter
+# read ReadSet::aligment_cache_; graph.o etc. are the reference objects built above.
+LIBDIR="$HERE/../gaml_b200"
+if [ -f "$LIBDIR/libgaml_b200.so" ]; then
+  GFLAGS=(-std=c++11 -O2 -w -Dprivate=public
+          -DBOOST_SERIALIZATION_UNORDERED_MAP_HPP -DBOOST_SERIALIZATION_UNORDERED_SET_HPP
+          -include unordered_map -include unordered_set -include "$HERE/../integration/prob_calculator.h"
+          -I"$HERE/../include" -I"$HERE/boost_shim" -I"$REF")
+  # (quote-includes search the including file's own directory first, so the reference's prob_calculator.h would
+  #  win over any -I; force-including the adapter first defines the shared include guard PROB_CALCULATOR_H__
+  #  and turns the reference header into a no-op.)
+  g++ "${GFLAGS[@]}" -c "$REF/gaml.cc" -o gaml_gpu.o &
+  g++ "${GFLAGS[@]}" -c "$REF/moves.cc" -o moves_gpu.o &
+  wait
+  g++ -o gaml_gpu gaml_gpu.o moves_gpu.o graph.o input_output.o graph_from_assembly.o \
+      -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200' 2>/dev/null
+  echo "build_ref: built $OUT/gaml_gpu (reference annealing loop + moves over the CUDA ProbCalculator)"
+fi
 echo "build_ref: built $OUT/gaml_ref and $OUT/ref_harness"

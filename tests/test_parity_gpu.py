@@ -206,3 +206,17 @@ def test_cpp_host_mirror_runs():
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "PASS" in out.stdout
+
+
+def test_reference_annealing_driver_over_cuda_is_identical(tmp_path):
+    """The reference's OWN gaml.cc Optimize loop + moves.cc, compiled unchanged against
+    integration/prob_calculator.h (oracle/_ref/gaml_gpu, prebuilt where /root/reference exists), must follow
+    exactly the trajectory of the pure reference binary: same proposals, same accept/reject decisions."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "gaml_ref")
+    gpu = os.path.join(ROOT, "oracle", "_ref", "gaml_gpu")
+    if not (os.path.exists(ref) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref/gaml_ref + gaml_gpu not prebuilt")
+    out = subprocess.run(["bash", os.path.join(ROOT, "tools", "run_e2e.sh"), str(tmp_path), "200"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("IDENTICAL TRAJECTORY") == 2, out.stdout

@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# End-to-end drop-in check on a GPU box: the reference's OWN annealing driver and moves (gaml.cc, moves.cc,
+# compiled unchanged) once over the reference ProbCalculator (gaml_ref) and once over the CUDA one (gaml_gpu),
+# same synthetic LastGraph + FASTQ input, same seeds. Traces must be identical; wall times give SA it/s.
+set -uo pipefail
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+OUT=${1:-$ROOT/gpurun_out/e2e}
+ITERS=${2:-500}
+mkdir -p "$OUT"
+rc=0
+for kind in single paired; do
+  D=/tmp/e2e_$kind
+  rm -rf "$D"
+  python "$ROOT/tools/make_e2e_dataset.py" "$D" --kind $kind --n-reads 50000 --iterations "$ITERS" > "$OUT/$kind.gen.log"
+  t0=$(date +%s.%N)
+  ( cd "$D" && stdbuf -oL "$ROOT/oracle/_ref/gaml_ref" gaml.cfg > ref.log 2>&1 )
+  t1=$(date +%s.%N)
+  ( cd "$D" && stdbuf -oL "$ROOT/oracle/_ref/gaml_gpu" gaml.cfg > gpu.log 2>&1 ) || { echo "gaml_gpu failed ($kind)"; tail -5 "$D/gpu.log"; rc=1; }
+  t2=$(date +%s.%N)
+  python -c "print('%.2f' % ($t1 - $t0))" > "$D/ref.time"; python -c "print('%.2f' % ($t2 - $t1))" > "$D/gpu.time"
+  python "$ROOT/tools/compare_traces.py" "$D/ref.log" "$D/gpu.log" | tee "$OUT/$kind.compare.txt" || rc=1
+  echo "$kind: reference $(cat $D/ref.time)s, cuda $(cat $D/gpu.time)s for $ITERS iterations (wall, includes the one-off CPU alignment of new keys)" | tee -a "$OUT/$kind.compare.txt"
+  grep -c "^itnum" "$D/gpu.log" > /dev/null
+  cp "$D/ref.log" "$OUT/$kind.ref.log"; cp "$D/gpu.log" "$OUT/$kind.gpu.log"
+done
+exit $rc
