@@ -303,9 +303,11 @@ def main():
         st = pc.stats()
         return st.last_device_ms, st.last_score_kernel_ms, part, tl
 
+    flat0 = api.flatten_walks(walks0)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
+
     def full_step_e2e():
         pc.reset_state()
-        part, tl = pc.calc_prob_partial(walks0)
+        part, tl = pc.calc_prob_partial_flat(*flat0)
         g = allgather_partials(part, dev) if world > 1 else part[None, :]
         return pc.combine(g, g.shape[0], tl)
 
@@ -345,11 +347,12 @@ def main():
     pc.reset_state()
     full_step_e2e()
     seq = wl.evals[1:1 + args.delta_steps]
+    seq_flat = [api.flatten_walks(w) for w in seq]
     barrier()
     t0 = time.perf_counter()
     delta_dev_ms, touched = 0.0, 0
-    for walks in seq:
-        part, tl = pc.calc_prob_partial(walks)
+    for nodes_offs in seq_flat:
+        part, tl = pc.calc_prob_partial_flat(*nodes_offs)
         if world > 1:
             allgather_partials(part, dev)
         s2 = pc.stats()
@@ -375,8 +378,8 @@ def main():
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps},
         "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "note": "gaml_calc_prob_partial (+ all-gather at N>1) with host walks in / host partials out; the alignment "
-                        "cache is resident state like the reference's aligment_cache_"},
+                "note": "gaml_calc_prob_partial (+ all-gather at N>1): host walk arrays in, host partials out, wall clock; "
+                        "the alignment cache is resident state like the reference's aligment_cache_"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "sa_iters_per_s": len(seq) / delta_s,

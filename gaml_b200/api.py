@@ -8,6 +8,7 @@ outputs. The library has no CPU fallback; creating a context without a B200 rais
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -19,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgaml_b200.so")
 
 INT32_MIN = -(2 ** 31)
+PARTIAL_DOUBLES = 5   # GAML_PARTIAL_DOUBLES
 
 
 class GamlError(RuntimeError):
@@ -102,12 +104,12 @@ def _p32(a: np.ndarray):
 
 
 def flatten_walks(walks: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    """vector<vector<int>> -> (concatenated node ids, n_walks+1 offsets), the C ABI's walk layout."""
     offs = np.zeros(len(walks) + 1, dtype=np.int64)
-    for i, w in enumerate(walks):
-        offs[i + 1] = offs[i] + len(w)
-    nodes = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
-    for i, w in enumerate(walks):
-        nodes[offs[i]:offs[i + 1]] = w
+    if len(walks):
+        np.cumsum(np.fromiter(map(len, walks), dtype=np.int64, count=len(walks)), out=offs[1:])
+    total = int(offs[-1])
+    nodes = np.fromiter(itertools.chain.from_iterable(walks), dtype=np.int32, count=total) if total else np.zeros(1, np.int32)
     return nodes, offs
 
 
@@ -213,9 +215,18 @@ class ProbCalculator:
         z = [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(self.sets))]
         return res.prob, z, res.total_len
 
+    def calc_prob_partial_flat(self, nodes: np.ndarray, offs: np.ndarray):
+        """gaml_calc_prob_partial on walks already in the C ABI's layout (what a C++ caller passes)."""
+        part = np.zeros(PARTIAL_DOUBLES * max(len(self.sets), 1), dtype=np.float64)
+        tl = C.c_int32()
+        self._check(self.lib.gaml_calc_prob_partial(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    len(offs) - 1, part.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    C.byref(tl)))
+        return part, tl.value
+
     def calc_prob_partial(self, paths: Sequence[Sequence[int]]):
         nodes, offs = flatten_walks(paths)
-        part = np.zeros(3 * max(len(self.sets), 1), dtype=np.float64)
+        part = np.zeros(PARTIAL_DOUBLES * max(len(self.sets), 1), dtype=np.float64)
         tl = C.c_int32()
         self._check(self.lib.gaml_calc_prob_partial(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
                                                     len(paths), part.ctypes.data_as(C.POINTER(C.c_double)),
@@ -240,7 +251,7 @@ class ProbCalculator:
         self._check(self.lib.gaml_eval_launch(self.h))
 
     def finish(self):
-        part = np.zeros(3 * max(len(self.sets), 1), dtype=np.float64)
+        part = np.zeros(PARTIAL_DOUBLES * max(len(self.sets), 1), dtype=np.float64)
         tl = C.c_int32()
         self._check(self.lib.gaml_eval_finish(self.h, part.ctypes.data_as(C.POINTER(C.c_double)), C.byref(tl)))
         return part, tl.value
@@ -262,9 +273,9 @@ class ProbCalculator:
 
 def combine_partials_raw(gathered: np.ndarray, kinds: Sequence[int], n_reads_total: Sequence[int],
                          weights: Sequence[float], total_len: int):
-    """Context-free combine of all-gathered shard partials ([n_shards, n_sets, 3]) -> (prob, zeros, total_len)."""
+    """Context-free combine of all-gathered shard partials ([n_shards, n_sets, PARTIAL_DOUBLES]) -> (prob, zeros, total_len)."""
     lib = load_library()
-    g = np.ascontiguousarray(gathered, dtype=np.float64).reshape(-1, len(kinds), 3)
+    g = np.ascontiguousarray(gathered, dtype=np.float64).reshape(-1, len(kinds), PARTIAL_DOUBLES)
     k = _i32(kinds)
     n = np.ascontiguousarray(n_reads_total, dtype=np.int64)
     w = np.ascontiguousarray(weights, dtype=np.float64)

@@ -15,16 +15,22 @@ struct Occ {
   int32_t skip_below;  // records with position+cur_pos below this are skipped (max_pos-5, graph.cc:577)
 };
 
-// Device-resident table indexed by key id. A slot is live iff epoch == the evaluation's epoch, so an
-// evaluation only writes the slots of the keys it touches. The first occurrence is inline.
-struct KeySlot {
-  uint32_t epoch;
-  int32_t n_occ;
-  int32_t occ_begin;   // into the evaluation's Occ array (all n_occ occurrences, first included)
-  int32_t pad;
-  Occ first;
+// Device-resident tables indexed by key id, two 16-byte words per key in two arrays. A key is live iff the epoch in
+// word A matches the evaluation's epoch, so an evaluation only writes the slots of the keys it touches. Word A is
+// all the streaming kernels need; word B (enumeration order, further occurrences) is read by the general paths.
+struct SlotA {
+  uint32_t epoch_flag;  // epoch (31 bits) | (n_occ > 1) << 31
+  int32_t walk;         // first occurrence: walk ordinal
+  int32_t cur_pos;
+  int32_t skip_below;
 };
-static_assert(sizeof(KeySlot) == 32, "KeySlot is two 128-bit words");
+struct SlotB {
+  int32_t seg;          // first occurrence: enumeration index
+  int32_t n_occ;
+  int32_t occ_begin;    // into the evaluation's Occ array (all n_occ occurrences, first included)
+  int32_t pad;
+};
+static_assert(sizeof(SlotA) == 16 && sizeof(SlotB) == 16, "slot words are 128-bit");
 
 struct SlotUpdate {    // host -> device, scattered into KeySlot[key] by apply_slots_kernel
   int32_t key;
@@ -58,7 +64,9 @@ struct PlcLong {
 
 struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one touched mate-1 key
 
-constexpr int kPartialStride = 4;   // per block: sum_hi, sum_lo, floored, spare
+constexpr int kAccumStride = 8;   // per set, u64: four 32-bit limbs of the exact 128-bit sum, floored, -inf terms, nan terms, spare
+constexpr int kOutStride = 6;     // per set, f64: integer part, 2^-40 units, floored, -inf terms, nan terms, flags
+struct Double2 { double x, y; };  // {1/c, -log(1/c)} entries of the log table
 
 struct MateView {
   const void* first;         // short stores: dense int4 per read {key, pos, edor | count<<16, row offset}; key<0 = none
@@ -66,7 +74,9 @@ struct MateView {
   const uint32_t* rowptr;    // n_reads + 1
   const void* crows;         // compact copy of the rows of the tier-2 reads (list order), RowShort*
   const uint32_t* cptr;      // n_complex + 1 offsets into crows
-  const KeySlot* slots;
+  const SlotA* slots_a;
+  const SlotB* slots_b;
+  int32_t n_keys;
   const Occ* occ;
   const double* pow_match;   // match^k     (graph.cc:1451)
   const double* pow_mismatch;// mismatch^k  (graph.cc:1452)
@@ -96,8 +106,11 @@ struct ScoreParams {
   const uint32_t* complex_list;
   const uint32_t* clens;     // lens[] gathered in list order
   int32_t n_complex;
-  // reduction
-  double* partials;          // [n_partial_blocks][kPartialStride]
+  // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
+  unsigned long long* accum;
+  const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
+  double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)
+  double rcp_two_len;
   // delta discovery
   const ArenaShort* arena1;
   const TouchRange* touch;

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <limits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -88,7 +89,7 @@ struct MateStore {
   std::vector<KeyMeta> keys;
   std::vector<int4> pending;          // staged arena records (ArenaShort / ArenaLong bit patterns)
   size_t arena_n = 0;                 // records on the device
-  DevBuf arena, rows, first, rowptr, cursor, slots, crows, cptr;
+  DevBuf arena, rows, first, rowptr, cursor, slots_a, slots_b, crows, cptr;
   bool dirty = true;
   std::vector<double> pow_match, pow_mismatch;
   DevBuf d_pow_match, d_pow_mismatch;
@@ -113,9 +114,10 @@ struct ReadSetState {
   std::vector<Walk> old_walks;
   bool has_state = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this set's streaming kernel(s)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // side-stream fork/join for the tier-2 kernel
   ~ReadSetState() {
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t e : {ev0, ev1, ev_fork, ev_join})
+      if (e) cudaEventDestroy(e);
   }
 };
 
@@ -127,8 +129,6 @@ struct SetPlan {
   int64_t touch_records = 0;
   int grid = 0;                 // blocks of the reducing kernel
   int cgrid = 0;                // blocks of the tier-2 (several records per read) kernel
-  int n_partials = 0;
-  int partial_begin = 0;
   size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
   size_t touch_off = 0, prefix_off = 0;
   int n_touch = 0;
@@ -143,17 +143,18 @@ struct gaml_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // tier-2 kernels run here, forked/joined with events
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string error;
   std::vector<int32_t> node_len, nmap;
   std::vector<std::unique_ptr<ReadSetState>> sets;
   std::vector<MateStore*> stores;
-  DevBuf d_tables;                // KeySlot* per store
+  DevBuf d_tables;                // SlotA* per store, then SlotB* per store
   bool tables_dirty = true;
   DevBuf d_blob;                  // per-evaluation staging (updates, occurrences, touch ranges, set_begin)
   void* h_blob = nullptr;         // pinned
   size_t h_blob_cap = 0;
-  DevBuf d_partials, d_out, d_flags, d_scratch, d_csr_temp;
+  DevBuf d_out, d_flags, d_scratch, d_csr_temp, d_logtab;
   double* h_out = nullptr;        // pinned, 4 doubles per set
   size_t h_out_cap = 0;
   unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
@@ -164,8 +165,7 @@ struct gaml_ctx {
   std::vector<SetPlan> plan;
   std::vector<Walk> plan_walks;
   int n_updates = 0;
-  size_t upd_off = 0, setbegin_off = 0, blob_bytes = 0;
-  int n_partials_total = 0;
+  size_t upd_off = 0, blob_bytes = 0;
   gaml_stats stats{};
 };
 
@@ -185,6 +185,10 @@ int fail(gaml_ctx* ctx, int code, const std::string& msg) {
   ctx->error = msg;
   return code;
 }
+
+// d_flags layout (u64 words, zeroed at the start of every evaluation): [0] scratch cursor | [1] error flag (u32) |
+// [2, 2+n) per-set overflow counters (u32 in u64 slots) | then per set kAccumStride words of exact accumulators
+size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (1 + kAccumStride); }
 
 double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, same expression order
   double z = (d - mean) / sd;
@@ -400,9 +404,10 @@ int commit(gaml_ctx* ctx) {
       if (!st.is_long) CU(st.first.reserve(std::max<size_t>(rs.n_local, 1) * 16, 0, false, ctx->stream));
       CU(st.rowptr.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
       CU(st.cursor.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
-      const size_t old_slots = st.slots.cap;
-      CU(st.slots.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(KeySlot), 0, true, ctx->stream));
-      if (st.slots.cap != old_slots) ctx->tables_dirty = true;
+      const size_t old_slots = st.slots_a.cap;
+      CU(st.slots_a.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotA), 0, true, ctx->stream));
+      CU(st.slots_b.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotB), 0, true, ctx->stream));
+      if (st.slots_a.cap != old_slots) ctx->tables_dirty = true;
       const size_t temp = csr_temp_bytes(rs.n_local);
       CU(ctx->d_csr_temp.reserve(std::max<size_t>(temp, 256), 0, false, ctx->stream));
       int launches = 0;
@@ -417,13 +422,12 @@ int commit(gaml_ctx* ctx) {
       CU(rs.d_complex.reserve(std::max<size_t>(rs.n_local, 1) * 4, 0, false, ctx->stream));
       uint32_t* flags = rs.mate[0].cursor.as<uint32_t>();   // scratch, free after build_csr
       int launches = 0;
+      uint32_t n_complex = 0;
       CU(build_complex_list(rs.mate[0].first.p, rs.n_mates == 2 ? rs.mate[1].first.p : nullptr, rs.n_local, flags,
-                            rs.d_complex.as<uint32_t>(), ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->stream, &launches));
+                            rs.d_complex.as<uint32_t>(), ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->stream, &launches,
+                            &n_complex));
       ctx->stats.kernel_launches += launches;
       launches = 0;
-      uint32_t n_complex = 0;
-      CU(cudaMemcpyAsync(&n_complex, flags + rs.n_local, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
       rs.n_complex = (int)n_complex;
       // compact copy of the listed reads' rows, per mate, + their packed lengths
       CU(rs.d_clens.reserve(std::max<size_t>(n_complex, 1) * 4, 0, false, ctx->stream));
@@ -445,11 +449,12 @@ int commit(gaml_ctx* ctx) {
     }
   }
   if (ctx->tables_dirty) {
-    std::vector<KeySlot*> tabs;
-    for (MateStore* s : ctx->stores) tabs.push_back(s->slots.as<KeySlot>());
-    CU(ctx->d_tables.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(KeySlot*), 0, false, ctx->stream));
+    std::vector<void*> tabs;   // [SlotA* per store][SlotB* per store]
+    for (MateStore* s : ctx->stores) tabs.push_back(s->slots_a.p);
+    for (MateStore* s : ctx->stores) tabs.push_back(s->slots_b.p);
+    CU(ctx->d_tables.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(void*), 0, false, ctx->stream));
     if (!tabs.empty())
-      CU(cudaMemcpyAsync(ctx->d_tables.p, tabs.data(), tabs.size() * sizeof(KeySlot*), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_tables.p, tabs.data(), tabs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ctx->tables_dirty = false;
   }
   CU(cudaStreamSynchronize(ctx->stream));
@@ -468,14 +473,13 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
   ctx->epoch++;
-  if (ctx->epoch == 0) return fail(ctx, GAML_ERR_STATE, "epoch counter wrapped");
+  if (ctx->epoch >= 0x7fffffffu) return fail(ctx, GAML_ERR_STATE, "epoch counter exhausted (2^31 evaluations): recreate the context");
 
   const size_t n_sets = ctx->sets.size();
   ctx->plan.assign(n_sets, SetPlan());
   std::vector<SlotUpdate> updates;
   std::vector<std::vector<Occ>> occs(ctx->stores.size());
   std::vector<std::vector<TouchRange>> touches(n_sets);
-  int partial_cursor = 0;
 
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
@@ -511,7 +515,6 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
       sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(kGridPairedComplex, rs.n_complex, ctx->sm_count) : 0;
-      sp.n_partials = sp.grid + (sp.full ? sp.cgrid + overflow_grid(ctx->sm_count) : 0);
     } else {
       OccBuilder ob;
       sp.full = true;
@@ -520,12 +523,8 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
       sp.grid = score_grid(rs.cfg.kind == GAML_KIND_SINGLE ? kGridSingleFull : kGridPacbioFull, rs.n_local, ctx->sm_count);
       sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
-      sp.n_partials = sp.grid + sp.cgrid + overflow_grid(ctx->sm_count);
     }
-    sp.partial_begin = partial_cursor;
-    partial_cursor += sp.n_partials;
   }
-  ctx->n_partials_total = partial_cursor;
 
   // ---- pack the staging blob: [updates][occ per store][touch + prefix per set][set_begin] -----
   auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -546,8 +545,6 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     sp.prefix_off = off;
     off = align16(off + (touches[s].size() + 1) * sizeof(uint32_t));
   }
-  ctx->setbegin_off = off;
-  off = align16(off + (n_sets + 1) * sizeof(int));
   ctx->blob_bytes = off;
   rc = ensure_pinned(ctx, off);
   if (rc != GAML_OK) return rc;
@@ -567,21 +564,17 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     if (acc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one evaluation");
     pre[touches[s].size()] = (uint32_t)acc;
   }
-  int* sb = reinterpret_cast<int*>(hb + ctx->setbegin_off);
-  for (size_t s = 0; s < n_sets; s++) sb[s] = ctx->plan[s].partial_begin;
-  sb[n_sets] = partial_cursor;
   ctx->n_updates = (int)updates.size();
 
   CU(ctx->d_blob.reserve(std::max<size_t>(off, 256), 0, false, ctx->stream));
-  CU(ctx->d_partials.reserve(std::max<size_t>((size_t)partial_cursor, 1) * kPartialStride * sizeof(double), 0, false, ctx->stream));
-  CU(ctx->d_out.reserve(std::max<size_t>(n_sets, 1) * 4 * sizeof(double), 0, false, ctx->stream));
-  CU(ctx->d_flags.reserve((2 + 2 * std::max<size_t>(n_sets, 1)) * sizeof(unsigned long long), 0, true, ctx->stream));
+  CU(ctx->d_out.reserve(std::max<size_t>(n_sets, 1) * kOutStride * sizeof(double), 0, false, ctx->stream));
+  CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, ctx->stream));
   CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
-  if (ctx->h_out_cap < n_sets * 4 + 4) {
+  if (ctx->h_out_cap < n_sets * kOutStride + kOutStride) {
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     ctx->h_out = nullptr;
-    CU(cudaMallocHost(&ctx->h_out, (n_sets * 4 + 4) * sizeof(double)));
-    ctx->h_out_cap = n_sets * 4 + 4;
+    CU(cudaMallocHost(&ctx->h_out, (n_sets * kOutStride + kOutStride) * sizeof(double)));
+    ctx->h_out_cap = n_sets * kOutStride + kOutStride;
   }
   CU(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.last_h2d_bytes = (int64_t)off;
@@ -591,7 +584,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   return GAML_OK;
 }
 
-// d_flags layout: [0] scratch cursor (u64) | [1] error flag (u32) | then per set one u32 overflow counter (in u64 slots)
+
 ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   ReadSetState& rs = *ctx->sets[s];
   const SetPlan& sp = ctx->plan[s];
@@ -604,7 +597,9 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
     P.m[m].rowptr = st.rowptr.as<uint32_t>();
     P.m[m].crows = st.crows.p;
     P.m[m].cptr = st.cptr.as<uint32_t>();
-    P.m[m].slots = st.slots.as<KeySlot>();
+    P.m[m].slots_a = st.slots_a.as<SlotA>();
+    P.m[m].slots_b = st.slots_b.as<SlotB>();
+    P.m[m].n_keys = (int)st.keys.size();
     P.m[m].occ = reinterpret_cast<const Occ*>(blob + sp.occ_off[m]);
     P.m[m].pow_match = st.d_pow_match.as<double>();
     P.m[m].pow_mismatch = st.d_pow_mismatch.as<double>();
@@ -632,7 +627,10 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.complex_list = rs.d_complex.as<uint32_t>();
   P.clens = rs.d_clens.as<uint32_t>();
   P.n_complex = rs.n_complex;
-  P.partials = ctx->d_partials.as<double>() + (size_t)sp.partial_begin * kPartialStride;
+  P.accum = fl + 2 + std::max<size_t>(ctx->sets.size(), 1) + s * kAccumStride;
+  P.log_tab = ctx->d_logtab.p;
+  P.two_len_d = (double)P.two_len;
+  P.rcp_two_len = 1.0 / P.two_len_d;
   P.arena1 = rs.mate[0].arena.as<ArenaShort>();
   P.touch = reinterpret_cast<const TouchRange*>(blob + sp.touch_off);
   P.touch_prefix = reinterpret_cast<const uint32_t*>(blob + sp.prefix_off);
@@ -646,12 +644,12 @@ int launch(gaml_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   const size_t n_sets = ctx->sets.size();
   CU(cudaEventRecord(ctx->ev[0], st));
-  CU(cudaMemsetAsync(ctx->d_flags.p, 0, (2 + 2 * std::max<size_t>(n_sets, 1)) * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(ctx->d_flags.p, 0, flags_words(n_sets) * sizeof(unsigned long long), st));
   char* blob = ctx->d_blob.as<char>();
   int launches = 0;
   if (ctx->n_updates > 0) {
     launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates,
-                       ctx->d_tables.as<KeySlot*>(), ctx->epoch, st);
+                       ctx->d_tables.as<SlotA*>(), ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, st);
     launches++;
   }
   CU(cudaEventRecord(ctx->ev[1], st));
@@ -666,7 +664,7 @@ int launch(gaml_ctx* ctx) {
     reads += rs.n_local;
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
-        launch_paired_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1);
+        launch_paired_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
         launches += 2 + (sp.cgrid > 0);
         any_full = true;
         // 16 B per live record + packed lengths (4) + probs write (8) per pair (no probs read: fused)
@@ -678,7 +676,7 @@ int launch(gaml_ctx* ctx) {
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       }
     } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
-      launch_single_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1);
+      launch_single_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
       launches += 2 + (sp.cgrid > 0);
       bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
     } else {
@@ -690,9 +688,8 @@ int launch(gaml_ctx* ctx) {
   CU(cudaEventRecord(ctx->ev[2], st));
   if (n_sets > 0) {
     unsigned long long* fl = ctx->d_flags.as<unsigned long long>();
-    launch_finalize(ctx->d_partials.as<double>(), reinterpret_cast<const int*>(blob + ctx->setbegin_off), (int)n_sets,
-                    ctx->d_out.as<double>(), reinterpret_cast<const uint32_t*>(fl + 1),
-                    reinterpret_cast<const uint32_t*>(fl + 2), st);
+    launch_finalize(fl + 2 + std::max<size_t>(n_sets, 1), (int)n_sets, ctx->d_out.as<double>(),
+                    reinterpret_cast<const uint32_t*>(fl + 1), reinterpret_cast<const uint32_t*>(fl + 2), st);
     launches++;
   }
   CU(cudaEventRecord(ctx->ev[3], st));
@@ -709,9 +706,9 @@ int launch(gaml_ctx* ctx) {
 int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
   const size_t n_sets = ctx->sets.size();
-  if (n_sets > 0) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out.p, n_sets * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_sets > 0) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out.p, n_sets * kOutStride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.last_d2h_bytes = (int64_t)(n_sets * 4 * sizeof(double));
+  ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kOutStride * sizeof(double));
   float ms = 0, ms2 = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
   for (auto& rs : ctx->sets) {
@@ -726,13 +723,10 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   uint32_t flags = 0, ovf = 0;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
-    const double* o = ctx->h_out + s * 4;
-    if (partials) {
-      partials[s * GAML_PARTIAL_DOUBLES + 0] = o[0];
-      partials[s * GAML_PARTIAL_DOUBLES + 1] = o[1];
-      partials[s * GAML_PARTIAL_DOUBLES + 2] = o[2];
-    }
-    const uint64_t f = (uint64_t)o[3];
+    const double* o = ctx->h_out + s * kOutStride;
+    if (partials)
+      for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) partials[s * GAML_PARTIAL_DOUBLES + k] = o[k];
+    const uint64_t f = (uint64_t)o[5];
     flags |= (uint32_t)(f & 15);
     ovf += (uint32_t)(f >> 4);
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
@@ -757,18 +751,21 @@ int combine_raw(const double* gathered, int n_shards, int n_sets, const int32_t*
     return GAML_ERR_ARG;
   std::vector<double> score(n_sets);
   for (int s = 0; s < n_sets; s++) {
-    // shard totals arrive as (hi, lo) pairs; add them in rank order with an error-free transformation
-    double hi = 0, lo = 0, fl = 0;
+    // shard totals are exact integers in units of 2^-40 (integer part, fraction units): add them exactly
+    __int128 ip = 0, fr = 0;
+    double fl = 0, neginf = 0, nan = 0;
     for (int k = 0; k < n_shards; k++) {
       const double* p = gathered + ((size_t)k * n_sets + s) * GAML_PARTIAL_DOUBLES;
-      double sum = hi + p[0];
-      double bb = sum - hi;
-      double err = (hi - (sum - bb)) + (p[0] - bb);
-      hi = sum;
-      lo += err + p[1];
+      ip += (__int128)(long long)p[0];
+      fr += (__int128)(long long)p[1];
       fl += p[2];
+      neginf += p[3];
+      nan += p[4];
     }
-    const double total = hi + lo;
+    const __int128 x = ip * ((__int128)1 << 40) + fr;
+    double total = (double)x * (1.0 / 1099511627776.0);   // one rounding: int128 -> double, then an exact scaling
+    if (nan > 0) total = std::numeric_limits<double>::quiet_NaN();
+    else if (neginf > 0) total = -std::numeric_limits<double>::infinity();
     double sc = total / (double)n_reads_total[s];   // total_prob / total_c, graph.cc:1515, 1536, 3087
     if (kinds[s] == GAML_KIND_PACBIO) {
       const int tl = total_len == 0 ? 1 : total_len;
@@ -841,12 +838,34 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
     return GAML_ERR_CUDA;
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  {
+    // log table for table_log (kernels.cu): interval i of z in [0.6875, 1.375) -> {invc = RN(1/centre), -log(invc)}
+    // with the logarithm of the ROUNDED reciprocal taken in long double, so log z = log1p(z*invc - 1) + logc exactly.
+    std::vector<double> tab(256);
+    for (int i = 0; i < 128; i++) {
+      const uint64_t lo = 0x3fe6000000000000ull + ((uint64_t)i << 45), hi = lo + ((uint64_t)1 << 45);
+      double zlo, zhi;
+      memcpy(&zlo, &lo, 8);
+      memcpy(&zhi, &hi, 8);
+      const double invc = (double)(2.0L / ((long double)zlo + (long double)zhi));
+      tab[2 * i] = invc;
+      tab[2 * i + 1] = (double)(-logl((long double)invc));
+    }
+    if (ctx->d_logtab.reserve(tab.size() * 8, 0, false, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(ctx->d_logtab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      g_create_error = "cannot upload the log table";
+      gaml_ctx_destroy(ctx);
+      return GAML_ERR_CUDA;
+    }
+  }
   *out = ctx;
   return GAML_OK;
 }
@@ -860,8 +879,9 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->stream, st2 = ctx->side_stream;
   delete ctx;
+  if (st2) cudaStreamDestroy(st2);
   if (st) cudaStreamDestroy(st);
 }
 
@@ -972,6 +992,8 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaEventCreateWithFlags(&rs.ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&rs.ev_join, cudaEventDisableTiming));
   CU(cudaEventCreate(&rs.ev0));
   CU(cudaEventCreate(&rs.ev1));
   for (int m = 0; m < rs.n_mates; m++) {

@@ -28,60 +28,126 @@ __device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_c
 
 __device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 
-// double-double accumulation (error-free TwoSum) so the shard total does not depend on grouping.
-struct DD { double hi, lo; };
-__device__ __forceinline__ void dd_add(DD& a, double b) {
-  double s = __dadd_rn(a.hi, b);
-  double bb = __dsub_rn(s, a.hi);
-  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b, bb));
-  a.hi = s;
-  a.lo = __dadd_rn(a.lo, e);
-}
-__device__ __forceinline__ void dd_merge(DD& a, const DD& b) {
-  dd_add(a, b.hi);
-  a.lo = __dadd_rn(a.lo, b.lo);
+// ---- exact accumulation of the per-read log terms -----------------------------------------------
+// Every term is rounded ONCE to a multiple of 2^-40 and added as a 128-bit integer, so the shard total is an
+// exact integer sum: associative, hence identical for any grid size, block order, shard count or collective
+// order. 2^-40 is 6e-15 relative on a typical term of -150; the rounding errors of 2 M terms
+// random-walk to ~1e-9 absolute on a total of ~3e8. Non-finite terms (log 0 = -inf, NaN) are counted instead.
+constexpr double kFixScale = 1099511627776.0;   // 2^40
+constexpr double kFixLimit = 4194304.0;         // |term| < 2^22 so that term * 2^40 fits an int64
+
+struct Acc {
+  unsigned long long lo;
+  long long hi;
+  unsigned neginf, bad;
+};
+__device__ __forceinline__ Acc acc_zero() { return Acc{0ull, 0ll, 0u, 0u}; }
+__device__ __forceinline__ void acc_add(Acc& a, double t) {
+  if (fabs(t) < kFixLimit) {
+    const long long q = __double2ll_rn(t * kFixScale);
+    const unsigned long long nlo = a.lo + (unsigned long long)q;
+    a.hi += (q >> 63) + (long long)(nlo < (unsigned long long)q);
+    a.lo = nlo;
+  } else if (t == -INFINITY) {
+    a.neginf++;
+  } else {
+    a.bad++;
+  }
 }
 
-// Block reduction of (dd sum, floored count) -> partials[slot]; warp shuffles then one smem hop.
-// Fixed shape, so the result is a pure function of the inputs (run-to-run deterministic).
-__device__ void block_reduce_store(DD acc, unsigned floored, double* partials, int slot) {
-  __shared__ double s_hi[kBlock / 32], s_lo[kBlock / 32];
-  __shared__ unsigned s_fl[kBlock / 32];
+// Block-wide exact sum -> per-set global accumulators {limb0..3 (32-bit limbs in u64), floored, neginf, bad}.
+// Warp level: the 128-bit value is cut into eight 16-bit chunks, each summed over the warp by one redux.sync
+// (sum < 2^21), lane 0 re-assembles modulo 2^128 (two's complement, so negatives just work); block level:
+// 32-bit limbs through shared-memory u64 atomics; grid level: one set of global u64 atomics per block.
+// Integer addition commutes, so the atomics do not make the result order dependent.
+__device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long long* accum) {
+  __shared__ unsigned long long sm[7];
+  if (threadIdx.x < 7) sm[threadIdx.x] = 0ull;
+  __syncthreads();
+  const unsigned w[4] = {(unsigned)a.lo, (unsigned)(a.lo >> 32), (unsigned)(unsigned long long)a.hi,
+                         (unsigned)((unsigned long long)a.hi >> 32)};
+  unsigned s[8];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    DD o;
-    o.hi = __shfl_down_sync(0xffffffffu, acc.hi, off);
-    o.lo = __shfl_down_sync(0xffffffffu, acc.lo, off);
-    dd_merge(acc, o);
-    floored += __shfl_down_sync(0xffffffffu, floored, off);
+  for (int j = 0; j < 4; j++) {
+    s[2 * j] = __reduce_add_sync(0xffffffffu, w[j] & 0xffffu);
+    s[2 * j + 1] = __reduce_add_sync(0xffffffffu, w[j] >> 16);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_hi[warp] = acc.hi; s_lo[warp] = acc.lo; s_fl[warp] = floored; }
+  const unsigned fl = __reduce_add_sync(0xffffffffu, floored);
+  const unsigned ni = __reduce_add_sync(0xffffffffu, a.neginf);
+  const unsigned bd = __reduce_add_sync(0xffffffffu, a.bad);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned __int128 x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) x += (unsigned __int128)s[j] << (16 * j);
+#pragma unroll
+    for (int j = 0; j < 4; j++) atomicAdd(&sm[j], (unsigned long long)(unsigned)(x >> (32 * j)));
+    if (fl) atomicAdd(&sm[4], (unsigned long long)fl);
+    if (ni) atomicAdd(&sm[5], (unsigned long long)ni);
+    if (bd) atomicAdd(&sm[6], (unsigned long long)bd);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    DD t{0.0, 0.0};
-    unsigned f = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-      dd_merge(t, DD{s_hi[w], s_lo[w]});
-      f += s_fl[w];
+    unsigned __int128 x = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) x += (unsigned __int128)sm[j] << (32 * j);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned long long limb = (unsigned long long)(unsigned)(x >> (32 * j));
+      if (limb) atomicAdd(accum + j, limb);
     }
-    double* p = partials + (size_t)slot * kPartialStride;
-    p[0] = t.hi;
-    p[1] = t.lo;
-    p[2] = (double)f;
-    p[3] = 0.0;
+    if (sm[4]) atomicAdd(accum + 4, sm[4]);
+    if (sm[5]) atomicAdd(accum + 5, sm[5]);
+    if (sm[6]) atomicAdd(accum + 6, sm[6]);
   }
+}
+
+// ---- log and division ------------------------------------------------------------------------------
+// log(v) for positive normal finite v from a 128-entry table {1/c, -log(1/c)} (host-built in long double,
+// engine.cu): v = 2^k z, z in [0.6875, 1.375); r = z*invc - 1 (one fma, |r| < 2^-7); log v = k ln2 + logc + log1p(r)
+// with a degree-7 Taylor polynomial (truncation < 2e-19). About 1 ulp; everything else falls back to log().
+__device__ __forceinline__ double table_log(const double2* __restrict__ tab, double v) {
+  const long long ix = __double_as_longlong(v);
+  if ((unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) return log(v);   // 0, denormal, inf, nan, < 0
+  const long long tmp = ix - 0x3fe6000000000000ll;
+  const int i = (int)((tmp >> 45) & 127);
+  const long long k = tmp >> 52;
+  const double z = __longlong_as_double(ix - (tmp & 0xfff0000000000000ll));
+  const double2 e = tab[i];
+  const double r = fma(z, e.x, -1.0);
+  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(r, p, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, -0.5);
+  p = fma(r * r, p, r);
+  return fma((double)k, 0.693147180559945309417232121458, e.y) + p;
+}
+
+// max(p / (2 total_len), thr), its log, and the floored flag: GetTotalProb, graph.cc:1505-1512.
+// The quotient is formed by Markstein's correction (q = p*y; q' = q + (p - q d) y with y = RN(1/d), two fmas),
+// which is the correctly rounded p/d; as a belt-and-braces guard the comparison that decides `floored` falls
+// back to the IEEE division whenever the quotient is within 2^-48 of the threshold.
+__device__ __forceinline__ double floored_term(const ScoreParams& P, const double2* log_tab, double p, double thr,
+                                               unsigned& floored) {
+  double q = __dmul_rn(p, P.rcp_two_len);
+  q = fma(fma(-q, P.two_len_d, p), P.rcp_two_len, q);
+  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = __ddiv_rn(p, P.two_len_d);
+  if (q < thr) { floored++; q = thr; }
+  return table_log(log_tab, q);
+}
+__device__ __forceinline__ double floored_term(const ScoreParams& P, double p, double thr, unsigned& floored) {
+  return floored_term(P, static_cast<const double2*>(P.log_tab), p, thr, floored);
 }
 
 // ---- placement enumeration ----------------------------------------------------------------
 // One live key occurrence applied to one record: F(occurrence int4 {walk, seg, cur_pos, skip_below}, row, row index).
 template <class F>
 __device__ __forceinline__ void visit_row(const MateView& mv, uint32_t epoch, const int4& rw, int idx, F&& f) {
-  const int4 hdr = ldg4(mv.slots + rw.x);
-  if ((uint32_t)hdr.x != epoch) return;
-  const int4 o0 = ldg4(reinterpret_cast<const int4*>(mv.slots + rw.x) + 1);
-  f(o0, rw, idx);
-  for (int t = 1; t < hdr.y; t++) f(ldg4(mv.occ + hdr.z + t), rw, idx);
+  const int4 a = ldg4(mv.slots_a + rw.x);                     // {epoch | multi<<31, walk, cur_pos, skip_below}
+  if (((uint32_t)a.x & 0x7fffffffu) != epoch) return;
+  const int4 b = ldg4(mv.slots_b + rw.x);                     // {seg, n_occ, occ_begin, -}
+  f(make_int4(a.y, b.x, a.z, a.w), rw, idx);
+  for (int t = 1; t < b.y; t++) f(ldg4(mv.occ + b.z + t), rw, idx);
 }
 
 // Short-read stores (hybrid layout): first[r] = {key, pos, edor | count<<16, row offset}; the read's
@@ -284,13 +350,6 @@ __device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int 
   return acc;
 }
 
-// log max(p/(2L), thr) and the floored flag: GetTotalProb, graph.cc:1505-1512.
-__device__ __forceinline__ double floored_log(double p, int two_len, double thr, unsigned& floored) {
-  double v = __ddiv_rn(p, (double)two_len);
-  if (v < thr) { floored++; v = thr; }
-  return log(v);
-}
-
 __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
   const uint32_t slot = atomicAdd(P.ovf_count, 1u);
   if (slot < P.ovf_cap) P.ovf_list[slot] = (uint32_t)r;
@@ -306,27 +365,28 @@ __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
 // several times in this evaluation (repeat node) sends the read to the scratch path.
 // Pair term of a tier-1 read (one record per mate). Every table access that does not depend on another table is
 // issued up front (both key slots, the four pow-table entries), so a read costs three memory round trips: the
-// coalesced first-records, the slot/pow batch (L1/L2 resident), the insert-pdf entry. Returns false when the
-// read is not tier 1's to score (tier-2 read, or a key with several occurrences -> scratch path).
-__device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, int r, const int4& rw1, const int4& rw2,
+// coalesced first-records, the slot/pow batch, the insert-pdf entry. sa1/sa2 are the packed 16-byte slot words
+// {epoch|multi<<31, walk, cur_pos, skip_below} (L1/L2 resident). Returns false when the read is not tier 1's to
+// score (tier-2 read, or a key with several occurrences -> scratch path).
+__device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const int4* __restrict__ sa1,
+                                                  const int4* __restrict__ sa2, int r, const int4& rw1, const int4& rw2,
                                                   uint32_t ll, double& acc) {
   acc = 0.0;
   if ((((rw1.z | rw2.z) >> 17) & 0x1fff) != 0) return false;   // count >= 2 on a mate: tier 2
   const int l1 = ll & 0xffff, l2 = ll >> 16;
-  const int k1 = max(rw1.x, 0), k2 = max(rw2.x, 0);            // key -1 (no record) reads slot 0 and is ignored below
-  const int4* s1 = reinterpret_cast<const int4*>(P.m[0].slots + k1);
-  const int4* s2 = reinterpret_cast<const int4*>(P.m[1].slots + k2);
-  const int4 h1 = __ldg(s1), o1 = __ldg(s1 + 1), h2 = __ldg(s2), o2 = __ldg(s2 + 1);
+  const int4 o1 = __ldg(sa1 + max(rw1.x, 0)), o2 = __ldg(sa2 + max(rw2.x, 0));   // key -1 (no record) reads slot 0, ignored below
   const int e1 = rw1.z & 0xffff, e2 = rw2.z & 0xffff;
   const double a1 = __ldg(P.m[0].pow_mismatch + e1), b1 = __ldg(P.m[0].pow_match + (l1 - e1));
   const double a2 = __ldg(P.m[1].pow_mismatch + e2), b2 = __ldg(P.m[1].pow_match + (l2 - e2));
-  if (rw1.x < 0 || rw2.x < 0 || (uint32_t)h1.x != P.epoch || (uint32_t)h2.x != P.epoch) return true;
-  if (h1.y > 1 || h2.y > 1) {
+  if (rw1.x < 0 || rw2.x < 0) return true;
+  const uint32_t f1 = (uint32_t)o1.x, f2 = (uint32_t)o2.x;
+  if ((f1 & 0x7fffffffu) != P.epoch || (f2 & 0x7fffffffu) != P.epoch) return true;
+  if ((f1 | f2) >> 31) {
     push_overflow(P, r);
     return false;
   }
   const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
-  if (p1 < o1.w || p2 < o2.w || o1.x != o2.x) return true;   // skip rule (graph.cc:577); pairs only inside one walk
+  if (p1 < o1.w || p2 < o2.w || o1.y != o2.y) return true;   // skip rule (graph.cc:577); pairs only inside one walk
   const int xo = (rw1.z >> 30) & 1, yo = (rw2.z >> 30) & 1;
   if (xo == yo) return true;                                   // graph.cc:1864
   int d;
@@ -339,48 +399,53 @@ __device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, int r, c
   }
   const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
   const double t = __dmul_rn(__dmul_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2)), ins);   // (p1*p2)*ins, graph.cc:1889
-  acc = (o1.x < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  acc = (o1.y < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
   return true;
 }
 
 __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P) {
-  DD sum{0.0, 0.0};
+  const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
+  const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
+  Acc sum = acc_zero();
   unsigned floored = 0;
   const int4* first1 = static_cast<const int4*>(P.m[0].first);
   const int4* first2 = static_cast<const int4*>(P.m[1].first);
   const int stride = gridDim.x * blockDim.x;
-  const int two_len = P.two_len;
+  const int n = P.n_reads;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   // Two reads per iteration: six independent coalesced loads in flight per thread before any use, and the two
   // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
-  for (; r + stride < P.n_reads; r += 2 * stride) {
+  // (Measured dead ends, profiles/r01_summary.md: register double-buffering of the next iteration's loads and
+  //  staging the slot words + log table in shared memory both cost registers/instructions and gained nothing.)
+  for (; r + stride < n; r += 2 * stride) {
     const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
     const int4 b1 = __ldg(first1 + r + stride), b2 = __ldg(first2 + r + stride);
     const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + stride);
     double acc_a, acc_b;
-    const bool ok_a = paired_simple_acc(P, r, a1, a2, la, acc_a);
-    const bool ok_b = paired_simple_acc(P, r + stride, b1, b2, lb, acc_b);
+    const bool ok_a = paired_simple_acc(P, sa1, sa2, r, a1, a2, la, acc_a);
+    const bool ok_b = paired_simple_acc(P, sa1, sa2, r + stride, b1, b2, lb, acc_b);
     const double thr_a = __ldg(P.thr_tab + (la & 0xffff) + (la >> 16)), thr_b = __ldg(P.thr_tab + (lb & 0xffff) + (lb >> 16));
     unsigned fa = 0, fb = 0;
-    const double ta = floored_log(acc_a, two_len, thr_a, fa), tb = floored_log(acc_b, two_len, thr_b, fb);
-    if (ok_a) { P.values[r] = acc_a; dd_add(sum, ta); floored += fa; }
-    if (ok_b) { P.values[r + stride] = acc_b; dd_add(sum, tb); floored += fb; }
+    const double ta = floored_term(P, log_tab, acc_a, thr_a, fa), tb = floored_term(P, log_tab, acc_b, thr_b, fb);
+    if (ok_a) { P.values[r] = acc_a; acc_add(sum, ta); floored += fa; }
+    if (ok_b) { P.values[r + stride] = acc_b; acc_add(sum, tb); floored += fb; }
   }
-  if (r < P.n_reads) {
+  if (r < n) {
     const uint32_t ll = __ldg(P.lens + r);
     double acc;
-    if (paired_simple_acc(P, r, __ldg(first1 + r), __ldg(first2 + r), ll, acc)) {
+    if (paired_simple_acc(P, sa1, sa2, r, __ldg(first1 + r), __ldg(first2 + r), ll, acc)) {
       P.values[r] = acc;
-      dd_add(sum, floored_log(acc, two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+      acc_add(sum, floored_term(P, log_tab, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
     }
   }
-  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // FULL, tier 2: the reads that own several records on a mate (list built once per cache commit), one thread
 // each, at most two live placements per mate in registers; anything bigger goes to the scratch path.
-__global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P, int slot0) {
-  DD sum{0.0, 0.0};
+__global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P) {
+  Acc sum = acc_zero();
   unsigned floored = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
     const int r = (int)__ldg(P.complex_list + k);
@@ -388,12 +453,12 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
     double acc = 0.0;
     if (paired_read<true>(P, k, acc)) {
       P.values[r] = acc;
-      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+      acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
     } else {
       push_overflow(P, r);
     }
   }
-  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
@@ -416,8 +481,8 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
 }
 
 // Reads with more than two placements on a mate: exact counts, scratch from a bump allocator, same replay.
-__global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode, int slot0) {
-  DD sum{0.0, 0.0};
+__global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode) {
+  Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -436,20 +501,32 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
       acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
       P.values[r] = acc;
     }
-    if (full_mode) dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    if (full_mode) acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
   }
-  if (full_mode) block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
+  if (full_mode) block_accumulate(sum, floored, P.accum);
 }
 
 // O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
 __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams P) {
-  DD sum{0.0, 0.0};
+  Acc sum = acc_zero();
   unsigned floored = 0;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
-    const uint32_t ll = __ldg(P.lens + r);
-    dd_add(sum, floored_log(P.values[r], P.two_len, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+  const int stride = gridDim.x * blockDim.x;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // software-pipelined like the full kernel: next read's state and lengths are in flight while this one's log runs
+  bool have = r < P.n_reads;
+  double v = 0.0;
+  uint32_t ll = 0;
+  if (have) { v = P.values[r]; ll = __ldg(P.lens + r); }
+  while (have) {
+    const int rn = r + stride;
+    const bool have_next = rn < P.n_reads;
+    double nv = 0.0;
+    uint32_t nll = 0;
+    if (have_next) { nv = P.values[rn]; nll = __ldg(P.lens + rn); }
+    acc_add(sum, floored_term(P, v, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    v = nv; ll = nll; r = rn; have = have_next;
   }
-  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // ---- single -------------------------------------------------------------------------------
@@ -480,7 +557,7 @@ __device__ __forceinline__ bool single_read(const ScoreParams& P, int r, int len
 
 // Tier 1: reads with at most one record (static) whose key occurs at most once in this evaluation.
 __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P) {
-  DD sum{0.0, 0.0};
+  Acc sum = acc_zero();
   unsigned floored = 0;
   const int4* first = static_cast<const int4*>(P.m[0].first);
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
@@ -489,9 +566,9 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
     if (((rw.z >> 17) & 0x1fff) != 0) continue;   // several records: tier 2
     double acc = 0.0;
     if (rw.x >= 0) {
-      const int4 h = ldg4(P.m[0].slots + rw.x);
-      if ((uint32_t)h.x == P.epoch) {
-        if (h.y > 1) {
+      const uint32_t ef = (uint32_t)ldg4(P.m[0].slots_a + rw.x).x;
+      if ((ef & 0x7fffffffu) == P.epoch) {
+        if (ef >> 31) {
           push_overflow(P, r);
           continue;
         }
@@ -499,13 +576,13 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
       }
     }
     P.values[r] = acc;
-    dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
   }
-  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
-__global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParams P, int slot0) {
-  DD sum{0.0, 0.0};
+__global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParams P) {
+  Acc sum = acc_zero();
   unsigned floored = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
     const int r = (int)__ldg(P.complex_list + k);
@@ -513,16 +590,16 @@ __global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParam
     double acc;
     if (single_read<true>(P, k, len, acc)) {
       P.values[r] = acc;
-      dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+      acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
     } else {
       push_overflow(P, r);
     }
   }
-  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
-__global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreParams P, int slot0) {
-  DD sum{0.0, 0.0};
+__global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreParams P) {
+  Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -539,9 +616,9 @@ __global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreP
       acc = single_sum(P, a, n1, len);
     }
     P.values[r] = acc;
-    dd_add(sum, floored_log(acc, P.two_len, __ldg(P.thr_tab + len), floored));
+    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
   }
-  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // ---- pacbio (log space; logdouble.hpp) -----------------------------------------------------
@@ -574,7 +651,7 @@ __device__ __forceinline__ double pacbio_floor(const ScoreParams& P, double v, i
 }
 
 __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P) {
-  DD sum{0.0, 0.0};
+  Acc sum = acc_zero();
   unsigned floored = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
     PlcLong a[kCapLong];
@@ -598,15 +675,15 @@ __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P
       for (int x = 0; x < n; x++) acc = lse_add(acc, a[x].logprob);
     }
     P.values[r] = acc;
-    dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+    acc_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
   }
-  block_reduce_store(sum, floored, P.partials, blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // One WARP per many-placement read: lanes fold a strided share of the read's records sequentially and the 32
 // partial log-sums are combined with the warp-shuffle LSE (order-free; within the 1e-12 per-read budget).
-__global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreParams P, int slot0) {
-  DD sum{0.0, 0.0};
+__global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreParams P) {
+  Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
   const int lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -618,70 +695,58 @@ __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreP
     double part = -INFINITY;
     for (uint32_t i = b + lane; i < e; i += 32) {
       const int4 rw = ldg4(rows + i);
-      const int4 hdr = ldg4(mv.slots + rw.x);
-      if ((uint32_t)hdr.x != P.epoch) continue;
+      if (((uint32_t)ldg4(mv.slots_a + rw.x).x & 0x7fffffffu) != P.epoch) continue;
+      const int n_occ = ldg4(mv.slots_b + rw.x).y;
       const double lp = __hiloint2double(rw.w, rw.z);
-      for (int t = 0; t < hdr.y; t++) part = lse_add(part, lp);   // same record under n_occ live lookups
+      for (int t = 0; t < n_occ; t++) part = lse_add(part, lp);   // same record under n_occ live lookups
     }
     const double acc = warp_lse(part);
     if (lane == 0) {
       P.values[r] = acc;
-      dd_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+      acc_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
     }
   }
-  block_reduce_store(sum, floored, P.partials, slot0 + blockIdx.x);
+  block_accumulate(sum, floored, P.accum);
 }
 
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
-__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch) {
+__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const SlotUpdate u = upd[i];
-  KeySlot s;
-  s.epoch = epoch;
-  s.n_occ = u.n_occ;
-  s.occ_begin = u.occ_begin;
-  s.pad = 0;
-  s.first = u.first;
-  tables[u.store][u.key] = s;
+  SlotA a;
+  a.epoch_flag = epoch | (u.n_occ > 1 ? 0x80000000u : 0u);
+  a.walk = u.first.walk;
+  a.cur_pos = u.first.cur_pos;
+  a.skip_below = u.first.skip_below;
+  SlotB b;
+  b.seg = u.first.seg;
+  b.n_occ = u.n_occ;
+  b.occ_begin = u.occ_begin;
+  b.pad = 0;
+  tab_a[u.store][u.key] = a;
+  tab_b[u.store][u.key] = b;
 }
 
-// out[set] = {sum_hi, sum_lo, floored, flags}: one block per set; thread t folds partials t, t+256, ... and the
-// 256 thread sums are folded in index order by thread 0 — a fixed association, independent of timing.
-__global__ void __launch_bounds__(kBlock) finalize_kernel(const double* partials, const int* set_begin, double* out,
-                                                          const uint32_t* error_flag, const uint32_t* ovf_counts) {
-  __shared__ double s_hi[kBlock], s_lo[kBlock], s_fl[kBlock];
-  const int s = blockIdx.x;
-  DD t{0.0, 0.0};
-  double fl = 0.0;
-  for (int b = set_begin[s] + threadIdx.x; b < set_begin[s + 1]; b += kBlock) {
-    const double* p = partials + (size_t)b * kPartialStride;
-    dd_merge(t, DD{p[0], p[1]});
-    fl += p[2];
-  }
-  s_hi[threadIdx.x] = t.hi;
-  s_lo[threadIdx.x] = t.lo;
-  s_fl[threadIdx.x] = fl;
-  __syncthreads();
-  for (int w = kBlock / 2; w > 0; w >>= 1) {
-    if (threadIdx.x < w) {
-      DD a{s_hi[threadIdx.x], s_lo[threadIdx.x]};
-      dd_merge(a, DD{s_hi[threadIdx.x + w], s_lo[threadIdx.x + w]});
-      s_hi[threadIdx.x] = a.hi;
-      s_lo[threadIdx.x] = a.lo;
-      s_fl[threadIdx.x] += s_fl[threadIdx.x + w];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    // renormalise so hi carries the rounded total
-    const double hi = __dadd_rn(s_hi[0], s_lo[0]);
-    const double lo = __dsub_rn(s_lo[0], __dsub_rn(hi, s_hi[0]));
-    out[s * 4 + 0] = hi;
-    out[s * 4 + 1] = lo;
-    out[s * 4 + 2] = s_fl[0];
-    out[s * 4 + 3] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
-  }
+// out[set] = {integer part, fraction in 2^-40 units, floored, -inf terms, nan terms, flags}: re-assembles the
+// 128-bit exact sum of the set from its 32-bit limbs. Both parts are integers below 2^53, exact in a double.
+__global__ void finalize_kernel(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
+                                const uint32_t* ovf_counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sets) return;
+  const unsigned long long* a = accum + (size_t)s * kAccumStride;
+  unsigned __int128 x = 0;
+  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  const __int128 v = (__int128)x;
+  const long long ip = (long long)(v >> 40);
+  const unsigned long long fr = (unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
+  double* o = out + (size_t)s * kOutStride;
+  o[0] = (double)ip;
+  o[1] = (double)fr;
+  o[2] = (double)a[4];
+  o[3] = (double)a[5];
+  o[4] = (double)a[6];
+  o[5] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
 }
 
 // ---- CSR build: arena (key-major) -> rows (read-major) --------------------------------------
@@ -738,25 +803,25 @@ __global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows
 
 // Static tier-2 list: reads owning more than one record on some mate, in read-id order (scan, not atomics,
 // so the list — and with it the association of the partial sums — is the same on every run).
-__global__ void complex_flags_kernel(const int4* first1, const int4* first2, int n_reads, uint32_t* flags) {
+// class of a read for tier 2: 0 = tier 1 (at most one record per mate), else 1 + min(cnt1,3)*4 + min(cnt2,3)
+__device__ __forceinline__ int complex_class(const int4* first1, const int4* first2, int r) {
+  const int c1 = (first1[r].z >> 16) & 0x3fff;
+  const int c2 = first2 ? ((first2[r].z >> 16) & 0x3fff) : 0;
+  if (c1 < 2 && c2 < 2) return 0;
+  return 1 + min(c1, 3) * 4 + min(c2, 3);
+}
+
+__global__ void complex_flags_kernel(const int4* first1, const int4* first2, int n_reads, uint32_t* flags, int cls) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_reads) return;
-  uint32_t f = 0;
-  if (r < n_reads) {
-    int z = first1[r].z;
-    if (first2) z |= first2[r].z;
-    f = ((z >> 17) & 0x1fff) != 0;
-  }
-  flags[r] = f;
+  flags[r] = (r < n_reads && complex_class(first1, first2, r) == cls) ? 1u : 0u;
 }
 
 __global__ void complex_scatter_kernel(const int4* first1, const int4* first2, int n_reads, const uint32_t* offs,
-                                       uint32_t* list) {
+                                       uint32_t* list, int cls) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
-  int z = first1[r].z;
-  if (first2) z |= first2[r].z;
-  if (((z >> 17) & 0x1fff) != 0) list[offs[r]] = (uint32_t)r;
+  if (complex_class(first1, first2, r) == cls) list[offs[r]] = (uint32_t)r;
 }
 
 __global__ void compact_count_kernel(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr,
@@ -816,18 +881,27 @@ int score_grid(int which, int n_items, int sm_count) {
 }
 int overflow_grid(int sm_count) { return sm_count; }
 
-void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st) {
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch, cudaStream_t st) {
   if (n <= 0) return;
-  apply_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(upd, n, tables, epoch);
+  apply_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(upd, n, tab_a, tab_b, epoch);
 }
 
 // e0/e1 bracket the streaming kernel(s) of the set on the launching stream (roofline timing).
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+// Tier 1 and tier 2 touch disjoint reads and only meet in the (commutative, integer) accumulators, so tier 2 runs
+// on a side stream next to tier 1: both are latency-bound kernels that leave most of the machine idle alone.
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                        const SideStream& side) {
   cudaEventRecord(e0, st);
+  if (cgrid > 0) {
+    cudaEventRecord(side.fork, st);
+    cudaStreamWaitEvent(side.stream, side.fork, 0);
+    paired_complex_kernel<<<cgrid, kBlock, 0, side.stream>>>(P);
+    cudaEventRecord(side.join, side.stream);
+  }
   paired_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  if (cgrid > 0) paired_complex_kernel<<<cgrid, kBlock, 0, st>>>(P, grid);
+  if (cgrid > 0) cudaStreamWaitEvent(st, side.join, 0);
   cudaEventRecord(e1, st);
-  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1, grid + cgrid);
+  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1);
 }
 
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count,
@@ -835,30 +909,37 @@ void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int gri
   cudaEventRecord(e0, st);
   if (n_touch_records > 0) {
     paired_delta_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P);
-    paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 0, 0);
+    paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 0);
   }
   paired_total_kernel<<<grid_total, kBlock, 0, st>>>(P);
   cudaEventRecord(e1, st);
 }
 
-void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                        const SideStream& side) {
   cudaEventRecord(e0, st);
+  if (cgrid > 0) {
+    cudaEventRecord(side.fork, st);
+    cudaStreamWaitEvent(side.stream, side.fork, 0);
+    single_complex_kernel<<<cgrid, kBlock, 0, side.stream>>>(P);
+    cudaEventRecord(side.join, side.stream);
+  }
   single_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  if (cgrid > 0) single_complex_kernel<<<cgrid, kBlock, 0, st>>>(P, grid);
+  if (cgrid > 0) cudaStreamWaitEvent(st, side.join, 0);
   cudaEventRecord(e1, st);
-  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid + cgrid);
+  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P);
 }
 
 void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
   cudaEventRecord(e0, st);
   pacbio_full_kernel<<<grid, kBlock, 0, st>>>(P);
   cudaEventRecord(e1, st);
-  pacbio_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, grid);
+  pacbio_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P);
 }
 
-void launch_finalize(const double* partials, const int* set_begin, int n_sets, double* out, const uint32_t* error_flag,
+void launch_finalize(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
                      const uint32_t* ovf_counts, cudaStream_t st) {
-  finalize_kernel<<<n_sets, kBlock, 0, st>>>(partials, set_begin, out, error_flag, ovf_counts);
+  finalize_kernel<<<(n_sets + 31) / 32, 32, 0, st>>>(accum, n_sets, out, error_flag, ovf_counts);
 }
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
@@ -896,18 +977,33 @@ cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_
 // Builds the static tier-2 list; flags must hold n_reads + 1 uint32 (scratch), list n_reads uint32. The number
 // of listed reads is left in flags[n_reads] (exclusive scan total).
 cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
-                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches) {
+                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out) {
+  // The list is ordered by (record-count class, read id): warps of the tier-2 kernel then hold reads of one shape
+  // — (2,1), (1,2), (2,2), ... — and do not execute each other's paths. One flag/scan/scatter pass per class.
   const int g = (n_reads + 1 + 255) / 256;
-  complex_flags_kernel<<<g, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2), n_reads, flags);
+  const int4* f1 = static_cast<const int4*>(first1);
+  const int4* f2 = static_cast<const int4*>(first2);
   size_t need = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, flags, flags, n_reads + 1, st);
   if (need > temp_bytes) return cudaErrorMemoryAllocation;
-  cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, flags, flags, n_reads + 1, st);
-  if (err != cudaSuccess) return err;
-  if (n_reads > 0)
-    complex_scatter_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2),
-                                                                 n_reads, flags, list);
-  (*launches) += 3;
+  uint32_t base = 0;
+  for (int cls = 1; cls <= 16; cls++) {
+    complex_flags_kernel<<<g, 256, 0, st>>>(f1, f2, n_reads, flags, cls);
+    cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, flags, flags, n_reads + 1, st);
+    if (err != cudaSuccess) return err;
+    uint32_t cnt = 0;
+    err = cudaMemcpyAsync(&cnt, flags + n_reads, 4, cudaMemcpyDeviceToHost, st);
+    if (err != cudaSuccess) return err;
+    err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) return err;
+    (*launches) += 2;
+    if (cnt > 0) {
+      complex_scatter_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(f1, f2, n_reads, flags, list + base, cls);
+      (*launches)++;
+      base += cnt;
+    }
+  }
+  *n_complex_out = base;
   return cudaGetLastError();
 }
 

@@ -10,22 +10,25 @@ enum { kGridPairedFull = 0, kGridPairedComplex, kGridPairedTotal, kGridSingleFul
 int score_grid(int which, int n_items, int sm_count);
 int overflow_grid(int sm_count);
 
-void launch_apply_slots(const SlotUpdate* upd, int n, KeySlot* const* tables, uint32_t epoch, cudaStream_t st);
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch, cudaStream_t st);
 // Each *_full launch is two kernels: the streaming pass (grid blocks -> partial slots [0,grid)) and the
 // many-placement pass (ovf_grid blocks -> partial slots [grid, grid+ovf_grid)).
 // e0 / e1 are recorded on `st` around the streaming kernel(s) of the set (the roofline timing).
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };   // tier 2 runs beside tier 1
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                        const SideStream& side);
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count, cudaStream_t st,
                          cudaEvent_t e0, cudaEvent_t e1);
-void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
+void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                        const SideStream& side);
 void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
-void launch_finalize(const double* partials, const int* set_begin, int n_sets, double* out, const uint32_t* error_flag,
+void launch_finalize(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
                      const uint32_t* ovf_counts, cudaStream_t st);
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
                       void* rows, void* first, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches);
 cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
-                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
+                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out);
 cudaError_t compact_offsets(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr, const uint32_t* lens,
                             uint32_t* clens, void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
 cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr, const void* rows,

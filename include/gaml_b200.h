@@ -75,9 +75,11 @@ typedef struct {
   int32_t n_sets;
 } gaml_result;
 
-/* Partial sums of one read-id shard: per set {sum_hi, sum_lo, floored}; combine across shards with
- * gaml_combine_partials after an all-gather. */
-#define GAML_PARTIAL_DOUBLES 3
+/* Partial sums of one read-id shard, per set: {integer part, fraction in 2^-40 units, floored reads, -inf terms,
+ * nan terms}. The first two are an EXACT integer sum of the shard's per-read log terms (each rounded once to
+ * 2^-40), so adding shards is exact and the combined total does not depend on the number of shards or on any
+ * summation order. Combine with gaml_combine_partials after an all-gather. */
+#define GAML_PARTIAL_DOUBLES 5
 
 typedef struct {
   int64_t kernel_launches;         /* kernels of THIS library launched since context creation */
@@ -137,7 +139,7 @@ int gaml_calc_prob(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk
 
 /* Same evaluation split for sharded (one process per GPU) use: `partials` receives
  * GAML_PARTIAL_DOUBLES doubles per set for THIS shard; all-gather them over ranks, then every rank calls
- * gaml_combine_partials with the n_shards x n_sets x 3 array (rank-major) to get the identical result. */
+ * gaml_combine_partials with the n_shards x n_sets x GAML_PARTIAL_DOUBLES array (rank-major) to get the identical result. */
 int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets,
                            int32_t n_walks, double* partials, int32_t* total_len);
 int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shards, int32_t total_len,

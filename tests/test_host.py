@@ -37,15 +37,29 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_combine_raw_is_pure_host_arithmetic():
-    # two shards, one paired + one pacbio set
-    g = np.array([[[-100.0, 1e-9, 3.0], [-50.0, 0.0, 1.0]], [[-200.0, -1e-9, 4.0], [-25.0, 0.0, 0.0]]])
+    # two shards, one paired + one pacbio set; partial = {integer part, 2^-40 units, floored, -inf terms, nan terms}
+    half = float(2 ** 39)
+    g = np.array([[[-101.0, half, 3.0, 0, 0], [-50.0, 0.0, 1.0, 0, 0]], [[-200.0, half, 4.0, 0, 0], [-25.0, 0.0, 0.0, 0, 0]]])
     prob, zeros, tl = api.combine_partials_raw(g, [1, 2], [10, 5], [1.0, 0.5], 1000)
     assert zeros == [(7, 10), (1, 5)] and tl == 1000
-    expect = (-300.0 / 10) * 1.0 + ((-75.0 / 5) - np.log(2000.0)) * 0.5
+    expect = (-300.0 / 10) * 1.0 + ((-75.0 / 5) - np.log(2000.0)) * 0.5      # -101 + .5 - 200 + .5 = -300
     assert prob == pytest.approx(expect, rel=1e-15)
     # total_len == 0 is replaced by 1 (graph.cc:3067-3069)
     prob0, _, _ = api.combine_partials_raw(g[:1], [1, 2], [10, 5], [1.0, 0.5], 0)
-    assert prob0 == pytest.approx(((-100.0 + 1e-9) / 10) + ((-50.0 / 5) - np.log(2.0)) * 0.5, rel=1e-15)
+    assert prob0 == pytest.approx((-100.5 / 10) + ((-50.0 / 5) - np.log(2.0)) * 0.5, rel=1e-15)
+    # a -inf term (log 0) makes the set's score -inf, like the reference's running sum would
+    g[0, 0, 3] = 1
+    assert api.combine_partials_raw(g, [1, 2], [10, 5], [1.0, 0.5], 1000)[0] == -np.inf
+    # exactness: shard order and grouping cannot change the result
+    rng = np.random.default_rng(0)
+    parts = np.zeros((8, 1, 5))
+    parts[:, 0, 0] = -rng.integers(10 ** 6, 10 ** 8, size=8)
+    parts[:, 0, 1] = rng.integers(0, 2 ** 40, size=8)
+    a = api.combine_partials_raw(parts, [1], [10 ** 6], [1.0], 5)[0]
+    b = api.combine_partials_raw(parts[::-1], [1], [10 ** 6], [1.0], 5)[0]
+    merged = parts.reshape(4, 2, 1, 5).sum(axis=1)      # pre-adding pairs of shards is exact too (integers < 2^53)
+    c = api.combine_partials_raw(merged, [1], [10 ** 6], [1.0], 5)[0]
+    assert a == b == c
 
 
 def test_workload_roundtrip(tmp_path):
@@ -122,9 +136,10 @@ for e, r in enumerate(ref):
     v = p[lo:hi] / (2 * L)
     fl = v < thr
     terms = np.log(np.where(fl, thr, v))
-    part = np.array([terms.sum(), 0.0, float(fl.sum())])
+    X = sum(int(x) for x in np.rint(terms * 2.0 ** 40))          # exact integer sum in units of 2^-40
+    part = np.array([float(X >> 40), float(X & (2 ** 40 - 1)), float(fl.sum()), 0.0, 0.0])
     g = allgather_partials(part)
-    assert g.shape == (world, 3)
+    assert g.shape == (world, 5)
     prob, zeros, tl = api.combine_partials_raw(g, [1], [spec.n_reads], [spec.weight], r.total_len)
     ok &= zeros == r.zeros and abs(prob - r.score) <= 1e-12 * abs(r.score)
 dist.barrier()
