@@ -7,7 +7,7 @@
 A step = one full log-likelihood evaluation (`ProbCalculator::CalcProb` on a fresh ScoringState,
 prob_calculator.h:63-109) of BASELINE config 2: synthetic 4.6 Mbp genome, 2 M innie read pairs 2x100 bp,
 insert 300+-30, injected alignment cache. With N GPUs every rank holds a config-2-sized read-id shard of an
-N-times larger genome/read set (weak scaling); partial log-likelihoods are all-gathered over NCCL.
+N-times larger genome/read set (weak scaling); partial log-likelihoods (exact 128-bit sums) are all-gathered over NCCL.
 
 One JSON line on stdout (rank 0). `value` is device time with all inputs resident in HBM (CUDA events on the
 library's stream, L2 flushed between steps); `e2e` is the same metric through gaml_calc_prob with host
@@ -249,7 +249,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gaml_b200 import api
-    from gaml_b200.dist import allgather_partials
+    from gaml_b200.dist import PartialGatherer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,12 +303,13 @@ def main():
         st = pc.stats()
         return st.last_device_ms, st.last_score_kernel_ms, part, tl
 
+    gather = PartialGatherer(api.PARTIAL_DOUBLES * len(wl.sets), dev)
     flat0 = api.flatten_walks(walks0)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
 
     def full_step_e2e():
         pc.reset_state()
         part, tl = pc.calc_prob_partial_flat(*flat0)
-        g = allgather_partials(part, dev) if world > 1 else part[None, :]
+        g = gather(part)
         return pc.combine(g, g.shape[0], tl)
 
     # ---- value: device-resident inputs, CUDA events, L2 flushed between steps ----
@@ -353,8 +354,8 @@ def main():
     delta_dev_ms, touched = 0.0, 0
     for nodes_offs in seq_flat:
         part, tl = pc.calc_prob_partial_flat(*nodes_offs)
-        if world > 1:
-            allgather_partials(part, dev)
+        g = gather(part)
+        pc.combine(g, g.shape[0], tl)
         s2 = pc.stats()
         delta_dev_ms += s2.last_device_ms
         touched += s2.last_records_gathered
@@ -372,7 +373,7 @@ def main():
                    "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
                    "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
                    "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events on the library stream, max over ranks",
-                   "parallelism": f"read-id shards x{world}, all-gather of 24 B partials per read set"},
+                   "parallelism": f"read-id shards x{world}, all-gather of 40 B exact partials per read set"},
         "roofline": {"bound": "hbm", "kernel": "paired_full_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps},

@@ -50,6 +50,7 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_add_readset", "gaml_cache_insert", "gaml_cache_insert_pacbio", "gaml_cache_contains",
            "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials", "gaml_combine_partials_raw",
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
+           "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
            "gaml_get_stats"]
 
 _lib = None
@@ -82,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.gaml_calc_prob_partial.argtypes = [vp, i32p, i64p, C.c_int32, dp, i32p]
     lib.gaml_combine_partials.argtypes = [vp, dp, C.c_int32, C.c_int32, C.POINTER(Result), i32p]
     lib.gaml_combine_partials_raw.argtypes = [dp, C.c_int32, C.c_int32, i32p, i64p, dp, C.c_int32, C.POINTER(Result), i32p]
+    lib.gaml_calc_prob_batch.argtypes = [vp, C.c_int32, i32p, i64p, i32p, i64p, i64p, dp, i32p, i32p]
+    lib.gaml_calc_prob_batch_partial.argtypes = [vp, C.c_int32, i32p, i64p, i32p, i64p, i64p, dp, i32p]
     lib.gaml_eval_prepare.argtypes = [vp, i32p, i64p, C.c_int32]
     lib.gaml_eval_launch.argtypes = [vp]
     lib.gaml_eval_finish.argtypes = [vp, dp, i32p]
@@ -255,6 +258,28 @@ class ProbCalculator:
         tl = C.c_int32()
         self._check(self.lib.gaml_eval_finish(self.h, part.ctypes.data_as(C.POINTER(C.c_double)), C.byref(tl)))
         return part, tl.value
+
+    def calc_prob_batch(self, candidates):
+        """candidates: list of (erased base-walk indices, added walks). -> (probs [n], total_lens [n], zeros [n][sets])."""
+        n = len(candidates)
+        er_off = np.zeros(n + 1, dtype=np.int64)
+        ca_off = np.zeros(n + 1, dtype=np.int64)
+        er, added = [], []
+        for i, (e, a) in enumerate(candidates):
+            er.extend(int(x) for x in e)
+            added.extend(a)
+            er_off[i + 1] = len(er)
+            ca_off[i + 1] = len(added)
+        er_a = _i32(er if er else [0])
+        nodes, w_off = flatten_walks(added)
+        probs = np.zeros(n, dtype=np.float64)
+        tls = np.zeros(n, dtype=np.int32)
+        zeros = np.zeros(n * 2 * max(len(self.sets), 1), dtype=np.int32)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self.lib.gaml_calc_prob_batch(self.h, n, _p32(er_a), er_off.ctypes.data_as(i64p), _p32(nodes),
+                                                  w_off.ctypes.data_as(i64p), ca_off.ctypes.data_as(i64p),
+                                                  probs.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls), _p32(zeros)))
+        return probs, tls, zeros.reshape(n, max(len(self.sets), 1), 2)
 
     def reset_state(self):
         self._check(self.lib.gaml_reset_state(self.h))

@@ -119,4 +119,30 @@ struct ScoreParams {
   uint32_t* stamp;           // per read: epoch of the evaluation that last claimed it
 };
 
+// ---- batched candidate evaluation (gaml_calc_prob_batch, BASELINE config 5) ------------------------------
+struct BatchCand {             // one candidate move, one paired read set
+  int32_t key_begin[2];        // this candidate's slice of the batch key/slot arrays, per mate (keys sorted)
+  int32_t key_count[2];
+  int32_t n_erased;            // walk ordinals < n_erased are subtracted
+  int32_t len_index;           // index of this candidate's total length among the batch's distinct values
+  int32_t pad[2];
+};
+struct BatchParams {
+  const BatchCand* cands;
+  int32_t n_cand;
+  const int32_t* keys[2];      // per mate: candidate-local sorted key ids
+  const void* slot_a[2];       // parallel SlotA / SlotB words (epoch field unused)
+  const void* slot_b[2];
+  const Occ* occ[2];
+  const TouchRange* ranges;    // mate-1 arena ranges of the touched keys, all candidates back to back
+  const uint32_t* range_prefix;// n_ranges + 1 prefix sums of the range lengths
+  const int32_t* range_cand;   // owning candidate of each range
+  int32_t n_ranges;
+  const double* two_len_d;     // distinct (double)(2*total_len) values and their correctly rounded reciprocals
+  const double* rcp_two_len;
+  int32_t n_len;
+  unsigned long long* accum_len;    // n_len x kAccumStride: exact sum over ALL reads of the base state's terms at that length
+  long long* accum_cand;            // n_cand x 4: {sum of low 32 bits, sum of high 32 bits (signed) of the term deltas, floored delta, bad}
+};
+
 }  // namespace gaml

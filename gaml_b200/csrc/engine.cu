@@ -155,6 +155,8 @@ struct gaml_ctx {
   void* h_blob = nullptr;         // pinned
   size_t h_blob_cap = 0;
   DevBuf d_out, d_flags, d_scratch, d_csr_temp, d_logtab;
+  DevBuf d_batch_blob, d_batch_acc, d_batch_out;   // gaml_calc_prob_batch
+  std::vector<double> h_batch_out;
   double* h_out = nullptr;        // pinned, 4 doubles per set
   size_t h_out_cap = 0;
   unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
@@ -802,6 +804,215 @@ int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, 
   return GAML_OK;
 }
 
+// ---- batched candidate evaluation (BASELINE config 5) ------------------------------------------------------
+// Candidate c = the last evaluated walk set with walks erased_idx[c] removed and its added walks appended. Host
+// work is O(#nodes of the touched walks) per candidate plus O(#base walks) once per batch.
+int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                            const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
+                            double* partials, int32_t* total_lens) {
+  if (n_cand <= 0 || !erased_off || !cand_added_off || !added_walk_off || !partials)
+    return fail(ctx, GAML_ERR_ARG, "bad batch arguments");
+  if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
+  const size_t n_sets = ctx->sets.size();
+  if (n_sets == 0) return fail(ctx, GAML_ERR_STATE, "no read sets");
+  for (auto& rs : ctx->sets) {
+    if (rs->cfg.kind != GAML_KIND_PAIRED)
+      return fail(ctx, GAML_ERR_UNSUPPORTED, "gaml_calc_prob_batch supports paired read sets only (single / pacbio sets keep no "
+                                             "incremental state: every candidate would be a full evaluation)");
+    if (!rs->has_state) return fail(ctx, GAML_ERR_STATE, "gaml_calc_prob_batch needs a base state: call gaml_calc_prob first");
+  }
+  int rc = commit(ctx);
+  if (rc != GAML_OK) return rc;
+  const std::vector<Walk>& base = ctx->sets[0]->old_walks;
+  const int n_base = (int)base.size();
+  // rank of every base walk in the iteration order of the reference's multiset (GetChanges, graph.cc:1747-1763):
+  // erasing the kept walks leaves the others in place, so a candidate's erased walks come out in rank order
+  std::vector<int> rank(n_base, 0);
+  {
+    std::unordered_multiset<Walk, WalkHash> idx(base.begin(), base.end());
+    std::unordered_map<Walk, std::vector<int>, WalkHash> where;
+    for (int i = n_base - 1; i >= 0; i--) where[base[i]].push_back(i);
+    int k = 0;
+    for (const Walk& w : idx) {
+      std::vector<int>& v = where[w];
+      rank[v.back()] = k++;
+      v.pop_back();
+    }
+  }
+  long long base_len = 0;
+  std::vector<int> base_walk_len(n_base);
+  for (int i = 0; i < n_base; i++) {
+    base_walk_len[i] = walk_length(ctx, base[i]);
+    base_len += base_walk_len[i];
+  }
+  // distinct total lengths
+  std::vector<int> cand_len(n_cand);
+  std::unordered_map<int, int> len_index;
+  std::vector<double> two_len_d, rcp;
+  std::vector<int> cand_len_index(n_cand);
+  std::vector<std::vector<Walk>> cand_added(n_cand);
+  std::vector<std::vector<int>> cand_erased(n_cand);
+  for (int c = 0; c < n_cand; c++) {
+    long long tl = base_len;
+    for (int64_t k = erased_off[c]; k < erased_off[c + 1]; k++) {
+      const int bi = erased_idx[k];
+      if (bi < 0 || bi >= n_base) return fail(ctx, GAML_ERR_ARG, "erased walk index outside the base walk set");
+      cand_erased[c].push_back(bi);
+      tl -= base_walk_len[bi];
+    }
+    std::sort(cand_erased[c].begin(), cand_erased[c].end(), [&](int a, int b) { return rank[a] < rank[b]; });
+    for (size_t k = 1; k < cand_erased[c].size(); k++)
+      if (cand_erased[c][k] == cand_erased[c][k - 1]) return fail(ctx, GAML_ERR_ARG, "erased walk listed twice");
+    for (int64_t w = cand_added_off[c]; w < cand_added_off[c + 1]; w++) {
+      Walk wk(added_nodes + added_walk_off[w], added_nodes + added_walk_off[w + 1]);
+      for (int x : wk)
+        if (x >= (int)ctx->node_len.size()) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
+      tl += walk_length(ctx, wk);
+      cand_added[c].push_back(std::move(wk));
+    }
+    cand_len[c] = (int)tl;
+    if (total_lens) total_lens[c] = (int)tl;
+    const int t = cand_len[c] == 0 ? 1 : cand_len[c];
+    const int two = (int)(2u * (unsigned)t);
+    auto it = len_index.find(two);
+    if (it == len_index.end()) {
+      it = len_index.emplace(two, (int)two_len_d.size()).first;
+      two_len_d.push_back((double)two);
+      rcp.push_back(1.0 / (double)two);
+    }
+    cand_len_index[c] = it->second;
+  }
+  const int n_len = (int)two_len_d.size();
+  ctx->h_batch_out.assign((size_t)n_cand * kOutStride, 0.0);
+  cudaStream_t st = ctx->stream;
+
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    std::vector<BatchCand> cands(n_cand);
+    std::vector<int32_t> keys[2];
+    std::vector<SlotA> sa[2];
+    std::vector<SlotB> sb[2];
+    std::vector<Occ> occ[2];
+    std::vector<TouchRange> ranges;
+    std::vector<uint32_t> range_prefix(1, 0);
+    std::vector<int32_t> range_cand;
+    uint64_t touch_total = 0;
+    for (int c = 0; c < n_cand; c++) {
+      OccBuilder ob[2];
+      SetPlan sp;
+      std::vector<TouchRange> touch;
+      int ord = 0;
+      for (int bi : cand_erased[c]) flatten_paired_walk(ctx, rs, base[bi], ord++, ob, sp, &touch);
+      for (const Walk& w : cand_added[c]) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, &touch);
+      BatchCand& cd = cands[c];
+      cd.n_erased = (int)cand_erased[c].size();
+      cd.len_index = cand_len_index[c];
+      cd.pad[0] = cd.pad[1] = 0;
+      for (int m = 0; m < 2; m++) {
+        std::stable_sort(ob[m].items.begin(), ob[m].items.end(),
+                         [](const std::pair<int, Occ>& a, const std::pair<int, Occ>& b) { return a.first < b.first; });
+        cd.key_begin[m] = (int)keys[m].size();
+        size_t i = 0;
+        while (i < ob[m].items.size()) {
+          size_t j = i;
+          while (j < ob[m].items.size() && ob[m].items[j].first == ob[m].items[i].first) j++;
+          const Occ& f = ob[m].items[i].second;
+          keys[m].push_back(ob[m].items[i].first);
+          sa[m].push_back(SlotA{(uint32_t)(j - i > 1 ? 0x80000000u : 0u), f.walk, f.cur_pos, f.skip_below});
+          sb[m].push_back(SlotB{f.seg, (int)(j - i), (int)occ[m].size(), 0});
+          for (size_t t = i; t < j; t++) occ[m].push_back(ob[m].items[t].second);
+          i = j;
+        }
+        cd.key_count[m] = (int)keys[m].size() - cd.key_begin[m];
+      }
+      // each touched mate-1 key once (a key of an erased walk often reappears in the added walk)
+      std::sort(touch.begin(), touch.end(), [](const TouchRange& a, const TouchRange& b) { return a.begin < b.begin; });
+      for (size_t t = 0; t < touch.size(); t++) {
+        if (t > 0 && touch[t].begin == touch[t - 1].begin) continue;
+        ranges.push_back(touch[t]);
+        range_cand.push_back(c);
+        touch_total += touch[t].count;
+        if (touch_total > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one batch");
+        range_prefix.push_back((uint32_t)touch_total);
+      }
+    }
+    // ---- blob ----
+    auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t o = off; off = align16(off + bytes); return o; };
+    const size_t o_cands = place(cands.size() * sizeof(BatchCand));
+    size_t o_keys[2], o_sa[2], o_sb[2], o_occ[2];
+    for (int m = 0; m < 2; m++) {
+      o_keys[m] = place(keys[m].size() * 4);
+      o_sa[m] = place(sa[m].size() * 16);
+      o_sb[m] = place(sb[m].size() * 16);
+      o_occ[m] = place(occ[m].size() * 16);
+    }
+    const size_t o_ranges = place(ranges.size() * sizeof(TouchRange));
+    const size_t o_prefix = place(range_prefix.size() * 4);
+    const size_t o_rcand = place(range_cand.size() * 4);
+    const size_t o_len = place(two_len_d.size() * 8);
+    const size_t o_rcp = place(rcp.size() * 8);
+    std::vector<char> blob(std::max<size_t>(off, 16));
+    auto put = [&](size_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
+    put(o_cands, cands.data(), cands.size() * sizeof(BatchCand));
+    for (int m = 0; m < 2; m++) {
+      put(o_keys[m], keys[m].data(), keys[m].size() * 4);
+      put(o_sa[m], sa[m].data(), sa[m].size() * 16);
+      put(o_sb[m], sb[m].data(), sb[m].size() * 16);
+      put(o_occ[m], occ[m].data(), occ[m].size() * 16);
+    }
+    put(o_ranges, ranges.data(), ranges.size() * sizeof(TouchRange));
+    put(o_prefix, range_prefix.data(), range_prefix.size() * 4);
+    put(o_rcand, range_cand.data(), range_cand.size() * 4);
+    put(o_len, two_len_d.data(), two_len_d.size() * 8);
+    put(o_rcp, rcp.data(), rcp.size() * 8);
+    CU(ctx->d_batch_blob.reserve(blob.size(), 0, false, st));
+    CU(cudaMemcpyAsync(ctx->d_batch_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    const size_t acc_bytes = ((size_t)n_len * kAccumStride + (size_t)n_cand * 4) * 8;
+    CU(ctx->d_batch_acc.reserve(acc_bytes, 0, false, st));
+    CU(cudaMemsetAsync(ctx->d_batch_acc.p, 0, acc_bytes, st));
+    CU(ctx->d_batch_out.reserve((size_t)n_cand * kOutStride * 8, 0, false, st));
+    CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, st));
+    CU(cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(unsigned long long), st));
+    CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, st));
+    // ---- params ----
+    ctx->plan.assign(n_sets, SetPlan());
+    ScoreParams P = make_params(ctx, s);
+    char* db = ctx->d_batch_blob.as<char>();
+    BatchParams B{};
+    B.cands = reinterpret_cast<const BatchCand*>(db + o_cands);
+    B.n_cand = n_cand;
+    for (int m = 0; m < 2; m++) {
+      B.keys[m] = reinterpret_cast<const int32_t*>(db + o_keys[m]);
+      B.slot_a[m] = db + o_sa[m];
+      B.slot_b[m] = db + o_sb[m];
+      B.occ[m] = reinterpret_cast<const Occ*>(db + o_occ[m]);
+    }
+    B.ranges = reinterpret_cast<const TouchRange*>(db + o_ranges);
+    B.range_prefix = reinterpret_cast<const uint32_t*>(db + o_prefix);
+    B.range_cand = reinterpret_cast<const int32_t*>(db + o_rcand);
+    B.n_ranges = (int)ranges.size();
+    B.two_len_d = reinterpret_cast<const double*>(db + o_len);
+    B.rcp_two_len = reinterpret_cast<const double*>(db + o_rcp);
+    B.n_len = n_len;
+    B.accum_len = ctx->d_batch_acc.as<unsigned long long>();
+    B.accum_cand = reinterpret_cast<long long*>(ctx->d_batch_acc.as<unsigned long long>() + (size_t)n_len * kAccumStride);
+    launch_batch(P, B, (uint32_t)touch_total, ctx->d_batch_out.as<double>(),
+                 reinterpret_cast<const uint32_t*>(ctx->d_flags.as<unsigned long long>() + 1), ctx->sm_count, st);
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches += 2 + (touch_total > 0);
+    CU(cudaMemcpyAsync(ctx->h_batch_out.data(), ctx->d_batch_out.p, (size_t)n_cand * kOutStride * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int c = 0; c < n_cand; c++) {
+      const double* o = ctx->h_batch_out.data() + (size_t)c * kOutStride;
+      if (((uint64_t)o[5]) & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
+      for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) partials[((size_t)c * n_sets + s) * GAML_PARTIAL_DOUBLES + k] = o[k];
+    }
+  }
+  return GAML_OK;
+}
+
 int check_ctx(gaml_ctx* ctx) { return ctx ? GAML_OK : GAML_ERR_ARG; }
 
 }  // namespace
@@ -1161,6 +1372,40 @@ int gaml_calc_prob(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk
   int rc = gaml_calc_prob_partial(ctx, walk_nodes, walk_offsets, n_walks, partials.data(), &tl);
   if (rc) return rc;
   return combine(ctx, partials.data(), 1, tl, result, zeros);
+}
+
+int gaml_calc_prob_batch_partial(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                                 const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
+                                 double* partials, int32_t* total_lens) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return calc_prob_batch_partial(ctx, n_cand, erased_idx, erased_off, added_nodes, added_walk_off, cand_added_off, partials,
+                                 total_lens);
+}
+
+int gaml_calc_prob_batch(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                         const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off, double* probs,
+                         int32_t* total_lens, int32_t* zeros) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (!probs || n_cand <= 0) return fail(ctx, GAML_ERR_ARG, "bad batch arguments");
+  for (auto& rs : ctx->sets)
+    if (rs->lo != 0 || rs->hi != rs->n_total)
+      return fail(ctx, GAML_ERR_STATE, "gaml_calc_prob_batch on a sharded context: use gaml_calc_prob_batch_partial + gaml_combine_partials");
+  const size_t n_sets = ctx->sets.size();
+  std::vector<double> partials((size_t)n_cand * std::max<size_t>(n_sets, 1) * GAML_PARTIAL_DOUBLES);
+  std::vector<int32_t> tls(n_cand);
+  int rc = gaml_calc_prob_batch_partial(ctx, n_cand, erased_idx, erased_off, added_nodes, added_walk_off, cand_added_off,
+                                        partials.data(), tls.data());
+  if (rc) return rc;
+  for (int c = 0; c < n_cand; c++) {
+    gaml_result res;
+    rc = combine(ctx, partials.data() + (size_t)c * n_sets * GAML_PARTIAL_DOUBLES, 1, tls[c], &res,
+                 zeros ? zeros + (size_t)c * 2 * n_sets : nullptr);
+    if (rc) return rc;
+    probs[c] = res.prob;
+    if (total_lens) total_lens[c] = tls[c];
+  }
+  return GAML_OK;
 }
 
 int gaml_reset_state(gaml_ctx* ctx) {

@@ -150,10 +150,33 @@ __device__ __forceinline__ void visit_row(const MateView& mv, uint32_t epoch, co
   for (int t = 1; t < b.y; t++) f(ldg4(mv.occ + b.z + t), rw, idx);
 }
 
+// Candidate-local key table of a batched evaluation (gaml_calc_prob_batch): the few keys of the walks one candidate
+// move erases/adds, sorted by key id, with the same two slot words. Found by binary search instead of the global
+// epoch-stamped table, so 1024 candidates with different walk sets can be scored in one launch.
+struct CandLookup {
+  const int* keys;
+  int n;
+  const int4* a;
+  const int4* b;
+  const Occ* occ;
+};
+template <class F>
+__device__ __forceinline__ void visit_row(const MateView&, const CandLookup& lk, const int4& rw, int idx, F&& f) {
+  int lo = 0, hi = lk.n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(lk.keys + mid) < rw.x) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= lk.n || __ldg(lk.keys + lo) != rw.x) return;
+  const int4 a = __ldg(lk.a + lo), b = __ldg(lk.b + lo);
+  f(make_int4(a.y, b.x, a.z, a.w), rw, idx);
+  for (int t = 1; t < b.y; t++) f(ldg4(lk.occ + b.z + t), rw, idx);
+}
+
 // Short-read stores (hybrid layout): first[r] = {key, pos, edor | count<<16, row offset}; the read's
 // other records follow at rows[offset+1 ..]. key < 0 = the read has no record at all.
-template <class F>
-__device__ __forceinline__ void for_each_short(const MateView& mv, uint32_t epoch, int r, F&& f) {
+template <class E, class F>
+__device__ __forceinline__ void for_each_short(const MateView& mv, const E& epoch, int r, F&& f) {
   int4 rw = ldg4(static_cast<const int4*>(mv.first) + r);
   if (rw.x < 0) return;
   int cnt = (rw.z >> 16) & 0x3fff;
@@ -167,8 +190,8 @@ __device__ __forceinline__ void for_each_short(const MateView& mv, uint32_t epoc
 
 // Compact copy of the records of the tier-2 reads (those owning several records on a mate): read k of the
 // static list owns crows[cptr[k] .. cptr[k+1]) — contiguous across neighbouring threads, so tier 2 streams.
-template <class F>
-__device__ __forceinline__ void for_each_compact(const MateView& mv, uint32_t epoch, int k, F&& f) {
+template <class E, class F>
+__device__ __forceinline__ void for_each_compact(const MateView& mv, const E& epoch, int k, F&& f) {
   const uint32_t b = __ldg(mv.cptr + k), e = __ldg(mv.cptr + k + 1);
   const RowShort* rows = static_cast<const RowShort*>(mv.crows);
   for (uint32_t i = b; i < e; i++) visit_row(mv, epoch, ldg4(rows + i), (int)(i - b), f);
@@ -238,8 +261,8 @@ struct Two {
   int walk0, pos0, edor0, walk1, pos1, edor1;
 };
 
-template <bool kCompact = false>
-__device__ __forceinline__ void scan_two(const MateView& mv, uint32_t epoch, int r, Two& t) {
+template <bool kCompact = false, class E = uint32_t>
+__device__ __forceinline__ void scan_two(const MateView& mv, const E& epoch, int r, Two& t) {
   t.n = 0;
   auto visit = [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
@@ -279,13 +302,13 @@ __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, i
 // Per-read paired update for reads with <= 2 live placements per mate. For lists sorted in enumeration
 // order the plain x-major / y-minor loop with a same-walk filter IS the reference's order: walks ascend with
 // x, erased walks (subtract) precede added ones (add). Returns false if the read needs the scratch path.
-template <bool kCompact = false>
-__device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
+template <bool kCompact = false, class E0 = uint32_t, class E1 = uint32_t>
+__device__ __forceinline__ bool paired_read_with(const ScoreParams& P, const E0& lk0, const E1& lk1, int r, double& acc) {
   Two a, b;
   const uint32_t ll = __ldg((kCompact ? P.clens : P.lens) + r);   // r is the list index k in the compact variant
-  scan_two<kCompact>(P.m[0], P.epoch, r, a);
+  scan_two<kCompact>(P.m[0], lk0, r, a);
   if (a.n == 0) return true;
-  scan_two<kCompact>(P.m[1], P.epoch, r, b);
+  scan_two<kCompact>(P.m[1], lk1, r, b);
   if (b.n == 0) return true;
   if (a.n > 2 || b.n > 2) return false;
   const int l1 = ll & 0xffff, l2 = ll >> 16;
@@ -304,8 +327,14 @@ __device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double&
   return true;
 }
 
+template <bool kCompact = false>
+__device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
+  return paired_read_with<kCompact>(P, P.epoch, P.epoch, r, acc);
+}
+
 // General replay from placement lists in memory (scratch path).
-__device__ int gather_short(const MateView& mv, uint32_t epoch, int r, Plc* out) {
+template <class E>
+__device__ int gather_short(const MateView& mv, const E& epoch, int r, Plc* out) {
   int n = 0;
   for_each_short(mv, epoch, r, [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
@@ -709,6 +738,136 @@ __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreP
   block_accumulate(sum, floored, P.accum);
 }
 
+// ---- batched candidate evaluation (BASELINE config 5) ------------------------------------------------
+// Candidate c replaces a few walks of the last evaluated walk set. Its score is
+//     sum over ALL reads of term(base value, L_c)  +  sum over reads touched by c of [term(new value, L_c) - term(base value, L_c)]
+// with exactly the per-read arithmetic of a normal evaluation; all sums are exact integers, so the result is the
+// double gaml_calc_prob would return for the candidate's walk set — without touching the state.
+__device__ __forceinline__ double floored_term_at(const double2* log_tab, double p, double d, double rcp, double thr,
+                                                  int& floored) {
+  double q = __dmul_rn(p, rcp);
+  q = fma(fma(-q, d, p), rcp, q);
+  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = __ddiv_rn(p, d);
+  floored = 0;
+  if (q < thr) { floored = 1; q = thr; }
+  return table_log(log_tab, q);
+}
+
+// First sum: one pass over the base state per distinct total length (blockIdx.y).
+__global__ void __launch_bounds__(kBlock) batch_base_kernel(const ScoreParams P, const BatchParams B) {
+  const int j = blockIdx.y;
+  const double d = B.two_len_d[j], rcp = B.rcp_two_len[j];
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
+  Acc sum = acc_zero();
+  unsigned floored = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
+    const uint32_t ll = __ldg(P.lens + r);
+    int fl;
+    acc_add(sum, floored_term_at(log_tab, P.values[r], d, rcp, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), fl));
+    floored += fl;
+  }
+  block_accumulate(sum, floored, B.accum_len + (size_t)j * kAccumStride);
+}
+
+// Second sum: one thread per mate-1 record under a key the candidate touches. The thread whose record is the
+// FIRST such record of its read (smallest arena index) owns the read for this candidate — no claim words, so
+// different candidates can share a read in the same launch.
+__global__ void __launch_bounds__(kBlock) batch_touch_kernel(const ScoreParams P, const BatchParams B) {
+  const uint32_t total = __ldg(B.range_prefix + B.n_ranges);
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = B.n_ranges;   // largest t with prefix[t] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(B.range_prefix + mid) <= i) lo = mid; else hi = mid;
+    }
+    const int c = __ldg(B.range_cand + lo);
+    const BatchCand cd = B.cands[c];
+    const uint32_t ai = B.ranges[lo].begin + (i - __ldg(B.range_prefix + lo));
+    const int r = ldg4(P.arena1 + ai).x;
+    CandLookup lk0{B.keys[0] + cd.key_begin[0], cd.key_count[0], static_cast<const int4*>(B.slot_a[0]) + cd.key_begin[0],
+                   static_cast<const int4*>(B.slot_b[0]) + cd.key_begin[0], B.occ[0]};
+    CandLookup lk1{B.keys[1] + cd.key_begin[1], cd.key_count[1], static_cast<const int4*>(B.slot_a[1]) + cd.key_begin[1],
+                   static_cast<const int4*>(B.slot_b[1]) + cd.key_begin[1], B.occ[1]};
+    {   // ownership: is there an earlier record of this read under a key of this candidate?
+      const MateView& mv = P.m[0];
+      const int4 f = ldg4(static_cast<const int4*>(mv.first) + r);
+      int cnt = (f.z >> 16) & 0x3fff;
+      const uint32_t base = (uint32_t)f.w;
+      if (cnt == 0x3fff) cnt = (int)(__ldg(mv.rowptr + r + 1) - base);
+      const RowShort* rows = static_cast<const RowShort*>(mv.rows);
+      bool owner = true;
+      for (int k = 0; k < cnt; k++) {
+        const int4 rw = ldg4(rows + base + k);
+        if ((uint32_t)rw.w >= ai) break;   // rows are in arena order
+        int l2 = 0, h2 = lk0.n;
+        while (l2 < h2) {
+          const int mid = (l2 + h2) >> 1;
+          if (__ldg(lk0.keys + mid) < rw.x) l2 = mid + 1; else h2 = mid;
+        }
+        if (l2 < lk0.n && __ldg(lk0.keys + l2) == rw.x) { owner = false; break; }
+      }
+      if (!owner) continue;
+    }
+    const double v0 = P.values[r];
+    double v1 = v0;
+    ScoreParams Q = P;   // the replay reads n_erased from the params
+    Q.n_erased = cd.n_erased;
+    if (!paired_read_with(Q, lk0, lk1, r, v1)) {
+      // many-placement read: same replay from a scratch allocation, inline (rare)
+      const int n1 = gather_short(P.m[0], lk0, r, nullptr), n2 = gather_short(P.m[1], lk1, r, nullptr);
+      const unsigned long long at = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
+      if (at + n1 + n2 > P.scratch_cap) {
+        atomicOr(P.error_flag, 2u);
+        continue;
+      }
+      Plc* a = P.scratch + at;
+      Plc* b = a + n1;
+      gather_short(P.m[0], lk0, r, a);
+      gather_short(P.m[1], lk1, r, b);
+      const uint32_t ll = __ldg(P.lens + r);
+      v1 = apply_pairs(Q, a, n1, b, n2, ll & 0xffff, ll >> 16, v0);
+    }
+    if (v1 == v0) continue;   // bit-identical value: identical term
+    const uint32_t ll = __ldg(P.lens + r);
+    const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
+    const double d = B.two_len_d[cd.len_index], rcp = B.rcp_two_len[cd.len_index];
+    int f0, f1;
+    const double t0 = floored_term_at(log_tab, v0, d, rcp, thr, f0), t1 = floored_term_at(log_tab, v1, d, rcp, thr, f1);
+    long long* acc = B.accum_cand + (size_t)c * 4;
+    if (fabs(t0) < kFixLimit && fabs(t1) < kFixLimit) {
+      const long long dq = __double2ll_rn(t1 * kFixScale) - __double2ll_rn(t0 * kFixScale);   // |q| < 2^62: no overflow
+      if (dq != 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)(uint32_t)dq);          // low 32 bits
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), (unsigned long long)(dq >> 32));        // high part, signed
+      }
+    } else {
+      atomicAdd(reinterpret_cast<unsigned long long*>(acc + 3), 1ull);   // non-finite term: reported as nan
+    }
+    if (f1 != f0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)(long long)(f1 - f0));
+  }
+}
+
+// out[c] = {integer part, 2^-40 units, floored, -inf terms, nan terms, flags} like finalize_kernel.
+__global__ void batch_finalize_kernel(const BatchParams B, double* out, const uint32_t* error_flag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B.n_cand) return;
+  const unsigned long long* a = B.accum_len + (size_t)B.cands[c].len_index * kAccumStride;
+  unsigned __int128 x = 0;
+  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  const long long* dl = B.accum_cand + (size_t)c * 4;
+  __int128 v = (__int128)x + (__int128)dl[0] + ((__int128)dl[1] << 32);
+  const long long ip = (long long)(v >> 40);
+  const unsigned long long fr = (unsigned long long)((unsigned __int128)v & (((unsigned __int128)1 << 40) - 1));
+  double* o = out + (size_t)c * kOutStride;
+  o[0] = (double)ip;
+  o[1] = (double)fr;
+  o[2] = (double)((long long)a[4] + dl[2]);
+  o[3] = (double)a[5];
+  o[4] = (double)((long long)a[6] + dl[3]);
+  o[5] = (double)(*error_flag);
+}
+
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1029,6 +1188,16 @@ cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* ro
     (*launches)++;
   }
   return cudaGetLastError();
+}
+
+void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
+                  int sm_count, cudaStream_t st) {
+  if (B.n_len > 0) {
+    const int gx = grid_for((size_t)P.n_reads, kBlock, sm_count, 4);
+    batch_base_kernel<<<dim3(gx, B.n_len), kBlock, 0, st>>>(P, B);
+  }
+  if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
+  batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag);
 }
 
 size_t csr_temp_bytes(int n_reads) {

@@ -33,6 +33,9 @@ cudaError_t compact_offsets(const uint32_t* list, int n_complex, const uint32_t*
                             uint32_t* clens, void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
 cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr, const void* rows,
                          void* crows, cudaStream_t st, int* launches);
+// Batched candidate evaluation of one paired set: base pass per distinct total length, touched-read pass, finalize.
+void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
+                  int sm_count, cudaStream_t st);
 size_t csr_temp_bytes(int n_reads);
 
 }  // namespace gaml

@@ -1,10 +1,11 @@
 """Read-id sharding across ranks (one process per GPU) — SURVEY.md §8e.
 
 Every read's term is independent given the walks, so each rank scores the contiguous read-id block it
-holds and the only exchange is the per-set partial {sum_hi, sum_lo, floored}: 24 bytes per read set per
-evaluation. The partials are ALL-GATHERED (not sum-reduced) and every rank adds them in rank order with
-an error-free transformation, so the rounded total does not depend on the collective's internal order;
-`torch.distributed` (NCCL over NVLink on the GPU box, gloo in CPU tests) is only the plumbing.
+holds and the only exchange is the per-set partial {integer part, 2^-40 units, floored, -inf terms, nan terms}:
+40 bytes per read set per evaluation. The partials are ALL-GATHERED and every rank adds them exactly (128-bit
+integers, `gaml_combine_partials`), so the total is bit-identical for any number of ranks and independent of the
+collective's internal order; `torch.distributed` (NCCL over NVLink on the GPU box, gloo in CPU tests) is only the
+plumbing.
 """
 from __future__ import annotations
 
@@ -19,8 +20,40 @@ def shard_bounds(n_reads: int, rank: int, world: int) -> Tuple[int, int]:
     return min(rank * per, n_reads), min((rank + 1) * per, n_reads)
 
 
+class PartialGatherer:
+    """All-gather of the per-rank partial vector with preallocated pinned/device staging buffers
+    (the exchange is latency bound: nothing is allocated per evaluation)."""
+
+    def __init__(self, n_doubles: int, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n = n_doubles
+        self.device = device
+        if self.world > 1:
+            pin = device is not None and torch.cuda.is_available()
+            self.h_in = torch.empty(n_doubles, dtype=torch.float64, pin_memory=pin)
+            self.h_out = torch.empty(self.world * n_doubles, dtype=torch.float64, pin_memory=pin)
+            dev = device if device is not None else "cpu"
+            self.d_in = torch.empty(n_doubles, dtype=torch.float64, device=dev)
+            self.d_out = torch.empty(self.world * n_doubles, dtype=torch.float64, device=dev)
+
+    def __call__(self, partials: np.ndarray) -> np.ndarray:
+        """[n] float64 of this rank -> [world, n] on every rank."""
+        if self.world == 1:
+            return np.asarray(partials, dtype=np.float64)[None, :]
+        self.h_in.numpy()[:] = partials
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.d_out, self.d_in)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        if self.device is not None and self.torch.cuda.is_available():
+            self.torch.cuda.current_stream().synchronize()
+        return self.h_out.numpy().reshape(self.world, self.n).copy()
+
+
 def allgather_partials(partials: np.ndarray, device=None) -> np.ndarray:
-    """[n_sets*3] float64 of this rank -> [world, n_sets*3] on every rank."""
+    """One-shot form of PartialGatherer (allocates): [n] float64 of this rank -> [world, n] on every rank."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -33,8 +66,8 @@ def allgather_partials(partials: np.ndarray, device=None) -> np.ndarray:
     return torch.stack(out).cpu().numpy()
 
 
-def sharded_calc_prob(pc, paths: Sequence[Sequence[int]], device=None):
-    """CalcProb over all ranks' shards: local partials -> all-gather -> ordered combine (same value on every rank)."""
+def sharded_calc_prob(pc, paths: Sequence[Sequence[int]], device=None, gatherer: "PartialGatherer" = None):
+    """CalcProb over all ranks' shards: local partials -> all-gather -> exact combine (same value on every rank)."""
     part, tl = pc.calc_prob_partial(paths)
-    g = allgather_partials(part, device)
+    g = gatherer(part) if gatherer is not None else allgather_partials(part, device)
     return pc.combine(g, g.shape[0], tl)

@@ -157,6 +157,21 @@ int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* w
 int gaml_eval_launch(gaml_ctx* ctx);
 int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len);
 
+/* Batched, STATELESS evaluation of candidate moves (BASELINE config 5; SURVEY §8b gaml_gpu_eval_batch): candidate c
+ * is the last evaluated walk set with the base walks erased_idx[erased_off[c] .. erased_off[c+1]) removed and the
+ * walks added_walk_off[cand_added_off[c] .. cand_added_off[c+1]) appended (added_nodes / added_walk_off in the
+ * layout of gaml_calc_prob). probs[c] is exactly the double gaml_calc_prob would return for that walk set if it were
+ * called now — the same per-read subtract/add replay from the current ScoringState and the same exact sum — but
+ * nothing is committed, so a move (LocalChange2, FixRepForNode2, FixGapLength: moves.cc:107-113, 715-726, 1158-1203)
+ * can score all its candidates in one launch and then commit the winner with gaml_calc_prob. Paired sets only.
+ * zeros (optional): n_cand x 2 n_sets. The _partial form returns n_cand x n_sets x GAML_PARTIAL_DOUBLES for shards. */
+int gaml_calc_prob_batch(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                         const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
+                         double* probs, int32_t* total_lens, int32_t* zeros);
+int gaml_calc_prob_batch_partial(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                                 const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
+                                 double* partials, int32_t* total_lens);
+
 /* Forget the paired ScoringState (== constructing a fresh ProbCalculator, prob_calculator.h:45-47): the
  * next evaluation re-scores every read from scratch ("full logL"). */
 int gaml_reset_state(gaml_ctx* ctx);

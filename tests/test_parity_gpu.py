@@ -220,3 +220,57 @@ def test_reference_annealing_driver_over_cuda_is_identical(tmp_path):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("IDENTICAL TRAJECTORY") == 2, out.stdout
+
+
+# ---- batched candidate evaluation (BASELINE config 5) ---------------------------------------------
+def _delta(base, cand):
+    """(indices of base walks not in cand, walks of cand not in base) as a multiset difference."""
+    from collections import Counter
+    need = Counter(tuple(w) for w in cand)
+    erased = []
+    for i, w in enumerate(base):
+        if need[tuple(w)] > 0:
+            need[tuple(w)] -= 1
+        else:
+            erased.append(i)
+    have = Counter(tuple(w) for w in base)
+    added = []
+    for w in cand:
+        if have[tuple(w)] > 0:
+            have[tuple(w)] -= 1
+        else:
+            added.append(list(w))
+    return erased, added
+
+
+def test_batched_candidates_equal_sequential_evaluation(oracle):
+    """gaml_calc_prob_batch must return, for every candidate, exactly the double that gaml_calc_prob returns when
+    the candidate's walk set is evaluated right after the same history (fresh context per candidate), must not
+    disturb the state, and must agree with the oracle."""
+    wl = synth.paired_workload(14, 2500, 6000, n_evals=26, seed=77)
+    n_hist = 8
+    history, cands = wl.evals[:n_hist], wl.evals[n_hist:]
+    base = history[-1]
+    pc = api.ProbCalculator.from_workload(wl)
+    for walks in history:
+        last = pc.calc_prob(walks)
+    state_before = pc.read_values(0).copy()
+    probs, tls, zeros = pc.calc_prob_batch([_delta(base, c) for c in cands])
+    assert np.array_equal(pc.read_values(0), state_before)          # stateless
+    assert pc.calc_prob(base) == last                                 # and the next normal evaluation is unaffected
+    pc.close()
+    for i, cand in enumerate(cands):
+        ref_pc = api.ProbCalculator.from_workload(wl)
+        for walks in history:
+            ref_pc.calc_prob(walks)
+        p, z, tl = ref_pc.calc_prob(cand)
+        ref_pc.close()
+        assert probs[i] == p, (i, probs[i], p)                        # bit-identical
+        assert int(tls[i]) == tl and (int(zeros[i, 0, 0]), int(zeros[i, 0, 1])) == z[0]
+    # oracle: history + one candidate, for a few candidates
+    for i in (0, len(cands) // 2, len(cands) - 1):
+        small = workload.Workload(node_len=wl.node_len, normalize_map=wl.normalize_map, sets=wl.sets,
+                                  evals=history + [cands[i]])
+        ref = oracle(small, f"batch{i}", dump=False)
+        assert abs(probs[i] - ref[-1].score) <= REL_TOTAL * abs(ref[-1].score)
+        assert int(tls[i]) == ref[-1].total_len and int(zeros[i, 0, 0]) == ref[-1].zeros[0][0]
