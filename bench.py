@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = config 2)")
     ap.add_argument("--delta-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1024, help="candidate moves per gaml_calc_prob_batch launch (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaml_b200" else args.warmup
 
@@ -363,6 +364,60 @@ def main():
     delta_s = max_over_ranks(time.perf_counter() - t0)
     delta_bytes = pc.stats().last_algorithmic_bytes
 
+    # ---- BASELINE config 5: 1024 candidate moves scored per launch against the current state (stateless) ----
+    base = seq[-1] if seq else walks0
+    rng = np.random.default_rng(123)
+    cands = []
+    multi = [i for i, w in enumerate(base) if sum(1 for x in w if x >= 0) >= 2]
+    for k in range(args.batch):
+        u = rng.random()
+        if u < 0.4 or not multi:                                   # extend: join two walks (sometimes with a gap)
+            i, j = (int(x) for x in rng.choice(len(base), size=2, replace=False))
+            mid = [-int(rng.integers(1, 400))] if rng.random() < 0.3 else []
+            cands.append(([i, j], [list(base[i]) + mid + list(base[j])]))
+        elif u < 0.7:                                              # interchange: swap the tails of two walks
+            i = multi[int(rng.integers(len(multi)))]
+            j = int(rng.integers(len(base)))
+            if j == i:
+                j = (j + 1) % len(base)
+            ci = int(rng.integers(1, len(base[i])))
+            cj = int(rng.integers(0, len(base[j]) + 1))
+            a, b = list(base[i][:ci]) + list(base[j][cj:]), list(base[j][:cj]) + list(base[i][ci:])
+            ok = all(w and w[0] >= 0 and w[-1] >= 0 for w in (a, b))
+            cands.append(([i, j], [a, b]) if ok else ([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
+        else:                                                      # disconnect: split one walk
+            i = multi[int(rng.integers(len(multi)))]
+            nodes_pos = [t for t in range(1, len(base[i])) if base[i][t] >= 0 and base[i][t - 1] >= 0]
+            if not nodes_pos:
+                cands.append(([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
+            else:
+                cut = nodes_pos[int(rng.integers(len(nodes_pos)))]
+                cands.append(([i], [list(base[i][:cut]), list(base[i][cut:])]))
+    batch_info = None
+    if args.batch > 0:
+        packed = pc.pack_candidates(cands)
+        gather_b = PartialGatherer(args.batch * api.PARTIAL_DOUBLES * len(wl.sets), dev)
+        kinds = [s_.kind for s_ in wl.sets]
+        def run_batch():
+            part, tls = pc.calc_prob_batch_partial_packed(packed)
+            g = gather_b(part.reshape(-1)).reshape(world, args.batch, len(wl.sets), api.PARTIAL_DOUBLES)
+            return [api.combine_partials_raw(g[:, c], kinds, [s_.n_reads for s_ in wl.sets], [s_.weight for s_ in wl.sets], int(tls[c]))[0]
+                    for c in range(args.batch)]
+        run_batch()
+        launches_b0 = pc.stats().kernel_launches
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            batch_probs = run_batch()
+        barrier()
+        batch_s = max_over_ranks(time.perf_counter() - t0) / 3
+        batch_info = {"candidates_per_launch": args.batch, "ms_per_batch": 1e3 * batch_s, "candidates_per_s": args.batch / batch_s,
+                      "mix": "40% extend / 30% interchange / 30% disconnect on the walk set reached after the incremental run",
+                      "kernel_launches_per_batch": int((pc.stats().kernel_launches - launches_b0) / 3),
+                      "best_candidate_prob": float(max(batch_probs)),
+                      "note": "gaml_calc_prob_batch_partial: host arrays in, exact partials out (+ all-gather and combine at N>1), wall clock; "
+                              "each score is bit-identical to a sequential gaml_calc_prob of that candidate"}
+
     peak, peak_src = measured_peak()
     achieved = bytes_local / (ker_ms / args.steps * 1e-3) / 1e9
     line = {
@@ -387,6 +442,7 @@ def main():
         "incremental": {"evals": len(seq), "e2e_ms_per_eval": 1e3 * delta_s / max(len(seq), 1),
                         "device_ms_per_eval": delta_dev_ms / max(len(seq), 1), "touched_alignments_per_eval": touched / max(len(seq), 1),
                         "algorithmic_bytes_last_eval": int(delta_bytes)},
+        "batch": batch_info,
         "cache_upload": {"seconds": t_upload, "bytes": int(cache_bytes)},
         "result": {"prob": prob, "total_len": tl_full, "floored": zeros[0][0]},
     }

@@ -259,6 +259,33 @@ class ProbCalculator:
         self._check(self.lib.gaml_eval_finish(self.h, part.ctypes.data_as(C.POINTER(C.c_double)), C.byref(tl)))
         return part, tl.value
 
+    @staticmethod
+    def pack_candidates(candidates):
+        """list of (erased base-walk indices, added walks) -> the flat host arrays of gaml_calc_prob_batch."""
+        n = len(candidates)
+        er_off = np.zeros(n + 1, dtype=np.int64)
+        ca_off = np.zeros(n + 1, dtype=np.int64)
+        er, added = [], []
+        for i, (e, a) in enumerate(candidates):
+            er.extend(int(x) for x in e)
+            added.extend(a)
+            er_off[i + 1] = len(er)
+            ca_off[i + 1] = len(added)
+        nodes, w_off = flatten_walks(added)
+        return n, _i32(er if er else [0]), er_off, nodes, w_off, ca_off
+
+    def calc_prob_batch_partial_packed(self, packed):
+        """gaml_calc_prob_batch_partial on pre-packed host arrays -> (partials [n, sets, PARTIAL_DOUBLES], total_lens [n])."""
+        n, er_a, er_off, nodes, w_off, ca_off = packed
+        ns = max(len(self.sets), 1)
+        part = np.zeros(n * ns * PARTIAL_DOUBLES, dtype=np.float64)
+        tls = np.zeros(n, dtype=np.int32)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self.lib.gaml_calc_prob_batch_partial(self.h, n, _p32(er_a), er_off.ctypes.data_as(i64p), _p32(nodes),
+                                                          w_off.ctypes.data_as(i64p), ca_off.ctypes.data_as(i64p),
+                                                          part.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls)))
+        return part.reshape(n, ns, PARTIAL_DOUBLES), tls
+
     def calc_prob_batch(self, candidates):
         """candidates: list of (erased base-walk indices, added walks). -> (probs [n], total_lens [n], zeros [n][sets])."""
         n = len(candidates)
