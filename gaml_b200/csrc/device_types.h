@@ -108,6 +108,8 @@ struct ScoreParams {
   int32_t n_complex;
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
   unsigned long long* accum;
+  uint32_t* ticket;          // blocks-finished counter of the set's last kernel (finish_set)
+  double* out;               // kOutStride doubles written by the last block
   const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
   double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)
   double rcp_two_len;

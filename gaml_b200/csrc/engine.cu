@@ -189,8 +189,9 @@ int fail(gaml_ctx* ctx, int code, const std::string& msg) {
 }
 
 // d_flags layout (u64 words, zeroed at the start of every evaluation): [0] scratch cursor | [1] error flag (u32) |
-// [2, 2+n) per-set overflow counters (u32 in u64 slots) | then per set kAccumStride words of exact accumulators
-size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (1 + kAccumStride); }
+// [2, 2+n) per-set overflow counters (u32 in u64 slots) | [2+n, 2+2n) per-set tickets | then per set kAccumStride
+// words of exact accumulators
+size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (2 + kAccumStride); }
 
 double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, same expression order
   double z = (d - mean) / sd;
@@ -629,7 +630,10 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.complex_list = rs.d_complex.as<uint32_t>();
   P.clens = rs.d_clens.as<uint32_t>();
   P.n_complex = rs.n_complex;
-  P.accum = fl + 2 + std::max<size_t>(ctx->sets.size(), 1) + s * kAccumStride;
+  const size_t ns = std::max<size_t>(ctx->sets.size(), 1);
+  P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);
+  P.accum = fl + 2 + 2 * ns + s * kAccumStride;
+  P.out = ctx->d_out.as<double>() + s * kOutStride;
   P.log_tab = ctx->d_logtab.p;
   P.two_len_d = (double)P.two_len;
   P.rcp_two_len = 1.0 / P.two_len_d;
@@ -646,14 +650,12 @@ int launch(gaml_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   const size_t n_sets = ctx->sets.size();
   CU(cudaEventRecord(ctx->ev[0], st));
-  CU(cudaMemsetAsync(ctx->d_flags.p, 0, flags_words(n_sets) * sizeof(unsigned long long), st));
   char* blob = ctx->d_blob.as<char>();
   int launches = 0;
-  if (ctx->n_updates > 0) {
-    launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates,
-                       ctx->d_tables.as<SlotA*>(), ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, st);
-    launches++;
-  }
+  launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates, ctx->d_tables.as<SlotA*>(),
+                     ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, ctx->d_flags.as<unsigned long long>(),
+                     (int)flags_words(n_sets), st);
+  launches++;
   CU(cudaEventRecord(ctx->ev[1], st));
   int64_t records = 0, reads = 0, bytes = 0;
   bool any_full = false;
@@ -688,12 +690,6 @@ int launch(gaml_ctx* ctx) {
     }
   }
   CU(cudaEventRecord(ctx->ev[2], st));
-  if (n_sets > 0) {
-    unsigned long long* fl = ctx->d_flags.as<unsigned long long>();
-    launch_finalize(fl + 2 + std::max<size_t>(n_sets, 1), (int)n_sets, ctx->d_out.as<double>(),
-                    reinterpret_cast<const uint32_t*>(fl + 1), reinterpret_cast<const uint32_t*>(fl + 2), st);
-    launches++;
-  }
   CU(cudaEventRecord(ctx->ev[3], st));
   CU(cudaGetLastError());
   ctx->stats.kernel_launches += launches;

@@ -101,6 +101,30 @@ __device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long l
   }
 }
 
+// Called by every block at the end of the LAST kernel of a read set: the block that draws the final ticket
+// re-assembles the set's exact 128-bit sum from its limbs and writes out[] = {integer part, fraction in 2^-40 units,
+// floored, -inf terms, nan terms, flags} (both parts are integers below 2^53, exact in a double).
+__device__ void finish_set(const ScoreParams& P) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  unsigned long long a[7];
+  for (int j = 0; j < 7; j++) a[j] = __ldcg(P.accum + j);
+  unsigned __int128 x = 0;
+  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  const __int128 v = (__int128)x;
+  P.out[0] = (double)(long long)(v >> 40);
+  P.out[1] = (double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
+  P.out[2] = (double)a[4];
+  P.out[3] = (double)a[5];
+  P.out[4] = (double)a[6];
+  P.out[5] = (double)__ldcg(P.error_flag) + 16.0 * (double)__ldcg(P.ovf_count);
+}
+
 // ---- log and division ------------------------------------------------------------------------------
 // log(v) for positive normal finite v from a 128-entry table {1/c, -log(1/c)} (host-built in long double,
 // engine.cu): v = 2^k z, z in [0.6875, 1.375); r = z*invc - 1 (one fma, |r| < 2^-7); log v = k ln2 + logc + log1p(r)
@@ -532,7 +556,10 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
     }
     if (full_mode) acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
   }
-  if (full_mode) block_accumulate(sum, floored, P.accum);
+  if (full_mode) {
+    block_accumulate(sum, floored, P.accum);
+    finish_set(P);
+  }
 }
 
 // O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
@@ -556,6 +583,7 @@ __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams 
     v = nv; ll = nll; r = rn; have = have_next;
   }
   block_accumulate(sum, floored, P.accum);
+  finish_set(P);
 }
 
 // ---- single -------------------------------------------------------------------------------
@@ -648,6 +676,7 @@ __global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreP
     acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
   }
   block_accumulate(sum, floored, P.accum);
+  finish_set(P);
 }
 
 // ---- pacbio (log space; logdouble.hpp) -----------------------------------------------------
@@ -736,6 +765,7 @@ __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreP
     }
   }
   block_accumulate(sum, floored, P.accum);
+  finish_set(P);
 }
 
 // ---- batched candidate evaluation (BASELINE config 5) ------------------------------------------------
@@ -869,8 +899,10 @@ __global__ void batch_finalize_kernel(const BatchParams B, double* out, const ui
 }
 
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
-__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch) {
+__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
+                                   unsigned long long* flags, int n_flag_words) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_flag_words) flags[i] = 0ull;   // scratch cursor, error flag, overflow counters, tickets, accumulators
   if (i >= n) return;
   const SlotUpdate u = upd[i];
   SlotA a;
@@ -885,27 +917,6 @@ __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* t
   b.pad = 0;
   tab_a[u.store][u.key] = a;
   tab_b[u.store][u.key] = b;
-}
-
-// out[set] = {integer part, fraction in 2^-40 units, floored, -inf terms, nan terms, flags}: re-assembles the
-// 128-bit exact sum of the set from its 32-bit limbs. Both parts are integers below 2^53, exact in a double.
-__global__ void finalize_kernel(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
-                                const uint32_t* ovf_counts) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_sets) return;
-  const unsigned long long* a = accum + (size_t)s * kAccumStride;
-  unsigned __int128 x = 0;
-  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
-  const __int128 v = (__int128)x;
-  const long long ip = (long long)(v >> 40);
-  const unsigned long long fr = (unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
-  double* o = out + (size_t)s * kOutStride;
-  o[0] = (double)ip;
-  o[1] = (double)fr;
-  o[2] = (double)a[4];
-  o[3] = (double)a[5];
-  o[4] = (double)a[6];
-  o[5] = (double)(*error_flag) + 16.0 * (double)ovf_counts[2 * s];   // counters sit in 8-byte slots
 }
 
 // ---- CSR build: arena (key-major) -> rows (read-major) --------------------------------------
@@ -1040,9 +1051,10 @@ int score_grid(int which, int n_items, int sm_count) {
 }
 int overflow_grid(int sm_count) { return sm_count; }
 
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch, cudaStream_t st) {
-  if (n <= 0) return;
-  apply_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(upd, n, tab_a, tab_b, epoch);
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
+                        unsigned long long* flags, int n_flag_words, cudaStream_t st) {
+  const int m = n > n_flag_words ? n : n_flag_words;
+  apply_slots_kernel<<<(m + 255) / 256, 256, 0, st>>>(upd, n, tab_a, tab_b, epoch, flags, n_flag_words);
 }
 
 // e0/e1 bracket the streaming kernel(s) of the set on the launching stream (roofline timing).
@@ -1094,11 +1106,6 @@ void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream
   pacbio_full_kernel<<<grid, kBlock, 0, st>>>(P);
   cudaEventRecord(e1, st);
   pacbio_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P);
-}
-
-void launch_finalize(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
-                     const uint32_t* ovf_counts, cudaStream_t st) {
-  finalize_kernel<<<(n_sets + 31) / 32, 32, 0, st>>>(accum, n_sets, out, error_flag, ovf_counts);
 }
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,

@@ -10,7 +10,8 @@ enum { kGridPairedFull = 0, kGridPairedComplex, kGridPairedTotal, kGridSingleFul
 int score_grid(int which, int n_items, int sm_count);
 int overflow_grid(int sm_count);
 
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch, cudaStream_t st);
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
+                        unsigned long long* flags, int n_flag_words, cudaStream_t st);
 // Each *_full launch is two kernels: the streaming pass (grid blocks -> partial slots [0,grid)) and the
 // many-placement pass (ovf_grid blocks -> partial slots [grid, grid+ovf_grid)).
 // e0 / e1 are recorded on `st` around the streaming kernel(s) of the set (the roofline timing).
@@ -22,8 +23,6 @@ void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int gri
 void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
                         const SideStream& side);
 void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
-void launch_finalize(const unsigned long long* accum, int n_sets, double* out, const uint32_t* error_flag,
-                     const uint32_t* ovf_counts, cudaStream_t st);
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
                       void* rows, void* first, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches);
