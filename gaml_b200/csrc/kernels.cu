@@ -497,14 +497,66 @@ __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P
 
 // FULL, tier 2: the reads that own several records on a mate (list built once per cache commit), one thread
 // each, at most two live placements per mate in registers; anything bigger goes to the scratch path.
+// One record of a tier-2 read placed through the global slot table (word A only).
+struct Placed1 { bool live; bool multi; int walk, pos, edor; };
+__device__ __forceinline__ Placed1 place_row(const ScoreParams& P, int m, const int4& rw, bool present) {
+  Placed1 p;
+  const int4 a = ldg4(P.m[m].slots_a + (present ? rw.x : 0));
+  const uint32_t ef = (uint32_t)a.x;
+  p.live = present && (ef & 0x7fffffffu) == P.epoch;
+  p.multi = p.live && (ef >> 31);
+  p.walk = a.y;
+  p.pos = wrap_add(rw.y, a.z);
+  if (p.pos < a.w) p.live = false;   // graph.cc:577
+  p.edor = rw.z;
+  return p;
+}
+
 __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P) {
   Acc sum = acc_zero();
   unsigned floored = 0;
+  const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
+  const RowShort* rows2 = static_cast<const RowShort*>(P.m[1].crows);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
     const int r = (int)__ldg(P.complex_list + k);
     const uint32_t ll = __ldg(P.clens + k);
+    const uint32_t b1 = __ldg(P.m[0].cptr + k), e1 = __ldg(P.m[0].cptr + k + 1);
+    const uint32_t b2 = __ldg(P.m[1].cptr + k), e2 = __ldg(P.m[1].cptr + k + 1);
+    const int n1 = (int)(e1 - b1), n2 = (int)(e2 - b2);
     double acc = 0.0;
-    if (paired_read<true>(P, k, acc)) {
+    bool done = false, ok = true;
+    if (n1 <= 2 && n2 <= 2) {
+      // Straight-line path for the shapes that make up this tier — (2,1), (1,2), (2,2): at most four candidate
+      // pairs. The state starts from 0 and every walk is "added" here (full evaluation), so with at most two
+      // non-dropped pairs the sum is order independent (0+a+b == 0+b+a); anything that needs the enumeration
+      // order (a de-dup, a repeated key, three or more terms) takes the general register path below.
+      const int4 z = make_int4(0, 0, 0, 0);
+      const int4 rx0 = n1 > 0 ? ldg4(rows1 + b1) : z, rx1 = n1 > 1 ? ldg4(rows1 + b1 + 1) : z;
+      const int4 ry0 = n2 > 0 ? ldg4(rows2 + b2) : z, ry1 = n2 > 1 ? ldg4(rows2 + b2 + 1) : z;
+      const Placed1 x0 = place_row(P, 0, rx0, n1 > 0), x1 = place_row(P, 0, rx1, n1 > 1);
+      const Placed1 y0 = place_row(P, 1, ry0, n2 > 0), y1 = place_row(P, 1, ry1, n2 > 1);
+      const bool need_order = x0.multi || x1.multi || y0.multi || y1.multi ||
+                              (x0.live && x1.live && x0.walk == x1.walk && x0.pos == x1.pos) ||
+                              (y0.live && y1.live && y0.walk == y1.walk && y0.pos == y1.pos);
+      if (!need_order) {
+        const int l1 = ll & 0xffff, l2 = ll >> 16;
+        double t[4];
+        int nt = 0;
+        const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = align_prob(P.m[0], x1.edor, l1);
+        double tt;
+        if (x0.live && y0.live && x0.walk == y0.walk && pair_term(P, x0.pos, x0.edor, y0.pos, y0.edor, l1, l2, px0, tt)) t[nt++] = tt;
+        if (x0.live && y1.live && x0.walk == y1.walk && pair_term(P, x0.pos, x0.edor, y1.pos, y1.edor, l1, l2, px0, tt)) t[nt++] = tt;
+        if (x1.live && y0.live && x1.walk == y0.walk && pair_term(P, x1.pos, x1.edor, y0.pos, y0.edor, l1, l2, px1, tt)) t[nt++] = tt;
+        if (x1.live && y1.live && x1.walk == y1.walk && pair_term(P, x1.pos, x1.edor, y1.pos, y1.edor, l1, l2, px1, tt)) t[nt++] = tt;
+        if (nt <= 2) {
+          if (nt >= 1) acc = __dadd_rn(acc, t[0]);
+          if (nt == 2) acc = __dadd_rn(acc, t[1]);
+          done = true;
+        }
+      }
+    }
+    if (!done) ok = paired_read<true>(P, k, acc);
+    if (ok) {
       P.values[r] = acc;
       acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
     } else {

@@ -274,3 +274,17 @@ def test_batched_candidates_equal_sequential_evaluation(oracle):
         ref = oracle(small, f"batch{i}", dump=False)
         assert abs(probs[i] - ref[-1].score) <= REL_TOTAL * abs(ref[-1].score)
         assert int(tls[i]) == ref[-1].total_len and int(zeros[i, 0, 0]) == ref[-1].zeros[0][0]
+
+
+# ---- BASELINE configs 1 and 3 at their stated sizes ---------------------------------------------------
+def test_config1_single_reads_full_size(oracle):
+    """Config 1: 100 kbp genome, 50 k single-end 100 bp reads; full logL + a scripted trajectory vs the oracle."""
+    wl = synth.single_workload(10, 10000, 50_000, n_evals=40, seed=7)
+    check_against(wl, oracle(wl, "c1"))
+
+
+def test_config3_paired_plus_pacbio_full_size(oracle):
+    """Config 3: the 4.6 Mbp / 2 M-pair set (weight 1.0) plus 46 k PacBio-like 10 kbp reads (weight 0.5)."""
+    wl = synth.mixed_workload(460, 10000, 2_000_000, 46_000, n_evals=3, seed=42, pacbio_len=10000)
+    assert [s.kind for s in wl.sets] == [1, 2] and wl.sets[1].weight == 0.5
+    check_against(wl, oracle(wl, "c3"))
