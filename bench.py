@@ -39,9 +39,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def make_workload(world: int, rank: int, n_evals: int, scale: float = 1.0):
-    """Config 2 per GPU: the genome and read set grow with `world`, each rank generates only its shard."""
+C4 = dict(n_unique=10000, unique_len=10000, n_pairs=50_000_000)
+
+
+def make_workload(world: int, rank: int, n_evals: int, scale: float = 1.0, kind: str = "c2"):
+    """Config 2 per GPU: the genome and read set grow with `world`, each rank generates only its shard.
+    kind="c4shard": BASELINE config 4 (100 Mbp, 50 M pairs) as ONE of eight read-id shards per GPU — rank r of
+    `world` GPUs holds shard r (so --gpus 8 is the whole of config 4, --gpus 1 is one eighth of it)."""
     from gaml_b200 import synth
+    if kind == "c4shard":
+        per = C4["n_pairs"] // 8
+        lo, hi = rank * per, (rank + 1) * per
+        wl = synth.paired_workload(C4["n_unique"], C4["unique_len"], per * world, n_evals=n_evals, seed=44, read_lo=lo, read_hi=hi)
+        return wl, (lo, hi)
     n_pairs_total = int(C2["n_pairs"] * scale) * world
     per = (n_pairs_total + world - 1) // world
     lo, hi = rank * per, min((rank + 1) * per, n_pairs_total)
@@ -240,6 +250,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = config 2)")
     ap.add_argument("--delta-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4shard"], help="c2 (default, BASELINE config 2 per GPU) or one "
+                    "eighth of config 4 per GPU")
     ap.add_argument("--batch", type=int, default=1024, help="candidate moves per gaml_calc_prob_batch launch (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaml_b200" else args.warmup
@@ -283,7 +295,7 @@ def main():
 
     t_gen = time.perf_counter()
     n_evals = 2 + args.delta_steps
-    wl, shard = make_workload(world, rank, n_evals, scale=args.scale)
+    wl, shard = make_workload(world, rank, n_evals, scale=args.scale, kind=args.workload)
     t_gen = time.perf_counter() - t_gen
     pc, t_upload, cache_bytes = load_calculator(wl, shard, local_rank, world, dev)
     log(f"[rank {rank}] workload generated in {t_gen:.1f}s; cache of {cache_bytes / 1e6:.1f} MB inserted+CSR built in {t_upload:.2f}s")
@@ -424,7 +436,8 @@ def main():
         "metric": "alignments_scored_per_s", "value": a_total * args.steps / (dev_ms_max * 1e-3), "unit": "alignments/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
+        "config": {"workload": (WORKLOAD_NAME if args.workload == "c2" else
+                                "C4 shard: synthetic 100 Mbp genome (10000 x ~10 kbp nodes), 6.25 M of 50 M innie read pairs 2x100 bp") + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
                    "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
                    "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
                    "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events on the library stream, max over ranks",
