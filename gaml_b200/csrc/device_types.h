@@ -113,6 +113,11 @@ struct ScoreParams {
   const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
   double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)
   double rcp_two_len;
+  // coverage-gap penalty events (null when the set has penalty_constant == 0)
+  unsigned long long* ev_keys;
+  uint32_t* ev_count;
+  uint32_t ev_cap;
+  const double* cov_thr;     // exp(mps + mppb * 2*len2) indexed by len2 (graph.cc:1855-1857)
   // delta discovery
   const ArenaShort* arena1;
   const TouchRange* touch;

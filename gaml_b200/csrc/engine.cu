@@ -113,6 +113,10 @@ struct ReadSetState {
   // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
   std::vector<Walk> old_walks;
   bool has_state = false;
+  int bad_bases = 0;            // ScoringState::bad_bases (graph.h:614)
+  bool penalty = false;         // paired set with penalty_constant != 0: coverage events are collected
+  DevBuf d_cov_thr, d_ev, d_ev_sorted, d_ev_temp, d_bad;
+  std::vector<int> h_bad;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this set's streaming kernel(s)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // side-stream fork/join for the tier-2 kernel
   ~ReadSetState() {
@@ -127,6 +131,11 @@ struct SetPlan {
   int total_len = 0;
   int64_t records = 0;          // A: live (record, occurrence) pairs in this shard
   int64_t touch_records = 0;
+  int64_t records1 = 0;         // live mate-1 records (bounds the number of pair terms for the coverage events)
+  // coverage-gap penalty (paired sets with penalty_constant != 0)
+  int n_cov_walks = 0, n_type1 = 0;
+  uint32_t ev_cap = 0;
+  size_t type1_off = 0, csbegin_off = 0, cs_off = 0, evcount_off = 0;
   int grid = 0;                 // blocks of the reducing kernel
   int cgrid = 0;                // blocks of the tier-2 (several records per read) kernel
   size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
@@ -246,14 +255,18 @@ struct OccBuilder {
 
 // Paired lookup rule (ReadSet::GetPositionsOnlyPath, graph.cc:535-598) for one walk, both mates.
 void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, int ord, OccBuilder ob[2],
-                         SetPlan& sp, std::vector<TouchRange>* touch) {
+                         SetPlan& sp, std::vector<TouchRange>* touch, std::vector<int>* contig_starts = nullptr) {
   std::vector<Walk> ctgs;
   std::vector<int> gaps;
   split_at_gaps(walk, ctgs, gaps);
   Walk key;
   int cur_len = 0;
+  if (contig_starts) contig_starts->assign(1, 0);   // events (0,1) and (cur_len,1) per later contig, graph.cc:1826, 1835
   for (size_t c = 0; c < ctgs.size(); c++) {
-    if (c > 0) cur_len += gaps[c - 1];
+    if (c > 0) {
+      cur_len += gaps[c - 1];
+      if (contig_starts) contig_starts->push_back(cur_len);
+    }
     const Walk& ctg = ctgs[c];
     int ctg_len = 0;
     for (int m = 0; m < 2; m++) {
@@ -275,6 +288,7 @@ void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk
           if (km.count) {
             ob[m].add(kid[t], ord, cur, skip);
             sp.records += km.count;
+            if (m == 0) sp.records1 += km.count;
             if (m == 0 && touch) touch->push_back(TouchRange{km.arena_off, km.count});
           }
           if (km.any) {
@@ -483,6 +497,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   std::vector<SlotUpdate> updates;
   std::vector<std::vector<Occ>> occs(ctx->stores.size());
   std::vector<std::vector<TouchRange>> touches(n_sets);
+  std::vector<std::vector<std::vector<int>>> cov_cs(n_sets);   // per penalty set: contig starts of every touched walk
 
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
@@ -509,8 +524,15 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       sp.n_erased = (int)erased.size();
       int ord = 0;
       std::vector<TouchRange>* tp = sp.full ? nullptr : &touches[s];
-      for (const Walk& w : erased) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp);
-      for (const Walk& w : added) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp);
+      std::vector<int> cs;
+      for (const Walk& w : erased) {
+        flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+        if (rs.penalty) cov_cs[s].push_back(cs);
+      }
+      for (const Walk& w : added) {
+        flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+        if (rs.penalty) cov_cs[s].push_back(cs);
+      }
       int tl = 0;
       for (const Walk& w : walks) tl += walk_length(ctx, w);   // GetTotalLen, graph.cc:1966
       sp.total_len = tl;
@@ -547,6 +569,22 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     off = align16(off + touches[s].size() * sizeof(TouchRange));
     sp.prefix_off = off;
     off = align16(off + (touches[s].size() + 1) * sizeof(uint32_t));
+    if (rs.penalty) {
+      sp.n_cov_walks = (int)cov_cs[s].size();
+      sp.n_type1 = 0;
+      for (auto& v : cov_cs[s]) sp.n_type1 += (int)v.size();
+      sp.type1_off = off;
+      off = align16(off + (size_t)sp.n_type1 * 8);
+      sp.csbegin_off = off;
+      off = align16(off + ((size_t)sp.n_cov_walks + 1) * 4);
+      sp.cs_off = off;
+      off = align16(off + (size_t)sp.n_type1 * 4);
+      sp.evcount_off = off;
+      off = align16(off + 4);
+      const uint64_t cap = (uint64_t)sp.n_type1 + 4ull * (uint64_t)sp.records1 + 4096ull;
+      if (cap > 0x7fffffffull) return fail(ctx, GAML_ERR_CAPACITY, "too many coverage events for one evaluation");
+      sp.ev_cap = (uint32_t)cap;
+    }
   }
   ctx->blob_bytes = off;
   rc = ensure_pinned(ctx, off);
@@ -566,6 +604,22 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     }
     if (acc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one evaluation");
     pre[touches[s].size()] = (uint32_t)acc;
+    if (ctx->sets[s]->penalty) {
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(hb + sp.type1_off);
+      int* csb = reinterpret_cast<int*>(hb + sp.csbegin_off);
+      int* csv = reinterpret_cast<int*>(hb + sp.cs_off);
+      int k = 0;
+      for (size_t w = 0; w < cov_cs[s].size(); w++) {
+        csb[w] = k;
+        for (int p : cov_cs[s][w]) {
+          keys[k] = ((unsigned long long)(uint32_t)w << 33) | ((unsigned long long)((uint32_t)p ^ 0x80000000u) << 1);
+          csv[k] = p;
+          k++;
+        }
+      }
+      csb[cov_cs[s].size()] = k;
+      *reinterpret_cast<uint32_t*>(hb + sp.evcount_off) = (uint32_t)k;
+    }
   }
   ctx->n_updates = (int)updates.size();
 
@@ -637,6 +691,12 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.log_tab = ctx->d_logtab.p;
   P.two_len_d = (double)P.two_len;
   P.rcp_two_len = 1.0 / P.two_len_d;
+  if (rs.penalty) {
+    P.ev_keys = rs.d_ev.as<unsigned long long>();
+    P.ev_count = reinterpret_cast<uint32_t*>(P.accum + 7);   // spare accumulator word of the set
+    P.ev_cap = sp.ev_cap;
+    P.cov_thr = rs.d_cov_thr.as<double>();
+  }
   P.arena1 = rs.mate[0].arena.as<ArenaShort>();
   P.touch = reinterpret_cast<const TouchRange*>(blob + sp.touch_off);
   P.touch_prefix = reinterpret_cast<const uint32_t*>(blob + sp.prefix_off);
@@ -666,6 +726,18 @@ int launch(gaml_ctx* ctx) {
     const int og = overflow_grid(ctx->sm_count);
     records += sp.records;
     reads += rs.n_local;
+    if (rs.penalty) {
+      // event buffer: padding keys, then the host's contig-start events, then the running count
+      CU(rs.d_ev.reserve((size_t)sp.ev_cap * 8, 0, false, st));
+      CU(rs.d_ev_sorted.reserve((size_t)sp.ev_cap * 8, 0, false, st));
+      CU(rs.d_ev_temp.reserve(std::max<size_t>(coverage_sort_temp_bytes(sp.ev_cap), 256), 0, false, st));
+      CU(rs.d_bad.reserve(std::max<size_t>(sp.n_cov_walks, 1) * 4, 0, false, st));
+      P.ev_keys = rs.d_ev.as<unsigned long long>();
+      CU(cudaMemsetAsync(rs.d_ev.p, 0xff, (size_t)sp.ev_cap * 8, st));
+      CU(cudaMemsetAsync(rs.d_bad.p, 0, std::max<size_t>(sp.n_cov_walks, 1) * 4, st));
+      if (sp.n_type1) CU(cudaMemcpyAsync(rs.d_ev.p, blob + sp.type1_off, (size_t)sp.n_type1 * 8, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(P.ev_count, blob + sp.evcount_off, 4, cudaMemcpyDeviceToDevice, st));
+    }
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
         launch_paired_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
@@ -678,6 +750,13 @@ int launch(gaml_ctx* ctx) {
         launches += sp.touch_records > 0 ? 3 : 1;
         // touched records + the O(R) pass: probs read (8) + packed lengths (4) per pair
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
+      }
+      if (rs.penalty) {
+        CU(launch_coverage(rs.d_ev.as<unsigned long long>(), rs.d_ev_sorted.as<unsigned long long>(), sp.ev_cap, rs.d_ev_temp.p,
+                           rs.d_ev_temp.cap, reinterpret_cast<const int*>(blob + sp.csbegin_off),
+                           reinterpret_cast<const int*>(blob + sp.cs_off), rs.cfg.step,
+                           rs.cfg.insert_mean + 5 * rs.cfg.insert_std, rs.d_bad.as<int>(), ctx->sm_count, st));
+        launches += 3;
       }
     } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
       launch_single_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
@@ -705,6 +784,13 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
   const size_t n_sets = ctx->sets.size();
   if (n_sets > 0) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out.p, n_sets * kOutStride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    if (!rs.penalty) continue;
+    rs.h_bad.assign(std::max(ctx->plan[s].n_cov_walks, 1), 0);
+    if (ctx->plan[s].n_cov_walks)
+      CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, (size_t)ctx->plan[s].n_cov_walks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kOutStride * sizeof(double));
   float ms = 0, ms2 = 0;
@@ -728,6 +814,11 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
     flags |= (uint32_t)(f & 15);
     ovf += (uint32_t)(f >> 4);
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
+      if (rs.penalty) {   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
+        if (ctx->plan[s].full) rs.bad_bases = 0;
+        for (int w = 0; w < ctx->plan[s].n_cov_walks; w++)
+          rs.bad_bases += w < ctx->plan[s].n_erased ? -rs.h_bad[w] : rs.h_bad[w];
+      }
       rs.old_walks = ctx->plan_walks;   // graph.cc:1986: state follows the last EVALUATED walks
       rs.has_state = true;
     }
@@ -740,11 +831,13 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   ctx->stats.last_overflow_reads = (int32_t)ovf;
   if (flags & 1) return fail(ctx, GAML_ERR_CAPACITY, "too many many-placement reads for the overflow list");
   if (flags & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
+  if (flags & 4) return fail(ctx, GAML_ERR_CAPACITY, "coverage-event buffer exhausted");
   return GAML_OK;
 }
 
 int combine_raw(const double* gathered, int n_shards, int n_sets, const int32_t* kinds, const int64_t* n_reads_total,
-                const double* weights, int total_len, gaml_result* result, int32_t* zeros) {
+                const double* weights, int total_len, gaml_result* result, int32_t* zeros,
+                const double* penalty_terms = nullptr) {
   if (!gathered || n_shards < 1 || n_sets < 0 || !result || (n_sets > 0 && (!kinds || !n_reads_total || !weights)))
     return GAML_ERR_ARG;
   std::vector<double> score(n_sets);
@@ -769,6 +862,7 @@ int combine_raw(const double* gathered, int n_shards, int n_sets, const int32_t*
       const int tl = total_len == 0 ? 1 : total_len;
       sc -= log((double)(int)(2u * (unsigned)tl));   // graph.cc:3087
     }
+    if (penalty_terms) sc = sc - penalty_terms[s];   // tp - bad_bases*no_cov_penalty, graph.cc:1742, 1988
     score[s] = sc;
     if (zeros) {
       zeros[2 * s] = (int32_t)fl;
@@ -789,13 +883,15 @@ int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, 
   const size_t n_sets = ctx->sets.size();
   std::vector<int32_t> kinds(n_sets);
   std::vector<int64_t> counts(n_sets);
-  std::vector<double> weights(n_sets);
+  std::vector<double> weights(n_sets), pen(n_sets);
   for (size_t s = 0; s < n_sets; s++) {
     kinds[s] = ctx->sets[s]->cfg.kind;
     counts[s] = ctx->sets[s]->n_total;
     weights[s] = ctx->sets[s]->cfg.weight;
+    pen[s] = ctx->sets[s]->bad_bases * ctx->sets[s]->cfg.penalty_constant;   // int * double like the reference
   }
-  int rc = combine_raw(gathered, n_shards, (int)n_sets, kinds.data(), counts.data(), weights.data(), total_len, result, zeros);
+  int rc = combine_raw(gathered, n_shards, (int)n_sets, kinds.data(), counts.data(), weights.data(), total_len, result, zeros,
+                       pen.data());
   if (rc) return fail(ctx, rc, "bad combine arguments");
   return GAML_OK;
 }
@@ -816,6 +912,7 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
       return fail(ctx, GAML_ERR_UNSUPPORTED, "gaml_calc_prob_batch supports paired read sets only (single / pacbio sets keep no "
                                              "incremental state: every candidate would be a full evaluation)");
     if (!rs->has_state) return fail(ctx, GAML_ERR_STATE, "gaml_calc_prob_batch needs a base state: call gaml_calc_prob first");
+    if (rs->penalty) return fail(ctx, GAML_ERR_UNSUPPORTED, "gaml_calc_prob_batch with penalty_constant != 0 is not supported yet");
   }
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
@@ -1116,9 +1213,14 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   if (!cfg || n_reads_total < 0 || shard_lo < 0 || shard_hi < shard_lo || shard_hi > n_reads_total)
     return fail(ctx, GAML_ERR_ARG, "bad read set shape");
   if (cfg->kind < 0 || cfg->kind > 2) return fail(ctx, GAML_ERR_ARG, "bad read set kind");
-  if (cfg->penalty_constant != 0.0)
-    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0: the coverage-gap penalty (graph.cc:1700-1742, 1893-1919, "
-                                           "3197-3250) is not on the device yet");
+  if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PACBIO)
+    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a pacbio set: the PacBio coverage sweep (graph.cc:3197-3250) "
+                                           "is not on the device yet");
+  if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PAIRED && (shard_lo != 0 || shard_hi != n_reads_total))
+    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a sharded paired set: a walk's coverage events live on "
+                                           "all shards (SURVEY §8e)");
+  // single sets: the reference's sweep never counts a gap (graph.cc:1710-1733: last_event_type is never >= 3), so
+  // bad_bases is identically 0 and the penalty term vanishes whatever penalty_constant is
   const int64_t n_local = shard_hi - shard_lo;
   if (n_local > 0x7fffffff) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^31 reads in one shard");
   if (n_local > 0 && !read_len1) return fail(ctx, GAML_ERR_ARG, "read_len1 is NULL");
@@ -1197,6 +1299,13 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     for (int d = 0; d < rs.ins_n; d++) ins[d] = insert_pdf((double)d, cfg->insert_mean, cfg->insert_std);
     CU(rs.d_ins.reserve(ins.size() * 8, 0, false, ctx->stream));
     CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (paired && cfg->penalty_constant != 0.0) {
+    rs.penalty = true;
+    std::vector<double> cthr(rs.max_len[1] + 1);
+    for (int l = 0; l <= rs.max_len[1]; l++) cthr[l] = exp(cfg->min_prob_start + cfg->min_prob_per_base * (l + l));   // graph.cc:1855-1857
+    CU(rs.d_cov_thr.reserve(cthr.size() * 8, 0, false, ctx->stream));
+    CU(cudaMemcpyAsync(rs.d_cov_thr.p, cthr.data(), cthr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaEventCreateWithFlags(&rs.ev_fork, cudaEventDisableTiming));
@@ -1409,6 +1518,7 @@ int gaml_reset_state(gaml_ctx* ctx) {
   for (auto& rs : ctx->sets) {
     rs->has_state = false;
     rs->old_walks.clear();
+    rs->bad_bases = 0;
   }
   return GAML_OK;
 }

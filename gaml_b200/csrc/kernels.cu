@@ -11,6 +11,7 @@
 // two live placements per mate (virtually all) are finished in registers; the rest are appended to a
 // per-set list and replayed by a second, dense kernel from a scratch arena, so the streaming kernel
 // never carries the general sort/de-dup code through its warps.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.h"
@@ -260,7 +261,24 @@ __device__ __forceinline__ double align_prob(const MateView& mv, int edor, int l
 }
 
 // One (x, y) combination of graph.cc:1861-1889; returns false when the orientation/order filter drops it.
-__device__ __forceinline__ bool pair_term(const ScoreParams& P, int xpos, int xedor, int ypos, int yedor, int l1,
+// Coverage-gap penalty input (graph.cc:1883-1888): a pair whose term exceeds exp(mps + mppb*2*len2) marks both of
+// its positions as "covered" in its walk. Events are appended as sortable keys walk<<33 | (pos ^ 2^31)<<1 | 1.
+__device__ __forceinline__ unsigned long long cov_key(int walk, int pos, int type3) {
+  return ((unsigned long long)(uint32_t)walk << 33) | ((unsigned long long)((uint32_t)pos ^ 0x80000000u) << 1) |
+         (unsigned long long)type3;
+}
+__device__ __forceinline__ void emit_cov(const ScoreParams& P, int walk, int xpos, int ypos, int l2, double term) {
+  if (!P.ev_keys || walk < 0 || !(term > __ldg(P.cov_thr + l2))) return;
+  const unsigned i = atomicAdd(P.ev_count, 2u);
+  if (i + 2u > P.ev_cap) {
+    atomicOr(P.error_flag, 4u);
+    return;
+  }
+  P.ev_keys[i] = cov_key(walk, max(xpos, ypos), 1);
+  P.ev_keys[i + 1] = cov_key(walk, min(xpos, ypos), 1);   // use_all_to_cov is always true here (prob_calculator.h:93)
+}
+
+__device__ __forceinline__ bool pair_term(const ScoreParams& P, int walk, int xpos, int xedor, int ypos, int yedor, int l1,
                                           int l2, double p1, double& term) {
   const int xo = (xedor >> 30) & 1, yo = (yedor >> 30) & 1;
   if (xo == yo) return false;
@@ -275,6 +293,7 @@ __device__ __forceinline__ bool pair_term(const ScoreParams& P, int xpos, int xe
   const double p2 = align_prob(P.m[1], yedor, l2);
   const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
   term = __dmul_rn(__dmul_rn(p1, p2), ins);
+  emit_cov(P, walk, xpos, ypos, l2, term);
   return true;
 }
 
@@ -320,7 +339,7 @@ __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, i
                                          int l2, double p1, double& acc) {
   if (xw != yw) return;
   double t;
-  if (pair_term(P, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  if (pair_term(P, xw, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
 }
 
 // Per-read paired update for reads with <= 2 live placements per mate. For lists sorted in enumeration
@@ -452,6 +471,7 @@ __device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const in
   }
   const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
   const double t = __dmul_rn(__dmul_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2)), ins);   // (p1*p2)*ins, graph.cc:1889
+  emit_cov(P, o1.y, p1, p2, l2, t);
   acc = (o1.y < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
   return true;
 }
@@ -525,7 +545,7 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
     const int n1 = (int)(e1 - b1), n2 = (int)(e2 - b2);
     double acc = 0.0;
     bool done = false, ok = true;
-    if (n1 <= 2 && n2 <= 2) {
+    if (n1 <= 2 && n2 <= 2 && !P.ev_keys) {   // (coverage events are emitted by the general path only)
       // Straight-line path for the shapes that make up this tier — (2,1), (1,2), (2,2): at most four candidate
       // pairs. The state starts from 0 and every walk is "added" here (full evaluation), so with at most two
       // non-dropped pairs the sum is order independent (0+a+b == 0+b+a); anything that needs the enumeration
@@ -544,10 +564,10 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
         int nt = 0;
         const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = align_prob(P.m[0], x1.edor, l1);
         double tt;
-        if (x0.live && y0.live && x0.walk == y0.walk && pair_term(P, x0.pos, x0.edor, y0.pos, y0.edor, l1, l2, px0, tt)) t[nt++] = tt;
-        if (x0.live && y1.live && x0.walk == y1.walk && pair_term(P, x0.pos, x0.edor, y1.pos, y1.edor, l1, l2, px0, tt)) t[nt++] = tt;
-        if (x1.live && y0.live && x1.walk == y0.walk && pair_term(P, x1.pos, x1.edor, y0.pos, y0.edor, l1, l2, px1, tt)) t[nt++] = tt;
-        if (x1.live && y1.live && x1.walk == y1.walk && pair_term(P, x1.pos, x1.edor, y1.pos, y1.edor, l1, l2, px1, tt)) t[nt++] = tt;
+        if (x0.live && y0.live && x0.walk == y0.walk && pair_term(P, -1, x0.pos, x0.edor, y0.pos, y0.edor, l1, l2, px0, tt)) t[nt++] = tt;
+        if (x0.live && y1.live && x0.walk == y1.walk && pair_term(P, -1, x0.pos, x0.edor, y1.pos, y1.edor, l1, l2, px0, tt)) t[nt++] = tt;
+        if (x1.live && y0.live && x1.walk == y0.walk && pair_term(P, -1, x1.pos, x1.edor, y0.pos, y0.edor, l1, l2, px1, tt)) t[nt++] = tt;
+        if (x1.live && y1.live && x1.walk == y1.walk && pair_term(P, -1, x1.pos, x1.edor, y1.pos, y1.edor, l1, l2, px1, tt)) t[nt++] = tt;
         if (nt <= 2) {
           if (nt >= 1) acc = __dadd_rn(acc, t[0]);
           if (nt == 2) acc = __dadd_rn(acc, t[1]);
@@ -950,6 +970,36 @@ __global__ void batch_finalize_kernel(const BatchParams B, double* out, const ui
   o[5] = (double)(*error_flag);
 }
 
+// ---- coverage-gap penalty of paired sets (graph.cc:1893-1919) ----------------------------------------
+// Events sorted by (walk, position, type): contig starts (type 1, host supplied) and covered positions (type 3).
+// bad_bases(walk) = sum over type-3 events whose distance to the PREVIOUS event of the walk exceeds `step`, when that
+// previous event is also type 3 (or the walk has no previous event) and the position is further than
+// insert_mean + 5 insert_std from the last contig start. Every event only looks at its predecessor, so the sweep is
+// one independent thread per event after the sort.
+__global__ void coverage_sweep_kernel(const unsigned long long* keys, unsigned n, const int* cs_begin, const int* cs,
+                                      double step, double min_from_start, int* bad) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    if (k == ~0ull || !(k & 1ull)) continue;   // padding or a contig start
+    const int walk = (int)(k >> 33);
+    const int pos = (int)(((uint32_t)(k >> 1)) ^ 0x80000000u);
+    int prev_pos = 0, prev_type = -1;
+    if (i > 0) {
+      const unsigned long long p = keys[i - 1];
+      if ((int)(p >> 33) == walk) {
+        prev_pos = (int)(((uint32_t)(p >> 1)) ^ 0x80000000u);
+        prev_type = (p & 1ull) ? 3 : 1;
+      }
+    }
+    int last_begin = 0;
+    for (int t = cs_begin[walk]; t < cs_begin[walk + 1]; t++) {   // contig starts of the walk, ascending (few)
+      if (cs[t] <= pos) last_begin = cs[t]; else break;
+    }
+    if ((double)(pos - prev_pos) > step && (prev_type == 3 || prev_type < 0) && (double)(pos - last_begin) > min_from_start)
+      atomicAdd(bad + walk, pos - prev_pos);
+  }
+}
+
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                                    unsigned long long* flags, int n_flag_words) {
@@ -1257,6 +1307,22 @@ void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_r
   }
   if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
   batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag);
+}
+
+size_t coverage_sort_temp_bytes(unsigned n) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, need, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)n);
+  return need;
+}
+
+cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long long* keys_sorted, unsigned n, void* temp,
+                            size_t temp_bytes, const int* cs_begin, const int* cs, double step, double min_from_start, int* bad,
+                            int sm_count, cudaStream_t st) {
+  size_t need = temp_bytes;
+  cudaError_t err = cub::DeviceRadixSort::SortKeys(temp, need, keys_in, keys_sorted, (int)n, 0, 64, st);
+  if (err != cudaSuccess) return err;
+  coverage_sweep_kernel<<<grid_for(n, 256, sm_count, 8), 256, 0, st>>>(keys_sorted, n, cs_begin, cs, step, min_from_start, bad);
+  return cudaGetLastError();
 }
 
 size_t csr_temp_bytes(int n_reads) {

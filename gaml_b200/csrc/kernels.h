@@ -35,6 +35,11 @@ cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* ro
 // Batched candidate evaluation of one paired set: base pass per distinct total length, touched-read pass, finalize.
 void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
                   int sm_count, cudaStream_t st);
+// Coverage-gap penalty of one paired set: radix sort of the event keys, then the one-thread-per-event sweep.
+size_t coverage_sort_temp_bytes(unsigned n);
+cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long long* keys_sorted, unsigned n, void* temp,
+                            size_t temp_bytes, const int* cs_begin, const int* cs, double step, double min_from_start, int* bad,
+                            int sm_count, cudaStream_t st);
 size_t csr_temp_bytes(int n_reads);
 
 }  // namespace gaml

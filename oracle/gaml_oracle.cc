@@ -61,6 +61,7 @@ struct ReadSetData {
   // paired state (graph.h:612-619)
   std::vector<Walk> old_walks;
   std::vector<double> probs;
+  int bad_bases = 0;
   // last per-read values (for dumps)
   std::vector<double> last;
 };
@@ -182,7 +183,9 @@ double ScoreSingle(const Graph& g, ReadSetData& rs, const std::vector<Walk>& wal
   for (int r = 0; r < rs.n_reads; r++)
     for (const Placed& q : at[r]) p[r] += rs.pow_mismatch[0][q.ed] * rs.pow_match[0][rs.len[0][r] - q.ed];
   *total_len = tl;
-  return MeanLogWithFloor(p, tl, rs, false, floored);  // penalty_constant*bad_bases: 0 in scope
+  // Coverage penalty of single reads: the reference's sweep (graph.cc:1710-1733) only counts a gap when
+  // last_event_type >= 3, and that variable is only ever assigned 1 or a negative type — bad_bases is identically 0.
+  return MeanLogWithFloor(p, tl, rs, false, floored) - 0 * rs.penalty;
 }
 
 // ---- paired reads, incremental (graph.cc:1745-1989) ----------------------------------------
@@ -218,14 +221,20 @@ void GatherWalkMate(const Graph& g, const ReadSetData& rs, int m, const Walk& ct
   }
 }
 
-void WalkPairTerms(const Graph& g, const ReadSetData& rs, const Walk& w, const std::vector<double>& ins_tab,
-                   std::vector<std::pair<int, double>>& terms) {  // graph.cc:1794-1892
+// Returns the walk's bad_bases (coverage-gap sweep, graph.cc:1893-1919); use_all_to_cov is always true on
+// this path (prob_calculator.h:93).
+int WalkPairTerms(const Graph& g, const ReadSetData& rs, const Walk& w, const std::vector<double>& ins_tab,
+                  std::vector<std::pair<int, double>>& terms) {  // graph.cc:1794-1892
   std::vector<int> gaps;
   std::vector<Walk> ctgs = SplitAtGaps(w, &gaps);
   std::unordered_map<int, std::vector<Placed>> at1, at2;
+  std::vector<std::pair<int, int>> events(1, std::make_pair(0, 1));   // (position, type): 1 = contig start, 3 = pair
   int cur = 0;
   for (size_t c = 0; c < ctgs.size(); c++) {
-    if (c > 0) cur += gaps[c - 1];
+    if (c > 0) {
+      cur += gaps[c - 1];
+      events.push_back(std::make_pair(cur, 1));   // graph.cc:1835
+    }
     GatherWalkMate(g, rs, 0, ctgs[c], cur, at1);
     GatherWalkMate(g, rs, 1, ctgs[c], cur, at2);
     cur += WalkLength(g, ctgs[c]);
@@ -235,6 +244,7 @@ void WalkPairTerms(const Graph& g, const ReadSetData& rs, const Walk& w, const s
     if (f == at2.end()) continue;
     int r = e.first;
     int l1 = rs.len[0][r], l2 = rs.len[1][r];
+    double cov_thr = exp(rs.mps + rs.mppb * (l2 + l2));   // mate-2 length twice, graph.cc:1855-1857
     for (const Placed& x : e.second) {
       double p1 = rs.pow_mismatch[0][x.ed] * rs.pow_match[0][l1 - x.ed];
       for (const Placed& y : f->second) {
@@ -249,10 +259,25 @@ void WalkPairTerms(const Graph& g, const ReadSetData& rs, const Walk& w, const s
           d = x.pos - y.pos + l1;
         }
         double ins = ((size_t)d < ins_tab.size()) ? ins_tab[d] : InsertPdf(d, rs.ins_mean, rs.ins_std);
+        if (p1 * p2 * ins > cov_thr) {   // graph.cc:1883-1888
+          events.push_back(std::make_pair(std::max(x.pos, y.pos), 3));
+          events.push_back(std::make_pair(std::min(x.pos, y.pos), 3));
+        }
         terms.push_back(std::make_pair(r, p1 * p2 * ins));
       }
     }
   }
+  std::sort(events.begin(), events.end());
+  int bad = 0, last_pos = 0, last_type = -1, last_begin = 0;
+  for (auto& ev : events) {   // graph.cc:1901-1919; exp_cov_move is the set's `step`
+    if (ev.second == 3 && ev.first - last_pos > rs.step && (last_type == 3 || last_type < 0) &&
+        ev.first - last_begin > rs.ins_mean + 5 * rs.ins_std)
+      bad += ev.first - last_pos;
+    if (ev.second == 1) last_begin = ev.first;
+    last_pos = ev.first;
+    last_type = ev.second;
+  }
+  return bad;
 }
 
 double ScorePaired(const Graph& g, ReadSetData& rs, const std::vector<Walk>& walks, int* floored, int* total_len) {
@@ -271,14 +296,14 @@ double ScorePaired(const Graph& g, ReadSetData& rs, const std::vector<Walk>& wal
   std::vector<double> ins_tab((int)(rs.ins_mean + 5 * rs.ins_std));  // graph.cc:1801-1804
   for (size_t i = 0; i < ins_tab.size(); i++) ins_tab[i] = InsertPdf((double)i, rs.ins_mean, rs.ins_std);
   std::vector<std::pair<int, double>> minus, plus;
-  for (const Walk& w : erased) WalkPairTerms(g, rs, w, ins_tab, minus);
-  for (const Walk& w : added) WalkPairTerms(g, rs, w, ins_tab, plus);
+  for (const Walk& w : erased) rs.bad_bases -= WalkPairTerms(g, rs, w, ins_tab, minus);   // graph.cc:1938
+  for (const Walk& w : added) rs.bad_bases += WalkPairTerms(g, rs, w, ins_tab, plus);     // graph.cc:1946
   for (auto& t : minus) rs.probs[t.first] -= t.second;  // graph.cc:1936-1942
   for (auto& t : plus) rs.probs[t.first] += t.second;   // graph.cc:1944-1950
   rs.old_walks = walks;                                 // graph.cc:1986
   rs.last = rs.probs;
   *total_len = tl;
-  return MeanLogWithFloor(rs.probs, tl, rs, true, floored);
+  return MeanLogWithFloor(rs.probs, tl, rs, true, floored) - rs.bad_bases * rs.penalty;   // graph.cc:1988
 }
 
 // ---- PacBio (graph.cc:3171-3261, 2410-2503, 3052-3088; logdouble.hpp:21-31) ----------------
@@ -343,6 +368,7 @@ struct Calculator {
     for (auto& s : sets) {
       s.old_walks.clear();
       s.probs.clear();
+      s.bad_bases = 0;
     }
   }
   double CalcProb(const std::vector<Walk>& walks, std::vector<std::pair<int, int>>& zeros, int& total_len) {

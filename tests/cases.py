@@ -156,7 +156,15 @@ def golden_cases():
         "synth_single": synth.single_workload(8, 1500, 600, n_evals=14, seed=21),
         "synth_paired": synth.paired_workload(10, 1800, 900, n_evals=24, seed=22),
         "synth_mixed": synth.mixed_workload(8, 5000, 600, 80, n_single=300, n_evals=12, seed=23, pacbio_len=4000),
+        "synth_paired_penalty": _with_penalty(synth.paired_workload(12, 2500, 350, n_evals=30, seed=24)),
     }
+
+
+def _with_penalty(wl: Workload) -> Workload:
+    """Sparse coverage + penalty_constant: exercises the coverage-gap sweep (example.cfg:13-14 style settings)."""
+    wl.sets[0].penalty_constant = 0.00007
+    wl.sets[0].step = wl.sets[0].insert_mean - 30.0
+    return wl
 
 
 def seeded_cases():

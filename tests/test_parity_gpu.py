@@ -81,10 +81,10 @@ def test_error_behaviour():
     bad["read_id"] = 10 ** 6
     with pytest.raises(api.GamlError, match="read_id"):
         pc.cache_insert(0, 0, (6, 4), bad)
-    spec = wl.sets[0]
-    spec.penalty_constant = 0.1
+    pb = workload.read_workload(os.path.join(GOLDEN, "hand_pacbio.wl")).sets[0]
+    pb.penalty_constant = 0.1          # the PacBio coverage sweep is the one penalty not on the device yet
     with pytest.raises(api.GamlError, match="penalty_constant"):
-        pc.add_readset(spec)
+        pc.add_readset(pb)
     # the context is still usable after rejected calls
     prob, _, _ = pc.calc_prob(wl.evals[0])
     ref = workload.read_results(os.path.join(GOLDEN, "hand_paired.ref.res"))
@@ -288,3 +288,27 @@ def test_config3_paired_plus_pacbio_full_size(oracle):
     wl = synth.mixed_workload(460, 10000, 2_000_000, 46_000, n_evals=3, seed=42, pacbio_len=10000)
     assert [s.kind for s in wl.sets] == [1, 2] and wl.sets[1].weight == 0.5
     check_against(wl, oracle(wl, "c3"))
+
+
+# ---- coverage-gap penalty ----------------------------------------------------------------
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_paired_coverage_penalty_matches_oracle(seed, oracle):
+    """penalty_constant != 0 on a sparsely covered genome: the per-walk bad_bases sweep (graph.cc:1893-1919) and its
+    incremental bookkeeping (graph.cc:1938, 1946, 1988) must reproduce the oracle's scores; per-read state stays
+    bit-exact. The same trajectory without penalty must differ (the penalty is really exercised)."""
+    wl = synth.paired_workload(14, 2500, 400, n_evals=40, seed=seed)
+    plain = oracle(wl, f"nopen{seed}")
+    wl.sets[0].penalty_constant = 0.00007
+    wl.sets[0].step = 300.0 - 30.0          # gaml.cc:860: step = insert_mean - penalty_step
+    ref = oracle(wl, f"pen{seed}")
+    assert any(a.score != b.score for a, b in zip(plain, ref))
+    check_against(wl, ref)
+
+
+def test_single_set_penalty_is_a_no_op_like_the_reference(oracle):
+    wl = synth.single_workload(10, 2500, 3000, n_evals=12, seed=5)
+    plain = oracle(wl, "s_nopen")
+    wl.sets[0].penalty_constant = 0.0001
+    ref = oracle(wl, "s_pen")
+    assert [r.score for r in plain] == [r.score for r in ref]      # graph.cc:1710-1733 never counts a gap
+    check_against(wl, ref)
