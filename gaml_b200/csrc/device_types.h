@@ -105,6 +105,8 @@ struct ScoreParams {
   // static tier-2 list (reads owning several records on a mate), built at cache commit
   const uint32_t* complex_list;
   const uint32_t* clens;     // lens[] gathered in list order
+  const void* cdesc;         // int4 per listed read {read, packed lengths, first compact row mate 1, mate 2}
+  int32_t class_begin[17];   // first list index of every record-count class min(cnt1,3)*4 + min(cnt2,3)
   int32_t n_complex;
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
   unsigned long long* accum;

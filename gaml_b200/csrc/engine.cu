@@ -105,7 +105,8 @@ struct ReadSetState {
   int max_len[2] = {0, 0};
   std::vector<int32_t> len[2];
   MateStore mate[2];
-  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens;
+  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
+  int32_t class_begin[17] = {0};
   int n_complex = 0;
   bool complex_dirty = true;
   int ins_n = 0;
@@ -442,7 +443,7 @@ int commit(gaml_ctx* ctx) {
       uint32_t n_complex = 0;
       CU(build_complex_list(rs.mate[0].first.p, rs.n_mates == 2 ? rs.mate[1].first.p : nullptr, rs.n_local, flags,
                             rs.d_complex.as<uint32_t>(), ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->stream, &launches,
-                            &n_complex));
+                            &n_complex, rs.class_begin));
       ctx->stats.kernel_launches += launches;
       launches = 0;
       rs.n_complex = (int)n_complex;
@@ -461,6 +462,11 @@ int commit(gaml_ctx* ctx) {
         CU(compact_copy(rs.d_complex.as<uint32_t>(), rs.n_complex, st.rowptr.as<uint32_t>(), st.cptr.as<uint32_t>(), st.rows.p,
                         st.crows.p, ctx->stream, &launches));
       }
+      CU(rs.d_cdesc.reserve(std::max<size_t>(n_complex, 1) * 16, 0, false, ctx->stream));
+      launch_cdesc_fill(rs.d_complex.as<uint32_t>(), rs.n_complex, rs.d_lens.as<uint32_t>(), rs.mate[0].cptr.as<uint32_t>(),
+                        rs.n_mates == 2 ? rs.mate[1].cptr.as<uint32_t>() : nullptr, rs.d_cdesc.p, ctx->stream);
+      launches++;
+      CU(cudaStreamSynchronize(ctx->stream));
       ctx->stats.kernel_launches += launches;
       rs.complex_dirty = false;
     }
@@ -683,6 +689,8 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.scratch_cap = ctx->scratch_entries;
   P.complex_list = rs.d_complex.as<uint32_t>();
   P.clens = rs.d_clens.as<uint32_t>();
+  P.cdesc = rs.d_cdesc.p;
+  memcpy(P.class_begin, rs.class_begin, sizeof(P.class_begin));
   P.n_complex = rs.n_complex;
   const size_t ns = std::max<size_t>(ctx->sets.size(), 1);
   P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);

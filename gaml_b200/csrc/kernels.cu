@@ -58,47 +58,44 @@ __device__ __forceinline__ void acc_add(Acc& a, double t) {
 
 // Block-wide exact sum -> per-set global accumulators {limb0..3 (32-bit limbs in u64), floored, neginf, bad}.
 // Warp level: the 128-bit value is cut into eight 16-bit chunks, each summed over the warp by one redux.sync
-// (sum < 2^21), lane 0 re-assembles modulo 2^128 (two's complement, so negatives just work); block level:
-// 32-bit limbs through shared-memory u64 atomics; grid level: one set of global u64 atomics per block.
+// (sum < 2^21); block level: the chunk sums meet in shared u32 counters and thread 0 re-assembles them modulo 2^128
+// (two's complement, so negatives just work); grid level: four 32-bit limbs by global u64 atomics per block.
 // Integer addition commutes, so the atomics do not make the result order dependent.
 __device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long long* accum) {
-  __shared__ unsigned long long sm[7];
-  if (threadIdx.x < 7) sm[threadIdx.x] = 0ull;
+  __shared__ unsigned sm[11];   // eight 16-bit-chunk sums (< 2^21 per warp, < 2^26 per block), floored, -inf, nan
+  if (threadIdx.x < 11) sm[threadIdx.x] = 0u;
   __syncthreads();
   const unsigned w[4] = {(unsigned)a.lo, (unsigned)(a.lo >> 32), (unsigned)(unsigned long long)a.hi,
                          (unsigned)((unsigned long long)a.hi >> 32)};
-  unsigned s[8];
+  unsigned s[11];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     s[2 * j] = __reduce_add_sync(0xffffffffu, w[j] & 0xffffu);
     s[2 * j + 1] = __reduce_add_sync(0xffffffffu, w[j] >> 16);
   }
-  const unsigned fl = __reduce_add_sync(0xffffffffu, floored);
-  const unsigned ni = __reduce_add_sync(0xffffffffu, a.neginf);
-  const unsigned bd = __reduce_add_sync(0xffffffffu, a.bad);
-  if ((threadIdx.x & 31) == 0) {
-    unsigned __int128 x = 0;
+  s[8] = __reduce_add_sync(0xffffffffu, floored);
+  s[9] = __reduce_add_sync(0xffffffffu, a.neginf);
+  s[10] = __reduce_add_sync(0xffffffffu, a.bad);
+  const int lane = threadIdx.x & 31;
+  if (lane < 11) {   // lane j publishes chunk j: one shared atomic per lane instead of a 128-bit re-assembly per warp
+    unsigned v = s[0];
 #pragma unroll
-    for (int j = 0; j < 8; j++) x += (unsigned __int128)s[j] << (16 * j);
-#pragma unroll
-    for (int j = 0; j < 4; j++) atomicAdd(&sm[j], (unsigned long long)(unsigned)(x >> (32 * j)));
-    if (fl) atomicAdd(&sm[4], (unsigned long long)fl);
-    if (ni) atomicAdd(&sm[5], (unsigned long long)ni);
-    if (bd) atomicAdd(&sm[6], (unsigned long long)bd);
+    for (int j = 1; j < 11; j++) v = lane == j ? s[j] : v;
+    if (v) atomicAdd(&sm[lane], v);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned __int128 x = 0;
+    unsigned __int128 x = 0;   // sum of chunk_j << 16j modulo 2^128 (two's complement: negatives just work)
 #pragma unroll
-    for (int j = 0; j < 4; j++) x += (unsigned __int128)sm[j] << (32 * j);
+    for (int j = 0; j < 8; j++) x += (unsigned __int128)sm[j] << (16 * j);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const unsigned long long limb = (unsigned long long)(unsigned)(x >> (32 * j));
       if (limb) atomicAdd(accum + j, limb);
     }
-    if (sm[4]) atomicAdd(accum + 4, sm[4]);
-    if (sm[5]) atomicAdd(accum + 5, sm[5]);
-    if (sm[6]) atomicAdd(accum + 6, sm[6]);
+    if (sm[8]) atomicAdd(accum + 4, (unsigned long long)sm[8]);
+    if (sm[9]) atomicAdd(accum + 5, (unsigned long long)sm[9]);
+    if (sm[10]) atomicAdd(accum + 6, (unsigned long long)sm[10]);
   }
 }
 
@@ -130,9 +127,14 @@ __device__ void finish_set(const ScoreParams& P) {
 // log(v) for positive normal finite v from a 128-entry table {1/c, -log(1/c)} (host-built in long double,
 // engine.cu): v = 2^k z, z in [0.6875, 1.375); r = z*invc - 1 (one fma, |r| < 2^-7); log v = k ln2 + logc + log1p(r)
 // with a degree-7 Taylor polynomial (truncation < 2e-19). About 1 ulp; everything else falls back to log().
+// Rare paths kept out of line so the compiler cannot if-convert them into the hot loops (ncu showed the IEEE
+// division being issued, predicated off, on every iteration when it was inline).
+__device__ __noinline__ double slow_log(double v) { return log(v); }
+__device__ __noinline__ double slow_div(double p, double d) { return __ddiv_rn(p, d); }
+
 __device__ __forceinline__ double table_log(const double2* __restrict__ tab, double v) {
   const long long ix = __double_as_longlong(v);
-  if ((unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) return log(v);   // 0, denormal, inf, nan, < 0
+  if ((unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) return slow_log(v);   // 0, denormal, inf, nan, < 0
   const long long tmp = ix - 0x3fe6000000000000ll;
   const int i = (int)((tmp >> 45) & 127);
   const long long k = tmp >> 52;
@@ -156,7 +158,7 @@ __device__ __forceinline__ double floored_term(const ScoreParams& P, const doubl
                                                unsigned& floored) {
   double q = __dmul_rn(p, P.rcp_two_len);
   q = fma(fma(-q, P.two_len_d, p), P.rcp_two_len, q);
-  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = __ddiv_rn(p, P.two_len_d);
+  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = slow_div(p, P.two_len_d);
   if (q < thr) { floored++; q = thr; }
   return table_log(log_tab, q);
 }
@@ -538,11 +540,18 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
   const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
   const RowShort* rows2 = static_cast<const RowShort*>(P.m[1].crows);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
-    const int r = (int)__ldg(P.complex_list + k);
-    const uint32_t ll = __ldg(P.clens + k);
-    const uint32_t b1 = __ldg(P.m[0].cptr + k), e1 = __ldg(P.m[0].cptr + k + 1);
-    const uint32_t b2 = __ldg(P.m[1].cptr + k), e2 = __ldg(P.m[1].cptr + k + 1);
-    const int n1 = (int)(e1 - b1), n2 = (int)(e2 - b2);
+    // one coalesced 16-byte descriptor per listed read {read, packed lengths, first row mate 1, first row mate 2}; the
+    // record counts follow from the read's class (the list is class ordered), so nothing else is loaded before the rows
+    const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);
+    const int r = dsc.x;
+    const uint32_t ll = (uint32_t)dsc.y;
+    const uint32_t b1 = (uint32_t)dsc.z, b2 = (uint32_t)dsc.w;
+    int cls = 0;
+#pragma unroll
+    for (int c = 1; c < 16; c++) cls += (k >= P.class_begin[c]) ? 1 : 0;   // class_begin[c] = first list index of class c
+    int n1 = cls >> 2, n2 = cls & 3;                                       // class id = min(cnt1,3)*4 + min(cnt2,3)
+    if (n1 == 3) n1 = (int)(__ldg(P.m[0].cptr + k + 1) - b1);
+    if (n2 == 3) n2 = (int)(__ldg(P.m[1].cptr + k + 1) - b2);
     double acc = 0.0;
     bool done = false, ok = true;
     if (n1 <= 2 && n2 <= 2 && !P.ev_keys) {   // (coverage events are emitted by the general path only)
@@ -849,7 +858,7 @@ __device__ __forceinline__ double floored_term_at(const double2* log_tab, double
                                                   int& floored) {
   double q = __dmul_rn(p, rcp);
   q = fma(fma(-q, d, p), rcp, q);
-  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = __ddiv_rn(p, d);
+  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = slow_div(p, d);
   floored = 0;
   if (q < thr) { floored = 1; q = thr; }
   return table_log(log_tab, q);
@@ -1109,6 +1118,14 @@ __global__ void compact_count_kernel(const uint32_t* list, int n_complex, const 
   cptr[k] = c;
 }
 
+__global__ void cdesc_fill_kernel(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1,
+                                  const uint32_t* cptr2, int4* desc) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_complex) return;
+  const uint32_t r = list[k];
+  desc[k] = make_int4((int)r, (int)lens[r], (int)cptr1[k], cptr2 ? (int)cptr2[k] : 0);
+}
+
 __global__ void compact_copy_kernel(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr,
                                     const int4* rows, int4* crows) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1245,7 +1262,8 @@ cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_
 // Builds the static tier-2 list; flags must hold n_reads + 1 uint32 (scratch), list n_reads uint32. The number
 // of listed reads is left in flags[n_reads] (exclusive scan total).
 cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
-                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out) {
+                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out,
+                               int32_t* class_begin /* 17 */) {
   // The list is ordered by (record-count class, read id): warps of the tier-2 kernel then hold reads of one shape
   // — (2,1), (1,2), (2,2), ... — and do not execute each other's paths. One flag/scan/scatter pass per class.
   const int g = (n_reads + 1 + 255) / 256;
@@ -1255,7 +1273,9 @@ cudaError_t build_complex_list(const void* first1, const void* first2, int n_rea
   cub::DeviceScan::ExclusiveSum(nullptr, need, flags, flags, n_reads + 1, st);
   if (need > temp_bytes) return cudaErrorMemoryAllocation;
   uint32_t base = 0;
+  class_begin[0] = 0;
   for (int cls = 1; cls <= 16; cls++) {
+    class_begin[cls - 1] = (int32_t)base;   // kernel-side class id = cls - 1 = min(cnt1,3)*4 + min(cnt2,3)
     complex_flags_kernel<<<g, 256, 0, st>>>(f1, f2, n_reads, flags, cls);
     cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, flags, flags, n_reads + 1, st);
     if (err != cudaSuccess) return err;
@@ -1271,6 +1291,7 @@ cudaError_t build_complex_list(const void* first1, const void* first2, int n_rea
       base += cnt;
     }
   }
+  class_begin[16] = (int32_t)base;
   *n_complex_out = base;
   return cudaGetLastError();
 }
@@ -1307,6 +1328,12 @@ void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_r
   }
   if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
   batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag);
+}
+
+void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,
+                       void* desc, cudaStream_t st) {
+  if (n_complex > 0)
+    cdesc_fill_kernel<<<(n_complex + 255) / 256, 256, 0, st>>>(list, n_complex, lens, cptr1, cptr2, static_cast<int4*>(desc));
 }
 
 size_t coverage_sort_temp_bytes(unsigned n) {

@@ -27,7 +27,10 @@ void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
                       void* rows, void* first, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches);
 cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
-                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out);
+                               void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out,
+                               int32_t* class_begin);
+void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,
+                       void* desc, cudaStream_t st);
 cudaError_t compact_offsets(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr, const uint32_t* lens,
                             uint32_t* clens, void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
 cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* rowptr, const uint32_t* cptr, const void* rows,
