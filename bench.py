@@ -341,6 +341,7 @@ def main():
     st = pc.stats()
     launches = st.kernel_launches - launches0
     a_local, bytes_local = st.last_records_gathered, st.last_algorithmic_bytes
+    full_overflow_reads = int(st.last_overflow_reads)
     dev_ms_max = max_over_ranks(dev_ms)
     a_total = sum_over_ranks(float(a_local))
 
@@ -450,6 +451,7 @@ def main():
                 "note": "gaml_calc_prob_partial (+ all-gather at N>1): host walk arrays in, host partials out, wall clock; "
                         "the alignment cache is resident state like the reference's aligment_cache_"},
         "gpu_launches": int(launches),
+        "scratch_path_reads_per_full_eval": full_overflow_reads,
         "clocks": clocks,
         "sa_iters_per_s": len(seq) / delta_s,
         "incremental": {"evals": len(seq), "e2e_ms_per_eval": 1e3 * delta_s / max(len(seq), 1),

@@ -299,42 +299,65 @@ __device__ __forceinline__ bool pair_term(const ScoreParams& P, int walk, int xp
   return true;
 }
 
-// Up to two placements of one mate, in registers.
-struct Two {
+// Up to kFew placements of one mate, in registers (every index below is a compile-time constant after unrolling).
+// An incremental evaluation doubles a read's placements — the same record sits on the erased walk and on the added
+// one — so four covers what two covers in a full evaluation.
+constexpr int kFew = 4;
+struct Few {
   int n;
-  unsigned long long ord0, ord1;
-  int walk0, pos0, edor0, walk1, pos1, edor1;
+  unsigned long long ord[kFew];
+  int walk[kFew], pos[kFew], edor[kFew];
 };
+using Two = Few;   // (single-read path and older call sites)
 
 template <bool kCompact = false, class E = uint32_t>
-__device__ __forceinline__ void scan_two(const MateView& mv, const E& epoch, int r, Two& t) {
+__device__ __forceinline__ void scan_two(const MateView& mv, const E& epoch, int r, Few& t) {
   t.n = 0;
   auto visit = [&](const int4& o, const int4& rw, int idx) {
     const int pos = wrap_add(rw.y, o.z);
     if (pos < o.w) return;   // graph.cc:577
     const unsigned long long ord = ((unsigned long long)(uint32_t)o.y << 32) | (uint32_t)idx;
-    if (t.n == 0) { t.ord0 = ord; t.walk0 = o.x; t.pos0 = pos; t.edor0 = rw.z; }
-    else if (t.n == 1) { t.ord1 = ord; t.walk1 = o.x; t.pos1 = pos; t.edor1 = rw.z; }
+#pragma unroll
+    for (int j = 0; j < kFew; j++)
+      if (t.n == j) { t.ord[j] = ord; t.walk[j] = o.x; t.pos[j] = pos; t.edor[j] = rw.z; }
     t.n++;
   };
   if (kCompact) for_each_compact(mv, epoch, r, visit);
   else for_each_short(mv, epoch, r, visit);
 }
 
-// Enumeration order + per-walk de-dup for at most two entries.
-__device__ __forceinline__ void order_two(Two& t) {
-  if (t.n != 2) return;
-  if (t.ord1 < t.ord0) {
-    unsigned long long o = t.ord0; t.ord0 = t.ord1; t.ord1 = o;
-    int x;
-    x = t.walk0; t.walk0 = t.walk1; t.walk1 = x;
-    x = t.pos0; t.pos0 = t.pos1; t.pos1 = x;
-    x = t.edor0; t.edor0 = t.edor1; t.edor1 = x;
+__device__ __forceinline__ void few_swap(Few& t, int i, int j) {
+  const unsigned long long o = t.ord[i]; t.ord[i] = t.ord[j]; t.ord[j] = o;
+  int x;
+  x = t.walk[i]; t.walk[i] = t.walk[j]; t.walk[j] = x;
+  x = t.pos[i]; t.pos[i] = t.pos[j]; t.pos[j] = x;
+  x = t.edor[i]; t.edor[i] = t.edor[j]; t.edor[j] = x;
+}
+
+// Enumeration order (sorting network; absent entries get the largest key) + per-walk de-dup: the first occurrence of
+// a (walk, position) keeps its slot, a later one overwrites its payload and disappears (graph.cc:583-592).
+// Returns a validity mask over the kFew slots.
+__device__ __forceinline__ unsigned order_few(Few& t) {
+#pragma unroll
+  for (int j = 0; j < kFew; j++)
+    if (j >= t.n) t.ord[j] = ~0ull;
+#define GAML_CSWAP(I, J) if (t.ord[J] < t.ord[I]) few_swap(t, I, J);
+  GAML_CSWAP(0, 1) GAML_CSWAP(2, 3) GAML_CSWAP(0, 2) GAML_CSWAP(1, 3) GAML_CSWAP(1, 2)
+#undef GAML_CSWAP
+  unsigned valid = (1u << t.n) - 1u;
+#pragma unroll
+  for (int j = 1; j < kFew; j++) {
+    bool merged = false;
+#pragma unroll
+    for (int i = 0; i < j; i++) {
+      if (!merged && ((valid >> i) & 1u) && ((valid >> j) & 1u) && t.walk[i] == t.walk[j] && t.pos[i] == t.pos[j]) {
+        t.edor[i] = t.edor[j];
+        valid &= ~(1u << j);
+        merged = true;
+      }
+    }
   }
-  if (t.walk0 == t.walk1 && t.pos0 == t.pos1) {   // graph.cc:583-590: later record replaces the payload
-    t.edor0 = t.edor1;
-    t.n = 1;
-  }
+  return valid;
 }
 
 __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, int xe, int yw, int yp, int ye, int l1,
@@ -344,30 +367,27 @@ __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, i
   if (pair_term(P, xw, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
 }
 
-// Per-read paired update for reads with <= 2 live placements per mate. For lists sorted in enumeration
+// Per-read paired update for reads with <= kFew live placements per mate. For lists sorted in enumeration
 // order the plain x-major / y-minor loop with a same-walk filter IS the reference's order: walks ascend with
 // x, erased walks (subtract) precede added ones (add). Returns false if the read needs the scratch path.
 template <bool kCompact = false, class E0 = uint32_t, class E1 = uint32_t>
 __device__ __forceinline__ bool paired_read_with(const ScoreParams& P, const E0& lk0, const E1& lk1, int r, double& acc) {
-  Two a, b;
+  Few a, b;
   const uint32_t ll = __ldg((kCompact ? P.clens : P.lens) + r);   // r is the list index k in the compact variant
   scan_two<kCompact>(P.m[0], lk0, r, a);
   if (a.n == 0) return true;
   scan_two<kCompact>(P.m[1], lk1, r, b);
   if (b.n == 0) return true;
-  if (a.n > 2 || b.n > 2) return false;
+  if (a.n > kFew || b.n > kFew) return false;
   const int l1 = ll & 0xffff, l2 = ll >> 16;
-  order_two(a);
-  order_two(b);
-  {
-    const double p1 = align_prob(P.m[0], a.edor0, l1);
-    one_pair(P, a.walk0, a.pos0, a.edor0, b.walk0, b.pos0, b.edor0, l1, l2, p1, acc);
-    if (b.n == 2) one_pair(P, a.walk0, a.pos0, a.edor0, b.walk1, b.pos1, b.edor1, l1, l2, p1, acc);
-  }
-  if (a.n == 2) {
-    const double p1 = align_prob(P.m[0], a.edor1, l1);
-    one_pair(P, a.walk1, a.pos1, a.edor1, b.walk0, b.pos0, b.edor0, l1, l2, p1, acc);
-    if (b.n == 2) one_pair(P, a.walk1, a.pos1, a.edor1, b.walk1, b.pos1, b.edor1, l1, l2, p1, acc);
+  const unsigned va = order_few(a), vb = order_few(b);
+#pragma unroll
+  for (int x = 0; x < kFew; x++) {
+    if (!((va >> x) & 1u)) continue;
+    const double p1 = align_prob(P.m[0], a.edor[x], l1);
+#pragma unroll
+    for (int y = 0; y < kFew; y++)
+      if ((vb >> y) & 1u) one_pair(P, a.walk[x], a.pos[x], a.edor[x], b.walk[y], b.pos[y], b.edor[y], l1, l2, p1, acc);
   }
   return true;
 }
@@ -553,39 +573,62 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
     if (n1 == 3) n1 = (int)(__ldg(P.m[0].cptr + k + 1) - b1);
     if (n2 == 3) n2 = (int)(__ldg(P.m[1].cptr + k + 1) - b2);
     double acc = 0.0;
-    bool done = false, ok = true;
-    if (n1 <= 2 && n2 <= 2 && !P.ev_keys) {   // (coverage events are emitted by the general path only)
-      // Straight-line path for the shapes that make up this tier — (2,1), (1,2), (2,2): at most four candidate
-      // pairs. The state starts from 0 and every walk is "added" here (full evaluation), so with at most two
-      // non-dropped pairs the sum is order independent (0+a+b == 0+b+a); anything that needs the enumeration
-      // order (a de-dup, a repeated key, three or more terms) takes the general register path below.
+    bool done = false;
+    if (n1 <= 3 && n2 <= 3) {
+      // Straight-line path for the shapes that make up this tier — up to three records per mate of which at most
+      // two are LIVE in this evaluation (typically: the same alignment under the window key and the single-node key,
+      // plus one alignment elsewhere): at most four candidate pairs. The state starts from 0 and every walk is
+      // "added" here (full evaluation), so with at most two non-dropped pairs the sum is order independent
+      // (0+a+b == 0+b+a). A duplicate placement (same walk, same position) with an identical payload is dropped
+      // whichever record is "later". Anything that really needs the enumeration order — a duplicate with a different
+      // payload, a repeated key, three live placements, three or more terms — goes to the ordered paths.
       const int4 z = make_int4(0, 0, 0, 0);
-      const int4 rx0 = n1 > 0 ? ldg4(rows1 + b1) : z, rx1 = n1 > 1 ? ldg4(rows1 + b1 + 1) : z;
-      const int4 ry0 = n2 > 0 ? ldg4(rows2 + b2) : z, ry1 = n2 > 1 ? ldg4(rows2 + b2 + 1) : z;
-      const Placed1 x0 = place_row(P, 0, rx0, n1 > 0), x1 = place_row(P, 0, rx1, n1 > 1);
-      const Placed1 y0 = place_row(P, 1, ry0, n2 > 0), y1 = place_row(P, 1, ry1, n2 > 1);
-      const bool need_order = x0.multi || x1.multi || y0.multi || y1.multi ||
-                              (x0.live && x1.live && x0.walk == x1.walk && x0.pos == x1.pos) ||
-                              (y0.live && y1.live && y0.walk == y1.walk && y0.pos == y1.pos);
+      const int4 rx0 = n1 > 0 ? ldg4(rows1 + b1) : z, rx1 = n1 > 1 ? ldg4(rows1 + b1 + 1) : z, rx2 = n1 > 2 ? ldg4(rows1 + b1 + 2) : z;
+      const int4 ry0 = n2 > 0 ? ldg4(rows2 + b2) : z, ry1 = n2 > 1 ? ldg4(rows2 + b2 + 1) : z, ry2 = n2 > 2 ? ldg4(rows2 + b2 + 2) : z;
+      Placed1 x0 = place_row(P, 0, rx0, n1 > 0), x1 = place_row(P, 0, rx1, n1 > 1);
+      const Placed1 x2 = place_row(P, 0, rx2, n1 > 2);
+      Placed1 y0 = place_row(P, 1, ry0, n2 > 0), y1 = place_row(P, 1, ry1, n2 > 1);
+      const Placed1 y2 = place_row(P, 1, ry2, n2 > 2);
+      bool too_many = false;
+      if (x2.live) {   // keep the (at most two) live ones in x0, x1
+        if (!x0.live) x0 = x2; else if (!x1.live) x1 = x2; else too_many = true;
+      }
+      if (y2.live) {
+        if (!y0.live) y0 = y2; else if (!y1.live) y1 = y2; else too_many = true;
+      }
+      bool need_order = too_many || x0.multi || x1.multi || y0.multi || y1.multi;
+      if (x0.live && x1.live && x0.walk == x1.walk && x0.pos == x1.pos) {
+        if (x0.edor == x1.edor) x1.live = false; else need_order = true;
+      }
+      if (y0.live && y1.live && y0.walk == y1.walk && y0.pos == y1.pos) {
+        if (y0.edor == y1.edor) y1.live = false; else need_order = true;
+      }
       if (!need_order) {
         const int l1 = ll & 0xffff, l2 = ll >> 16;
-        double t[4];
+        double t0 = 0.0, t1 = 0.0;   // the first two non-dropped terms (more than two -> scratch path)
+        int w0 = 0, xp0 = 0, yp0 = 0, w1 = 0, xp1 = 0, yp1 = 0;
         int nt = 0;
         const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = align_prob(P.m[0], x1.edor, l1);
         double tt;
-        if (x0.live && y0.live && x0.walk == y0.walk && pair_term(P, -1, x0.pos, x0.edor, y0.pos, y0.edor, l1, l2, px0, tt)) t[nt++] = tt;
-        if (x0.live && y1.live && x0.walk == y1.walk && pair_term(P, -1, x0.pos, x0.edor, y1.pos, y1.edor, l1, l2, px0, tt)) t[nt++] = tt;
-        if (x1.live && y0.live && x1.walk == y0.walk && pair_term(P, -1, x1.pos, x1.edor, y0.pos, y0.edor, l1, l2, px1, tt)) t[nt++] = tt;
-        if (x1.live && y1.live && x1.walk == y1.walk && pair_term(P, -1, x1.pos, x1.edor, y1.pos, y1.edor, l1, l2, px1, tt)) t[nt++] = tt;
+#define GAML_TRY_PAIR(X, Y, PX)                                                                                         \
+  if (X.live && Y.live && X.walk == Y.walk && pair_term(P, -1, X.pos, X.edor, Y.pos, Y.edor, l1, l2, PX, tt)) {         \
+    if (nt == 0) { t0 = tt; w0 = X.walk; xp0 = X.pos; yp0 = Y.pos; }                                                    \
+    else if (nt == 1) { t1 = tt; w1 = X.walk; xp1 = X.pos; yp1 = Y.pos; }                                               \
+    nt++;                                                                                                               \
+  }
+        GAML_TRY_PAIR(x0, y0, px0)
+        GAML_TRY_PAIR(x0, y1, px0)
+        GAML_TRY_PAIR(x1, y0, px1)
+        GAML_TRY_PAIR(x1, y1, px1)
+#undef GAML_TRY_PAIR
         if (nt <= 2) {
-          if (nt >= 1) acc = __dadd_rn(acc, t[0]);
-          if (nt == 2) acc = __dadd_rn(acc, t[1]);
+          if (nt >= 1) { acc = __dadd_rn(acc, t0); emit_cov(P, w0, xp0, yp0, l2, t0); }
+          if (nt == 2) { acc = __dadd_rn(acc, t1); emit_cov(P, w1, xp1, yp1, l2, t1); }
           done = true;
         }
       }
     }
-    if (!done) ok = paired_read<true>(P, k, acc);
-    if (ok) {
+    if (done) {
       P.values[r] = acc;
       acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
     } else {
@@ -621,19 +664,23 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int r = (int)P.ovf_list[k];
-    const int n1 = gather_short(P.m[0], P.epoch, r, nullptr), n2 = gather_short(P.m[1], P.epoch, r, nullptr);
-    const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
     double acc = full_mode ? 0.0 : P.values[r];
     const uint32_t ll = __ldg(P.lens + r);
-    if (base + n1 + n2 > P.scratch_cap) {
-      atomicOr(P.error_flag, 2u);
-    } else {
-      Plc* a = P.scratch + base;
-      Plc* b = a + n1;
-      gather_short(P.m[0], P.epoch, r, a);
-      gather_short(P.m[1], P.epoch, r, b);
-      acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
+    if (paired_read(P, r, acc)) {   // ordered register path: at most two LIVE placements per mate, any record count
       P.values[r] = acc;
+    } else {
+      const int n1 = gather_short(P.m[0], P.epoch, r, nullptr), n2 = gather_short(P.m[1], P.epoch, r, nullptr);
+      const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
+      if (base + n1 + n2 > P.scratch_cap) {
+        atomicOr(P.error_flag, 2u);
+      } else {
+        Plc* a = P.scratch + base;
+        Plc* b = a + n1;
+        gather_short(P.m[0], P.epoch, r, a);
+        gather_short(P.m[1], P.epoch, r, b);
+        acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
+        P.values[r] = acc;
+      }
     }
     if (full_mode) acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
   }
@@ -681,15 +728,14 @@ __device__ double single_sum(const ScoreParams& P, Plc* a, int n, int len) {
 // One read through the register path (<= 2 live placements); false = needs the scratch path.
 template <bool kCompact = false>
 __device__ __forceinline__ bool single_read(const ScoreParams& P, int r, int len, double& acc) {
-  Two a;
+  Few a;
   scan_two<kCompact>(P.m[0], P.epoch, r, a);
-  if (a.n > 2) return false;
+  if (a.n > kFew) return false;
   acc = 0.0;
-  if (a.n >= 1) {
-    order_two(a);   // all walks are one group here (walk ordinal 0): de-duplicates on the global position
-    acc = __dadd_rn(acc, align_prob(P.m[0], a.edor0, len));
-    if (a.n == 2) acc = __dadd_rn(acc, align_prob(P.m[0], a.edor1, len));
-  }
+  const unsigned valid = order_few(a);   // all walks are one group here (walk ordinal 0): de-dup on the global position
+#pragma unroll
+  for (int x = 0; x < kFew; x++)
+    if ((valid >> x) & 1u) acc = __dadd_rn(acc, align_prob(P.m[0], a.edor[x], len));
   return true;
 }
 
@@ -1168,7 +1214,7 @@ int score_grid(int which, int n_items, int sm_count) {
   }
   return grid_for((size_t)n_items, kBlock, sm_count, per_sm[which]);
 }
-int overflow_grid(int sm_count) { return sm_count; }
+int overflow_grid(int sm_count) { return 8 * sm_count; }   // list length is unknown at launch: one resident wave of small blocks
 
 void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                         unsigned long long* flags, int n_flag_words, cudaStream_t st) {
