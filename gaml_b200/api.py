@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("last_reads_scanned", C.c_int64), ("last_algorithmic_bytes", C.c_int64),
                 ("last_h2d_bytes", C.c_int64), ("last_d2h_bytes", C.c_int64), ("last_device_ms", C.c_double),
                 ("last_score_kernel_ms", C.c_double), ("last_was_full", C.c_int32),
-                ("last_overflow_reads", C.c_int32)]
+                ("last_overflow_reads", C.c_int32), ("last_prepare_host_us", C.c_double),
+                ("last_launch_host_us", C.c_double), ("last_finish_host_us", C.c_double)]
 
 
 EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream", "gaml_set_graph",
@@ -51,7 +52,7 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials", "gaml_combine_partials_raw",
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
-           "gaml_get_stats"]
+           "gaml_get_stats", "gaml_set_profiling"]
 
 _lib = None
 
@@ -91,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.gaml_reset_state.argtypes = [vp]
     lib.gaml_read_values.argtypes = [vp, C.c_int, dp, C.c_int64]
     lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.gaml_set_profiling.argtypes = [vp, C.c_int32]
     for name in EXPORTS:
         if name not in ("gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream"):
             getattr(lib, name).restype = C.c_int
@@ -316,6 +318,10 @@ class ProbCalculator:
         out = np.zeros(max(n, 1), dtype=np.float64)
         self._check(self.lib.gaml_read_values(self.h, set_id, out.ctypes.data_as(C.POINTER(C.c_double)), n))
         return out[:n]
+
+    def set_profiling(self, enabled: bool) -> None:
+        """Per-set CUDA events around the streaming kernels (stats().last_score_kernel_ms); off by default."""
+        self._check(self.lib.gaml_set_profiling(self.h, 1 if enabled else 0))
 
     def stats(self) -> Stats:
         s = Stats()

@@ -66,6 +66,8 @@ struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one t
 
 constexpr int kAccumStride = 8;   // per set, u64: four 32-bit limbs of the exact 128-bit sum, floored, -inf terms, nan terms, spare
 constexpr int kOutStride = 6;     // per set, f64: integer part, 2^-40 units, floored, -inf terms, nan terms, flags
+constexpr int kResultStride = 8;  // per set in the host-mapped result buffer: the kOutStride values, then the epoch of the
+                                  // evaluation that wrote them (the host's completion flag), then a spare
 struct Double2 { double x, y; };  // {1/c, -log(1/c)} entries of the log table
 
 struct MateView {
@@ -111,7 +113,7 @@ struct ScoreParams {
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
   unsigned long long* accum;
   uint32_t* ticket;          // blocks-finished counter of the set's last kernel (finish_set)
-  double* out;               // kOutStride doubles written by the last block
+  double* out;               // kResultStride doubles in HOST-MAPPED pinned memory, written by the last block (finish_set)
   const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
   double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)
   double rcp_two_len;

@@ -13,12 +13,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <limits>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <memory>
+#include <memory_resource>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -42,6 +45,20 @@ struct WalkHash {
     return seed;
   }
 };
+
+// Element of the GetChanges multiset: a walk by reference with its precomputed hash (same hash values and equality as
+// the reference's unordered_multiset<vector<int>>, hence the same bucket placement and iteration order).
+struct WalkRef { const Walk* w; size_t h; };
+struct WalkRefHash { size_t operator()(const WalkRef& r) const { return r.h; } };
+struct WalkRefEq { bool operator()(const WalkRef& a, const WalkRef& b) const { return a.h == b.h && *a.w == *b.w; } };
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield");
+#endif
+}
 
 thread_local std::string g_create_error;
 
@@ -83,6 +100,56 @@ struct KeyMeta {
   bool any = false;         // the key has at least one record (any read)
 };
 
+// Walk-relative lookups of one walk in one paired set (build_walk_flat) and their cache.
+struct FlatEntry { int32_t key, cur, skip; uint32_t count, arena_off; };
+struct WalkFlat {
+  std::vector<FlatEntry> e[2];
+  std::vector<int> contig_starts;
+  int64_t records = 0, records1 = 0;
+};
+struct FlatCache {   // chained hash table keyed by walk content; the caller supplies the (already computed) hash
+  struct Node { size_t h; Walk w; WalkFlat f; int next; };
+  std::vector<Node> nodes;
+  std::vector<int> buckets;
+  void clear() { nodes.clear(); buckets.clear(); }
+  const WalkFlat* find(const Walk& w, size_t h) const {
+    if (buckets.empty()) return nullptr;
+    for (int i = buckets[h & (buckets.size() - 1)]; i >= 0; i = nodes[i].next)
+      if (nodes[i].h == h && nodes[i].w == w) return &nodes[i].f;
+    return nullptr;
+  }
+  WalkFlat& insert(const Walk& w, size_t h) {
+    if (nodes.size() >= buckets.size()) {
+      buckets.assign(std::max<size_t>(1024, buckets.size() * 2), -1);
+      for (size_t i = 0; i < nodes.size(); i++) {
+        int& b = buckets[nodes[i].h & (buckets.size() - 1)];
+        nodes[i].next = b;
+        b = (int)i;
+      }
+    }
+    int& b = buckets[h & (buckets.size() - 1)];
+    nodes.push_back(Node{h, w, WalkFlat(), b});
+    b = (int)nodes.size() - 1;
+    return nodes.back().f;
+  }
+};
+
+// Per-store accumulation of the occurrences of one evaluation.
+struct OccBuilder {
+  std::vector<std::pair<int, Occ>> items;   // (key id, occurrence) in enumeration order
+  int next_seg = 0;
+  void reset() { items.clear(); next_seg = 0; }
+  void add(int key, int walk, int cur_pos, int skip_below) {
+    items.push_back({key, Occ{walk, next_seg++, cur_pos, skip_below}});
+  }
+};
+
+struct WalkSet {
+  std::vector<Walk> walks;
+  std::vector<size_t> hash;   // WalkHash of every walk
+  int n = 0;                  // walks in use (the vectors only grow, so inner buffers are reused)
+};
+
 struct MateStore {
   bool is_long = false;
   std::unordered_map<Walk, int, WalkHash> key_ids;
@@ -94,6 +161,8 @@ struct MateStore {
   std::vector<double> pow_match, pow_mismatch;
   DevBuf d_pow_match, d_pow_mismatch;
   int table_index = -1;               // position in ctx->d_tables
+  std::vector<uint32_t> key_stamp;    // group_occurrences scratch: epoch that last saw the key / its SlotUpdate index
+  std::vector<int> key_slot, fill_cursor;
   size_t total_records() const { return arena_n + pending.size(); }
 };
 
@@ -112,16 +181,15 @@ struct ReadSetState {
   int ins_n = 0;
   double floor_a = 0, floor_b = 0;
   // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
-  std::vector<Walk> old_walks;
-  bool has_state = false;
+  bool has_state = false;       // old_paths = the context's last evaluated walk set (gaml_ctx::prev)
+  FlatCache flat_cache;         // per distinct walk: its lookups in this set (cleared when the set's cache grows)
   int bad_bases = 0;            // ScoringState::bad_bases (graph.h:614)
   bool penalty = false;         // paired set with penalty_constant != 0: coverage events are collected
   DevBuf d_cov_thr, d_ev, d_ev_sorted, d_ev_temp, d_bad;
   std::vector<int> h_bad;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this set's streaming kernel(s)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // side-stream fork/join for the tier-2 kernel
   ~ReadSetState() {
-    for (cudaEvent_t e : {ev0, ev1, ev_fork, ev_join})
+    for (cudaEvent_t e : {ev0, ev1})
       if (e) cudaEventDestroy(e);
   }
 };
@@ -153,7 +221,7 @@ struct gaml_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t side_stream = nullptr;   // tier-2 kernels run here, forked/joined with events
+  bool profile = false;           // gaml_set_profiling: per-set events around the streaming kernels
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string error;
   std::vector<int32_t> node_len, nmap;
@@ -164,10 +232,12 @@ struct gaml_ctx {
   DevBuf d_blob;                  // per-evaluation staging (updates, occurrences, touch ranges, set_begin)
   void* h_blob = nullptr;         // pinned
   size_t h_blob_cap = 0;
-  DevBuf d_out, d_flags, d_scratch, d_csr_temp, d_logtab;
+  DevBuf d_flags, d_scratch, d_csr_temp, d_logtab;
   DevBuf d_batch_blob, d_batch_acc, d_batch_out;   // gaml_calc_prob_batch
   std::vector<double> h_batch_out;
-  double* h_out = nullptr;        // pinned, 4 doubles per set
+  double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
+  double* d_out_mapped = nullptr; // device-side address of h_out
+  bool timing_pending = false;    // events of the last evaluation not yet turned into gaml_stats times
   size_t h_out_cap = 0;
   unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
   uint32_t ovf_cap = 1u << 20;
@@ -175,7 +245,20 @@ struct gaml_ctx {
   // pending evaluation
   bool prepared = false, launched = false;
   std::vector<SetPlan> plan;
-  std::vector<Walk> plan_walks;
+  // walk sets: cur = the evaluation being prepared, prev = the last FINISHED evaluation (ScoringState::old_paths of
+  // every paired set that has state, graph.cc:1986); ping-pong so that steady-state evaluations allocate nothing
+  WalkSet wsets[2];
+  int cur_set = 0;
+  WalkSet& cur() { return wsets[cur_set]; }
+  WalkSet& prev() { return wsets[cur_set ^ 1]; }
+  // per-evaluation host staging, reused
+  std::vector<SlotUpdate> h_updates;
+  std::vector<std::vector<Occ>> h_occs;
+  std::vector<std::vector<TouchRange>> h_touches;
+  std::vector<OccBuilder> h_ob;   // one per store
+  std::vector<WalkRef> h_refs;
+  alignas(16) char pool_buf[1 << 18];   // nodes + buckets of the GetChanges multiset (bump-allocated, released per use;
+  std::pmr::monotonic_buffer_resource pool{pool_buf, sizeof(pool_buf)};   // larger walk sets spill to the heap)
   int n_updates = 0;
   size_t upd_off = 0, blob_bytes = 0;
   gaml_stats stats{};
@@ -245,28 +328,24 @@ int find_key(const MateStore& st, const Walk& key) {
   return it == st.key_ids.end() ? -1 : it->second;
 }
 
-// Per-store accumulation of the occurrences of one evaluation.
-struct OccBuilder {
-  std::vector<std::pair<int, Occ>> items;   // (key id, occurrence) in enumeration order
-  int next_seg = 0;
-  void add(int key, int walk, int cur_pos, int skip_below) {
-    items.push_back({key, Occ{walk, next_seg++, cur_pos, skip_below}});
-  }
-};
-
-// Paired lookup rule (ReadSet::GetPositionsOnlyPath, graph.cc:535-598) for one walk, both mates.
-void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, int ord, OccBuilder ob[2],
-                         SetPlan& sp, std::vector<TouchRange>* touch, std::vector<int>* contig_starts = nullptr) {
+// Paired lookup rule (ReadSet::GetPositionsOnlyPath, graph.cc:535-598) for one walk, both mates: the keys the
+// walk looks up, in the reference's order, with walk-relative offsets. It depends only on the walk and on the
+// set's key metadata, so it is computed once per distinct walk and cached until the set's cache grows — an
+// annealing step re-submits ~all walks unchanged.
+void build_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, WalkFlat& out) {
   std::vector<Walk> ctgs;
   std::vector<int> gaps;
   split_at_gaps(walk, ctgs, gaps);
   Walk key;
   int cur_len = 0;
-  if (contig_starts) contig_starts->assign(1, 0);   // events (0,1) and (cur_len,1) per later contig, graph.cc:1826, 1835
+  out.e[0].clear();
+  out.e[1].clear();
+  out.records = out.records1 = 0;
+  out.contig_starts.assign(1, 0);   // events (0,1) and (cur_len,1) per later contig, graph.cc:1826, 1835
   for (size_t c = 0; c < ctgs.size(); c++) {
     if (c > 0) {
       cur_len += gaps[c - 1];
-      if (contig_starts) contig_starts->push_back(cur_len);
+      out.contig_starts.push_back(cur_len);
     }
     const Walk& ctg = ctgs[c];
     int ctg_len = 0;
@@ -287,10 +366,9 @@ void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk
           const KeyMeta& km = st.keys[kid[t]];
           const int skip = seen_max - 5;   // graph.cc:577
           if (km.count) {
-            ob[m].add(kid[t], ord, cur, skip);
-            sp.records += km.count;
-            if (m == 0) sp.records1 += km.count;
-            if (m == 0 && touch) touch->push_back(TouchRange{km.arena_off, km.count});
+            out.e[m].push_back(FlatEntry{kid[t], cur, skip, km.count, km.arena_off});
+            out.records += km.count;
+            if (m == 0) out.records1 += km.count;
           }
           if (km.any) {
             const int gp = (int)((unsigned)km.max_pos + (unsigned)cur);
@@ -306,13 +384,40 @@ void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk
   }
 }
 
+size_t hash_walk(const Walk& w) { return WalkHash()(w); }
+
+const WalkFlat& cached_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, size_t h) {
+  FlatCache& fc = rs.flat_cache;
+  if (const WalkFlat* f = fc.find(walk, h)) return *f;
+  if (fc.nodes.size() >= (1u << 17)) fc.clear();   // bound the memory of a very long annealing run
+  WalkFlat& f = fc.insert(walk, h);
+  build_walk_flat(ctx, rs, walk, f);
+  return f;
+}
+
+// Appends one walk's lookups to the evaluation (walk ordinal `ord`): occurrences per mate store, record counts,
+// and — for incremental evaluations — the mate-1 arena ranges the delta kernel enumerates.
+void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, size_t h, int ord, OccBuilder* ob[2],
+                         SetPlan& sp, std::vector<TouchRange>* touch, std::vector<int>* contig_starts = nullptr) {
+  const WalkFlat& f = cached_walk_flat(ctx, rs, walk, h);
+  for (int m = 0; m < 2; m++)
+    for (const FlatEntry& e : f.e[m]) {
+      ob[m]->add(e.key, ord, e.cur, e.skip);
+      if (m == 0 && touch) touch->push_back(TouchRange{e.arena_off, e.count});
+    }
+  sp.records += f.records;
+  sp.records1 += f.records1;
+  if (contig_starts) *contig_starts = f.contig_starts;
+}
+
 // Single lookup rule (CalcScoreForPaths + ReadSet::AddPositions, graph.cc:1665-1686, 600-649).
-void flatten_single(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Walk>& walks, OccBuilder& ob, SetPlan& sp) {
+void flatten_single(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, int n_walks, OccBuilder& ob, SetPlan& sp) {
   std::vector<Walk> ctgs;
   std::vector<int> gaps;
   Walk key;
   unsigned stride = 0, tl = 0;
-  for (const Walk& w : walks) {
+  for (int wi = 0; wi < n_walks; wi++) {
+    const Walk& w = walks[wi];
     split_at_gaps(w, ctgs, gaps);
     for (size_t c = 0; c < ctgs.size(); c++) {
       if (c > 0) tl += (unsigned)gaps[c - 1];
@@ -334,11 +439,12 @@ void flatten_single(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Wal
 }
 
 // PacBio lookup rule (PacbioReadSet::GetReadProbabilities, graph.cc:2410-2503) on normalised walks.
-void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Walk>& walks, OccBuilder& ob, SetPlan& sp) {
+void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, int n_walks, OccBuilder& ob, SetPlan& sp) {
   unsigned tl = 0;
   Walk key;
   std::vector<int> begin, end;
-  for (Walk w : walks) {
+  for (int wi = 0; wi < n_walks; wi++) {
+    Walk w = walks[wi];
     for (int& x : w)
       if (x >= 0) x = ctx->nmap[x];   // graph.h:268-273
     const size_t n = w.size();
@@ -367,26 +473,46 @@ void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const std::vector<Wal
   sp.total_len = (int)tl;
 }
 
-// Groups a store's occurrences by key: emits one SlotUpdate per key and the Occ array (occurrences of a
-// key contiguous, in enumeration order).
-void group_occurrences(OccBuilder& ob, int table_index, std::vector<SlotUpdate>& updates, std::vector<Occ>& occ) {
-  std::stable_sort(ob.items.begin(), ob.items.end(),
-                   [](const std::pair<int, Occ>& a, const std::pair<int, Occ>& b) { return a.first < b.first; });
+// Groups a store's occurrences by key: one SlotUpdate per live key (carrying its first occurrence) and, for the
+// keys that occur several times (repeat nodes), their occurrences contiguous in enumeration order in the Occ array
+// — the kernels read occ[occ_begin + t] only for t >= 1, so single-occurrence keys need no Occ entry.
+// Counting pass over a per-key stamp table, no sort.
+void group_occurrences(OccBuilder& ob, MateStore& st, uint32_t epoch, std::vector<SlotUpdate>& updates, std::vector<Occ>& occ) {
   occ.clear();
-  occ.reserve(ob.items.size());
-  size_t i = 0;
-  while (i < ob.items.size()) {
-    size_t j = i;
-    while (j < ob.items.size() && ob.items[j].first == ob.items[i].first) j++;
-    SlotUpdate u;
-    u.key = ob.items[i].first;
-    u.n_occ = (int)(j - i);
-    u.occ_begin = (int)occ.size();
-    u.store = table_index;
-    u.first = ob.items[i].second;
-    updates.push_back(u);
-    for (size_t t = i; t < j; t++) occ.push_back(ob.items[t].second);
-    i = j;
+  if (st.key_stamp.size() < st.keys.size()) {
+    st.key_stamp.resize(st.keys.size(), 0u);
+    st.key_slot.resize(st.keys.size(), 0);
+  }
+  const size_t first_update = updates.size();
+  for (const std::pair<int, Occ>& it : ob.items) {
+    const int k = it.first;
+    if (st.key_stamp[k] != epoch) {
+      st.key_stamp[k] = epoch;
+      st.key_slot[k] = (int)updates.size();
+      SlotUpdate u;
+      u.key = k;
+      u.n_occ = 1;
+      u.occ_begin = 0;
+      u.store = st.table_index;
+      u.first = it.second;
+      updates.push_back(u);
+    } else {
+      updates[st.key_slot[k]].n_occ++;
+    }
+  }
+  int total = 0;
+  for (size_t i = first_update; i < updates.size(); i++)
+    if (updates[i].n_occ > 1) {
+      updates[i].occ_begin = total;
+      total += updates[i].n_occ;
+    }
+  if (total == 0) return;
+  occ.resize(total);
+  st.fill_cursor.assign(updates.size() - first_update, 0);
+  for (const std::pair<int, Occ>& it : ob.items) {
+    const size_t slot = (size_t)st.key_slot[it.first];
+    const SlotUpdate& u = updates[slot];
+    if (u.n_occ > 1) occ[u.occ_begin + st.fill_cursor[slot - first_update]++] = it.second;
   }
 }
 
@@ -434,6 +560,7 @@ int commit(gaml_ctx* ctx) {
       ctx->stats.kernel_launches += launches;
       st.dirty = false;
       rs.complex_dirty = true;
+      rs.flat_cache.clear();   // key ids / record counts / max positions changed
     }
     if (rs.complex_dirty && rs.cfg.kind != GAML_KIND_PACBIO) {
       // static tier-2 list: reads that own more than one record on some mate
@@ -487,11 +614,21 @@ int commit(gaml_ctx* ctx) {
 int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walks) {
   if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
-  std::vector<Walk> walks(n_walks);
+  WalkSet& ws = ctx->cur();
+  if ((int)ws.walks.size() < n_walks) {
+    ws.walks.resize(n_walks);
+    ws.hash.resize(n_walks);
+  }
+  ws.n = n_walks;
+  const int n_nodes = (int)ctx->node_len.size();
+  int total_len = 0;   // GetTotalLen, graph.cc:1966 (int arithmetic like the reference)
   for (int w = 0; w < n_walks; w++) {
-    walks[w].assign(nodes + offs[w], nodes + offs[w + 1]);
-    for (int x : walks[w])
-      if (x >= (int)ctx->node_len.size()) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
+    Walk& wk = ws.walks[w];
+    wk.assign(nodes + offs[w], nodes + offs[w + 1]);
+    for (int x : wk)
+      if (x >= n_nodes) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
+    ws.hash[w] = hash_walk(wk);
+    total_len += walk_length(ctx, wk);
   }
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
@@ -500,58 +637,80 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
 
   const size_t n_sets = ctx->sets.size();
   ctx->plan.assign(n_sets, SetPlan());
-  std::vector<SlotUpdate> updates;
-  std::vector<std::vector<Occ>> occs(ctx->stores.size());
-  std::vector<std::vector<TouchRange>> touches(n_sets);
+  std::vector<SlotUpdate>& updates = ctx->h_updates;
+  std::vector<std::vector<Occ>>& occs = ctx->h_occs;
+  std::vector<std::vector<TouchRange>>& touches = ctx->h_touches;
+  updates.clear();
+  occs.resize(ctx->stores.size());
+  ctx->h_ob.resize(ctx->stores.size());
+  touches.resize(n_sets);
+  for (auto& t : touches) t.clear();
+  for (auto& o : ctx->h_ob) o.reset();
   std::vector<std::vector<std::vector<int>>> cov_cs(n_sets);   // per penalty set: contig starts of every touched walk
+
+  // GetChanges (graph.cc:1745-1764) is the same for every paired set with state (they all follow the last evaluated
+  // walks): same container, same hash values, same insertion order as the reference, so the erased walks come out in
+  // the reference's iteration order. The elements are (pointer, cached hash) pairs in a bump-allocated pool.
+  struct Changed { const Walk* w; size_t h; };
+  std::vector<Changed> erased, added;
+  bool changes_done = false;
+  auto get_changes = [&]() {
+    if (changes_done) return;
+    changes_done = true;
+    const WalkSet& old = ctx->prev();
+    ctx->h_refs.clear();
+    for (int i = 0; i < old.n; i++) ctx->h_refs.push_back(WalkRef{&old.walks[i], old.hash[i]});
+    ctx->pool.release();
+    std::pmr::unordered_multiset<WalkRef, WalkRefHash, WalkRefEq> idx(ctx->h_refs.begin(), ctx->h_refs.end(), 0, WalkRefHash(),
+                                                                      WalkRefEq(), &ctx->pool);
+    for (int i = 0; i < ws.n; i++) {
+      auto f = idx.find(WalkRef{&ws.walks[i], ws.hash[i]});
+      if (f == idx.end()) added.push_back(Changed{&ws.walks[i], ws.hash[i]});
+      else idx.erase(f);
+    }
+    for (const WalkRef& r : idx) erased.push_back(Changed{r.w, r.h});
+  };
 
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
     SetPlan& sp = ctx->plan[s];
     sp.grid = 0;
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
-      OccBuilder ob[2];
-      std::vector<Walk> erased, added;
-      if (!rs.has_state) {
-        sp.full = true;
-        added = walks;
-      } else {
-        sp.full = false;
-        // GetChanges, graph.cc:1745-1764 — same container, same hash, same insertion order.
-        std::unordered_multiset<Walk, WalkHash> idx(rs.old_walks.begin(), rs.old_walks.end());
-        for (const Walk& w : walks) {
-          auto f = idx.find(w);
-          if (f == idx.end()) added.push_back(w);
-          else idx.erase(f);
-        }
-        erased.insert(erased.end(), idx.begin(), idx.end());
-      }
+      OccBuilder* ob[2] = {&ctx->h_ob[rs.mate[0].table_index], &ctx->h_ob[rs.mate[1].table_index]};
+      sp.full = !rs.has_state;
+      if (!sp.full) get_changes();
       sp.grid = score_grid(sp.full ? kGridPairedFull : kGridPairedTotal, rs.n_local, ctx->sm_count);
-      sp.n_erased = (int)erased.size();
+      sp.n_erased = sp.full ? 0 : (int)erased.size();
       int ord = 0;
       std::vector<TouchRange>* tp = sp.full ? nullptr : &touches[s];
       std::vector<int> cs;
-      for (const Walk& w : erased) {
-        flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
-        if (rs.penalty) cov_cs[s].push_back(cs);
+      if (sp.full) {
+        for (int i = 0; i < ws.n; i++) {
+          flatten_paired_walk(ctx, rs, ws.walks[i], ws.hash[i], ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          if (rs.penalty) cov_cs[s].push_back(cs);
+        }
+      } else {
+        for (const Changed& c : erased) {
+          flatten_paired_walk(ctx, rs, *c.w, c.h, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          if (rs.penalty) cov_cs[s].push_back(cs);
+        }
+        for (const Changed& c : added) {
+          flatten_paired_walk(ctx, rs, *c.w, c.h, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          if (rs.penalty) cov_cs[s].push_back(cs);
+        }
       }
-      for (const Walk& w : added) {
-        flatten_paired_walk(ctx, rs, w, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
-        if (rs.penalty) cov_cs[s].push_back(cs);
-      }
-      int tl = 0;
-      for (const Walk& w : walks) tl += walk_length(ctx, w);   // GetTotalLen, graph.cc:1966
-      sp.total_len = tl;
-      for (int m = 0; m < 2; m++) group_occurrences(ob[m], rs.mate[m].table_index, updates, occs[rs.mate[m].table_index]);
+      sp.total_len = total_len;
+      for (int m = 0; m < 2; m++)
+        group_occurrences(*ob[m], rs.mate[m], ctx->epoch, updates, occs[rs.mate[m].table_index]);
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
       sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(kGridPairedComplex, rs.n_complex, ctx->sm_count) : 0;
     } else {
-      OccBuilder ob;
+      OccBuilder& ob = ctx->h_ob[rs.mate[0].table_index];
       sp.full = true;
-      if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, walks, ob, sp);
-      else flatten_pacbio(ctx, rs, walks, ob, sp);
-      group_occurrences(ob, rs.mate[0].table_index, updates, occs[rs.mate[0].table_index]);
+      if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, ws.walks.data(), ws.n, ob, sp);
+      else flatten_pacbio(ctx, rs, ws.walks.data(), ws.n, ob, sp);
+      group_occurrences(ob, rs.mate[0], ctx->epoch, updates, occs[rs.mate[0].table_index]);
       sp.grid = score_grid(rs.cfg.kind == GAML_KIND_SINGLE ? kGridSingleFull : kGridPacbioFull, rs.n_local, ctx->sm_count);
       sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
     }
@@ -630,18 +789,22 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->n_updates = (int)updates.size();
 
   CU(ctx->d_blob.reserve(std::max<size_t>(off, 256), 0, false, ctx->stream));
-  CU(ctx->d_out.reserve(std::max<size_t>(n_sets, 1) * kOutStride * sizeof(double), 0, false, ctx->stream));
   CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, ctx->stream));
   CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
-  if (ctx->h_out_cap < n_sets * kOutStride + kOutStride) {
-    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->h_out_cap < (n_sets + 1) * kResultStride) {
+    if (ctx->h_out) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFreeHost(ctx->h_out);
+    }
     ctx->h_out = nullptr;
-    CU(cudaMallocHost(&ctx->h_out, (n_sets * kOutStride + kOutStride) * sizeof(double)));
-    ctx->h_out_cap = n_sets * kOutStride + kOutStride;
+    const size_t cap = (n_sets + 1) * kResultStride;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_out), cap * sizeof(double), cudaHostAllocMapped));
+    memset(ctx->h_out, 0, cap * sizeof(double));
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_out_mapped), ctx->h_out, 0));
+    ctx->h_out_cap = cap;
   }
   CU(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.last_h2d_bytes = (int64_t)off;
-  ctx->plan_walks.swap(walks);
   ctx->prepared = true;
   ctx->launched = false;
   return GAML_OK;
@@ -695,7 +858,7 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   const size_t ns = std::max<size_t>(ctx->sets.size(), 1);
   P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);
   P.accum = fl + 2 + 2 * ns + s * kAccumStride;
-  P.out = ctx->d_out.as<double>() + s * kOutStride;
+  P.out = ctx->d_out_mapped + s * kResultStride;
   P.log_tab = ctx->d_logtab.p;
   P.two_len_d = (double)P.two_len;
   P.rcp_two_len = 1.0 / P.two_len_d;
@@ -724,9 +887,10 @@ int launch(gaml_ctx* ctx) {
                      ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, ctx->d_flags.as<unsigned long long>(),
                      (int)flags_words(n_sets), st);
   launches++;
-  CU(cudaEventRecord(ctx->ev[1], st));
   int64_t records = 0, reads = 0, bytes = 0;
   bool any_full = false;
+  const bool profile = ctx->profile;
+  bool chained = true;   // the operation before the next kernel on `st` is a kernel of this evaluation's chain
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
     const SetPlan& sp = ctx->plan[s];
@@ -745,16 +909,17 @@ int launch(gaml_ctx* ctx) {
       CU(cudaMemsetAsync(rs.d_bad.p, 0, std::max<size_t>(sp.n_cov_walks, 1) * 4, st));
       if (sp.n_type1) CU(cudaMemcpyAsync(rs.d_ev.p, blob + sp.type1_off, (size_t)sp.n_type1 * 8, cudaMemcpyDeviceToDevice, st));
       CU(cudaMemcpyAsync(P.ev_count, blob + sp.evcount_off, 4, cudaMemcpyDeviceToDevice, st));
+      chained = false;
     }
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
-        launch_paired_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
+        launch_paired_full(P, sp.grid, sp.cgrid, og, st, chained, profile, rs.ev0, rs.ev1);
         launches += 2 + (sp.cgrid > 0);
         any_full = true;
         // 16 B per live record + packed lengths (4) + probs write (8) per pair (no probs read: fused)
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       } else {
-        launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, og, ctx->sm_count, st, rs.ev0, rs.ev1);
+        launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, og, ctx->sm_count, st, chained, profile, rs.ev0, rs.ev1);
         launches += sp.touch_records > 0 ? 3 : 1;
         // touched records + the O(R) pass: probs read (8) + packed lengths (4) per pair
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
@@ -765,18 +930,22 @@ int launch(gaml_ctx* ctx) {
                            reinterpret_cast<const int*>(blob + sp.cs_off), rs.cfg.step,
                            rs.cfg.insert_mean + 5 * rs.cfg.insert_std, rs.d_bad.as<int>(), ctx->sm_count, st));
         launches += 3;
+        chained = false;
+      } else {
+        chained = !(profile && !sp.full);   // the delta wrapper ends with its e1 record when profiling
       }
     } else if (rs.cfg.kind == GAML_KIND_SINGLE) {
-      launch_single_full(P, sp.grid, sp.cgrid, og, st, rs.ev0, rs.ev1, SideStream{ctx->side_stream, rs.ev_fork, rs.ev_join});
+      launch_single_full(P, sp.grid, sp.cgrid, og, st, chained, profile, rs.ev0, rs.ev1);
+      chained = true;
       launches += 2 + (sp.cgrid > 0);
       bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
     } else {
-      launch_pacbio_full(P, sp.grid, og, st, rs.ev0, rs.ev1);
+      launch_pacbio_full(P, sp.grid, og, st, chained, profile, rs.ev0, rs.ev1);
+      chained = true;
       launches += 2;
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     }
   }
-  CU(cudaEventRecord(ctx->ev[2], st));
   CU(cudaEventRecord(ctx->ev[3], st));
   CU(cudaGetLastError());
   ctx->stats.kernel_launches += launches;
@@ -791,31 +960,50 @@ int launch(gaml_ctx* ctx) {
 int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
   const size_t n_sets = ctx->sets.size();
-  if (n_sets > 0) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out.p, n_sets * kOutStride * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  bool need_sync = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
     if (!rs.penalty) continue;
     rs.h_bad.assign(std::max(ctx->plan[s].n_cov_walks, 1), 0);
     if (ctx->plan[s].n_cov_walks)
       CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, (size_t)ctx->plan[s].n_cov_walks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    need_sync = true;
   }
-  CU(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kOutStride * sizeof(double));
-  float ms = 0, ms2 = 0;
-  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
-  for (auto& rs : ctx->sets) {
-    float t = 0;
-    if (cudaEventElapsedTime(&t, rs->ev0, rs->ev1) == cudaSuccess) ms2 += t;
+  if (need_sync) {
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else {
+    // The last block of every set's last kernel wrote the set's result and then this evaluation's epoch into the
+    // host-mapped buffer: spin on the flags instead of paying a copy and a stream synchronisation. The stream is
+    // polled now and then so that a failed launch surfaces as an error instead of a hang.
+    const double want = (double)ctx->epoch;
+    const volatile double* ho = ctx->h_out;
+    for (size_t s = 0; s < n_sets; s++) {
+      unsigned spins = 0;
+      while (ho[s * kResultStride + 6] != want) {
+        cpu_relax();
+        if ((++spins & 0x3fffu) == 0) {
+          const cudaError_t q = cudaStreamQuery(ctx->stream);
+          if (q == cudaErrorNotReady) continue;
+          if (q != cudaSuccess) {
+            ctx->error = std::string("evaluation failed on the device: ") + cudaGetErrorString(q);
+            return GAML_ERR_CUDA;
+          }
+          if (ho[s * kResultStride + 6] != want) return fail(ctx, GAML_ERR_CUDA, "evaluation finished without publishing its result");
+        }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
   }
-  ctx->stats.last_device_ms = ms;
-  ctx->stats.last_score_kernel_ms = ms2;
+  ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kResultStride * sizeof(double));
+  ctx->timing_pending = true;
   ctx->stats.evals++;
   ctx->prepared = ctx->launched = false;
   int tl = 0;
   uint32_t flags = 0, ovf = 0;
+  bool any_paired = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
-    const double* o = ctx->h_out + s * kOutStride;
+    const double* o = ctx->h_out + s * kResultStride;
     if (partials)
       for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) partials[s * GAML_PARTIAL_DOUBLES + k] = o[k];
     const uint64_t f = (uint64_t)o[5];
@@ -827,10 +1015,11 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
         for (int w = 0; w < ctx->plan[s].n_cov_walks; w++)
           rs.bad_bases += w < ctx->plan[s].n_erased ? -rs.h_bad[w] : rs.h_bad[w];
       }
-      rs.old_walks = ctx->plan_walks;   // graph.cc:1986: state follows the last EVALUATED walks
-      rs.has_state = true;
+      rs.has_state = true;   // graph.cc:1986: state follows the last EVALUATED walks (ctx->prev() after the swap below)
+      any_paired = true;
     }
   }
+  if (any_paired) ctx->cur_set ^= 1;   // the evaluated walks become old_paths; the other buffer is reused next time
   // CalcProb leaves the value of the last set it ran: single sets, then paired, then pacbio (prob_calculator.h:70-107)
   for (int kind = 0; kind < 3; kind++)
     for (size_t s = 0; s < n_sets; s++)
@@ -924,13 +1113,13 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
   }
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
-  const std::vector<Walk>& base = ctx->sets[0]->old_walks;
-  const int n_base = (int)base.size();
+  const std::vector<Walk>& base = ctx->prev().walks;   // old_paths of every set (only the first n_base entries are in use)
+  const int n_base = ctx->prev().n;
   // rank of every base walk in the iteration order of the reference's multiset (GetChanges, graph.cc:1747-1763):
   // erasing the kept walks leaves the others in place, so a candidate's erased walks come out in rank order
   std::vector<int> rank(n_base, 0);
   {
-    std::unordered_multiset<Walk, WalkHash> idx(base.begin(), base.end());
+    std::unordered_multiset<Walk, WalkHash> idx(base.begin(), base.begin() + n_base);
     std::unordered_map<Walk, std::vector<int>, WalkHash> where;
     for (int i = n_base - 1; i >= 0; i--) where[base[i]].push_back(i);
     int k = 0;
@@ -999,29 +1188,31 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     std::vector<int32_t> range_cand;
     uint64_t touch_total = 0;
     for (int c = 0; c < n_cand; c++) {
-      OccBuilder ob[2];
+      OccBuilder obs[2];
+      OccBuilder* ob[2] = {&obs[0], &obs[1]};
       SetPlan sp;
       std::vector<TouchRange> touch;
       int ord = 0;
-      for (int bi : cand_erased[c]) flatten_paired_walk(ctx, rs, base[bi], ord++, ob, sp, &touch);
-      for (const Walk& w : cand_added[c]) flatten_paired_walk(ctx, rs, w, ord++, ob, sp, &touch);
+      for (int bi : cand_erased[c]) flatten_paired_walk(ctx, rs, base[bi], ctx->prev().hash[bi], ord++, ob, sp, &touch);
+      for (const Walk& w : cand_added[c]) flatten_paired_walk(ctx, rs, w, hash_walk(w), ord++, ob, sp, &touch);
       BatchCand& cd = cands[c];
       cd.n_erased = (int)cand_erased[c].size();
       cd.len_index = cand_len_index[c];
       cd.pad[0] = cd.pad[1] = 0;
       for (int m = 0; m < 2; m++) {
-        std::stable_sort(ob[m].items.begin(), ob[m].items.end(),
+        std::vector<std::pair<int, Occ>>& items = obs[m].items;
+        std::stable_sort(items.begin(), items.end(),
                          [](const std::pair<int, Occ>& a, const std::pair<int, Occ>& b) { return a.first < b.first; });
         cd.key_begin[m] = (int)keys[m].size();
         size_t i = 0;
-        while (i < ob[m].items.size()) {
+        while (i < items.size()) {
           size_t j = i;
-          while (j < ob[m].items.size() && ob[m].items[j].first == ob[m].items[i].first) j++;
-          const Occ& f = ob[m].items[i].second;
-          keys[m].push_back(ob[m].items[i].first);
+          while (j < items.size() && items[j].first == items[i].first) j++;
+          const Occ& f = items[i].second;
+          keys[m].push_back(items[i].first);
           sa[m].push_back(SlotA{(uint32_t)(j - i > 1 ? 0x80000000u : 0u), f.walk, f.cur_pos, f.skip_below});
           sb[m].push_back(SlotB{f.seg, (int)(j - i), (int)occ[m].size(), 0});
-          for (size_t t = i; t < j; t++) occ[m].push_back(ob[m].items[t].second);
+          for (size_t t = i; t < j; t++) occ[m].push_back(items[t].second);
           i = j;
         }
         cd.key_count[m] = (int)keys[m].size() - cd.key_begin[m];
@@ -1150,8 +1341,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
     return GAML_ERR_CUDA;
@@ -1191,9 +1381,8 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
-  cudaStream_t st = ctx->stream, st2 = ctx->side_stream;
+  cudaStream_t st = ctx->stream;
   delete ctx;
-  if (st2) cudaStreamDestroy(st2);
   if (st) cudaStreamDestroy(st);
 }
 
@@ -1316,8 +1505,6 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     CU(cudaMemcpyAsync(rs.d_cov_thr.p, cthr.data(), cthr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaEventCreateWithFlags(&rs.ev_fork, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&rs.ev_join, cudaEventDisableTiming));
   CU(cudaEventCreate(&rs.ev0));
   CU(cudaEventCreate(&rs.ev1));
   for (int m = 0; m < rs.n_mates; m++) {
@@ -1437,19 +1624,28 @@ int gaml_cache_commit(gaml_ctx* ctx) {
 int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   cudaSetDevice(ctx->device);
-  return prepare(ctx, walk_nodes, walk_offsets, n_walks);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = prepare(ctx, walk_nodes, walk_offsets, n_walks);
+  ctx->stats.last_prepare_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 int gaml_eval_launch(gaml_ctx* ctx) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   cudaSetDevice(ctx->device);
-  return launch(ctx);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = launch(ctx);
+  ctx->stats.last_launch_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   cudaSetDevice(ctx->device);
-  return finish(ctx, partials, total_len);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = finish(ctx, partials, total_len);
+  ctx->stats.last_finish_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
 }
 
 int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
@@ -1525,7 +1721,6 @@ int gaml_reset_state(gaml_ctx* ctx) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   for (auto& rs : ctx->sets) {
     rs->has_state = false;
-    rs->old_walks.clear();
     rs->bad_bases = 0;
   }
   return GAML_OK;
@@ -1542,8 +1737,27 @@ int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n) {
   return GAML_OK;
 }
 
+int gaml_set_profiling(gaml_ctx* ctx, int32_t enabled) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  ctx->profile = enabled != 0;
+  return GAML_OK;
+}
+
 int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out) {
   if (check_ctx(ctx) || !out) return GAML_ERR_ARG;
+  if (ctx->timing_pending) {   // finish() returns on the result flag, possibly before the stream's closing event
+    cudaSetDevice(ctx->device);
+    float ms = 0, ms2 = 0;
+    if (cudaEventSynchronize(ctx->ev[3]) == cudaSuccess) cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+    if (ctx->profile)
+      for (auto& rs : ctx->sets) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, rs->ev0, rs->ev1) == cudaSuccess) ms2 += t;
+      }
+    ctx->stats.last_device_ms = ms;
+    ctx->stats.last_score_kernel_ms = ms2;
+    ctx->timing_pending = false;
+  }
   *out = ctx->stats;
   return GAML_OK;
 }

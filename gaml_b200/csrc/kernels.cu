@@ -14,6 +14,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <utility>
+
 #include "kernels.h"
 
 namespace gaml {
@@ -28,6 +30,16 @@ constexpr int kOvfBlock = 128;
 __device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
 
 __device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+
+// Programmatic dependent launch (sm_90+): the kernels of one evaluation form a chain on one stream, each launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization. pdl_release() lets the NEXT kernel of the chain be launched and
+// its blocks become resident while this one still runs; pdl_wait() blocks until the PREVIOUS kernel has completed and
+// its writes are visible. Every kernel calls pdl_wait() before it touches anything an earlier kernel of the chain
+// wrote (slot words, zeroed flags/accumulators, the overflow list, the read state), so completion is transitive along
+// the chain. Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- exact accumulation of the per-read log terms -----------------------------------------------
 // Every term is rounded ONCE to a multiple of 2^-40 and added as a 128-bit integer, so the shard total is an
@@ -101,7 +113,8 @@ __device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long l
 
 // Called by every block at the end of the LAST kernel of a read set: the block that draws the final ticket
 // re-assembles the set's exact 128-bit sum from its limbs and writes out[] = {integer part, fraction in 2^-40 units,
-// floored, -inf terms, nan terms, flags} (both parts are integers below 2^53, exact in a double).
+// floored, -inf terms, nan terms, flags} (both parts are integers below 2^53, exact in a double) straight into the
+// host's result buffer (zero-copy), followed by the evaluation's epoch as the completion flag.
 __device__ void finish_set(const ScoreParams& P) {
   __shared__ bool s_last;
   __threadfence();
@@ -121,6 +134,9 @@ __device__ void finish_set(const ScoreParams& P) {
   P.out[3] = (double)a[5];
   P.out[4] = (double)a[6];
   P.out[5] = (double)__ldcg(P.error_flag) + 16.0 * (double)__ldcg(P.ovf_count);
+  // P.out is host-mapped pinned memory: publish the values, then the completion flag the host spins on
+  __threadfence_system();
+  *reinterpret_cast<volatile double*>(P.out + 6) = (double)P.epoch;
 }
 
 // ---- log and division ------------------------------------------------------------------------------
@@ -509,6 +525,13 @@ __global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P
   const int stride = gridDim.x * blockDim.x;
   const int n = P.n_reads;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // The cache (first-records, lengths) is static: pull the first iteration's lines towards L2 while the previous
+  // kernel of the chain (apply_slots) is still running, then wait for it before the slot words are read.
+  if (r + stride < n && (threadIdx.x & 7) == 0) {   // 8 consecutive 16-byte records = one 128-byte line
+    prefetch_l2(first1 + r); prefetch_l2(first2 + r); prefetch_l2(first1 + r + stride); prefetch_l2(first2 + r + stride);
+  }
+  pdl_wait();
+  pdl_release();   // AFTER the wait: tier 2 (next in the chain) starts without a wait of its own, see there
   // Two reads per iteration: six independent coalesced loads in flight per thread before any use, and the two
   // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
   // (Measured dead ends, profiles/r01_summary.md: register double-buffering of the next iteration's loads and
@@ -555,6 +578,11 @@ __device__ __forceinline__ Placed1 place_row(const ScoreParams& P, int m, const 
 }
 
 __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P) {
+  // Tier 2 needs nothing from tier 1 (disjoint reads, commutative integer accumulators, atomic list appends) — only
+  // the slot words and zeroed flags of apply_slots. Tier 1 releases this kernel after ITS wait on apply_slots, so
+  // every block here starts after apply_slots has completed and runs beside tier 1's tail without waiting. The wait
+  // moves to the END of the kernel: it makes "tier 2 complete" imply "tier 1 complete" for the kernel after it.
+  pdl_release();
   Acc sum = acc_zero();
   unsigned floored = 0;
   const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
@@ -635,12 +663,15 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
       push_overflow(P, r);
     }
   }
+  pdl_wait();
   block_accumulate(sum, floored, P.accum);
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
 // thread to stamp a read owns it and replays that read's subtract/add sequence.
 __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams P) {
+  pdl_release();
+  pdl_wait();
   const uint32_t total = __ldg(P.touch_prefix + P.n_touch);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int lo = 0, hi = P.n_touch;   // largest t with prefix[t] <= i
@@ -659,6 +690,8 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
 
 // Reads with more than two placements on a mate: exact counts, scratch from a bump allocator, same replay.
 __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode) {
+  pdl_release();
+  pdl_wait();
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
@@ -692,6 +725,8 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
 
 // O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
 __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams P) {
+  pdl_release();
+  pdl_wait();
   Acc sum = acc_zero();
   unsigned floored = 0;
   const int stride = gridDim.x * blockDim.x;
@@ -741,6 +776,8 @@ __device__ __forceinline__ bool single_read(const ScoreParams& P, int r, int len
 
 // Tier 1: reads with at most one record (static) whose key occurs at most once in this evaluation.
 __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P) {
+  pdl_wait();
+  pdl_release();   // after the wait: tier 2 starts without one (see paired_complex_kernel)
   Acc sum = acc_zero();
   unsigned floored = 0;
   const int4* first = static_cast<const int4*>(P.m[0].first);
@@ -766,6 +803,7 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
 }
 
 __global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParams P) {
+  pdl_release();   // no wait here, one at the end: same chain discipline as paired_complex_kernel
   Acc sum = acc_zero();
   unsigned floored = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
@@ -779,10 +817,13 @@ __global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParam
       push_overflow(P, r);
     }
   }
+  pdl_wait();
   block_accumulate(sum, floored, P.accum);
 }
 
 __global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreParams P) {
+  pdl_release();
+  pdl_wait();
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
@@ -836,6 +877,8 @@ __device__ __forceinline__ double pacbio_floor(const ScoreParams& P, double v, i
 }
 
 __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P) {
+  pdl_release();
+  pdl_wait();
   Acc sum = acc_zero();
   unsigned floored = 0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
@@ -868,6 +911,8 @@ __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P
 // One WARP per many-placement read: lanes fold a strided share of the read's records sequentially and the 32
 // partial log-sums are combined with the warp-shuffle LSE (order-free; within the 1e-12 per-read budget).
 __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreParams P) {
+  pdl_release();
+  pdl_wait();
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
@@ -1058,6 +1103,7 @@ __global__ void coverage_sweep_kernel(const unsigned long long* keys, unsigned n
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                                    unsigned long long* flags, int n_flag_words) {
+  pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_flag_words) flags[i] = 0ull;   // scratch cursor, error flag, overflow counters, tickets, accumulators
   if (i >= n) return;
@@ -1216,61 +1262,69 @@ int score_grid(int which, int n_items, int sm_count) {
 }
 int overflow_grid(int sm_count) { return 8 * sm_count; }   // list length is unknown at launch: one resident wave of small blocks
 
+// One kernel of an evaluation's chain; pdl = launched as a programmatic dependent of the kernel before it on `st`.
+template <class... KArgs, class... Args>
+void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                         unsigned long long* flags, int n_flag_words, cudaStream_t st) {
   const int m = n > n_flag_words ? n : n_flag_words;
   apply_slots_kernel<<<(m + 255) / 256, 256, 0, st>>>(upd, n, tab_a, tab_b, epoch, flags, n_flag_words);
 }
 
-// e0/e1 bracket the streaming kernel(s) of the set on the launching stream (roofline timing).
-// Tier 1 and tier 2 touch disjoint reads and only meet in the (commutative, integer) accumulators, so tier 2 runs
-// on a side stream next to tier 1: both are latency-bound kernels that leave most of the machine idle alone.
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
-                        const SideStream& side) {
-  cudaEventRecord(e0, st);
-  if (cgrid > 0) {
-    cudaEventRecord(side.fork, st);
-    cudaStreamWaitEvent(side.stream, side.fork, 0);
-    paired_complex_kernel<<<cgrid, kBlock, 0, side.stream>>>(P);
-    cudaEventRecord(side.join, side.stream);
-  }
-  paired_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  if (cgrid > 0) cudaStreamWaitEvent(st, side.join, 0);
-  cudaEventRecord(e1, st);
-  paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 1);
+// Every wrapper below appends its kernels to the evaluation's chain. `chained` = the operation before it on `st` is a
+// kernel of the chain (so the first kernel may be a programmatic dependent too). With `profile` the streaming
+// kernel(s) of the set are bracketed by e0/e1 (the roofline timing); an event between two kernels makes the second
+// wait for the first in the ordinary way, so profiling costs the overlap at those two boundaries.
+// Tier 1 and tier 2 touch disjoint reads and only meet in the (commutative, integer) accumulators.
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
+                        cudaEvent_t e0, cudaEvent_t e1) {
+  if (profile) cudaEventRecord(e0, st);
+  launch_chain(paired_full_kernel, grid, kBlock, st, chained && !profile, P);
+  if (cgrid > 0) launch_chain(paired_complex_kernel, cgrid, kBlock, st, true, P);
+  if (profile) cudaEventRecord(e1, st);
+  launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
 }
 
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count,
-                         cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
-  cudaEventRecord(e0, st);
+                         cudaStream_t st, bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1) {
+  if (profile) cudaEventRecord(e0, st);
+  bool dep = chained && !profile;
   if (n_touch_records > 0) {
-    paired_delta_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P);
-    paired_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P, 0);
+    launch_chain(paired_delta_kernel, grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, st, dep, P);
+    launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, true, P, 0);
+    dep = true;
   }
-  paired_total_kernel<<<grid_total, kBlock, 0, st>>>(P);
-  cudaEventRecord(e1, st);
+  launch_chain(paired_total_kernel, grid_total, kBlock, st, dep, P);
+  if (profile) cudaEventRecord(e1, st);
 }
 
-void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
-                        const SideStream& side) {
-  cudaEventRecord(e0, st);
-  if (cgrid > 0) {
-    cudaEventRecord(side.fork, st);
-    cudaStreamWaitEvent(side.stream, side.fork, 0);
-    single_complex_kernel<<<cgrid, kBlock, 0, side.stream>>>(P);
-    cudaEventRecord(side.join, side.stream);
-  }
-  single_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  if (cgrid > 0) cudaStreamWaitEvent(st, side.join, 0);
-  cudaEventRecord(e1, st);
-  single_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P);
+void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
+                        cudaEvent_t e0, cudaEvent_t e1) {
+  if (profile) cudaEventRecord(e0, st);
+  launch_chain(single_full_kernel, grid, kBlock, st, chained && !profile, P);
+  if (cgrid > 0) launch_chain(single_complex_kernel, cgrid, kBlock, st, true, P);
+  if (profile) cudaEventRecord(e1, st);
+  launch_chain(single_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P);
 }
 
-void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
-  cudaEventRecord(e0, st);
-  pacbio_full_kernel<<<grid, kBlock, 0, st>>>(P);
-  cudaEventRecord(e1, st);
-  pacbio_overflow_kernel<<<ovf_grid, kOvfBlock, 0, st>>>(P);
+void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, bool chained, bool profile, cudaEvent_t e0,
+                        cudaEvent_t e1) {
+  if (profile) cudaEventRecord(e0, st);
+  launch_chain(pacbio_full_kernel, grid, kBlock, st, chained && !profile, P);
+  if (profile) cudaEventRecord(e1, st);
+  launch_chain(pacbio_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P);
 }
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,

@@ -12,17 +12,18 @@ int overflow_grid(int sm_count);
 
 void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                         unsigned long long* flags, int n_flag_words, cudaStream_t st);
-// Each *_full launch is two kernels: the streaming pass (grid blocks -> partial slots [0,grid)) and the
-// many-placement pass (ovf_grid blocks -> partial slots [grid, grid+ovf_grid)).
-// e0 / e1 are recorded on `st` around the streaming kernel(s) of the set (the roofline timing).
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };   // tier 2 runs beside tier 1
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
-                        const SideStream& side);
+// Each wrapper appends the kernels of one read set to the evaluation's chain on `st` (programmatic dependent
+// launches, kernels.cu): streaming pass (tier 1, tier 2), many-placement pass, per-set finalize in the last block.
+// chained: the operation before it on `st` is a kernel of the chain. profile: record e0 / e1 around the streaming
+// kernel(s) of the set (the roofline timing) — which serialises those two boundaries in the ordinary way.
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
+                        cudaEvent_t e0, cudaEvent_t e1);
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count, cudaStream_t st,
-                         cudaEvent_t e0, cudaEvent_t e1);
-void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
-                        const SideStream& side);
-void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1);
+                         bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1);
+void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
+                        cudaEvent_t e0, cudaEvent_t e1);
+void launch_pacbio_full(const ScoreParams& P, int grid, int ovf_grid, cudaStream_t st, bool chained, bool profile, cudaEvent_t e0,
+                        cudaEvent_t e1);
 
 cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_long, uint32_t* rowptr, uint32_t* cursor,
                       void* rows, void* first, void* temp, size_t temp_bytes, int sm_count, cudaStream_t st, int* launches);

@@ -90,9 +90,12 @@ typedef struct {
   int64_t last_h2d_bytes;          /* bytes copied host->device by the last evaluation */
   int64_t last_d2h_bytes;
   double last_device_ms;           /* CUDA-event time of the last evaluation's kernels on the ctx stream */
-  double last_score_kernel_ms;     /* CUDA-event time of the dominant scoring kernel(s) only */
+  double last_score_kernel_ms;     /* CUDA-event time of the dominant scoring kernel(s) only (gaml_set_profiling on; else 0) */
   int32_t last_was_full;           /* 1 if the paired sets were re-scored from scratch */
   int32_t last_overflow_reads;     /* reads that took the scratch (many-placement) path */
+  double last_prepare_host_us;     /* host wall time inside gaml_eval_prepare / launch / finish of the last evaluation */
+  double last_launch_host_us;      /*   (prepare = walk flattening + H2D enqueue, launch = kernel enqueue, */
+  double last_finish_host_us;      /*    finish = D2H enqueue + stream synchronize: includes waiting for the device) */
 } gaml_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -181,6 +184,11 @@ int gaml_reset_state(gaml_ctx* ctx);
 int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n);
 
 int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out);
+/* Measurement aid, no reference counterpart. enabled != 0: every evaluation also records CUDA events around each
+ * set's streaming kernel(s) (gaml_stats.last_score_kernel_ms, the roofline timing). An event between two kernels
+ * makes the second wait for the first in the ordinary way, so the programmatic dependent launches that chain an
+ * evaluation's kernels are given up at those boundaries: leave it off (the default) outside profiling. */
+int gaml_set_profiling(gaml_ctx* ctx, int32_t enabled);
 
 #ifdef __cplusplus
 }
