@@ -44,7 +44,8 @@ class Stats(C.Structure):
                 ("last_h2d_bytes", C.c_int64), ("last_d2h_bytes", C.c_int64), ("last_device_ms", C.c_double),
                 ("last_score_kernel_ms", C.c_double), ("last_was_full", C.c_int32),
                 ("last_overflow_reads", C.c_int32), ("last_prepare_host_us", C.c_double),
-                ("last_launch_host_us", C.c_double), ("last_finish_host_us", C.c_double)]
+                ("last_launch_host_us", C.c_double), ("last_finish_host_us", C.c_double),
+                ("delta_only_evals", C.c_int64)]
 
 
 EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream", "gaml_set_graph",
@@ -116,6 +117,20 @@ def flatten_walks(walks: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarra
     total = int(offs[-1])
     nodes = np.fromiter(itertools.chain.from_iterable(walks), dtype=np.int32, count=total) if total else np.zeros(1, np.int32)
     return nodes, offs
+
+
+class FlatWalks:
+    """Walks in the C ABI's layout with their ctypes pointers made once (what a C++ caller simply holds): keeps
+    the Python plumbing out of timed loops."""
+    __slots__ = ("nodes", "offs", "n", "p_nodes", "p_offs")
+
+    def __init__(self, walks=None, nodes=None, offs=None):
+        if walks is not None:
+            nodes, offs = flatten_walks(walks)
+        self.nodes, self.offs = nodes, offs
+        self.n = len(offs) - 1
+        self.p_nodes = nodes.ctypes.data_as(C.POINTER(C.c_int32))
+        self.p_offs = offs.ctypes.data_as(C.POINTER(C.c_int64))
 
 
 class ProbCalculator:
@@ -220,14 +235,25 @@ class ProbCalculator:
         z = [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(self.sets))]
         return res.prob, z, res.total_len
 
-    def calc_prob_partial_flat(self, nodes: np.ndarray, offs: np.ndarray):
-        """gaml_calc_prob_partial on walks already in the C ABI's layout (what a C++ caller passes)."""
-        part = np.zeros(PARTIAL_DOUBLES * max(len(self.sets), 1), dtype=np.float64)
-        tl = C.c_int32()
-        self._check(self.lib.gaml_calc_prob_partial(self.h, _p32(nodes), offs.ctypes.data_as(C.POINTER(C.c_int64)),
-                                                    len(offs) - 1, part.ctypes.data_as(C.POINTER(C.c_double)),
-                                                    C.byref(tl)))
-        return part, tl.value
+    def _io_buffers(self):
+        n = PARTIAL_DOUBLES * max(len(self.sets), 1)
+        io = getattr(self, "_io", None)
+        if io is None or io[0].size != n:
+            part = np.zeros(n, dtype=np.float64)
+            tl = C.c_int32()
+            zeros = np.zeros(2 * max(len(self.sets), 1), dtype=np.int32)
+            io = self._io = (part, part.ctypes.data_as(C.POINTER(C.c_double)), tl, C.byref(tl), Result(), zeros, _p32(zeros))
+        return io
+
+    def calc_prob_partial_flat(self, nodes, offs: Optional[np.ndarray] = None):
+        """gaml_calc_prob_partial on walks already in the C ABI's layout (what a C++ caller passes): a FlatWalks, or
+        the (nodes, offsets) arrays."""
+        fw = nodes if isinstance(nodes, FlatWalks) else FlatWalks(nodes=nodes, offs=offs)
+        part, p_part, tl, p_tl = self._io_buffers()[:4]
+        rc = self.lib.gaml_calc_prob_partial(self.h, fw.p_nodes, fw.p_offs, fw.n, p_part, p_tl)
+        if rc < 0:
+            self._check(rc)
+        return part.copy(), tl.value
 
     def calc_prob_partial(self, paths: Sequence[Sequence[int]]):
         nodes, offs = flatten_walks(paths)
@@ -239,11 +265,15 @@ class ProbCalculator:
         return part, tl.value
 
     def combine(self, gathered: np.ndarray, n_shards: int, total_len: int):
-        g = np.ascontiguousarray(gathered, dtype=np.float64)
-        res = Result()
-        zeros = np.zeros(2 * max(len(self.sets), 1), dtype=np.int32)
-        self._check(self.lib.gaml_combine_partials(self.h, g.ctypes.data_as(C.POINTER(C.c_double)), n_shards,
-                                                   total_len, C.byref(res), _p32(zeros)))
+        res, zeros, p_zeros = self._io_buffers()[4:]
+        gb = getattr(self, "_gbuf", None)
+        if gb is None or gb[0].size != gathered.size:
+            buf = np.zeros(gathered.size, dtype=np.float64)
+            gb = self._gbuf = (buf, buf.ctypes.data_as(C.POINTER(C.c_double)))
+        gb[0][:] = gathered.reshape(-1)
+        rc = self.lib.gaml_combine_partials(self.h, gb[1], n_shards, total_len, C.byref(res), p_zeros)
+        if rc < 0:
+            self._check(rc)
         z = [(int(zeros[2 * i]), int(zeros[2 * i + 1])) for i in range(len(self.sets))]
         return res.prob, z, res.total_len
 

@@ -113,6 +113,9 @@ struct ScoreParams {
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
   unsigned long long* accum;
   uint32_t* ticket;          // blocks-finished counter of the set's last kernel (finish_set)
+  unsigned long long* state_acc;   // paired sets: running total on the device {low, high, floored, -inf, nan} (finish_set)
+  int32_t state_add;         // 1: this evaluation accumulated a delta to add to state_acc; 0: it replaces it
+  int32_t delta_only;        // 1: incremental evaluation at an unchanged total length (no O(R) pass)
   double* out;               // kResultStride doubles in HOST-MAPPED pinned memory, written by the last block (finish_set)
   const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
   double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)

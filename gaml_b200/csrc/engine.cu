@@ -181,6 +181,10 @@ struct ReadSetState {
   int ins_n = 0;
   double floor_a = 0, floor_b = 0;
   // ScoringState (graph.h:612-619): probs live in d_values, old_paths here
+  // running total of the per-read log terms, kept exactly on the device (finish_set): valid for two_len == total_two_len
+  DevBuf d_state_acc;
+  bool total_valid = false;
+  int total_two_len = 0;
   bool has_state = false;       // old_paths = the context's last evaluated walk set (gaml_ctx::prev)
   FlatCache flat_cache;         // per distinct walk: its lookups in this set (cleared when the set's cache grows)
   int bad_bases = 0;            // ScoringState::bad_bases (graph.h:614)
@@ -196,6 +200,7 @@ struct ReadSetState {
 
 struct SetPlan {
   bool full = true;
+  bool delta_only = false;      // incremental evaluation at the running total's length: no O(R) pass
   int n_erased = 0;
   int total_len = 0;
   int64_t records = 0;          // A: live (record, occurrence) pairs in this shard
@@ -237,6 +242,7 @@ struct gaml_ctx {
   std::vector<double> h_batch_out;
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
+  bool running_total = true;      // GAML_B200_NO_RUNNING_TOTAL=1 forces the O(R) pass on every incremental evaluation (tests)
   bool timing_pending = false;    // events of the last evaluation not yet turned into gaml_stats times
   size_t h_out_cap = 0;
   unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
@@ -700,6 +706,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
         }
       }
       sp.total_len = total_len;
+      {
+        const int tl1 = total_len == 0 ? 1 : total_len;
+        sp.delta_only = ctx->running_total && !sp.full && rs.total_valid && rs.total_two_len == (int)(2u * (unsigned)tl1);
+      }
       for (int m = 0; m < 2; m++)
         group_occurrences(*ob[m], rs.mate[m], ctx->epoch, updates, occs[rs.mate[m].table_index]);
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
@@ -859,6 +869,9 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);
   P.accum = fl + 2 + 2 * ns + s * kAccumStride;
   P.out = ctx->d_out_mapped + s * kResultStride;
+  P.state_acc = rs.cfg.kind == GAML_KIND_PAIRED ? rs.d_state_acc.as<unsigned long long>() : nullptr;
+  P.state_add = sp.delta_only ? 1 : 0;
+  P.delta_only = sp.delta_only ? 1 : 0;
   P.log_tab = ctx->d_logtab.p;
   P.two_len_d = (double)P.two_len;
   P.rcp_two_len = 1.0 / P.two_len_d;
@@ -920,9 +933,9 @@ int launch(gaml_ctx* ctx) {
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
       } else {
         launch_paired_delta(P, (uint32_t)sp.touch_records, sp.grid, og, ctx->sm_count, st, chained, profile, rs.ev0, rs.ev1);
-        launches += sp.touch_records > 0 ? 3 : 1;
-        // touched records + the O(R) pass: probs read (8) + packed lengths (4) per pair
-        bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
+        launches += sp.delta_only ? (sp.touch_records > 0 ? 2 : 1) : (sp.touch_records > 0 ? 3 : 1);
+        // touched records (+ the O(R) pass when the total length changed: probs read (8) + packed lengths (4) per pair)
+        bytes += 16 * sp.records + (sp.delta_only ? 0 : 12 * (int64_t)rs.n_local);
       }
       if (rs.penalty) {
         CU(launch_coverage(rs.d_ev.as<unsigned long long>(), rs.d_ev_sorted.as<unsigned long long>(), sp.ev_cap, rs.d_ev_temp.p,
@@ -953,6 +966,8 @@ int launch(gaml_ctx* ctx) {
   ctx->stats.last_reads_scanned = reads;
   ctx->stats.last_algorithmic_bytes = bytes;
   ctx->stats.last_was_full = any_full ? 1 : 0;
+  for (size_t s = 0; s < n_sets; s++)
+    if (ctx->plan[s].delta_only) ctx->stats.delta_only_evals++;
   ctx->launched = true;
   return GAML_OK;
 }
@@ -1014,6 +1029,11 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
         if (ctx->plan[s].full) rs.bad_bases = 0;
         for (int w = 0; w < ctx->plan[s].n_cov_walks; w++)
           rs.bad_bases += w < ctx->plan[s].n_erased ? -rs.h_bad[w] : rs.h_bad[w];
+      }
+      {
+        const int tl1 = ctx->plan[s].total_len == 0 ? 1 : ctx->plan[s].total_len;
+        rs.total_two_len = (int)(2u * (unsigned)tl1);
+        rs.total_valid = (f & 15) == 0;   // a failed evaluation leaves no usable running total
       }
       rs.has_state = true;   // graph.cc:1986: state follows the last EVALUATED walks (ctx->prev() after the swap below)
       any_paired = true;
@@ -1341,6 +1361,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
+  if (const char* s = getenv("GAML_B200_NO_RUNNING_TOTAL")) ctx->running_total = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -1472,6 +1493,7 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   CU(rs.d_values.reserve(std::max<int64_t>(n_local, 1) * 8, 0, true, ctx->stream));
   CU(rs.d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));
   if (paired) CU(rs.d_stamp.reserve(std::max<int64_t>(n_local, 1) * 4, 0, true, ctx->stream));
+  if (paired) CU(rs.d_state_acc.reserve(kAccumStride * sizeof(unsigned long long), 0, true, ctx->stream));
   // floor thresholds
   std::vector<double> thr;
   if (cfg->kind != GAML_KIND_PACBIO) {
@@ -1721,6 +1743,7 @@ int gaml_reset_state(gaml_ctx* ctx) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   for (auto& rs : ctx->sets) {
     rs->has_state = false;
+    rs->total_valid = false;
     rs->bad_bases = 0;
   }
   return GAML_OK;

@@ -55,17 +55,23 @@ struct Acc {
   unsigned neginf, bad;
 };
 __device__ __forceinline__ Acc acc_zero() { return Acc{0ull, 0ll, 0u, 0u}; }
+__device__ __forceinline__ void acc_add_q(Acc& a, long long q) {
+  const unsigned long long nlo = a.lo + (unsigned long long)q;
+  a.hi += (q >> 63) + (long long)(nlo < (unsigned long long)q);
+  a.lo = nlo;
+}
 __device__ __forceinline__ void acc_add(Acc& a, double t) {
-  if (fabs(t) < kFixLimit) {
-    const long long q = __double2ll_rn(t * kFixScale);
-    const unsigned long long nlo = a.lo + (unsigned long long)q;
-    a.hi += (q >> 63) + (long long)(nlo < (unsigned long long)q);
-    a.lo = nlo;
-  } else if (t == -INFINITY) {
-    a.neginf++;
-  } else {
-    a.bad++;
-  }
+  if (fabs(t) < kFixLimit) acc_add_q(a, __double2ll_rn(t * kFixScale));
+  else if (t == -INFINITY) a.neginf++;
+  else a.bad++;
+}
+// Removes a term that an EARLIER evaluation added (same value, same total length -> the same rounded integer): the
+// running total of a paired set is then updated in O(touched reads) instead of re-summed over all reads. The counters
+// wrap modulo 2^32 here and are sign-extended when they reach the 64-bit accumulators.
+__device__ __forceinline__ void acc_sub(Acc& a, double t) {
+  if (fabs(t) < kFixLimit) acc_add_q(a, -__double2ll_rn(t * kFixScale));
+  else if (t == -INFINITY) a.neginf--;
+  else a.bad--;
 }
 
 // Block-wide exact sum -> per-set global accumulators {limb0..3 (32-bit limbs in u64), floored, neginf, bad}.
@@ -105,9 +111,10 @@ __device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long l
       const unsigned long long limb = (unsigned long long)(unsigned)(x >> (32 * j));
       if (limb) atomicAdd(accum + j, limb);
     }
-    if (sm[8]) atomicAdd(accum + 4, (unsigned long long)sm[8]);
-    if (sm[9]) atomicAdd(accum + 5, (unsigned long long)sm[9]);
-    if (sm[10]) atomicAdd(accum + 6, (unsigned long long)sm[10]);
+    // counters may be net negative in a delta-only evaluation: sign-extend (the 64-bit sums are modulo 2^64)
+    if (sm[8]) atomicAdd(accum + 4, (unsigned long long)(long long)(int)sm[8]);
+    if (sm[9]) atomicAdd(accum + 5, (unsigned long long)(long long)(int)sm[9]);
+    if (sm[10]) atomicAdd(accum + 6, (unsigned long long)(long long)(int)sm[10]);
   }
 }
 
@@ -127,6 +134,17 @@ __device__ void finish_set(const ScoreParams& P) {
   for (int j = 0; j < 7; j++) a[j] = __ldcg(P.accum + j);
   unsigned __int128 x = 0;
   for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  if (P.state_acc) {
+    // paired sets keep their running total {low, high 64 bits, floored, -inf, nan} on the device: a delta-only
+    // evaluation accumulated (new term - old term) of the touched reads and adds it, any other sets it
+    if (P.state_add) {
+      x += ((unsigned __int128)__ldcg(P.state_acc + 1) << 64) | (unsigned __int128)__ldcg(P.state_acc);
+      for (int j = 4; j < 7; j++) a[j] += __ldcg(P.state_acc + j - 2);
+    }
+    P.state_acc[0] = (unsigned long long)x;
+    P.state_acc[1] = (unsigned long long)(x >> 64);
+    for (int j = 4; j < 7; j++) P.state_acc[j - 2] = a[j];
+  }
   const __int128 v = (__int128)x;
   P.out[0] = (double)(long long)(v >> 40);
   P.out[1] = (double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
@@ -672,6 +690,8 @@ __global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParam
 __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams P) {
   pdl_release();
   pdl_wait();
+  Acc sum = acc_zero();
+  unsigned floored = 0;
   const uint32_t total = __ldg(P.touch_prefix + P.n_touch);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int lo = 0, hi = P.n_touch;   // largest t with prefix[t] <= i
@@ -682,13 +702,28 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
     const TouchRange tr = P.touch[lo];
     const int r = ldg4(P.arena1 + tr.begin + (i - __ldg(P.touch_prefix + lo))).x;
     if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;
-    double acc = P.values[r];
-    if (paired_read(P, r, acc)) P.values[r] = acc;
-    else push_overflow(P, r);
+    const double old = P.values[r];
+    double acc = old;
+    if (paired_read(P, r, acc)) {
+      P.values[r] = acc;
+      if (P.delta_only) {   // same total length as the running total: swap this read's term in it
+        const uint32_t ll = __ldg(P.lens + r);
+        const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
+        unsigned f_old = 0;
+        acc_sub(sum, floored_term(P, old, thr, f_old));
+        acc_add(sum, floored_term(P, acc, thr, floored));
+        floored -= f_old;
+      }
+    } else {
+      push_overflow(P, r);
+    }
   }
+  if (P.delta_only) block_accumulate(sum, floored, P.accum);
 }
 
 // Reads with more than two placements on a mate: exact counts, scratch from a bump allocator, same replay.
+// full_mode 1: full evaluation (state from 0, terms summed, per-set finalize); 0: delta followed by the O(R) total pass;
+// 2: delta-only evaluation (new term - old term into the running total, per-set finalize).
 __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode) {
   pdl_release();
   pdl_wait();
@@ -697,7 +732,8 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int r = (int)P.ovf_list[k];
-    double acc = full_mode ? 0.0 : P.values[r];
+    const double old = full_mode == 1 ? 0.0 : P.values[r];
+    double acc = old;
     const uint32_t ll = __ldg(P.lens + r);
     if (paired_read(P, r, acc)) {   // ordered register path: at most two LIVE placements per mate, any record count
       P.values[r] = acc;
@@ -715,7 +751,15 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
         P.values[r] = acc;
       }
     }
-    if (full_mode) acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    if (full_mode) {
+      const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
+      acc_add(sum, floored_term(P, acc, thr, floored));
+      if (full_mode == 2) {   // delta-only evaluation: the read's previous term leaves the running total
+        unsigned f_old = 0;
+        acc_sub(sum, floored_term(P, old, thr, f_old));
+        floored -= f_old;
+      }
+    }
   }
   if (full_mode) {
     block_accumulate(sum, floored, P.accum);
@@ -1303,10 +1347,16 @@ void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int gri
   bool dep = chained && !profile;
   if (n_touch_records > 0) {
     launch_chain(paired_delta_kernel, grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, st, dep, P);
-    launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, true, P, 0);
     dep = true;
   }
-  launch_chain(paired_total_kernel, grid_total, kBlock, st, dep, P);
+  if (P.delta_only) {
+    // total length unchanged since the running total was formed: the touched reads' terms were swapped in place, the
+    // many-placement pass finishes the set (it runs even with nothing to do: it publishes the result)
+    launch_chain(paired_overflow_kernel, n_touch_records > 0 ? ovf_grid : 1, kOvfBlock, st, dep, P, 2);
+  } else {
+    if (n_touch_records > 0) launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, true, P, 0);
+    launch_chain(paired_total_kernel, grid_total, kBlock, st, dep, P);
+  }
   if (profile) cudaEventRecord(e1, st);
 }
 

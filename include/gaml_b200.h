@@ -95,7 +95,9 @@ typedef struct {
   int32_t last_overflow_reads;     /* reads that took the scratch (many-placement) path */
   double last_prepare_host_us;     /* host wall time inside gaml_eval_prepare / launch / finish of the last evaluation */
   double last_launch_host_us;      /*   (prepare = walk flattening + H2D enqueue, launch = kernel enqueue, */
-  double last_finish_host_us;      /*    finish = D2H enqueue + stream synchronize: includes waiting for the device) */
+  double last_finish_host_us;      /*    finish = wait for the device's result flag (+ D2H of penalty counters)) */
+  int64_t delta_only_evals;        /* paired-set evaluations that updated the running total in O(touched reads): incremental,
+                                      total length unchanged, so no O(R) pass (GetTotalProb's sum is kept exactly on the device) */
 } gaml_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -164,6 +164,27 @@ def test_c2_incremental_state_equals_full_rescore(c2):
     assert again == full
 
 
+def test_running_total_is_exactly_the_full_resum(monkeypatch):
+    """An incremental evaluation at an unchanged total length swaps the touched reads' terms in the running total
+    (exact 128-bit integers) instead of re-summing all reads: the partials must be IDENTICAL to those of a context
+    that re-sums on every evaluation, over a whole scripted trajectory (joins, splits, tail swaps, flips, rejections)."""
+    wl = synth.paired_workload(46, 10000, 200_000, n_evals=60, seed=9)
+    fast = api.ProbCalculator.from_workload(wl)
+    monkeypatch.setenv("GAML_B200_NO_RUNNING_TOTAL", "1")
+    slow = api.ProbCalculator.from_workload(wl)
+    monkeypatch.delenv("GAML_B200_NO_RUNNING_TOTAL")
+    for e, walks in enumerate(wl.evals):
+        pf, tf = fast.calc_prob_partial(walks)
+        ps, ts = slow.calc_prob_partial(walks)
+        assert tf == ts
+        assert np.array_equal(pf, ps), (e, pf, ps)
+        if e % 20 == 19:
+            assert np.array_equal(fast.read_values(0), slow.read_values(0))
+    assert fast.stats().delta_only_evals >= 10 and slow.stats().delta_only_evals == 0
+    fast.close()
+    slow.close()
+
+
 def test_c2_there_and_back_again(c2):
     wl, pc = c2
     pc.reset_state()

@@ -10,8 +10,8 @@ from gaml_b200 import api, synth
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 wl = synth.paired_workload(int(460 * scale), 10000, int(2_000_000 * scale), n_evals=202, seed=42)
 pc = api.ProbCalculator.from_workload(wl)
-flat0 = api.flatten_walks(wl.evals[0])
-seq = [api.flatten_walks(w) for w in wl.evals[1:201]]
+flat0 = api.FlatWalks(wl.evals[0])
+seq = [api.FlatWalks(w) for w in wl.evals[1:201]]
 
 
 def run(kind, items, reset):
@@ -20,7 +20,7 @@ def run(kind, items, reset):
         if reset:
             pc.reset_state()
         t0 = time.perf_counter()
-        pc.calc_prob_partial_flat(*it)
+        pc.calc_prob_partial_flat(it)
         acc["wall"] += 1e6 * (time.perf_counter() - t0)
         s = pc.stats()
         acc["prepare"] += s.last_prepare_host_us
@@ -33,5 +33,5 @@ def run(kind, items, reset):
 for rep in range(3):
     run("full       ", [flat0] * 20, True)
     pc.reset_state()
-    pc.calc_prob_partial_flat(*flat0)
+    pc.calc_prob_partial_flat(flat0)
     run("incremental", seq, False)
