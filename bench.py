@@ -145,7 +145,7 @@ def ncu_traffic():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("paired_full_kernel_dram_bytes_per_launch")
+            return json.load(open(p)).get("paired_stream_kernel_dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -335,6 +335,7 @@ def main():
         return time.perf_counter() - t0, res
 
     # ---- value: device-resident inputs, CUDA events, L2 flushed between steps ----
+    pc.set_profiling(1)   # two events around each evaluation, nodes of its CUDA graph
     for _ in range(args.warmup):
         full_step_device()
     sampler = ClockSampler(local_rank)
@@ -351,14 +352,21 @@ def main():
     # roofline timing of the streaming pass: the same steps again with the library's per-kernel events switched on
     # (an event between two kernels serialises them, so the chained launches of the timed region above are given up
     # at the two boundaries of the streaming pass; the kernels themselves are identical)
-    pc.set_profiling(True)
+    pc.set_profiling(2)
     full_step_device()
     ker_ms = 0.0
     for _ in range(args.steps):
         ker_ms += full_step_device()[1]
-    pc.set_profiling(False)
+    # device timeline of one more step: globaltimer stamps at each kernel's first block start / last block end
+    # (no events, chain and graph intact) — shows how the kernels of an evaluation overlap
+    pc.set_profiling(3)
+    full_step_device()
+    full_step_device()
+    timeline = {k: [round(a, 2), round(b, 2)] for k, (a, b) in pc.read_timeline().items()}
+    pc.set_profiling(0)
     a_local, bytes_local = st.last_records_gathered, st.last_algorithmic_bytes
-    full_overflow_reads = int(st.last_overflow_reads)
+    full_overflow_reads = {"multi_pass_items": int(st.last_multi_items), "many_placement_pass_reads": int(st.last_overflow_reads),
+                           "scratch_placements": int(st.last_scratch_placements)}
     dev_ms_max = max_over_ranks(dev_ms)
     a_total = sum_over_ranks(float(a_local))
 
@@ -394,12 +402,14 @@ def main():
     # the same trajectory once more, untimed, reading the library's per-evaluation device time and counters
     pc.reset_state()
     full_step_e2e()
+    pc.set_profiling(1)
     delta_dev_ms, touched = 0.0, 0
     for nodes_offs in seq_flat:
         pc.calc_prob_partial_flat(nodes_offs)
         s2 = pc.stats()
         delta_dev_ms += s2.last_device_ms
         touched += s2.last_records_gathered
+    pc.set_profiling(0)
     delta_bytes = pc.stats().last_algorithmic_bytes
 
     # ---- BASELINE config 5: 1024 candidate moves scored per launch against the current state (stateless) ----
@@ -466,20 +476,21 @@ def main():
                                 "C4 shard: synthetic 100 Mbp genome (10000 x ~10 kbp nodes), 6.25 M of 50 M innie read pairs 2x100 bp") + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
                    "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
                    "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
-                   "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events on the library stream, max over ranks",
+                   "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events around each evaluation (recorded as nodes of its CUDA graph on the library stream), max over ranks",
                    "parallelism": f"read-id shards x{world}, all-gather of 40 B exact partials per read set"},
-        "roofline": {"bound": "hbm", "kernel": "paired_full_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "paired_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps,
                      "timing": f"CUDA events around the streaming pass (tier 1 + tier 2 kernels) on the library stream, {args.steps} extra "
-                               "steps after the timed region with gaml_set_profiling on, L2 flushed between steps"},
+                               "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
         "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "note": "gaml_calc_prob_partial (+ all-gather at N>1): host walk arrays in, host partials out, wall clock per step "
                         "(max over ranks), L2 flushed between steps; "
                         "the alignment cache is resident state like the reference's aligment_cache_"},
         "gpu_launches": int(launches),
-        "scratch_path_reads_per_full_eval": full_overflow_reads,
+        "device_timeline_us": timeline,
+        "ordered_paths_per_full_eval": full_overflow_reads,
         "clocks": clocks,
         "sa_iters_per_s": len(seq) / delta_s,
         "incremental": {"evals": len(seq), "e2e_ms_per_eval": 1e3 * delta_s / max(len(seq), 1),

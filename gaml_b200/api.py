@@ -45,6 +45,7 @@ class Stats(C.Structure):
                 ("last_score_kernel_ms", C.c_double), ("last_was_full", C.c_int32),
                 ("last_overflow_reads", C.c_int32), ("last_prepare_host_us", C.c_double),
                 ("last_launch_host_us", C.c_double), ("last_finish_host_us", C.c_double),
+                ("last_scratch_placements", C.c_int64), ("last_multi_items", C.c_int64),
                 ("delta_only_evals", C.c_int64)]
 
 
@@ -53,7 +54,7 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials", "gaml_combine_partials_raw",
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
-           "gaml_get_stats", "gaml_set_profiling"]
+           "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline"]
 
 _lib = None
 
@@ -94,6 +95,7 @@ def load_library() -> C.CDLL:
     lib.gaml_read_values.argtypes = [vp, C.c_int, dp, C.c_int64]
     lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.gaml_set_profiling.argtypes = [vp, C.c_int32]
+    lib.gaml_read_timeline.argtypes = [vp, C.POINTER(C.c_double), C.c_int32]
     for name in EXPORTS:
         if name not in ("gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream"):
             getattr(lib, name).restype = C.c_int
@@ -349,9 +351,16 @@ class ProbCalculator:
         self._check(self.lib.gaml_read_values(self.h, set_id, out.ctypes.data_as(C.POINTER(C.c_double)), n))
         return out[:n]
 
-    def set_profiling(self, enabled: bool) -> None:
-        """Per-set CUDA events around the streaming kernels (stats().last_score_kernel_ms); off by default."""
-        self._check(self.lib.gaml_set_profiling(self.h, 1 if enabled else 0))
+    def set_profiling(self, level) -> None:
+        """0 off (default); 1 events around the evaluation (stats().last_device_ms); 2 + per-set events around the
+        streaming kernels (stats().last_score_kernel_ms); 3 device globaltimer stamps per kernel (read_timeline)."""
+        self._check(self.lib.gaml_set_profiling(self.h, int(level)))
+
+    def read_timeline(self) -> dict:
+        out = np.zeros(12, dtype=np.float64)
+        self._check(self.lib.gaml_read_timeline(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), 12))
+        names = ["apply_slots", "tier1", "tier2", "many_placement", "delta_or_multi", "total"]
+        return {n: (float(out[2 * i]), float(out[2 * i + 1])) for i, n in enumerate(names) if out[2 * i] >= 0}
 
     def stats(self) -> Stats:
         s = Stats()

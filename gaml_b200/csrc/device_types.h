@@ -108,11 +108,25 @@ struct ScoreParams {
   const uint32_t* complex_list;
   const uint32_t* clens;     // lens[] gathered in list order
   const void* cdesc;         // int4 per listed read {read, packed lengths, first compact row mate 1, mate 2}
-  int32_t class_begin[17];   // first list index of every record-count class min(cnt1,3)*4 + min(cnt2,3)
+  int32_t class_begin[17];   // first list index of every record-count class, in list order (complex_class ranks)
   int32_t n_complex;
+  int32_t n_main;            // list entries tier 2 streams (ranks 0..4); the rest is the multi pass's static part
+  uint32_t cbase[2][5];      // per mate: first compact row of classes 0..4 (rows per read are uniform within a class)
+  // multi pass: arena ranges (both mates) of the keys that occur several times in this evaluation
+  const ArenaShort* arena2;
+  const TouchRange* mtouch;        // n_mtouch ranges, the first n_mtouch1 in mate 1's arena
+  const uint32_t* mtouch_prefix;   // n_mtouch + 1
+  int32_t n_mtouch, n_mtouch1;
+  // chain discipline of the streaming kernels (set per launch)
+  int32_t chain_first;       // 1: first kernel after apply_slots in its group: waits at its top; 0: waits at its end
+  int32_t finish_here;       // 1: this kernel's last block publishes the set when nothing was listed for the pass after it
+  uint32_t* tile_counter;    // next tile of [0] tier 1, [1] the rare shapes, [2] tier 2 (zeroed by apply_slots)
+  uint32_t* ticket2;         // blocks-finished counter of the set's last kernel (finish_set)
+  uint32_t* done;            // set by finish_set_if_complete
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
   unsigned long long* accum;
-  uint32_t* ticket;          // blocks-finished counter of the set's last kernel (finish_set)
+  uint32_t* ticket;          // blocks-finished counter of the set's last streaming kernel (finish_set_if_complete)
+  unsigned long long* timeline;    // profiling level 2: per kernel {first block start, last block end} in globaltimer ns; else null
   unsigned long long* state_acc;   // paired sets: running total on the device {low, high, floored, -inf, nan} (finish_set)
   int32_t state_add;         // 1: this evaluation accumulated a delta to add to state_acc; 0: it replaces it
   int32_t delta_only;        // 1: incremental evaluation at an unchanged total length (no O(R) pass)

@@ -176,6 +176,7 @@ struct ReadSetState {
   MateStore mate[2];
   DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
   int32_t class_begin[17] = {0};
+  uint32_t cbase[2][5] = {{0}};  // first compact row of the five tier-2 classes, per mate
   int n_complex = 0;
   bool complex_dirty = true;
   int ins_n = 0;
@@ -215,6 +216,10 @@ struct SetPlan {
   size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
   size_t touch_off = 0, prefix_off = 0;
   int n_touch = 0;
+  // full paired evaluations: arena ranges of the keys that occur several times (the multi pass)
+  size_t mtouch_off = 0, mprefix_off = 0;
+  int n_mtouch = 0, n_mtouch1 = 0;
+  int64_t multi_records = 0;
 };
 
 }  // namespace
@@ -226,7 +231,11 @@ struct gaml_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  bool profile = false;           // gaml_set_profiling: per-set events around the streaming kernels
+  bool timed = false;             // gaml_set_profiling >= 1: events around the whole evaluation (gaml_stats.last_device_ms)
+  bool profile = false;           // gaml_set_profiling 2: + per-set events around the streaming kernels (direct launches)
+  bool timeline = false;          // gaml_set_profiling 3: device-side globaltimer stamps per kernel instead (no events)
+  DevBuf d_timeline;
+  unsigned long long h_timeline[kTimelineWords] = {0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string error;
   std::vector<int32_t> node_len, nmap;
@@ -242,6 +251,10 @@ struct gaml_ctx {
   std::vector<double> h_batch_out;
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
+  // CUDA graphs of the evaluations' kernel chains, keyed by the sequence of kernels (GAML_B200_NO_GRAPHS=1 disables)
+  struct GraphEntry { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; std::vector<cudaGraphNode_t> nodes; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  bool use_graphs = true;
   bool running_total = true;      // GAML_B200_NO_RUNNING_TOTAL=1 forces the O(R) pass on every incremental evaluation (tests)
   bool timing_pending = false;    // events of the last evaluation not yet turned into gaml_stats times
   size_t h_out_cap = 0;
@@ -260,7 +273,7 @@ struct gaml_ctx {
   // per-evaluation host staging, reused
   std::vector<SlotUpdate> h_updates;
   std::vector<std::vector<Occ>> h_occs;
-  std::vector<std::vector<TouchRange>> h_touches;
+  std::vector<std::vector<TouchRange>> h_touches, h_mtouches;
   std::vector<OccBuilder> h_ob;   // one per store
   std::vector<WalkRef> h_refs;
   alignas(16) char pool_buf[1 << 18];   // nodes + buckets of the GetChanges multiset (bump-allocated, released per use;
@@ -288,9 +301,11 @@ int fail(gaml_ctx* ctx, int code, const std::string& msg) {
 }
 
 // d_flags layout (u64 words, zeroed at the start of every evaluation): [0] scratch cursor | [1] error flag (u32) |
-// [2, 2+n) per-set overflow counters (u32 in u64 slots) | [2+n, 2+2n) per-set tickets | then per set kAccumStride
+// [2, 2+n) per-set overflow counters (u32 in u64 slots) | [2+n, 2+2n) tickets of the last streaming kernel |
+// [2+2n, 2+3n) tickets of the last kernel | [2+3n, 2+4n) "published early" marks | [2+4n, 2+6n) tile counters of
+// tier 1 and tier 2 | then per set kAccumStride
 // words of exact accumulators
-size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (2 + kAccumStride); }
+size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (6 + kAccumStride); }
 
 double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, same expression order
   double z = (d - mean) / sd;
@@ -595,6 +610,10 @@ int commit(gaml_ctx* ctx) {
         CU(compact_copy(rs.d_complex.as<uint32_t>(), rs.n_complex, st.rowptr.as<uint32_t>(), st.cptr.as<uint32_t>(), st.rows.p,
                         st.crows.p, ctx->stream, &launches));
       }
+      memset(rs.cbase, 0, sizeof(rs.cbase));
+      for (int m = 0; m < rs.n_mates; m++)
+        for (int c = 0; c < 5; c++)   // class_begin[c] <= n_complex, cptr has n_complex + 1 entries
+          CU(cudaMemcpyAsync(&rs.cbase[m][c], rs.mate[m].cptr.as<uint32_t>() + rs.class_begin[c], 4, cudaMemcpyDeviceToHost, ctx->stream));
       CU(rs.d_cdesc.reserve(std::max<size_t>(n_complex, 1) * 16, 0, false, ctx->stream));
       launch_cdesc_fill(rs.d_complex.as<uint32_t>(), rs.n_complex, rs.d_lens.as<uint32_t>(), rs.mate[0].cptr.as<uint32_t>(),
                         rs.n_mates == 2 ? rs.mate[1].cptr.as<uint32_t>() : nullptr, rs.d_cdesc.p, ctx->stream);
@@ -651,6 +670,9 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->h_ob.resize(ctx->stores.size());
   touches.resize(n_sets);
   for (auto& t : touches) t.clear();
+  std::vector<std::vector<TouchRange>>& mtouches = ctx->h_mtouches;
+  mtouches.resize(n_sets);
+  for (auto& t : mtouches) t.clear();
   for (auto& o : ctx->h_ob) o.reset();
   std::vector<std::vector<std::vector<int>>> cov_cs(n_sets);   // per penalty set: contig starts of every touched walk
 
@@ -710,11 +732,27 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
         const int tl1 = total_len == 0 ? 1 : total_len;
         sp.delta_only = ctx->running_total && !sp.full && rs.total_valid && rs.total_two_len == (int)(2u * (unsigned)tl1);
       }
+      const size_t u0 = updates.size();
       for (int m = 0; m < 2; m++)
         group_occurrences(*ob[m], rs.mate[m], ctx->epoch, updates, occs[rs.mate[m].table_index]);
+      if (sp.full) {   // records under keys that occur several times: enumerated by the multi pass, mate 1's ranges first
+        std::vector<TouchRange>& mt = mtouches[s];
+        for (int m = 0; m < 2; m++) {
+          for (size_t u = u0; u < updates.size(); u++) {
+            if (updates[u].n_occ < 2 || updates[u].store != rs.mate[m].table_index) continue;
+            const KeyMeta& km = rs.mate[m].keys[updates[u].key];
+            if (km.count) {
+              mt.push_back(TouchRange{km.arena_off, km.count});
+              sp.multi_records += km.count;
+            }
+          }
+          if (m == 0) sp.n_mtouch1 = (int)mt.size();
+        }
+        sp.n_mtouch = (int)mt.size();
+      }
       for (const TouchRange& t : touches[s]) sp.touch_records += t.count;
       sp.n_touch = (int)touches[s].size();
-      sp.cgrid = sp.full && rs.n_complex > 0 ? score_grid(kGridPairedComplex, rs.n_complex, ctx->sm_count) : 0;
+      sp.cgrid = sp.full && rs.class_begin[5] > 0 ? score_grid(kGridPairedComplex, rs.class_begin[5], ctx->sm_count) : 0;
     } else {
       OccBuilder& ob = ctx->h_ob[rs.mate[0].table_index];
       sp.full = true;
@@ -744,6 +782,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     off = align16(off + touches[s].size() * sizeof(TouchRange));
     sp.prefix_off = off;
     off = align16(off + (touches[s].size() + 1) * sizeof(uint32_t));
+    sp.mtouch_off = off;
+    off = align16(off + mtouches[s].size() * sizeof(TouchRange));
+    sp.mprefix_off = off;
+    off = align16(off + (mtouches[s].size() + 1) * sizeof(uint32_t));
     if (rs.penalty) {
       sp.n_cov_walks = (int)cov_cs[s].size();
       sp.n_type1 = 0;
@@ -779,6 +821,15 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     }
     if (acc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one evaluation");
     pre[touches[s].size()] = (uint32_t)acc;
+    if (!mtouches[s].empty()) memcpy(hb + sp.mtouch_off, mtouches[s].data(), mtouches[s].size() * sizeof(TouchRange));
+    uint32_t* mpre = reinterpret_cast<uint32_t*>(hb + sp.mprefix_off);
+    uint64_t macc = 0;
+    for (size_t t = 0; t < mtouches[s].size(); t++) {
+      mpre[t] = (uint32_t)macc;
+      macc += mtouches[s][t].count;
+    }
+    if (macc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 records under repeated keys in one evaluation");
+    mpre[mtouches[s].size()] = (uint32_t)macc;
     if (ctx->sets[s]->penalty) {
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(hb + sp.type1_off);
       int* csb = reinterpret_cast<int*>(hb + sp.csbegin_off);
@@ -865,10 +916,23 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.cdesc = rs.d_cdesc.p;
   memcpy(P.class_begin, rs.class_begin, sizeof(P.class_begin));
   P.n_complex = rs.n_complex;
+  P.n_main = rs.class_begin[5];
+  memcpy(P.cbase, rs.cbase, sizeof(P.cbase));
+  P.arena2 = rs.n_mates == 2 ? rs.mate[1].arena.as<ArenaShort>() : nullptr;
+  P.mtouch = reinterpret_cast<const TouchRange*>(blob + sp.mtouch_off);
+  P.mtouch_prefix = reinterpret_cast<const uint32_t*>(blob + sp.mprefix_off);
+  P.n_mtouch = sp.n_mtouch;
+  P.n_mtouch1 = sp.n_mtouch1;
   const size_t ns = std::max<size_t>(ctx->sets.size(), 1);
   P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);
-  P.accum = fl + 2 + 2 * ns + s * kAccumStride;
+  P.ticket2 = reinterpret_cast<uint32_t*>(fl + 2 + 2 * ns + s);
+  P.done = reinterpret_cast<uint32_t*>(fl + 2 + 3 * ns + s);
+  P.tile_counter = reinterpret_cast<uint32_t*>(fl + 2 + 4 * ns + 2 * s);
+  P.accum = fl + 2 + 6 * ns + s * kAccumStride;
+  P.chain_first = 1;
+  P.finish_here = 0;
   P.out = ctx->d_out_mapped + s * kResultStride;
+  P.timeline = ctx->timeline ? ctx->d_timeline.as<unsigned long long>() : nullptr;
   P.state_acc = rs.cfg.kind == GAML_KIND_PAIRED ? rs.d_state_acc.as<unsigned long long>() : nullptr;
   P.state_add = sp.delta_only ? 1 : 0;
   P.delta_only = sp.delta_only ? 1 : 0;
@@ -889,16 +953,88 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   return P;
 }
 
+// Submits the recorded kernel chain of one evaluation. Steady state: the chain's CUDA graph exists (same kernels in
+// the same order, with their programmatic-dependent-launch edges) — its kernel nodes get this evaluation's grids and
+// parameter blocks and the graph goes to the device in one submission, instead of one driver call per kernel with the
+// device idling in between. First time a chain shape is seen: captured from the stream while it is issued.
+int replay_chain(gaml_ctx* ctx, LaunchList& list) {
+  cudaStream_t st = ctx->stream;
+  const bool timed = ctx->timed;   // the evaluation's two events become nodes of the graph: pure device time
+  uint64_t key = 1469598103934665603ull ^ (timed ? 0x9e3779b97f4a7c15ull : 0ull);
+  for (int i = 0; i < list.n; i++) {
+    const uint64_t v[3] = {(uint64_t)(uintptr_t)list.item[i].func, (uint64_t)list.item[i].pdl, (uint64_t)list.item[i].block};
+    for (uint64_t x : v) key = (key ^ x) * 1099511628211ull;
+  }
+  auto it = ctx->graphs.find(key);
+  if (it == ctx->graphs.end()) {
+    gaml_ctx::GraphEntry ge;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    // (cudaEventRecordExternal: a real event-record node; a plain record inside a capture is only a dependency marker)
+    cudaError_t err = timed ? cudaEventRecordWithFlags(ctx->ev[0], st, cudaEventRecordExternal) : cudaSuccess;
+    for (int i = 0; i < list.n && err == cudaSuccess; i++) {
+      err = issue_launch(list.item[i], st);
+      if (err != cudaSuccess) break;
+      cudaStreamCaptureStatus status;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t n_deps = 0;
+      err = cudaStreamGetCaptureInfo_v3(st, &status, nullptr, nullptr, &deps, nullptr, &n_deps);
+      if (err == cudaSuccess && (status != cudaStreamCaptureStatusActive || n_deps != 1)) err = cudaErrorUnknown;
+      if (err == cudaSuccess) ge.nodes.push_back(deps[0]);
+    }
+    if (err == cudaSuccess && timed) err = cudaEventRecordWithFlags(ctx->ev[3], st, cudaEventRecordExternal);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end_err = cudaStreamEndCapture(st, &graph);
+    if (err == cudaSuccess) err = end_err;
+    if (err == cudaSuccess) err = cudaGraphInstantiate(&ge.exec, graph, 0);
+    ge.graph = graph;   // kept: the node handles used for the per-evaluation parameter updates belong to it
+    if (err != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      // graphs unavailable for this chain: issue it directly from now on
+      cudaGetLastError();
+      ctx->use_graphs = false;
+      if (timed) CU(cudaEventRecord(ctx->ev[0], st));
+      for (int i = 0; i < list.n; i++) CU(issue_launch(list.item[i], st));
+      if (timed) CU(cudaEventRecord(ctx->ev[3], st));
+      return GAML_OK;
+    }
+    it = ctx->graphs.emplace(key, std::move(ge)).first;
+  } else {
+    for (int i = 0; i < list.n; i++) {
+      const PendingLaunch& pl = list.item[i];
+      cudaKernelNodeParams np{};
+      np.func = const_cast<void*>(pl.func);
+      np.gridDim = dim3(pl.grid);
+      np.blockDim = dim3(pl.block);
+      np.sharedMemBytes = 0;
+      np.kernelParams = const_cast<void**>(pl.arg_ptrs);
+      np.extra = nullptr;
+      CU(cudaGraphExecKernelNodeSetParams(it->second.exec, it->second.nodes[i], &np));
+    }
+  }
+  CU(cudaGraphLaunch(it->second.exec, st));
+  return GAML_OK;
+}
+
 int launch(gaml_ctx* ctx) {
   if (!ctx->prepared) return fail(ctx, GAML_ERR_STATE, "gaml_eval_launch without gaml_eval_prepare");
   cudaStream_t st = ctx->stream;
   const size_t n_sets = ctx->sets.size();
-  CU(cudaEventRecord(ctx->ev[0], st));
+  if (ctx->timeline) {
+    CU(ctx->d_timeline.reserve(kTimelineWords * 8, 0, true, st));
+    CU(cudaMemsetAsync(ctx->d_timeline.p, 0, kTimelineWords * 8, st));
+  }
   char* blob = ctx->d_blob.as<char>();
   int launches = 0;
+  bool any_penalty = false;
+  for (auto& rs : ctx->sets) any_penalty |= rs->penalty;
+  LaunchList chain;
+  const bool record = ctx->use_graphs && !ctx->profile && !any_penalty && ctx->sets.size() <= 3;
+  struct RecorderGuard { ~RecorderGuard() { set_launch_recorder(nullptr); } } recorder_guard;
+  if (record) set_launch_recorder(&chain);
+  else if (ctx->timed) CU(cudaEventRecord(ctx->ev[0], st));
   launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates, ctx->d_tables.as<SlotA*>(),
                      ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, ctx->d_flags.as<unsigned long long>(),
-                     (int)flags_words(n_sets), st);
+                     (int)flags_words(n_sets), ctx->timeline ? ctx->d_timeline.as<unsigned long long>() : nullptr, st);
   launches++;
   int64_t records = 0, reads = 0, bytes = 0;
   bool any_full = false;
@@ -926,8 +1062,9 @@ int launch(gaml_ctx* ctx) {
     }
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
-        launch_paired_full(P, sp.grid, sp.cgrid, og, st, chained, profile, rs.ev0, rs.ev1);
-        launches += 2 + (sp.cgrid > 0);
+        const uint32_t n_multi = (uint32_t)sp.multi_records;
+        launch_paired_full(P, sp.grid, sp.cgrid, n_multi, og, ctx->sm_count, st, chained, profile, rs.ev0, rs.ev1);
+        launches += 2 + (n_multi > 0);
         any_full = true;
         // 16 B per live record + packed lengths (4) + probs write (8) per pair (no probs read: fused)
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
@@ -959,7 +1096,12 @@ int launch(gaml_ctx* ctx) {
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     }
   }
-  CU(cudaEventRecord(ctx->ev[3], st));
+  if (record) {
+    set_launch_recorder(nullptr);
+    const int rc = replay_chain(ctx, chain);
+    if (rc != GAML_OK) return rc;
+  }
+  if (!record && ctx->timed) CU(cudaEventRecord(ctx->ev[3], st));
   CU(cudaGetLastError());
   ctx->stats.kernel_launches += launches;
   ctx->stats.last_records_gathered = records;
@@ -1010,7 +1152,8 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
     std::atomic_thread_fence(std::memory_order_acquire);
   }
   ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kResultStride * sizeof(double));
-  ctx->timing_pending = true;
+  ctx->timing_pending = ctx->timed;
+  if (!ctx->timed) ctx->stats.last_device_ms = ctx->stats.last_score_kernel_ms = 0;
   ctx->stats.evals++;
   ctx->prepared = ctx->launched = false;
   int tl = 0;
@@ -1046,6 +1189,14 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
       if (ctx->sets[s]->cfg.kind == kind) tl = ctx->plan[s].total_len;
   if (total_len) *total_len = tl;
   ctx->stats.last_overflow_reads = (int32_t)ovf;
+  ctx->stats.last_scratch_placements = n_sets ? (int64_t)ctx->h_out[(n_sets - 1) * kResultStride + 7] : 0;
+  {
+    int64_t mi = 0;
+    for (size_t s = 0; s < n_sets; s++)
+      if (ctx->plan[s].full && ctx->sets[s]->cfg.kind == GAML_KIND_PAIRED)
+        mi += ctx->plan[s].multi_records;
+    ctx->stats.last_multi_items = mi;
+  }
   if (flags & 1) return fail(ctx, GAML_ERR_CAPACITY, "too many many-placement reads for the overflow list");
   if (flags & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
   if (flags & 4) return fail(ctx, GAML_ERR_CAPACITY, "coverage-event buffer exhausted");
@@ -1362,6 +1513,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
   if (const char* s = getenv("GAML_B200_NO_RUNNING_TOTAL")) ctx->running_total = !(s[0] && s[0] != '0');
+  if (const char* s = getenv("GAML_B200_NO_GRAPHS")) ctx->use_graphs = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -1403,6 +1555,10 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStream_t st = ctx->stream;
+  for (auto& g : ctx->graphs) {
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    if (g.second.graph) cudaGraphDestroy(g.second.graph);
+  }
   delete ctx;
   if (st) cudaStreamDestroy(st);
 }
@@ -1760,9 +1916,28 @@ int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n) {
   return GAML_OK;
 }
 
-int gaml_set_profiling(gaml_ctx* ctx, int32_t enabled) {
+int gaml_set_profiling(gaml_ctx* ctx, int32_t level) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
-  ctx->profile = enabled != 0;
+  ctx->timed = level == 1 || level == 2;
+  ctx->profile = level == 2;
+  ctx->timeline = level == 3;
+  return GAML_OK;
+}
+
+int gaml_read_timeline(gaml_ctx* ctx, double* out_us, int32_t n) {
+  if (check_ctx(ctx) || !out_us || n < kTimelineWords) return GAML_ERR_ARG;
+  if (!ctx->timeline || !ctx->d_timeline.p) return fail(ctx, GAML_ERR_STATE, "gaml_set_profiling(ctx, 3) and one evaluation first");
+  cudaSetDevice(ctx->device);
+  CU(cudaMemcpyAsync(ctx->h_timeline, ctx->d_timeline.p, kTimelineWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  unsigned long long t0 = ~0ull;
+  for (int k = 0; k < kTimelineWords; k += 2)
+    if (ctx->h_timeline[k]) t0 = std::min(t0, ~ctx->h_timeline[k]);
+  for (int k = 0; k < kTimelineWords; k += 2) {
+    const bool ran = ctx->h_timeline[k] != 0;
+    out_us[k] = ran ? (double)(~ctx->h_timeline[k] - t0) * 1e-3 : -1.0;
+    out_us[k + 1] = ran ? (double)(ctx->h_timeline[k + 1] - t0) * 1e-3 : -1.0;
+  }
   return GAML_OK;
 }
 

@@ -14,6 +14,11 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 #include <utility>
 
 #include "kernels.h"
@@ -39,6 +44,19 @@ __device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a
 // the chain. Both are no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Device timeline (gaml_set_profiling level 2): start of the kernel's first block, end of its last block.
+enum { kTlApply = 0, kTlTier1, kTlTier2, kTlOverflow, kTlDelta, kTlTotal, kTlKernels };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* tl, int k) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k, ~global_ns());   // complemented: the buffer is reset to all zeros
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int k) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, global_ns());
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- exact accumulation of the per-read log terms -----------------------------------------------
@@ -118,44 +136,77 @@ __device__ void block_accumulate(const Acc& a, unsigned floored, unsigned long l
   }
 }
 
-// Called by every block at the end of the LAST kernel of a read set: the block that draws the final ticket
-// re-assembles the set's exact 128-bit sum from its limbs and writes out[] = {integer part, fraction in 2^-40 units,
-// floored, -inf terms, nan terms, flags} (both parts are integers below 2^53, exact in a double) straight into the
-// host's result buffer (zero-copy), followed by the evaluation's epoch as the completion flag.
-__device__ void finish_set(const ScoreParams& P) {
+// Thread 0 of the block that completes a read set: re-assembles the set's exact 128-bit sum from its limbs and writes
+// out[] = {integer part, fraction in 2^-40 units, floored, -inf terms, nan terms, flags} (both parts are integers
+// below 2^53, exact in a double) straight into the host's result buffer (zero-copy), followed by the evaluation's
+// epoch as the completion flag. Out of line and fed by value: it runs once per evaluation, and a reference to the
+// kernel's parameter block would force a local copy of all of it in every thread of the streaming kernels.
+struct PublishArgs {
+  const unsigned long long* accum;
+  unsigned long long* state_acc;
+  double* out;
+  const uint32_t* error_flag;
+  const uint32_t* ovf_count;
+  const unsigned long long* scratch_cursor;
+  uint32_t* ticket;
+  uint32_t* done;
+  uint32_t epoch;
+  int32_t state_add;
+};
+__device__ __forceinline__ PublishArgs publish_args(const ScoreParams& P, uint32_t* ticket) {
+  return PublishArgs{P.accum, P.state_acc, P.out, P.error_flag, P.ovf_count, P.scratch_cursor, ticket, P.done, P.epoch, P.state_add};
+}
+
+__device__ __noinline__ void publish_set(PublishArgs A) {
+  __threadfence();
+  unsigned long long a[7];
+  for (int j = 0; j < 7; j++) a[j] = __ldcg(A.accum + j);
+  unsigned __int128 x = 0;
+  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  if (A.state_acc) {
+    // paired sets keep their running total {low, high 64 bits, floored, -inf, nan} on the device: a delta-only
+    // evaluation accumulated (new term - old term) of the touched reads and adds it, any other sets it
+    if (A.state_add) {
+      x += ((unsigned __int128)__ldcg(A.state_acc + 1) << 64) | (unsigned __int128)__ldcg(A.state_acc);
+      for (int j = 4; j < 7; j++) a[j] += __ldcg(A.state_acc + j - 2);
+    }
+    A.state_acc[0] = (unsigned long long)x;
+    A.state_acc[1] = (unsigned long long)(x >> 64);
+    for (int j = 4; j < 7; j++) A.state_acc[j - 2] = a[j];
+  }
+  const __int128 v = (__int128)x;
+  A.out[0] = (double)(long long)(v >> 40);
+  A.out[1] = (double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
+  A.out[2] = (double)a[4];
+  A.out[3] = (double)a[5];
+  A.out[4] = (double)a[6];
+  A.out[5] = (double)__ldcg(A.error_flag) + 16.0 * (double)__ldcg(A.ovf_count);
+  A.out[7] = (double)__ldcg(A.scratch_cursor);   // placements parked in the scratch arena so far in this evaluation
+  // out is host-mapped pinned memory: publish the values, then the completion flag the host spins on
+  __threadfence_system();
+  *reinterpret_cast<volatile double*>(A.out + 6) = (double)A.epoch;
+}
+
+// Block-level tail of a set's kernels. early = false: called by every block of the set's LAST kernel, the block that
+// draws the final ticket publishes. early = true: called by every block of the set's last STREAMING kernel
+// (P.finish_here): if no read was listed for the many-placement pass, the last block publishes right away and marks the
+// set done — the pass that follows in the chain then has nothing to do, and the host has its result one kernel earlier.
+__device__ __noinline__ void finish_blocks(PublishArgs A, bool early) {
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(P.ticket, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
-  __threadfence();
-  unsigned long long a[7];
-  for (int j = 0; j < 7; j++) a[j] = __ldcg(P.accum + j);
-  unsigned __int128 x = 0;
-  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
-  if (P.state_acc) {
-    // paired sets keep their running total {low, high 64 bits, floored, -inf, nan} on the device: a delta-only
-    // evaluation accumulated (new term - old term) of the touched reads and adds it, any other sets it
-    if (P.state_add) {
-      x += ((unsigned __int128)__ldcg(P.state_acc + 1) << 64) | (unsigned __int128)__ldcg(P.state_acc);
-      for (int j = 4; j < 7; j++) a[j] += __ldcg(P.state_acc + j - 2);
-    }
-    P.state_acc[0] = (unsigned long long)x;
-    P.state_acc[1] = (unsigned long long)(x >> 64);
-    for (int j = 4; j < 7; j++) P.state_acc[j - 2] = a[j];
+  if (early) {
+    __threadfence();
+    if (__ldcg(A.ovf_count) != 0) return;
   }
-  const __int128 v = (__int128)x;
-  P.out[0] = (double)(long long)(v >> 40);
-  P.out[1] = (double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
-  P.out[2] = (double)a[4];
-  P.out[3] = (double)a[5];
-  P.out[4] = (double)a[6];
-  P.out[5] = (double)__ldcg(P.error_flag) + 16.0 * (double)__ldcg(P.ovf_count);
-  // P.out is host-mapped pinned memory: publish the values, then the completion flag the host spins on
-  __threadfence_system();
-  *reinterpret_cast<volatile double*>(P.out + 6) = (double)P.epoch;
+  publish_set(A);
+  if (early) *A.done = 1u;
 }
+__device__ __forceinline__ void finish_set(const ScoreParams& P) { finish_blocks(publish_args(P, P.ticket2), false); }
+__device__ __forceinline__ void finish_set_if_complete(const ScoreParams& P) { finish_blocks(publish_args(P, P.ticket), true); }
 
 // ---- log and division ------------------------------------------------------------------------------
 // log(v) for positive normal finite v from a 128-entry table {1/c, -log(1/c)} (host-built in long double,
@@ -431,6 +482,103 @@ __device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double&
   return paired_read_with<kCompact>(P, P.epoch, P.epoch, r, acc);
 }
 
+// Level-batched form of paired_read for the shapes the ordered paths mostly see (incremental evaluations, where a
+// record's key is usually live twice — on the erased walk and on the added one — and the multi / many-placement
+// passes). paired_read walks one dependent load after
+// another (first record -> slot A -> slot B -> further occurrences -> next row ...) per mate; these kernels run one
+// read per thread, so that chain IS their run time. Here everything at the same depth is issued together for both
+// mates: {first records, lengths} -> {the other rows} -> {both slot words of every row} -> {second occurrences}.
+// Covers up to four records per mate, keys occurring at most twice, at most four live placements per mate.
+// Returns 1 = scored, -1 = shape not covered.
+__device__ __forceinline__ void few_push(Few& t, int walk, int seg, int cur, int skip, const int4& rw, int idx) {
+  const int pos = wrap_add(rw.y, cur);
+  if (pos < skip) return;   // graph.cc:577
+  const unsigned long long ord = ((unsigned long long)(uint32_t)seg << 32) | (uint32_t)idx;
+#pragma unroll
+  for (int j = 0; j < kFew; j++)
+    if (t.n == j) { t.ord[j] = ord; t.walk[j] = walk; t.pos[j] = pos; t.edor[j] = rw.z; }
+  t.n++;
+}
+
+constexpr int kBatchRec = 4;   // records per mate the level-batched path loads (absent ones are predicated off)
+
+__device__ __forceinline__ int paired_read_fast(const ScoreParams& P, int r, double& acc) {
+  int4 rw[2][kBatchRec], sa[2][kBatchRec], sb[2][kBatchRec], oc[2][kBatchRec];
+  int cnt[2];
+  rw[0][0] = ldg4(static_cast<const int4*>(P.m[0].first) + r);
+  rw[1][0] = ldg4(static_cast<const int4*>(P.m[1].first) + r);
+  const uint32_t ll = __ldg(P.lens + r);
+  if (rw[0][0].x < 0 || rw[1][0].x < 0) return 1;   // a mate without any record: no pair term can exist
+  cnt[0] = (rw[0][0].z >> 16) & 0x3fff;
+  cnt[1] = (rw[1][0].z >> 16) & 0x3fff;
+  if (cnt[0] > kBatchRec || cnt[1] > kBatchRec) return -1;
+  // level 2: the other rows
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const RowShort* rows = static_cast<const RowShort*>(P.m[m].rows) + (uint32_t)rw[m][0].w;
+#pragma unroll
+    for (int i = 1; i < kBatchRec; i++) rw[m][i] = i < cnt[m] ? ldg4(rows + i) : rw[m][0];
+    rw[m][0].z &= 0x4000ffff;
+  }
+  // level 3: both slot words of every row (an absent row repeats the first row's key: same cache line)
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int i = 0; i < kBatchRec; i++) {
+      sa[m][i] = ldg4(P.m[m].slots_a + rw[m][i].x);
+      sb[m][i] = ldg4(P.m[m].slots_b + rw[m][i].x);
+    }
+  const uint32_t e = P.epoch;
+  bool live[2][kBatchRec];
+  bool too_many = false;
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int i = 0; i < kBatchRec; i++) {
+      live[m][i] = i < cnt[m] && ((uint32_t)sa[m][i].x & 0x7fffffffu) == e;
+      too_many |= live[m][i] && sb[m][i].y > 2;
+    }
+  if (too_many) return -1;
+  // level 4: the second occurrence of the keys that have one
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int i = 0; i < kBatchRec; i++)
+      oc[m][i] = (live[m][i] && sb[m][i].y == 2) ? ldg4(P.m[m].occ + sb[m][i].z + 1) : make_int4(0, 0, 0, 0);
+  Few t[2];
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    t[m].n = 0;
+#pragma unroll
+    for (int i = 0; i < kBatchRec; i++) {
+      if (!live[m][i]) continue;
+      few_push(t[m], sa[m][i].y, sb[m][i].x, sa[m][i].z, sa[m][i].w, rw[m][i], i);
+      if (sb[m][i].y == 2) few_push(t[m], oc[m][i].x, oc[m][i].y, oc[m][i].z, oc[m][i].w, rw[m][i], i);
+    }
+  }
+  if (t[0].n == 0 || t[1].n == 0) return 1;
+  if (t[0].n > kFew || t[1].n > kFew) return -1;
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  const unsigned va = order_few(t[0]), vb = order_few(t[1]);
+#pragma unroll
+  for (int x = 0; x < kFew; x++) {
+    if (!((va >> x) & 1u)) continue;
+    const double p1 = align_prob(P.m[0], t[0].edor[x], l1);
+#pragma unroll
+    for (int y = 0; y < kFew; y++)
+      if ((vb >> y) & 1u)
+        one_pair(P, t[0].walk[x], t[0].pos[x], t[0].edor[x], t[1].walk[y], t[1].pos[y], t[1].edor[y], l1, l2, p1, acc);
+  }
+  return 1;
+}
+
+// The ordered register paths in turn: level-batched shapes first, then the general walk; false = scratch path.
+__device__ __forceinline__ bool paired_read_ordered(const ScoreParams& P, int r, double& acc) {
+  const int st = paired_read_fast(P, r, acc);
+  if (st > 0) return true;
+  return paired_read(P, r, acc);
+}
+
 // General replay from placement lists in memory (scratch path).
 template <class E>
 __device__ int gather_short(const MateView& mv, const E& epoch, int r, Plc* out) {
@@ -495,7 +643,7 @@ __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
 // issued up front (both key slots, the four pow-table entries), so a read costs three memory round trips: the
 // coalesced first-records, the slot/pow batch, the insert-pdf entry. sa1/sa2 are the packed 16-byte slot words
 // {epoch|multi<<31, walk, cur_pos, skip_below} (L1/L2 resident). Returns false when the read is not tier 1's to
-// score (tier-2 read, or a key with several occurrences -> scratch path).
+// score (tier-2 read, or a key with several occurrences -> paired_multi_kernel).
 __device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const int4* __restrict__ sa1,
                                                   const int4* __restrict__ sa2, int r, const int4& rw1, const int4& rw2,
                                                   uint32_t ll, double& acc) {
@@ -506,13 +654,12 @@ __device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const in
   const int e1 = rw1.z & 0xffff, e2 = rw2.z & 0xffff;
   const double a1 = __ldg(P.m[0].pow_mismatch + e1), b1 = __ldg(P.m[0].pow_match + (l1 - e1));
   const double a2 = __ldg(P.m[1].pow_mismatch + e2), b2 = __ldg(P.m[1].pow_match + (l2 - e2));
-  if (rw1.x < 0 || rw2.x < 0) return true;
   const uint32_t f1 = (uint32_t)o1.x, f2 = (uint32_t)o2.x;
-  if ((f1 & 0x7fffffffu) != P.epoch || (f2 & 0x7fffffffu) != P.epoch) return true;
-  if ((f1 | f2) >> 31) {
-    push_overflow(P, r);
-    return false;
-  }
+  const bool live1 = rw1.x >= 0 && (f1 & 0x7fffffffu) == P.epoch, live2 = rw2.x >= 0 && (f2 & 0x7fffffffu) == P.epoch;
+  // a record under a key that occurs several times in this evaluation: the read belongs to paired_multi_kernel, which
+  // enumerates exactly the records of those keys (either mate), so it is skipped here, not listed
+  if ((live1 && (f1 >> 31)) || (live2 && (f2 >> 31))) return false;
+  if (!live1 || !live2) return true;
   const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
   if (p1 < o1.w || p2 < o2.w || o1.y != o2.y) return true;   // skip rule (graph.cc:577); pairs only inside one walk
   const int xo = (rw1.z >> 30) & 1, yo = (rw2.z >> 30) & 1;
@@ -532,61 +679,19 @@ __device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const in
   return true;
 }
 
-__global__ void __launch_bounds__(kBlock) paired_full_kernel(const ScoreParams P) {
-  const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
-  const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
-  const double2* log_tab = static_cast<const double2*>(P.log_tab);
-  Acc sum = acc_zero();
-  unsigned floored = 0;
-  const int4* first1 = static_cast<const int4*>(P.m[0].first);
-  const int4* first2 = static_cast<const int4*>(P.m[1].first);
-  const int stride = gridDim.x * blockDim.x;
-  const int n = P.n_reads;
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  // The cache (first-records, lengths) is static: pull the first iteration's lines towards L2 while the previous
-  // kernel of the chain (apply_slots) is still running, then wait for it before the slot words are read.
-  if (r + stride < n && (threadIdx.x & 7) == 0) {   // 8 consecutive 16-byte records = one 128-byte line
-    prefetch_l2(first1 + r); prefetch_l2(first2 + r); prefetch_l2(first1 + r + stride); prefetch_l2(first2 + r + stride);
-  }
-  pdl_wait();
-  pdl_release();   // AFTER the wait: tier 2 (next in the chain) starts without a wait of its own, see there
-  // Two reads per iteration: six independent coalesced loads in flight per thread before any use, and the two
-  // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
-  // (Measured dead ends, profiles/r01_summary.md: register double-buffering of the next iteration's loads and
-  //  staging the slot words + log table in shared memory both cost registers/instructions and gained nothing.)
-  for (; r + stride < n; r += 2 * stride) {
-    const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
-    const int4 b1 = __ldg(first1 + r + stride), b2 = __ldg(first2 + r + stride);
-    const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + stride);
-    double acc_a, acc_b;
-    const bool ok_a = paired_simple_acc(P, sa1, sa2, r, a1, a2, la, acc_a);
-    const bool ok_b = paired_simple_acc(P, sa1, sa2, r + stride, b1, b2, lb, acc_b);
-    const double thr_a = __ldg(P.thr_tab + (la & 0xffff) + (la >> 16)), thr_b = __ldg(P.thr_tab + (lb & 0xffff) + (lb >> 16));
-    unsigned fa = 0, fb = 0;
-    const double ta = floored_term(P, log_tab, acc_a, thr_a, fa), tb = floored_term(P, log_tab, acc_b, thr_b, fb);
-    if (ok_a) { P.values[r] = acc_a; acc_add(sum, ta); floored += fa; }
-    if (ok_b) { P.values[r + stride] = acc_b; acc_add(sum, tb); floored += fb; }
-  }
-  if (r < n) {
-    const uint32_t ll = __ldg(P.lens + r);
-    double acc;
-    if (paired_simple_acc(P, sa1, sa2, r, __ldg(first1 + r), __ldg(first2 + r), ll, acc)) {
-      P.values[r] = acc;
-      acc_add(sum, floored_term(P, log_tab, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
-    }
-  }
-  block_accumulate(sum, floored, P.accum);
-}
-
-// FULL, tier 2: the reads that own several records on a mate (list built once per cache commit), one thread
-// each, at most two live placements per mate in registers; anything bigger goes to the scratch path.
-// One record of a tier-2 read placed through the global slot table (word A only).
+// FULL, tier 2 (second phase of the streaming kernel): the reads that own exactly two records on a mate and at most two on the other — (1,2), (2,1), (2,2)
+// and the pairless (0,2), (2,0) — from a list built once per cache commit, class ordered, so a warp holds reads of ONE
+// shape and the kernel is straight-line code with compile-time record counts. The records sit in a compact copy in
+// list order; within a class every read owns the same number of rows, so the row addresses follow from the list index
+// alone and the rows are requested together with the read's descriptor (three memory levels per read, like tier 1:
+// {descriptor, rows} -> slot words -> pow/insert tables). Reads with three or more records on a mate are rare and go
+// to paired_multi_kernel's static list.
 struct Placed1 { bool live; bool multi; int walk, pos, edor; };
-__device__ __forceinline__ Placed1 place_row(const ScoreParams& P, int m, const int4& rw, bool present) {
+__device__ __forceinline__ Placed1 place_row(const ScoreParams& P, int m, const int4& rw) {
   Placed1 p;
-  const int4 a = ldg4(P.m[m].slots_a + (present ? rw.x : 0));
+  const int4 a = ldg4(P.m[m].slots_a + rw.x);   // {epoch | multi<<31, walk, cur_pos, skip_below}
   const uint32_t ef = (uint32_t)a.x;
-  p.live = present && (ef & 0x7fffffffu) == P.epoch;
+  p.live = (ef & 0x7fffffffu) == P.epoch;
   p.multi = p.live && (ef >> 31);
   p.walk = a.y;
   p.pos = wrap_add(rw.y, a.z);
@@ -595,99 +700,316 @@ __device__ __forceinline__ Placed1 place_row(const ScoreParams& P, int m, const 
   return p;
 }
 
-__global__ void __launch_bounds__(kBlock) paired_complex_kernel(const ScoreParams P) {
-  // Tier 2 needs nothing from tier 1 (disjoint reads, commutative integer accumulators, atomic list appends) — only
-  // the slot words and zeroed flags of apply_slots. Tier 1 releases this kernel after ITS wait on apply_slots, so
-  // every block here starts after apply_slots has completed and runs beside tier 1's tail without waiting. The wait
-  // moves to the END of the kernel: it makes "tier 2 complete" imply "tier 1 complete" for the kernel after it.
-  pdl_release();
-  Acc sum = acc_zero();
-  unsigned floored = 0;
-  const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
-  const RowShort* rows2 = static_cast<const RowShort*>(P.m[1].crows);
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
-    // one coalesced 16-byte descriptor per listed read {read, packed lengths, first row mate 1, first row mate 2}; the
-    // record counts follow from the read's class (the list is class ordered), so nothing else is loaded before the rows
-    const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);
-    const int r = dsc.x;
-    const uint32_t ll = (uint32_t)dsc.y;
-    const uint32_t b1 = (uint32_t)dsc.z, b2 = (uint32_t)dsc.w;
-    int cls = 0;
-#pragma unroll
-    for (int c = 1; c < 16; c++) cls += (k >= P.class_begin[c]) ? 1 : 0;   // class_begin[c] = first list index of class c
-    int n1 = cls >> 2, n2 = cls & 3;                                       // class id = min(cnt1,3)*4 + min(cnt2,3)
-    if (n1 == 3) n1 = (int)(__ldg(P.m[0].cptr + k + 1) - b1);
-    if (n2 == 3) n2 = (int)(__ldg(P.m[1].cptr + k + 1) - b2);
-    double acc = 0.0;
-    bool done = false;
-    if (n1 <= 3 && n2 <= 3) {
-      // Straight-line path for the shapes that make up this tier — up to three records per mate of which at most
-      // two are LIVE in this evaluation (typically: the same alignment under the window key and the single-node key,
-      // plus one alignment elsewhere): at most four candidate pairs. The state starts from 0 and every walk is
-      // "added" here (full evaluation), so with at most two non-dropped pairs the sum is order independent
-      // (0+a+b == 0+b+a). A duplicate placement (same walk, same position) with an identical payload is dropped
-      // whichever record is "later". Anything that really needs the enumeration order — a duplicate with a different
-      // payload, a repeated key, three live placements, three or more terms — goes to the ordered paths.
-      const int4 z = make_int4(0, 0, 0, 0);
-      const int4 rx0 = n1 > 0 ? ldg4(rows1 + b1) : z, rx1 = n1 > 1 ? ldg4(rows1 + b1 + 1) : z, rx2 = n1 > 2 ? ldg4(rows1 + b1 + 2) : z;
-      const int4 ry0 = n2 > 0 ? ldg4(rows2 + b2) : z, ry1 = n2 > 1 ? ldg4(rows2 + b2 + 1) : z, ry2 = n2 > 2 ? ldg4(rows2 + b2 + 2) : z;
-      Placed1 x0 = place_row(P, 0, rx0, n1 > 0), x1 = place_row(P, 0, rx1, n1 > 1);
-      const Placed1 x2 = place_row(P, 0, rx2, n1 > 2);
-      Placed1 y0 = place_row(P, 1, ry0, n2 > 0), y1 = place_row(P, 1, ry1, n2 > 1);
-      const Placed1 y2 = place_row(P, 1, ry2, n2 > 2);
-      bool too_many = false;
-      if (x2.live) {   // keep the (at most two) live ones in x0, x1
-        if (!x0.live) x0 = x2; else if (!x1.live) x1 = x2; else too_many = true;
-      }
-      if (y2.live) {
-        if (!y0.live) y0 = y2; else if (!y1.live) y1 = y2; else too_many = true;
-      }
-      bool need_order = too_many || x0.multi || x1.multi || y0.multi || y1.multi;
-      if (x0.live && x1.live && x0.walk == x1.walk && x0.pos == x1.pos) {
-        if (x0.edor == x1.edor) x1.live = false; else need_order = true;
-      }
-      if (y0.live && y1.live && y0.walk == y1.walk && y0.pos == y1.pos) {
-        if (y0.edor == y1.edor) y1.live = false; else need_order = true;
-      }
-      if (!need_order) {
-        const int l1 = ll & 0xffff, l2 = ll >> 16;
-        double t0 = 0.0, t1 = 0.0;   // the first two non-dropped terms (more than two -> scratch path)
-        int w0 = 0, xp0 = 0, yp0 = 0, w1 = 0, xp1 = 0, yp1 = 0;
-        int nt = 0;
-        const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = align_prob(P.m[0], x1.edor, l1);
-        double tt;
+// One tier-2 read with N1 / N2 records. 1 = scored (acc), 0 = belongs to paired_multi_kernel (a live key occurs
+// several times), -1 = needs the enumeration order (many-placement pass).
+// The state starts from 0 and every walk is "added" (full evaluation), so with at most two non-dropped pair terms the
+// sum is order independent (0+a+b == 0+b+a). A duplicate placement (same walk, same position) with an identical
+// payload is dropped whichever record is "later"; one with a different payload, or three and more terms, need the order.
+template <int N1, int N2>
+__device__ __forceinline__ int tier2_read(const ScoreParams& P, const RowShort* __restrict__ rows1,
+                                          const RowShort* __restrict__ rows2, uint32_t b1, uint32_t b2, uint32_t ll, double& acc) {
+  acc = 0.0;
+  if (N1 == 0 || N2 == 0) return 1;   // no record on a mate: no pair term
+  const int4 rx0 = ldg4(rows1 + b1), rx1 = N1 > 1 ? ldg4(rows1 + b1 + 1) : rx0;
+  const int4 ry0 = ldg4(rows2 + b2), ry1 = N2 > 1 ? ldg4(rows2 + b2 + 1) : ry0;
+  Placed1 x0 = place_row(P, 0, rx0), x1 = place_row(P, 0, rx1);
+  Placed1 y0 = place_row(P, 1, ry0), y1 = place_row(P, 1, ry1);
+  if (N1 < 2) x1.live = x1.multi = false;
+  if (N2 < 2) y1.live = y1.multi = false;
+  if (x0.multi || x1.multi || y0.multi || y1.multi) return 0;
+  if (N1 > 1 && x0.live && x1.live && x0.walk == x1.walk && x0.pos == x1.pos) {
+    if (x0.edor == x1.edor) x1.live = false; else return -1;
+  }
+  if (N2 > 1 && y0.live && y1.live && y0.walk == y1.walk && y0.pos == y1.pos) {
+    if (y0.edor == y1.edor) y1.live = false; else return -1;
+  }
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  double t0 = 0.0, t1 = 0.0;   // the first two non-dropped terms
+  int w0 = 0, xp0 = 0, yp0 = 0, w1 = 0, xp1 = 0, yp1 = 0;
+  int nt = 0;
+  const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = N1 > 1 ? align_prob(P.m[0], x1.edor, l1) : 0.0;
+  double tt;
 #define GAML_TRY_PAIR(X, Y, PX)                                                                                         \
   if (X.live && Y.live && X.walk == Y.walk && pair_term(P, -1, X.pos, X.edor, Y.pos, Y.edor, l1, l2, PX, tt)) {         \
     if (nt == 0) { t0 = tt; w0 = X.walk; xp0 = X.pos; yp0 = Y.pos; }                                                    \
     else if (nt == 1) { t1 = tt; w1 = X.walk; xp1 = X.pos; yp1 = Y.pos; }                                               \
     nt++;                                                                                                               \
   }
-        GAML_TRY_PAIR(x0, y0, px0)
-        GAML_TRY_PAIR(x0, y1, px0)
-        GAML_TRY_PAIR(x1, y0, px1)
-        GAML_TRY_PAIR(x1, y1, px1)
+  GAML_TRY_PAIR(x0, y0, px0)
+  if (N2 > 1) { GAML_TRY_PAIR(x0, y1, px0) }
+  if (N1 > 1) { GAML_TRY_PAIR(x1, y0, px1) }
+  if (N1 > 1 && N2 > 1) { GAML_TRY_PAIR(x1, y1, px1) }
 #undef GAML_TRY_PAIR
-        if (nt <= 2) {
-          if (nt >= 1) { acc = __dadd_rn(acc, t0); emit_cov(P, w0, xp0, yp0, l2, t0); }
-          if (nt == 2) { acc = __dadd_rn(acc, t1); emit_cov(P, w1, xp1, yp1, l2, t1); }
-          done = true;
-        }
-      }
+  if (nt > 2) return -1;
+  if (nt >= 1) { acc = __dadd_rn(acc, t0); emit_cov(P, w0, xp0, yp0, l2, t0); }
+  if (nt == 2) { acc = __dadd_rn(acc, t1); emit_cov(P, w1, xp1, yp1, l2, t1); }
+  return 1;
+}
+
+// Tier-2 phase of the streaming kernel: tiles of 256 list entries, a block's first tile is its own index.
+__device__ __forceinline__ void tier2_tiles(const ScoreParams& P, int* s_tile, Acc& sum, unsigned& floored) {
+  const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
+  const RowShort* rows2 = static_cast<const RowShort*>(P.m[1].crows);
+  const int n_tiles = (P.n_main + kBlock - 1) / kBlock;
+  int tile = blockIdx.x, buf = 0;
+  for (; tile < n_tiles; __syncthreads(), tile = s_tile[buf], buf ^= 1) {
+    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 2, 1u);
+    const int k = tile * kBlock + (int)threadIdx.x;
+    if (k >= P.n_main) continue;
+    // list classes in order: (1,2) (2,1) (2,2) (0,2) (2,0); descriptor {read, packed lengths, -, -}
+    int cls = 0;
+#pragma unroll
+    for (int c = 1; c < 5; c++) cls += (k >= P.class_begin[c]) ? 1 : 0;
+    const uint32_t j = (uint32_t)(k - P.class_begin[cls]);
+    const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);
+    const int r = dsc.x;
+    const uint32_t ll = (uint32_t)dsc.y;
+    double acc;
+    int st;
+    switch (cls) {
+      case 0: st = tier2_read<1, 2>(P, rows1, rows2, P.cbase[0][0] + j, P.cbase[1][0] + 2 * j, ll, acc); break;
+      case 1: st = tier2_read<2, 1>(P, rows1, rows2, P.cbase[0][1] + 2 * j, P.cbase[1][1] + j, ll, acc); break;
+      case 2: st = tier2_read<2, 2>(P, rows1, rows2, P.cbase[0][2] + 2 * j, P.cbase[1][2] + 2 * j, ll, acc); break;
+      default: st = 1; acc = 0.0; break;   // (0,2), (2,0): no pair term
     }
-    if (done) {
+    if (st > 0) {
       P.values[r] = acc;
       acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
-    } else {
+    } else if (st < 0) {
       push_overflow(P, r);
     }
   }
-  pdl_wait();
+}
+
+// Rare-shape phase of the streaming kernel: the listed reads with three or more records on a mate (list entries
+// [n_main, n_complex)). Their records are walked in a loop — row from the compact copy, then its slot word — keeping
+// at most two live, distinct placements per mate, which is what nearly all of them have in any one evaluation (most of
+// a read's extra records sit under keys of joins that are not part of the current walks). Same rules as tier2_read:
+// a live key that occurs several times -> the read is the multi pass's; anything that needs the enumeration order
+// (three live placements, a duplicate with a different payload, three pair terms) -> many-placement pass.
+struct TwoLive { Placed1 p0, p1; int n; bool multi, order; };
+__device__ __forceinline__ void two_live_scan(const ScoreParams& P, int m, const RowShort* __restrict__ rows, uint32_t b,
+                                              uint32_t n, TwoLive& t) {
+  t.n = 0;
+  t.multi = t.order = false;
+  t.p0 = t.p1 = Placed1{false, false, 0, 0, 0};   // (pair_up indexes the pow tables with edor even for absent placements)
+  for (uint32_t i = 0; i < n; i += 2) {   // two rows per step: their slot words are requested together
+    const int4 r0 = ldg4(rows + b + i), r1 = i + 1 < n ? ldg4(rows + b + i + 1) : r0;
+    Placed1 q[2] = {place_row(P, m, r0), place_row(P, m, r1)};
+    if (i + 1 >= n) q[1].live = q[1].multi = false;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (!q[j].live) continue;
+      t.multi |= q[j].multi;
+      if (t.n > 0 && t.p0.walk == q[j].walk && t.p0.pos == q[j].pos) {
+        if (t.p0.edor != q[j].edor) t.order = true;
+      } else if (t.n > 1 && t.p1.walk == q[j].walk && t.p1.pos == q[j].pos) {
+        if (t.p1.edor != q[j].edor) t.order = true;
+      } else if (t.n == 0) {
+        t.p0 = q[j];
+        t.n = 1;
+      } else if (t.n == 1) {
+        t.p1 = q[j];
+        t.n = 2;
+      } else {
+        t.order = true;
+      }
+    }
+  }
+}
+
+// Pair terms of up to two live placements per mate; false when three or more terms survive (order matters then).
+__device__ __forceinline__ bool pair_up(const ScoreParams& P, const Placed1& x0, const Placed1& x1, const Placed1& y0,
+                                        const Placed1& y1, uint32_t ll, double& acc) {
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  double t0 = 0.0, t1 = 0.0;   // the first two non-dropped terms
+  int w0 = 0, xp0 = 0, yp0 = 0, w1 = 0, xp1 = 0, yp1 = 0;
+  int nt = 0;
+  const double px0 = align_prob(P.m[0], x0.edor, l1), px1 = align_prob(P.m[0], x1.edor, l1);
+  double tt;
+#define GAML_TRY_PAIR(X, Y, PX)                                                                                         \
+  if (X.live && Y.live && X.walk == Y.walk && pair_term(P, -1, X.pos, X.edor, Y.pos, Y.edor, l1, l2, PX, tt)) {         \
+    if (nt == 0) { t0 = tt; w0 = X.walk; xp0 = X.pos; yp0 = Y.pos; }                                                    \
+    else if (nt == 1) { t1 = tt; w1 = X.walk; xp1 = X.pos; yp1 = Y.pos; }                                               \
+    nt++;                                                                                                               \
+  }
+  GAML_TRY_PAIR(x0, y0, px0)
+  GAML_TRY_PAIR(x0, y1, px0)
+  GAML_TRY_PAIR(x1, y0, px1)
+  GAML_TRY_PAIR(x1, y1, px1)
+#undef GAML_TRY_PAIR
+  if (nt > 2) return false;
+  acc = 0.0;
+  if (nt >= 1) { acc = __dadd_rn(acc, t0); emit_cov(P, w0, xp0, yp0, l2, t0); }
+  if (nt == 2) { acc = __dadd_rn(acc, t1); emit_cov(P, w1, xp1, yp1, l2, t1); }
+  return true;
+}
+
+__device__ __forceinline__ void rare_tiles(const ScoreParams& P, int* s_tile, Acc& sum, unsigned& floored) {
+  const RowShort* rows1 = static_cast<const RowShort*>(P.m[0].crows);
+  const RowShort* rows2 = static_cast<const RowShort*>(P.m[1].crows);
+  const int n_rare = P.n_complex - P.n_main;
+  const int n_tiles = (n_rare + kBlock - 1) / kBlock;
+  int tile = blockIdx.x, buf = 0;
+  for (; tile < n_tiles; __syncthreads(), tile = s_tile[buf], buf ^= 1) {
+    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 1, 1u);
+    const int k = P.n_main + tile * kBlock + (int)threadIdx.x;
+    if (k >= P.n_complex) continue;
+    const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);   // {read, packed lengths, first compact row mate 1, mate 2}
+    const uint32_t e1 = __ldg(P.m[0].cptr + k + 1), e2 = __ldg(P.m[1].cptr + k + 1);
+    const int r = dsc.x;
+    const uint32_t ll = (uint32_t)dsc.y;
+    TwoLive x, y;
+    two_live_scan(P, 0, rows1, (uint32_t)dsc.z, e1 - (uint32_t)dsc.z, x);
+    two_live_scan(P, 1, rows2, (uint32_t)dsc.w, e2 - (uint32_t)dsc.w, y);
+    if (x.multi || y.multi) continue;   // the multi pass's read
+    double acc = 0.0;
+    if (x.order || y.order || !pair_up(P, x.p0, x.p1, y.p0, y.p1, ll, acc)) {
+      push_overflow(P, r);
+      continue;
+    }
+    P.values[r] = acc;
+    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+  }
+}
+
+// FULL, the streaming kernel: tier 1 (every read with at most one record per mate, straight from the dense
+// first-record arrays) and then tier 2 (the static list of reads with two records on a mate, from the compact copy) in
+// one launch — both are tile loops over static data drawn from counters, so a block simply moves on to tier-2 tiles when
+// the tier-1 tiles run out, without a kernel boundary (ramp, tail, launch) in between.
+__global__ void __launch_bounds__(kBlock, 5) paired_stream_kernel(const ScoreParams P) {
+  tl_begin(P.timeline, kTlTier1);
+  const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
+  const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
+  Acc sum = acc_zero();
+  unsigned floored = 0;
+  const int4* first1 = static_cast<const int4*>(P.m[0].first);
+  const int4* first2 = static_cast<const int4*>(P.m[1].first);
+  const int n = P.n_reads;
+  // Work is handed out in tiles of 2 x 256 consecutive reads from a counter (zeroed by apply_slots): blocks that
+  // become resident late — the multi pass in front of this kernel holds part of the register file for a while — or run
+  // slowly simply take fewer tiles. The exact integer accumulators make the result independent of who sums what.
+  // A block's first tile is its own index, so its lines can be pulled towards L2 before the wait below.
+  constexpr int kTile = 2 * kBlock;
+  const int n_tiles = (n + kTile - 1) / kTile;
+  __shared__ int s_tile[2];
+  int tile = blockIdx.x, buf = 0;
+  if (tile < n_tiles && (threadIdx.x & 7) == 0) {   // 8 consecutive 16-byte records = one 128-byte line
+    const int r0 = min(tile * kTile + (int)threadIdx.x, n - 1), r1 = min(r0 + kBlock, n - 1);
+    prefetch_l2(first1 + r0); prefetch_l2(first2 + r0); prefetch_l2(first1 + r1); prefetch_l2(first2 + r1);
+  }
+  // First kernel after apply_slots (no multi pass before it): wait here, release after. Otherwise the multi pass did
+  // that, every block of this kernel starts after apply_slots completed, and the wait moves to the end.
+  if (P.chain_first) pdl_wait();
+  pdl_release();   // AFTER the wait: the next streaming kernel starts without a wait of its own, see tier 2
+  // The rare-shape tiles go first: their long dependent chains overlap with everything after them instead of forming
+  // the kernel's tail.
+  if (P.n_complex > P.n_main) {
+    rare_tiles(P, s_tile, sum, floored);
+    __syncthreads();
+  }
+  // Two reads per thread and tile: six independent coalesced loads in flight per thread before any use, and the two
+  // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
+  // (Measured dead ends, profiles/r01_summary.md: register double-buffering of the next iteration's loads and
+  //  staging the slot words + log table in shared memory both cost registers/instructions and gained nothing.)
+  while (tile < n_tiles) {
+    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // next tile, used after this one
+    const int r = tile * kTile + (int)threadIdx.x;
+    if (tile * kTile + kTile <= n) {
+      const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
+      const int4 b1 = __ldg(first1 + r + kBlock), b2 = __ldg(first2 + r + kBlock);
+      const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + kBlock);
+      double acc_a, acc_b;
+      const bool ok_a = paired_simple_acc(P, sa1, sa2, r, a1, a2, la, acc_a);
+      const bool ok_b = paired_simple_acc(P, sa1, sa2, r + kBlock, b1, b2, lb, acc_b);
+      const double thr_a = __ldg(P.thr_tab + (la & 0xffff) + (la >> 16)), thr_b = __ldg(P.thr_tab + (lb & 0xffff) + (lb >> 16));
+      unsigned fa = 0, fb = 0;
+      const double ta = floored_term(P, log_tab, acc_a, thr_a, fa), tb = floored_term(P, log_tab, acc_b, thr_b, fb);
+      if (ok_a) { P.values[r] = acc_a; acc_add(sum, ta); floored += fa; }
+      if (ok_b) { P.values[r + kBlock] = acc_b; acc_add(sum, tb); floored += fb; }
+    } else {   // the last, partial tile
+      for (int q = r; q < n; q += kBlock) {
+        const uint32_t ll = __ldg(P.lens + q);
+        double acc;
+        if (paired_simple_acc(P, sa1, sa2, q, __ldg(first1 + q), __ldg(first2 + q), ll, acc)) {
+          P.values[q] = acc;
+          acc_add(sum, floored_term(P, log_tab, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+        }
+      }
+    }
+    __syncthreads();
+    tile = s_tile[buf];
+    buf ^= 1;
+  }
+  tl_end(P.timeline, kTlTier1);
+  if (P.n_main > 0) {
+    tl_begin(P.timeline, kTlTier2);
+    tier2_tiles(P, s_tile, sum, floored);
+    tl_end(P.timeline, kTlTier2);
+  }
+  if (!P.chain_first) pdl_wait();
   block_accumulate(sum, floored, P.accum);
+  if (P.finish_here) finish_set_if_complete(P);
+}
+
+
+// General replay of one read: the ordered register paths, then the scratch path (exact counts, scratch from a bump
+// allocator). Returns false when the scratch arena is exhausted (error flag set).
+__device__ __forceinline__ bool paired_read_any(const ScoreParams& P, int r, uint32_t ll, double& acc) {
+  if (paired_read_ordered(P, r, acc)) return true;   // at most four LIVE placements per mate
+  const int n1 = gather_short(P.m[0], P.epoch, r, nullptr), n2 = gather_short(P.m[1], P.epoch, r, nullptr);
+  const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
+  if (base + n1 + n2 > P.scratch_cap) {
+    atomicOr(P.error_flag, 2u);
+    return false;
+  }
+  Plc* a = P.scratch + base;
+  Plc* b = a + n1;
+  gather_short(P.m[0], P.epoch, r, a);
+  gather_short(P.m[1], P.epoch, r, b);
+  acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
+  return true;
+}
+
+// FULL, multi pass: the reads a full evaluation cannot stream — every read with a record under a key that occurs
+// several times in this evaluation (repeat nodes), enumerated from those keys' ranges of the key-major arenas of both
+// mates, like the delta kernel does. A read reachable twice is claimed once through its stamp. It depends on apply_slots only, so it is the FIRST kernel
+// of the chain after it: a small grid whose latency-bound, divergent work runs underneath the streaming kernels
+// instead of after them.
+__global__ void __launch_bounds__(kOvfBlock) paired_multi_kernel(const ScoreParams P) {
+  tl_begin(P.timeline, kTlDelta);
+  if (P.chain_first) pdl_wait();
+  pdl_release();
+  Acc sum = acc_zero();
+  unsigned floored = 0;
+  const uint32_t total = __ldg(P.mtouch_prefix + P.n_mtouch);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    int lo = 0, hi = P.n_mtouch;   // largest t with prefix[t] <= q
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.mtouch_prefix + mid) <= q) lo = mid; else hi = mid;
+    }
+    const TouchRange tr = P.mtouch[lo];
+    const ArenaShort* arena = lo < P.n_mtouch1 ? P.arena1 : P.arena2;
+    const int r = ldg4(arena + tr.begin + (q - __ldg(P.mtouch_prefix + lo))).x;
+    if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;   // reachable through several keys / both mates
+    const uint32_t ll = __ldg(P.lens + r);
+    double acc = 0.0;
+    if (!paired_read_any(P, r, ll, acc)) continue;
+    P.values[r] = acc;
+    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+  }
+  if (!P.chain_first) pdl_wait();
+  block_accumulate(sum, floored, P.accum);
+  if (P.finish_here) finish_set_if_complete(P);
+  tl_end(P.timeline, kTlDelta);
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
 // thread to stamp a read owns it and replays that read's subtract/add sequence.
-__global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams P) {
+__global__ void __launch_bounds__(kOvfBlock) paired_delta_kernel(const ScoreParams P) {
+  tl_begin(P.timeline, kTlDelta);
   pdl_release();
   pdl_wait();
   Acc sum = acc_zero();
@@ -704,7 +1026,7 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
     if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;
     const double old = P.values[r];
     double acc = old;
-    if (paired_read(P, r, acc)) {
+    if (paired_read_ordered(P, r, acc)) {
       P.values[r] = acc;
       if (P.delta_only) {   // same total length as the running total: swap this read's term in it
         const uint32_t ll = __ldg(P.lens + r);
@@ -718,15 +1040,25 @@ __global__ void __launch_bounds__(kBlock) paired_delta_kernel(const ScoreParams 
       push_overflow(P, r);
     }
   }
-  if (P.delta_only) block_accumulate(sum, floored, P.accum);
+  if (P.delta_only) {
+    block_accumulate(sum, floored, P.accum);
+    finish_set_if_complete(P);
+  }
+  tl_end(P.timeline, kTlDelta);
 }
 
-// Reads with more than two placements on a mate: exact counts, scratch from a bump allocator, same replay.
+// Many-placement pass: the reads the streaming / delta kernel listed because they need the enumeration order.
 // full_mode 1: full evaluation (state from 0, terms summed, per-set finalize); 0: delta followed by the O(R) total pass;
-// 2: delta-only evaluation (new term - old term into the running total, per-set finalize).
+// 2: delta-only evaluation (new term - old term into the running total, per-set finalize). In modes 1 and 2 the kernel
+// before it has already published the set when it listed nothing (P.done).
 __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreParams P, int full_mode) {
+  tl_begin(P.timeline, kTlOverflow);
   pdl_release();
   pdl_wait();
+  if (full_mode && __ldcg(P.done)) {
+    tl_end(P.timeline, kTlOverflow);
+    return;
+  }
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
@@ -735,22 +1067,7 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
     const double old = full_mode == 1 ? 0.0 : P.values[r];
     double acc = old;
     const uint32_t ll = __ldg(P.lens + r);
-    if (paired_read(P, r, acc)) {   // ordered register path: at most two LIVE placements per mate, any record count
-      P.values[r] = acc;
-    } else {
-      const int n1 = gather_short(P.m[0], P.epoch, r, nullptr), n2 = gather_short(P.m[1], P.epoch, r, nullptr);
-      const unsigned long long base = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
-      if (base + n1 + n2 > P.scratch_cap) {
-        atomicOr(P.error_flag, 2u);
-      } else {
-        Plc* a = P.scratch + base;
-        Plc* b = a + n1;
-        gather_short(P.m[0], P.epoch, r, a);
-        gather_short(P.m[1], P.epoch, r, b);
-        acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
-        P.values[r] = acc;
-      }
-    }
+    if (paired_read_any(P, r, ll, acc)) P.values[r] = acc;
     if (full_mode) {
       const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
       acc_add(sum, floored_term(P, acc, thr, floored));
@@ -765,10 +1082,12 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
     block_accumulate(sum, floored, P.accum);
     finish_set(P);
   }
+  tl_end(P.timeline, kTlOverflow);
 }
 
 // O(R) pass after a delta: GetTotalProb over the persistent probs (graph.cc:1495-1516).
 __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams P) {
+  tl_begin(P.timeline, kTlTotal);
   pdl_release();
   pdl_wait();
   Acc sum = acc_zero();
@@ -791,6 +1110,7 @@ __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams 
   }
   block_accumulate(sum, floored, P.accum);
   finish_set(P);
+  tl_end(P.timeline, kTlTotal);
 }
 
 // ---- single -------------------------------------------------------------------------------
@@ -821,7 +1141,7 @@ __device__ __forceinline__ bool single_read(const ScoreParams& P, int r, int len
 // Tier 1: reads with at most one record (static) whose key occurs at most once in this evaluation.
 __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P) {
   pdl_wait();
-  pdl_release();   // after the wait: tier 2 starts without one (see paired_complex_kernel)
+  pdl_release();   // after the wait: tier 2 starts without one (see launch_paired_full)
   Acc sum = acc_zero();
   unsigned floored = 0;
   const int4* first = static_cast<const int4*>(P.m[0].first);
@@ -847,7 +1167,7 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
 }
 
 __global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParams P) {
-  pdl_release();   // no wait here, one at the end: same chain discipline as paired_complex_kernel
+  pdl_release();   // no wait here, one at the end: same chain discipline as the paired streaming kernel
   Acc sum = acc_zero();
   unsigned floored = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_complex; k += gridDim.x * blockDim.x) {
@@ -1146,11 +1466,15 @@ __global__ void coverage_sweep_kernel(const unsigned long long* keys, unsigned n
 
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                                   unsigned long long* flags, int n_flag_words) {
+                                   unsigned long long* flags, int n_flag_words, unsigned long long* timeline) {
   pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  tl_begin(timeline, kTlApply);
   if (i < n_flag_words) flags[i] = 0ull;   // scratch cursor, error flag, overflow counters, tickets, accumulators
-  if (i >= n) return;
+  if (i >= n) {
+    tl_end(timeline, kTlApply);
+    return;
+  }
   const SlotUpdate u = upd[i];
   SlotA a;
   a.epoch_flag = epoch | (u.n_occ > 1 ? 0x80000000u : 0u);
@@ -1164,6 +1488,7 @@ __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* t
   b.pad = 0;
   tab_a[u.store][u.key] = a;
   tab_b[u.store][u.key] = b;
+  tl_end(timeline, kTlApply);
 }
 
 // ---- CSR build: arena (key-major) -> rows (read-major) --------------------------------------
@@ -1220,12 +1545,17 @@ __global__ void sort_rows_kernel(const uint32_t* rowptr, int n_reads, int4* rows
 
 // Static tier-2 list: reads owning more than one record on some mate, in read-id order (scan, not atomics,
 // so the list — and with it the association of the partial sums — is the same on every run).
-// class of a read for tier 2: 0 = tier 1 (at most one record per mate), else 1 + min(cnt1,3)*4 + min(cnt2,3)
+// class of a read for the static list: 0 = tier 1 (at most one record per mate), else 1 + rank, where the shapes
+// tier 2 streams come first — (1,2) (2,1) (2,2) (0,2) (2,0) = ranks 0..4 — and the shapes with three or more records
+// on a mate (the multi pass's static part) after them.
 __device__ __forceinline__ int complex_class(const int4* first1, const int4* first2, int r) {
   const int c1 = (first1[r].z >> 16) & 0x3fff;
   const int c2 = first2 ? ((first2[r].z >> 16) & 0x3fff) : 0;
   if (c1 < 2 && c2 < 2) return 0;
-  return 1 + min(c1, 3) * 4 + min(c2, 3);
+  const int id = min(c1, 3) * 4 + min(c2, 3);
+  //                       id: 0   1   2  3   4   5   6  7  8  9  10 11 12 13 14  15
+  constexpr int kRank[16] = {12, 13, 3, 5, 14, 15, 0, 6, 4, 1, 2, 7, 8, 9, 10, 11};
+  return 1 + kRank[id];
 }
 
 __global__ void complex_flags_kernel(const int4* first1, const int4* first2, int n_reads, uint32_t* flags, int cls) {
@@ -1294,8 +1624,8 @@ int score_grid(int which, int n_items, int sm_count) {
   if (which < 0 || which > 5) which = 0;
   if (per_sm[which] == 0) {
     switch (which) {
-      case kGridPairedFull: per_sm[which] = resident_blocks(paired_full_kernel, kBlock); break;
-      case kGridPairedComplex: per_sm[which] = resident_blocks(paired_complex_kernel, kBlock); break;
+      case kGridPairedFull: per_sm[which] = resident_blocks(paired_stream_kernel, kBlock); break;
+      case kGridPairedComplex: per_sm[which] = resident_blocks(paired_stream_kernel, kBlock); break;
       case kGridPairedTotal: per_sm[which] = resident_blocks(paired_total_kernel, kBlock); break;
       case kGridSingleFull: per_sm[which] = resident_blocks(single_full_kernel, kBlock); break;
       case kGridSingleComplex: per_sm[which] = resident_blocks(single_complex_kernel, kBlock); break;
@@ -1304,27 +1634,60 @@ int score_grid(int which, int n_items, int sm_count) {
   }
   return grid_for((size_t)n_items, kBlock, sm_count, per_sm[which]);
 }
-int overflow_grid(int sm_count) { return 8 * sm_count; }   // list length is unknown at launch: one resident wave of small blocks
+// The many-placement passes' list length is unknown at launch: one block per SM, grid-stride beyond (they usually find
+// nothing, or a few hundred reads; every extra block is an extra trip through the tail of the chain).
+int overflow_grid(int sm_count) { return sm_count; }
 
 // One kernel of an evaluation's chain; pdl = launched as a programmatic dependent of the kernel before it on `st`.
-template <class... KArgs, class... Args>
-void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args&&... args) {
+thread_local LaunchList* g_recorder = nullptr;
+void set_launch_recorder(LaunchList* list) { g_recorder = list; }
+
+cudaError_t issue_launch(const PendingLaunch& pl, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(pl.block);
   cfg.stream = st;
   cudaLaunchAttribute attr{};
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  cfg.numAttrs = pl.pdl ? 1 : 0;
+  return cudaLaunchKernelExC(&cfg, pl.func, const_cast<void**>(pl.arg_ptrs));
+}
+
+template <class T>
+void pack_arg(PendingLaunch& pl, size_t& off, const T& v) {
+  off = (off + alignof(T) - 1) & ~(alignof(T) - 1);
+  memcpy(pl.arg_buf + off, &v, sizeof(T));
+  pl.arg_ptrs[pl.n_args++] = pl.arg_buf + off;
+  off += sizeof(T);
+}
+
+template <class... KArgs, class... Args>
+void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args&&... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
+  static_assert((sizeof(KArgs) + ... + 0) + 16 * sizeof...(KArgs) <= sizeof(PendingLaunch::arg_buf), "argument buffer too small");
+  PendingLaunch local;
+  LaunchList* rec = g_recorder;
+  PendingLaunch& pl = (rec && rec->n < 16) ? rec->item[rec->n] : local;
+  pl.func = reinterpret_cast<const void*>(kernel);
+  pl.grid = (unsigned)grid;
+  pl.block = (unsigned)block;
+  pl.pdl = pdl;
+  pl.n_args = 0;
+  size_t off = 0;
+  (pack_arg<std::remove_cv_t<std::remove_reference_t<KArgs>>>(pl, off, static_cast<std::remove_cv_t<std::remove_reference_t<KArgs>>>(args)), ...);
+  if (rec && rec->n < 16) {
+    rec->n++;
+    return;
+  }
+  issue_launch(pl, st);
 }
 
 void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                        unsigned long long* flags, int n_flag_words, cudaStream_t st) {
+                        unsigned long long* flags, int n_flag_words, unsigned long long* timeline, cudaStream_t st) {
   const int m = n > n_flag_words ? n : n_flag_words;
-  apply_slots_kernel<<<(m + 255) / 256, 256, 0, st>>>(upd, n, tab_a, tab_b, epoch, flags, n_flag_words);
+  launch_chain(apply_slots_kernel, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, epoch, flags, n_flag_words, timeline);
 }
 
 // Every wrapper below appends its kernels to the evaluation's chain. `chained` = the operation before it on `st` is a
@@ -1332,11 +1695,32 @@ void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB
 // kernel(s) of the set are bracketed by e0/e1 (the roofline timing); an event between two kernels makes the second
 // wait for the first in the ordinary way, so profiling costs the overlap at those two boundaries.
 // Tier 1 and tier 2 touch disjoint reads and only meet in the (commutative, integer) accumulators.
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
-                        cudaEvent_t e0, cudaEvent_t e1) {
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_multi_items, int ovf_grid, int sm_count,
+                        cudaStream_t st, bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1) {
+  // chain: [multi pass] -> streaming kernel (tier 1 + tier 2) -> many-placement pass. Only two kernels of a chain are in
+  // flight at a time (kernel n+2 starts when kernel n has completed), so the multi pass — a small grid of
+  // register-hungry blocks with a long dependent chain, needing apply_slots only — goes FIRST and runs underneath the
+  // streaming kernel, whose tile counters absorb the register file it holds meanwhile. It waits for apply_slots at its
+  // top and releases after; the streaming kernel then starts without waiting and waits at its END, which makes
+  // completion transitive for the last kernel. (cgrid is unused here: tier 2 is a phase of the streaming kernel.)
+  (void)cgrid;
+  ScoreParams Q = P;
+  bool dep = chained && !profile;
+  bool first = true;
+  if (n_multi_items > 0) {
+    Q.chain_first = 1;
+    Q.finish_here = 0;
+    // at most ONE resident wave: the streaming kernel behind it is released only when every block of this grid has
+    // started, so blocks queuing for a second wave would hold it back for the duration of the first
+    static const int per_sm = resident_blocks(paired_multi_kernel, kOvfBlock);
+    launch_chain(paired_multi_kernel, grid_for(n_multi_items, kOvfBlock, sm_count, per_sm), kOvfBlock, st, dep, Q);
+    dep = true;
+    first = false;
+  }
   if (profile) cudaEventRecord(e0, st);
-  launch_chain(paired_full_kernel, grid, kBlock, st, chained && !profile, P);
-  if (cgrid > 0) launch_chain(paired_complex_kernel, cgrid, kBlock, st, true, P);
+  Q.chain_first = first || profile ? 1 : 0;
+  Q.finish_here = 1;
+  launch_chain(paired_stream_kernel, grid, kBlock, st, dep && !profile, Q);
   if (profile) cudaEventRecord(e1, st);
   launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
 }
@@ -1346,7 +1730,8 @@ void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int gri
   if (profile) cudaEventRecord(e0, st);
   bool dep = chained && !profile;
   if (n_touch_records > 0) {
-    launch_chain(paired_delta_kernel, grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, st, dep, P);
+    static const int per_sm = resident_blocks(paired_delta_kernel, kOvfBlock);   // one resident wave, grid-stride beyond
+    launch_chain(paired_delta_kernel, grid_for(n_touch_records, kOvfBlock, sm_count, per_sm), kOvfBlock, st, dep, P);
     dep = true;
   }
   if (P.delta_only) {

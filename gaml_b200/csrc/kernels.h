@@ -6,18 +6,38 @@
 
 namespace gaml {
 
+// One kernel launch of an evaluation, recorded instead of issued: the engine replays the list either directly or —
+// the steady state — by updating the kernel nodes of a CUDA graph captured from the same sequence and launching that
+// (one submission instead of one per kernel; the programmatic dependent launch edges are captured with it).
+struct PendingLaunch {
+  const void* func = nullptr;
+  unsigned grid = 1, block = 1;
+  bool pdl = false;
+  int n_args = 0;
+  void* arg_ptrs[10];
+  alignas(16) unsigned char arg_buf[1536];
+};
+struct LaunchList {
+  PendingLaunch item[16];
+  int n = 0;
+};
+// While a list is set (per thread), launch_chain-based wrappers append to it instead of launching.
+void set_launch_recorder(LaunchList* list);
+cudaError_t issue_launch(const PendingLaunch& pl, cudaStream_t st);
+
 enum { kGridPairedFull = 0, kGridPairedComplex, kGridPairedTotal, kGridSingleFull, kGridSingleComplex, kGridPacbioFull };
 int score_grid(int which, int n_items, int sm_count);
 int overflow_grid(int sm_count);
 
 void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                        unsigned long long* flags, int n_flag_words, cudaStream_t st);
+                        unsigned long long* flags, int n_flag_words, unsigned long long* timeline, cudaStream_t st);
+constexpr int kTimelineWords = 12;   // profiling level 2: {start, end} ns of apply, tier 1, tier 2, many-placement, delta, total
 // Each wrapper appends the kernels of one read set to the evaluation's chain on `st` (programmatic dependent
 // launches, kernels.cu): streaming pass (tier 1, tier 2), many-placement pass, per-set finalize in the last block.
 // chained: the operation before it on `st` is a kernel of the chain. profile: record e0 / e1 around the streaming
 // kernel(s) of the set (the roofline timing) — which serialises those two boundaries in the ordinary way.
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,
-                        cudaEvent_t e0, cudaEvent_t e1);
+void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_multi_items, int ovf_grid, int sm_count,
+                        cudaStream_t st, bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1);
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count, cudaStream_t st,
                          bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1);
 void launch_single_full(const ScoreParams& P, int grid, int cgrid, int ovf_grid, cudaStream_t st, bool chained, bool profile,

@@ -89,13 +89,17 @@ typedef struct {
   int64_t last_algorithmic_bytes;  /* 16*A + per-read bytes of the pass that ran */
   int64_t last_h2d_bytes;          /* bytes copied host->device by the last evaluation */
   int64_t last_d2h_bytes;
-  double last_device_ms;           /* CUDA-event time of the last evaluation's kernels on the ctx stream */
-  double last_score_kernel_ms;     /* CUDA-event time of the dominant scoring kernel(s) only (gaml_set_profiling on; else 0) */
+  double last_device_ms;           /* CUDA-event time of the last evaluation's kernels (gaml_set_profiling >= 1; else 0) */
+  double last_score_kernel_ms;     /* CUDA-event time of the streaming kernel(s) only (gaml_set_profiling 2; else 0) */
   int32_t last_was_full;           /* 1 if the paired sets were re-scored from scratch */
-  int32_t last_overflow_reads;     /* reads that took the scratch (many-placement) path */
+  int32_t last_overflow_reads;     /* reads a streaming/delta kernel handed to the many-placement pass (they need the order) */
   double last_prepare_host_us;     /* host wall time inside gaml_eval_prepare / launch / finish of the last evaluation */
   double last_launch_host_us;      /*   (prepare = walk flattening + H2D enqueue, launch = kernel enqueue, */
   double last_finish_host_us;      /*    finish = wait for the device's result flag (+ D2H of penalty counters)) */
+  int64_t last_scratch_placements; /* placements the last evaluation parked in the scratch arena (reads with more than four
+                                      live placements on a mate) */
+  int64_t last_multi_items;        /* full evaluations: items of the multi pass = reads with 3+ records on a mate + records under
+                                      keys that occur several times in the evaluation (repeat nodes) */
   int64_t delta_only_evals;        /* paired-set evaluations that updated the running total in O(touched reads): incremental,
                                       total length unchanged, so no O(R) pass (GetTotalProb's sum is kept exactly on the device) */
 } gaml_stats;
@@ -186,11 +190,16 @@ int gaml_reset_state(gaml_ctx* ctx);
 int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n);
 
 int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out);
-/* Measurement aid, no reference counterpart. enabled != 0: every evaluation also records CUDA events around each
- * set's streaming kernel(s) (gaml_stats.last_score_kernel_ms, the roofline timing). An event between two kernels
- * makes the second wait for the first in the ordinary way, so the programmatic dependent launches that chain an
- * evaluation's kernels are given up at those boundaries: leave it off (the default) outside profiling. */
-int gaml_set_profiling(gaml_ctx* ctx, int32_t enabled);
+/* Measurement aids, no reference counterpart. level 0 (default): nothing is timed. 1: two CUDA events around the
+ * whole evaluation (gaml_stats.last_device_ms) — recorded as nodes of the evaluation's CUDA graph, i.e. pure device
+ * time. 2: also events around each set's streaming kernel(s) (gaml_stats.last_score_kernel_ms, the roofline timing);
+ * an event between two kernels makes the second wait for the first in the ordinary way, so the graph and the
+ * programmatic dependent launches that chain an evaluation's kernels are given up. 3: no events; instead the device's
+ * globaltimer is stamped at the start of each kernel's first block and the end of its last block (chain intact):
+ * gaml_read_timeline -> out_us[12] = {start, end} in microseconds since the first stamp for {apply_slots, tier 1 phase,
+ * tier 2 phase, many-placement pass, delta / multi pass, total pass} of the last evaluation's paired set; -1 = not run. */
+int gaml_set_profiling(gaml_ctx* ctx, int32_t level);
+int gaml_read_timeline(gaml_ctx* ctx, double* out_us, int32_t n);
 
 #ifdef __cplusplus
 }

@@ -66,7 +66,8 @@ def test_many_placement_reads_take_the_scratch_path():
     wl = workload.read_workload(os.path.join(GOLDEN, "hand_paired.wl"))
     pc = api.ProbCalculator.from_workload(wl)
     pc.calc_prob(wl.evals[0])
-    assert pc.stats().last_overflow_reads >= 1
+    st = pc.stats()
+    assert st.last_multi_items + st.last_overflow_reads >= 1 and st.last_scratch_placements >= 1
     pc.close()
 
 

@@ -10,6 +10,7 @@ from gaml_b200 import api, synth
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 wl = synth.paired_workload(int(460 * scale), 10000, int(2_000_000 * scale), n_evals=202, seed=42)
 pc = api.ProbCalculator.from_workload(wl)
+pc.set_profiling(1)
 flat0 = api.FlatWalks(wl.evals[0])
 seq = [api.FlatWalks(w) for w in wl.evals[1:201]]
 
@@ -35,3 +36,13 @@ for rep in range(3):
     pc.reset_state()
     pc.calc_prob_partial_flat(flat0)
     run("incremental", seq, False)
+
+# device timeline of one full and a few incremental evaluations (globaltimer stamps, chain intact)
+pc.set_profiling(3)
+pc.reset_state()
+pc.calc_prob_partial_flat(flat0)
+print("timeline full       ", {k: (round(a, 1), round(b, 1)) for k, (a, b) in pc.read_timeline().items()}, flush=True)
+for it in seq[:6]:
+    pc.calc_prob_partial_flat(it)
+    print("timeline incremental", {k: (round(a, 1), round(b, 1)) for k, (a, b) in pc.read_timeline().items()}, flush=True)
+pc.set_profiling(0)
