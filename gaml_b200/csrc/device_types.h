@@ -66,8 +66,9 @@ struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one t
 
 constexpr int kAccumStride = 8;   // per set, u64: four 32-bit limbs of the exact 128-bit sum, floored, -inf terms, nan terms, spare
 constexpr int kOutStride = 6;     // per set, f64: integer part, 2^-40 units, floored, -inf terms, nan terms, flags
-constexpr int kResultStride = 8;  // per set in the host-mapped result buffer: the kOutStride values, then the epoch of the
-                                  // evaluation that wrote them (the host's completion flag), then a spare
+constexpr unsigned long long kResultSeal = 0x5eed5eed5eed5eedull;   // word 7 = seal ^ xor of words 0..6
+constexpr int kResultStride = 8;  // per set in the host-mapped result buffer (one 64-byte line): the kOutStride values,
+                                  // the epoch of the evaluation that wrote them (the host's completion flag), a checksum
 struct Double2 { double x, y; };  // {1/c, -log(1/c)} entries of the log table
 
 struct MateView {

@@ -251,6 +251,7 @@ struct gaml_ctx {
   std::vector<double> h_batch_out;
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
+  std::vector<double> h_res;      // validated copy of h_out taken by finish()
   // CUDA graphs of the evaluations' kernel chains, keyed by the sequence of kernels (GAML_B200_NO_GRAPHS=1 disables)
   struct GraphEntry { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; std::vector<cudaGraphNode_t> nodes; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
@@ -1126,17 +1127,31 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
       CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, (size_t)ctx->plan[s].n_cov_walks * 4, cudaMemcpyDeviceToHost, ctx->stream));
     need_sync = true;
   }
+  ctx->h_res.resize(std::max<size_t>(n_sets, 1) * kResultStride);
   if (need_sync) {
     CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_res.data(), ctx->h_out, n_sets * kResultStride * sizeof(double));
   } else {
     // The last block of every set's last kernel wrote the set's result and then this evaluation's epoch into the
     // host-mapped buffer: spin on the flags instead of paying a copy and a stream synchronisation. The stream is
     // polled now and then so that a failed launch surfaces as an error instead of a hang.
+    // A line counts only when its flag word carries this evaluation's epoch AND its checksum matches: the device
+    // writes all eight words with one store and no fence, so a partially arrived line must be told from a whole one.
     const double want = (double)ctx->epoch;
-    const volatile double* ho = ctx->h_out;
+    uint64_t want_bits;
+    memcpy(&want_bits, &want, 8);
+    const volatile uint64_t* ho = reinterpret_cast<const volatile uint64_t*>(ctx->h_out);
     for (size_t s = 0; s < n_sets; s++) {
       unsigned spins = 0;
-      while (ho[s * kResultStride + 6] != want) {
+      for (;;) {
+        uint64_t w[8];
+        for (int j = 0; j < 8; j++) w[j] = ho[s * kResultStride + j];
+        uint64_t sum = kResultSeal;
+        for (int j = 0; j < 7; j++) sum ^= w[j];
+        if (w[6] == want_bits && w[7] == sum) {
+          memcpy(ctx->h_res.data() + s * kResultStride, w, sizeof(w));
+          break;
+        }
         cpu_relax();
         if ((++spins & 0x3fffu) == 0) {
           const cudaError_t q = cudaStreamQuery(ctx->stream);
@@ -1145,7 +1160,7 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
             ctx->error = std::string("evaluation failed on the device: ") + cudaGetErrorString(q);
             return GAML_ERR_CUDA;
           }
-          if (ho[s * kResultStride + 6] != want) return fail(ctx, GAML_ERR_CUDA, "evaluation finished without publishing its result");
+          if ((spins >> 14) > 64) return fail(ctx, GAML_ERR_CUDA, "evaluation finished without publishing its result");
         }
       }
     }
@@ -1158,15 +1173,17 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   ctx->prepared = ctx->launched = false;
   int tl = 0;
   uint32_t flags = 0, ovf = 0;
+  int64_t scratch_placements = 0;
   bool any_paired = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
-    const double* o = ctx->h_out + s * kResultStride;
+    const double* o = ctx->h_res.data() + s * kResultStride;   // the validated copy
     if (partials)
       for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) partials[s * GAML_PARTIAL_DOUBLES + k] = o[k];
     const uint64_t f = (uint64_t)o[5];
     flags |= (uint32_t)(f & 15);
-    ovf += (uint32_t)(f >> 4);
+    ovf += (uint32_t)((f >> 4) & 0xffffff);
+    scratch_placements = std::max<int64_t>(scratch_placements, (int64_t)(f >> 28));
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (rs.penalty) {   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
         if (ctx->plan[s].full) rs.bad_bases = 0;
@@ -1189,7 +1206,7 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
       if (ctx->sets[s]->cfg.kind == kind) tl = ctx->plan[s].total_len;
   if (total_len) *total_len = tl;
   ctx->stats.last_overflow_reads = (int32_t)ovf;
-  ctx->stats.last_scratch_placements = n_sets ? (int64_t)ctx->h_out[(n_sets - 1) * kResultStride + 7] : 0;
+  ctx->stats.last_scratch_placements = scratch_placements;
   {
     int64_t mi = 0;
     for (size_t s = 0; s < n_sets; s++)

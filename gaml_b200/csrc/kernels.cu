@@ -157,34 +157,51 @@ __device__ __forceinline__ PublishArgs publish_args(const ScoreParams& P, uint32
   return PublishArgs{P.accum, P.state_acc, P.out, P.error_flag, P.ovf_count, P.scratch_cursor, ticket, P.done, P.epoch, P.state_add};
 }
 
+// Called by the first warp of the completing block. Lane 0 assembles the eight result words; lanes 0..7 then store
+// one word each with ONE instruction — a single 64-byte write to the host instead of eight, and no system-wide fence
+// between payload and flag: word 6 is the evaluation's epoch (the flag the host spins on) and word 7 a checksum of
+// the other seven, so the host accepts the line only when it is complete, whatever order its bytes arrive in.
 __device__ __noinline__ void publish_set(PublishArgs A) {
-  __threadfence();
-  unsigned long long a[7];
-  for (int j = 0; j < 7; j++) a[j] = __ldcg(A.accum + j);
-  unsigned __int128 x = 0;
-  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
-  if (A.state_acc) {
-    // paired sets keep their running total {low, high 64 bits, floored, -inf, nan} on the device: a delta-only
-    // evaluation accumulated (new term - old term) of the touched reads and adds it, any other sets it
-    if (A.state_add) {
-      x += ((unsigned __int128)__ldcg(A.state_acc + 1) << 64) | (unsigned __int128)__ldcg(A.state_acc);
-      for (int j = 4; j < 7; j++) a[j] += __ldcg(A.state_acc + j - 2);
+  const int lane = threadIdx.x & 31;
+  unsigned long long w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane == 0) {
+    __threadfence();
+    unsigned long long a[7];
+    for (int j = 0; j < 7; j++) a[j] = __ldcg(A.accum + j);
+    unsigned __int128 x = 0;
+    for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+    if (A.state_acc) {
+      // paired sets keep their running total {low, high 64 bits, floored, -inf, nan} on the device: a delta-only
+      // evaluation accumulated (new term - old term) of the touched reads and adds it, any other sets it
+      if (A.state_add) {
+        x += ((unsigned __int128)__ldcg(A.state_acc + 1) << 64) | (unsigned __int128)__ldcg(A.state_acc);
+        for (int j = 4; j < 7; j++) a[j] += __ldcg(A.state_acc + j - 2);
+      }
+      A.state_acc[0] = (unsigned long long)x;
+      A.state_acc[1] = (unsigned long long)(x >> 64);
+      for (int j = 4; j < 7; j++) A.state_acc[j - 2] = a[j];
     }
-    A.state_acc[0] = (unsigned long long)x;
-    A.state_acc[1] = (unsigned long long)(x >> 64);
-    for (int j = 4; j < 7; j++) A.state_acc[j - 2] = a[j];
+    const __int128 v = (__int128)x;
+    const unsigned long long scratch = __ldcg(A.scratch_cursor);   // placements parked in the scratch arena
+    w[0] = (unsigned long long)__double_as_longlong((double)(long long)(v >> 40));
+    w[1] = (unsigned long long)__double_as_longlong((double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1)));
+    w[2] = (unsigned long long)__double_as_longlong((double)a[4]);
+    w[3] = (unsigned long long)__double_as_longlong((double)a[5]);
+    w[4] = (unsigned long long)__double_as_longlong((double)a[6]);
+    // flags: error bits (4) | listed reads (24 bits) | scratch placements (24 bits, saturating)
+    w[5] = (unsigned long long)__double_as_longlong((double)__ldcg(A.error_flag) + 16.0 * (double)min(__ldcg(A.ovf_count), 0xffffffu) +
+                                                    268435456.0 * (double)min(scratch, 0xffffffull));
+    w[6] = (unsigned long long)__double_as_longlong((double)A.epoch);
+    w[7] = kResultSeal;
+    for (int j = 0; j < 7; j++) w[7] ^= w[j];
   }
-  const __int128 v = (__int128)x;
-  A.out[0] = (double)(long long)(v >> 40);
-  A.out[1] = (double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1));
-  A.out[2] = (double)a[4];
-  A.out[3] = (double)a[5];
-  A.out[4] = (double)a[6];
-  A.out[5] = (double)__ldcg(A.error_flag) + 16.0 * (double)__ldcg(A.ovf_count);
-  A.out[7] = (double)__ldcg(A.scratch_cursor);   // placements parked in the scratch arena so far in this evaluation
-  // out is host-mapped pinned memory: publish the values, then the completion flag the host spins on
-  __threadfence_system();
-  *reinterpret_cast<volatile double*>(A.out + 6) = (double)A.epoch;
+  unsigned long long mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const unsigned long long v = __shfl_sync(0xffffffffu, w[j], 0);
+    if (lane == j) mine = v;
+  }
+  if (lane < 8) reinterpret_cast<unsigned long long*>(A.out)[lane] = mine;
 }
 
 // Block-level tail of a set's kernels. early = false: called by every block of the set's LAST kernel, the block that
@@ -195,15 +212,18 @@ __device__ __noinline__ void finish_blocks(PublishArgs A, bool early) {
   __shared__ bool s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
-  if (early) {
-    __threadfence();
-    if (__ldcg(A.ovf_count) != 0) return;
+  if (threadIdx.x == 0) {
+    bool last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    if (last && early) {
+      __threadfence();
+      last = __ldcg(A.ovf_count) == 0;
+    }
+    s_last = last;
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
   publish_set(A);
-  if (early) *A.done = 1u;
+  if (early && threadIdx.x == 0) *A.done = 1u;
 }
 __device__ __forceinline__ void finish_set(const ScoreParams& P) { finish_blocks(publish_args(P, P.ticket2), false); }
 __device__ __forceinline__ void finish_set_if_complete(const ScoreParams& P) { finish_blocks(publish_args(P, P.ticket), true); }
@@ -1719,7 +1739,7 @@ void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_mu
   }
   if (profile) cudaEventRecord(e0, st);
   Q.chain_first = first || profile ? 1 : 0;
-  Q.finish_here = 1;
+  Q.finish_here = profile ? 0 : 1;   // when profiling, e0/e1 bracket the streaming work alone: the last kernel publishes
   launch_chain(paired_stream_kernel, grid, kBlock, st, dep && !profile, Q);
   if (profile) cudaEventRecord(e1, st);
   launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
