@@ -447,6 +447,8 @@ def main():
         gather_b = PartialGatherer(args.batch * api.PARTIAL_DOUBLES * len(wl.sets), dev)
         kinds = [s_.kind for s_ in wl.sets]
         def run_batch():
+            if world == 1:   # one GPU: the library combines (gaml_calc_prob_batch), as a host caller would use it
+                return list(pc.calc_prob_batch_packed(packed)[0])
             part, tls = pc.calc_prob_batch_partial_packed(packed)
             g = gather_b(part.reshape(-1)).reshape(world, args.batch, len(wl.sets), api.PARTIAL_DOUBLES)
             return [api.combine_partials_raw(g[:, c], kinds, [s_.n_reads for s_ in wl.sets], [s_.weight for s_ in wl.sets], int(tls[c]))[0]
@@ -463,7 +465,7 @@ def main():
                       "mix": "40% extend / 30% interchange / 30% disconnect on the walk set reached after the incremental run",
                       "kernel_launches_per_batch": int((pc.stats().kernel_launches - launches_b0) / 3),
                       "best_candidate_prob": float(max(batch_probs)),
-                      "note": "gaml_calc_prob_batch_partial: host arrays in, exact partials out (+ all-gather and combine at N>1), wall clock; "
+                      "note": "gaml_calc_prob_batch (N=1) / gaml_calc_prob_batch_partial + all-gather + combine (N>1): host arrays in, scores out, wall clock; "
                               "each score is bit-identical to a sequential gaml_calc_prob of that candidate"}
 
     peak, peak_src = measured_peak()

@@ -320,6 +320,18 @@ class ProbCalculator:
                                                           part.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls)))
         return part.reshape(n, ns, PARTIAL_DOUBLES), tls
 
+    def calc_prob_batch_packed(self, packed):
+        """gaml_calc_prob_batch (scores combined in the library) on pre-packed host arrays -> (probs [n], total_lens [n])."""
+        n, er_a, er_off, nodes, w_off, ca_off = packed
+        probs = np.zeros(n, dtype=np.float64)
+        tls = np.zeros(n, dtype=np.int32)
+        zeros = np.zeros(n * 2 * max(len(self.sets), 1), dtype=np.int32)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self.lib.gaml_calc_prob_batch(self.h, n, _p32(er_a), er_off.ctypes.data_as(i64p), _p32(nodes),
+                                                  w_off.ctypes.data_as(i64p), ca_off.ctypes.data_as(i64p),
+                                                  probs.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls), _p32(zeros)))
+        return probs, tls
+
     def calc_prob_batch(self, candidates):
         """candidates: list of (erased base-walk indices, added walks). -> (probs [n], total_lens [n], zeros [n][sets])."""
         n = len(candidates)
