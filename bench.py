@@ -267,6 +267,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the scoring path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -316,8 +319,22 @@ def main():
         st = pc.stats()
         return st.last_device_ms, st.last_score_kernel_ms, part, tl
 
-    gather = PartialGatherer(api.PARTIAL_DOUBLES * len(wl.sets), dev)
-    flat0 = api.FlatWalks(walks0)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
+    gather = PartialGatherer(api.PARTIAL_DOUBLES * len(wl.sets), dev)   # torch all-gather: only for the candidate batches
+    exchange = None
+    if world > 1:
+        # the ranks' 64-byte result lines meet in a host shared-memory segment the kernels write into directly
+        from gaml_b200.dist import ResultExchange
+        exchange = ResultExchange(rank, world)
+        exchange.attach(pc)
+    flat0 = api.FlatWalks(walks0)
+
+    def eval_all_ranks(fw):
+        """One evaluation through the C ABI, all ranks' partials combined: (prob, zeros, total_len)."""
+        if exchange is not None:
+            g, tl = pc.calc_prob_gathered_flat(fw)
+            return pc.combine(g, world, tl)
+        part, tl = pc.calc_prob_partial_flat(fw)
+        return pc.combine(part[None, :], 1, tl)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
 
     def flush_l2():
         flush.fill_(1)
@@ -329,9 +346,7 @@ def main():
         pc.reset_state()
         flush_l2()
         t0 = time.perf_counter()
-        part, tl = pc.calc_prob_partial_flat(flat0)
-        g = gather(part)
-        res = pc.combine(g, g.shape[0], tl)
+        res = eval_all_ranks(flat0)
         return time.perf_counter() - t0, res
 
     # ---- value: device-resident inputs, CUDA events, L2 flushed between steps ----
@@ -393,9 +408,7 @@ def main():
     only0 = pc.stats().delta_only_evals
     t0 = time.perf_counter()
     for nodes_offs in seq_flat:
-        part, tl = pc.calc_prob_partial_flat(nodes_offs)
-        g = gather(part)
-        pc.combine(g, g.shape[0], tl)
+        eval_all_ranks(nodes_offs)
     barrier()
     delta_s = max_over_ranks(time.perf_counter() - t0)
     delta_only = pc.stats().delta_only_evals - only0
@@ -405,7 +418,7 @@ def main():
     pc.set_profiling(1)
     delta_dev_ms, touched = 0.0, 0
     for nodes_offs in seq_flat:
-        pc.calc_prob_partial_flat(nodes_offs)
+        eval_all_ranks(nodes_offs)
         s2 = pc.stats()
         delta_dev_ms += s2.last_device_ms
         touched += s2.last_records_gathered
@@ -479,7 +492,7 @@ def main():
                    "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
                    "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
                    "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events around each evaluation (recorded as nodes of its CUDA graph on the library stream), max over ranks",
-                   "parallelism": f"read-id shards x{world}, all-gather of 40 B exact partials per read set"},
+                   "parallelism": f"read-id shards x{world}; the ranks' 64-byte result lines are written by the kernels' last blocks into a host shared-memory segment every rank reads (no collective call on the path)"},
         "roofline": {"bound": "hbm", "kernel": "paired_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps,
@@ -487,7 +500,7 @@ def main():
                                "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
         "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "note": "gaml_calc_prob_partial (+ all-gather at N>1): host walk arrays in, host partials out, wall clock per step "
+                "note": "gaml_calc_prob_partial (N=1) / gaml_calc_prob_gathered (N>1, every rank's result line through the shared segment) + exact combine: host walk arrays in, score out, wall clock per step "
                         "(max over ranks), L2 flushed between steps; "
                         "the alignment cache is resident state like the reference's aligment_cache_"},
         "gpu_launches": int(launches),
@@ -518,7 +531,8 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     pc.close()
     if world > 1:
         dist.destroy_process_group()

@@ -54,7 +54,8 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_cache_commit", "gaml_calc_prob", "gaml_calc_prob_partial", "gaml_combine_partials", "gaml_combine_partials_raw",
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
-           "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline"]
+           "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline", "gaml_set_result_exchange",
+           "gaml_eval_finish_gathered", "gaml_calc_prob_gathered"]
 
 _lib = None
 
@@ -96,6 +97,10 @@ def load_library() -> C.CDLL:
     lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.gaml_set_profiling.argtypes = [vp, C.c_int32]
     lib.gaml_read_timeline.argtypes = [vp, C.POINTER(C.c_double), C.c_int32]
+    lib.gaml_set_result_exchange.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
+    lib.gaml_eval_finish_gathered.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.gaml_calc_prob_gathered.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_int32)]
     for name in EXPORTS:
         if name not in ("gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream"):
             getattr(lib, name).restype = C.c_int
@@ -158,6 +163,10 @@ class ProbCalculator:
 
     def close(self):
         if getattr(self, "h", None):
+            try:
+                self.clear_result_exchange()
+            except Exception:
+                pass
             self.lib.gaml_ctx_destroy(self.h)
             self.h = None
 
@@ -362,6 +371,36 @@ class ProbCalculator:
         out = np.zeros(max(n, 1), dtype=np.float64)
         self._check(self.lib.gaml_read_values(self.h, set_id, out.ctypes.data_as(C.POINTER(C.c_double)), n))
         return out[:n]
+
+    def set_result_exchange(self, shm_buf, rank: int, world: int) -> None:
+        """shm_buf: a writable buffer over a host shared-memory segment every rank has mapped (dist.ResultExchange)."""
+        self._exch_keep = shm_buf
+        addr = C.addressof(C.c_char.from_buffer(shm_buf))
+        self._check(self.lib.gaml_set_result_exchange(self.h, C.c_void_p(addr), len(shm_buf), rank, world))
+        self._exch_world = world
+        ns = max(len(self.sets), 1)
+        g = np.zeros(world * ns * PARTIAL_DOUBLES, dtype=np.float64)
+        self._gath = (g, g.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def clear_result_exchange(self) -> None:
+        if getattr(self, "_exch_keep", None) is not None:
+            self._check(self.lib.gaml_set_result_exchange(self.h, None, 0, 0, 1))
+            self._exch_keep = None
+
+    def calc_prob_gathered_flat(self, fw: "FlatWalks"):
+        """gaml_calc_prob_gathered: this rank's evaluation, then every rank's partials ([world, sets, PARTIAL_DOUBLES])."""
+        g, p_g = self._gath
+        tl, p_tl = self._io_buffers()[2:4]
+        rc = self.lib.gaml_calc_prob_gathered(self.h, fw.p_nodes, fw.p_offs, fw.n, p_g, p_tl)
+        if rc < 0:
+            self._check(rc)
+        return g.reshape(self._exch_world, -1), tl.value
+
+    def finish_gathered(self):
+        g, p_g = self._gath
+        tl, p_tl = self._io_buffers()[2:4]
+        self._check(self.lib.gaml_eval_finish_gathered(self.h, p_g, p_tl))
+        return g.reshape(self._exch_world, -1).copy(), tl.value
 
     def set_profiling(self, level) -> None:
         """0 off (default); 1 events around the evaluation (stats().last_device_ms); 2 + per-set events around the

@@ -252,6 +252,12 @@ struct gaml_ctx {
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
   std::vector<double> h_res;      // validated copy of h_out taken by finish()
+  // result exchange between the ranks of a multi-GPU job (gaml_set_result_exchange): a host shared-memory segment
+  // mapped into every rank's GPU; each rank's publishing block writes its 64-byte line there, every host reads all
+  double* exch_host = nullptr;
+  double* exch_dev = nullptr;
+  int exch_rank = 0, exch_world = 1;
+  bool exch_owned = false;        // this context registered the segment with CUDA (and unregisters it)
   // CUDA graphs of the evaluations' kernel chains, keyed by the sequence of kernels (GAML_B200_NO_GRAPHS=1 disables)
   struct GraphEntry { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; std::vector<cudaGraphNode_t> nodes; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
@@ -873,6 +879,12 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
 }
 
 
+// Result line of (rank, set) for the evaluation with this epoch: two generations (epoch parity) so that a rank that is
+// one evaluation ahead does not overwrite a line a slower rank has yet to read.
+size_t exch_line(const gaml_ctx* ctx, int rank, size_t s) {
+  return ((size_t)(ctx->epoch & 1u) * (size_t)ctx->exch_world + (size_t)rank) * GAML_EXCHANGE_MAX_SETS + s;
+}
+
 ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   ReadSetState& rs = *ctx->sets[s];
   const SetPlan& sp = ctx->plan[s];
@@ -932,7 +944,7 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.accum = fl + 2 + 6 * ns + s * kAccumStride;
   P.chain_first = 1;
   P.finish_here = 0;
-  P.out = ctx->d_out_mapped + s * kResultStride;
+  P.out = ctx->exch_dev ? ctx->exch_dev + exch_line(ctx, ctx->exch_rank, s) * kResultStride : ctx->d_out_mapped + s * kResultStride;
   P.timeline = ctx->timeline ? ctx->d_timeline.as<unsigned long long>() : nullptr;
   P.state_acc = rs.cfg.kind == GAML_KIND_PAIRED ? rs.d_state_acc.as<unsigned long long>() : nullptr;
   P.state_add = sp.delta_only ? 1 : 0;
@@ -1115,9 +1127,38 @@ int launch(gaml_ctx* ctx) {
   return GAML_OK;
 }
 
-int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
+// Waits for one 64-byte result line of this evaluation (flag word = epoch, checksum intact) and copies it out.
+int wait_line(gaml_ctx* ctx, const volatile uint64_t* line, uint64_t want_bits, double* dst, bool own) {
+  unsigned spins = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    uint64_t w[8];
+    for (int j = 0; j < 8; j++) w[j] = line[j];
+    uint64_t sum = kResultSeal;
+    for (int j = 0; j < 7; j++) sum ^= w[j];
+    if (w[6] == want_bits && w[7] == sum) {
+      memcpy(dst, w, sizeof(w));
+      return GAML_OK;
+    }
+    cpu_relax();
+    if ((++spins & 0x3fffu) == 0) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        ctx->error = std::string("evaluation failed on the device: ") + cudaGetErrorString(q);
+        return GAML_ERR_CUDA;
+      }
+      const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (own && q == cudaSuccess && waited > 1.0) return fail(ctx, GAML_ERR_CUDA, "evaluation finished without publishing its result");
+      if (!own && waited > 60.0) return fail(ctx, GAML_ERR_STATE, "a peer rank did not publish its result within 60 s");
+    }
+  }
+}
+
+int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered = nullptr) {
   if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
   const size_t n_sets = ctx->sets.size();
+  if (gathered && !ctx->exch_host) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish_gathered needs gaml_set_result_exchange");
+  const double* own_lines = ctx->exch_host ? ctx->exch_host + exch_line(ctx, ctx->exch_rank, 0) * kResultStride : ctx->h_out;
   bool need_sync = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
@@ -1130,7 +1171,7 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   ctx->h_res.resize(std::max<size_t>(n_sets, 1) * kResultStride);
   if (need_sync) {
     CU(cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->h_res.data(), ctx->h_out, n_sets * kResultStride * sizeof(double));
+    memcpy(ctx->h_res.data(), own_lines, n_sets * kResultStride * sizeof(double));
   } else {
     // The last block of every set's last kernel wrote the set's result and then this evaluation's epoch into the
     // host-mapped buffer: spin on the flags instead of paying a copy and a stream synchronisation. The stream is
@@ -1140,31 +1181,30 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
     const double want = (double)ctx->epoch;
     uint64_t want_bits;
     memcpy(&want_bits, &want, 8);
-    const volatile uint64_t* ho = reinterpret_cast<const volatile uint64_t*>(ctx->h_out);
+    const volatile uint64_t* ho = reinterpret_cast<const volatile uint64_t*>(own_lines);
     for (size_t s = 0; s < n_sets; s++) {
-      unsigned spins = 0;
-      for (;;) {
-        uint64_t w[8];
-        for (int j = 0; j < 8; j++) w[j] = ho[s * kResultStride + j];
-        uint64_t sum = kResultSeal;
-        for (int j = 0; j < 7; j++) sum ^= w[j];
-        if (w[6] == want_bits && w[7] == sum) {
-          memcpy(ctx->h_res.data() + s * kResultStride, w, sizeof(w));
-          break;
-        }
-        cpu_relax();
-        if ((++spins & 0x3fffu) == 0) {
-          const cudaError_t q = cudaStreamQuery(ctx->stream);
-          if (q == cudaErrorNotReady) continue;
-          if (q != cudaSuccess) {
-            ctx->error = std::string("evaluation failed on the device: ") + cudaGetErrorString(q);
-            return GAML_ERR_CUDA;
-          }
-          if ((spins >> 14) > 64) return fail(ctx, GAML_ERR_CUDA, "evaluation finished without publishing its result");
-        }
-      }
+      const int rc = wait_line(ctx, ho + s * kResultStride, want_bits, ctx->h_res.data() + s * kResultStride, true);
+      if (rc != GAML_OK) return rc;
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (gathered) {   // every rank's partials of this evaluation (the ranks evaluate in lockstep: same epoch everywhere)
+    const double want = (double)ctx->epoch;
+    uint64_t want_bits;
+    memcpy(&want_bits, &want, 8);
+    for (int rk = 0; rk < ctx->exch_world; rk++)
+      for (size_t s = 0; s < n_sets; s++) {
+        double line[kResultStride];
+        if (rk == ctx->exch_rank) {
+          memcpy(line, ctx->h_res.data() + s * kResultStride, sizeof(line));
+        } else {
+          const volatile uint64_t* src = reinterpret_cast<const volatile uint64_t*>(ctx->exch_host + exch_line(ctx, rk, s) * kResultStride);
+          const int rc = wait_line(ctx, src, want_bits, line, false);
+          if (rc != GAML_OK) return rc;
+          if (((uint64_t)line[5]) & 15) return fail(ctx, GAML_ERR_CAPACITY, "a peer rank reported a capacity error");
+        }
+        for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) gathered[((size_t)rk * n_sets + s) * GAML_PARTIAL_DOUBLES + k] = line[k];
+      }
   }
   ctx->stats.last_d2h_bytes = (int64_t)(n_sets * kResultStride * sizeof(double));
   ctx->timing_pending = ctx->timed;
@@ -1569,6 +1609,7 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
   ctx->sets.clear();
   if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->exch_host && ctx->exch_owned) cudaHostUnregister(ctx->exch_host);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStream_t st = ctx->stream;
@@ -1841,6 +1882,56 @@ int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len) {
   const int rc = finish(ctx, partials, total_len);
   ctx->stats.last_finish_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
   return rc;
+}
+
+int gaml_eval_finish_gathered(gaml_ctx* ctx, double* gathered, int32_t* total_len) {
+  if (check_ctx(ctx) || !gathered) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = finish(ctx, nullptr, total_len, gathered);
+  ctx->stats.last_finish_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+int gaml_calc_prob_gathered(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
+                            double* gathered, int32_t* total_len) {
+  int rc = gaml_eval_prepare(ctx, walk_nodes, walk_offsets, n_walks);
+  if (rc) return rc;
+  rc = gaml_eval_launch(ctx);
+  if (rc) return rc;
+  return gaml_eval_finish_gathered(ctx, gathered, total_len);
+}
+
+int gaml_set_result_exchange(gaml_ctx* ctx, void* shared_base, int64_t bytes, int32_t rank, int32_t world) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
+  if (ctx->exch_host) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->exch_owned) cudaHostUnregister(ctx->exch_host);
+    ctx->exch_host = ctx->exch_dev = nullptr;
+    ctx->exch_world = 1;
+    ctx->exch_rank = 0;
+  }
+  if (!shared_base) return GAML_OK;
+  const int64_t need = 2ll * world * GAML_EXCHANGE_MAX_SETS * kResultStride * (int64_t)sizeof(double);
+  if (world < 1 || rank < 0 || rank >= world || bytes < need)
+    return fail(ctx, GAML_ERR_ARG, "result exchange: need 2 * world * GAML_EXCHANGE_MAX_SETS * 64 bytes and 0 <= rank < world");
+  if (ctx->sets.size() > GAML_EXCHANGE_MAX_SETS) return fail(ctx, GAML_ERR_CAPACITY, "more read sets than GAML_EXCHANGE_MAX_SETS");
+  {
+    // (two contexts of ONE process may share a segment — the tests do: the second registration finds it mapped already)
+    const cudaError_t e = cudaHostRegister(shared_base, (size_t)need, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    ctx->exch_owned = e == cudaSuccess;
+    if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();
+    else CU(e);
+  }
+  void* dev = nullptr;
+  CU(cudaHostGetDevicePointer(&dev, shared_base, 0));
+  ctx->exch_host = static_cast<double*>(shared_base);
+  ctx->exch_dev = static_cast<double*>(dev);
+  ctx->exch_rank = rank;
+  ctx->exch_world = world;
+  return GAML_OK;
 }
 
 int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,

@@ -71,3 +71,37 @@ def sharded_calc_prob(pc, paths: Sequence[Sequence[int]], device=None, gatherer:
     part, tl = pc.calc_prob_partial(paths)
     g = gatherer(part) if gatherer is not None else allgather_partials(part, device)
     return pc.combine(g, g.shape[0], tl)
+
+
+class ResultExchange:
+    """Host shared-memory segment for the ranks' 64-byte result lines (gaml_set_result_exchange): rank 0 creates and
+    zeroes it, the others attach; `torch.distributed` is used only to hand the name round and as the setup barrier.
+    After attach(pc) every evaluation's all-gather is done by the kernels' publishing blocks writing into this segment."""
+
+    MAX_SETS = 8
+
+    def __init__(self, rank: int, world: int, name: str = None):
+        import mmap
+        import os
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        self.bytes = max(2 * world * self.MAX_SETS * 64, mmap.PAGESIZE)
+        self.bytes = (self.bytes + mmap.PAGESIZE - 1) // mmap.PAGESIZE * mmap.PAGESIZE
+        names = [name or f"/dev/shm/gaml_b200_exch_{os.getpid()}"]
+        if dist.is_initialized() and world > 1:
+            dist.broadcast_object_list(names, src=0)
+        self.path = names[0]
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.write(b"\0" * self.bytes)
+        if dist.is_initialized() and world > 1:
+            dist.barrier()
+        self.fd = os.open(self.path, os.O_RDWR)
+        self.map = mmap.mmap(self.fd, self.bytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        if dist.is_initialized() and world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)   # stays alive while mapped
+
+    def attach(self, pc) -> None:
+        pc.set_result_exchange(self.map, self.rank, self.world)

@@ -166,6 +166,22 @@ int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* w
 int gaml_eval_launch(gaml_ctx* ctx);
 int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len);
 
+/* Multi-GPU jobs (one process and one context per GPU, read-id shards; no reference counterpart): the only exchange of
+ * an evaluation is each rank's 64-byte result line per read set. shared_base is a host shared-memory segment that
+ * every rank has mapped (e.g. POSIX shm; page aligned; at least 2 * world * GAML_EXCHANGE_MAX_SETS * 64 bytes; zeroed
+ * once by its creator). The library maps it into the GPU, and from then on the block that completes a read set writes
+ * its line straight into the segment — the collective is fused into the kernel: no copy, no NCCL call, no stream
+ * synchronisation on the evaluation's path. gaml_eval_finish_gathered = gaml_eval_finish, then waits for the lines of
+ * ALL ranks: gathered[world][n_sets][GAML_PARTIAL_DOUBLES], ready for gaml_combine_partials. The ranks must evaluate
+ * in lockstep (the same sequence of evaluations), which an SPMD annealing driver does by construction.
+ * shared_base == NULL detaches. */
+#define GAML_EXCHANGE_MAX_SETS 8
+int gaml_set_result_exchange(gaml_ctx* ctx, void* shared_base, int64_t bytes, int32_t rank, int32_t world);
+int gaml_eval_finish_gathered(gaml_ctx* ctx, double* gathered, int32_t* total_len);
+/* prepare + launch + finish_gathered in one call (the multi-GPU form of gaml_calc_prob_partial) */
+int gaml_calc_prob_gathered(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
+                            double* gathered, int32_t* total_len);
+
 /* Batched, STATELESS evaluation of candidate moves (BASELINE config 5; SURVEY §8b gaml_gpu_eval_batch): candidate c
  * is the last evaluated walk set with the base walks erased_idx[erased_off[c] .. erased_off[c+1]) removed and the
  * walks added_walk_off[cand_added_off[c] .. cand_added_off[c+1]) appended (added_nodes / added_walk_off in the

@@ -135,6 +135,36 @@ def test_two_shards_on_one_gpu_combine_to_the_unsharded_result(oracle):
 
 
 # ---- full-size properties (BASELINE config 2) ---------------------------------------------------
+def test_result_exchange_between_two_contexts_matches_the_unsharded_result(oracle):
+    """Two read-id shards as two contexts ("ranks") sharing one result-exchange segment: each publishing block writes
+    its 64-byte line into the segment, each side gathers both lines and combines them — the totals must equal the
+    unsharded context's exactly, over a whole incremental trajectory (the exchange is double-buffered by epoch)."""
+    import mmap
+    wl = synth.paired_workload(46, 10000, 200_000, n_evals=12, seed=11)
+    whole = api.ProbCalculator.from_workload(wl)
+    seg = mmap.mmap(-1, max(2 * 2 * 8 * 64, mmap.PAGESIZE))
+    ranks = []
+    for rk in range(2):
+        pc = api.ProbCalculator.from_workload(wl, shard_of=(rk, 2))
+        pc.set_result_exchange(seg, rk, 2)
+        ranks.append(pc)
+    for e, walks in enumerate(wl.evals):
+        ref = whole.calc_prob(walks)
+        for pc in ranks:
+            pc.prepare(walks)
+            pc.launch()
+        outs = []
+        for pc in ranks:
+            g, tl = pc.finish_gathered()
+            outs.append(pc.combine(g, 2, tl))
+        assert outs[0] == outs[1], e
+        assert outs[0][1] == ref[1] and outs[0][2] == ref[2], e
+        assert outs[0][0] == ref[0], (e, outs[0][0], ref[0])   # exact integer partial sums: bit-identical for any sharding
+    for pc in ranks:
+        pc.close()
+    whole.close()
+
+
 @pytest.fixture(scope="module")
 def c2():
     wl = synth.paired_workload(460, 10000, 2_000_000, n_evals=10, seed=42)
