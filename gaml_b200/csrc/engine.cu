@@ -29,28 +29,17 @@
 
 #include "../../include/gaml_b200.h"
 #include "kernels.h"
+#include "walk_set.h"
 
 namespace gaml {
 namespace {
 
-using Walk = std::vector<int>;
 constexpr int kWindowLen = 300;   // kMinSubpathLength, graph.cc:27
 
-// graph.h:21-45: the reference's hash for vector<int>; it fixes the iteration order of the
-// unordered_multiset in GetChanges, hence the order in which erased walks are subtracted.
+// graph.h:21-45: the reference's hash for vector<int> (walk_set.h: hash_nodes)
 struct WalkHash {
-  size_t operator()(const Walk& v) const {
-    size_t seed = 0;
-    for (size_t i = 0; i < v.size(); i++) seed ^= std::hash<int>()(v[i]) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
-    return seed;
-  }
+  size_t operator()(const Walk& v) const { return hash_nodes(v.data(), (int)v.size()); }
 };
-
-// Element of the GetChanges multiset: a walk by reference with its precomputed hash (same hash values and equality as
-// the reference's unordered_multiset<vector<int>>, hence the same bucket placement and iteration order).
-struct WalkRef { const Walk* w; size_t h; };
-struct WalkRefHash { size_t operator()(const WalkRef& r) const { return r.h; } };
-struct WalkRefEq { bool operator()(const WalkRef& a, const WalkRef& b) const { return a.h == b.h && *a.w == *b.w; } };
 
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
@@ -112,10 +101,11 @@ struct FlatCache {   // chained hash table keyed by walk content; the caller sup
   std::vector<Node> nodes;
   std::vector<int> buckets;
   void clear() { nodes.clear(); buckets.clear(); }
-  const WalkFlat* find(const Walk& w, size_t h) const {
+  const WalkFlat* find(const int* p, int n, size_t h) const {
     if (buckets.empty()) return nullptr;
     for (int i = buckets[h & (buckets.size() - 1)]; i >= 0; i = nodes[i].next)
-      if (nodes[i].h == h && nodes[i].w == w) return &nodes[i].f;
+      if (nodes[i].h == h && (int)nodes[i].w.size() == n && (n == 0 || memcmp(nodes[i].w.data(), p, sizeof(int) * (size_t)n) == 0))
+        return &nodes[i].f;
     return nullptr;
   }
   WalkFlat& insert(const Walk& w, size_t h) {
@@ -142,12 +132,6 @@ struct OccBuilder {
   void add(int key, int walk, int cur_pos, int skip_below) {
     items.push_back({key, Occ{walk, next_seg++, cur_pos, skip_below}});
   }
-};
-
-struct WalkSet {
-  std::vector<Walk> walks;
-  std::vector<size_t> hash;   // WalkHash of every walk
-  int n = 0;                  // walks in use (the vectors only grow, so inner buffers are reused)
 };
 
 struct MateStore {
@@ -282,7 +266,14 @@ struct gaml_ctx {
   std::vector<std::vector<Occ>> h_occs;
   std::vector<std::vector<TouchRange>> h_touches, h_mtouches;
   std::vector<OccBuilder> h_ob;   // one per store
-  std::vector<WalkRef> h_refs;
+  std::vector<WalkView> h_refs;
+  std::vector<Walk> h_walks;
+  bool fast_changes = true;       // GAML_B200_NO_FAST_CHANGES=1: always build the reference's container (tests)
+  HashCounts prev_counts;         // multiplicity of every walk hash in prev() (kept in step by finish())
+  bool have_prev = false;         // prev() holds a finished evaluation's walks
+  WalkDiff cur_diff;              // cur() against prev(), from prepare()
+  int prev_total_len = 0, cur_total_len = 0;
+  Changes h_changes;
   alignas(16) char pool_buf[1 << 18];   // nodes + buckets of the GetChanges multiset (bump-allocated, released per use;
   std::pmr::monotonic_buffer_resource pool{pool_buf, sizeof(pool_buf)};   // larger walk sets spill to the heap)
   int n_updates = 0;
@@ -414,20 +405,21 @@ void build_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, Wa
 
 size_t hash_walk(const Walk& w) { return WalkHash()(w); }
 
-const WalkFlat& cached_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, size_t h) {
+const WalkFlat& cached_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const WalkView& v) {
   FlatCache& fc = rs.flat_cache;
-  if (const WalkFlat* f = fc.find(walk, h)) return *f;
+  if (const WalkFlat* f = fc.find(v.p, v.n, v.h)) return *f;
   if (fc.nodes.size() >= (1u << 17)) fc.clear();   // bound the memory of a very long annealing run
-  WalkFlat& f = fc.insert(walk, h);
+  const Walk walk(v.p, v.p + v.n);
+  WalkFlat& f = fc.insert(walk, v.h);
   build_walk_flat(ctx, rs, walk, f);
   return f;
 }
 
 // Appends one walk's lookups to the evaluation (walk ordinal `ord`): occurrences per mate store, record counts,
 // and — for incremental evaluations — the mate-1 arena ranges the delta kernel enumerates.
-void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, size_t h, int ord, OccBuilder* ob[2],
+void flatten_paired_walk(const gaml_ctx* ctx, ReadSetState& rs, const WalkView& walk, int ord, OccBuilder* ob[2],
                          SetPlan& sp, std::vector<TouchRange>* touch, std::vector<int>* contig_starts = nullptr) {
-  const WalkFlat& f = cached_walk_flat(ctx, rs, walk, h);
+  const WalkFlat& f = cached_walk_flat(ctx, rs, walk);
   for (int m = 0; m < 2; m++)
     for (const FlatEntry& e : f.e[m]) {
       ob[m]->add(e.key, ord, e.cur, e.skip);
@@ -647,21 +639,32 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
   WalkSet& ws = ctx->cur();
-  if ((int)ws.walks.size() < n_walks) {
-    ws.walks.resize(n_walks);
-    ws.hash.resize(n_walks);
-  }
-  ws.n = n_walks;
+  const WalkSet* old_set = ctx->have_prev ? &ctx->prev() : nullptr;
+  const WalkDiff diff = load_walks(ws, old_set, nodes, offs, n_walks);   // hashes only the walks that changed
+  ctx->cur_diff = diff;
   const int n_nodes = (int)ctx->node_len.size();
-  int total_len = 0;   // GetTotalLen, graph.cc:1966 (int arithmetic like the reference)
-  for (int w = 0; w < n_walks; w++) {
-    Walk& wk = ws.walks[w];
-    wk.assign(nodes + offs[w], nodes + offs[w + 1]);
-    for (int x : wk)
-      if (x >= n_nodes) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
-    ws.hash[w] = hash_walk(wk);
-    total_len += walk_length(ctx, wk);
+  // node ids and GetTotalLen (graph.cc:1966, int arithmetic like the reference): over the changed walks when the rest is
+  // the previous evaluation's, else over all of them
+  auto span_len = [&](const WalkSet& w, int lo, int hi, bool check, bool& bad) {
+    unsigned t = 0;
+    for (int64_t k = w.offs[lo]; k < w.offs[hi]; k++) {
+      const int x = w.nodes[(size_t)k];
+      if (check && x >= n_nodes) { bad = true; return 0u; }
+      t += (unsigned)(x < 0 ? -x : ctx->node_len[x]);
+    }
+    return t;
+  };
+  bool bad = false;
+  int total_len;
+  if (diff.valid) {
+    const unsigned removed = span_len(*old_set, diff.prefix, old_set->n - diff.suffix, false, bad);
+    const unsigned added_len = span_len(ws, diff.prefix, ws.n - diff.suffix, true, bad);
+    total_len = (int)((unsigned)ctx->prev_total_len - removed + added_len);
+  } else {
+    total_len = (int)span_len(ws, 0, ws.n, true, bad);
   }
+  if (bad) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
+  ctx->cur_total_len = total_len;
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
   ctx->epoch++;
@@ -681,29 +684,26 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   mtouches.resize(n_sets);
   for (auto& t : mtouches) t.clear();
   for (auto& o : ctx->h_ob) o.reset();
+  ctx->h_walks.clear();
   std::vector<std::vector<std::vector<int>>> cov_cs(n_sets);   // per penalty set: contig starts of every touched walk
 
   // GetChanges (graph.cc:1745-1764) is the same for every paired set with state (they all follow the last evaluated
-  // walks): same container, same hash values, same insertion order as the reference, so the erased walks come out in
-  // the reference's iteration order. The elements are (pointer, cached hash) pairs in a bump-allocated pool.
-  struct Changed { const Walk* w; size_t h; };
-  std::vector<Changed> erased, added;
+  // walks). Fast path: the difference is confined to the region where the new walk list departs from the previous one
+  // and the erased walks are ordered by the container's rule; otherwise the reference's own container is built
+  // (walk_set.h; tests/cpp/test_walk_changes.cc checks the one against the other).
+  std::vector<WalkView>& erased = ctx->h_changes.erased;
+  std::vector<WalkView>& added = ctx->h_changes.added;
   bool changes_done = false;
   auto get_changes = [&]() {
     if (changes_done) return;
     changes_done = true;
     const WalkSet& old = ctx->prev();
-    ctx->h_refs.clear();
-    for (int i = 0; i < old.n; i++) ctx->h_refs.push_back(WalkRef{&old.walks[i], old.hash[i]});
-    ctx->pool.release();
-    std::pmr::unordered_multiset<WalkRef, WalkRefHash, WalkRefEq> idx(ctx->h_refs.begin(), ctx->h_refs.end(), 0, WalkRefHash(),
-                                                                      WalkRefEq(), &ctx->pool);
-    for (int i = 0; i < ws.n; i++) {
-      auto f = idx.find(WalkRef{&ws.walks[i], ws.hash[i]});
-      if (f == idx.end()) added.push_back(Changed{&ws.walks[i], ws.hash[i]});
-      else idx.erase(f);
+    if (ctx->fast_changes && get_changes_fast(old, ws, diff, ctx->prev_counts, ctx->h_changes)) {
+      ctx->stats.fast_change_evals++;
+      return;
     }
-    for (const WalkRef& r : idx) erased.push_back(Changed{r.w, r.h});
+    ctx->pool.release();
+    get_changes_reference(old, ws, ctx->h_changes, ctx->h_refs, &ctx->pool);
   };
 
   for (size_t s = 0; s < n_sets; s++) {
@@ -721,16 +721,16 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       std::vector<int> cs;
       if (sp.full) {
         for (int i = 0; i < ws.n; i++) {
-          flatten_paired_walk(ctx, rs, ws.walks[i], ws.hash[i], ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          flatten_paired_walk(ctx, rs, ws.view(i), ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
           if (rs.penalty) cov_cs[s].push_back(cs);
         }
       } else {
-        for (const Changed& c : erased) {
-          flatten_paired_walk(ctx, rs, *c.w, c.h, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+        for (const WalkView& c : erased) {
+          flatten_paired_walk(ctx, rs, c, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
           if (rs.penalty) cov_cs[s].push_back(cs);
         }
-        for (const Changed& c : added) {
-          flatten_paired_walk(ctx, rs, *c.w, c.h, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+        for (const WalkView& c : added) {
+          flatten_paired_walk(ctx, rs, c, ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
           if (rs.penalty) cov_cs[s].push_back(cs);
         }
       }
@@ -763,8 +763,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     } else {
       OccBuilder& ob = ctx->h_ob[rs.mate[0].table_index];
       sp.full = true;
-      if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, ws.walks.data(), ws.n, ob, sp);
-      else flatten_pacbio(ctx, rs, ws.walks.data(), ws.n, ob, sp);
+      if (ctx->h_walks.empty() && ws.n > 0)   // single / pacbio sets re-read every walk: materialise them once per evaluation
+        for (int i = 0; i < ws.n; i++) ctx->h_walks.push_back(ws.walk(i));
+      if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, ctx->h_walks.data(), ws.n, ob, sp);
+      else flatten_pacbio(ctx, rs, ctx->h_walks.data(), ws.n, ob, sp);
       group_occurrences(ob, rs.mate[0], ctx->epoch, updates, occs[rs.mate[0].table_index]);
       sp.grid = score_grid(rs.cfg.kind == GAML_KIND_SINGLE ? kGridSingleFull : kGridPacbioFull, rs.n_local, ctx->sm_count);
       sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
@@ -1239,7 +1241,21 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
       any_paired = true;
     }
   }
-  if (any_paired) ctx->cur_set ^= 1;   // the evaluated walks become old_paths; the other buffer is reused next time
+  if (any_paired) {   // the evaluated walks become old_paths; the other buffer is reused next time
+    const WalkSet& now = ctx->cur();
+    const WalkDiff& d = ctx->cur_diff;
+    if (ctx->have_prev && d.valid && ctx->prev_counts.valid && !ctx->prev_counts.crowded()) {
+      const WalkSet& was = ctx->prev();
+      for (int i = d.prefix; i < was.n - d.suffix; i++) ctx->prev_counts.add(was.hash[i], -1);
+      for (int i = d.prefix; i < now.n - d.suffix; i++) ctx->prev_counts.add(now.hash[i], +1);
+    } else {
+      ctx->prev_counts.rebuild(now);
+    }
+    ctx->prev_total_len = ctx->cur_total_len;
+    ctx->cur_set ^= 1;
+    ctx->have_prev = true;
+    ctx->cur_diff.valid = false;
+  }
   // CalcProb leaves the value of the last set it ran: single sets, then paired, then pacbio (prob_calculator.h:70-107)
   for (int kind = 0; kind < 3; kind++)
     for (size_t s = 0; s < n_sets; s++)
@@ -1341,8 +1357,10 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
   }
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
-  const std::vector<Walk>& base = ctx->prev().walks;   // old_paths of every set (only the first n_base entries are in use)
-  const int n_base = ctx->prev().n;
+  const WalkSet& base_set = ctx->prev();   // old_paths of every set
+  const int n_base = base_set.n;
+  std::vector<Walk> base(n_base);
+  for (int i = 0; i < n_base; i++) base[i] = base_set.walk(i);
   // rank of every base walk in the iteration order of the reference's multiset (GetChanges, graph.cc:1747-1763):
   // erasing the kept walks leaves the others in place, so a candidate's erased walks come out in rank order
   std::vector<int> rank(n_base, 0);
@@ -1421,8 +1439,9 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
       SetPlan sp;
       std::vector<TouchRange> touch;
       int ord = 0;
-      for (int bi : cand_erased[c]) flatten_paired_walk(ctx, rs, base[bi], ctx->prev().hash[bi], ord++, ob, sp, &touch);
-      for (const Walk& w : cand_added[c]) flatten_paired_walk(ctx, rs, w, hash_walk(w), ord++, ob, sp, &touch);
+      for (int bi : cand_erased[c]) flatten_paired_walk(ctx, rs, base_set.view(bi), ord++, ob, sp, &touch);
+      for (const Walk& w : cand_added[c])
+        flatten_paired_walk(ctx, rs, WalkView{w.data(), (int)w.size(), hash_walk(w), -1}, ord++, ob, sp, &touch);
       BatchCand& cd = cands[c];
       cd.n_erased = (int)cand_erased[c].size();
       cd.len_index = cand_len_index[c];
@@ -1571,6 +1590,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   if (const char* s = getenv("GAML_B200_SCRATCH_ENTRIES")) ctx->scratch_entries = strtoull(s, nullptr, 10);
   if (const char* s = getenv("GAML_B200_NO_RUNNING_TOTAL")) ctx->running_total = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_GRAPHS")) ctx->use_graphs = !(s[0] && s[0] != '0');
+  if (const char* s = getenv("GAML_B200_NO_FAST_CHANGES")) ctx->fast_changes = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -1634,6 +1654,12 @@ int gaml_set_graph(gaml_ctx* ctx, int32_t n_nodes, const int32_t* node_len, cons
     ctx->nmap[i] = normalize_map ? normalize_map[i] : i;
     if (ctx->nmap[i] < 0 || ctx->nmap[i] >= n_nodes) return fail(ctx, GAML_ERR_ARG, "normalize_map out of range");
     if (node_len[i] < 0) return fail(ctx, GAML_ERR_ARG, "negative node length");
+  }
+  ctx->have_prev = false;   // lengths and lookups of remembered walks refer to the old graph
+  for (auto& rs : ctx->sets) {
+    rs->flat_cache.clear();
+    rs->has_state = false;
+    rs->total_valid = false;
   }
   return GAML_OK;
 }

@@ -100,6 +100,8 @@ typedef struct {
                                       live placements on a mate) */
   int64_t last_multi_items;        /* full evaluations: items of the multi pass = reads with 3+ records on a mate + records under
                                       keys that occur several times in the evaluation (repeat nodes) */
+  int64_t fast_change_evals;       /* incremental evaluations whose erased/added walks came from the diff against the previous
+                                      walk list (walk_set.h) instead of the reference's container */
   int64_t delta_only_evals;        /* paired-set evaluations that updated the running total in O(touched reads): incremental,
                                       total length unchanged, so no O(R) pass (GetTotalProb's sum is kept exactly on the device) */
 } gaml_stats;

@@ -159,3 +159,13 @@ def test_world_size_2_sharded_combine_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "RANK0_OK" in out.stdout and "RANK1_OK" in out.stdout
+
+
+def test_fast_get_changes_equals_the_reference_container():
+    """tests/cpp/test_walk_changes.cc: the diff-based GetChanges (walk_set.h) against the reference's algorithm on the
+    real std::unordered_multiset over 18 000 random evaluations (CPU only)."""
+    import __graft_entry__ as entry
+    entry.build()
+    out = subprocess.run([entry.CHANGES_TEST_BIN], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK"), out.stdout

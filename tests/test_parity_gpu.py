@@ -202,16 +202,21 @@ def test_running_total_is_exactly_the_full_resum(monkeypatch):
     wl = synth.paired_workload(46, 10000, 200_000, n_evals=60, seed=9)
     fast = api.ProbCalculator.from_workload(wl)
     monkeypatch.setenv("GAML_B200_NO_RUNNING_TOTAL", "1")
+    monkeypatch.setenv("GAML_B200_NO_FAST_CHANGES", "1")   # ... and finds its erased/added walks with the reference's container
+    monkeypatch.setenv("GAML_B200_NO_GRAPHS", "1")         # ... and launches its kernels one by one
     slow = api.ProbCalculator.from_workload(wl)
     monkeypatch.delenv("GAML_B200_NO_RUNNING_TOTAL")
+    monkeypatch.delenv("GAML_B200_NO_FAST_CHANGES")
+    monkeypatch.delenv("GAML_B200_NO_GRAPHS")
     for e, walks in enumerate(wl.evals):
         pf, tf = fast.calc_prob_partial(walks)
         ps, ts = slow.calc_prob_partial(walks)
         assert tf == ts
         assert np.array_equal(pf, ps), (e, pf, ps)
-        if e % 20 == 19:
+        if e % 10 == 9:
             assert np.array_equal(fast.read_values(0), slow.read_values(0))
     assert fast.stats().delta_only_evals >= 10 and slow.stats().delta_only_evals == 0
+    assert fast.stats().fast_change_evals >= 30 and slow.stats().fast_change_evals == 0
     fast.close()
     slow.close()
 
