@@ -55,7 +55,7 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
            "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline", "gaml_set_result_exchange",
-           "gaml_eval_finish_gathered", "gaml_calc_prob_gathered"]
+           "gaml_eval_finish_gathered", "gaml_calc_prob_gathered", "gaml_cache_save", "gaml_cache_load"]
 
 _lib = None
 
@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.gaml_set_profiling.argtypes = [vp, C.c_int32]
     lib.gaml_read_timeline.argtypes = [vp, C.POINTER(C.c_double), C.c_int32]
+    lib.gaml_cache_save.argtypes = [vp, C.c_int, C.c_char_p]
+    lib.gaml_cache_load.argtypes = [vp, C.c_int, C.c_char_p]
     lib.gaml_set_result_exchange.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
     lib.gaml_eval_finish_gathered.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.gaml_calc_prob_gathered.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double),
@@ -395,6 +397,12 @@ class ProbCalculator:
         if rc < 0:
             self._check(rc)
         return g.reshape(self._exch_world, -1), tl.value
+
+    def cache_save(self, set_id: int, path: str) -> None:
+        self._check(self.lib.gaml_cache_save(self.h, set_id, path.encode()))
+
+    def cache_load(self, set_id: int, path: str) -> None:
+        self._check(self.lib.gaml_cache_load(self.h, set_id, path.encode()))
 
     def finish_gathered(self):
         g, p_g = self._gath

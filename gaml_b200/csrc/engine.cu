@@ -1868,6 +1868,107 @@ int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t
   return GAML_OK;
 }
 
+// ---- flat on-disk cache: the stores of one read set exactly as they sit in memory ---------------
+// File: "GAMLCC01", {int32 kind, int32 n_mates, int64 n_total, int64 lo, int64 hi}; per mate {int64 n_keys, int64
+// n_records}, per key {int32 key_len, key_len x int32 node ids, uint32 count, int32 max_pos, int32 any}, then the
+// key-major arena, 16 bytes per record — which is what the device holds, so loading is one read + one upload.
+namespace {
+struct CacheFileHeader { char magic[8]; int32_t kind, n_mates; int64_t n_total, lo, hi; };
+struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
+}  // namespace
+
+int gaml_cache_save(gaml_ctx* ctx, int set, const char* path) {
+  if (check_ctx(ctx) || !path) return GAML_ERR_ARG;
+  if (set < 0 || set >= (int)ctx->sets.size()) return fail(ctx, GAML_ERR_ARG, "no such read set");
+  cudaSetDevice(ctx->device);
+  int rc = commit(ctx);
+  if (rc != GAML_OK) return rc;
+  ReadSetState& rs = *ctx->sets[set];
+  FileCloser fc{fopen(path, "wb")};
+  if (!fc.f) return fail(ctx, GAML_ERR_ARG, std::string("cannot open ") + path + " for writing");
+  CacheFileHeader h{};
+  memcpy(h.magic, "GAMLCC01", 8);
+  h.kind = rs.cfg.kind;
+  h.n_mates = rs.n_mates;
+  h.n_total = rs.n_total;
+  h.lo = rs.lo;
+  h.hi = rs.hi;
+  bool ok = fwrite(&h, sizeof(h), 1, fc.f) == 1;
+  std::vector<int4> host;
+  for (int m = 0; m < rs.n_mates && ok; m++) {
+    MateStore& st = rs.mate[m];
+    const int64_t counts[2] = {(int64_t)st.keys.size(), (int64_t)st.arena_n};
+    ok = fwrite(counts, sizeof(counts), 1, fc.f) == 1;
+    std::vector<const Walk*> by_id(st.keys.size(), nullptr);
+    for (const auto& kv : st.key_ids) by_id[kv.second] = &kv.first;
+    for (size_t k = 0; k < st.keys.size() && ok; k++) {
+      const Walk& w = *by_id[k];
+      const int32_t len = (int32_t)w.size();
+      const int32_t meta[3] = {(int32_t)st.keys[k].count, st.keys[k].max_pos, st.keys[k].any ? 1 : 0};
+      ok = fwrite(&len, 4, 1, fc.f) == 1 && (len == 0 || fwrite(w.data(), 4, (size_t)len, fc.f) == (size_t)len) &&
+           fwrite(meta, sizeof(meta), 1, fc.f) == 1;
+    }
+    host.resize(st.arena_n);
+    if (st.arena_n) {
+      CU(cudaMemcpyAsync(host.data(), st.arena.p, st.arena_n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      ok = ok && fwrite(host.data(), 16, st.arena_n, fc.f) == st.arena_n;
+    }
+  }
+  if (!ok) return fail(ctx, GAML_ERR_ARG, std::string("short write to ") + path);
+  return GAML_OK;
+}
+
+int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
+  if (check_ctx(ctx) || !path) return GAML_ERR_ARG;
+  if (set < 0 || set >= (int)ctx->sets.size()) return fail(ctx, GAML_ERR_ARG, "no such read set");
+  ReadSetState& rs = *ctx->sets[set];
+  for (int m = 0; m < rs.n_mates; m++)
+    if (!rs.mate[m].keys.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_cache_load needs an empty read set");
+  FileCloser fc{fopen(path, "rb")};
+  if (!fc.f) return fail(ctx, GAML_ERR_ARG, std::string("cannot open ") + path);
+  CacheFileHeader h{};
+  if (fread(&h, sizeof(h), 1, fc.f) != 1 || memcmp(h.magic, "GAMLCC01", 8) != 0) return fail(ctx, GAML_ERR_ARG, "not a gaml_b200 cache file");
+  if (h.kind != rs.cfg.kind || h.n_mates != rs.n_mates || h.n_total != rs.n_total || h.lo != rs.lo || h.hi != rs.hi)
+    return fail(ctx, GAML_ERR_ARG, "cache file was written for a different read set (kind, read count or shard)");
+  const int n_nodes = (int)ctx->node_len.size();
+  for (int m = 0; m < rs.n_mates; m++) {
+    MateStore& st = rs.mate[m];
+    int64_t counts[2];
+    if (fread(counts, sizeof(counts), 1, fc.f) != 1 || counts[0] < 0 || counts[1] < 0 || counts[1] > 0xfffffff0ll)
+      return fail(ctx, GAML_ERR_ARG, "corrupt cache file (store header)");
+    uint64_t off = 0;
+    Walk w;
+    for (int64_t k = 0; k < counts[0]; k++) {
+      int32_t len, meta[3];
+      if (fread(&len, 4, 1, fc.f) != 1 || len <= 0 || len > (1 << 20)) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (key length)");
+      w.resize((size_t)len);
+      if (fread(w.data(), 4, (size_t)len, fc.f) != (size_t)len || fread(meta, sizeof(meta), 1, fc.f) != 1)
+        return fail(ctx, GAML_ERR_ARG, "corrupt cache file (key)");
+      for (int x : w)
+        if (x >= n_nodes && n_nodes > 0) return fail(ctx, GAML_ERR_ARG, "cache key references a node outside the graph");
+      KeyMeta km;
+      km.arena_off = (uint32_t)off;
+      km.count = (uint32_t)meta[0];
+      km.max_pos = meta[1];
+      km.any = meta[2] != 0;
+      off += km.count;
+      if (!st.key_ids.emplace(w, (int)st.keys.size()).second) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (duplicate key)");
+      st.keys.push_back(km);
+    }
+    if (off != (uint64_t)counts[1]) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record count)");
+    st.pending.resize((size_t)counts[1]);
+    if (counts[1] && fread(st.pending.data(), 16, (size_t)counts[1], fc.f) != (size_t)counts[1])
+      return fail(ctx, GAML_ERR_ARG, "corrupt cache file (records)");
+    for (const int4& v : st.pending) {   // {read, pos, edor, key} / {read, key, logprob}
+      const int key = st.is_long ? v.y : v.w;
+      if (v.x < 0 || v.x >= rs.n_local || key < 0 || key >= (int)st.keys.size()) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record)");
+    }
+    st.dirty = true;
+  }
+  return GAML_OK;
+}
+
 int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
   MateStore* st;

@@ -140,6 +140,13 @@ int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, in
 /* Uploads staged inserts and rebuilds the per-read CSR on the device (also done lazily by CalcProb). */
 int gaml_cache_commit(gaml_ctx* ctx);
 
+/* Flat on-disk form of one read set's cache (replaces ReadSet::SaveAligments / LoadAligments, graph.cc:1035-1100, whose
+ * Boost archive the reference has switched off): keys with their metadata, then the key-major record arena exactly as
+ * the device holds it. gaml_cache_load wants the read set created (gaml_add_readset with the same kind, read count and
+ * shard) and still empty; the device index is built at the next commit as usual. */
+int gaml_cache_save(gaml_ctx* ctx, int set, const char* path);
+int gaml_cache_load(gaml_ctx* ctx, int set, const char* path);
+
 /* ---- scoring ---------------------------------------------------------------------------- */
 /* ProbCalculator::CalcProb(paths, zeros, total_len) (prob_calculator.h:63-109). Walks are concatenated
  * node ids (negative = gap of that many N's) with n_walks+1 offsets. STATEFUL exactly like the

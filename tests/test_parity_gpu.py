@@ -165,6 +165,38 @@ def test_result_exchange_between_two_contexts_matches_the_unsharded_result(oracl
     whole.close()
 
 
+def test_flat_cache_file_round_trip(tmp_path):
+    """gaml_cache_save / gaml_cache_load: a context whose read sets were filled from the flat cache files scores a
+    trajectory identically (partials and per-read values bit for bit) to the one the files were written from —
+    paired + single + PacBio sets, and a read-id shard."""
+    wl = synth.mixed_workload(10, 6000, 3000, 300, n_single=1000, n_evals=6, seed=21, pacbio_len=5000)
+    for shard_of in (None, (1, 2)):
+        src = api.ProbCalculator.from_workload(wl, shard_of=shard_of)
+        for s in range(len(wl.sets)):
+            src.cache_save(s, str(tmp_path / f"set{s}.gcc"))
+        dst = api.ProbCalculator(wl.node_len, wl.normalize_map)
+        for s, spec in enumerate(wl.sets):
+            shard = None
+            if shard_of is not None:
+                shard = dist.shard_bounds(spec.n_reads, *shard_of)
+            assert dst.add_readset(spec, shard) == s
+            dst.cache_load(s, str(tmp_path / f"set{s}.gcc"))
+        with pytest.raises(api.GamlError):
+            dst.cache_load(0, str(tmp_path / "set0.gcc"))   # not empty any more
+        for walks in wl.evals:
+            a, ta = src.calc_prob_partial(walks)
+            b, tb = dst.calc_prob_partial(walks)
+            assert ta == tb and np.array_equal(a, b)
+        for s in range(len(wl.sets)):
+            assert np.array_equal(src.read_values(s), dst.read_values(s), equal_nan=True)
+        src.close()
+        dst.close()
+    bad = api.ProbCalculator.from_workload(wl)
+    with pytest.raises(api.GamlError):
+        bad.cache_load(0, str(tmp_path / "no_such_file.gcc"))
+    bad.close()
+
+
 @pytest.fixture(scope="module")
 def c2():
     wl = synth.paired_workload(460, 10000, 2_000_000, n_evals=10, seed=42)
