@@ -640,14 +640,14 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
   WalkSet& ws = ctx->cur();
   const WalkSet* old_set = ctx->have_prev ? &ctx->prev() : nullptr;
-  const WalkDiff diff = load_walks(ws, old_set, nodes, offs, n_walks);   // hashes only the walks that changed
-  ctx->cur_diff = diff;
+  WalkDiff& diff = ctx->cur_diff;
+  load_walks(ws, old_set, nodes, offs, n_walks, diff);   // aligns with the previous list, hashes only the walks that changed
   const int n_nodes = (int)ctx->node_len.size();
   // node ids and GetTotalLen (graph.cc:1966, int arithmetic like the reference): over the changed walks when the rest is
   // the previous evaluation's, else over all of them
-  auto span_len = [&](const WalkSet& w, int lo, int hi, bool check, bool& bad) {
+  auto walk_len = [&](const WalkSet& w, int i, bool check, bool& bad) {
     unsigned t = 0;
-    for (int64_t k = w.offs[lo]; k < w.offs[hi]; k++) {
+    for (int64_t k = w.offs[i]; k < w.offs[i + 1]; k++) {
       const int x = w.nodes[(size_t)k];
       if (check && x >= n_nodes) { bad = true; return 0u; }
       t += (unsigned)(x < 0 ? -x : ctx->node_len[x]);
@@ -655,14 +655,15 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     return t;
   };
   bool bad = false;
-  int total_len;
+  unsigned tl_u = 0;
   if (diff.valid) {
-    const unsigned removed = span_len(*old_set, diff.prefix, old_set->n - diff.suffix, false, bad);
-    const unsigned added_len = span_len(ws, diff.prefix, ws.n - diff.suffix, true, bad);
-    total_len = (int)((unsigned)ctx->prev_total_len - removed + added_len);
+    tl_u = (unsigned)ctx->prev_total_len;
+    for (int i : diff.old_changed) tl_u -= walk_len(*old_set, i, false, bad);
+    for (int i : diff.new_changed) tl_u += walk_len(ws, i, true, bad);
   } else {
-    total_len = (int)span_len(ws, 0, ws.n, true, bad);
+    for (int i = 0; i < ws.n && !bad; i++) tl_u += walk_len(ws, i, true, bad);
   }
+  const int total_len = (int)tl_u;
   if (bad) return fail(ctx, GAML_ERR_ARG, "walk references a node outside the graph");
   ctx->cur_total_len = total_len;
   int rc = commit(ctx);
@@ -1246,8 +1247,8 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
     const WalkDiff& d = ctx->cur_diff;
     if (ctx->have_prev && d.valid && ctx->prev_counts.valid && !ctx->prev_counts.crowded()) {
       const WalkSet& was = ctx->prev();
-      for (int i = d.prefix; i < was.n - d.suffix; i++) ctx->prev_counts.add(was.hash[i], -1);
-      for (int i = d.prefix; i < now.n - d.suffix; i++) ctx->prev_counts.add(now.hash[i], +1);
+      for (int i : d.old_changed) ctx->prev_counts.add(was.hash[i], -1);
+      for (int i : d.new_changed) ctx->prev_counts.add(now.hash[i], +1);
     } else {
       ctx->prev_counts.rebuild(now);
     }

@@ -7,8 +7,9 @@
 // and that order decides in which sequence the erased walks' terms are subtracted from a read's running probability
 // (bit-exact replay). get_changes_reference() runs exactly that, with the same hash values, on
 // (pointer, length, hash) elements. An annealing step, though, re-submits all walks but one to four unchanged, so
-// get_changes_fast() first diffs the new walk list against the previous one (common prefix / suffix), confines the
-// multiset difference to the changed region, and orders two or more erased walks by the container's rule instead of
+// load_walks() first diffs the new walk list against the previous one (runs of equal walks, resynchronised after each
+// edit), get_changes_fast() confines the multiset difference to the few walks that changed and orders two or more
+// erased walks by the container's rule instead of
 // building it: libstdc++ chains all nodes in one list; a bucket's nodes sit together, a new node goes to the FRONT of
 // its bucket, and a bucket that receives its first node goes to the front of the whole list. With no equal elements
 // involved (checked; otherwise the reference path runs) the iteration order therefore is: buckets by the index of
@@ -46,48 +47,134 @@ struct WalkSet {
   std::vector<int32_t> nodes;
   std::vector<int64_t> offs;   // n + 1
   std::vector<size_t> hash;    // n
+  std::vector<uint32_t> bkt;   // n: hash % bkt_count — the walk's bucket when THIS set is the reference's old_paths
+  size_t bkt_count = 0;        // bucket_count_for(n)
   int n = 0;
   WalkView view(int i) const { return WalkView{nodes.data() + offs[i], (int)(offs[i + 1] - offs[i]), hash[i], i}; }
   Walk walk(int i) const { return Walk(nodes.begin() + offs[i], nodes.begin() + offs[i + 1]); }
 };
 
-// cur = old[0, prefix) + NEW REGION + old[n_old - suffix, n_old); the old region is old[prefix, n_old - suffix)
-struct WalkDiff {
-  bool valid = false;
-  int prefix = 0, suffix = 0;
+// x mod d for a fixed d (Lemire, Kaser, Kurz: "Faster remainder by direct computation", 64-bit version)
+struct FastMod {
+  unsigned __int128 M;
+  uint64_t d;
+  explicit FastMod(uint64_t d_) : M(~(unsigned __int128)0 / d_ + 1), d(d_) {}
+  uint64_t operator()(uint64_t a) const {
+    const unsigned __int128 low = M * a;
+    const unsigned __int128 bottom = (unsigned __int128)(uint64_t)low * d;
+    const unsigned __int128 top = (unsigned __int128)(uint64_t)(low >> 64) * d;
+    return (uint64_t)((top + (bottom >> 64)) >> 64);
+  }
 };
 
-// Copies the caller's walk arrays into `cur`; hashes only the walks that differ from `old` (null: all of them).
-inline WalkDiff load_walks(WalkSet& cur, const WalkSet* old, const int32_t* nodes, const int64_t* offs, int n_walks) {
+// Bucket count libstdc++ gives unordered_multiset(first, last) for n elements.
+inline size_t bucket_count_for(size_t n) {
+  std::__detail::_Prime_rehash_policy pol;
+  return pol._M_next_bkt(pol._M_bkt_for_elements(n));
+}
+
+// The walks of the new list that have no equal partner at the aligned position of the old list, and vice versa
+// (ascending indices). valid = the alignment succeeded with few enough changes for the fast path.
+struct WalkDiff {
+  bool valid = false;
+  std::vector<int> old_changed, new_changed;
+};
+constexpr int kMaxChanged = 64;
+
+// Length of the common prefix of a[0..limit) and b[0..limit) + shift, compared in blocks (a vectorised pass over the
+// long agreeing runs instead of a branch per element); common_suffix likewise from the back.
+template <class T>
+inline int64_t common_prefix(const T* a, const T* b, int64_t limit, T shift) {
+  int64_t k = 0;
+  constexpr int64_t kBlockLen = 256;
+  while (k + kBlockLen <= limit) {
+    T diff = 0;
+    for (int64_t i = 0; i < kBlockLen; i++) diff |= (T)(a[k + i] ^ (T)(b[k + i] + shift));
+    if (diff != 0) break;
+    k += kBlockLen;
+  }
+  while (k < limit && a[k] == (T)(b[k] + shift)) k++;
+  return k;
+}
+
+// Copies the caller's walk arrays into `cur` and aligns them with `old` (null: no previous list): equal walks keep
+// their hashes, the others are hashed and reported in the diff. Two cursors walk both lists; a run of equal walks is
+// found on the flat arrays (boundaries and nodes compared in bulk); at a mismatch the cursors resynchronise on the
+// nearest equal pair within a few walks (an edited, removed or inserted walk), else the rest counts as changed.
+inline void load_walks(WalkSet& cur, const WalkSet* old, const int32_t* nodes, const int64_t* offs, int n_walks, WalkDiff& d) {
   const int64_t base = n_walks > 0 ? offs[0] : 0, total = n_walks > 0 ? offs[n_walks] - base : 0;
   cur.n = n_walks;
   cur.nodes.assign(nodes + base, nodes + base + total);
   cur.offs.resize((size_t)n_walks + 1);
-  for (int i = 0; i <= n_walks; i++) cur.offs[i] = (n_walks > 0 ? offs[i] : 0) - base;
+  if (n_walks > 0)
+    for (int i = 0; i <= n_walks; i++) cur.offs[i] = offs[i] - base;
+  else
+    cur.offs[0] = 0;
   cur.hash.resize((size_t)n_walks);
-  WalkDiff d;
-  int lo = 0, hi_new = n_walks;
-  if (old) {
-    auto equal_at = [&](int i_new, int i_old) {
-      const int64_t ln = cur.offs[i_new + 1] - cur.offs[i_new], lo_ = old->offs[i_old + 1] - old->offs[i_old];
-      return ln == lo_ && (ln == 0 || memcmp(cur.nodes.data() + cur.offs[i_new], old->nodes.data() + old->offs[i_old],
-                                            sizeof(int32_t) * (size_t)ln) == 0);
-    };
-    const int m = std::min(n_walks, old->n);
-    int p = 0;
-    while (p < m && equal_at(p, p)) p++;
-    int q = 0;
-    while (q < m - p && equal_at(n_walks - 1 - q, old->n - 1 - q)) q++;
-    for (int i = 0; i < p; i++) cur.hash[i] = old->hash[i];
-    for (int i = 0; i < q; i++) cur.hash[n_walks - 1 - i] = old->hash[old->n - 1 - i];
-    d.valid = true;
-    d.prefix = p;
-    d.suffix = q;
-    lo = p;
-    hi_new = n_walks - q;
+  cur.bkt.resize((size_t)n_walks);
+  cur.bkt_count = bucket_count_for((size_t)std::max(n_walks, 1));
+  const FastMod mod(cur.bkt_count);
+  const bool same_buckets = old && old->bkt_count == cur.bkt_count;   // the prime changes only when n crosses a table entry
+  d.valid = false;
+  d.old_changed.clear();
+  d.new_changed.clear();
+  auto hash_new = [&](int i) {
+    cur.hash[i] = hash_nodes(cur.nodes.data() + cur.offs[i], (int)(cur.offs[i + 1] - cur.offs[i]));
+    cur.bkt[i] = (uint32_t)mod(cur.hash[i]);
+  };
+  if (!old) {
+    for (int i = 0; i < n_walks; i++) hash_new(i);
+    return;
   }
-  for (int i = lo; i < hi_new; i++) cur.hash[i] = hash_nodes(cur.nodes.data() + cur.offs[i], (int)(cur.offs[i + 1] - cur.offs[i]));
-  return d;
+  auto equal_at = [&](int x, int y) {   // old[x] == new[y]
+    const int64_t lo_ = old->offs[x + 1] - old->offs[x], ln = cur.offs[y + 1] - cur.offs[y];
+    return lo_ == ln && (ln == 0 || memcmp(cur.nodes.data() + cur.offs[y], old->nodes.data() + old->offs[x], sizeof(int32_t) * (size_t)ln) == 0);
+  };
+  int x = 0, y = 0;
+  bool overflow = false;
+  while (x < old->n && y < n_walks) {
+    // run of equal walks from (x, y): boundaries (shifted), then nodes
+    const int64_t lim = std::min(old->n - x, n_walks - y);
+    const int64_t r1 = common_prefix<int64_t>(cur.offs.data() + y + 1, old->offs.data() + x + 1, lim, cur.offs[y] - old->offs[x]);
+    const int64_t span = cur.offs[y + r1] - cur.offs[y];
+    const int64_t same = common_prefix<int32_t>(cur.nodes.data() + cur.offs[y], old->nodes.data() + old->offs[x], span, 0);
+    int64_t r = r1;
+    if (same < span) r = (std::upper_bound(cur.offs.begin() + y, cur.offs.begin() + y + r1 + 1, cur.offs[y] + same) - (cur.offs.begin() + y)) - 1;
+    if (r > 0) {
+      memcpy(cur.hash.data() + y, old->hash.data() + x, sizeof(size_t) * (size_t)r);
+      if (same_buckets) memcpy(cur.bkt.data() + y, old->bkt.data() + x, sizeof(uint32_t) * (size_t)r);
+      x += (int)r;
+      y += (int)r;
+      continue;
+    }
+    // mismatch at (x, y): nearest equal pair within a few walks
+    int best_dx = -1, best_dy = -1;
+    for (int sdist = 1; sdist <= 6 && best_dx < 0; sdist++)
+      for (int dx = 0; dx <= sdist && best_dx < 0; dx++) {
+        const int dy = sdist - dx;
+        if (x + dx < old->n && y + dy < n_walks && equal_at(x + dx, y + dy)) { best_dx = dx; best_dy = dy; }
+      }
+    if (best_dx < 0) break;   // no resynchronisation point: everything from here on counts as changed
+    for (int k = 0; k < best_dx; k++) d.old_changed.push_back(x + k);
+    for (int k = 0; k < best_dy; k++) { hash_new(y + k); d.new_changed.push_back(y + k); }
+    x += best_dx;
+    y += best_dy;
+    if ((int)d.old_changed.size() > kMaxChanged || (int)d.new_changed.size() > kMaxChanged) { overflow = true; break; }
+  }
+  if ((old->n - x) > kMaxChanged || (n_walks - y) > kMaxChanged) overflow = true;
+  for (; y < n_walks; y++) {
+    hash_new(y);
+    if (!overflow) d.new_changed.push_back(y);
+  }
+  if (!overflow)
+    for (; x < old->n; x++) d.old_changed.push_back(x);
+  if (!same_buckets)
+    for (int i = 0; i < n_walks; i++) cur.bkt[i] = (uint32_t)mod(cur.hash[i]);
+  d.valid = !overflow && (int)d.old_changed.size() <= kMaxChanged && (int)d.new_changed.size() <= kMaxChanged;
+  if (!d.valid) {
+    d.old_changed.clear();
+    d.new_changed.clear();
+  }
 }
 
 // How many walks of a set carry a given hash (open addressing; an entry whose count drops to zero stays as a tombstone
@@ -152,78 +239,72 @@ inline void get_changes_reference(const WalkSet& old, const WalkSet& cur, Change
   for (const WalkView& r : idx) out.erased.push_back(r);
 }
 
-// x mod d for a fixed d (Lemire, Kaser, Kurz: "Faster remainder by direct computation", 64-bit version)
-struct FastMod {
-  unsigned __int128 M;
-  uint64_t d;
-  explicit FastMod(uint64_t d_) : M(~(unsigned __int128)0 / d_ + 1), d(d_) {}
-  uint64_t operator()(uint64_t a) const {
-    const unsigned __int128 low = M * a;
-    const unsigned __int128 bottom = (unsigned __int128)(uint64_t)low * d;
-    const unsigned __int128 top = (unsigned __int128)(uint64_t)(low >> 64) * d;
-    return (uint64_t)((top + (bottom >> 64)) >> 64);
-  }
-};
-
-// Bucket count libstdc++ gives unordered_multiset(first, last) for n elements.
-inline size_t bucket_count_for(size_t n) {
-  std::__detail::_Prime_rehash_policy pol;
-  return pol._M_next_bkt(pol._M_bkt_for_elements(n));
-}
-
 // Same result as get_changes_reference, from the diff. false = not applicable (equal walks are involved): use the
 // reference path. old_counts must describe `old`.
 inline bool get_changes_fast(const WalkSet& old, const WalkSet& cur, const WalkDiff& d, const HashCounts& old_counts, Changes& out) {
   if (!d.valid || !old_counts.valid) return false;
   out.erased.clear();
   out.added.clear();
-  const int a0 = d.prefix, a1 = old.n - d.suffix, b0 = d.prefix, b1 = cur.n - d.suffix;
-  if (a1 - a0 > 64 || b1 - b0 > 64) return false;   // a wholesale change: the quadratic matching below is not meant for it
-  // no walk outside the changed region may share a hash with one inside it (then the multiset difference is confined
-  // to the region, and no erased walk has an equal one elsewhere in the container)
+  const std::vector<int>& A = d.old_changed;
+  const std::vector<int>& B = d.new_changed;
+  // no walk outside the changed ones may share a hash with one of them (then the multiset difference is confined to
+  // them: every other walk has an equal partner in the other list)
   auto outside = [&](uint64_t h) {
     int c = old_counts.get(h);
-    for (int i = a0; i < a1; i++) c -= old.hash[i] == h;
+    for (int i : A) c -= old.hash[i] == h;
     return c;
   };
-  for (int i = a0; i < a1; i++)
+  for (int i : A)
     if (outside(old.hash[i]) != 0) return false;
-  for (int i = b0; i < b1; i++)
+  for (int i : B)
     if (outside(cur.hash[i]) != 0) return false;
-  // inside the region: every new walk, in order, takes an unmatched equal old walk or is added
-  bool taken[64] = {false};
-  for (int i = b0; i < b1; i++) {
+  // among the changed walks: every new one, in order, takes an unmatched equal old walk or is added
+  bool taken[kMaxChanged] = {false};
+  for (int i : B) {
     const WalkView v = cur.view(i);
     int hit = -1;   // (find() returns the most recently inserted of several equal elements)
-    for (int j = a1 - 1; j >= a0 && hit < 0; j--)
-      if (!taken[j - a0] && same_walk(old.view(j), v)) hit = j;
-    if (hit >= 0) taken[hit - a0] = true;
+    for (int j = (int)A.size() - 1; j >= 0 && hit < 0; j--)
+      if (!taken[j] && same_walk(old.view(A[j]), v)) hit = j;
+    if (hit >= 0) taken[hit] = true;
     else out.added.push_back(v);
   }
-  for (int j = a0; j < a1; j++)
-    if (!taken[j - a0]) out.erased.push_back(old.view(j));
+  for (size_t j = 0; j < A.size(); j++)
+    if (!taken[j]) out.erased.push_back(old.view(A[j]));
   if (out.erased.size() < 2) return true;
   // an element with an equal one anywhere in the container sits next to it, out of index order: the rule below holds
   // for elements that are unique in the old set
   for (const WalkView& e : out.erased)
     if (old_counts.get(e.h) != 1) return false;
   // the container's iteration order: buckets by the index of their first element (descending), then index (descending)
-  const FastMod mod(bucket_count_for((size_t)old.n));
+  if (old.bkt_count != bucket_count_for((size_t)std::max(old.n, 1))) return false;   // (cannot happen: load_walks keeps it)
   const size_t k = out.erased.size();
-  uint64_t bkt[64];
-  int first[64];
+  uint32_t bkt[kMaxChanged];
+  int first[kMaxChanged];
   int last_needed = 0;
   for (size_t x = 0; x < k; x++) {
-    bkt[x] = mod(out.erased[x].h);
+    bkt[x] = old.bkt[out.erased[x].index];
     first[x] = out.erased[x].index;   // an element is in its own bucket: the bucket's first element is at or before it
     last_needed = std::max(last_needed, out.erased[x].index);
   }
-  for (int j = 0; j < last_needed; j++) {
-    const uint64_t b = mod(old.hash[j]);
-    for (size_t x = 0; x < k; x++)
-      if (b == bkt[x] && j < first[x]) first[x] = j;
+  if (k == 2) {   // the common case (a join, a tail swap), kept tight
+    const uint32_t b0 = bkt[0], b1 = bkt[1];
+    int f0 = first[0], f1 = first[1];
+    const uint32_t* bp = old.bkt.data();
+    for (int j = 0; j < last_needed; j++) {
+      const uint32_t b = bp[j];
+      if (b == b0 && j < f0) f0 = j;
+      if (b == b1 && j < f1) f1 = j;
+    }
+    first[0] = f0;
+    first[1] = f1;
+  } else {
+    for (int j = 0; j < last_needed; j++) {
+      const uint32_t b = old.bkt[j];
+      for (size_t x = 0; x < k; x++)
+        if (b == bkt[x] && j < first[x]) first[x] = j;
+    }
   }
-  int order[64];
+  int order[kMaxChanged];
   for (size_t x = 0; x < k; x++) order[x] = (int)x;
   std::sort(order, order + k, [&](int x, int y) {
     if (first[x] != first[y]) return first[x] > first[y];

@@ -36,7 +36,8 @@ int main() {
     WalkSet sets[2];
     int which = 0;
     flatten(cur);
-    load_walks(sets[which], nullptr, g_nodes.data(), g_offs.data(), (int)cur.size());
+    WalkDiff d0;
+    load_walks(sets[which], nullptr, g_nodes.data(), g_offs.data(), (int)cur.size(), d0);
     HashCounts counts;
     counts.rebuild(sets[which]);
     std::pmr::monotonic_buffer_resource pool(1 << 16);
@@ -83,7 +84,8 @@ int main() {
       flatten(nw);
       WalkSet& old = sets[which];
       WalkSet& nxt = sets[which ^ 1];
-      const WalkDiff d = load_walks(nxt, &old, g_nodes.data(), g_offs.data(), (int)nw.size());
+      WalkDiff d;
+      load_walks(nxt, &old, g_nodes.data(), g_offs.data(), (int)nw.size(), d);
       for (int i = 0; i < nxt.n; i++)
         if (nxt.hash[i] != hash_nodes(nxt.nodes.data() + nxt.offs[i], (int)(nxt.offs[i + 1] - nxt.offs[i]))) {
           printf("FAIL: hash carried over wrongly (trial %d step %d walk %d)\n", trial, step, i);
@@ -109,9 +111,12 @@ int main() {
         }
       }
       // the evaluated set becomes the old one: update the counts by the diff, like the engine does
-      for (int i = d.prefix; i < old.n - d.suffix; i++) counts.add(old.hash[i], -1);
-      for (int i = d.prefix; i < nxt.n - d.suffix; i++) counts.add(nxt.hash[i], +1);
-      if (counts.crowded()) counts.rebuild(nxt);
+      if (d.valid && !counts.crowded()) {
+        for (int i : d.old_changed) counts.add(old.hash[i], -1);
+        for (int i : d.new_changed) counts.add(nxt.hash[i], +1);
+      } else {
+        counts.rebuild(nxt);
+      }
       for (int i = 0; i < nxt.n; i++)
         if (counts.get(nxt.hash[i]) < 1) { printf("FAIL: counts lost a walk\n"); return 1; }
       which ^= 1;

@@ -7,8 +7,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gaml_b200 import api, synth
 
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-wl = synth.paired_workload(int(460 * scale), 10000, int(2_000_000 * scale), n_evals=202, seed=42)
+n_unique = int(sys.argv[1]) if len(sys.argv) > 1 else 460        # walks (nodes) of the workload: 460 = config 2, 10000 = config 4
+n_pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
+wl = synth.paired_workload(n_unique, 10000, n_pairs, n_evals=202, seed=42)
 pc = api.ProbCalculator.from_workload(wl)
 pc.set_profiling(1)
 flat0 = api.FlatWalks(wl.evals[0])
