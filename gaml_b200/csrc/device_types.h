@@ -148,6 +148,26 @@ struct ScoreParams {
   uint32_t* stamp;           // per read: epoch of the evaluation that last claimed it
 };
 
+// ---- PacBio coverage penalty (graph.cc:3197-3250) -----------------------------------------------------------------
+struct Int2 { int32_t x, y; };
+struct PbCovParams {
+  const void* seeds;            // int4 {walk, start, end, -}: the artificial interval and one interval per node of every walk
+  int32_t n_seed;
+  const void* occ;              // int4 {walk, offset of the key's first node, arena range begin, count} per live key occurrence
+  const uint32_t* occ_prefix;   // n_occ + 1 prefix sums of the counts
+  int32_t n_occ;
+  const ArenaLong* arena;
+  const void* arena_pos;        // int2 {position, position_end} per arena record
+  const uint32_t* lens;
+  double log_mismatch, log_match;   // GetMinReadProb, graph.h:478-481
+  unsigned long long* ikey;     // intervals: (walk, start) keys, 2 x cap (unsorted, sorted)
+  int32_t* iend;                // their ends, 2 x cap
+  unsigned long long* pkey;     // event positions (walk, pos), 4 x cap
+  uint32_t* count;              // intervals emitted
+  uint32_t cap;
+  uint32_t* error_flag;
+};
+
 // ---- batched candidate evaluation (gaml_calc_prob_batch, BASELINE config 5) ------------------------------
 struct BatchCand {             // one candidate move, one paired read set
   int32_t key_begin[2];        // this candidate's slice of the batch key/slot arrays, per mate (keys sorted)

@@ -139,6 +139,8 @@ struct MateStore {
   std::unordered_map<Walk, int, WalkHash> key_ids;
   std::vector<KeyMeta> keys;
   std::vector<int4> pending;          // staged arena records (ArenaShort / ArenaLong bit patterns)
+  std::vector<Int2> pending_pos;      // long stores: {position, position_end} of the staged records (coverage penalty)
+  DevBuf arena_pos;                   // long stores: Int2 per arena record
   size_t arena_n = 0;                 // records on the device
   DevBuf arena, rows, first, rowptr, cursor, slots_a, slots_b, crows, cptr;
   bool dirty = true;
@@ -175,6 +177,12 @@ struct ReadSetState {
   int bad_bases = 0;            // ScoringState::bad_bases (graph.h:614)
   bool penalty = false;         // paired set with penalty_constant != 0: coverage events are collected
   DevBuf d_cov_thr, d_ev, d_ev_sorted, d_ev_temp, d_bad;
+  // PacBio coverage penalty (graph.cc:3197-3250)
+  bool pb_penalty = false;
+  DevBuf d_pb_ikey, d_pb_iend, d_pb_pkey, d_pb_packed, d_pb_runmax, d_pb_temp, d_pb_count;
+  std::vector<int4> h_pb_seeds, h_pb_occ;
+  std::vector<uint32_t> h_pb_prefix;
+  std::vector<int> h_pb_walk_len;
   std::vector<int> h_bad;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this set's streaming kernel(s)
   ~ReadSetState() {
@@ -201,6 +209,8 @@ struct SetPlan {
   size_t touch_off = 0, prefix_off = 0;
   int n_touch = 0;
   // full paired evaluations: arena ranges of the keys that occur several times (the multi pass)
+  size_t pb_seeds_off = 0, pb_occ_off = 0, pb_prefix_off = 0, pb_len_off = 0;   // PacBio coverage penalty inputs
+  uint32_t pb_cap = 0;
   size_t mtouch_off = 0, mprefix_off = 0;
   int n_mtouch = 0, n_mtouch1 = 0;
   int64_t multi_records = 0;
@@ -463,6 +473,10 @@ void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, in
   unsigned tl = 0;
   Walk key;
   std::vector<int> begin, end;
+  rs.h_pb_seeds.clear();
+  rs.h_pb_occ.clear();
+  rs.h_pb_prefix.clear();
+  rs.h_pb_walk_len.clear();
   for (int wi = 0; wi < n_walks; wi++) {
     Walk w = walks[wi];
     for (int& x : w)
@@ -477,6 +491,12 @@ void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, in
       end[i] = off;
     }
     tl += (unsigned)off;
+    if (rs.pb_penalty) {   // coverage sweep inputs of this walk: its length, the artificial interval, one interval per node
+      rs.h_pb_walk_len.push_back(off);
+      rs.h_pb_seeds.push_back(make_int4(wi, -1000, 2000, 0));   // events (-1000, 1), (2000, -3000), graph.cc:3199-3200
+      for (size_t i = 0; i < n; i++)
+        if (w[i] >= 0) rs.h_pb_seeds.push_back(make_int4(wi, begin[i], end[i], 0));
+    }
     for (size_t i = 0; i < n; i++) {
       key.clear();
       for (size_t j = i; j < n; j++) {
@@ -485,6 +505,10 @@ void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, in
         if (kid >= 0 && rs.mate[0].keys[kid].count) {
           ob.add(kid, 0, begin[i], INT_MIN);
           sp.records += rs.mate[0].keys[kid].count;
+          if (rs.pb_penalty) {
+            const KeyMeta& km = rs.mate[0].keys[kid];
+            rs.h_pb_occ.push_back(make_int4(wi, begin[i], (int)km.arena_off, (int)km.count));
+          }
         }
         if ((end[j] - begin[i]) - (end[i] - begin[i]) > rs.max_len[0]) break;   // graph.cc:2450
       }
@@ -556,13 +580,19 @@ int commit(gaml_ctx* ctx) {
       const size_t total = st.total_records();
       if (total > 0xfffffff0ull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 alignment records in one mate store");
       CU(st.arena.reserve(std::max<size_t>(total, 1) * 16, st.arena_n * 16, false, ctx->stream));
+      if (st.is_long) CU(st.arena_pos.reserve(std::max<size_t>(total, 1) * 8, st.arena_n * 8, false, ctx->stream));
       if (!st.pending.empty()) {
         CU(cudaMemcpyAsync(st.arena.as<char>() + st.arena_n * 16, st.pending.data(), st.pending.size() * 16,
                            cudaMemcpyHostToDevice, ctx->stream));
+        if (st.is_long)
+          CU(cudaMemcpyAsync(st.arena_pos.as<char>() + st.arena_n * 8, st.pending_pos.data(), st.pending_pos.size() * 8,
+                             cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         st.arena_n = total;
         st.pending.clear();
         st.pending.shrink_to_fit();
+        st.pending_pos.clear();
+        st.pending_pos.shrink_to_fit();
       }
       CU(st.rows.reserve(std::max<size_t>(total, 1) * 16, 0, false, ctx->stream));
       if (!st.is_long) CU(st.first.reserve(std::max<size_t>(rs.n_local, 1) * 16, 0, false, ctx->stream));
@@ -796,6 +826,21 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     off = align16(off + mtouches[s].size() * sizeof(TouchRange));
     sp.mprefix_off = off;
     off = align16(off + (mtouches[s].size() + 1) * sizeof(uint32_t));
+    if (rs.pb_penalty) {
+      sp.pb_seeds_off = off;
+      off = align16(off + rs.h_pb_seeds.size() * 16);
+      sp.pb_occ_off = off;
+      off = align16(off + rs.h_pb_occ.size() * 16);
+      sp.pb_prefix_off = off;
+      off = align16(off + (rs.h_pb_occ.size() + 1) * 4);
+      sp.pb_len_off = off;
+      off = align16(off + std::max<size_t>(rs.h_pb_walk_len.size(), 1) * 4);
+      uint64_t recs = 0;
+      for (const int4& o : rs.h_pb_occ) recs += (uint32_t)o.w;
+      const uint64_t cap = rs.h_pb_seeds.size() + recs + 16;
+      if (cap > 0x3fffffffull) return fail(ctx, GAML_ERR_CAPACITY, "too many PacBio coverage intervals for one evaluation");
+      sp.pb_cap = (uint32_t)cap;
+    }
     if (rs.penalty) {
       sp.n_cov_walks = (int)cov_cs[s].size();
       sp.n_type1 = 0;
@@ -840,6 +885,19 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     }
     if (macc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 records under repeated keys in one evaluation");
     mpre[mtouches[s].size()] = (uint32_t)macc;
+    if (ctx->sets[s]->pb_penalty) {
+      ReadSetState& rp = *ctx->sets[s];
+      if (!rp.h_pb_seeds.empty()) memcpy(hb + sp.pb_seeds_off, rp.h_pb_seeds.data(), rp.h_pb_seeds.size() * 16);
+      if (!rp.h_pb_occ.empty()) memcpy(hb + sp.pb_occ_off, rp.h_pb_occ.data(), rp.h_pb_occ.size() * 16);
+      uint32_t* pp = reinterpret_cast<uint32_t*>(hb + sp.pb_prefix_off);
+      uint32_t run = 0;
+      for (size_t t = 0; t < rp.h_pb_occ.size(); t++) {
+        pp[t] = run;
+        run += (uint32_t)rp.h_pb_occ[t].w;
+      }
+      pp[rp.h_pb_occ.size()] = run;
+      if (!rp.h_pb_walk_len.empty()) memcpy(hb + sp.pb_len_off, rp.h_pb_walk_len.data(), rp.h_pb_walk_len.size() * 4);
+    }
     if (ctx->sets[s]->penalty) {
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(hb + sp.type1_off);
       int* csb = reinterpret_cast<int*>(hb + sp.csbegin_off);
@@ -1042,7 +1100,7 @@ int launch(gaml_ctx* ctx) {
   char* blob = ctx->d_blob.as<char>();
   int launches = 0;
   bool any_penalty = false;
-  for (auto& rs : ctx->sets) any_penalty |= rs->penalty;
+  for (auto& rs : ctx->sets) any_penalty |= rs->penalty || rs->pb_penalty;
   LaunchList chain;
   const bool record = ctx->use_graphs && !ctx->profile && !any_penalty && ctx->sets.size() <= 3;
   struct RecorderGuard { ~RecorderGuard() { set_launch_recorder(nullptr); } } recorder_guard;
@@ -1109,6 +1167,39 @@ int launch(gaml_ctx* ctx) {
       launch_pacbio_full(P, sp.grid, og, st, chained, profile, rs.ev0, rs.ev1);
       chained = true;
       launches += 2;
+      if (rs.pb_penalty) {
+        const size_t cap = sp.pb_cap;
+        CU(rs.d_pb_ikey.reserve(cap * 2 * 8, 0, false, st));
+        CU(rs.d_pb_iend.reserve(cap * 2 * 4, 0, false, st));
+        CU(rs.d_pb_pkey.reserve(cap * 4 * 8, 0, false, st));
+        CU(rs.d_pb_packed.reserve(cap * 8, 0, false, st));
+        CU(rs.d_pb_runmax.reserve(cap * 8, 0, false, st));
+        CU(rs.d_pb_temp.reserve(std::max<size_t>(pacbio_coverage_temp_bytes(sp.pb_cap), 256), 0, false, st));
+        CU(rs.d_pb_count.reserve(256, 0, true, st));
+        CU(rs.d_bad.reserve(256, 0, true, st));
+        PbCovParams C{};
+        C.seeds = blob + sp.pb_seeds_off;
+        C.n_seed = (int)rs.h_pb_seeds.size();
+        C.occ = blob + sp.pb_occ_off;
+        C.occ_prefix = reinterpret_cast<const uint32_t*>(blob + sp.pb_prefix_off);
+        C.n_occ = (int)rs.h_pb_occ.size();
+        C.arena = rs.mate[0].arena.as<ArenaLong>();
+        C.arena_pos = rs.mate[0].arena_pos.p;
+        C.lens = rs.d_lens.as<uint32_t>();
+        C.log_mismatch = log(rs.cfg.mismatch_prob);   // logdouble(double) = log, graph.h:448, logdouble.hpp:18
+        C.log_match = log(rs.cfg.match_prob);
+        C.ikey = rs.d_pb_ikey.as<unsigned long long>();
+        C.iend = rs.d_pb_iend.as<int32_t>();
+        C.pkey = rs.d_pb_pkey.as<unsigned long long>();
+        C.count = rs.d_pb_count.as<uint32_t>();
+        C.cap = sp.pb_cap;
+        C.error_flag = P.error_flag;
+        CU(launch_pacbio_coverage(C, rs.d_pb_packed.as<unsigned long long>(), rs.d_pb_runmax.as<unsigned long long>(),
+                                  rs.d_pb_temp.p, rs.d_pb_temp.cap, reinterpret_cast<const int*>(blob + sp.pb_len_off),
+                                  rs.cfg.step, rs.d_bad.as<int>(), ctx->sm_count, st));
+        launches += 6;
+        chained = false;
+      }
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     }
   }
@@ -1165,6 +1256,12 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
   bool need_sync = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
+    if (rs.pb_penalty) {   // one int: this evaluation's bad bases over all walks (a local in CalcScoreForPacbio)
+      rs.h_bad.assign(1, 0);
+      CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      need_sync = true;
+      continue;
+    }
     if (!rs.penalty) continue;
     rs.h_bad.assign(std::max(ctx->plan[s].n_cov_walks, 1), 0);
     if (ctx->plan[s].n_cov_walks)
@@ -1227,6 +1324,7 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
     flags |= (uint32_t)(f & 15);
     ovf += (uint32_t)((f >> 4) & 0xffffff);
     scratch_placements = std::max<int64_t>(scratch_placements, (int64_t)(f >> 28));
+    if (rs.pb_penalty) rs.bad_bases = rs.h_bad[0];
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (rs.penalty) {   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
         if (ctx->plan[s].full) rs.bad_bases = 0;
@@ -1672,12 +1770,11 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   if (!cfg || n_reads_total < 0 || shard_lo < 0 || shard_hi < shard_lo || shard_hi > n_reads_total)
     return fail(ctx, GAML_ERR_ARG, "bad read set shape");
   if (cfg->kind < 0 || cfg->kind > 2) return fail(ctx, GAML_ERR_ARG, "bad read set kind");
-  if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PACBIO)
-    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a pacbio set: the PacBio coverage sweep (graph.cc:3197-3250) "
-                                           "is not on the device yet");
-  if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PAIRED && (shard_lo != 0 || shard_hi != n_reads_total))
-    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a sharded paired set: a walk's coverage events live on "
-                                           "all shards (SURVEY §8e)");
+  if (cfg->penalty_constant != 0.0 && cfg->kind != GAML_KIND_SINGLE && (shard_lo != 0 || shard_hi != n_reads_total))
+    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a sharded paired / pacbio set: a walk's coverage events live "
+                                           "on all shards (SURVEY §8e)");
+  if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PACBIO && !(cfg->match_prob > 0.0 && cfg->mismatch_prob > 0.0))
+    return fail(ctx, GAML_ERR_ARG, "a pacbio set with penalty_constant != 0 needs match_prob and mismatch_prob (GetMinReadProb, graph.h:478)");
   // single sets: the reference's sweep never counts a gap (graph.cc:1710-1733: last_event_type is never >= 3), so
   // bad_bases is identically 0 and the penalty term vanishes whatever penalty_constant is
   const int64_t n_local = shard_hi - shard_lo;
@@ -1760,6 +1857,7 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     CU(rs.d_ins.reserve(ins.size() * 8, 0, false, ctx->stream));
     CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (cfg->kind == GAML_KIND_PACBIO && cfg->penalty_constant != 0.0) rs.pb_penalty = true;
   if (paired && cfg->penalty_constant != 0.0) {
     rs.penalty = true;
     std::vector<double> cthr(rs.max_len[1] + 1);
@@ -1860,6 +1958,7 @@ int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t
     int4 v;
     memcpy(&v, &al, 16);
     st->pending.push_back(v);
+    st->pending_pos.push_back(Int2{a.position, a.position_end});
     km.count++;
   }
   km.any = n_records > 0;
@@ -1872,7 +1971,8 @@ int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t
 // ---- flat on-disk cache: the stores of one read set exactly as they sit in memory ---------------
 // File: "GAMLCC01", {int32 kind, int32 n_mates, int64 n_total, int64 lo, int64 hi}; per mate {int64 n_keys, int64
 // n_records}, per key {int32 key_len, key_len x int32 node ids, uint32 count, int32 max_pos, int32 any}, then the
-// key-major arena, 16 bytes per record — which is what the device holds, so loading is one read + one upload.
+// key-major arena, 16 bytes per record (PacBio stores: then {position, position_end}, 8 bytes per record) — which is what
+// the device holds, so loading is one read + one upload.
 namespace {
 struct CacheFileHeader { char magic[8]; int32_t kind, n_mates; int64_t n_total, lo, hi; };
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
@@ -1914,6 +2014,12 @@ int gaml_cache_save(gaml_ctx* ctx, int set, const char* path) {
       CU(cudaMemcpyAsync(host.data(), st.arena.p, st.arena_n * 16, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
       ok = ok && fwrite(host.data(), 16, st.arena_n, fc.f) == st.arena_n;
+      if (st.is_long) {   // {position, position_end} of every record, after the arena
+        std::vector<Int2> pos(st.arena_n);
+        CU(cudaMemcpyAsync(pos.data(), st.arena_pos.p, st.arena_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ok = ok && fwrite(pos.data(), 8, st.arena_n, fc.f) == st.arena_n;
+      }
     }
   }
   if (!ok) return fail(ctx, GAML_ERR_ARG, std::string("short write to ") + path);
@@ -1961,6 +2067,11 @@ int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
     st.pending.resize((size_t)counts[1]);
     if (counts[1] && fread(st.pending.data(), 16, (size_t)counts[1], fc.f) != (size_t)counts[1])
       return fail(ctx, GAML_ERR_ARG, "corrupt cache file (records)");
+    if (st.is_long) {
+      st.pending_pos.resize((size_t)counts[1]);
+      if (counts[1] && fread(st.pending_pos.data(), 8, (size_t)counts[1], fc.f) != (size_t)counts[1])
+        return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record positions)");
+    }
     for (const int4& v : st.pending) {   // {read, pos, edor, key} / {read, key, logprob}
       const int key = st.is_long ? v.y : v.w;
       if (v.x < 0 || v.x >= rs.n_local || key < 0 || key >= (int)st.keys.size()) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record)");

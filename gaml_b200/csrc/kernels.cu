@@ -1484,6 +1484,103 @@ __global__ void coverage_sweep_kernel(const unsigned long long* keys, unsigned n
   }
 }
 
+// ---- PacBio coverage penalty (CalcScoreForPacbio, graph.cc:3197-3250) --------------------------------------------
+// Per walk the reference sorts interval events — an artificial interval [-1000, 2000), one interval per node, one per
+// alignment at least as probable as its read's minimum (graph.h:478) — and sweeps them with a multiset of open starts;
+// after each event: good_start = min(earliest open start + step, next event, len - 250), and the stretch from
+// max(2500, event) to good_start counts as bad. Only the LAST event of a position can contribute (for the others the
+// next event is at the same position), and at that point the multiset holds exactly the intervals with
+// start <= x < end — so the sweep needs no order inside a position and no multiset: sort the intervals of all walks by
+// (walk, start), take the running maximum of their ends per walk, and the earliest-started interval still open at x is
+// the first one whose running maximum exceeds x (binary search), if it has started.
+__device__ __forceinline__ unsigned long long pb_key(int walk, int pos) {
+  return ((unsigned long long)(uint32_t)walk << 32) | (unsigned long long)((uint32_t)pos ^ 0x80000000u);
+}
+__device__ __forceinline__ int pb_key_pos(unsigned long long k) { return (int)((uint32_t)k ^ 0x80000000u); }
+
+__global__ void pacbio_cov_emit_kernel(const PbCovParams C) {
+  const uint32_t total = (uint32_t)C.n_seed + __ldg(C.occ_prefix + C.n_occ);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    int walk, start, end;
+    if (q < (uint32_t)C.n_seed) {
+      const int4 sd = ldg4(static_cast<const int4*>(C.seeds) + q);   // {walk, start, end, -}: the artificial interval and the nodes
+      walk = sd.x; start = sd.y; end = sd.z;
+    } else {
+      const uint32_t t = q - (uint32_t)C.n_seed;
+      int lo = 0, hi = C.n_occ;   // largest o with prefix[o] <= t
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(C.occ_prefix + mid) <= t) lo = mid; else hi = mid;
+      }
+      const int4 oc = ldg4(static_cast<const int4*>(C.occ) + lo);   // {walk, offset of the key's first node in the walk, arena range begin, count}
+      const uint32_t rec = (uint32_t)oc.z + (t - __ldg(C.occ_prefix + lo));
+      const ArenaLong al = C.arena[rec];
+      const double len = (double)__ldg(C.lens + al.read);
+      const double min_lp = __dadd_rn(__dmul_rn(C.log_mismatch, __dmul_rn(len, 0.25)), __dmul_rn(C.log_match, __dmul_rn(len, 0.75)));
+      if (al.logprob < min_lp) continue;   // graph.cc:3215
+      const int2 be = static_cast<const int2*>(C.arena_pos)[rec];
+      walk = oc.x; start = oc.y + be.x; end = oc.y + be.y;
+    }
+    const uint32_t slot = atomicAdd(C.count, 1u);
+    if (slot >= C.cap) { atomicOr(C.error_flag, 4u); continue; }
+    C.ikey[slot] = pb_key(walk, start);
+    C.iend[slot] = end;
+    C.pkey[2 * slot] = pb_key(walk, start);
+    C.pkey[2 * slot + 1] = pb_key(walk, end);
+  }
+}
+
+// (walk, running maximum of the interval ends) packed for a segmented inclusive max scan
+__global__ void pacbio_cov_pack_kernel(const unsigned long long* ikey, const int* iend, unsigned long long* packed, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[i] = (ikey[i] & 0xffffffff00000000ull) | (unsigned long long)((uint32_t)iend[i] ^ 0x80000000u);
+}
+struct PbSegMax {
+  __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
+    if ((a >> 32) != (b >> 32)) return b;
+    return (uint32_t)a > (uint32_t)b ? a : b;
+  }
+};
+
+__global__ void pacbio_cov_sweep_kernel(const unsigned long long* pkey, const unsigned long long* ikey, const unsigned long long* run_max,
+                                        const uint32_t* count, uint32_t cap, const int* walk_len, double step, int* bad) {
+  const uint32_t n_int = min(*count, cap), n_pos = 2 * n_int;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pos; j += gridDim.x * blockDim.x) {
+    const unsigned long long k = pkey[j];
+    const int walk = (int)(k >> 32), x = pb_key_pos(k);
+    bool has_next = false;
+    int next_x = 0;
+    if (j + 1 < n_pos) {
+      const unsigned long long kn = pkey[j + 1];
+      if ((int)(kn >> 32) == walk) {
+        has_next = true;
+        next_x = pb_key_pos(kn);
+      }
+    }
+    if (has_next && next_x == x) continue;   // not the last event of this position
+    // earliest-started interval of this walk that is still open after position x
+    uint32_t lo = 0, hi = n_int;             // first interval with key >= (walk, -inf)
+    const unsigned long long wk = (unsigned long long)(uint32_t)walk << 32;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ikey[mid] < wk) lo = mid + 1; else hi = mid; }
+    const uint32_t seg_lo = lo;
+    hi = n_int;                              // first interval of a later walk
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((ikey[mid] >> 32) <= (unsigned long long)(uint32_t)walk) lo = mid + 1; else hi = mid; }
+    const uint32_t seg_hi = lo;
+    uint32_t a = seg_lo, b = seg_hi;         // first interval whose running maximum of ends exceeds x
+    while (a < b) {
+      const uint32_t mid = (a + b) >> 1;
+      if ((int)((uint32_t)run_max[mid] ^ 0x80000000u) > x) b = mid; else a = mid + 1;
+    }
+    const int tl = walk_len[walk];
+    int good_start = tl - 250;
+    if (a < seg_hi && pb_key_pos(ikey[a]) <= x) good_start = (int)((double)pb_key_pos(ikey[a]) + step);
+    if (has_next) good_start = min(next_x, good_start);
+    good_start = min(good_start, tl - 250);
+    const int from = max(2500, x);
+    if (good_start > from) atomicAdd(bad, good_start - from);
+  }
+}
+
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                                    unsigned long long* flags, int n_flag_words, unsigned long long* timeline) {
@@ -1904,6 +2001,45 @@ cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long lon
   cudaError_t err = cub::DeviceRadixSort::SortKeys(temp, need, keys_in, keys_sorted, (int)n, 0, 64, st);
   if (err != cudaSuccess) return err;
   coverage_sweep_kernel<<<grid_for(n, 256, sm_count, 8), 256, 0, st>>>(keys_sorted, n, cs_begin, cs, step, min_from_start, bad);
+  return cudaGetLastError();
+}
+
+size_t pacbio_coverage_temp_bytes(uint32_t cap) {
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int*)nullptr,
+                                  (int*)nullptr, (int)cap);
+  cub::DeviceRadixSort::SortKeys(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)(2 * cap));
+  cub::DeviceScan::InclusiveScan(nullptr, c, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, PbSegMax(), (int)cap);
+  return std::max(a, std::max(b, c));
+}
+
+// ikey/iend/pkey hold 2 x their capacity (unsorted half, sorted half); unused slots are padded with all-ones keys, which
+// sort behind every real (walk, position). bad is one int.
+cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* packed, unsigned long long* run_max, void* temp,
+                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st) {
+  const uint32_t cap = C.cap;
+  cudaError_t err = cudaMemsetAsync(C.ikey, 0xff, (size_t)cap * 2 * 8, st);
+  if (err == cudaSuccess) err = cudaMemsetAsync(C.pkey, 0xff, (size_t)cap * 4 * 8, st);
+  if (err == cudaSuccess) err = cudaMemsetAsync(C.count, 0, 4, st);
+  if (err == cudaSuccess) err = cudaMemsetAsync(bad, 0, 4, st);
+  if (err != cudaSuccess) return err;
+  pacbio_cov_emit_kernel<<<grid_for(cap, 256, sm_count, 8), 256, 0, st>>>(C);
+  unsigned long long* ikey_sorted = C.ikey + cap;
+  int* iend_sorted = C.iend + cap;
+  unsigned long long* pkey_sorted = C.pkey + 2 * (size_t)cap;
+  size_t need = temp_bytes;
+  err = cub::DeviceRadixSort::SortPairs(temp, need, (const unsigned long long*)C.ikey, ikey_sorted, (const int*)C.iend, iend_sorted,
+                                        (int)cap, 0, 64, st);
+  if (err != cudaSuccess) return err;
+  pacbio_cov_pack_kernel<<<(cap + 255) / 256, 256, 0, st>>>(ikey_sorted, iend_sorted, packed, cap);
+  need = temp_bytes;
+  err = cub::DeviceScan::InclusiveScan(temp, need, (const unsigned long long*)packed, run_max, PbSegMax(), (int)cap, st);
+  if (err != cudaSuccess) return err;
+  need = temp_bytes;
+  err = cub::DeviceRadixSort::SortKeys(temp, need, (const unsigned long long*)C.pkey, pkey_sorted, (int)(2 * cap), 0, 64, st);
+  if (err != cudaSuccess) return err;
+  pacbio_cov_sweep_kernel<<<grid_for(2 * (size_t)cap, 256, sm_count, 8), 256, 0, st>>>(pkey_sorted, ikey_sorted, run_max, C.count, cap,
+                                                                                       walk_len, step, bad);
   return cudaGetLastError();
 }
 

@@ -64,6 +64,10 @@ size_t coverage_sort_temp_bytes(unsigned n);
 cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long long* keys_sorted, unsigned n, void* temp,
                             size_t temp_bytes, const int* cs_begin, const int* cs, double step, double min_from_start, int* bad,
                             int sm_count, cudaStream_t st);
+// PacBio coverage penalty of one set: emit intervals, sort by (walk, start), running max of ends, sort positions, sweep.
+size_t pacbio_coverage_temp_bytes(uint32_t cap);
+cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* packed, unsigned long long* run_max, void* temp,
+                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st);
 size_t csr_temp_bytes(int n_reads);
 
 }  // namespace gaml

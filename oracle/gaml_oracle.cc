@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -318,14 +319,26 @@ double ScorePacbio(const Graph& g, ReadSetData& rs, const std::vector<Walk>& wal
   std::vector<double>& lp = rs.last;
   lp.assign(rs.n_reads, -std::numeric_limits<double>::infinity());
   int tl = 0;
+  int bad_bases = 0;
+  // GetMinReadProb (graph.h:478-481): mismatch^(len/4) * match^(3 len/4) as a logdouble
+  const double lmm = log(rs.mismatch), lm = log(rs.match);
   for (Walk w : walks) {
     for (int& x : w)
       if (x >= 0) x = g.nmap[x];  // graph.h:268-273
     size_t n = w.size();
     std::vector<int> begin(n), end(n);
     int off = 0;
+    // coverage events of this walk (graph.cc:3197-3223): an artificial interval, one interval per node, ...
+    std::vector<std::pair<int, int>> events;
+    events.push_back({-1000, 1});
+    events.push_back({2000, -3000});
     for (size_t i = 0; i < n; i++) {
       begin[i] = off;
+      if (w[i] >= 0) {
+        int cl = g.node_len[w[i]];
+        events.push_back({off, 1});
+        events.push_back({off + cl, -cl});
+      }
       off += w[i] < 0 ? -w[i] : g.node_len[w[i]];
       end[i] = off;
     }
@@ -336,9 +349,29 @@ double ScorePacbio(const Graph& g, ReadSetData& rs, const std::vector<Walk>& wal
         key.push_back(w[j]);
         auto it = rs.lcache.find(key);
         if (it != rs.lcache.end())
-          for (const LongRec& r : it->second) LseAdd(lp[r.read], r.logprob);  // no de-dup, graph.cc:2487-2500
+          for (const LongRec& r : it->second) {
+            LseAdd(lp[r.read], r.logprob);  // no de-dup, graph.cc:2487-2500
+            // ... and one per alignment at least as probable as the read's minimum (graph.cc:3213-3221)
+            const double min_lp = lmm * (rs.len[0][r.read] * 0.25) + lm * (rs.len[0][r.read] * 0.75);
+            if (r.logprob < min_lp) continue;
+            events.push_back({begin[i] + r.pos, 1});
+            events.push_back({begin[i] + r.pos_end, (begin[i] + r.pos) - (begin[i] + r.pos_end)});
+          }
         if ((end[j] - begin[i]) - (end[i] - begin[i]) > rs.max_len[0]) break;  // graph.cc:2450
       }
+    }
+    // the sweep (graph.cc:3225-3250): stretches that begin further than exp_cov_move after the earliest open interval
+    std::sort(events.begin(), events.end());
+    std::multiset<int> inters;
+    const int wl = off;
+    for (size_t j = 0; j < events.size(); j++) {
+      if (events[j].second == 1) inters.insert(events[j].first);
+      else inters.erase(inters.find(events[j].first + events[j].second));
+      int good_start = wl - 250;
+      if (!inters.empty()) good_start = (int)(*inters.begin() + rs.step);
+      if (j + 1 < events.size()) good_start = std::min(events[j + 1].first, good_start);
+      good_start = std::min(good_start, wl - 250);
+      if (good_start > std::max(2500, events[j].first)) bad_bases += good_start - std::max(2500, events[j].first);
     }
   }
   *total_len = tl;
@@ -357,7 +390,7 @@ double ScorePacbio(const Graph& g, ReadSetData& rs, const std::vector<Walk>& wal
     acc += v;
     cnt++;
   }
-  return acc / cnt - log((double)(2 * den));
+  return (acc / cnt - log((double)(2 * den))) - bad_bases * rs.penalty;   // graph.cc:3259-3260
 }
 
 // ---- ProbCalculator::CalcProb (prob_calculator.h:63-109) -----------------------------------

@@ -157,7 +157,21 @@ def golden_cases():
         "synth_paired": synth.paired_workload(10, 1800, 900, n_evals=24, seed=22),
         "synth_mixed": synth.mixed_workload(8, 5000, 600, 80, n_single=300, n_evals=12, seed=23, pacbio_len=4000),
         "synth_paired_penalty": _with_penalty(synth.paired_workload(12, 2500, 350, n_evals=30, seed=24)),
+        "synth_pacbio_penalty": _with_pacbio_penalty(synth.mixed_workload(8, 5000, 300, 60, n_evals=10, seed=25, pacbio_len=4000)),
     }
+
+
+def _with_pacbio_penalty(wl: Workload, step: float = 700.0) -> Workload:
+    """PacBio coverage penalty (graph.cc:3197-3250): sparse long reads, a penalty step below the typical gap, and
+    match / mismatch probabilities that put GetMinReadProb (graph.h:478) inside the records' logprob range so that
+    some alignments do not count as coverage."""
+    pb = wl.sets[-1]
+    pb.penalty_constant = 0.0004
+    pb.step = step
+    pb.match_prob = 0.9
+    # min read prob at the mean read length = -2000, the middle of the synthetic logprob range [-2500, -1500]
+    pb.mismatch_prob = float(np.exp((-2000.0 / float(np.mean(pb.read_len[0])) - 0.75 * np.log(0.9)) / 0.25))
+    return wl
 
 
 def _with_penalty(wl: Workload) -> Workload:
@@ -175,4 +189,6 @@ def seeded_cases():
         out[f"paired_s{seed}"] = synth.paired_workload(14, 2500, 5000, n_evals=40, seed=seed)
         out[f"mixed_s{seed}"] = synth.mixed_workload(10, 6000, 3000, 300, n_single=1000, n_evals=20, seed=seed,
                                                      pacbio_len=5000)
+        out[f"pacbio_penalty_s{seed}"] = _with_pacbio_penalty(
+            synth.mixed_workload(10, 6000, 1500, 120 + 60 * seed, n_evals=14, seed=30 + seed, pacbio_len=5000), step=500.0 + 400.0 * seed)
     return out

@@ -83,9 +83,9 @@ def test_error_behaviour():
     with pytest.raises(api.GamlError, match="read_id"):
         pc.cache_insert(0, 0, (6, 4), bad)
     pb = workload.read_workload(os.path.join(GOLDEN, "hand_pacbio.wl")).sets[0]
-    pb.penalty_constant = 0.1          # the PacBio coverage sweep is the one penalty not on the device yet
+    pb.penalty_constant = 0.1          # a coverage penalty needs all reads of a walk: refused on a read-id shard
     with pytest.raises(api.GamlError, match="penalty_constant"):
-        pc.add_readset(pb)
+        pc.add_readset(pb, shard=(0, max(pb.n_reads // 2, 1)))
     # the context is still usable after rejected calls
     prob, _, _ = pc.calc_prob(wl.evals[0])
     ref = workload.read_results(os.path.join(GOLDEN, "hand_paired.ref.res"))
@@ -392,6 +392,23 @@ def test_paired_coverage_penalty_matches_oracle(seed, oracle):
     ref = oracle(wl, f"pen{seed}")
     assert any(a.score != b.score for a, b in zip(plain, ref))
     check_against(wl, ref)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_pacbio_coverage_penalty_matches_oracle(seed, oracle):
+    """penalty_constant != 0 on a PacBio set (graph.cc:3197-3250): intervals of nodes and of the alignments above the
+    read's minimum probability, earliest-open-start sweep per walk. bad_bases is an integer, so the penalised total must
+    agree with the oracle like the unpenalised one; the same trajectory without penalty must differ."""
+    wl = seeded_cases()[f"pacbio_penalty_s{seed}"]
+    ref = oracle(wl, f"pbpen{seed}", dump=True)
+    check_against(wl, ref)
+    pen = wl.sets[-1].penalty_constant
+    wl.sets[-1].penalty_constant = 0.0
+    pc = api.ProbCalculator.from_workload(wl)
+    plain = [pc.calc_prob(w)[0] for w in wl.evals]
+    pc.close()
+    wl.sets[-1].penalty_constant = pen
+    assert any(abs(a - r.score) > 1e-6 for a, r in zip(plain, ref))
 
 
 def test_single_set_penalty_is_a_no_op_like_the_reference(oracle):
