@@ -55,7 +55,8 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_eval_prepare", "gaml_eval_launch", "gaml_eval_finish", "gaml_reset_state", "gaml_read_values",
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
            "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline", "gaml_set_result_exchange",
-           "gaml_eval_finish_gathered", "gaml_calc_prob_gathered", "gaml_cache_save", "gaml_cache_load"]
+           "gaml_eval_finish_gathered", "gaml_calc_prob_gathered", "gaml_cache_save", "gaml_cache_load",
+           "gaml_pacbio_alignment_logprob"]
 
 _lib = None
 
@@ -97,6 +98,9 @@ def load_library() -> C.CDLL:
     lib.gaml_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.gaml_set_profiling.argtypes = [vp, C.c_int32]
     lib.gaml_read_timeline.argtypes = [vp, C.POINTER(C.c_double), C.c_int32]
+    u8p, i64p_, i32p_ = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    lib.gaml_pacbio_alignment_logprob.argtypes = [vp, C.c_double, C.c_double, C.c_int32, C.c_int64, u8p, i64p_, u8p, i64p_, i32p_,
+                                                  i32p_, u8p, i64p_, C.POINTER(C.c_double)]
     lib.gaml_cache_save.argtypes = [vp, C.c_int, C.c_char_p]
     lib.gaml_cache_load.argtypes = [vp, C.c_int, C.c_char_p]
     lib.gaml_set_result_exchange.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
@@ -397,6 +401,25 @@ class ProbCalculator:
         if rc < 0:
             self._check(rc)
         return g.reshape(self._exch_world, -1), tl.value
+
+    def pacbio_alignment_logprob(self, alns, match_prob: float, mismatch_prob: float, band: int = 2) -> np.ndarray:
+        """gaml_pacbio_alignment_logprob over a list of alnprob.Alignment."""
+        from . import alnprob
+        s1, s1_off, s2, s2_off, posstart, op_len, op_chr, op_off = alnprob.flatten(alns)
+        out = np.zeros(len(alns), dtype=np.float64)
+        u8p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+        def u8(a):
+            a = np.ascontiguousarray(a if len(a) else np.zeros(1, np.uint8))
+            return a, a.ctypes.data_as(u8p)
+        k1, p1 = u8(s1)
+        k2, p2 = u8(s2)
+        k3, p3 = u8(op_chr)
+        ol = np.ascontiguousarray(op_len if len(op_len) else np.zeros(1, np.int32))
+        self._check(self.lib.gaml_pacbio_alignment_logprob(self.h, match_prob, mismatch_prob, band, len(alns), p1,
+                                                           s1_off.ctypes.data_as(i64p), p2, s2_off.ctypes.data_as(i64p),
+                                                           _p32(posstart if len(posstart) else np.zeros(1, np.int32)), _p32(ol), p3,
+                                                           op_off.ctypes.data_as(i64p), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def cache_save(self, set_id: int, path: str) -> None:
         self._check(self.lib.gaml_cache_save(self.h, set_id, path.encode()))

@@ -168,6 +168,24 @@ struct PbCovParams {
   uint32_t* error_flag;
 };
 
+// ---- PacBio alignment probability (graph.cc:2175-2297) --------------------------------------------------------------
+struct AlnMeta {
+  int64_t s1_off, s2_off, range_off, scratch_off;
+  int32_t s1_len, s2_len, posstart, first_row, n_rows, width;   // width = widest row (scratch strip: 2 x width doubles)
+  int32_t pad[2];
+};
+struct AlnProbParams {
+  const AlnMeta* meta;
+  long long n;
+  const unsigned char* s1;
+  const unsigned char* s2;
+  const int32_t* lo;        // per alignment and row: first / last column of the row's cells (lo > hi: none)
+  const int32_t* hi;
+  double* scratch;
+  double log_match, log_mismatch;
+  double* out;
+};
+
 // ---- batched candidate evaluation (gaml_calc_prob_batch, BASELINE config 5) ------------------------------
 struct BatchCand {             // one candidate move, one paired read set
   int32_t key_begin[2];        // this candidate's slice of the batch key/slot arrays, per mate (keys sorted)

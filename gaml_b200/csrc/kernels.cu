@@ -1581,6 +1581,56 @@ __global__ void pacbio_cov_sweep_kernel(const unsigned long long* pkey, const un
   }
 }
 
+// ---- PacBio alignment probability (PacbioReadSet::AligmentProbability, graph.cc:2175-2297) -----------------------
+// Forward DP in log space over the cells around an alignment's CIGAR path: cell(row, col) = the probability of
+// generating the read's first `col` bases from the walk's bases up to `row`, summed over the three predecessors
+// (diagonal: match/mismatch, up: walk base against a gap, left: gap against a read base); the result is the sum of the
+// cells in the read's last column. The cells of a row are one column range [lo, hi] (prepared on the host from the
+// CIGAR and the band). One thread per alignment, rows and columns in the reference's order — the additions of the
+// log-sum-exp chain are not associative, so the order is part of the result — with the previous and the current row in
+// a per-thread scratch strip. Compute bound (three exp + log1p per cell); the strips stay in L1/L2.
+__global__ void __launch_bounds__(128) pacbio_alnprob_kernel(const AlnProbParams A) {
+  const double ninf = -INFINITY;
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < A.n; a += (long long)gridDim.x * blockDim.x) {
+    const AlnMeta m = A.meta[a];
+    const unsigned char* s1 = A.s1 + m.s1_off;
+    const unsigned char* s2 = A.s2 + m.s2_off;
+    const int* lo = A.lo + m.range_off;
+    const int* hi = A.hi + m.range_off;
+    double* prev = A.scratch + m.scratch_off;
+    double* cur = prev + m.width;
+    double ret = ninf;
+    int plo = 1, phi = 0;   // previous row's range (empty)
+    for (int i = 0; i < m.n_rows; i++) {
+      const int l = lo[i], h = hi[i];
+      const int p1 = m.first_row + i + m.posstart - 1;
+      const bool row_ok = p1 >= 0 && p1 < m.s1_len;
+      const unsigned char c1 = row_ok ? s1[p1] : 0;
+      const double up_lp = c1 == '\n' ? ninf : A.log_mismatch;   // MatchProbability(s1[.], '-'), graph.h:555-563
+      double left = ninf;   // value of (row, col - 1); outside the row's range: no such cell
+      bool have_left = false;
+      for (int c = l; c <= h; c++) {
+        double v = c == 0 ? 0.0 : ninf;   // column 0: probability 1, graph.cc:2240-2244
+        if (c != 0 && c - 1 >= 0 && c - 1 < m.s2_len && row_ok) {
+          const unsigned char c2 = s2[c - 1];
+          if (c - 1 >= plo && c - 1 <= phi)
+            v = lse_add(v, __dadd_rn(prev[c - 1 - plo], (c1 == '\n' || c2 == '\n') ? ninf : (c1 != c2 ? A.log_mismatch : A.log_match)));
+          if (c >= plo && c <= phi) v = lse_add(v, __dadd_rn(prev[c - plo], up_lp));
+          if (have_left) v = lse_add(v, __dadd_rn(left, c2 == '\n' ? ninf : A.log_mismatch));
+          if (c == m.s2_len) ret = lse_add(ret, v);
+        }
+        cur[c - l] = v;
+        left = v;
+        have_left = true;
+      }
+      double* t = prev; prev = cur; cur = t;
+      plo = l;
+      phi = h;
+    }
+    A.out[a] = ret;
+  }
+}
+
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
 __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
                                    unsigned long long* flags, int n_flag_words, unsigned long long* timeline) {
@@ -2002,6 +2052,11 @@ cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long lon
   if (err != cudaSuccess) return err;
   coverage_sweep_kernel<<<grid_for(n, 256, sm_count, 8), 256, 0, st>>>(keys_sorted, n, cs_begin, cs, step, min_from_start, bad);
   return cudaGetLastError();
+}
+
+void launch_pacbio_alnprob(const AlnProbParams& A, int sm_count, cudaStream_t st) {
+  const int grid = grid_for((size_t)A.n, 128, sm_count, 8);
+  pacbio_alnprob_kernel<<<grid, 128, 0, st>>>(A);
 }
 
 size_t pacbio_coverage_temp_bytes(uint32_t cap) {

@@ -68,6 +68,8 @@ cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long lon
 size_t pacbio_coverage_temp_bytes(uint32_t cap);
 cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* packed, unsigned long long* run_max, void* temp,
                                    size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st);
+// PacBio alignment probability: one thread per alignment over host-prepared row ranges.
+void launch_pacbio_alnprob(const AlnProbParams& A, int sm_count, cudaStream_t st);
 size_t csr_temp_bytes(int n_reads);
 
 }  // namespace gaml

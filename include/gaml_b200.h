@@ -140,6 +140,18 @@ int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, in
 /* Uploads staged inserts and rebuilds the per-read CSR on the device (also done lazily by CalcProb). */
 int gaml_cache_commit(gaml_ctx* ctx);
 
+/* PacBio alignment probability on the device (PacbioReadSet::AligmentProbability, graph.cc:2175-2297; the value
+ * ProcessBlasrOutput stores as PacbioAligment::prob, graph.cc:2756, 2902 — the dominant cost while a PacBio cache is
+ * cold): the forward probability, in log space, of read s2 given walk sequence s1 over the band around the aligner's
+ * CIGAR path. Alignment a uses s1[s1_off[a] .. s1_off[a+1]) (the walk's sequence or a window of it; '\n' separates
+ * contigs), s2[s2_off[a] .. s2_off[a+1]), posstart[a] (offset of the alignment in its s1) and the CIGAR operations
+ * op_off[a] .. op_off[a+1) as (op_len, op_chr in "MID"). match_prob / mismatch_prob are the set's
+ * (PacbioReadSet::match_prob_ / mismatch_prob_, graph.h:576-577); band is 2 in the reference. logprob_out[a] = logval. */
+int gaml_pacbio_alignment_logprob(gaml_ctx* ctx, double match_prob, double mismatch_prob, int32_t band, int64_t n,
+                                  const uint8_t* s1, const int64_t* s1_off, const uint8_t* s2, const int64_t* s2_off,
+                                  const int32_t* posstart, const int32_t* op_len, const uint8_t* op_chr, const int64_t* op_off,
+                                  double* logprob_out);
+
 /* Flat on-disk form of one read set's cache (replaces ReadSet::SaveAligments / LoadAligments, graph.cc:1035-1100, whose
  * Boost archive the reference has switched off): keys with their metadata, then the key-major record arena exactly as
  * the device holds it. gaml_cache_load wants the read set created (gaml_add_readset with the same kind, read count and

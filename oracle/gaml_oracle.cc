@@ -424,10 +424,86 @@ struct Calculator {
 };
 
 // ---- file IO -------------------------------------------------------------------------------
+// ---- PacBio alignment probability (PacbioReadSet::AligmentProbability, graph.cc:2175-2297) -----------------------
+// Forward DP in log space over the cells around an alignment's CIGAR path. The reference collects the cells as a list
+// of (row, column) pairs and "uniquifies" it (graph.cc:2150-2173): per row, every column between the smallest and the
+// largest one listed. Here a row's cells are kept as that [lo, hi] range from the start, which is the same set.
+struct RowRanges {
+  int first_row = 0;
+  std::vector<int> lo, hi;   // per row from first_row; lo > hi = the row has no cell
+  void Cover(int row, int c_lo, int c_hi) {
+    if (lo.empty()) { first_row = row; lo.push_back(c_lo); hi.push_back(c_hi); return; }
+    while (row < first_row) { lo.insert(lo.begin(), 1000000); hi.insert(hi.begin(), -1000000); first_row--; }
+    while (row >= first_row + (int)lo.size()) { lo.push_back(1000000); hi.push_back(-1000000); }
+    int i = row - first_row;
+    lo[i] = std::min(lo[i], c_lo);
+    hi[i] = std::max(hi[i], c_hi);
+  }
+};
+
+double AlignmentLogProb(const std::string& s1, const std::string& s2, int posstart, const std::vector<std::pair<int, int>>& ops,
+                        int band, double match, double mismatch) {
+  std::string cigar;   // ExpandCigar, graph.cc:2127-2134
+  for (auto& o : ops) cigar.append((size_t)o.first, (char)o.second);
+  int bl = 0, el = 0;  // GetCigarEnds, graph.cc:2136-2149: leading / trailing insertion runs
+  for (size_t i = 0; i < cigar.size(); i++)
+    if (cigar[i] != 'I') { bl = (int)i; break; }
+  for (int i = (int)cigar.size() - 1; i >= 0; i--)
+    if (cigar[i] != 'I') { el = (int)cigar.size() - i; break; }
+  bl = std::min(bl, 200);
+  el = std::min(el, 200);
+  RowRanges path;
+  path.Cover(0, 0, 0);
+  if (bl > 0)
+    for (int i = -bl; i < 3; i++) path.Cover(i, 0, bl - 1);   // graph.cc:2188-2192
+  int row = 0, col = 0;
+  for (char c : cigar) {   // graph.cc:2193-2203
+    if (c == 'M') { row++; col++; }
+    else if (c == 'I') col++;
+    else if (c == 'D') row++;
+    path.Cover(row, col, col);
+  }
+  for (int i = row; i < row + el; i++) path.Cover(i, col - el, col);   // graph.cc:2204-2208
+  RowRanges cells;   // every listed cell widened by the band in both directions, graph.cc:2210-2222
+  for (size_t i = 0; i < path.lo.size(); i++) {
+    if (path.lo[i] > path.hi[i]) continue;
+    for (int d = -band; d <= band; d++) cells.Cover(path.first_row + (int)i + d, path.lo[i] - band, path.hi[i] + band);
+  }
+  const double lmatch = log(match), lmismatch = log(mismatch);
+  auto match_lp = [&](char a, char b) {   // MatchProbability, graph.h:555-563 ('\n' separates contigs: probability 0)
+    if (a == '\n' || b == '\n') return -std::numeric_limits<double>::infinity();
+    return a != b ? lmismatch : lmatch;
+  };
+  const int n_rows = (int)cells.lo.size();
+  std::vector<std::vector<double>> res(n_rows);
+  for (int i = 0; i < n_rows; i++)
+    if (cells.lo[i] <= cells.hi[i]) res[i].assign((size_t)(cells.hi[i] - cells.lo[i] + 1), -std::numeric_limits<double>::infinity());
+  auto inside = [&](int r, int c) { return r >= 0 && c - cells.lo[r] >= 0 && c - cells.lo[r] < (int)res[r].size(); };
+  double ret = log(0.0);   // logdouble ret = 0
+  for (int i = 0; i < n_rows; i++)
+    for (int c = cells.lo[i]; c <= cells.hi[i]; c++)
+      if (c == 0) res[i][0 - cells.lo[i]] = 0.0;   // probability 1, graph.cc:2240-2244
+  for (int i = 0; i < n_rows; i++) {
+    const int r_abs = cells.first_row + i;
+    for (int c = cells.lo[i]; c <= cells.hi[i]; c++) {
+      if (c == 0) continue;
+      if (c - 1 < 0 || c - 1 >= (int)s2.size()) continue;
+      const int p1 = r_abs + posstart - 1;
+      if (p1 < 0 || p1 >= (int)s1.size()) continue;
+      double& cell = res[i][c - cells.lo[i]];
+      if (inside(i - 1, c - 1)) LseAdd(cell, res[i - 1][c - 1 - cells.lo[i - 1]] + match_lp(s1[p1], s2[c - 1]));
+      if (inside(i - 1, c)) LseAdd(cell, res[i - 1][c - cells.lo[i - 1]] + match_lp(s1[p1], '-'));
+      if (inside(i, c - 1)) LseAdd(cell, res[i][c - 1 - cells.lo[i]] + match_lp('-', s2[c - 1]));
+      if (c == (int)s2.size()) LseAdd(ret, cell);
+    }
+  }
+  return ret;
+}
+
 struct Reader {
   std::vector<char> buf;
   size_t off = 8;
-  explicit Reader(const char* path) {
+  explicit Reader(const char* path, const char* magic = "GAMLWL1\0") {
     FILE* f = fopen(path, "rb");
     if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
     fseek(f, 0, SEEK_END);
@@ -436,7 +512,7 @@ struct Reader {
     buf.resize(n);
     if (fread(buf.data(), 1, n, f) != (size_t)n) exit(2);
     fclose(f);
-    if (n < 8 || memcmp(buf.data(), "GAMLWL1\0", 8) != 0) { fprintf(stderr, "bad magic\n"); exit(2); }
+    if (n < 8 || memcmp(buf.data(), magic, 8) != 0) { fprintf(stderr, "bad magic\n"); exit(2); }
   }
   int i32() { int v; memcpy(&v, &buf[off], 4); off += 4; return v; }
   double f64() { double v; memcpy(&v, &buf[off], 8); off += 8; return v; }
@@ -445,9 +521,41 @@ struct Reader {
 
 }  // namespace
 
+// --alnprob mode: same file formats as oracle/ref_harness.cc's
+int AlignProbMode(const char* in_path, const char* out_path) {
+  Reader rd(in_path, "GAMLAP1\0");
+  const double match = rd.f64(), mismatch = rd.f64();
+  const int band = rd.i32(), n = rd.i32();
+  std::vector<double> out(n);
+  double secs = 0;
+  for (int a = 0; a < n; a++) {
+    const int posstart = rd.i32();
+    const int n1 = rd.i32();
+    std::string s1(&rd.buf[rd.off], &rd.buf[rd.off] + n1);
+    rd.off += n1;
+    const int n2 = rd.i32();
+    std::string s2(&rd.buf[rd.off], &rd.buf[rd.off] + n2);
+    rd.off += n2;
+    const int n_ops = rd.i32();
+    std::vector<std::pair<int, int>> ops(n_ops);
+    for (auto& o : ops) { o.first = rd.i32(); o.second = rd.i32(); }
+    auto t0 = std::chrono::steady_clock::now();
+    out[a] = AlignmentLogProb(s1, s2, posstart, ops, band, match, mismatch);
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  FILE* f = fopen(out_path, "wb");
+  if (!f) return 2;
+  fwrite(out.data(), 8, out.size(), f);
+  fwrite(&secs, 8, 1, f);
+  fclose(f);
+  fprintf(stderr, "gaml_oracle --alnprob: %d alignments, %.6f s\n", n, secs);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && strcmp(argv[1], "--alnprob") == 0) return AlignProbMode(argv[2], argv[3]);
   if (argc < 3) {
-    fprintf(stderr, "usage: %s <workload> <results> [dump] [repeat]\n", argv[0]);
+    fprintf(stderr, "usage: %s <workload> <results> [dump] [repeat]\n       %s --alnprob <alignments> <logvals>\n", argv[0], argv[0]);
     return 2;
   }
   bool dump = argc > 3 && atoi(argv[3]) != 0;

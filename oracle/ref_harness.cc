@@ -11,6 +11,7 @@
 //   4. writes a GAMLRS1 result file (score, total_len, floored counts, optional per-read values).
 //
 // usage: ref_harness <workload> <results> [dump=0|1] [repeat=1]
+//        ref_harness --alnprob <alignments> <logvals>     (PacbioReadSet::AligmentProbability on injected alignments)
 #include <algorithm>
 #include <cassert>
 #include <chrono>
@@ -79,9 +80,49 @@ void FillReadSet(ReadSet* rs, int n_reads, const std::vector<int>& lens) {
 
 }  // namespace
 
+// Second mode: the reference's PacBio alignment probability (PacbioReadSet::AligmentProbability, graph.cc:2175-2297)
+// on injected alignments. Input (GAMLAP1): f64 match, f64 mismatch, i32 band, i32 n; per alignment i32 posstart,
+// i32 |s1|, s1, i32 |s2|, s2, i32 n_ops, n_ops x (i32 length, i32 op character). Output: n x f64 logval, then seconds.
+int AlignProbMode(const char* in_path, const char* out_path) {
+  Reader rd(in_path);
+  if (memcmp(rd.buf.data(), "GAMLAP1\0", 8) != 0) { fprintf(stderr, "bad magic\n"); return 2; }
+  rd.off = 8;
+  const double match = rd.f64(), mismatch = rd.f64();
+  const int band = rd.i32(), n = rd.i32();
+  PacbioReadSet pb("/nonexistent/pbap", "", match, mismatch);
+  std::vector<double> out(n);
+  double secs = 0;
+  for (int a = 0; a < n; a++) {
+    PacbioReadSet::PacbioAligmentData ad;
+    ad.posstart = rd.i32();
+    const int n1 = rd.i32();
+    std::string s1(&rd.buf[rd.off], &rd.buf[rd.off] + n1);
+    rd.off += n1;
+    const int n2 = rd.i32();
+    std::string s2(&rd.buf[rd.off], &rd.buf[rd.off] + n2);
+    rd.off += n2;
+    const int n_ops = rd.i32();
+    for (int k = 0; k < n_ops; k++) {
+      const int len = rd.i32(), op = rd.i32();
+      ad.cigar.push_back(make_pair(len, (char)op));
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    out[a] = pb.AligmentProbability(s1, s2, ad, band).logval;
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  FILE* f = fopen(out_path, "wb");
+  if (!f) { fprintf(stderr, "cannot write %s\n", out_path); return 2; }
+  fwrite(out.data(), 8, out.size(), f);
+  fwrite(&secs, 8, 1, f);
+  fclose(f);
+  fprintf(stderr, "ref_harness --alnprob: %d alignments, %.6f s in AligmentProbability\n", n, secs);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 4 && strcmp(argv[1], "--alnprob") == 0) return AlignProbMode(argv[2], argv[3]);
   if (argc < 3) {
-    fprintf(stderr, "usage: %s <workload> <results> [dump] [repeat]\n", argv[0]);
+    fprintf(stderr, "usage: %s <workload> <results> [dump] [repeat]\n       %s --alnprob <alignments> <logvals>\n", argv[0], argv[0]);
     return 2;
   }
   const bool dump = argc > 3 && atoi(argv[3]) != 0;

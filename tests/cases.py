@@ -192,3 +192,24 @@ def seeded_cases():
         out[f"pacbio_penalty_s{seed}"] = _with_pacbio_penalty(
             synth.mixed_workload(10, 6000, 1500, 120 + 60 * seed, n_evals=14, seed=30 + seed, pacbio_len=5000), step=500.0 + 400.0 * seed)
     return out
+
+
+def alnprob_cases():
+    """name -> (alignments, match, mismatch, band) for the PacBio alignment probability (graph.cc:2175-2297): golden
+    fixtures small enough to commit."""
+    from gaml_b200 import alnprob
+    return {
+        "alnprob_band2": (alnprob.make_alignments(24, 260, seed=41), 0.85, 0.05, 2),
+        "alnprob_separators_band1": (alnprob.make_alignments(16, 180, seed=42, separators=True), 0.8, 0.066, 1),
+        "alnprob_band3": (alnprob.make_alignments(10, 220, seed=43, clip=30), 0.9, 0.03, 3),
+    }
+
+
+def alnprob_seeded():
+    """Larger cases, oracle vs reference here and CUDA vs oracle on the GPU box."""
+    from gaml_b200 import alnprob
+    return {
+        "long_band2": (alnprob.make_alignments(40, 2500, seed=51), 0.85, 0.05, 2),
+        "many_short": (alnprob.make_alignments(600, 150, seed=52, separators=True), 0.85, 0.05, 2),
+        "clipped": (alnprob.make_alignments(30, 400, seed=53, clip=260), 0.85, 0.05, 2),
+    }

@@ -33,6 +33,22 @@ def main():
         res = workload.read_results(rp)
         print(f"{name}: {len(res)} evals, {os.path.getsize(wp)} + {os.path.getsize(rp)} bytes, "
               f"scores {res[0].score!r} .. {res[-1].score!r}")
+    alnprob_golden(harness)
+
+
+def alnprob_golden(harness):
+    """PacBio alignment probabilities (PacbioReadSet::AligmentProbability) of synthetic alignments, from the reference."""
+    from cases import alnprob_cases
+    from gaml_b200 import alnprob
+    for name, (alns, match, mismatch, band) in alnprob_cases().items():
+        ip = os.path.join(HERE, name + ".ap")
+        rp = os.path.join(HERE, name + ".ref.lp")
+        alnprob.write_alignments(ip, alns, match, mismatch, band)
+        subprocess.run([harness, "--alnprob", ip, rp], check=True)
+        vals, _ = alnprob.read_logvals(rp, len(alns))
+        with open(rp, "wb") as f:          # keep the values only (the harness appends its run time)
+            f.write(vals.astype("<f8").tobytes())
+        print(f"{name}: {len(alns)} alignments, {os.path.getsize(ip)} + {os.path.getsize(rp)} bytes, logvals {vals[:3]}")
 
 
 if __name__ == "__main__":

@@ -64,3 +64,41 @@ def test_golden_cover_edge_cases():
     assert (pb.normalize_map != np.arange(len(pb.normalize_map))).any()
     rp = workload.read_results(os.path.join(GOLDEN, "hand_pacbio.ref.res"))
     assert np.isneginf(rp[0].per_read[0]).any()             # reads with no alignment: -inf LSE identity
+
+
+# ---- PacBio alignment probability (PacbioReadSet::AligmentProbability, graph.cc:2175-2297) -------------------------
+def _run_alnprob(binary, ap_path, n, tmp_path, tag):
+    import subprocess
+    from gaml_b200 import alnprob
+    out = os.path.join(str(tmp_path), tag + ".lp")
+    subprocess.run([binary, "--alnprob", ap_path, out], check=True, stderr=subprocess.DEVNULL)
+    return alnprob.read_logvals(out, n)[0]
+
+
+ALNPROB_GOLDEN = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "alnprob_*.ap")))
+
+
+def test_alnprob_golden_present():
+    assert len(ALNPROB_GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("name", ALNPROB_GOLDEN)
+def test_oracle_alnprob_matches_reference_golden(name, tmp_path):
+    """The committed logvals came out of the reference's own AligmentProbability (ref_harness --alnprob)."""
+    ref = np.frombuffer(open(os.path.join(GOLDEN, name + ".ref.lp"), "rb").read(), dtype="<f8")
+    got = _run_alnprob(ORACLE_BIN, os.path.join(GOLDEN, name + ".ap"), len(ref), tmp_path, name)
+    assert np.array_equal(got, ref), np.nonzero(got != ref)[0][:5]
+    assert np.isinf(ref).sum() < len(ref)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HARNESS), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("name", ["long_band2", "many_short", "clipped"])
+def test_oracle_alnprob_matches_reference_live(name, tmp_path):
+    from cases import alnprob_seeded
+    from gaml_b200 import alnprob
+    alns, match, mismatch, band = alnprob_seeded()[name]
+    ap = os.path.join(str(tmp_path), name + ".ap")
+    alnprob.write_alignments(ap, alns, match, mismatch, band)
+    ref = _run_alnprob(REF_HARNESS, ap, len(alns), tmp_path, name + "_ref")
+    got = _run_alnprob(ORACLE_BIN, ap, len(alns), tmp_path, name + "_ora")
+    assert np.array_equal(got, ref)

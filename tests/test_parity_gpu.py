@@ -418,3 +418,67 @@ def test_single_set_penalty_is_a_no_op_like_the_reference(oracle):
     ref = oracle(wl, "s_pen")
     assert [r.score for r in plain] == [r.score for r in ref]      # graph.cc:1710-1733 never counts a gap
     check_against(wl, ref)
+
+
+# ---- PacBio alignment probability on the device --------------------------------------------------
+ALNPROB_GOLDEN = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "alnprob_*.ap")))
+
+
+def _read_ap(path):
+    """GAMLAP1 -> (alignments, match, mismatch, band)."""
+    import struct
+    from gaml_b200 import alnprob
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"GAMLAP1\0"
+    match, mismatch, band, n = struct.unpack_from("<ddii", raw, 8)
+    off = 8 + 24
+    alns = []
+    for _ in range(n):
+        posstart, n1 = struct.unpack_from("<ii", raw, off); off += 8
+        s1 = raw[off:off + n1]; off += n1
+        (n2,) = struct.unpack_from("<i", raw, off); off += 4
+        s2 = raw[off:off + n2]; off += n2
+        (k,) = struct.unpack_from("<i", raw, off); off += 4
+        cigar = []
+        for _ in range(k):
+            ln, op = struct.unpack_from("<ii", raw, off); off += 8
+            cigar.append((ln, chr(op)))
+        alns.append(alnprob.Alignment(s1, s2, posstart, cigar))
+    return alns, match, mismatch, band
+
+
+def _close_logvals(got, ref):
+    fin = np.isfinite(ref)
+    assert np.array_equal(fin, np.isfinite(got))
+    assert np.all(np.abs(got[fin] - ref[fin]) <= REL_READ * np.abs(ref[fin])), np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin]))
+
+
+@pytest.mark.parametrize("name", ALNPROB_GOLDEN)
+def test_cuda_alnprob_matches_reference_golden(name):
+    """gaml_pacbio_alignment_logprob against logvals written by the reference's own AligmentProbability: same cells, same
+    order of additions; only exp/log1p differ from glibc (<= 1e-12 relative on the log value, the per-read bar)."""
+    alns, match, mismatch, band = _read_ap(os.path.join(GOLDEN, name + ".ap"))
+    ref = np.frombuffer(open(os.path.join(GOLDEN, name + ".ref.lp"), "rb").read(), dtype="<f8")
+    pc = api.ProbCalculator([100], None)
+    got = pc.pacbio_alignment_logprob(alns, match, mismatch, band)
+    pc.close()
+    _close_logvals(got, ref)
+
+
+@pytest.mark.parametrize("name", ["long_band2", "many_short", "clipped"])
+def test_cuda_alnprob_matches_oracle_seeded(name, tmp_path):
+    from cases import alnprob_seeded
+    from gaml_b200 import alnprob
+    from conftest import ORACLE_BIN
+    alns, match, mismatch, band = alnprob_seeded()[name]
+    ap, lp = str(tmp_path / "a.ap"), str(tmp_path / "a.lp")
+    alnprob.write_alignments(ap, alns, match, mismatch, band)
+    subprocess.run([ORACLE_BIN, "--alnprob", ap, lp], check=True, stderr=subprocess.DEVNULL)
+    ref = alnprob.read_logvals(lp, len(alns))[0]
+    pc = api.ProbCalculator([100], None)
+    got = pc.pacbio_alignment_logprob(alns, match, mismatch, band)
+    assert len(pc.pacbio_alignment_logprob([], match, mismatch, band)) == 0
+    with pytest.raises(api.GamlError):
+        pc.pacbio_alignment_logprob([alnprob.Alignment(b"ACGT", b"ACGT", 1, [(4, "X")])], match, mismatch, band)
+    pc.close()
+    _close_logvals(got, ref)
