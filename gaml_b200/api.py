@@ -405,8 +405,13 @@ class ProbCalculator:
     def pacbio_alignment_logprob(self, alns, match_prob: float, mismatch_prob: float, band: int = 2) -> np.ndarray:
         """gaml_pacbio_alignment_logprob over a list of alnprob.Alignment."""
         from . import alnprob
-        s1, s1_off, s2, s2_off, posstart, op_len, op_chr, op_off = alnprob.flatten(alns)
-        out = np.zeros(len(alns), dtype=np.float64)
+        return self.pacbio_alignment_logprob_flat(alnprob.flatten(alns), match_prob, mismatch_prob, band)
+
+    def pacbio_alignment_logprob_flat(self, flat, match_prob: float, mismatch_prob: float, band: int = 2) -> np.ndarray:
+        """The same on arrays already in the C ABI's layout (alnprob.flatten)."""
+        s1, s1_off, s2, s2_off, posstart, op_len, op_chr, op_off = flat
+        n_alns = len(posstart)
+        out = np.zeros(n_alns, dtype=np.float64)
         u8p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
         def u8(a):
             a = np.ascontiguousarray(a if len(a) else np.zeros(1, np.uint8))
@@ -415,7 +420,7 @@ class ProbCalculator:
         k2, p2 = u8(s2)
         k3, p3 = u8(op_chr)
         ol = np.ascontiguousarray(op_len if len(op_len) else np.zeros(1, np.int32))
-        self._check(self.lib.gaml_pacbio_alignment_logprob(self.h, match_prob, mismatch_prob, band, len(alns), p1,
+        self._check(self.lib.gaml_pacbio_alignment_logprob(self.h, match_prob, mismatch_prob, band, n_alns, p1,
                                                            s1_off.ctypes.data_as(i64p), p2, s2_off.ctypes.data_as(i64p),
                                                            _p32(posstart if len(posstart) else np.zeros(1, np.int32)), _p32(ol), p3,
                                                            op_off.ctypes.data_as(i64p), out.ctypes.data_as(C.POINTER(C.c_double))))

@@ -170,20 +170,26 @@ struct PbCovParams {
 
 // ---- PacBio alignment probability (graph.cc:2175-2297) --------------------------------------------------------------
 struct AlnMeta {
-  int64_t s1_off, s2_off, range_off, scratch_off;
-  int32_t s1_len, s2_len, posstart, first_row, n_rows, width;   // width = widest row (scratch strip: 2 x width doubles)
-  int32_t pad[2];
+  int64_t s1_off, s2_off, op_off, scratch_off;
+  int32_t s1_len, s2_len, posstart, n_ops;
+  int32_t bl, el;              // leading / trailing insertion runs (GetCigarEnds, capped at 200)
+  int32_t row_end, col_end;    // where the CIGAR path ends
+  int32_t width;               // upper bound of a row's cells (scratch strip: 2 x width doubles)
+  int32_t pad[3];
 };
+constexpr int kAlnMaxBand = 8;
 struct AlnProbParams {
   const AlnMeta* meta;
   long long n;
   const unsigned char* s1;
   const unsigned char* s2;
-  const int32_t* lo;        // per alignment and row: first / last column of the row's cells (lo > hi: none)
-  const int32_t* hi;
+  const int32_t* op_len;    // CIGAR operations of all alignments
+  const unsigned char* op_chr;
+  int32_t band;
   double* scratch;
   double log_match, log_mismatch;
   double* out;
+  uint32_t* error_flag;     // bit 0: a row was wider than the host's bound (result NaN)
 };
 
 // ---- batched candidate evaluation (gaml_calc_prob_batch, BASELINE config 5) ------------------------------

@@ -242,6 +242,7 @@ struct gaml_ctx {
   size_t h_blob_cap = 0;
   DevBuf d_flags, d_scratch, d_csr_temp, d_logtab;
   DevBuf d_batch_blob, d_batch_acc, d_batch_out;   // gaml_calc_prob_batch
+  DevBuf d_aln[8];                                  // gaml_pacbio_alignment_logprob
   std::vector<double> h_batch_out;
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
@@ -2082,157 +2083,118 @@ int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
 }
 
 // ---- PacBio alignment probability ---------------------------------------------------------------
-// The cells the reference's DP visits (graph.cc:2177-2222): cell (0,0), a block in front of an alignment that starts
-// with insertions, the CIGAR path, a block behind one that ends with insertions — each row then holds every column
-// between its smallest and largest listed one (Uniquify, graph.cc:2150-2173) — and all of that widened by the band in
-// both directions. Returned as one [lo, hi] column range per row from `first_row`.
-namespace {
-struct RowCover {
-  int first_row = 0;
-  std::vector<int> lo, hi;
-  void init(int row_min, int row_max) {
-    first_row = row_min;
-    lo.assign((size_t)(row_max - row_min + 1), 1000000);
-    hi.assign(lo.size(), -1000000);
-  }
-  void cover(int row, int a, int b) {
-    const size_t i = (size_t)(row - first_row);
-    lo[i] = std::min(lo[i], a);
-    hi[i] = std::max(hi[i], b);
-  }
-};
-
-void alignment_rows(const int32_t* op_len, const uint8_t* op_chr, int64_t n_ops, int band, RowCover& out, RowCover& tmp) {
-  // leading / trailing insertion runs (GetCigarEnds, graph.cc:2136-2149), path extent
-  int64_t total = 0, rows = 0;
-  for (int64_t k = 0; k < n_ops; k++) {
-    total += op_len[k];
-    if (op_chr[k] == 'M' || op_chr[k] == 'D') rows += op_len[k];
-  }
-  int bl = 0, el = 0;
-  {
-    int64_t pos = 0;
-    bool found = false;
-    for (int64_t k = 0; k < n_ops && !found; k++) {
-      if (op_len[k] > 0 && op_chr[k] != 'I') { bl = (int)std::min<int64_t>(pos, 200); found = true; }
-      pos += op_len[k];
-    }
-    pos = 0;
-    found = false;
-    for (int64_t k = n_ops - 1; k >= 0 && !found; k--) {
-      if (op_len[k] > 0 && op_chr[k] != 'I') { el = (int)std::min<int64_t>(pos + 1, 200); found = true; }
-      pos += op_len[k];
-    }
-    (void)total;
-  }
-  const int row_end = (int)rows;
-  const int row_min = bl > 0 ? -bl : 0;
-  const int row_max = std::max(std::max(row_end, bl > 0 ? 2 : 0), el > 0 ? row_end + el - 1 : 0);
-  tmp.init(row_min, row_max);
-  tmp.cover(0, 0, 0);
-  if (bl > 0)
-    for (int i = -bl; i < 3; i++) tmp.cover(i, 0, bl - 1);
-  int row = 0, col = 0;
-  for (int64_t k = 0; k < n_ops; k++) {
-    const uint8_t c = op_chr[k];
-    for (int t = 0; t < op_len[k]; t++) {
-      if (c == 'M') { row++; col++; }
-      else if (c == 'I') col++;
-      else if (c == 'D') row++;
-      tmp.cover(row, col, col);
-    }
-  }
-  for (int i = row; i < row + el; i++) tmp.cover(i, col - el, col);
-  out.init(row_min - band, row_max + band);
-  for (size_t i = 0; i < tmp.lo.size(); i++) {
-    if (tmp.lo[i] > tmp.hi[i]) continue;
-    for (int d = -band; d <= band; d++) out.cover(tmp.first_row + (int)i + d, tmp.lo[i] - band, tmp.hi[i] + band);
-  }
-  // trim empty rows at both ends (the reference's first row is its first listed cell's)
-  size_t b = 0, e = out.lo.size();
-  while (b < e && out.lo[b] > out.hi[b]) b++;
-  while (e > b && out.lo[e - 1] > out.hi[e - 1]) e--;
-  if (b > 0 || e < out.lo.size()) {
-    out.lo = std::vector<int>(out.lo.begin() + (long)b, out.lo.begin() + (long)e);
-    out.hi = std::vector<int>(out.hi.begin() + (long)b, out.hi.begin() + (long)e);
-    out.first_row += (int)b;
-  }
-}
-}  // namespace
-
+// The host only summarises each CIGAR (O(#operations)): the leading / trailing insertion runs (GetCigarEnds,
+// graph.cc:2136-2149), where the path ends, and a bound on a row's width for the scratch strips. The cells themselves
+// are derived on the device while the DP runs (kernels.cu).
 int gaml_pacbio_alignment_logprob(gaml_ctx* ctx, double match_prob, double mismatch_prob, int32_t band, int64_t n,
                                   const uint8_t* s1, const int64_t* s1_off, const uint8_t* s2, const int64_t* s2_off,
                                   const int32_t* posstart, const int32_t* op_len, const uint8_t* op_chr, const int64_t* op_off,
                                   double* logprob_out) {
   if (check_ctx(ctx)) return GAML_ERR_ARG;
-  if (n < 0 || band < 0 || band > 64 || !(match_prob > 0.0) || !(mismatch_prob > 0.0))
+  if (n < 0 || band < 0 || !(match_prob > 0.0) || !(mismatch_prob > 0.0))
     return fail(ctx, GAML_ERR_ARG, "bad alignment-probability arguments");
+  if (band > kAlnMaxBand) return fail(ctx, GAML_ERR_UNSUPPORTED, "band larger than 8 (the reference uses 2, graph.cc:2755)");
   if (n == 0) return GAML_OK;
   if (!s1 || !s1_off || !s2 || !s2_off || !posstart || !op_len || !op_chr || !op_off || !logprob_out)
     return fail(ctx, GAML_ERR_ARG, "NULL array");
   cudaSetDevice(ctx->device);
+  const auto t_host0 = std::chrono::steady_clock::now();
   std::vector<AlnMeta> meta((size_t)n);
-  std::vector<int32_t> lo, hi;
-  RowCover rc, tmp;
   int64_t scratch = 0;
   for (int64_t a = 0; a < n; a++) {
     const int64_t k0 = op_off[a], k1 = op_off[a + 1];
-    if (k1 < k0) return fail(ctx, GAML_ERR_ARG, "cigar offsets not ascending");
-    for (int64_t k = k0; k < k1; k++)
-      if (op_len[k] < 0 || (op_chr[k] != 'M' && op_chr[k] != 'I' && op_chr[k] != 'D'))
-        return fail(ctx, GAML_ERR_ARG, "cigar operations must be M, I or D with non-negative lengths");
-    alignment_rows(op_len + k0, op_chr + k0, k1 - k0, band, rc, tmp);
+    if (k1 < k0 || k1 - k0 > 0x7fffffff) return fail(ctx, GAML_ERR_ARG, "cigar offsets not ascending");
+    int64_t rows = 0, cols = 0, lead = 0, trail = 0, run = 0, max_run = 0;
+    bool seen = false;
+    for (int64_t k = k0; k < k1; k++) {
+      const int64_t len = op_len[k];
+      const uint8_t c = op_chr[k];
+      if (len < 0 || (c != 'M' && c != 'I' && c != 'D')) return fail(ctx, GAML_ERR_ARG, "cigar operations must be M, I or D with non-negative lengths");
+      if (len == 0) continue;
+      if (c == 'I') {
+        cols += len;
+        run += len;
+        trail += len;
+        if (!seen) lead += len;
+      } else {
+        rows += len;
+        if (c == 'M') cols += len;
+        seen = true;
+        run = 0;
+        trail = 0;
+      }
+      max_run = std::max(max_run, run);
+    }
+    if (rows > 0x3fffffff || cols > 0x3fffffff) return fail(ctx, GAML_ERR_CAPACITY, "alignment too long");
     AlnMeta& m = meta[(size_t)a];
     m.s1_off = s1_off[a];
     m.s1_len = (int32_t)(s1_off[a + 1] - s1_off[a]);
     m.s2_off = s2_off[a];
     m.s2_len = (int32_t)(s2_off[a + 1] - s2_off[a]);
+    m.op_off = k0;
+    m.n_ops = (int32_t)(k1 - k0);
     m.posstart = posstart[a];
-    m.first_row = rc.first_row;
-    m.n_rows = (int32_t)rc.lo.size();
-    m.range_off = (int64_t)lo.size();
-    int w = 1;
-    for (size_t i = 0; i < rc.lo.size(); i++) w = std::max(w, rc.hi[i] - rc.lo[i] + 1);
-    m.width = w;
+    m.bl = seen ? (int32_t)std::min<int64_t>(lead, 200) : 0;
+    m.el = seen ? (int32_t)std::min<int64_t>(trail + 1, 200) : 0;
+    m.row_end = (int32_t)rows;
+    m.col_end = (int32_t)cols;
+    // a row's cells span at most 2*band+1 path rows (2*band diagonal steps and their insertion runs), the band on both
+    // sides, and one of the two blocks
+    const int64_t w = 4 * (int64_t)band + 3 + (2 * (int64_t)band + 1) * max_run + std::max<int64_t>(m.bl, m.el + 1);
+    if (w > 0x0fffffff) return fail(ctx, GAML_ERR_CAPACITY, "insertion run too long");
+    m.width = (int32_t)w;
     m.scratch_off = scratch;
-    scratch += 2 * (int64_t)w;
-    m.pad[0] = m.pad[1] = 0;
-    lo.insert(lo.end(), rc.lo.begin(), rc.lo.end());
-    hi.insert(hi.end(), rc.hi.begin(), rc.hi.end());
+    scratch += 2 * w;
+    m.pad[0] = m.pad[1] = m.pad[2] = 0;
   }
   cudaStream_t st = ctx->stream;
-  const size_t n1 = (size_t)s1_off[n], n2 = (size_t)s2_off[n];
-  DevBuf d_meta, d_s1, d_s2, d_lo, d_hi, d_scratch, d_out;
+  const size_t n1 = (size_t)s1_off[n], n2 = (size_t)s2_off[n], n_ops = (size_t)op_off[n];
+  DevBuf &d_meta = ctx->d_aln[0], &d_s1 = ctx->d_aln[1], &d_s2 = ctx->d_aln[2], &d_len = ctx->d_aln[3], &d_chr = ctx->d_aln[4],
+         &d_scratch = ctx->d_aln[5], &d_out = ctx->d_aln[6], &d_flag = ctx->d_aln[7];   // kept between calls
   CU(d_meta.reserve(meta.size() * sizeof(AlnMeta), 0, false, st));
   CU(d_s1.reserve(std::max<size_t>(n1, 1), 0, false, st));
   CU(d_s2.reserve(std::max<size_t>(n2, 1), 0, false, st));
-  CU(d_lo.reserve(std::max<size_t>(lo.size(), 1) * 4, 0, false, st));
-  CU(d_hi.reserve(std::max<size_t>(hi.size(), 1) * 4, 0, false, st));
+  CU(d_len.reserve(std::max<size_t>(n_ops, 1) * 4, 0, false, st));
+  CU(d_chr.reserve(std::max<size_t>(n_ops, 1), 0, false, st));
   CU(d_scratch.reserve(std::max<int64_t>(scratch, 1) * 8, 0, false, st));
   CU(d_out.reserve((size_t)n * 8, 0, false, st));
+  CU(d_flag.reserve(256, 0, true, st));
+  CU(cudaMemsetAsync(d_flag.p, 0, 4, st));
   CU(cudaMemcpyAsync(d_meta.p, meta.data(), meta.size() * sizeof(AlnMeta), cudaMemcpyHostToDevice, st));
   if (n1) CU(cudaMemcpyAsync(d_s1.p, s1, n1, cudaMemcpyHostToDevice, st));
   if (n2) CU(cudaMemcpyAsync(d_s2.p, s2, n2, cudaMemcpyHostToDevice, st));
-  if (!lo.empty()) {
-    CU(cudaMemcpyAsync(d_lo.p, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_hi.p, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, st));
+  if (n_ops) {
+    CU(cudaMemcpyAsync(d_len.p, op_len, n_ops * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_chr.p, op_chr, n_ops, cudaMemcpyHostToDevice, st));
   }
   AlnProbParams A{};
   A.meta = d_meta.as<AlnMeta>();
   A.n = n;
   A.s1 = d_s1.as<unsigned char>();
   A.s2 = d_s2.as<unsigned char>();
-  A.lo = d_lo.as<int32_t>();
-  A.hi = d_hi.as<int32_t>();
+  A.op_len = d_len.as<int32_t>();
+  A.op_chr = d_chr.as<unsigned char>();
+  A.band = band;
   A.scratch = d_scratch.as<double>();
   A.log_match = log(match_prob);
   A.log_mismatch = log(mismatch_prob);
   A.out = d_out.as<double>();
+  A.error_flag = d_flag.as<uint32_t>();
+  ctx->stats.last_prepare_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_host0).count();
+  CU(cudaEventRecord(ctx->ev[0], st));
   launch_pacbio_alnprob(A, ctx->sm_count, st);
+  CU(cudaEventRecord(ctx->ev[3], st));
   CU(cudaGetLastError());
   ctx->stats.kernel_launches += 1;
+  uint32_t flag = 0;
   CU(cudaMemcpyAsync(logprob_out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  ctx->stats.last_device_ms = ms;   // the DP kernel alone
+  ctx->timing_pending = false;
+  if (flag & 1u) return fail(ctx, GAML_ERR_CAPACITY, "an alignment's row was wider than the scratch strip bound");
   return GAML_OK;
 }
 

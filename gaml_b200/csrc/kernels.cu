@@ -1585,29 +1585,93 @@ __global__ void pacbio_cov_sweep_kernel(const unsigned long long* pkey, const un
 // Forward DP in log space over the cells around an alignment's CIGAR path: cell(row, col) = the probability of
 // generating the read's first `col` bases from the walk's bases up to `row`, summed over the three predecessors
 // (diagonal: match/mismatch, up: walk base against a gap, left: gap against a read base); the result is the sum of the
-// cells in the read's last column. The cells of a row are one column range [lo, hi] (prepared on the host from the
-// CIGAR and the band). One thread per alignment, rows and columns in the reference's order — the additions of the
-// log-sum-exp chain are not associative, so the order is part of the result — with the previous and the current row in
-// a per-thread scratch strip. Compute bound (three exp + log1p per cell); the strips stay in L1/L2.
+// cells in the read's last column.
+// The reference lists the cells — (0,0), a block in front of an alignment that starts with insertions, the path, a
+// block behind one that ends with insertions — fills every row between its smallest and largest listed column
+// (Uniquify, graph.cc:2150-2173) and widens everything by the band in both directions (graph.cc:2210-2222). Here one
+// thread per alignment walks the CIGAR ONCE, `band` rows ahead of the DP, keeping the column ranges of the 2*band+1
+// path rows that reach the current DP row in a ring: nothing per row is prepared on the host or stored. Rows and
+// columns run in the reference's order — the additions of the log-sum-exp chain are not associative, so the order
+// is part of the result — with the previous and the current row in a per-thread scratch strip (L1/L2 resident).
+// Compute bound: up to three exp + log1p per cell.
+struct CigarWalk {   // yields the column range of the path's cells row by row
+  const int32_t* len;
+  const unsigned char* chr;
+  int n_ops, k, rem, col;
+  __device__ __forceinline__ void norm() {
+    while (k < n_ops && rem == 0) {
+      k++;
+      if (k < n_ops) rem = len[k];
+    }
+  }
+  __device__ __forceinline__ void start(const int32_t* l, const unsigned char* c, int n) {
+    len = l; chr = c; n_ops = n; k = 0; col = 0;
+    rem = n > 0 ? l[0] : 0;
+    norm();
+  }
+  __device__ __forceinline__ void insertions() {
+    while (k < n_ops && chr[k] == 'I') { col += rem; rem = 0; norm(); }
+  }
+  // row 0: cell (0,0) and the leading insertions; row > 0: one M or D step into the row, then insertions
+  __device__ __forceinline__ bool row(int r, int& lo, int& hi) {
+    if (r > 0) {
+      if (k >= n_ops) return false;
+      if (chr[k] == 'M') col++;
+      rem--;
+      norm();
+    }
+    lo = col;
+    insertions();
+    hi = col;
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(128) pacbio_alnprob_kernel(const AlnProbParams A) {
   const double ninf = -INFINITY;
+  const int B = A.band;
+  constexpr int kRing = 2 * kAlnMaxBand + 1;
   for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < A.n; a += (long long)gridDim.x * blockDim.x) {
     const AlnMeta m = A.meta[a];
     const unsigned char* s1 = A.s1 + m.s1_off;
     const unsigned char* s2 = A.s2 + m.s2_off;
-    const int* lo = A.lo + m.range_off;
-    const int* hi = A.hi + m.range_off;
     double* prev = A.scratch + m.scratch_off;
     double* cur = prev + m.width;
+    const int row_min = m.bl > 0 ? -m.bl : 0;
+    const int row_max = max(max(m.row_end, m.bl > 0 ? 2 : 0), m.el > 0 ? m.row_end + m.el - 1 : 0);
+    CigarWalk cw;
+    cw.start(A.op_len + m.op_off, A.op_chr + m.op_off, m.n_ops);
+    int ring_lo[kRing], ring_hi[kRing];   // listed cells of path rows r-B .. r+B (lo > hi: none), slot = row mod ring
+#pragma unroll
+    for (int i = 0; i < kRing; i++) { ring_lo[i] = 1000000; ring_hi[i] = -1000000; }
+    const int ring = 2 * B + 1;
     double ret = ninf;
-    int plo = 1, phi = 0;   // previous row's range (empty)
-    for (int i = 0; i < m.n_rows; i++) {
-      const int l = lo[i], h = hi[i];
-      const int p1 = m.first_row + i + m.posstart - 1;
+    int plo = 1, phi = 0;   // previous DP row's range (empty)
+    bool failed = false;
+    for (int r = row_min - B; r <= row_max + B; r++) {
+      {   // listed cells of row R = r + B enter the window (rows are produced in ascending order, each once)
+        const int R = r + B;
+        int lo = 1000000, hi = -1000000;
+        if (R >= row_min && R <= row_max) {
+          int a_, b_;
+          if (R >= 0 && cw.row(R, a_, b_)) { lo = a_; hi = b_; }
+          if (m.bl > 0 && R >= -m.bl && R < 3) { lo = min(lo, 0); hi = max(hi, m.bl - 1); }                      // graph.cc:2188-2192
+          if (m.el > 0 && R >= m.row_end && R < m.row_end + m.el) { lo = min(lo, m.col_end - m.el); hi = max(hi, m.col_end); }   // 2204-2208
+        }
+        const int slot = ((R % ring) + ring) % ring;
+        ring_lo[slot] = lo;
+        ring_hi[slot] = hi;
+      }
+      int l = 1000000, h = -1000000;
+      for (int i = 0; i < ring; i++)
+        if (ring_lo[i] <= ring_hi[i]) { l = min(l, ring_lo[i] - B); h = max(h, ring_hi[i] + B); }
+      if (l > h) { plo = 1; phi = 0; continue; }
+      if (h - l + 1 > m.width) { failed = true; break; }
+      const int p1 = r + m.posstart - 1;
       const bool row_ok = p1 >= 0 && p1 < m.s1_len;
       const unsigned char c1 = row_ok ? s1[p1] : 0;
       const double up_lp = c1 == '\n' ? ninf : A.log_mismatch;   // MatchProbability(s1[.], '-'), graph.h:555-563
-      double left = ninf;   // value of (row, col - 1); outside the row's range: no such cell
+      double left = ninf;   // value of (row, col - 1); at the row's first cell there is none
       bool have_left = false;
       for (int c = l; c <= h; c++) {
         double v = c == 0 ? 0.0 : ninf;   // column 0: probability 1, graph.cc:2240-2244
@@ -1626,6 +1690,10 @@ __global__ void __launch_bounds__(128) pacbio_alnprob_kernel(const AlnProbParams
       double* t = prev; prev = cur; cur = t;
       plo = l;
       phi = h;
+    }
+    if (failed) {
+      atomicOr(A.error_flag, 1u);
+      ret = NAN;
     }
     A.out[a] = ret;
   }
