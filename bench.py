@@ -118,6 +118,9 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 5.0:   # nvidia-smi needs a second to come up on an 8-GPU box
+            time.sleep(0.05)
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -356,7 +359,10 @@ def main():
     sampler = ClockSampler(local_rank)
     launches0 = pc.stats().kernel_launches
     barrier()
-    sampler.start()
+    import gc
+    gc.disable()              # no collector pauses inside the timed loops (every rank waits for the slowest one)
+    if rank == 0:             # one nvidia-smi poller per job, not per rank
+        sampler.start()
     dev_ms = 0.0
     for _ in range(args.steps):
         d, _k, part, tl = full_step_device()
