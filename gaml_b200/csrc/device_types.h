@@ -88,6 +88,9 @@ struct MateView {
 struct ScoreParams {
   MateView m[2];
   const uint32_t* lens;      // single/pacbio: read length; paired: len1 | len2<<16
+  const void* pairs;         // paired: one PackedPair (16 B) per pair for the streaming kernel's tier 1, or null (kernels.cu)
+  uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
+  int32_t lens_uniform;
   const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)
   int32_t ins_n;
   const double* thr_tab;     // single/paired: exp(mps + mppb*len) indexed by len (paired: len1+len2)

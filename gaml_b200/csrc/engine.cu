@@ -161,6 +161,10 @@ struct ReadSetState {
   std::vector<int32_t> len[2];
   MateStore mate[2];
   DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
+  DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
+  bool pairs_ok = false;
+  bool lens_uniform = false;    // every pair of the set has the same packed lengths
+  uint32_t uniform_ll = 0;
   int32_t class_begin[17] = {0};
   uint32_t cbase[2][5] = {{0}};  // first compact row of the five tier-2 classes, per mate
   int n_complex = 0;
@@ -648,7 +652,20 @@ int commit(gaml_ctx* ctx) {
       launch_cdesc_fill(rs.d_complex.as<uint32_t>(), rs.n_complex, rs.d_lens.as<uint32_t>(), rs.mate[0].cptr.as<uint32_t>(),
                         rs.n_mates == 2 ? rs.mate[1].cptr.as<uint32_t>() : nullptr, rs.d_cdesc.p, ctx->stream);
       launches++;
+      rs.pairs_ok = false;
+      uint32_t pack_bad = 0;
+      if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0) {
+        // tier 1's packed copy of both mates' first records (16 B per pair instead of 2 x 16 B + lengths)
+        CU(rs.d_pairs.reserve((size_t)rs.n_local * 16, 0, false, ctx->stream));
+        uint32_t* bad = static_cast<uint32_t*>(ctx->d_csr_temp.p);   // scratch, free after build_csr / the list build
+        CU(cudaMemsetAsync(bad, 0, 4, ctx->stream));
+        launch_pack_pairs(rs.mate[0].first.p, rs.mate[1].first.p, rs.n_local, rs.d_pairs.p, bad, ctx->stream);
+        launches++;
+        pack_bad = 1;
+        CU(cudaMemcpyAsync(&pack_bad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      }
       CU(cudaStreamSynchronize(ctx->stream));
+      if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0) rs.pairs_ok = pack_bad == 0;
       ctx->stats.kernel_launches += launches;
       rs.complex_dirty = false;
     }
@@ -967,6 +984,9 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
     P.m[m].pow_mismatch = st.d_pow_mismatch.as<double>();
   }
   P.lens = rs.d_lens.as<uint32_t>();
+  P.pairs = rs.pairs_ok ? rs.d_pairs.p : nullptr;
+  P.lens_uniform = rs.lens_uniform ? 1 : 0;
+  P.uniform_ll = rs.uniform_ll;
   P.ins_tab = rs.d_ins.as<double>();
   P.ins_n = rs.ins_n;
   P.thr_tab = rs.d_thr.as<double>();
@@ -1827,6 +1847,9 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   std::vector<uint32_t> packed(std::max<int64_t>(n_local, 1));
   for (int64_t i = 0; i < n_local; i++)
     packed[i] = paired ? ((uint32_t)rs.len[0][i] | ((uint32_t)rs.len[1][i] << 16)) : (uint32_t)rs.len[0][i];
+  rs.lens_uniform = paired && n_local > 0;
+  for (int64_t i = 1; i < n_local && rs.lens_uniform; i++) rs.lens_uniform = packed[i] == packed[0];
+  rs.uniform_ll = rs.lens_uniform ? packed[0] : 0u;
   CU(rs.d_lens.reserve(packed.size() * 4, 0, false, ctx->stream));
   CU(cudaMemcpyAsync(rs.d_lens.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(rs.d_values.reserve(std::max<int64_t>(n_local, 1) * 8, 0, true, ctx->stream));

@@ -30,9 +30,22 @@ namespace {
 constexpr int kCapLong = 8;        // pacbio placements handled in local memory before the scratch path
 constexpr int kBlock = 256;
 constexpr int kOvfBlock = 128;
+constexpr int kStreamBlocksPerSM = 5;   // paired_stream_kernel: resident blocks per SM the register budget is set for
 
 // ---- small helpers ------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+// Streamed-once data: read-only path, not kept in L1 (the lines would only evict the slot and probability tables).
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// PackedPair (16 B per pair, built at cache commit when every record fits): what tier 1 of the streaming kernel needs of
+// a pair's two first records — x = key1 | edit1<<22 | orient1<<29 | none1<<30 | tier2<<31, y = the same for mate 2
+// (bit 31 unused), z = pos1, w = pos2. tier2 = some mate owns two or more records (the read is on the static list).
+constexpr int kPackKeyBits = 22;
+constexpr uint32_t kPackKeyMask = (1u << kPackKeyBits) - 1u;
+constexpr uint32_t kPackEdMask = 0x7fu;
 
 __device__ __forceinline__ int wrap_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 
@@ -893,32 +906,219 @@ __device__ __forceinline__ void rare_tiles(const ScoreParams& P, int* s_tile, Ac
   }
 }
 
+// Tier-1 tile body: kR reads per lane of one warp tile, every step written without branches so that the kR
+// dependent chains (first records -> {slot words, pow tables, threshold} -> insert pdf -> products -> quotient -> log)
+// are issued side by side: one trip per memory level for all of them. Filters of paired_simple_acc become predicates
+// (a dropped pair is a term of +0.0, which is what the state holds for such a read); the two rare fix-ups (IEEE division
+// next to the floor threshold, libm log for 0/denormal/non-finite) are taken once, after the common work of all kR reads.
+template <bool kCov, bool kPacked, int kR>
+__device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __restrict__ src1, const uint4* __restrict__ src2,
+                                           int lane, const int4* __restrict__ sa1, const int4* __restrict__ sa2,
+                                           const double2* __restrict__ log_tab, int q_first, int n, Acc& sum, unsigned& floored) {
+  // level 1: the records of this lane's kR reads (read q_first + 32 j + lane; reads past the end are clamped to the last
+  // one and masked out below) and the lengths unless the whole set shares them
+  int qi[kR];
+  bool valid[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const int q = q_first + 32 * j + lane;
+    valid[j] = q < n;
+    qi[j] = min(q, n - 1);
+  }
+  uint4 u1[kR], u2[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    u1[j] = ldg_stream(src1 + qi[j]);
+    if (!kPacked) u2[j] = ldg_stream(src2 + qi[j]);
+  }
+  int key1[kR], key2[kR], pos1[kR], pos2[kR], e1[kR], e2[kR], xo[kR], yo[kR];
+  bool has1[kR], has2[kR], tier2[kR];
+  uint32_t ll[kR];
+  if (P.lens_uniform) {
+#pragma unroll
+    for (int j = 0; j < kR; j++) ll[j] = P.uniform_ll;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kR; j++) ll[j] = __ldg(P.lens + qi[j]);
+  }
+  if (kPacked) {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const uint4 pr = u1[j];
+      key1[j] = (int)(pr.x & kPackKeyMask);
+      key2[j] = (int)(pr.y & kPackKeyMask);
+      e1[j] = (int)((pr.x >> kPackKeyBits) & kPackEdMask);
+      e2[j] = (int)((pr.y >> kPackKeyBits) & kPackEdMask);
+      xo[j] = (int)((pr.x >> 29) & 1u);
+      yo[j] = (int)((pr.y >> 29) & 1u);
+      has1[j] = ((pr.x >> 30) & 1u) == 0u;
+      has2[j] = ((pr.y >> 30) & 1u) == 0u;
+      tier2[j] = (pr.x >> 31) != 0u;
+      pos1[j] = (int)pr.z;
+      pos2[j] = (int)pr.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const int4 rw1 = make_int4((int)u1[j].x, (int)u1[j].y, (int)u1[j].z, (int)u1[j].w);
+      const int4 rw2 = make_int4((int)u2[j].x, (int)u2[j].y, (int)u2[j].z, (int)u2[j].w);
+      key1[j] = max(rw1.x, 0);   // key -1 (no record) reads slot 0, ignored below
+      key2[j] = max(rw2.x, 0);
+      has1[j] = rw1.x >= 0;
+      has2[j] = rw2.x >= 0;
+      e1[j] = rw1.z & 0xffff;
+      e2[j] = rw2.z & 0xffff;
+      xo[j] = (rw1.z >> 30) & 1;
+      yo[j] = (rw2.z >> 30) & 1;
+      tier2[j] = (((rw1.z | rw2.z) >> 17) & 0x1fff) != 0;   // count >= 2 on a mate
+      pos1[j] = rw1.y;
+      pos2[j] = rw2.y;
+    }
+  }
+  // level 2: slot words of both keys, pow tables, floor threshold (L1/L2 resident)
+  int4 o1[kR], o2[kR];
+  double pa[kR], pb[kR], thr[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    o1[j] = __ldg(sa1 + key1[j]);
+    o2[j] = __ldg(sa2 + key2[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
+    pa[j] = __dmul_rn(__ldg(P.m[0].pow_mismatch + e1[j]), __ldg(P.m[0].pow_match + (l1 - e1[j])));
+    pb[j] = __dmul_rn(__ldg(P.m[1].pow_mismatch + e2[j]), __ldg(P.m[1].pow_match + (l2 - e2[j])));
+    thr[j] = __ldg(P.thr_tab + l1 + l2);
+  }
+  bool mine[kR], ok[kR];
+  int dist[kR], px[kR], py[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
+    const uint32_t f1 = (uint32_t)o1[j].x, f2 = (uint32_t)o2[j].x;
+    const bool live1 = has1[j] && (f1 & 0x7fffffffu) == P.epoch, live2 = has2[j] && (f2 & 0x7fffffffu) == P.epoch;
+    const bool multi = (live1 && (f1 >> 31)) || (live2 && (f2 >> 31));             // paired_multi_kernel's read
+    mine[j] = valid[j] && !tier2[j] && !multi;
+    const int p1 = wrap_add(pos1[j], o1[j].z), p2 = wrap_add(pos2[j], o2[j].z);
+    px[j] = p1;
+    py[j] = p2;
+    const bool fwd = p1 < p2;
+    const int d = fwd ? p2 - p1 + l2 : p1 - p2 + l1;                               // graph.cc:1866-1875
+    const bool placed = live1 && live2 && p1 >= o1[j].w && p2 >= o2[j].w && o1[j].y == o2[j].y;   // graph.cc:577; one walk
+    ok[j] = mine[j] && placed && xo[j] != yo[j] && xo[j] == (fwd ? 0 : 1) && (unsigned)d < (unsigned)P.ins_n;
+    dist[j] = ok[j] ? d : 0;
+  }
+  double acc[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const double ins = __ldg(P.ins_tab + dist[j]);
+    const double t = __dmul_rn(__dmul_rn(pa[j], pb[j]), ins);                        // (p1*p2)*ins, graph.cc:1889
+    const double signed_t = (o1[j].y < P.n_erased) ? __dsub_rn(0.0, t) : __dadd_rn(0.0, t);
+    acc[j] = ok[j] ? signed_t : 0.0;
+    if (kCov) {
+      if (ok[j]) emit_cov(P, o1[j].y, px[j], py[j], (int)(ll[j] >> 16), t);
+    }
+  }
+  // max(p / (2 total_len), thr): Markstein quotient, IEEE division next to the threshold (floored_term)
+  double q[kR];
+  bool near_thr = false;
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    double v = __dmul_rn(acc[j], P.rcp_two_len);
+    v = fma(fma(-v, P.two_len_d, acc[j]), P.rcp_two_len, v);
+    q[j] = v;
+    near_thr |= fabs(v - thr[j]) <= thr[j] * 3.5527136788005009e-15;
+  }
+  if (near_thr) {
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+      if (fabs(q[j] - thr[j]) <= thr[j] * 3.5527136788005009e-15) q[j] = slow_div(acc[j], P.two_len_d);
+  }
+  unsigned fl[kR];
+  double lg[kR];
+  bool special = false;
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    fl[j] = q[j] < thr[j] ? 1u : 0u;
+    q[j] = fl[j] ? thr[j] : q[j];
+    // table_log's fast path, computed unconditionally (garbage, not a trap, for 0/denormal/non-finite input)
+    const long long ix = __double_as_longlong(q[j]);
+    special |= (unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull;
+    const long long tmp = ix - 0x3fe6000000000000ll;
+    const int i = (int)((tmp >> 45) & 127);
+    const long long k = tmp >> 52;
+    const double z = __longlong_as_double(ix - (tmp & 0xfff0000000000000ll));
+    const double2 e = log_tab[i];
+    const double r = fma(z, e.x, -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(r, p, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r * r, p, r);
+    lg[j] = fma((double)k, 0.693147180559945309417232121458, e.y) + p;
+  }
+  if (special) {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const long long ix = __double_as_longlong(q[j]);
+      if ((unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) lg[j] = slow_log(q[j]);
+    }
+  }
+  bool odd = false;   // a term outside the fixed-point range (log 0 = -inf, NaN): counted, not added
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    if (mine[j]) P.values[qi[j]] = acc[j];
+    const bool fin = fabs(lg[j]) < kFixLimit;
+    odd |= mine[j] && !fin;
+    acc_add_q(sum, (mine[j] && fin) ? __double2ll_rn(lg[j] * kFixScale) : 0ll);
+    floored += mine[j] ? fl[j] : 0u;
+  }
+  if (odd) {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      if (mine[j] && !(fabs(lg[j]) < kFixLimit)) {
+        if (lg[j] == -INFINITY) sum.neginf++; else sum.bad++;
+      }
+    }
+  }
+}
+
 // FULL, the streaming kernel: tier 1 (every read with at most one record per mate, straight from the dense
 // first-record arrays) and then tier 2 (the static list of reads with two records on a mate, from the compact copy) in
 // one launch — both are tile loops over static data drawn from counters, so a block simply moves on to tier-2 tiles when
 // the tier-1 tiles run out, without a kernel boundary (ramp, tail, launch) in between.
-__global__ void __launch_bounds__(kBlock, 5) paired_stream_kernel(const ScoreParams P) {
+template <bool kCov, bool kPacked, int kBPS, int kR>
+__global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const ScoreParams P) {
   tl_begin(P.timeline, kTlTier1);
   const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
   const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
   const double2* log_tab = static_cast<const double2*>(P.log_tab);
   Acc sum = acc_zero();
   unsigned floored = 0;
-  const int4* first1 = static_cast<const int4*>(P.m[0].first);
-  const int4* first2 = static_cast<const int4*>(P.m[1].first);
   const int n = P.n_reads;
-  // Work is handed out in tiles of 2 x 256 consecutive reads from a counter (zeroed by apply_slots): blocks that
-  // become resident late — the multi pass in front of this kernel holds part of the register file for a while — or run
-  // slowly simply take fewer tiles. The exact integer accumulators make the result independent of who sums what.
-  // A block's first tile is its own index, so its lines can be pulled towards L2 before the wait below.
-  constexpr int kTile = 2 * kBlock;
-  const int n_tiles = (n + kTile - 1) / kTile;
   __shared__ int s_tile[2];
-  int tile = blockIdx.x, buf = 0;
-  if (tile < n_tiles && (threadIdx.x & 7) == 0) {   // 8 consecutive 16-byte records = one 128-byte line
-    const int r0 = min(tile * kTile + (int)threadIdx.x, n - 1), r1 = min(r0 + kBlock, n - 1);
-    prefetch_l2(first1 + r0); prefetch_l2(first2 + r0); prefetch_l2(first1 + r1); prefetch_l2(first2 + r1);
-  }
+  // Tier 1: work is handed out in tiles of kR x 256 consecutive reads (a warp takes kR x 32 consecutive ones of them). A
+  // block's first two tiles are static (its own index, then + gridDim), the rest is drawn from a counter (zeroed by
+  // apply_slots) TWO tiles ahead: blocks that become resident late — the multi pass in front of this kernel holds part of
+  // the register file for a while — or run slowly simply take fewer tiles, and the next tile's lines are pulled into L2
+  // (prefetch.global.L2, no registers held) while the current tile is being worked on, so its demand loads find them
+  // there. The exact integer accumulators make the result independent of who sums what.
+  constexpr int kTile = kR * kBlock;
+  constexpr int kRecLines = kTile * 16 / 128;   // 128-byte lines of one record array per tile
+  const int n_tiles = (n + kTile - 1) / kTile;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint4* __restrict__ src1 = static_cast<const uint4*>(kPacked ? P.pairs : P.m[0].first);
+  const uint4* __restrict__ src2 = static_cast<const uint4*>(P.m[1].first);
+  auto prefetch_tile = [&](int t) {
+    if (t >= n_tiles) return;
+    const int q = min(t * kTile + ((int)threadIdx.x % kRecLines) * 8, n - 1);   // 8 consecutive 16-byte records = one line
+    if ((int)threadIdx.x < kRecLines) prefetch_l2(src1 + q);
+    else if (!kPacked && (int)threadIdx.x < 2 * kRecLines) prefetch_l2(src2 + q);
+  };
+  static_assert(2 * kRecLines <= kBlock, "one prefetch per thread");
+  int tile = blockIdx.x, next = (int)blockIdx.x + (int)gridDim.x, buf = 0;
+  prefetch_tile(tile);   // static data: may be requested before the wait below
   // First kernel after apply_slots (no multi pass before it): wait here, release after. Otherwise the multi pass did
   // that, every block of this kernel starts after apply_slots completed, and the wait moves to the end.
   if (P.chain_first) pdl_wait();
@@ -929,41 +1129,18 @@ __global__ void __launch_bounds__(kBlock, 5) paired_stream_kernel(const ScorePar
     rare_tiles(P, s_tile, sum, floored);
     __syncthreads();
   }
-  // Two reads per thread and tile: six independent coalesced loads in flight per thread before any use, and the two
-  // division+log chains (the longest dependent fp64 sequences here) are issued side by side.
-  // (Measured dead ends, profiles/r01_summary.md: register double-buffering of the next iteration's loads and
-  //  staging the slot words + log table in shared memory both cost registers/instructions and gained nothing.)
   while (tile < n_tiles) {
-    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // next tile, used after this one
-    const int r = tile * kTile + (int)threadIdx.x;
-    if (tile * kTile + kTile <= n) {
-      const int4 a1 = __ldg(first1 + r), a2 = __ldg(first2 + r);
-      const int4 b1 = __ldg(first1 + r + kBlock), b2 = __ldg(first2 + r + kBlock);
-      const uint32_t la = __ldg(P.lens + r), lb = __ldg(P.lens + r + kBlock);
-      double acc_a, acc_b;
-      const bool ok_a = paired_simple_acc(P, sa1, sa2, r, a1, a2, la, acc_a);
-      const bool ok_b = paired_simple_acc(P, sa1, sa2, r + kBlock, b1, b2, lb, acc_b);
-      const double thr_a = __ldg(P.thr_tab + (la & 0xffff) + (la >> 16)), thr_b = __ldg(P.thr_tab + (lb & 0xffff) + (lb >> 16));
-      unsigned fa = 0, fb = 0;
-      const double ta = floored_term(P, log_tab, acc_a, thr_a, fa), tb = floored_term(P, log_tab, acc_b, thr_b, fb);
-      if (ok_a) { P.values[r] = acc_a; acc_add(sum, ta); floored += fa; }
-      if (ok_b) { P.values[r + kBlock] = acc_b; acc_add(sum, tb); floored += fb; }
-    } else {   // the last, partial tile
-      for (int q = r; q < n; q += kBlock) {
-        const uint32_t ll = __ldg(P.lens + q);
-        double acc;
-        if (paired_simple_acc(P, sa1, sa2, q, __ldg(first1 + q), __ldg(first2 + q), ll, acc)) {
-          P.values[q] = acc;
-          acc_add(sum, floored_term(P, log_tab, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
-        }
-      }
-    }
+    if (threadIdx.x == 0) s_tile[buf] = 2 * (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // the tile after next
+    prefetch_tile(next);
+    tier1_body<kCov, kPacked, kR>(P, src1, src2, lane, sa1, sa2, log_tab, tile * kTile + wib * (32 * kR), n, sum, floored);
     __syncthreads();
-    tile = s_tile[buf];
+    tile = next;
+    next = s_tile[buf];
     buf ^= 1;
   }
   tl_end(P.timeline, kTlTier1);
   if (P.n_main > 0) {
+    __syncthreads();   // s_tile is shared with the rare-shape phase
     tl_begin(P.timeline, kTlTier2);
     tier2_tiles(P, s_tile, sum, floored);
     tl_end(P.timeline, kTlTier2);
@@ -1847,6 +2024,21 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 // ---- launch wrappers ------------------------------------------------------------------------
 // Grids are sized to exactly one resident wave (SM count x blocks that fit per SM for that kernel) so the
 // grid-stride loops have no partial second wave.
+// The streaming kernel's instantiation: penalised sets (coverage events) and sets whose records do not fit PackedPair
+// stream the 16-byte first records; everything else the packed pairs.
+using StreamKernel = void (*)(const ScoreParams);
+StreamKernel stream_kernel(bool cov, bool packed) {
+  static const int v = [] { const char* e = getenv("GAML_STREAM_VARIANT"); return e ? atoi(e) : 0; }();   // EXPERIMENT
+  if (cov) return paired_stream_kernel<true, false, 4, 2>;
+  if (!packed || v == 9) return paired_stream_kernel<false, false, 4, 2>;
+  switch (v) {
+    case 1: return paired_stream_kernel<false, true, 5, 2>;
+    case 2: return paired_stream_kernel<false, true, 4, 4>;
+    case 3: return paired_stream_kernel<false, true, 6, 2>;
+    default: return paired_stream_kernel<false, true, 4, 2>;
+  }
+}
+
 template <class K>
 int resident_blocks(K kernel, int block) {
   int n = 0;
@@ -1859,8 +2051,8 @@ int score_grid(int which, int n_items, int sm_count) {
   if (which < 0 || which > 5) which = 0;
   if (per_sm[which] == 0) {
     switch (which) {
-      case kGridPairedFull: per_sm[which] = resident_blocks(paired_stream_kernel, kBlock); break;
-      case kGridPairedComplex: per_sm[which] = resident_blocks(paired_stream_kernel, kBlock); break;
+      case kGridPairedFull: per_sm[which] = resident_blocks(stream_kernel(false, true), kBlock); break;
+      case kGridPairedComplex: per_sm[which] = resident_blocks(stream_kernel(false, true), kBlock); break;
       case kGridPairedTotal: per_sm[which] = resident_blocks(paired_total_kernel, kBlock); break;
       case kGridSingleFull: per_sm[which] = resident_blocks(single_full_kernel, kBlock); break;
       case kGridSingleComplex: per_sm[which] = resident_blocks(single_complex_kernel, kBlock); break;
@@ -1955,7 +2147,7 @@ void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_mu
   if (profile) cudaEventRecord(e0, st);
   Q.chain_first = first || profile ? 1 : 0;
   Q.finish_here = profile ? 0 : 1;   // when profiling, e0/e1 bracket the streaming work alone: the last kernel publishes
-  launch_chain(paired_stream_kernel, grid, kBlock, st, dep && !profile, Q);
+  launch_chain(stream_kernel(P.ev_keys != nullptr, P.pairs != nullptr), grid, kBlock, st, dep && !profile, Q);
   if (profile) cudaEventRecord(e1, st);
   launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
 }
@@ -2098,6 +2290,30 @@ void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_r
   }
   if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
   batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag);
+}
+
+// Packs the two dense first-record arrays of a paired set into PackedPair; *bad != 0 afterwards when some record does not
+// fit (key >= 2^22 or edit distance > 127) and the set keeps streaming the 16-byte records.
+__global__ void pack_pairs_kernel(const int4* first1, const int4* first2, int n, uint4* out, uint32_t* bad) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int4 a = ldg4(first1 + r), b = ldg4(first2 + r);
+  const bool none1 = a.x < 0, none2 = b.x < 0;
+  const uint32_t k1 = none1 ? 0u : (uint32_t)a.x, k2 = none2 ? 0u : (uint32_t)b.x;
+  const uint32_t ed1 = (uint32_t)a.z & 0xffffu, ed2 = (uint32_t)b.z & 0xffffu;
+  if (k1 > kPackKeyMask || k2 > kPackKeyMask || ed1 > kPackEdMask || ed2 > kPackEdMask) *bad = 1u;
+  const uint32_t tier2 = ((((uint32_t)a.z | (uint32_t)b.z) >> 17) & 0x1fffu) != 0u ? 1u : 0u;
+  uint4 v;
+  v.x = (k1 & kPackKeyMask) | ((ed1 & kPackEdMask) << kPackKeyBits) | ((((uint32_t)a.z >> 30) & 1u) << 29) | ((none1 ? 1u : 0u) << 30) | (tier2 << 31);
+  v.y = (k2 & kPackKeyMask) | ((ed2 & kPackEdMask) << kPackKeyBits) | ((((uint32_t)b.z >> 30) & 1u) << 29) | ((none2 ? 1u : 0u) << 30);
+  v.z = (uint32_t)a.y;
+  v.w = (uint32_t)b.y;
+  out[r] = v;
+}
+void launch_pack_pairs(const void* first1, const void* first2, int n, void* out, uint32_t* bad, cudaStream_t st) {
+  if (n > 0)
+    pack_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2), n,
+                                                       static_cast<uint4*>(out), bad);
 }
 
 void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,

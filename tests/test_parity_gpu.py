@@ -482,3 +482,31 @@ def test_cuda_alnprob_matches_oracle_seeded(name, tmp_path):
         pc.pacbio_alignment_logprob([alnprob.Alignment(b"ACGT", b"ACGT", 1, [(4, "X")])], match, mismatch, band)
     pc.close()
     _close_logvals(got, ref)
+
+
+def test_records_that_do_not_fit_the_packed_pairs_stream_the_plain_records(oracle):
+    """Tier 1 of the streaming kernel reads a 16-byte packed copy of each pair's two first records (key < 2^22, edit
+    distance <= 127). A set with a larger edit distance keeps the plain 16-byte records: same results either way."""
+    wl = synth.paired_workload(10, 3000, 3000, n_evals=6, seed=77, read_len=250, insert_mean=600.0, insert_std=40.0)
+    spec = wl.sets[0]
+    bumped = 0
+    for cache in spec.caches:
+        for key in sorted(cache.keys()):
+            recs = cache[key]
+            if len(recs) and bumped < 40:
+                recs["edit_dist"][0] = 128 + bumped      # still <= read length + 6
+                bumped += 1
+    assert bumped >= 20
+    check_against(wl, oracle(wl, "unpackable"))
+
+
+def test_ragged_lengths_with_packed_pairs(oracle):
+    """Per-pair lengths differ: the packed records are used, the lengths are read from their own array."""
+    wl = synth.paired_workload(10, 3000, 3000, n_evals=6, seed=78)
+    spec = wl.sets[0]
+    rng = np.random.default_rng(5)
+    spec.read_len[0] = np.asarray(spec.read_len[0]).copy()
+    spec.read_len[1] = np.asarray(spec.read_len[1]).copy()
+    spec.read_len[0][::3] -= rng.integers(1, 20, size=len(spec.read_len[0][::3])).astype(spec.read_len[0].dtype)
+    spec.read_len[1][::5] -= rng.integers(1, 20, size=len(spec.read_len[1][::5])).astype(spec.read_len[1].dtype)
+    check_against(wl, oracle(wl, "ragged_packed"))
