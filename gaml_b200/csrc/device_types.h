@@ -115,6 +115,8 @@ struct ScoreParams {
   int32_t class_begin[17];   // first list index of every record-count class, in list order (complex_class ranks)
   int32_t n_complex;
   int32_t n_main;            // list entries tier 2 streams (ranks 0..4); the rest is the multi pass's static part
+  const void* t2pack;        // packed tier-2 entries of classes (1,2) (2,1) (2,2), unit-major per class (kernels.cu), or null
+  uint32_t t2base[3];        // first uint4 of each class in t2pack
   uint32_t cbase[2][5];      // per mate: first compact row of classes 0..4 (rows per read are uniform within a class)
   // multi pass: arena ranges (both mates) of the keys that occur several times in this evaluation
   const ArenaShort* arena2;

@@ -162,6 +162,9 @@ struct ReadSetState {
   MateStore mate[2];
   DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
+  DevBuf d_t2pack;              // paired: packed tier-2 entries (kernels.cu), valid when t2pack_ok
+  bool t2pack_ok = false;
+  uint32_t t2base[3] = {0, 0, 0};
   bool pairs_ok = false;
   bool lens_uniform = false;    // every pair of the set has the same packed lengths
   uint32_t uniform_ll = 0;
@@ -664,8 +667,27 @@ int commit(gaml_ctx* ctx) {
         pack_bad = 1;
         CU(cudaMemcpyAsync(&pack_bad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
       }
-      CU(cudaStreamSynchronize(ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));   // cbase (copied above) and pack_bad are on the host now
       if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0) rs.pairs_ok = pack_bad == 0;
+      rs.t2pack_ok = false;
+      if (rs.pairs_ok && rs.class_begin[3] > 0) {
+        // tier 2's packed entries: classes (1,2), (2,1) two units per read, (2,2) three, unit major per class
+        const size_t n0 = (size_t)(rs.class_begin[1] - rs.class_begin[0]), n1 = (size_t)(rs.class_begin[2] - rs.class_begin[1]),
+                     n2 = (size_t)(rs.class_begin[3] - rs.class_begin[2]);
+        rs.t2base[0] = 0;
+        rs.t2base[1] = (uint32_t)(2 * n0);
+        rs.t2base[2] = (uint32_t)(2 * n0 + 2 * n1);
+        CU(rs.d_t2pack.reserve((2 * n0 + 2 * n1 + 3 * n2) * 16, 0, false, ctx->stream));
+        uint32_t* bad = static_cast<uint32_t*>(ctx->d_csr_temp.p);
+        CU(cudaMemsetAsync(bad, 0, 4, ctx->stream));
+        launch_pack_tier2(rs.d_cdesc.p, rs.mate[0].crows.p, rs.mate[1].crows.p, rs.class_begin, rs.cbase, rs.t2base, rs.d_t2pack.p,
+                          bad, ctx->stream);
+        launches++;
+        uint32_t t2_bad = 1;
+        CU(cudaMemcpyAsync(&t2_bad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        rs.t2pack_ok = t2_bad == 0;
+      }
       ctx->stats.kernel_launches += launches;
       rs.complex_dirty = false;
     }
@@ -1013,6 +1035,8 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.n_complex = rs.n_complex;
   P.n_main = rs.class_begin[5];
   memcpy(P.cbase, rs.cbase, sizeof(P.cbase));
+  P.t2pack = rs.t2pack_ok ? rs.d_t2pack.p : nullptr;
+  memcpy(P.t2base, rs.t2base, sizeof(P.t2base));
   P.arena2 = rs.n_mates == 2 ? rs.mate[1].arena.as<ArenaShort>() : nullptr;
   P.mtouch = reinterpret_cast<const TouchRange*>(blob + sp.mtouch_off);
   P.mtouch_prefix = reinterpret_cast<const uint32_t*>(blob + sp.mprefix_off);

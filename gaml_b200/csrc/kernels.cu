@@ -814,6 +814,149 @@ __device__ __forceinline__ void tier2_tiles(const ScoreParams& P, int* s_tile, A
   }
 }
 
+// ---- tier 2 from packed entries ----------------------------------------------------------------------------------
+// Packed copy of the tier-2 list's classes (1,2), (2,1), (2,2), built at commit when every record fits: a record is
+// 8 bytes {key | edit<<22 | orient<<29, pos}; an entry is 2 (three records) or 3 (four records) uint4 units, stored unit
+// major per class so that every unit load of a warp is one coalesced request:
+//   (1,2): u0 = {read, lengths, x0}        u1 = {y0, y1}
+//   (2,1): u0 = {read, lengths, y0}        u1 = {x0, x1}
+//   (2,2): u0 = {read, lengths, -, -}      u1 = {x0, x1}      u2 = {y0, y1}
+// 40 / 48 bytes per read instead of a 16-byte descriptor plus 48 / 64 bytes of rows.
+struct Rec8 { uint32_t w; int pos; };
+__device__ __forceinline__ Rec8 rec8(uint32_t a, uint32_t b) { return Rec8{a, (int)b}; }
+
+// One tier-2 read, written like tier1_body: every load that does not depend on another is requested at once (slot words
+// of all records, pow tables, threshold; then the insert pdf of all combinations), filters are predicates, no branches.
+// Same rules as tier2_read: status 1 = scored (acc), 0 = a live key occurs several times (the multi pass's read),
+// -1 = the enumeration order matters (duplicate placement with a different payload, or three and more pair terms).
+template <int N1, int N2>
+__device__ __forceinline__ int tier2_packed_read(const ScoreParams& P, const int4* __restrict__ sa1, const int4* __restrict__ sa2,
+                                                 const Rec8 (&x)[2], const Rec8 (&y)[2], uint32_t ll, double& acc, double& thr) {
+  const int l1 = ll & 0xffff, l2 = ll >> 16;
+  int4 ox[2], oy[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    ox[i] = __ldg(sa1 + (x[i < N1 ? i : 0].w & kPackKeyMask));
+    oy[i] = __ldg(sa2 + (y[i < N2 ? i : 0].w & kPackKeyMask));
+  }
+  double px[2], py[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int ex = (int)((x[i < N1 ? i : 0].w >> kPackKeyBits) & kPackEdMask), ey = (int)((y[i < N2 ? i : 0].w >> kPackKeyBits) & kPackEdMask);
+    px[i] = __dmul_rn(__ldg(P.m[0].pow_mismatch + ex), __ldg(P.m[0].pow_match + (l1 - ex)));
+    py[i] = __dmul_rn(__ldg(P.m[1].pow_mismatch + ey), __ldg(P.m[1].pow_match + (l2 - ey)));
+  }
+  thr = __ldg(P.thr_tab + l1 + l2);
+  bool lx[2], ly[2], multi = false;
+  int wx[2], wy[2], qx[2], qy[2], orx[2], ory[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const uint32_t fx = (uint32_t)ox[i].x, fy = (uint32_t)oy[i].x;
+    const bool hx = i < N1, hy = i < N2;
+    const bool ex = hx && (fx & 0x7fffffffu) == P.epoch, ey = hy && (fy & 0x7fffffffu) == P.epoch;
+    multi |= (ex && (fx >> 31)) || (ey && (fy >> 31));
+    wx[i] = ox[i].y; wy[i] = oy[i].y;
+    qx[i] = wrap_add(x[hx ? i : 0].pos, ox[i].z); qy[i] = wrap_add(y[hy ? i : 0].pos, oy[i].z);
+    lx[i] = ex && qx[i] >= ox[i].w;   // graph.cc:577
+    ly[i] = ey && qy[i] >= oy[i].w;
+    orx[i] = (int)((x[hx ? i : 0].w >> 29) & 1u); ory[i] = (int)((y[hy ? i : 0].w >> 29) & 1u);
+  }
+  bool order = false;
+  if (N1 > 1) {   // duplicate placement: identical payload -> dropped, different payload -> the order decides
+    const bool dup = lx[0] && lx[1] && wx[0] == wx[1] && qx[0] == qx[1];
+    const bool same = ((x[0].w ^ x[1].w) >> kPackKeyBits) == 0u;
+    order |= dup && !same;
+    lx[1] = lx[1] && !dup;
+  }
+  if (N2 > 1) {
+    const bool dup = ly[0] && ly[1] && wy[0] == wy[1] && qy[0] == qy[1];
+    const bool same = ((y[0].w ^ y[1].w) >> kPackKeyBits) == 0u;
+    order |= dup && !same;
+    ly[1] = ly[1] && !dup;
+  }
+  bool ok[2][2];
+  int dist[2][2];
+  int nt = 0;
+#pragma unroll
+  for (int i = 0; i < N1; i++) {
+#pragma unroll
+    for (int j = 0; j < N2; j++) {
+      const bool fwd = qx[i] < qy[j];
+      const int d = fwd ? qy[j] - qx[i] + l2 : qx[i] - qy[j] + l1;   // graph.cc:1866-1875
+      const bool term = lx[i] && ly[j] && wx[i] == wy[j] && orx[i] != ory[j] && orx[i] == (fwd ? 0 : 1);
+      nt += term ? 1 : 0;
+      ok[i][j] = term && (unsigned)d < (unsigned)P.ins_n;
+      dist[i][j] = ok[i][j] ? d : 0;
+    }
+  }
+  double t[2][2];
+#pragma unroll
+  for (int i = 0; i < N1; i++) {
+#pragma unroll
+    for (int j = 0; j < N2; j++) t[i][j] = __dmul_rn(__dmul_rn(px[i], py[j]), __ldg(P.ins_tab + dist[i][j]));   // (p1*p2)*ins
+  }
+  // at most two terms survive below: 0 + a + b in any order is the same double, and absent terms are exact zeros
+  acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < N1; i++) {
+#pragma unroll
+    for (int j = 0; j < N2; j++) acc = __dadd_rn(acc, ok[i][j] ? t[i][j] : 0.0);
+  }
+  return multi ? 0 : ((order || nt > 2) ? -1 : 1);
+}
+
+// Tier-2 phase from the packed entries: tiles of 256 list entries, a block's first tile is its own index.
+__device__ __forceinline__ void tier2_packed_tiles(const ScoreParams& P, int* s_tile, Acc& sum, unsigned& floored) {
+  const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
+  const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
+  const uint4* __restrict__ pk = static_cast<const uint4*>(P.t2pack);
+  const int n_tiles = (P.n_main + kBlock - 1) / kBlock;
+  int tile = blockIdx.x, buf = 0;
+  for (; tile < n_tiles; __syncthreads(), tile = s_tile[buf], buf ^= 1) {
+    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 2, 1u);
+    const int k = tile * kBlock + (int)threadIdx.x;
+    if (k >= P.n_main) continue;
+    int cls = 0;
+#pragma unroll
+    for (int c = 1; c < 5; c++) cls += (k >= P.class_begin[c]) ? 1 : 0;
+    const uint32_t j = (uint32_t)(k - P.class_begin[cls]);
+    int r, st;
+    uint32_t ll;
+    double acc = 0.0, thr;
+    if (cls < 3) {
+      const uint32_t n_c = (uint32_t)(P.class_begin[cls + 1] - P.class_begin[cls]);
+      const uint4* base = pk + P.t2base[cls];
+      const uint4 u0 = ldg_stream(base + j), u1 = ldg_stream(base + n_c + j);
+      r = (int)u0.x;
+      ll = u0.y;
+      if (cls == 0) {
+        const Rec8 x[2] = {rec8(u0.z, u0.w), rec8(u0.z, u0.w)}, y[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)};
+        st = tier2_packed_read<1, 2>(P, sa1, sa2, x, y, ll, acc, thr);
+      } else if (cls == 1) {
+        const Rec8 x[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)}, y[2] = {rec8(u0.z, u0.w), rec8(u0.z, u0.w)};
+        st = tier2_packed_read<2, 1>(P, sa1, sa2, x, y, ll, acc, thr);
+      } else {
+        const uint4 u2 = ldg_stream(base + 2 * n_c + j);
+        const Rec8 x[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)}, y[2] = {rec8(u2.x, u2.y), rec8(u2.z, u2.w)};
+        st = tier2_packed_read<2, 2>(P, sa1, sa2, x, y, ll, acc, thr);
+      }
+    } else {   // (0,2), (2,0): no pair term
+      const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);
+      r = dsc.x;
+      ll = (uint32_t)dsc.y;
+      st = 1;
+      thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
+    }
+    if (st > 0) {
+      P.values[r] = acc;
+      acc_add(sum, floored_term(P, log_tab, acc, thr, floored));
+    } else if (st < 0) {
+      push_overflow(P, r);
+    }
+  }
+}
+
 // Rare-shape phase of the streaming kernel: the listed reads with three or more records on a mate (list entries
 // [n_main, n_complex)). Their records are walked in a loop — row from the compact copy, then its slot word — keeping
 // at most two live, distinct placements per mate, which is what nearly all of them have in any one evaluation (most of
@@ -1142,7 +1285,8 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
   if (P.n_main > 0) {
     __syncthreads();   // s_tile is shared with the rare-shape phase
     tl_begin(P.timeline, kTlTier2);
-    tier2_tiles(P, s_tile, sum, floored);
+    if (!kCov && P.t2pack) tier2_packed_tiles(P, s_tile, sum, floored);
+    else tier2_tiles(P, s_tile, sum, floored);
     tl_end(P.timeline, kTlTier2);
   }
   if (!P.chain_first) pdl_wait();
@@ -2310,6 +2454,53 @@ __global__ void pack_pairs_kernel(const int4* first1, const int4* first2, int n,
   v.w = (uint32_t)b.y;
   out[r] = v;
 }
+// Packs the tier-2 list's classes (1,2), (2,1), (2,2) (see tier2_packed_tiles); *bad != 0 when a record does not fit.
+__global__ void pack_tier2_kernel(const int4* cdesc, const RowShort* rows1, const RowShort* rows2, int n_entries, int b1, int b2,
+                                  uint32_t cb1_0, uint32_t cb1_1, uint32_t cb1_2, uint32_t cb2_0, uint32_t cb2_1, uint32_t cb2_2,
+                                  uint32_t tb0, uint32_t tb1, uint32_t tb2, uint4* out, uint32_t* bad) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_entries) return;
+  const int cls = (k >= b1 ? 1 : 0) + (k >= b2 ? 1 : 0);
+  const int cb = cls == 0 ? 0 : (cls == 1 ? b1 : b2);
+  const uint32_t n_c = (uint32_t)((cls == 0 ? b1 : (cls == 1 ? b2 : n_entries)) - cb);
+  const uint32_t j = (uint32_t)(k - cb);
+  const int n1 = cls == 0 ? 1 : 2, n2 = cls == 1 ? 1 : 2;
+  const uint32_t r1 = (cls == 0 ? cb1_0 : (cls == 1 ? cb1_1 : cb1_2)) + (uint32_t)n1 * j;
+  const uint32_t r2 = (cls == 0 ? cb2_0 : (cls == 1 ? cb2_1 : cb2_2)) + (uint32_t)n2 * j;
+  const uint32_t tb = cls == 0 ? tb0 : (cls == 1 ? tb1 : tb2);
+  bool unfit = false;
+  auto pack = [&](const RowShort& rw, uint32_t& a, uint32_t& b) {
+    const uint32_t ed = (uint32_t)rw.edor & 0xffffu;
+    if (rw.key < 0 || (uint32_t)rw.key > kPackKeyMask || ed > kPackEdMask) unfit = true;
+    a = ((uint32_t)rw.key & kPackKeyMask) | ((ed & kPackEdMask) << kPackKeyBits) | ((((uint32_t)rw.edor >> 30) & 1u) << 29);
+    b = (uint32_t)rw.pos;
+  };
+  const int4 dsc = cdesc[k];
+  uint4 u0, u1, u2;
+  u0.x = (uint32_t)dsc.x; u0.y = (uint32_t)dsc.y; u0.z = u0.w = 0u;
+  const RowShort x0 = rows1[r1], x1 = rows1[r1 + (n1 > 1 ? 1 : 0)], y0 = rows2[r2], y1 = rows2[r2 + (n2 > 1 ? 1 : 0)];
+  if (cls == 0) {
+    pack(x0, u0.z, u0.w); pack(y0, u1.x, u1.y); pack(y1, u1.z, u1.w);
+  } else if (cls == 1) {
+    pack(y0, u0.z, u0.w); pack(x0, u1.x, u1.y); pack(x1, u1.z, u1.w);
+  } else {
+    pack(x0, u1.x, u1.y); pack(x1, u1.z, u1.w); pack(y0, u2.x, u2.y); pack(y1, u2.z, u2.w);
+    out[tb + 2 * n_c + j] = u2;
+  }
+  out[tb + j] = u0;
+  out[tb + n_c + j] = u1;
+  if (unfit) *bad = 1u;
+}
+void launch_pack_tier2(const void* cdesc, const void* rows1, const void* rows2, const int32_t* class_begin, const uint32_t cbase[2][5],
+                       const uint32_t tbase[3], void* out, uint32_t* bad, cudaStream_t st) {
+  const int n = class_begin[3];
+  if (n > 0)
+    pack_tier2_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(cdesc), static_cast<const RowShort*>(rows1),
+                                                       static_cast<const RowShort*>(rows2), n, class_begin[1], class_begin[2],
+                                                       cbase[0][0], cbase[0][1], cbase[0][2], cbase[1][0], cbase[1][1], cbase[1][2],
+                                                       tbase[0], tbase[1], tbase[2], static_cast<uint4*>(out), bad);
+}
+
 void launch_pack_pairs(const void* first1, const void* first2, int n, void* out, uint32_t* bad, cudaStream_t st) {
   if (n > 0)
     pack_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2), n,

@@ -50,6 +50,8 @@ cudaError_t build_csr(const void* arena, size_t n_records, int n_reads, bool is_
 cudaError_t build_complex_list(const void* first1, const void* first2, int n_reads, uint32_t* flags, uint32_t* list,
                                void* temp, size_t temp_bytes, cudaStream_t st, int* launches, uint32_t* n_complex_out,
                                int32_t* class_begin);
+void launch_pack_tier2(const void* cdesc, const void* rows1, const void* rows2, const int32_t* class_begin, const uint32_t cbase[2][5],
+                       const uint32_t tbase[3], void* out, uint32_t* bad, cudaStream_t st);
 void launch_pack_pairs(const void* first1, const void* first2, int n, void* out, uint32_t* bad, cudaStream_t st);
 void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,
                        void* desc, cudaStream_t st);
