@@ -375,9 +375,11 @@ def main():
     # at the two boundaries of the streaming pass; the kernels themselves are identical)
     pc.set_profiling(2)
     full_step_device()
-    ker_ms = 0.0
+    ker_ms, ker_list = 0.0, []
     for _ in range(args.steps):
-        ker_ms += full_step_device()[1]
+        ker_list.append(full_step_device()[1])
+        ker_ms += ker_list[-1]
+    ker_list.sort()
     # device timeline of one more step: globaltimer stamps at each kernel's first block start / last block end
     # (no events, chain and graph intact) — shows how the kernels of an evaluation overlap
     pc.set_profiling(3)
@@ -501,7 +503,7 @@ def main():
                    "parallelism": f"read-id shards x{world}; the ranks' 64-byte result lines are written by the kernels' last blocks into a host shared-memory segment every rank reads (no collective call on the path)"},
         "roofline": {"bound": "hbm", "kernel": "paired_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps,
+                     "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps, "kernel_ms_median": ker_list[len(ker_list) // 2], "kernel_ms_min": ker_list[0], "kernel_ms_max": ker_list[-1],
                      "timing": f"CUDA events around the streaming pass (tier 1 + tier 2 kernels) on the library stream, {args.steps} extra "
                                "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
         "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),

@@ -2172,15 +2172,11 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 // stream the 16-byte first records; everything else the packed pairs.
 using StreamKernel = void (*)(const ScoreParams);
 StreamKernel stream_kernel(bool cov, bool packed) {
-  static const int v = [] { const char* e = getenv("GAML_STREAM_VARIANT"); return e ? atoi(e) : 0; }();   // EXPERIMENT
+  // 4 resident blocks of 256 threads (64 registers), two reads per lane and tile. Measured alternatives that were no
+  // faster (profiles/r01_summary.md): 5 blocks at 48 registers (spills), four reads per lane, 128-thread blocks,
+  // warp-drawn tiles (with and without cp.async staging), the gathered tables in shared memory.
   if (cov) return paired_stream_kernel<true, false, 4, 2>;
-  if (!packed || v == 9) return paired_stream_kernel<false, false, 4, 2>;
-  switch (v) {
-    case 1: return paired_stream_kernel<false, true, 5, 2>;
-    case 2: return paired_stream_kernel<false, true, 4, 4>;
-    case 3: return paired_stream_kernel<false, true, 6, 2>;
-    default: return paired_stream_kernel<false, true, 4, 2>;
-  }
+  return packed ? paired_stream_kernel<false, true, 4, 2> : paired_stream_kernel<false, false, 4, 2>;
 }
 
 template <class K>
