@@ -1,1 +1,1 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/r01_bench_2gpu.json 2> gpurun_out/r01_bench_2gpu.log
+timeout 300 python tools/host_overhead.py > gpurun_out/host_overhead.txt 2>&1
