@@ -88,6 +88,7 @@ struct MateView {
 struct ScoreParams {
   MateView m[2];
   const uint32_t* lens;      // single/pacbio: read length; paired: len1 | len2<<16
+  const void* comb;          // paired: per mate-1 key {SlotA of that key, SlotA of the SAME key in mate 2's store} (32 B), or null
   const void* pairs;         // paired: one PackedPair (16 B) per pair for the streaming kernel's tier 1, or null (kernels.cu)
   uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
   int32_t lens_uniform;

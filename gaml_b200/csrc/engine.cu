@@ -162,6 +162,8 @@ struct ReadSetState {
   MateStore mate[2];
   DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
+  DevBuf d_comb, d_partner12, d_partner21;   // paired: combined first slot words by mate-1 key id + the key maps (kernels.cu)
+  bool comb_ok = false;
   DevBuf d_t2pack;              // paired: packed tier-2 entries (kernels.cu), valid when t2pack_ok
   bool t2pack_ok = false;
   uint32_t t2base[3] = {0, 0, 0};
@@ -242,6 +244,7 @@ struct gaml_ctx {
   std::vector<int32_t> node_len, nmap;
   std::vector<std::unique_ptr<ReadSetState>> sets;
   std::vector<MateStore*> stores;
+  StoreTables h_tables{};         // the same pointers by value, valid when stores.size() <= kInlineStores
   DevBuf d_tables;                // SlotA* per store, then SlotB* per store
   bool tables_dirty = true;
   DevBuf d_blob;                  // per-evaluation staging (updates, occurrences, touch ranges, set_begin)
@@ -658,11 +661,33 @@ int commit(gaml_ctx* ctx) {
       rs.pairs_ok = false;
       uint32_t pack_bad = 0;
       if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0) {
+        // key maps between the two mates' stores (same node sequence) and the combined slot table
+        {
+          MateStore &s1 = rs.mate[0], &s2 = rs.mate[1];
+          std::vector<int32_t> p12(std::max<size_t>(s1.keys.size(), 1), -1), p21(std::max<size_t>(s2.keys.size(), 1), -1);
+          for (const auto& kv : s1.key_ids) {
+            auto it = s2.key_ids.find(kv.first);
+            if (it != s2.key_ids.end()) {
+              p12[kv.second] = it->second;
+              p21[it->second] = kv.second;
+            }
+          }
+          const void* old_comb = rs.d_comb.p;
+          const void* old_p21 = rs.d_partner21.p;
+          CU(rs.d_partner12.reserve(p12.size() * 4, 0, false, ctx->stream));
+          CU(rs.d_partner21.reserve(p21.size() * 4, 0, false, ctx->stream));
+          CU(cudaMemcpyAsync(rs.d_partner12.p, p12.data(), p12.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+          CU(cudaMemcpyAsync(rs.d_partner21.p, p21.data(), p21.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+          CU(rs.d_comb.reserve(p12.size() * 2 * sizeof(SlotA), 0, true, ctx->stream));
+          CU(cudaStreamSynchronize(ctx->stream));   // p12 / p21 are locals
+          if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21 || !rs.comb_ok) ctx->tables_dirty = true;
+          rs.comb_ok = true;
+        }
         // tier 1's packed copy of both mates' first records (16 B per pair instead of 2 x 16 B + lengths)
         CU(rs.d_pairs.reserve((size_t)rs.n_local * 16, 0, false, ctx->stream));
         uint32_t* bad = static_cast<uint32_t*>(ctx->d_csr_temp.p);   // scratch, free after build_csr / the list build
         CU(cudaMemsetAsync(bad, 0, 4, ctx->stream));
-        launch_pack_pairs(rs.mate[0].first.p, rs.mate[1].first.p, rs.n_local, rs.d_pairs.p, bad, ctx->stream);
+        launch_pack_pairs(rs.mate[0].first.p, rs.mate[1].first.p, rs.n_local, rs.d_partner12.as<int32_t>(), rs.d_pairs.p, bad, ctx->stream);
         launches++;
         pack_bad = 1;
         CU(cudaMemcpyAsync(&pack_bad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -693,9 +718,30 @@ int commit(gaml_ctx* ctx) {
     }
   }
   if (ctx->tables_dirty) {
-    std::vector<void*> tabs;   // [SlotA* per store][SlotB* per store]
+    std::vector<void*> tabs;   // [SlotA* per store][SlotB* per store][combined-table base per store][its key map per store]
     for (MateStore* s : ctx->stores) tabs.push_back(s->slots_a.p);
     for (MateStore* s : ctx->stores) tabs.push_back(s->slots_b.p);
+    std::vector<void*> cbase(ctx->stores.size(), nullptr), cmap(ctx->stores.size(), nullptr);
+    for (auto& rsp2 : ctx->sets) {
+      ReadSetState& r2 = *rsp2;
+      if (!r2.comb_ok || r2.n_mates != 2) continue;
+      for (size_t i = 0; i < ctx->stores.size(); i++) {
+        if (ctx->stores[i] == &r2.mate[0]) cbase[i] = r2.d_comb.p;
+        if (ctx->stores[i] == &r2.mate[1]) {
+          cbase[i] = r2.d_comb.as<SlotA>() + 1;
+          cmap[i] = r2.d_partner21.p;
+        }
+      }
+    }
+    for (void* q : cbase) tabs.push_back(q);
+    for (void* q : cmap) tabs.push_back(q);
+    ctx->h_tables = StoreTables{};
+    for (size_t i = 0; i < ctx->stores.size() && i < (size_t)kInlineStores; i++) {
+      ctx->h_tables.a[i] = ctx->stores[i]->slots_a.as<SlotA>();
+      ctx->h_tables.b[i] = ctx->stores[i]->slots_b.as<SlotB>();
+      ctx->h_tables.cb[i] = static_cast<SlotA*>(cbase[i]);
+      ctx->h_tables.cm[i] = static_cast<const int32_t*>(cmap[i]);
+    }
     CU(ctx->d_tables.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(void*), 0, false, ctx->stream));
     if (!tabs.empty())
       CU(cudaMemcpyAsync(ctx->d_tables.p, tabs.data(), tabs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
@@ -1007,6 +1053,7 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   }
   P.lens = rs.d_lens.as<uint32_t>();
   P.pairs = rs.pairs_ok ? rs.d_pairs.p : nullptr;
+  P.comb = rs.pairs_ok && rs.comb_ok ? rs.d_comb.p : nullptr;
   P.lens_uniform = rs.lens_uniform ? 1 : 0;
   P.uniform_ll = rs.uniform_ll;
   P.ins_tab = rs.d_ins.as<double>();
@@ -1152,7 +1199,9 @@ int launch(gaml_ctx* ctx) {
   if (record) set_launch_recorder(&chain);
   else if (ctx->timed) CU(cudaEventRecord(ctx->ev[0], st));
   launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates, ctx->d_tables.as<SlotA*>(),
-                     ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->epoch, ctx->d_flags.as<unsigned long long>(),
+                     ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->d_tables.as<SlotA*>() + 2 * ctx->stores.size(),
+                     ctx->d_tables.as<const int32_t*>() + 3 * ctx->stores.size(),
+                     ctx->stores.size() <= (size_t)kInlineStores ? &ctx->h_tables : nullptr, ctx->epoch, ctx->d_flags.as<unsigned long long>(),
                      (int)flags_words(n_sets), ctx->timeline ? ctx->d_timeline.as<unsigned long long>() : nullptr, st);
   launches++;
   int64_t records = 0, reads = 0, bytes = 0;

@@ -42,7 +42,12 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 }
 // PackedPair (16 B per pair, built at cache commit when every record fits): what tier 1 of the streaming kernel needs of
 // a pair's two first records — x = key1 | edit1<<22 | orient1<<29 | none1<<30 | tier2<<31, y = the same for mate 2
-// (bit 31 unused), z = pos1, w = pos2. tier2 = some mate owns two or more records (the read is on the static list).
+// (bit 31: both mates under the same key, see apply_slots_kernel), z = pos1, w = pos2. tier2 = some mate owns two or more records (the read is on the static list).
+// 256-bit read-only load (sm_100: LDG.E.256): one request, one L1 tag lookup per distinct line for both halves
+__device__ __forceinline__ void ldg256(const uint4* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 constexpr int kPackKeyBits = 22;
 constexpr uint32_t kPackKeyMask = (1u << kPackKeyBits) - 1u;
 constexpr uint32_t kPackEdMask = 0x7fu;
@@ -1075,7 +1080,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
     if (!kPacked) u2[j] = ldg_stream(src2 + qi[j]);
   }
   int key1[kR], key2[kR], pos1[kR], pos2[kR], e1[kR], e2[kR], xo[kR], yo[kR];
-  bool has1[kR], has2[kR], tier2[kR];
+  bool has1[kR], has2[kR], tier2[kR], same[kR];
   uint32_t ll[kR];
   if (P.lens_uniform) {
 #pragma unroll
@@ -1097,6 +1102,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       has1[j] = ((pr.x >> 30) & 1u) == 0u;
       has2[j] = ((pr.y >> 30) & 1u) == 0u;
       tier2[j] = (pr.x >> 31) != 0u;
+      same[j] = (pr.y >> 31) != 0u;
       pos1[j] = (int)pr.z;
       pos2[j] = (int)pr.w;
     }
@@ -1114,6 +1120,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       xo[j] = (rw1.z >> 30) & 1;
       yo[j] = (rw2.z >> 30) & 1;
       tier2[j] = (((rw1.z | rw2.z) >> 17) & 0x1fff) != 0;   // count >= 2 on a mate
+      same[j] = false;
       pos1[j] = rw1.y;
       pos2[j] = rw2.y;
     }
@@ -1121,10 +1128,26 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
   // level 2: slot words of both keys, pow tables, floor threshold (L1/L2 resident)
   int4 o1[kR], o2[kR];
   double pa[kR], pb[kR], thr[kR];
+  if (kPacked && P.comb) {
+    // one 256-bit gather per read: {mate 1's slot word, the same key's word in mate 2's store}; the few pairs whose mates
+    // lie under different keys take mate 2's word from its own table (predicated second gather)
+    const uint4* __restrict__ comb = static_cast<const uint4*>(P.comb);
 #pragma unroll
-  for (int j = 0; j < kR; j++) {
-    o1[j] = __ldg(sa1 + key1[j]);
-    o2[j] = __ldg(sa2 + key2[j]);
+    for (int j = 0; j < kR; j++) {
+      uint4 a, b;
+      ldg256(comb + 2 * key1[j], a, b);
+      o1[j] = make_int4((int)a.x, (int)a.y, (int)a.z, (int)a.w);
+      o2[j] = make_int4((int)b.x, (int)b.y, (int)b.z, (int)b.w);
+    }
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+      if (!same[j]) o2[j] = __ldg(sa2 + key2[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      o1[j] = __ldg(sa1 + key1[j]);
+      o2[j] = __ldg(sa2 + key2[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < kR; j++) {
@@ -2021,8 +2044,14 @@ __global__ void __launch_bounds__(128) pacbio_alnprob_kernel(const AlnProbParams
 }
 
 // ---- per-evaluation tables, reduction of partials -------------------------------------------
-__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                                   unsigned long long* flags, int n_flag_words, unsigned long long* timeline) {
+// comb_base[store] / comb_map[store]: paired sets keep a second copy of the first slot word in a table indexed by MATE 1's
+// key id that holds, side by side, the word of that key in mate 1's store and the word of the same key (same node
+// sequence) in mate 2's store (base + 1, index through the mate-2 -> mate-1 key map): tier 1 of the streaming kernel
+// fetches both with one 256-bit gather for the pairs whose mates lie under the same key (nearly all of them).
+template <bool kInline>
+__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+                                   const int32_t* const* comb_map, const StoreTables T, uint32_t epoch, unsigned long long* flags,
+                                   int n_flag_words, unsigned long long* timeline) {
   pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   tl_begin(timeline, kTlApply);
@@ -2042,8 +2071,14 @@ __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* t
   b.n_occ = u.n_occ;
   b.occ_begin = u.occ_begin;
   b.pad = 0;
-  tab_a[u.store][u.key] = a;
-  tab_b[u.store][u.key] = b;
+  (kInline ? T.a[u.store] : tab_a[u.store])[u.key] = a;
+  (kInline ? T.b[u.store] : tab_b[u.store])[u.key] = b;
+  SlotA* cb = kInline ? T.cb[u.store] : comb_base[u.store];
+  if (cb) {
+    const int32_t* mp = kInline ? T.cm[u.store] : comb_map[u.store];
+    const int idx = mp ? mp[u.key] : u.key;
+    if (idx >= 0) cb[2 * idx] = a;
+  }
   tl_end(timeline, kTlApply);
 }
 
@@ -2233,6 +2268,7 @@ void pack_arg(PendingLaunch& pl, size_t& off, const T& v) {
 template <class... KArgs, class... Args>
 void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args&&... args) {
   static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
+  static_assert(sizeof...(KArgs) <= sizeof(PendingLaunch::arg_ptrs) / sizeof(void*), "too many kernel arguments");
   static_assert((sizeof(KArgs) + ... + 0) + 16 * sizeof...(KArgs) <= sizeof(PendingLaunch::arg_buf), "argument buffer too small");
   PendingLaunch local;
   LaunchList* rec = g_recorder;
@@ -2251,10 +2287,16 @@ void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st
   issue_launch(pl, st);
 }
 
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                        unsigned long long* flags, int n_flag_words, unsigned long long* timeline, cudaStream_t st) {
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+                        const int32_t* const* comb_map, const StoreTables* inline_tabs, uint32_t epoch, unsigned long long* flags,
+                        int n_flag_words, unsigned long long* timeline, cudaStream_t st) {
   const int m = n > n_flag_words ? n : n_flag_words;
-  launch_chain(apply_slots_kernel, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, epoch, flags, n_flag_words, timeline);
+  if (inline_tabs)
+    launch_chain(apply_slots_kernel<true>, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, comb_base, comb_map, *inline_tabs,
+                 epoch, flags, n_flag_words, timeline);
+  else
+    launch_chain(apply_slots_kernel<false>, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, comb_base, comb_map, StoreTables{},
+                 epoch, flags, n_flag_words, timeline);
 }
 
 // Every wrapper below appends its kernels to the evaluation's chain. `chained` = the operation before it on `st` is a
@@ -2434,7 +2476,7 @@ void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_r
 
 // Packs the two dense first-record arrays of a paired set into PackedPair; *bad != 0 afterwards when some record does not
 // fit (key >= 2^22 or edit distance > 127) and the set keeps streaming the 16-byte records.
-__global__ void pack_pairs_kernel(const int4* first1, const int4* first2, int n, uint4* out, uint32_t* bad) {
+__global__ void pack_pairs_kernel(const int4* first1, const int4* first2, int n, const int32_t* partner12, uint4* out, uint32_t* bad) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int4 a = ldg4(first1 + r), b = ldg4(first2 + r);
@@ -2445,7 +2487,9 @@ __global__ void pack_pairs_kernel(const int4* first1, const int4* first2, int n,
   const uint32_t tier2 = ((((uint32_t)a.z | (uint32_t)b.z) >> 17) & 0x1fffu) != 0u ? 1u : 0u;
   uint4 v;
   v.x = (k1 & kPackKeyMask) | ((ed1 & kPackEdMask) << kPackKeyBits) | ((((uint32_t)a.z >> 30) & 1u) << 29) | ((none1 ? 1u : 0u) << 30) | (tier2 << 31);
-  v.y = (k2 & kPackKeyMask) | ((ed2 & kPackEdMask) << kPackKeyBits) | ((((uint32_t)b.z >> 30) & 1u) << 29) | ((none2 ? 1u : 0u) << 30);
+  // bit 31 of y: both mates lie under the same key (mate 2's key is the partner of mate 1's): one combined slot gather
+  const uint32_t same = (partner12 && !none1 && !none2 && partner12[k1] == (int32_t)k2) ? 1u : 0u;
+  v.y = (k2 & kPackKeyMask) | ((ed2 & kPackEdMask) << kPackKeyBits) | ((((uint32_t)b.z >> 30) & 1u) << 29) | ((none2 ? 1u : 0u) << 30) | (same << 31);
   v.z = (uint32_t)a.y;
   v.w = (uint32_t)b.y;
   out[r] = v;
@@ -2497,10 +2541,10 @@ void launch_pack_tier2(const void* cdesc, const void* rows1, const void* rows2, 
                                                        tbase[0], tbase[1], tbase[2], static_cast<uint4*>(out), bad);
 }
 
-void launch_pack_pairs(const void* first1, const void* first2, int n, void* out, uint32_t* bad, cudaStream_t st) {
+void launch_pack_pairs(const void* first1, const void* first2, int n, const int32_t* partner12, void* out, uint32_t* bad, cudaStream_t st) {
   if (n > 0)
     pack_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first1), static_cast<const int4*>(first2), n,
-                                                       static_cast<uint4*>(out), bad);
+                                                       partner12, static_cast<uint4*>(out), bad);
 }
 
 void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,

@@ -14,7 +14,7 @@ struct PendingLaunch {
   unsigned grid = 1, block = 1;
   bool pdl = false;
   int n_args = 0;
-  void* arg_ptrs[10];
+  void* arg_ptrs[16];
   alignas(16) unsigned char arg_buf[1536];
 };
 struct LaunchList {
@@ -29,8 +29,19 @@ enum { kGridPairedFull = 0, kGridPairedComplex, kGridPairedTotal, kGridSingleFul
 int score_grid(int which, int n_items, int sm_count);
 int overflow_grid(int sm_count);
 
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, uint32_t epoch,
-                        unsigned long long* flags, int n_flag_words, unsigned long long* timeline, cudaStream_t st);
+// Per-store table pointers passed BY VALUE (kernel parameter space) when a context has at most kInlineStores mate stores:
+// apply_slots then needs no dependent load to find a store's tables. a/b: first/second slot words; cb/cm: the combined
+// table of a paired set and the mate-2 -> mate-1 key map (see apply_slots_kernel).
+constexpr int kInlineStores = 8;
+struct StoreTables {
+  SlotA* a[kInlineStores];
+  SlotB* b[kInlineStores];
+  SlotA* cb[kInlineStores];
+  const int32_t* cm[kInlineStores];
+};
+void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+                        const int32_t* const* comb_map, const StoreTables* inline_tabs, uint32_t epoch, unsigned long long* flags,
+                        int n_flag_words, unsigned long long* timeline, cudaStream_t st);
 constexpr int kTimelineWords = 12;   // profiling level 2: {start, end} ns of apply, tier 1, tier 2, many-placement, delta, total
 // Each wrapper appends the kernels of one read set to the evaluation's chain on `st` (programmatic dependent
 // launches, kernels.cu): streaming pass (tier 1, tier 2), many-placement pass, per-set finalize in the last block.
@@ -52,7 +63,7 @@ cudaError_t build_complex_list(const void* first1, const void* first2, int n_rea
                                int32_t* class_begin);
 void launch_pack_tier2(const void* cdesc, const void* rows1, const void* rows2, const int32_t* class_begin, const uint32_t cbase[2][5],
                        const uint32_t tbase[3], void* out, uint32_t* bad, cudaStream_t st);
-void launch_pack_pairs(const void* first1, const void* first2, int n, void* out, uint32_t* bad, cudaStream_t st);
+void launch_pack_pairs(const void* first1, const void* first2, int n, const int32_t* partner12, void* out, uint32_t* bad, cudaStream_t st);
 void launch_cdesc_fill(const uint32_t* list, int n_complex, const uint32_t* lens, const uint32_t* cptr1, const uint32_t* cptr2,
                        void* desc, cudaStream_t st);
 cudaError_t compact_offsets(const uint32_t* list, int n_complex, const uint32_t* rowptr, uint32_t* cptr, const uint32_t* lens,
