@@ -671,51 +671,10 @@ __device__ __forceinline__ void push_overflow(const ScoreParams& P, int r) {
 }
 
 // FULL, tier 1 (the streaming kernel): every read of the shard is re-scored from an empty state and the total
-// is reduced in the same pass (CalcScoreForPathsNew on a fresh ScoringState + GetTotalProb).
-// A warp reads 32 consecutive first-records of each mate (two coalesced 512-byte requests) plus the packed
-// lengths; all three loads are issued before anything depends on them, then the two key slots. Reads that
-// own more than one record on a mate are a STATIC property of the cache: they are skipped here (idle lanes,
-// no divergent code) and handled densely by tier 2 from a list built at commit time. A key that occurs
-// several times in this evaluation (repeat node) sends the read to the scratch path.
-// Pair term of a tier-1 read (one record per mate). Every table access that does not depend on another table is
-// issued up front (both key slots, the four pow-table entries), so a read costs three memory round trips: the
-// coalesced first-records, the slot/pow batch, the insert-pdf entry. sa1/sa2 are the packed 16-byte slot words
-// {epoch|multi<<31, walk, cur_pos, skip_below} (L1/L2 resident). Returns false when the read is not tier 1's to
-// score (tier-2 read, or a key with several occurrences -> paired_multi_kernel).
-__device__ __forceinline__ bool paired_simple_acc(const ScoreParams& P, const int4* __restrict__ sa1,
-                                                  const int4* __restrict__ sa2, int r, const int4& rw1, const int4& rw2,
-                                                  uint32_t ll, double& acc) {
-  acc = 0.0;
-  if ((((rw1.z | rw2.z) >> 17) & 0x1fff) != 0) return false;   // count >= 2 on a mate: tier 2
-  const int l1 = ll & 0xffff, l2 = ll >> 16;
-  const int4 o1 = __ldg(sa1 + max(rw1.x, 0)), o2 = __ldg(sa2 + max(rw2.x, 0));   // key -1 (no record) reads slot 0, ignored below
-  const int e1 = rw1.z & 0xffff, e2 = rw2.z & 0xffff;
-  const double a1 = __ldg(P.m[0].pow_mismatch + e1), b1 = __ldg(P.m[0].pow_match + (l1 - e1));
-  const double a2 = __ldg(P.m[1].pow_mismatch + e2), b2 = __ldg(P.m[1].pow_match + (l2 - e2));
-  const uint32_t f1 = (uint32_t)o1.x, f2 = (uint32_t)o2.x;
-  const bool live1 = rw1.x >= 0 && (f1 & 0x7fffffffu) == P.epoch, live2 = rw2.x >= 0 && (f2 & 0x7fffffffu) == P.epoch;
-  // a record under a key that occurs several times in this evaluation: the read belongs to paired_multi_kernel, which
-  // enumerates exactly the records of those keys (either mate), so it is skipped here, not listed
-  if ((live1 && (f1 >> 31)) || (live2 && (f2 >> 31))) return false;
-  if (!live1 || !live2) return true;
-  const int p1 = wrap_add(rw1.y, o1.z), p2 = wrap_add(rw2.y, o2.z);
-  if (p1 < o1.w || p2 < o2.w || o1.y != o2.y) return true;   // skip rule (graph.cc:577); pairs only inside one walk
-  const int xo = (rw1.z >> 30) & 1, yo = (rw2.z >> 30) & 1;
-  if (xo == yo) return true;                                   // graph.cc:1864
-  int d;
-  if (p1 < p2) {
-    if (xo != 0) return true;
-    d = p2 - p1 + l2;                                          // graph.cc:1866-1870
-  } else {
-    if (xo != 1) return true;
-    d = p1 - p2 + l1;                                          // graph.cc:1871-1875
-  }
-  const double ins = ((unsigned)d < (unsigned)P.ins_n) ? __ldg(P.ins_tab + d) : 0.0;
-  const double t = __dmul_rn(__dmul_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2)), ins);   // (p1*p2)*ins, graph.cc:1889
-  emit_cov(P, o1.y, p1, p2, l2, t);
-  acc = (o1.y < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
-  return true;
-}
+// is reduced in the same pass (CalcScoreForPathsNew on a fresh ScoringState + GetTotalProb); the tile body is
+// tier1_body below. Reads that own more than one record on a mate are a STATIC property of the cache: they are skipped
+// there (idle lanes, no divergent code) and handled densely by tier 2 from a list built at commit time. A key that occurs
+// several times in this evaluation (repeat node) leaves the read to paired_multi_kernel.
 
 // FULL, tier 2 (second phase of the streaming kernel): the reads that own exactly two records on a mate and at most two on the other — (1,2), (2,1), (2,2)
 // and the pairless (0,2), (2,0) — from a list built once per cache commit, class ordered, so a warp holds reads of ONE
@@ -1056,7 +1015,8 @@ __device__ __forceinline__ void rare_tiles(const ScoreParams& P, int* s_tile, Ac
 
 // Tier-1 tile body: kR reads per lane of one warp tile, every step written without branches so that the kR
 // dependent chains (first records -> {slot words, pow tables, threshold} -> insert pdf -> products -> quotient -> log)
-// are issued side by side: one trip per memory level for all of them. Filters of paired_simple_acc become predicates
+// are issued side by side: one trip per memory level for all of them. The filters of the pair term (liveness, skip rule
+// graph.cc:577, one walk, orientation/order graph.cc:1864-1875, insert-table range) are predicates
 // (a dropped pair is a term of +0.0, which is what the state holds for such a read); the two rare fix-ups (IEEE division
 // next to the floor threshold, libm log for 0/denormal/non-finite) are taken once, after the common work of all kR reads.
 template <bool kCov, bool kPacked, int kR>
