@@ -90,6 +90,8 @@ struct ScoreParams {
   const uint32_t* lens;      // single/pacbio: read length; paired: len1 | len2<<16
   const void* comb;          // paired: per mate-1 key {SlotA of that key, SlotA of the SAME key in mate 2's store} (32 B), or null
   const void* pairs;         // paired: one PackedPair (16 B) per pair for the streaming kernel's tier 1, or null (kernels.cu)
+  const double* uni_prob[2]; // paired, lens_uniform: per mate mismatch^e * match^(len-e) for e in [0,128), host-computed (same rounding), or null
+  double uni_thr;            //   and the floor threshold of every pair
   uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
   int32_t lens_uniform;
   const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)

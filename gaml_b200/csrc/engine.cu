@@ -162,6 +162,8 @@ struct ReadSetState {
   MateStore mate[2];
   DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
+  DevBuf d_uni_prob[2];           // paired, uniform lengths: alignment probability by edit distance, per mate (kernels.cu)
+  double uni_thr = 0.0;
   DevBuf d_comb, d_partner12, d_partner21;   // paired: combined first slot words by mate-1 key id + the key maps (kernels.cu)
   bool comb_ok = false;
   DevBuf d_t2pack;              // paired: packed tier-2 entries (kernels.cu), valid when t2pack_ok
@@ -1056,6 +1058,8 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.comb = rs.pairs_ok && rs.comb_ok ? rs.d_comb.p : nullptr;
   P.lens_uniform = rs.lens_uniform ? 1 : 0;
   P.uniform_ll = rs.uniform_ll;
+  for (int m = 0; m < 2; m++) P.uni_prob[m] = rs.lens_uniform && rs.d_uni_prob[m].p ? rs.d_uni_prob[m].as<double>() : nullptr;
+  P.uni_thr = rs.uni_thr;
   P.ins_tab = rs.d_ins.as<double>();
   P.ins_n = rs.ins_n;
   P.thr_tab = rs.d_thr.as<double>();
@@ -1937,6 +1941,22 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     for (int l = 0; l <= top; l++) thr[l] = exp(cfg->min_prob_start + cfg->min_prob_per_base * (l));   // graph.cc:1506-1507, 1528
     CU(rs.d_thr.reserve(thr.size() * 8, 0, false, ctx->stream));
     CU(cudaMemcpyAsync(rs.d_thr.p, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (paired && rs.lens_uniform) {
+      // every pair has the same lengths: tabulate mismatch^e * match^(len-e) (graph.cc:1859-1863; one IEEE product, the
+      // same double the device forms with __dmul_rn) for the edit distances the packed records can hold
+      const int l[2] = {(int)(rs.uniform_ll & 0xffff), (int)(rs.uniform_ll >> 16)};
+      for (int m = 0; m < 2; m++) {
+        const MateStore& st = rs.mate[m];
+        std::vector<double> tab(128, 0.0);
+        for (int e = 0; e < 128; e++)
+          if (e <= l[m] && (size_t)e < st.pow_mismatch.size() && (size_t)(l[m] - e) < st.pow_match.size())
+            tab[e] = st.pow_mismatch[e] * st.pow_match[l[m] - e];
+        CU(rs.d_uni_prob[m].reserve(tab.size() * 8, 0, false, ctx->stream));
+        CU(cudaMemcpyAsync(rs.d_uni_prob[m].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // tab is a local
+      }
+      rs.uni_thr = thr[l[0] + l[1]];
+    }
   } else {
     rs.floor_a = log(exp(cfg->min_prob_start));      // logdouble(exp(mps)), graph.cc:3075
     rs.floor_b = log(exp(cfg->min_prob_per_base));   // logdouble(exp(mppb)), graph.cc:3076

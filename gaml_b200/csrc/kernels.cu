@@ -1109,12 +1109,23 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       o2[j] = __ldg(sa2 + key2[j]);
     }
   }
+  if (kPacked && P.uni_prob[0]) {
+    // set-uniform lengths: the alignment probability depends on the edit distance alone (one table entry per mate
+    // instead of two entries and a product) and the threshold is a kernel parameter
 #pragma unroll
-  for (int j = 0; j < kR; j++) {
-    const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
-    pa[j] = __dmul_rn(__ldg(P.m[0].pow_mismatch + e1[j]), __ldg(P.m[0].pow_match + (l1 - e1[j])));
-    pb[j] = __dmul_rn(__ldg(P.m[1].pow_mismatch + e2[j]), __ldg(P.m[1].pow_match + (l2 - e2[j])));
-    thr[j] = __ldg(P.thr_tab + l1 + l2);
+    for (int j = 0; j < kR; j++) {
+      pa[j] = __ldg(P.uni_prob[0] + e1[j]);
+      pb[j] = __ldg(P.uni_prob[1] + e2[j]);
+      thr[j] = P.uni_thr;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
+      pa[j] = __dmul_rn(__ldg(P.m[0].pow_mismatch + e1[j]), __ldg(P.m[0].pow_match + (l1 - e1[j])));
+      pb[j] = __dmul_rn(__ldg(P.m[1].pow_mismatch + e2[j]), __ldg(P.m[1].pow_match + (l2 - e2[j])));
+      thr[j] = __ldg(P.thr_tab + l1 + l2);
+    }
   }
   bool mine[kR], ok[kR];
   int dist[kR], px[kR], py[kR];
