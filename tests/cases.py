@@ -158,7 +158,37 @@ def golden_cases():
         "synth_mixed": synth.mixed_workload(8, 5000, 600, 80, n_single=300, n_evals=12, seed=23, pacbio_len=4000),
         "synth_paired_penalty": _with_penalty(synth.paired_workload(12, 2500, 350, n_evals=30, seed=24)),
         "synth_pacbio_penalty": _with_pacbio_penalty(synth.mixed_workload(8, 5000, 300, 60, n_evals=10, seed=25, pacbio_len=4000)),
+        "synth_paired_bigedit": paired_big_edit(8, 2500, 700, n_evals=10, seed=26),
+        "synth_paired_ragged": paired_ragged(8, 2000, 700, n_evals=10, seed=27),
     }
+
+
+def paired_big_edit(n_unique: int, unique_len: int, n_pairs: int, n_evals: int, seed: int) -> Workload:
+    """250 bp pairs with some edit distances of 128 and more: such records do not fit the 16-byte packed pairs / 8-byte
+    packed tier-2 records of the streaming kernel (7 bits of edit distance), so the set streams the plain records."""
+    wl = synth.paired_workload(n_unique, unique_len, n_pairs, n_evals=n_evals, seed=seed, read_len=250, insert_mean=600.0,
+                               insert_std=40.0)
+    bumped = 0
+    for cache in wl.sets[0].caches:
+        for key in sorted(cache.keys()):
+            recs = cache[key]
+            if len(recs) and bumped < 40:
+                recs["edit_dist"][0] = 128 + bumped      # still <= read length + 6
+                bumped += 1
+    assert bumped >= 10
+    return wl
+
+
+def paired_ragged(n_unique: int, unique_len: int, n_pairs: int, n_evals: int, seed: int) -> Workload:
+    """Per-pair lengths differ: the packed records are used, lengths / pow tables / thresholds come from their arrays."""
+    wl = synth.paired_workload(n_unique, unique_len, n_pairs, n_evals=n_evals, seed=seed)
+    spec = wl.sets[0]
+    rng = np.random.default_rng(seed)
+    for m, step in ((0, 3), (1, 5)):
+        lens = np.asarray(spec.read_len[m]).copy()
+        lens[::step] -= rng.integers(1, 20, size=len(lens[::step])).astype(lens.dtype)
+        spec.read_len[m] = lens
+    return wl
 
 
 def _with_pacbio_penalty(wl: Workload, step: float = 700.0) -> Workload:
