@@ -5,14 +5,21 @@
   python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path (oracle/_ref)
 
 A step = one full log-likelihood evaluation (`ProbCalculator::CalcProb` on a fresh ScoringState,
-prob_calculator.h:63-109) of BASELINE config 2: synthetic 4.6 Mbp genome, 2 M innie read pairs 2x100 bp,
-insert 300+-30, injected alignment cache. With N GPUs every rank holds a config-2-sized read-id shard of an
-N-times larger genome/read set (weak scaling); partial log-likelihoods (exact 128-bit sums) are all-gathered over NCCL.
+prob_calculator.h:63-109).
+  N = 1: BASELINE config 2 — synthetic 4.6 Mbp genome, 2 M innie read pairs 2x100 bp, insert 300+-30, injected cache.
+  N > 1: BASELINE config 4 — the 100 Mbp / 10 000-node genome with 6.25 M read pairs (one eighth of the 50 M) per GPU,
+         sharded by read id: N = 8 is the whole of config 4, N = 2 / 4 the same genome at a quarter / half of the coverage
+         (weak scaling: the per-GPU shard is fixed).
+Every rank scores its shard; the ranks' 64-byte result lines are exchanged by the evaluation's own kernels over NVLink
+peer memory (--exchange peer, default), a host shared-memory segment (host) or one ncclAllReduce (nccl), and every rank
+combines them exactly.
 
-One JSON line on stdout (rank 0). `value` is device time with all inputs resident in HBM (CUDA events on the
-library's stream, L2 flushed between steps); `e2e` is the same metric through gaml_calc_prob with host
-buffers in and out, wall clock. `roofline` is the dominant kernel against the measured HBM copy peak.
-The incremental (delta) evaluations of the annealing loop are reported beside it as `sa_iters_per_s`.
+One JSON line on stdout (rank 0). `value` is device time with all inputs resident in HBM — CUDA events around each
+evaluation's kernel chain on the library's stream, which for N > 1 ends with the kernel that has received every rank's
+line, i.e. the exchange is INSIDE the timed region; L2 flushed between steps, all ranks released together after the
+flush. `e2e` is the same metric through gaml_calc_prob_partial / gaml_calc_prob_gathered with host buffers in and out,
+wall clock. `roofline` is the dominant kernel of this rank against the measured HBM copy peak. The incremental (delta)
+evaluations of the annealing loop are reported beside it as `sa_iters_per_s`.
 """
 from __future__ import annotations
 
@@ -143,17 +150,6 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("paired_stream_kernel_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
-
-
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
@@ -213,15 +209,36 @@ def run_cpu(wl, n_procs: int, repeats: int, tmp: str):
     return secs.max(axis=0), aligns, kind
 
 
+def workload_kind(args, world: int) -> str:
+    return args.workload if args.workload != "auto" else ("c2" if world == 1 else "c4shard")
+
+
+def config_for(kind: str, world: int, scale: float = 1.0) -> dict:
+    """The `config` object of the JSON line — identical for both arms."""
+    if kind == "c2":
+        name = WORKLOAD_NAME + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else "")
+        pairs = int(C2["n_pairs"] * scale) * world
+    else:
+        name = (f"C4: synthetic 100 Mbp genome (10000 x ~10 kbp nodes + 3 repeat nodes x2), innie read pairs 2x100 bp, insert 300+-30, "
+                f"edit distance 0-2, 10% of mates with a second alignment; one walk per long node; {C4['n_pairs'] // 8} read pairs "
+                f"(1/8 of config 4's 50 M) per GPU, sharded by read id over {world} GPU(s)" + (" = the whole of config 4" if world == 8 else ""))
+        pairs = (C4["n_pairs"] // 8) * world
+    return {"workload": name, "step": "one full logL evaluation (CalcProb on a fresh ScoringState)", "read_pairs": pairs,
+            "parallelism": f"read-id shards x{world}" if world > 1 else "one GPU"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
     n_procs = max(1, min(cores, 64))
-    wl, _ = make_workload(1, 0, 1, scale=args.scale)
+    kind = workload_kind(args, world)
+    # the job's workload is `world` shards; the CPU scores shard 0 of it as the bounded sample (a rate, not a total)
+    wl, _ = make_workload(world, 0, 1, scale=args.scale, kind=kind)
     with tempfile.TemporaryDirectory() as tmp:
-        per_step, aligns, kind = run_cpu(wl, n_procs, args.steps + args.warmup, tmp)
+        per_step, aligns, kind_cpu = run_cpu(wl, n_procs, args.steps + args.warmup, tmp)
     timed = per_step[args.warmup:]
     total = float(timed.sum())
     value = aligns * len(timed) / total
@@ -229,16 +246,59 @@ def reference_arm(args):
         "impl": "reference", "metric": "alignments_scored_per_s", "value": value, "unit": "alignments/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
-                   "alignments_per_step": aligns},
-        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": n_procs, "kind": kind,
-                         "sample": f"whole C2 workload split into {n_procs} contiguous read-id blocks, one single-threaded "
-                                   f"reference process per block, {len(timed)} timed full evaluations each; step time = slowest process"},
+        "config": config_for(kind, world, args.scale),
+        "alignments_per_step": aligns,
+        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": n_procs, "kind": kind_cpu,
+                         "sample": (f"one GPU's shard of the workload ({wl.sets[0].n_reads} read pairs) split into {n_procs} contiguous read-id "
+                                    f"blocks, one single-threaded reference process per block, {len(timed)} timed full evaluations each; "
+                                    "step time = slowest process; the rate stands for the whole job (the CPU's cores are busy either way)")},
         "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def ncu_traffic(kind: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture of THIS workload, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kind, {}).get("paired_stream_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def make_candidates(base, n, rng):
+    """BASELINE config 5's mix: 40 % extend, 30 % interchange, 30 % disconnect, each on 1-2 walks of `base`."""
+    cands = []
+    multi = [i for i, w in enumerate(base) if sum(1 for x in w if x >= 0) >= 2]
+    for _ in range(n):
+        u = rng.random()
+        if u < 0.4 or not multi:                                   # extend: join two walks (sometimes with a gap)
+            i, j = (int(x) for x in rng.choice(len(base), size=2, replace=False))
+            mid = [-int(rng.integers(1, 400))] if rng.random() < 0.3 else []
+            cands.append(([i, j], [list(base[i]) + mid + list(base[j])]))
+        elif u < 0.7:                                              # interchange: swap the tails of two walks
+            i = multi[int(rng.integers(len(multi)))]
+            j = int(rng.integers(len(base)))
+            if j == i:
+                j = (j + 1) % len(base)
+            ci = int(rng.integers(1, len(base[i])))
+            cj = int(rng.integers(0, len(base[j]) + 1))
+            a, b = list(base[i][:ci]) + list(base[j][cj:]), list(base[j][:cj]) + list(base[i][ci:])
+            ok = all(w and w[0] >= 0 and w[-1] >= 0 for w in (a, b))
+            cands.append(([i, j], [a, b]) if ok else ([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
+        else:                                                      # disconnect: split one walk
+            i = multi[int(rng.integers(len(multi)))]
+            nodes_pos = [t for t in range(1, len(base[i])) if base[i][t] >= 0 and base[i][t - 1] >= 0]
+            if not nodes_pos:
+                cands.append(([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
+            else:
+                cut = nodes_pos[int(rng.integers(len(nodes_pos)))]
+                cands.append(([i], [list(base[i][:cut]), list(base[i][cut:])]))
+    return cands
 
 
 # ------------------------------------------------------------------------------------------------
@@ -250,12 +310,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gaml_b200", choices=["gaml_b200", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = config 2)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the c2 workload (debug only; 1.0 = config 2)")
     ap.add_argument("--delta-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4shard"], help="c2 (default, BASELINE config 2 per GPU) or one "
-                    "eighth of config 4 per GPU")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4shard"],
+                    help="auto (default): config 2 on one GPU, one eighth of config 4 per GPU on several")
     ap.add_argument("--batch", type=int, default=1024, help="candidate moves per gaml_calc_prob_batch launch (0 = skip)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "host", "nccl"],
+                    help="how the ranks' result lines meet (N > 1): NVLink peer memory, host shared memory, ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaml_b200" else args.warmup
 
@@ -265,7 +327,6 @@ def main():
     import torch
     import torch.distributed as dist
     from gaml_b200 import api
-    from gaml_b200.dist import PartialGatherer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,55 +360,79 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    kind = workload_kind(args, world)
     t_gen = time.perf_counter()
     n_evals = 2 + args.delta_steps
-    wl, shard = make_workload(world, rank, n_evals, scale=args.scale, kind=args.workload)
+    wl, shard = make_workload(world, rank, n_evals, scale=args.scale, kind=kind)
     t_gen = time.perf_counter() - t_gen
     pc, t_upload, cache_bytes = load_calculator(wl, shard, local_rank, world, dev)
-    log(f"[rank {rank}] workload generated in {t_gen:.1f}s; cache of {cache_bytes / 1e6:.1f} MB inserted+CSR built in {t_upload:.2f}s")
+    log(f"[rank {rank}] workload {kind} generated in {t_gen:.1f}s; cache of {cache_bytes / 1e6:.1f} MB inserted+CSR built in {t_upload:.2f}s")
     walks0 = wl.evals[0]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     flush_view = flush.view(torch.int32)
     flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
 
-    def full_step_device():
-        """One full evaluation; returns (device ms of the evaluation's kernels, ms of the dominant kernel)."""
-        pc.reset_state()
-        pc.prepare(walks0)
+    exchange_name = None
+    if world > 1:
+        from gaml_b200 import dist as gdist
+        if args.exchange != "nccl":
+            gdist.NcclExchange(rank, world).attach(pc)   # the communicator also serves the candidate batches; attached first:
+                                                         # a kernel-fused exchange attached after it takes over the result lines
+        if args.exchange == "peer":
+            gdist.PeerExchange(rank, world).attach(pc)
+            exchange_name = ("NVLink peer memory: the block that completes a read set stores its 64-byte result line into every rank's "
+                             "exchange buffer; the chain's last kernel waits for all ranks' lines (inside the timed region)")
+        elif args.exchange == "nccl":
+            gdist.NcclExchange(rank, world).attach(pc)
+            exchange_name = "one ncclAllReduce(sum, fp64) of the ranks' result lines per evaluation on the library's stream"
+        else:
+            gdist.ResultExchange(rank, world).attach(pc)
+            exchange_name = "host shared-memory segment written by the kernels' last blocks, read by every rank's host"
+    flat0 = api.FlatWalks(walks0)
+
+    def flush_l2():
         flush.fill_(1)            # write > L2 ...
         flush_sink.copy_(flush_view.sum())   # ... then read it back so L2 is left holding CLEAN foreign lines
         torch.cuda.synchronize()
-        pc.launch()
-        part, tl = pc.finish()
-        st = pc.stats()
-        return st.last_device_ms, st.last_score_kernel_ms, part, tl
 
-    gather = PartialGatherer(api.PARTIAL_DOUBLES * len(wl.sets), dev)   # torch all-gather: only for the candidate batches
-    exchange = None
-    if world > 1:
-        # the ranks' 64-byte result lines meet in a host shared-memory segment the kernels write into directly
-        from gaml_b200.dist import ResultExchange
-        exchange = ResultExchange(rank, world)
-        exchange.attach(pc)
-    flat0 = api.FlatWalks(walks0)
+    def rendezvous():
+        """All ranks leave together AFTER their own flush: a step's clock never contains another rank's flush."""
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def finish_all():
+        if world > 1:
+            g, tl = pc.finish_gathered()
+            return g, tl
+        part, tl = pc.finish()
+        return part[None, :], tl
+
+    def full_step_device():
+        """One full evaluation, inputs resident: (device ms of the evaluation's chain incl. the exchange, ms of the
+        dominant kernel, gathered partials, total_len)."""
+        pc.reset_state()
+        pc.prepare(walks0)
+        flush_l2()
+        rendezvous()
+        pc.launch()
+        g, tl = finish_all()
+        st = pc.stats()
+        return st.last_device_ms, st.last_score_kernel_ms, g, tl
 
     def eval_all_ranks(fw):
         """One evaluation through the C ABI, all ranks' partials combined: (prob, zeros, total_len)."""
-        if exchange is not None:
+        if world > 1:
             g, tl = pc.calc_prob_gathered_flat(fw)
             return pc.combine(g, world, tl)
         part, tl = pc.calc_prob_partial_flat(fw)
         return pc.combine(part[None, :], 1, tl)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
 
-    def flush_l2():
-        flush.fill_(1)
-        flush_sink.copy_(flush_view.sum())
-        torch.cuda.synchronize()
-
     def full_step_e2e():
-        """(wall seconds of the C-ABI call + collective + combine, result); reset and L2 flush are outside the clock."""
+        """(wall seconds of the C-ABI call incl. the exchange + combine, result); reset, L2 flush and the rendezvous are outside."""
         pc.reset_state()
         flush_l2()
+        rendezvous()
         t0 = time.perf_counter()
         res = eval_all_ranks(flat0)
         return time.perf_counter() - t0, res
@@ -365,11 +450,12 @@ def main():
         sampler.start()
     dev_ms = 0.0
     for _ in range(args.steps):
-        d, _k, part, tl = full_step_device()
-        dev_ms += d
+        d, _k, g_full, tl = full_step_device()
+        dev_ms += max_over_ranks(d) if world > 1 else d   # per step: the slowest rank's chain (they end together anyway)
     barrier()
     st = pc.stats()
     launches = st.kernel_launches - launches0
+    a_local, bytes_local = st.last_records_gathered, st.last_algorithmic_bytes
     # roofline timing of the streaming pass: the same steps again with the library's per-kernel events switched on
     # (an event between two kernels serialises them, so the chained launches of the timed region above are given up
     # at the two boundaries of the streaming pass; the kernels themselves are identical)
@@ -387,27 +473,26 @@ def main():
     full_step_device()
     timeline = {k: [round(a, 2), round(b, 2)] for k, (a, b) in pc.read_timeline().items()}
     pc.set_profiling(0)
-    a_local, bytes_local = st.last_records_gathered, st.last_algorithmic_bytes
+    st = pc.stats()
     full_overflow_reads = {"multi_pass_items": int(st.last_multi_items), "many_placement_pass_reads": int(st.last_overflow_reads),
                            "scratch_placements": int(st.last_scratch_placements)}
-    dev_ms_max = max_over_ranks(dev_ms)
     a_total = sum_over_ranks(float(a_local))
 
-    # ---- e2e: host walks in, host result out, wall clock, collective included ----
+    # ---- e2e: host walks in, host result out, wall clock, exchange included ----
     for _ in range(args.warmup):
         full_step_e2e()
     barrier()
     e2e_s = 0.0
     for _ in range(args.steps):
-        barrier()
         dt, (prob, zeros, tl_full) = full_step_e2e()
         e2e_s += max_over_ranks(dt)
     barrier()
     clocks = sampler.stop()
     st = pc.stats()
     h2d, d2h = st.last_h2d_bytes, st.last_d2h_bytes
+    prep_full_us = st.last_prepare_host_us
 
-    # ---- incremental evaluations of the annealing loop (delta kernel + O(R) pass) ----
+    # ---- incremental evaluations of the annealing loop (delta kernel + O(R) pass), ranks in lockstep ----
     pc.reset_state()
     full_step_e2e()
     seq = wl.evals[1:1 + args.delta_steps]
@@ -424,56 +509,27 @@ def main():
     pc.reset_state()
     full_step_e2e()
     pc.set_profiling(1)
-    delta_dev_ms, touched = 0.0, 0
+    delta_dev_ms, touched, delta_bytes, prep_us = 0.0, 0, 0, 0.0
     for nodes_offs in seq_flat:
         eval_all_ranks(nodes_offs)
         s2 = pc.stats()
         delta_dev_ms += s2.last_device_ms
         touched += s2.last_records_gathered
+        delta_bytes += s2.last_algorithmic_bytes
+        prep_us += s2.last_prepare_host_us
     pc.set_profiling(0)
-    delta_bytes = pc.stats().last_algorithmic_bytes
 
     # ---- BASELINE config 5: 1024 candidate moves scored per launch against the current state (stateless) ----
     base = seq[-1] if seq else walks0
-    rng = np.random.default_rng(123)
-    cands = []
-    multi = [i for i, w in enumerate(base) if sum(1 for x in w if x >= 0) >= 2]
-    for k in range(args.batch):
-        u = rng.random()
-        if u < 0.4 or not multi:                                   # extend: join two walks (sometimes with a gap)
-            i, j = (int(x) for x in rng.choice(len(base), size=2, replace=False))
-            mid = [-int(rng.integers(1, 400))] if rng.random() < 0.3 else []
-            cands.append(([i, j], [list(base[i]) + mid + list(base[j])]))
-        elif u < 0.7:                                              # interchange: swap the tails of two walks
-            i = multi[int(rng.integers(len(multi)))]
-            j = int(rng.integers(len(base)))
-            if j == i:
-                j = (j + 1) % len(base)
-            ci = int(rng.integers(1, len(base[i])))
-            cj = int(rng.integers(0, len(base[j]) + 1))
-            a, b = list(base[i][:ci]) + list(base[j][cj:]), list(base[j][:cj]) + list(base[i][ci:])
-            ok = all(w and w[0] >= 0 and w[-1] >= 0 for w in (a, b))
-            cands.append(([i, j], [a, b]) if ok else ([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
-        else:                                                      # disconnect: split one walk
-            i = multi[int(rng.integers(len(multi)))]
-            nodes_pos = [t for t in range(1, len(base[i])) if base[i][t] >= 0 and base[i][t - 1] >= 0]
-            if not nodes_pos:
-                cands.append(([i], [[(x ^ 1) if x >= 0 else x for x in reversed(base[i])]]))
-            else:
-                cut = nodes_pos[int(rng.integers(len(nodes_pos)))]
-                cands.append(([i], [list(base[i][:cut]), list(base[i][cut:])]))
     batch_info = None
     if args.batch > 0:
+        cands = make_candidates(base, args.batch, np.random.default_rng(123))
         packed = pc.pack_candidates(cands)
-        gather_b = PartialGatherer(args.batch * api.PARTIAL_DOUBLES * len(wl.sets), dev)
-        kinds = [s_.kind for s_ in wl.sets]
+
         def run_batch():
             if world == 1:   # one GPU: the library combines (gaml_calc_prob_batch), as a host caller would use it
                 return list(pc.calc_prob_batch_packed(packed)[0])
-            part, tls = pc.calc_prob_batch_partial_packed(packed)
-            g = gather_b(part.reshape(-1)).reshape(world, args.batch, len(wl.sets), api.PARTIAL_DOUBLES)
-            return [api.combine_partials_raw(g[:, c], kinds, [s_.n_reads for s_ in wl.sets], [s_.weight for s_ in wl.sets], int(tls[c]))[0]
-                    for c in range(args.batch)]
+            return list(pc.calc_prob_batch_gathered_packed(packed)[0])   # one all-reduce of all candidates' partials inside the library
         run_batch()
         launches_b0 = pc.stats().kernel_launches
         barrier()
@@ -486,30 +542,31 @@ def main():
                       "mix": "40% extend / 30% interchange / 30% disconnect on the walk set reached after the incremental run",
                       "kernel_launches_per_batch": int((pc.stats().kernel_launches - launches_b0) / 3),
                       "best_candidate_prob": float(max(batch_probs)),
-                      "note": "gaml_calc_prob_batch (N=1) / gaml_calc_prob_batch_partial + all-gather + combine (N>1): host arrays in, scores out, wall clock; "
-                              "each score is bit-identical to a sequential gaml_calc_prob of that candidate"}
+                      "note": "gaml_calc_prob_batch (N=1) / gaml_calc_prob_batch_gathered (N>1: one ncclAllReduce of all candidates' exact partials inside the library): "
+                              "host arrays in, scores out, wall clock; each score is bit-identical to a sequential gaml_calc_prob of that candidate"}
 
     peak, peak_src = measured_peak()
     achieved = bytes_local / (ker_ms / args.steps * 1e-3) / 1e9
+    cfg = config_for(kind, world, args.scale)
     line = {
-        "metric": "alignments_scored_per_s", "value": a_total * args.steps / (dev_ms_max * 1e-3), "unit": "alignments/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "metric": "alignments_scored_per_s", "value": a_total * args.steps / (dev_ms * 1e-3), "unit": "alignments/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (WORKLOAD_NAME if args.workload == "c2" else
-                                "C4 shard: synthetic 100 Mbp genome (10000 x ~10 kbp nodes), 6.25 M of 50 M innie read pairs 2x100 bp") + (f" — per GPU; {world} GPUs hold {world}x the genome and reads, sharded by read id" if world > 1 else ""),
-                   "step": "one full logL evaluation (CalcProb on a fresh ScoringState)",
-                   "alignments_per_step": int(a_total), "read_pairs": int(wl.sets[0].n_reads),
-                   "l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)", "timing": "CUDA events around each evaluation (recorded as nodes of its CUDA graph on the library stream), max over ranks",
-                   "parallelism": f"read-id shards x{world}; the ranks' 64-byte result lines are written by the kernels' last blocks into a host shared-memory segment every rank reads (no collective call on the path)"},
+        "config": cfg,
+        "alignments_per_step": int(a_total),
+        "measurement": {"l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)",
+                        "timing": "CUDA events around each evaluation's kernel chain (nodes of its CUDA graph on the library stream); N > 1: all ranks "
+                                  "released together after their flush, the chain ends with the exchange's gather kernel, per step the max over ranks",
+                        "exchange": exchange_name},
         "roofline": {"bound": "hbm", "kernel": "paired_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(kind), "peak_source": peak_src, "per": "GPU (rank 0's shard)",
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps, "kernel_ms_median": ker_list[len(ker_list) // 2], "kernel_ms_min": ker_list[0], "kernel_ms_max": ker_list[-1],
-                     "timing": f"CUDA events around the streaming pass (tier 1 + tier 2 kernels) on the library stream, {args.steps} extra "
+                     "timing": f"CUDA events around the streaming kernel (rare shapes + tier 1 + tier 2, one launch) on the library stream, {args.steps} extra "
                                "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
         "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "note": "gaml_calc_prob_partial (N=1) / gaml_calc_prob_gathered (N>1, every rank's result line through the shared segment) + exact combine: host walk arrays in, score out, wall clock per step "
-                        "(max over ranks), L2 flushed between steps; "
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps, "host_prepare_us": prep_full_us,
+                "note": "gaml_calc_prob_partial (N=1) / gaml_calc_prob_gathered (N>1, the exchange included) + exact combine: host walk arrays in, "
+                        "score out, wall clock per step (max over ranks), L2 flushed between steps, ranks released together after the flush; "
                         "the alignment cache is resident state like the reference's aligment_cache_"},
         "gpu_launches": int(launches),
         "device_timeline_us": timeline,
@@ -518,10 +575,10 @@ def main():
         "sa_iters_per_s": len(seq) / delta_s,
         "incremental": {"evals": len(seq), "e2e_ms_per_eval": 1e3 * delta_s / max(len(seq), 1),
                         "device_ms_per_eval": delta_dev_ms / max(len(seq), 1), "touched_alignments_per_eval": touched / max(len(seq), 1),
-                        "algorithmic_bytes_last_eval": int(delta_bytes),
+                        "algorithmic_bytes_per_eval": delta_bytes / max(len(seq), 1), "host_prepare_us_per_eval": prep_us / max(len(seq), 1),
                         "evals_without_O(R)_pass": int(delta_only),
-                        "note": "each evaluation = gaml_calc_prob_partial on host walk arrays (+ all-gather, combine), wall clock; an "
-                                "evaluation whose total length equals the previous one's swaps the touched reads' terms in the exact "
+                        "note": "each evaluation = gaml_calc_prob_partial / gaml_calc_prob_gathered on host walk arrays (+ combine), wall clock, ranks in "
+                                "lockstep; an evaluation whose total length equals the previous one's swaps the touched reads' terms in the exact "
                                 "running total instead of re-summing all reads"},
         "batch": batch_info,
         "cache_upload": {"seconds": t_upload, "bytes": int(cache_bytes)},
@@ -529,13 +586,13 @@ def main():
     }
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        # bounded CPU sample on the box's host: the reference's own scorer, 1 core, whole C2, a few full evaluations
+        # bounded CPU sample on the box's host: the reference's own scorer, 1 core, the whole workload, a few full evaluations
         with tempfile.TemporaryDirectory() as tmp:
             t0 = time.perf_counter()
-            per_step, aligns, kind = run_cpu(wl, 1, 5, tmp)
-            log(f"cpu baseline ({kind}) took {time.perf_counter() - t0:.1f}s")
+            per_step, aligns, kind_cpu = run_cpu(wl, 1, 5, tmp)
+            log(f"cpu baseline ({kind_cpu}) took {time.perf_counter() - t0:.1f}s")
         line["cpu_baseline"] = {"value": aligns * len(per_step) / float(per_step.sum()), "unit": "alignments/s", "cores": 1,
-                                "kind": kind, "sample": "whole C2 workload, 5 full evaluations on one core (the reference is single-threaded)"}
+                                "kind": kind_cpu, "sample": f"whole {kind} workload, 5 full evaluations on one core (the reference is single-threaded)"}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -56,7 +56,8 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_calc_prob_batch", "gaml_calc_prob_batch_partial",
            "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline", "gaml_set_result_exchange",
            "gaml_eval_finish_gathered", "gaml_calc_prob_gathered", "gaml_cache_save", "gaml_cache_load",
-           "gaml_pacbio_alignment_logprob"]
+           "gaml_pacbio_alignment_logprob", "gaml_peer_exchange_create", "gaml_peer_exchange_open", "gaml_peer_exchange_close",
+           "gaml_nccl_unique_id", "gaml_nccl_exchange_init", "gaml_calc_prob_batch_gathered"]
 
 _lib = None
 
@@ -107,6 +108,12 @@ def load_library() -> C.CDLL:
     lib.gaml_eval_finish_gathered.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.gaml_calc_prob_gathered.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double),
                                             C.POINTER(C.c_int32)]
+    lib.gaml_calc_prob_batch_gathered.argtypes = [vp, C.c_int32, i32p, i64p, i32p, i64p, i64p, dp, i32p, i32p]
+    lib.gaml_peer_exchange_create.argtypes = [vp, C.c_int32, C.c_int32, vp, C.POINTER(vp)]
+    lib.gaml_peer_exchange_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.gaml_peer_exchange_close.argtypes = [vp]
+    lib.gaml_nccl_unique_id.argtypes = [vp]
+    lib.gaml_nccl_exchange_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream"):
             getattr(lib, name).restype = C.c_int
@@ -347,6 +354,18 @@ class ProbCalculator:
                                                   probs.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls), _p32(zeros)))
         return probs, tls
 
+    def calc_prob_batch_gathered_packed(self, packed):
+        """gaml_calc_prob_batch_gathered: every rank's shard, one all-reduce, exact combine -> (probs [n], total_lens [n])."""
+        n, er_a, er_off, nodes, w_off, ca_off = packed
+        probs = np.zeros(n, dtype=np.float64)
+        tls = np.zeros(n, dtype=np.int32)
+        zeros = np.zeros(n * 2 * max(len(self.sets), 1), dtype=np.int32)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self.lib.gaml_calc_prob_batch_gathered(self.h, n, _p32(er_a), er_off.ctypes.data_as(i64p), _p32(nodes),
+                                                           w_off.ctypes.data_as(i64p), ca_off.ctypes.data_as(i64p),
+                                                           probs.ctypes.data_as(C.POINTER(C.c_double)), _p32(tls), _p32(zeros)))
+        return probs, tls
+
     def calc_prob_batch(self, candidates):
         """candidates: list of (erased base-walk indices, added walks). -> (probs [n], total_lens [n], zeros [n][sets])."""
         n = len(candidates)
@@ -387,6 +406,38 @@ class ProbCalculator:
         ns = max(len(self.sets), 1)
         g = np.zeros(world * ns * PARTIAL_DOUBLES, dtype=np.float64)
         self._gath = (g, g.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def _gather_buffers(self, world: int) -> None:
+        self._exch_world = world
+        ns = max(len(self.sets), 1)
+        g = np.zeros(world * ns * PARTIAL_DOUBLES, dtype=np.float64)
+        self._gath = (g, g.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def peer_exchange_create(self, rank: int, world: int):
+        """gaml_peer_exchange_create -> (this rank's cudaIpcMemHandle_t as 64 bytes, its device pointer)."""
+        handle = (C.c_char * 64)()
+        ptr = C.c_void_p()
+        self._check(self.lib.gaml_peer_exchange_create(self.h, rank, world, C.cast(handle, C.c_void_p), C.byref(ptr)))
+        return bytes(handle), ptr.value
+
+    def peer_exchange_open(self, handles: Optional[Sequence[bytes]] = None, local_ptrs: Optional[Sequence[Optional[int]]] = None) -> None:
+        """handles: every rank's 64-byte IPC handle (rank order); local_ptrs: device pointers of contexts in THIS process."""
+        world = len(handles) if handles is not None else len(local_ptrs)
+        hb = b"".join(handles) if handles is not None else None
+        arr = None
+        if local_ptrs is not None:
+            arr = (C.c_void_p * world)(*[C.c_void_p(p) if p else C.c_void_p() for p in local_ptrs])
+        self._check(self.lib.gaml_peer_exchange_open(self.h, hb, arr))
+        self._gather_buffers(world)
+
+    def peer_exchange_close(self) -> None:
+        self._check(self.lib.gaml_peer_exchange_close(self.h))
+
+    def nccl_exchange_init(self, unique_id: Optional[bytes], rank: int, world: int) -> None:
+        """gaml_nccl_exchange_init: unique_id = 128 bytes from nccl_unique_id() of ONE rank, broadcast to all (None detaches)."""
+        self._check(self.lib.gaml_nccl_exchange_init(self.h, unique_id, rank, world))
+        if unique_id is not None:
+            self._gather_buffers(world)
 
     def clear_result_exchange(self) -> None:
         if getattr(self, "_exch_keep", None) is not None:
@@ -453,6 +504,15 @@ class ProbCalculator:
         s = Stats()
         self._check(self.lib.gaml_get_stats(self.h, C.byref(s)))
         return s
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId for gaml_nccl_exchange_init (call on one rank, broadcast)."""
+    buf = (C.c_char * 128)()
+    rc = load_library().gaml_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc < 0:
+        raise GamlError(f"gaml_nccl_unique_id failed ({rc}): {load_library().gaml_last_error(None).decode()}")
+    return bytes(buf)
 
 
 def combine_partials_raw(gathered: np.ndarray, kinds: Sequence[int], n_reads_total: Sequence[int],

@@ -65,11 +65,16 @@ struct PlcLong {
 struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one touched mate-1 key
 
 constexpr int kAccumStride = 8;   // per set, u64: four 32-bit limbs of the exact 128-bit sum, floored, -inf terms, nan terms, spare
+constexpr int kBatchBin = 5;      // batch base pass, per bin, u64: low / high 32-bit lanes of sum(Q - qthr), reads, -inf, nan
 constexpr int kOutStride = 6;     // per set, f64: integer part, 2^-40 units, floored, -inf terms, nan terms, flags
 constexpr unsigned long long kResultSeal = 0x5eed5eed5eed5eedull;   // word 7 = seal ^ xor of words 0..6
 constexpr int kResultStride = 8;  // per set in the host-mapped result buffer (one 64-byte line): the kOutStride values,
                                   // the epoch of the evaluation that wrote them (the host's completion flag), a checksum
 struct Double2 { double x, y; };  // {1/c, -log(1/c)} entries of the log table
+// One entry of a uniform-length paired set's term table: the pair term (p1*p2)*ins for (edit 1, edit 2, insert distance)
+// and its fixed-point logarithm (kTermOdd when the logarithm is not finite).
+struct TermEntry { double t; long long q; };
+constexpr long long kTermOdd = (long long)0x8000000000000000ull;
 
 struct MateView {
   const void* first;         // short stores: dense int4 per read {key, pos, edor | count<<16, row offset}; key<0 = none
@@ -91,12 +96,23 @@ struct ScoreParams {
   const void* comb;          // paired: per mate-1 key {SlotA of that key, SlotA of the SAME key in mate 2's store} (32 B), or null
   const void* pairs;         // paired: one PackedPair (16 B) per pair for the streaming kernel's tier 1, or null (kernels.cu)
   const double* uni_prob[2]; // paired, lens_uniform: per mate mismatch^e * match^(len-e) for e in [0,128), host-computed (same rounding), or null
-  double uni_thr;            //   and the floor threshold of every pair
+  double uni_pstar;          //   and the floor test / floored term of every pair (see pstar_tab / qthr_tab)
+  long long uni_qthr;
+  const void* tq;            // paired, lens_uniform: TermEntry[1 + (e1 << tq_shift | e2) * ins_n + dist] for e1, e2 < 1 << tq_shift
+  int32_t tq_shift;          //   (entry 0: no pair term), or null
+  const void* fast;          // with a term table: one FastPair (16 B) per pair for tier 1 (kernels.cu), or null
+  const uint32_t* xlist;     //   and the cross list: tier-1 reads the fast records leave to the general body (ascending read ids)
+  int32_t n_cross;
   uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
   int32_t lens_uniform;
   const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)
   int32_t ins_n;
-  const double* thr_tab;     // single/paired: exp(mps + mppb*len) indexed by len (paired: len1+len2)
+  // The per-read log term (GetTotalProb, graph.cc:1495-1537: log max(p / 2L, thr)), indexed by len (paired: len1+len2):
+  //   floored <=> RN(p / 2L) < thr <=> p < pstar_tab[len]   (the smallest double whose IEEE quotient by 2L reaches thr: host, exact)
+  //   floored: qthr_tab[len] = FIX(log thr);  otherwise FIX(LOG p) - FIX(log 2L), the second part applied once per set (ql)
+  const double* pstar_tab;   // per evaluation (depends on L), in the staging blob
+  const long long* qthr_tab; // per set
+  long long ql;              // FIX(log 2L), host-computed
   double floor_a, floor_b;   // pacbio: log(exp(mps)), log(exp(mppb)) (graph.cc:3075-3076)
   double* values;            // paired: ScoringState::probs; single: sum p1; pacbio: LSE
   uint32_t epoch;
@@ -129,7 +145,7 @@ struct ScoreParams {
   // chain discipline of the streaming kernels (set per launch)
   int32_t chain_first;       // 1: first kernel after apply_slots in its group: waits at its top; 0: waits at its end
   int32_t finish_here;       // 1: this kernel's last block publishes the set when nothing was listed for the pass after it
-  uint32_t* tile_counter;    // next tile of [0] tier 1, [1] the rare shapes, [2] tier 2 (zeroed by apply_slots)
+  uint32_t* tile_counter;    // next tile of [0] tier 1, [1] the rare shapes, [2] tier 2, [3] the cross list (zeroed by apply_slots)
   uint32_t* ticket2;         // blocks-finished counter of the set's last kernel (finish_set)
   uint32_t* done;            // set by finish_set_if_complete
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)
@@ -140,9 +156,13 @@ struct ScoreParams {
   int32_t state_add;         // 1: this evaluation accumulated a delta to add to state_acc; 0: it replaces it
   int32_t delta_only;        // 1: incremental evaluation at an unchanged total length (no O(R) pass)
   double* out;               // kResultStride doubles in HOST-MAPPED pinned memory, written by the last block (finish_set)
+  // multi-GPU result exchange over peer memory (NVLink): the publishing block also stores the set's 64-byte line into
+  // line `peer_line` of every rank's exchange buffer (peer_bufs[0 .. peer_world), this rank's own included)
+  unsigned long long* const* peer_bufs;
+  int32_t peer_world;
+  uint32_t peer_line;
+  double* part_out;          // device copy of the line for a collective library (NCCL all-reduce), or null
   const void* log_tab;       // 128 x {1/c, -log(1/c)} (double2)
-  double two_len_d;          // (double)(2*total_len) and its correctly rounded reciprocal (host-computed)
-  double rcp_two_len;
   // coverage-gap penalty events (null when the set has penalty_constant == 0)
   unsigned long long* ev_keys;
   uint32_t* ev_count;
@@ -219,10 +239,16 @@ struct BatchParams {
   const uint32_t* range_prefix;// n_ranges + 1 prefix sums of the range lengths
   const int32_t* range_cand;   // owning candidate of each range
   int32_t n_ranges;
-  const double* two_len_d;     // distinct (double)(2*total_len) values and their correctly rounded reciprocals
-  const double* rcp_two_len;
+  // The batch's distinct total lengths, ASCENDING (so that a read's floor test pstar grows with the index), for every
+  // length class (distinct len1+len2) of the set: pstar[cls * n_len + j]; len_class maps len1+len2 -> cls.
+  const double* pstar;
+  const long long* qthr_cls;   // per class: FIX(log thr)
+  const int32_t* len_class;
+  const long long* ql;         // n_len: FIX(log 2L)
   int32_t n_len;
-  unsigned long long* accum_len;    // n_len x kAccumStride: exact sum over ALL reads of the base state's terms at that length
+  unsigned long long* hist;         // (n_len + 1) x kBatchBin: per "first floored length index" bin of the base pass (kernels.cu)
+  unsigned long long* accum_len;    // n_len x kAccumStride: {low, high 64 bits of the exact sum of all reads' FIX terms at that
+                                    // length (before the - n FIX(log 2L) part), floored, -inf, nan}
   long long* accum_cand;            // n_cand x 4: {sum of low 32 bits, sum of high 32 bits (signed) of the term deltas, floored delta, bad}
 };
 

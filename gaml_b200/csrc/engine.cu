@@ -11,6 +11,7 @@
 //     reference's on the same host.
 // Everything that touches an alignment record runs in kernels.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -160,10 +161,23 @@ struct ReadSetState {
   int max_len[2] = {0, 0};
   std::vector<int32_t> len[2];
   MateStore mate[2];
-  DevBuf d_lens, d_values, d_stamp, d_ins, d_thr, d_ovf_list, d_complex, d_clens, d_cdesc;
+  DevBuf d_lens, d_values, d_stamp, d_ins, d_ovf_list, d_complex, d_clens, d_cdesc;
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
   DevBuf d_uni_prob[2];           // paired, uniform lengths: alignment probability by edit distance, per mate (kernels.cu)
-  double uni_thr = 0.0;
+  DevBuf d_fast, d_xlist;         // with a term table: FastPair per pair + the cross list (kernels.cu), valid when fast_ok
+  bool fast_ok = false;
+  int n_cross = 0;
+  DevBuf d_tq;                    // paired, uniform lengths: term table (pair term + its fixed-point logarithm), kernels.cu
+  int tq_shift = 0;               //   edit distances below 1 << tq_shift are tabulated (0 = no table)
+  // the per-read log term (kernels.cu acc_term): thresholds exp(mps + mppb*len) by length index (paired: len1 + len2), the
+  // fixed-point log of each (device table), the length indices that occur, and the floor test of the last total length
+  std::vector<double> h_thr;
+  std::vector<long long> h_qthr;
+  std::vector<int> len_classes;
+  std::vector<double> h_pstar;
+  int pstar_two_len = 0;
+  bool pstar_valid = false;
+  DevBuf d_qthr;
   DevBuf d_comb, d_partner12, d_partner21;   // paired: combined first slot words by mate-1 key id + the key maps (kernels.cu)
   bool comb_ok = false;
   DevBuf d_t2pack;              // paired: packed tier-2 entries (kernels.cu), valid when t2pack_ok
@@ -218,6 +232,7 @@ struct SetPlan {
   int cgrid = 0;                // blocks of the tier-2 (several records per read) kernel
   size_t occ_off[2] = {0, 0};   // byte offsets inside the staging blob
   size_t touch_off = 0, prefix_off = 0;
+  size_t pstar_off = 0;         // floor tests of this evaluation's total length, by length index (short-read sets)
   int n_touch = 0;
   // full paired evaluations: arena ranges of the keys that occur several times (the multi pass)
   size_t pb_seeds_off = 0, pb_occ_off = 0, pb_prefix_off = 0, pb_len_off = 0;   // PacBio coverage penalty inputs
@@ -265,6 +280,24 @@ struct gaml_ctx {
   double* exch_dev = nullptr;
   int exch_rank = 0, exch_world = 1;
   bool exch_owned = false;        // this context registered the segment with CUDA (and unregisters it)
+  // (b) peer memory over NVLink (gaml_peer_exchange_*): every rank owns a small device buffer of result lines
+  // [2 generations][world][GAML_EXCHANGE_MAX_SETS][64 B]; the publishing block of an evaluation stores its line into the
+  // buffer of EVERY rank (peer_ptrs, IPC-mapped), and the chain's last kernel (exchange_gather_kernel) waits for all lines
+  // in its own buffer and hands them to the host in one piece (h_gather: world x n_sets lines + one flag line)
+  DevBuf d_peer_lines, d_peer_table;
+  std::vector<void*> peer_ptrs;
+  std::vector<char> peer_opened;  // entries of peer_ptrs that came from cudaIpcOpenMemHandle
+  int peer_rank = 0, peer_world = 0;
+  bool peer_on = false;
+  unsigned long long* h_gather = nullptr;   // pinned + mapped
+  unsigned long long* d_gather_mapped = nullptr;
+  // (c) a collective library (gaml_nccl_exchange_init): all-reduce of the ranks' lines on the evaluation's stream
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+  int nccl_rank = 0, nccl_world = 0;
+  bool nccl_on = false;
+  DevBuf d_part, d_part_sum;
+  unsigned long long exchange_timeout_ns = 20ull * 1000 * 1000 * 1000;   // a peer's line missing for this long fails the evaluation
   // CUDA graphs of the evaluations' kernel chains, keyed by the sequence of kernels (GAML_B200_NO_GRAPHS=1 disables)
   struct GraphEntry { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; std::vector<cudaGraphNode_t> nodes; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
@@ -274,7 +307,9 @@ struct gaml_ctx {
   size_t h_out_cap = 0;
   unsigned long long scratch_entries = 1ull << 22;   // 4 Mi placements (96 MiB) for many-placement reads
   uint32_t ovf_cap = 1u << 20;
-  uint32_t epoch = 0;
+  uint32_t epoch = 0;             // device epoch: advanced by every successfully prepared evaluation
+  uint32_t stamp_gen = 0;         // host generation of the stores' key_stamp tables: advanced by every prepare()
+  bool capacity_grew = false;     // the last evaluation failed for capacity and the buffers it overran have been enlarged
   // pending evaluation
   bool prepared = false, launched = false;
   std::vector<SetPlan> plan;
@@ -333,6 +368,28 @@ double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, s
   double e = exp(-z * z / 2.0);
   double c = sqrt(2 * M_PI) * sd;
   return e / c;
+}
+
+// The floor test of GetTotalProb (graph.cc:1505-1512, 1527-1532) as a test on the read's value itself: the smallest
+// double p whose IEEE quotient p / d (d = 2 * total_len) is not below thr. RN(p / d) is monotone in p, so
+// "RN(p / d) < thr" is exactly "p < floor_pstar(thr, d)".
+double floor_pstar(double thr, double d) {
+  if (!(thr > 0.0)) return 0.0;   // nothing is below a zero threshold
+  double p = thr * d;
+  while (p > 0.0 && p / d >= thr) p = std::nextafter(p, 0.0);
+  while (p / d < thr) p = std::nextafter(p, std::numeric_limits<double>::infinity());
+  return p;
+}
+
+constexpr double kFixScaleHost = 1099511627776.0;   // 2^40 (kernels.cu kFixScale)
+long long fix_log_host(double v) {                   // FIX(log v) for the host-side constants of the term (thr, 2L)
+  if (!(v > 0.0)) return 0;
+  return std::llrint(std::log(v) * kFixScaleHost);
+}
+
+int two_len_of(int total_len) {   // the reference's int expression 2*total_len with total_len == 0 -> 1 (graph.cc:1500-1505)
+  const int tl = total_len == 0 ? 1 : total_len;
+  return (int)(2u * (unsigned)tl);
 }
 
 // ---- walk helpers -------------------------------------------------------------------------
@@ -696,6 +753,21 @@ int commit(gaml_ctx* ctx) {
       }
       CU(cudaStreamSynchronize(ctx->stream));   // cbase (copied above) and pack_bad are on the host now
       if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0) rs.pairs_ok = pack_bad == 0;
+      rs.fast_ok = false;
+      if (rs.pairs_ok && rs.comb_ok && rs.lens_uniform && rs.tq_shift > 0) {
+        // tier 1's fast records: everything about a same-key pair that does not depend on the walks, resolved into a
+        // term-table index; the remaining tier-1 reads go on the cross list
+        CU(rs.d_fast.reserve((size_t)rs.n_local * 16, 0, false, ctx->stream));
+        CU(rs.d_xlist.reserve((size_t)rs.n_local * 4, 0, false, ctx->stream));
+        uint32_t* flags = rs.mate[0].cursor.as<uint32_t>();   // scratch (n_local + 1), free after the list build above
+        CU(build_fast_pairs(rs.d_pairs.p, rs.n_local, rs.tq_shift, rs.ins_n, rs.uniform_ll, rs.d_fast.p, flags, rs.d_xlist.as<uint32_t>(),
+                            ctx->d_csr_temp.p, ctx->d_csr_temp.cap, ctx->stream, &launches));
+        uint32_t n_cross = 0;
+        CU(cudaMemcpyAsync(&n_cross, flags + rs.n_local, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        rs.n_cross = (int)n_cross;
+        rs.fast_ok = true;
+      }
       rs.t2pack_ok = false;
       if (rs.pairs_ok && rs.class_begin[3] > 0) {
         // tier 2's packed entries: classes (1,2), (2,1) two units per read, (2,2) three, unit major per class
@@ -756,6 +828,12 @@ int commit(gaml_ctx* ctx) {
 int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walks) {
   if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
+  // an evaluation in flight updates the read state and the walk bookkeeping when it is finished: preparing another one
+  // underneath it would score deltas against the wrong old walks
+  if (ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is in flight: call gaml_eval_finish before preparing the next one");
+  if (ctx->prepared) CU(cudaStreamSynchronize(ctx->stream));   // a prepared-but-abandoned evaluation: its staging copy may still read h_blob
+  ctx->prepared = false;
+  if (ctx->epoch + 1 >= 0x7fffffffu) return fail(ctx, GAML_ERR_STATE, "epoch counter exhausted (2^31 evaluations): recreate the context");
   WalkSet& ws = ctx->cur();
   const WalkSet* old_set = ctx->have_prev ? &ctx->prev() : nullptr;
   WalkDiff& diff = ctx->cur_diff;
@@ -786,8 +864,13 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->cur_total_len = total_len;
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
-  ctx->epoch++;
-  if (ctx->epoch >= 0x7fffffffu) return fail(ctx, GAML_ERR_STATE, "epoch counter exhausted (2^31 evaluations): recreate the context");
+  // host-side generation of the per-key stamp tables (group_occurrences). The device epoch (slot liveness, result lines)
+  // advances only at the end, once this function can no longer fail: the ranks of a multi-GPU job stay in step even when
+  // one of them rejects a walk set.
+  if (++ctx->stamp_gen == 0) {
+    for (MateStore* st : ctx->stores) std::fill(st->key_stamp.begin(), st->key_stamp.end(), 0u);
+    ctx->stamp_gen = 1;
+  }
 
   const size_t n_sets = ctx->sets.size();
   ctx->plan.assign(n_sets, SetPlan());
@@ -860,7 +943,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       }
       const size_t u0 = updates.size();
       for (int m = 0; m < 2; m++)
-        group_occurrences(*ob[m], rs.mate[m], ctx->epoch, updates, occs[rs.mate[m].table_index]);
+        group_occurrences(*ob[m], rs.mate[m], ctx->stamp_gen, updates, occs[rs.mate[m].table_index]);
       if (sp.full) {   // records under keys that occur several times: enumerated by the multi pass, mate 1's ranges first
         std::vector<TouchRange>& mt = mtouches[s];
         for (int m = 0; m < 2; m++) {
@@ -886,7 +969,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
         for (int i = 0; i < ws.n; i++) ctx->h_walks.push_back(ws.walk(i));
       if (rs.cfg.kind == GAML_KIND_SINGLE) flatten_single(ctx, rs, ctx->h_walks.data(), ws.n, ob, sp);
       else flatten_pacbio(ctx, rs, ctx->h_walks.data(), ws.n, ob, sp);
-      group_occurrences(ob, rs.mate[0], ctx->epoch, updates, occs[rs.mate[0].table_index]);
+      group_occurrences(ob, rs.mate[0], ctx->stamp_gen, updates, occs[rs.mate[0].table_index]);
       sp.grid = score_grid(rs.cfg.kind == GAML_KIND_SINGLE ? kGridSingleFull : kGridPacbioFull, rs.n_local, ctx->sm_count);
       sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
     }
@@ -914,6 +997,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     off = align16(off + mtouches[s].size() * sizeof(TouchRange));
     sp.mprefix_off = off;
     off = align16(off + (mtouches[s].size() + 1) * sizeof(uint32_t));
+    if (rs.cfg.kind != GAML_KIND_PACBIO) {
+      sp.pstar_off = off;
+      off = align16(off + std::max<size_t>(rs.h_thr.size(), 1) * sizeof(double));
+    }
     if (rs.pb_penalty) {
       sp.pb_seeds_off = off;
       off = align16(off + rs.h_pb_seeds.size() * 16);
@@ -973,6 +1060,17 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     }
     if (macc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 records under repeated keys in one evaluation");
     mpre[mtouches[s].size()] = (uint32_t)macc;
+    if (ctx->sets[s]->cfg.kind != GAML_KIND_PACBIO) {   // floor tests at this evaluation's total length (acc_term, kernels.cu)
+      ReadSetState& rt = *ctx->sets[s];
+      const int two_len = two_len_of(sp.total_len);
+      if (!rt.pstar_valid || rt.pstar_two_len != two_len) {
+        rt.h_pstar.assign(rt.h_thr.size(), 0.0);
+        for (int li : rt.len_classes) rt.h_pstar[li] = floor_pstar(rt.h_thr[li], (double)two_len);
+        rt.pstar_two_len = two_len;
+        rt.pstar_valid = true;
+      }
+      if (!rt.h_pstar.empty()) memcpy(hb + sp.pstar_off, rt.h_pstar.data(), rt.h_pstar.size() * sizeof(double));
+    }
     if (ctx->sets[s]->pb_penalty) {
       ReadSetState& rp = *ctx->sets[s];
       if (!rp.h_pb_seeds.empty()) memcpy(hb + sp.pb_seeds_off, rp.h_pb_seeds.data(), rp.h_pb_seeds.size() * 16);
@@ -1020,8 +1118,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_out_mapped), ctx->h_out, 0));
     ctx->h_out_cap = cap;
   }
+  for (auto& rsp : ctx->sets) CU(rsp->d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));   // grows after a capacity error
   CU(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.last_h2d_bytes = (int64_t)off;
+  ctx->epoch++;
   ctx->prepared = true;
   ctx->launched = false;
   return GAML_OK;
@@ -1033,6 +1133,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
 size_t exch_line(const gaml_ctx* ctx, int rank, size_t s) {
   return ((size_t)(ctx->epoch & 1u) * (size_t)ctx->exch_world + (size_t)rank) * GAML_EXCHANGE_MAX_SETS + s;
 }
+
+// The per-evaluation result lines go through NCCL only when no kernel-fused exchange is attached; the communicator also
+// serves the candidate batches (gaml_calc_prob_batch_gathered) next to either of those.
+bool nccl_lines(const gaml_ctx* ctx) { return ctx->nccl_on && !ctx->peer_on && !ctx->exch_host; }
 
 ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   ReadSetState& rs = *ctx->sets[s];
@@ -1059,18 +1163,28 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.lens_uniform = rs.lens_uniform ? 1 : 0;
   P.uniform_ll = rs.uniform_ll;
   for (int m = 0; m < 2; m++) P.uni_prob[m] = rs.lens_uniform && rs.d_uni_prob[m].p ? rs.d_uni_prob[m].as<double>() : nullptr;
-  P.uni_thr = rs.uni_thr;
+  P.tq = rs.lens_uniform && rs.tq_shift > 0 ? rs.d_tq.p : nullptr;
+  P.tq_shift = rs.tq_shift;
+  P.fast = rs.fast_ok && rs.pairs_ok && rs.comb_ok ? rs.d_fast.p : nullptr;
+  P.xlist = rs.d_xlist.as<uint32_t>();
+  P.n_cross = rs.fast_ok ? rs.n_cross : 0;
   P.ins_tab = rs.d_ins.as<double>();
   P.ins_n = rs.ins_n;
-  P.thr_tab = rs.d_thr.as<double>();
+  P.pstar_tab = reinterpret_cast<const double*>(blob + sp.pstar_off);
+  P.qthr_tab = rs.d_qthr.as<long long>();
+  if (rs.lens_uniform && rs.pstar_valid) {
+    const size_t li = (size_t)(rs.uniform_ll & 0xffff) + (size_t)(rs.uniform_ll >> 16);
+    P.uni_pstar = rs.h_pstar[li];
+    P.uni_qthr = rs.h_qthr[li];
+  }
   P.floor_a = rs.floor_a;
   P.floor_b = rs.floor_b;
   P.values = rs.d_values.as<double>();
   P.epoch = ctx->epoch;
   P.n_erased = sp.n_erased;
   P.n_reads = rs.n_local;
-  const int tl = sp.total_len == 0 ? 1 : sp.total_len;   // graph.cc:1500-1502
-  P.two_len = (int)(2u * (unsigned)tl);                   // the reference's int expression 2*total_len
+  P.two_len = two_len_of(sp.total_len);                   // the reference's int expression 2*total_len, graph.cc:1500-1505
+  P.ql = rs.cfg.kind == GAML_KIND_PACBIO ? 0 : fix_log_host((double)P.two_len);   // PacBio: - log 2L is the host's, graph.cc:3087
   unsigned long long* fl = ctx->d_flags.as<unsigned long long>();
   P.scratch_cursor = fl;
   P.error_flag = reinterpret_cast<uint32_t*>(fl + 1);
@@ -1102,13 +1216,17 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.chain_first = 1;
   P.finish_here = 0;
   P.out = ctx->exch_dev ? ctx->exch_dev + exch_line(ctx, ctx->exch_rank, s) * kResultStride : ctx->d_out_mapped + s * kResultStride;
+  if (ctx->peer_on) {
+    P.peer_bufs = ctx->d_peer_table.as<unsigned long long*>();
+    P.peer_world = ctx->peer_world;
+    P.peer_line = (uint32_t)(((size_t)(ctx->epoch & 1u) * (size_t)ctx->peer_world + (size_t)ctx->peer_rank) * GAML_EXCHANGE_MAX_SETS + s);
+  }
+  if (nccl_lines(ctx)) P.part_out = ctx->d_part.as<double>() + s * kResultStride;
   P.timeline = ctx->timeline ? ctx->d_timeline.as<unsigned long long>() : nullptr;
   P.state_acc = rs.cfg.kind == GAML_KIND_PAIRED ? rs.d_state_acc.as<unsigned long long>() : nullptr;
   P.state_add = sp.delta_only ? 1 : 0;
   P.delta_only = sp.delta_only ? 1 : 0;
   P.log_tab = ctx->d_logtab.p;
-  P.two_len_d = (double)P.two_len;
-  P.rcp_two_len = 1.0 / P.two_len_d;
   if (rs.penalty) {
     P.ev_keys = rs.d_ev.as<unsigned long long>();
     P.ev_count = reinterpret_cast<uint32_t*>(P.accum + 7);   // spare accumulator word of the set
@@ -1182,6 +1300,71 @@ int replay_chain(gaml_ctx* ctx, LaunchList& list) {
     }
   }
   CU(cudaGraphLaunch(it->second.exec, st));
+  return GAML_OK;
+}
+
+// ---- a collective library as the exchange (gaml_nccl_exchange_init) -------------------------------------------------
+// NCCL is bound at run time (dlopen: the copy the host program has loaded already, else libnccl.so.2), so the library
+// has no link-time dependency on it.
+struct NcclId { char bytes[128]; };
+struct NcclApi {
+  int (*get_unique_id)(NcclId*) = nullptr;
+  int (*comm_init_rank)(void**, int, NcclId, int) = nullptr;
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  const char* (*get_error_string)(int) = nullptr;
+  void* lib = nullptr;
+};
+NcclApi* nccl_api(std::string* why) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+    if (lib) {
+      api.get_unique_id = reinterpret_cast<int (*)(NcclId*)>(dlsym(lib, "ncclGetUniqueId"));
+      api.comm_init_rank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(lib, "ncclCommInitRank"));
+      api.all_reduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(lib, "ncclAllReduce"));
+      api.comm_destroy = reinterpret_cast<int (*)(void*)>(dlsym(lib, "ncclCommDestroy"));
+      api.get_error_string = reinterpret_cast<const char* (*)(int)>(dlsym(lib, "ncclGetErrorString"));
+      if (api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy) api.lib = lib;
+    }
+  }
+  if (!api.lib && why) *why = "NCCL (libnccl.so.2) is not available in this process";
+  return api.lib ? &api : nullptr;
+}
+
+// One ncclAllReduce(sum, fp64) over the ranks' result lines of this evaluation on the evaluation's stream,
+// then a one-thread-per-set kernel that re-seals the summed lines into host-mapped memory. Every field of a line is an
+// integer far below 2^53 (integer part and 2^-40 units of the exact sum, counts), so the sums of doubles are exact.
+int nccl_reduce_lines(gaml_ctx* ctx, int n_sets) {
+  NcclApi* api = nccl_api(&ctx->error);
+  if (!api) return GAML_ERR_STATE;
+  const int rc = api->all_reduce(ctx->d_part.p, ctx->d_part_sum.p, (size_t)n_sets * kResultStride, /*ncclDouble*/ 8, /*ncclSum*/ 0,
+                                 ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail(ctx, GAML_ERR_CUDA, std::string("ncclAllReduce: ") + (api->get_error_string ? api->get_error_string(rc) : "error"));
+  launch_reduced_publish(ctx->d_part_sum.as<double>(), n_sets, ctx->epoch, ctx->d_gather_mapped, ctx->stream);
+  CU(cudaGetLastError());
+  return GAML_OK;
+}
+
+int nccl_all_reduce_doubles(gaml_ctx* ctx, double* buf, size_t count) {   // in place, on the context's stream
+  NcclApi* api = nccl_api(&ctx->error);
+  if (!api || !ctx->nccl_comm) return fail(ctx, GAML_ERR_STATE, "no NCCL communicator: gaml_nccl_exchange_init first");
+  const int rc = api->all_reduce(buf, buf, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail(ctx, GAML_ERR_CUDA, std::string("ncclAllReduce: ") + (api->get_error_string ? api->get_error_string(rc) : "error"));
+  return GAML_OK;
+}
+
+int ensure_gather_area(gaml_ctx* ctx, int world) {
+  if (ctx->h_gather) return GAML_OK;
+  (void)world;
+  const size_t words = ((size_t)64 * GAML_EXCHANGE_MAX_SETS + 1) * kResultStride;   // up to 64 ranks + the flag line
+  CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_gather), words * 8, cudaHostAllocMapped));
+  memset(ctx->h_gather, 0, words * 8);
+  CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_gather_mapped), ctx->h_gather, 0));
   return GAML_OK;
 }
 
@@ -1301,12 +1484,26 @@ int launch(gaml_ctx* ctx) {
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
     }
   }
+  if (ctx->peer_on && n_sets > 0) {
+    // last kernel of the chain: wait for every rank's line of this evaluation in this rank's exchange buffer
+    const unsigned long long* gen = ctx->d_peer_lines.as<unsigned long long>() +
+                                    (size_t)(ctx->epoch & 1u) * (size_t)ctx->peer_world * GAML_EXCHANGE_MAX_SETS * kResultStride;
+    launch_exchange_gather(gen, ctx->peer_world, (int)n_sets, GAML_EXCHANGE_MAX_SETS, ctx->epoch, ctx->d_gather_mapped,
+                           ctx->d_gather_mapped + (size_t)ctx->peer_world * GAML_EXCHANGE_MAX_SETS * kResultStride,
+                           ctx->exchange_timeout_ns, st);
+    launches++;
+  }
   if (record) {
     set_launch_recorder(nullptr);
     const int rc = replay_chain(ctx, chain);
     if (rc != GAML_OK) return rc;
   }
   if (!record && ctx->timed) CU(cudaEventRecord(ctx->ev[3], st));
+  if (nccl_lines(ctx) && n_sets > 0) {
+    const int rc = nccl_reduce_lines(ctx, (int)n_sets);
+    if (rc != GAML_OK) return rc;
+    launches++;
+  }
   CU(cudaGetLastError());
   ctx->stats.kernel_launches += launches;
   ctx->stats.last_records_gathered = records;
@@ -1349,8 +1546,31 @@ int wait_line(gaml_ctx* ctx, const volatile uint64_t* line, uint64_t want_bits, 
 int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered = nullptr) {
   if (!ctx->launched) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish without gaml_eval_launch");
   const size_t n_sets = ctx->sets.size();
-  if (gathered && !ctx->exch_host) return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish_gathered needs gaml_set_result_exchange");
-  const double* own_lines = ctx->exch_host ? ctx->exch_host + exch_line(ctx, ctx->exch_rank, 0) * kResultStride : ctx->h_out;
+  if (gathered && !ctx->exch_host && !ctx->peer_on && !ctx->nccl_on)
+    return fail(ctx, GAML_ERR_STATE, "gaml_eval_finish_gathered needs a result exchange (gaml_set_result_exchange, gaml_peer_exchange_open "
+                                     "or gaml_nccl_exchange_init)");
+  const double want_d = (double)ctx->epoch;
+  uint64_t want_bits;
+  memcpy(&want_bits, &want_d, 8);
+  const int gather_world = ctx->peer_on ? ctx->peer_world : (ctx->nccl_on ? ctx->nccl_world : ctx->exch_world);
+  const bool peer_gather = gathered && ctx->peer_on;
+  if (peer_gather) {
+    // the chain's last kernel has collected every rank's lines in this rank's own pinned memory: ONE flag line to wait for
+    const size_t flag_at = (size_t)ctx->peer_world * GAML_EXCHANGE_MAX_SETS * kResultStride;
+    double flag[kResultStride];
+    const int rc = wait_line(ctx, reinterpret_cast<const volatile uint64_t*>(ctx->h_gather + flag_at), want_bits, flag, true);
+    if (rc != GAML_OK) return rc;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    uint64_t status;
+    memcpy(&status, &flag[0], 8);
+    if (status != 0) {
+      ctx->prepared = ctx->launched = false;
+      for (auto& rsp : ctx->sets) rsp->has_state = rsp->total_valid = false;
+      return fail(ctx, GAML_ERR_STATE, "a peer rank did not publish its result in time (ranks out of lockstep?)");
+    }
+  }
+  const double* own_lines = peer_gather ? reinterpret_cast<const double*>(ctx->h_gather) + (size_t)ctx->peer_rank * n_sets * kResultStride
+                            : (ctx->exch_host ? ctx->exch_host + exch_line(ctx, ctx->exch_rank, 0) * kResultStride : ctx->h_out);
   bool need_sync = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
@@ -1370,15 +1590,14 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
   if (need_sync) {
     CU(cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->h_res.data(), own_lines, n_sets * kResultStride * sizeof(double));
+  } else if (peer_gather) {
+    memcpy(ctx->h_res.data(), own_lines, n_sets * kResultStride * sizeof(double));   // complete: the flag line was written after them
   } else {
     // The last block of every set's last kernel wrote the set's result and then this evaluation's epoch into the
     // host-mapped buffer: spin on the flags instead of paying a copy and a stream synchronisation. The stream is
     // polled now and then so that a failed launch surfaces as an error instead of a hang.
     // A line counts only when its flag word carries this evaluation's epoch AND its checksum matches: the device
     // writes all eight words with one store and no fence, so a partially arrived line must be told from a whole one.
-    const double want = (double)ctx->epoch;
-    uint64_t want_bits;
-    memcpy(&want_bits, &want, 8);
     const volatile uint64_t* ho = reinterpret_cast<const volatile uint64_t*>(own_lines);
     for (size_t s = 0; s < n_sets; s++) {
       const int rc = wait_line(ctx, ho + s * kResultStride, want_bits, ctx->h_res.data() + s * kResultStride, true);
@@ -1387,13 +1606,25 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
     std::atomic_thread_fence(std::memory_order_acquire);
   }
   if (gathered) {   // every rank's partials of this evaluation (the ranks evaluate in lockstep: same epoch everywhere)
-    const double want = (double)ctx->epoch;
-    uint64_t want_bits;
-    memcpy(&want_bits, &want, 8);
-    for (int rk = 0; rk < ctx->exch_world; rk++)
+    for (int rk = 0; rk < gather_world; rk++)
       for (size_t s = 0; s < n_sets; s++) {
         double line[kResultStride];
-        if (rk == ctx->exch_rank) {
+        if (nccl_lines(ctx)) {
+          // the all-reduce left the SUM over ranks: reported as shard 0's partials, the other shards' as zeros — the
+          // combine step adds the shards, so the result is the same double
+          if (rk == 0) {
+            const int rc = wait_line(ctx, reinterpret_cast<const volatile uint64_t*>(ctx->h_gather + s * kResultStride), want_bits, line, true);
+            if (rc != GAML_OK) return rc;
+            if (((uint64_t)line[5]) & 15) {   // (flags are summed too: any rank's error bits make the sum non-zero mod 16 or beyond)
+              for (auto& rsp : ctx->sets) rsp->has_state = rsp->total_valid = false;
+            }
+          } else {
+            memset(line, 0, sizeof(line));
+          }
+        } else if (peer_gather) {
+          memcpy(line, reinterpret_cast<const double*>(ctx->h_gather) + ((size_t)rk * n_sets + s) * kResultStride, sizeof(line));
+          if (rk != ctx->peer_rank && (((uint64_t)line[5]) & 15)) return fail(ctx, GAML_ERR_CAPACITY, "a peer rank reported a capacity error");
+        } else if (rk == ctx->exch_rank) {
           memcpy(line, ctx->h_res.data() + s * kResultStride, sizeof(line));
         } else {
           const volatile uint64_t* src = reinterpret_cast<const volatile uint64_t*>(ctx->exch_host + exch_line(ctx, rk, s) * kResultStride);
@@ -1432,7 +1663,7 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
       {
         const int tl1 = ctx->plan[s].total_len == 0 ? 1 : ctx->plan[s].total_len;
         rs.total_two_len = (int)(2u * (unsigned)tl1);
-        rs.total_valid = (f & 15) == 0;   // a failed evaluation leaves no usable running total
+        rs.total_valid = true;   // (cleared again below when the evaluation reported a capacity error)
       }
       rs.has_state = true;   // graph.cc:1986: state follows the last EVALUATED walks (ctx->prev() after the swap below)
       any_paired = true;
@@ -1466,6 +1697,24 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
       if (ctx->plan[s].full && ctx->sets[s]->cfg.kind == GAML_KIND_PAIRED)
         mi += ctx->plan[s].multi_records;
     ctx->stats.last_multi_items = mi;
+  }
+  ctx->capacity_grew = false;
+  if (flags & 15) {
+    // the kernels skipped the reads they had no room for: their per-read state (ScoringState::probs) was not updated, so
+    // nothing incremental may build on this evaluation — the next one re-scores every read. The buffer that overflowed is
+    // enlarged for it (the one-shot entry points retry by themselves).
+    for (auto& rsp : ctx->sets) {
+      rsp->has_state = false;
+      rsp->total_valid = false;
+    }
+    if ((flags & 1) && ctx->ovf_cap < (1u << 30)) {
+      ctx->ovf_cap *= 4;
+      ctx->capacity_grew = true;
+    }
+    if ((flags & 2) && ctx->scratch_entries < (1ull << 27)) {
+      ctx->scratch_entries *= 4;
+      ctx->capacity_grew = true;
+    }
   }
   if (flags & 1) return fail(ctx, GAML_ERR_CAPACITY, "too many many-placement reads for the overflow list");
   if (flags & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
@@ -1539,7 +1788,7 @@ int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, 
 // work is O(#nodes of the touched walks) per candidate plus O(#base walks) once per batch.
 int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx, const int64_t* erased_off,
                             const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
-                            double* partials, int32_t* total_lens) {
+                            double* partials, int32_t* total_lens, bool reduce_over_ranks = false) {
   if (n_cand <= 0 || !erased_off || !cand_added_off || !added_walk_off || !partials)
     return fail(ctx, GAML_ERR_ARG, "bad batch arguments");
   if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
@@ -1578,10 +1827,10 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     base_walk_len[i] = walk_length(ctx, base[i]);
     base_len += base_walk_len[i];
   }
-  // distinct total lengths
+  // distinct total lengths, ascending (the base pass relies on the floor test growing with the index)
   std::vector<int> cand_len(n_cand);
-  std::unordered_map<int, int> len_index;
-  std::vector<double> two_len_d, rcp;
+  std::vector<int> cand_two(n_cand);
+  std::vector<int> two_lens;
   std::vector<int> cand_len_index(n_cand);
   std::vector<std::vector<Walk>> cand_added(n_cand);
   std::vector<std::vector<int>> cand_erased(n_cand);
@@ -1605,17 +1854,16 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     }
     cand_len[c] = (int)tl;
     if (total_lens) total_lens[c] = (int)tl;
-    const int t = cand_len[c] == 0 ? 1 : cand_len[c];
-    const int two = (int)(2u * (unsigned)t);
-    auto it = len_index.find(two);
-    if (it == len_index.end()) {
-      it = len_index.emplace(two, (int)two_len_d.size()).first;
-      two_len_d.push_back((double)two);
-      rcp.push_back(1.0 / (double)two);
-    }
-    cand_len_index[c] = it->second;
+    cand_two[c] = two_len_of(cand_len[c]);
+    two_lens.push_back(cand_two[c]);
   }
-  const int n_len = (int)two_len_d.size();
+  std::sort(two_lens.begin(), two_lens.end());
+  two_lens.erase(std::unique(two_lens.begin(), two_lens.end()), two_lens.end());
+  for (int c = 0; c < n_cand; c++)
+    cand_len_index[c] = (int)(std::lower_bound(two_lens.begin(), two_lens.end(), cand_two[c]) - two_lens.begin());
+  std::vector<long long> ql(two_lens.size());
+  for (size_t j = 0; j < two_lens.size(); j++) ql[j] = fix_log_host((double)two_lens[j]);
+  const int n_len = (int)two_lens.size();
   ctx->h_batch_out.assign((size_t)n_cand * kOutStride, 0.0);
   cudaStream_t st = ctx->stream;
 
@@ -1687,8 +1935,20 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     const size_t o_ranges = place(ranges.size() * sizeof(TouchRange));
     const size_t o_prefix = place(range_prefix.size() * 4);
     const size_t o_rcand = place(range_cand.size() * 4);
-    const size_t o_len = place(two_len_d.size() * 8);
-    const size_t o_rcp = place(rcp.size() * 8);
+    // floor tests: per length class of the set (distinct len1 + len2) and distinct total length
+    std::vector<int32_t> len_class(std::max<size_t>(rs.h_thr.size(), 1), 0);
+    std::vector<long long> qthr_cls(std::max<size_t>(rs.len_classes.size(), 1), 0);
+    std::vector<double> pstar(std::max<size_t>(rs.len_classes.size(), 1) * (size_t)n_len, 0.0);
+    for (size_t k = 0; k < rs.len_classes.size(); k++) {
+      const int li = rs.len_classes[k];
+      len_class[li] = (int32_t)k;
+      qthr_cls[k] = rs.h_qthr[li];
+      for (int j = 0; j < n_len; j++) pstar[k * (size_t)n_len + j] = floor_pstar(rs.h_thr[li], (double)two_lens[j]);
+    }
+    const size_t o_pstar = place(pstar.size() * 8);
+    const size_t o_qcls = place(qthr_cls.size() * 8);
+    const size_t o_lcls = place(len_class.size() * 4);
+    const size_t o_ql = place(ql.size() * 8);
     std::vector<char> blob(std::max<size_t>(off, 16));
     auto put = [&](size_t o, const void* p, size_t bytes) { if (bytes) memcpy(blob.data() + o, p, bytes); };
     put(o_cands, cands.data(), cands.size() * sizeof(BatchCand));
@@ -1701,11 +1961,14 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     put(o_ranges, ranges.data(), ranges.size() * sizeof(TouchRange));
     put(o_prefix, range_prefix.data(), range_prefix.size() * 4);
     put(o_rcand, range_cand.data(), range_cand.size() * 4);
-    put(o_len, two_len_d.data(), two_len_d.size() * 8);
-    put(o_rcp, rcp.data(), rcp.size() * 8);
+    put(o_pstar, pstar.data(), pstar.size() * 8);
+    put(o_qcls, qthr_cls.data(), qthr_cls.size() * 8);
+    put(o_lcls, len_class.data(), len_class.size() * 4);
+    put(o_ql, ql.data(), ql.size() * 8);
     CU(ctx->d_batch_blob.reserve(blob.size(), 0, false, st));
     CU(cudaMemcpyAsync(ctx->d_batch_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-    const size_t acc_bytes = ((size_t)n_len * kAccumStride + (size_t)n_cand * 4) * 8;
+    const size_t hist_words = (size_t)batch_hist_bins(n_len) * kBatchBin;
+    const size_t acc_bytes = (((size_t)n_len + 1) * kAccumStride + (size_t)n_cand * 4 + hist_words) * 8;
     CU(ctx->d_batch_acc.reserve(acc_bytes, 0, false, st));
     CU(cudaMemsetAsync(ctx->d_batch_acc.p, 0, acc_bytes, st));
     CU(ctx->d_batch_out.reserve((size_t)n_cand * kOutStride * 8, 0, false, st));
@@ -1729,15 +1992,24 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     B.range_prefix = reinterpret_cast<const uint32_t*>(db + o_prefix);
     B.range_cand = reinterpret_cast<const int32_t*>(db + o_rcand);
     B.n_ranges = (int)ranges.size();
-    B.two_len_d = reinterpret_cast<const double*>(db + o_len);
-    B.rcp_two_len = reinterpret_cast<const double*>(db + o_rcp);
+    B.pstar = reinterpret_cast<const double*>(db + o_pstar);
+    B.qthr_cls = reinterpret_cast<const long long*>(db + o_qcls);
+    B.len_class = reinterpret_cast<const int32_t*>(db + o_lcls);
+    B.ql = reinterpret_cast<const long long*>(db + o_ql);
     B.n_len = n_len;
     B.accum_len = ctx->d_batch_acc.as<unsigned long long>();
-    B.accum_cand = reinterpret_cast<long long*>(ctx->d_batch_acc.as<unsigned long long>() + (size_t)n_len * kAccumStride);
+    B.accum_cand = reinterpret_cast<long long*>(B.accum_len + ((size_t)n_len + 1) * kAccumStride);
+    B.hist = B.accum_len + ((size_t)n_len + 1) * kAccumStride + (size_t)n_cand * 4;
     launch_batch(P, B, (uint32_t)touch_total, ctx->d_batch_out.as<double>(),
                  reinterpret_cast<const uint32_t*>(ctx->d_flags.as<unsigned long long>() + 1), ctx->sm_count, st);
     CU(cudaGetLastError());
-    ctx->stats.kernel_launches += 2 + (touch_total > 0);
+    ctx->stats.kernel_launches += batch_launches(n_len, touch_total > 0);
+    if (reduce_over_ranks) {
+      // all shards' partials of every candidate, summed by one all-reduce on the stream (exact: integers in doubles)
+      const int rc2 = nccl_all_reduce_doubles(ctx, ctx->d_batch_out.as<double>(), (size_t)n_cand * kOutStride);
+      if (rc2 != GAML_OK) return rc2;
+      ctx->stats.kernel_launches++;
+    }
     CU(cudaMemcpyAsync(ctx->h_batch_out.data(), ctx->d_batch_out.p, (size_t)n_cand * kOutStride * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int c = 0; c < n_cand; c++) {
@@ -1827,6 +2099,11 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
   if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->exch_host && ctx->exch_owned) cudaHostUnregister(ctx->exch_host);
+  for (size_t p = 0; p < ctx->peer_ptrs.size(); p++)
+    if (ctx->peer_opened[p] && ctx->peer_ptrs[p]) cudaIpcCloseMemHandle(ctx->peer_ptrs[p]);
+  if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+  if (ctx->nccl_comm)
+    if (NcclApi* api = nccl_api(nullptr)) api->comm_destroy(ctx->nccl_comm);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   cudaStream_t st = ctx->stream;
@@ -1933,14 +2210,21 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   CU(rs.d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));
   if (paired) CU(rs.d_stamp.reserve(std::max<int64_t>(n_local, 1) * 4, 0, true, ctx->stream));
   if (paired) CU(rs.d_state_acc.reserve(kAccumStride * sizeof(unsigned long long), 0, true, ctx->stream));
-  // floor thresholds
-  std::vector<double> thr;
+  // floor thresholds by length index (paired: len1 + len2), their fixed-point logs, and the length indices that occur
   if (cfg->kind != GAML_KIND_PACBIO) {
     const int top = rs.max_len[0] + (paired ? rs.max_len[1] : 0);
-    thr.resize(top + 1);
-    for (int l = 0; l <= top; l++) thr[l] = exp(cfg->min_prob_start + cfg->min_prob_per_base * (l));   // graph.cc:1506-1507, 1528
-    CU(rs.d_thr.reserve(thr.size() * 8, 0, false, ctx->stream));
-    CU(cudaMemcpyAsync(rs.d_thr.p, thr.data(), thr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rs.h_thr.resize(top + 1);
+    rs.h_qthr.resize(top + 1);
+    for (int l = 0; l <= top; l++) {
+      rs.h_thr[l] = exp(cfg->min_prob_start + cfg->min_prob_per_base * (l));   // graph.cc:1506-1507, 1528
+      rs.h_qthr[l] = fix_log_host(rs.h_thr[l]);                                // log of the reference's own threshold
+    }
+    std::vector<char> seen(top + 1, 0);
+    for (int64_t i = 0; i < n_local; i++) seen[rs.len[0][i] + (paired ? rs.len[1][i] : 0)] = 1;
+    for (int l = 0; l <= top; l++)
+      if (seen[l]) rs.len_classes.push_back(l);
+    CU(rs.d_qthr.reserve(rs.h_qthr.size() * 8, 0, false, ctx->stream));
+    CU(cudaMemcpyAsync(rs.d_qthr.p, rs.h_qthr.data(), rs.h_qthr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (paired && rs.lens_uniform) {
       // every pair has the same lengths: tabulate mismatch^e * match^(len-e) (graph.cc:1859-1863; one IEEE product, the
       // same double the device forms with __dmul_rn) for the edit distances the packed records can hold
@@ -1955,7 +2239,6 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
         CU(cudaMemcpyAsync(rs.d_uni_prob[m].p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));   // tab is a local
       }
-      rs.uni_thr = thr[l[0] + l[1]];
     }
   } else {
     rs.floor_a = log(exp(cfg->min_prob_start));      // logdouble(exp(mps)), graph.cc:3075
@@ -1973,6 +2256,20 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
     for (int d = 0; d < rs.ins_n; d++) ins[d] = insert_pdf((double)d, cfg->insert_mean, cfg->insert_std);
     CU(rs.d_ins.reserve(ins.size() * 8, 0, false, ctx->stream));
     CU(cudaMemcpyAsync(rs.d_ins.p, ins.data(), ins.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (rs.lens_uniform && rs.ins_n > 0 && !getenv("GAML_B200_NO_TERM_TABLE")) {
+      // term table: (edit 1, edit 2, insert distance) -> pair term + its fixed-point logarithm, for the edit distances
+      // below 2^shift — as many as fit 16 MiB (L2 resident; the entries a data set really uses are a few KB)
+      int shift = 5;
+      while (shift >= 2 && ((size_t)1 << (2 * shift)) * (size_t)rs.ins_n * sizeof(TermEntry) > (size_t)16 << 20) shift--;
+      if (shift >= 2) {
+        CU(rs.d_tq.reserve((1 + ((size_t)1 << (2 * shift)) * (size_t)rs.ins_n) * sizeof(TermEntry), 0, false, ctx->stream));
+        launch_build_term_table(rs.d_uni_prob[0].as<double>(), rs.d_uni_prob[1].as<double>(), rs.d_ins.as<double>(), rs.ins_n, shift,
+                                ctx->d_logtab.p, rs.d_tq.p, ctx->sm_count, ctx->stream);
+        CU(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        rs.tq_shift = shift;
+      }
+    }
   }
   if (cfg->kind == GAML_KIND_PACBIO && cfg->penalty_constant != 0.0) rs.pb_penalty = true;
   if (paired && cfg->penalty_constant != 0.0) {
@@ -2019,17 +2316,21 @@ int gaml_cache_insert(gaml_ctx* ctx, int set, int mate, const int32_t* key, int3
   KeyMeta km;
   km.arena_off = (uint32_t)st->total_records();
   int mx = INT_MIN;
-  const int max_ed = rs->max_len[mate] + 6;
+  // every record is checked BEFORE anything is staged: a rejected call leaves the store untouched (records of reads
+  // outside this shard are only checked for what does not need their length)
   for (int64_t i = 0; i < n_records; i++) {
     const gaml_alignment& a = records[i];
     if (a.read_id < 0 || a.read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
     if (a.orientation != 0 && a.orientation != 1) return fail(ctx, GAML_ERR_ARG, "record orientation must be 0 or 1");
-    if (a.edit_dist < 0 || a.edit_dist > max_ed || a.edit_dist > 0xffff)
-      return fail(ctx, GAML_ERR_ARG, "record edit_dist outside the pow tables");
+    if (a.edit_dist < 0 || a.edit_dist > 0xffff) return fail(ctx, GAML_ERR_ARG, "record edit_dist outside the pow tables");
+    if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
+    if (a.edit_dist > rs->len[mate][(size_t)(a.read_id - rs->lo)]) return fail(ctx, GAML_ERR_ARG, "edit_dist larger than the read length");
+  }
+  for (int64_t i = 0; i < n_records; i++) {
+    const gaml_alignment& a = records[i];
     mx = std::max(mx, a.position);
     if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
     const int local = (int)(a.read_id - rs->lo);
-    if (rs->len[mate][local] - a.edit_dist < 0) return fail(ctx, GAML_ERR_ARG, "edit_dist larger than the read length");
     int4 v;
     v.x = local;
     v.y = a.position;
@@ -2064,9 +2365,10 @@ int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t
   if (st->key_ids.count(k)) return fail(ctx, GAML_ERR_KEY_EXISTS, "cache key inserted twice");
   KeyMeta km;
   km.arena_off = (uint32_t)st->total_records();
+  for (int64_t i = 0; i < n_records; i++)   // checked before anything is staged
+    if (records[i].read_id < 0 || records[i].read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
   for (int64_t i = 0; i < n_records; i++) {
     const gaml_pacbio_alignment& a = records[i];
-    if (a.read_id < 0 || a.read_id >= rs->n_total) return fail(ctx, GAML_ERR_ARG, "record read_id out of range");
     if (a.read_id < rs->lo || a.read_id >= rs->hi) continue;
     ArenaLong al;
     al.read = (int)(a.read_id - rs->lo);
@@ -2156,8 +2458,18 @@ int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
   if (h.kind != rs.cfg.kind || h.n_mates != rs.n_mates || h.n_total != rs.n_total || h.lo != rs.lo || h.hi != rs.hi)
     return fail(ctx, GAML_ERR_ARG, "cache file was written for a different read set (kind, read count or shard)");
   const int n_nodes = (int)ctx->node_len.size();
+  // The whole file is parsed and checked into temporaries first — with the checks gaml_cache_insert applies to every
+  // record — and moved into the stores only when all of it is sound: a corrupt or stale file leaves the read set empty
+  // (so that loading can be retried) and can never plant an out-of-table edit distance on the device.
+  struct Loaded {
+    std::unordered_map<Walk, int, WalkHash> key_ids;
+    std::vector<KeyMeta> keys;
+    std::vector<int4> pending;
+    std::vector<Int2> pending_pos;
+  } tmp[2];
   for (int m = 0; m < rs.n_mates; m++) {
-    MateStore& st = rs.mate[m];
+    const bool is_long = rs.mate[m].is_long;
+    Loaded& ld = tmp[m];
     int64_t counts[2];
     if (fread(counts, sizeof(counts), 1, fc.f) != 1 || counts[0] < 0 || counts[1] < 0 || counts[1] > 0xfffffff0ll)
       return fail(ctx, GAML_ERR_ARG, "corrupt cache file (store header)");
@@ -2171,28 +2483,45 @@ int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
         return fail(ctx, GAML_ERR_ARG, "corrupt cache file (key)");
       for (int x : w)
         if (x >= n_nodes && n_nodes > 0) return fail(ctx, GAML_ERR_ARG, "cache key references a node outside the graph");
+      if (meta[0] < 0) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (key record count)");
       KeyMeta km;
       km.arena_off = (uint32_t)off;
       km.count = (uint32_t)meta[0];
       km.max_pos = meta[1];
       km.any = meta[2] != 0;
       off += km.count;
-      if (!st.key_ids.emplace(w, (int)st.keys.size()).second) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (duplicate key)");
-      st.keys.push_back(km);
+      if (!ld.key_ids.emplace(w, (int)ld.keys.size()).second) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (duplicate key)");
+      ld.keys.push_back(km);
     }
     if (off != (uint64_t)counts[1]) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record count)");
-    st.pending.resize((size_t)counts[1]);
-    if (counts[1] && fread(st.pending.data(), 16, (size_t)counts[1], fc.f) != (size_t)counts[1])
+    ld.pending.resize((size_t)counts[1]);
+    if (counts[1] && fread(ld.pending.data(), 16, (size_t)counts[1], fc.f) != (size_t)counts[1])
       return fail(ctx, GAML_ERR_ARG, "corrupt cache file (records)");
-    if (st.is_long) {
-      st.pending_pos.resize((size_t)counts[1]);
-      if (counts[1] && fread(st.pending_pos.data(), 8, (size_t)counts[1], fc.f) != (size_t)counts[1])
+    if (is_long) {
+      ld.pending_pos.resize((size_t)counts[1]);
+      if (counts[1] && fread(ld.pending_pos.data(), 8, (size_t)counts[1], fc.f) != (size_t)counts[1])
         return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record positions)");
     }
-    for (const int4& v : st.pending) {   // {read, pos, edor, key} / {read, key, logprob}
-      const int key = st.is_long ? v.y : v.w;
-      if (v.x < 0 || v.x >= rs.n_local || key < 0 || key >= (int)st.keys.size()) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record)");
+    size_t at = 0;
+    for (size_t k = 0; k < ld.keys.size(); k++) {   // records are key-major: record `at` must carry key k
+      for (uint32_t t = 0; t < ld.keys[k].count; t++, at++) {
+        const int4& v = ld.pending[at];   // {read, pos, edor, key} / {read, key, logprob}
+        const int key = is_long ? v.y : v.w;
+        if (v.x < 0 || v.x >= rs.n_local || key != (int)k) return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record)");
+        if (!is_long) {
+          const int ed = v.z & 0xffff;
+          if ((v.z & ~(0xffff | (1 << 30))) != 0 || ed > rs.len[m][(size_t)v.x])
+            return fail(ctx, GAML_ERR_ARG, "corrupt cache file (record edit distance / orientation)");
+        }   // (PacBio {position, position_end} are only ever used arithmetically, never as indices)
+      }
     }
+  }
+  for (int m = 0; m < rs.n_mates; m++) {
+    MateStore& st = rs.mate[m];
+    st.key_ids = std::move(tmp[m].key_ids);
+    st.keys = std::move(tmp[m].keys);
+    st.pending = std::move(tmp[m].pending);
+    st.pending_pos = std::move(tmp[m].pending_pos);
     st.dirty = true;
   }
   return GAML_OK;
@@ -2406,13 +2735,144 @@ int gaml_set_result_exchange(gaml_ctx* ctx, void* shared_base, int64_t bytes, in
   return GAML_OK;
 }
 
+// ---- result exchange over peer memory (NVLink) -------------------------------------------------------------------
+static void peer_exchange_release(gaml_ctx* ctx) {
+  for (size_t p = 0; p < ctx->peer_ptrs.size(); p++)
+    if (ctx->peer_opened[p] && ctx->peer_ptrs[p]) cudaIpcCloseMemHandle(ctx->peer_ptrs[p]);
+  ctx->peer_ptrs.clear();
+  ctx->peer_opened.clear();
+  ctx->peer_on = false;
+}
+
+int gaml_peer_exchange_create(gaml_ctx* ctx, int32_t rank, int32_t world, void* ipc_handle_out, void** buffer_out) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(ctx, GAML_ERR_ARG, "peer exchange: 0 <= rank < world <= 64");
+  if (ctx->sets.size() > GAML_EXCHANGE_MAX_SETS) return fail(ctx, GAML_ERR_CAPACITY, "more read sets than GAML_EXCHANGE_MAX_SETS");
+  CU(cudaStreamSynchronize(ctx->stream));
+  peer_exchange_release(ctx);
+  const size_t bytes = 2 * (size_t)world * GAML_EXCHANGE_MAX_SETS * kResultStride * sizeof(double);
+  if (!ctx->d_peer_lines.p) {   // allocated once per context: an exported buffer is never moved
+    CU(ctx->d_peer_lines.reserve(2 * (size_t)64 * GAML_EXCHANGE_MAX_SETS * kResultStride * sizeof(double), 0, true, ctx->stream));
+  }
+  CU(cudaMemsetAsync(ctx->d_peer_lines.p, 0, bytes, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_peer_lines.p));
+    static_assert(sizeof(h) == GAML_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  if (buffer_out) *buffer_out = ctx->d_peer_lines.p;
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  return GAML_OK;
+}
+
+int gaml_peer_exchange_open(gaml_ctx* ctx, const void* ipc_handles, void* const* local_buffers) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
+  if (ctx->peer_world < 1 || !ctx->d_peer_lines.p) return fail(ctx, GAML_ERR_STATE, "gaml_peer_exchange_create first");
+  peer_exchange_release(ctx);
+  const int world = ctx->peer_world;
+  ctx->peer_ptrs.assign(world, nullptr);
+  ctx->peer_opened.assign(world, 0);
+  for (int p = 0; p < world; p++) {
+    if (p == ctx->peer_rank) {
+      ctx->peer_ptrs[p] = ctx->d_peer_lines.p;
+    } else if (local_buffers && local_buffers[p]) {
+      ctx->peer_ptrs[p] = local_buffers[p];   // another context of this process (IPC handles cannot be opened by their creator)
+    } else if (ipc_handles) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)p * GAML_IPC_HANDLE_BYTES, sizeof(h));
+      void* ptr = nullptr;
+      const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        peer_exchange_release(ctx);
+        return fail(ctx, GAML_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer access between the GPUs is required): ") + cudaGetErrorString(e));
+      }
+      ctx->peer_ptrs[p] = ptr;
+      ctx->peer_opened[p] = 1;
+    } else {
+      peer_exchange_release(ctx);
+      return fail(ctx, GAML_ERR_ARG, "peer exchange: no handle or buffer for a rank");
+    }
+  }
+  CU(ctx->d_peer_table.reserve(64 * sizeof(void*), 0, false, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_peer_table.p, ctx->peer_ptrs.data(), (size_t)world * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int rc = ensure_gather_area(ctx, world);
+  if (rc != GAML_OK) return rc;
+  ctx->peer_on = true;
+  return GAML_OK;
+}
+
+int gaml_peer_exchange_close(gaml_ctx* ctx) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  peer_exchange_release(ctx);
+  return GAML_OK;
+}
+
+// ---- result exchange through NCCL --------------------------------------------------------------------------------
+int gaml_nccl_unique_id(void* out128) {
+  if (!out128) return GAML_ERR_ARG;
+  NcclApi* api = nccl_api(&g_create_error);
+  if (!api) return GAML_ERR_STATE;
+  NcclId id;
+  if (api->get_unique_id(&id) != 0) {
+    g_create_error = "ncclGetUniqueId failed";
+    return GAML_ERR_CUDA;
+  }
+  memcpy(out128, &id, sizeof(id));
+  return GAML_OK;
+}
+
+int gaml_nccl_exchange_init(gaml_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
+  NcclApi* api = nccl_api(&ctx->error);
+  if (!api) return GAML_ERR_STATE;
+  if (ctx->nccl_comm) {
+    cudaStreamSynchronize(ctx->stream);
+    api->comm_destroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->nccl_on = false;
+  }
+  if (!unique_id128) return GAML_OK;   // detach
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(ctx, GAML_ERR_ARG, "nccl exchange: 0 <= rank < world <= 64");
+  NcclId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  const int rc = api->comm_init_rank(&ctx->nccl_comm, world, id, rank);
+  if (rc != 0) return fail(ctx, GAML_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->get_error_string ? api->get_error_string(rc) : "error"));
+  const size_t bytes = (size_t)GAML_EXCHANGE_MAX_SETS * kResultStride * sizeof(double);
+  CU(ctx->d_part.reserve(bytes, 0, true, ctx->stream));
+  CU(ctx->d_part_sum.reserve(bytes, 0, true, ctx->stream));
+  int rc2 = ensure_gather_area(ctx, world);
+  if (rc2 != GAML_OK) return rc2;
+  ctx->nccl_rank = rank;
+  ctx->nccl_world = world;
+  ctx->nccl_on = true;
+  return GAML_OK;
+}
+
 int gaml_calc_prob_partial(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
                            double* partials, int32_t* total_len) {
-  int rc = gaml_eval_prepare(ctx, walk_nodes, walk_offsets, n_walks);
-  if (rc) return rc;
-  rc = gaml_eval_launch(ctx);
-  if (rc) return rc;
-  return gaml_eval_finish(ctx, partials, total_len);
+  // A capacity error (scratch arena / overflow list too small for this walk set) enlarges the buffer and invalidates the
+  // incremental state; the reference never fails here, so the call repeats the evaluation — a full re-score — itself.
+  // (Not with a result exchange attached: the ranks count evaluations in lockstep.)
+  for (int attempt = 0;; attempt++) {
+    int rc = gaml_eval_prepare(ctx, walk_nodes, walk_offsets, n_walks);
+    if (rc) return rc;
+    rc = gaml_eval_launch(ctx);
+    if (rc) return rc;
+    rc = gaml_eval_finish(ctx, partials, total_len);
+    if (rc != GAML_ERR_CAPACITY || !ctx->capacity_grew || ctx->exch_host || ctx->peer_on || ctx->nccl_on || attempt >= 6) return rc;
+  }
 }
 
 int gaml_combine_partials(gaml_ctx* ctx, const double* gathered, int32_t n_shards, int32_t total_len, gaml_result* result,
@@ -2465,6 +2925,30 @@ int gaml_calc_prob_batch(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_id
                                         partials.data(), tls.data());
   if (rc) return rc;
   for (int c = 0; c < n_cand; c++) {
+    gaml_result res;
+    rc = combine(ctx, partials.data() + (size_t)c * n_sets * GAML_PARTIAL_DOUBLES, 1, tls[c], &res,
+                 zeros ? zeros + (size_t)c * 2 * n_sets : nullptr);
+    if (rc) return rc;
+    probs[c] = res.prob;
+    if (total_lens) total_lens[c] = tls[c];
+  }
+  return GAML_OK;
+}
+
+int gaml_calc_prob_batch_gathered(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                                  const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off, double* probs,
+                                  int32_t* total_lens, int32_t* zeros) {
+  if (check_ctx(ctx)) return GAML_ERR_ARG;
+  if (!probs || n_cand <= 0) return fail(ctx, GAML_ERR_ARG, "bad batch arguments");
+  if (!ctx->nccl_comm) return fail(ctx, GAML_ERR_STATE, "gaml_calc_prob_batch_gathered needs gaml_nccl_exchange_init");
+  cudaSetDevice(ctx->device);
+  const size_t n_sets = ctx->sets.size();
+  std::vector<double> partials((size_t)n_cand * std::max<size_t>(n_sets, 1) * GAML_PARTIAL_DOUBLES);
+  std::vector<int32_t> tls(n_cand);
+  int rc = calc_prob_batch_partial(ctx, n_cand, erased_idx, erased_off, added_nodes, added_walk_off, cand_added_off, partials.data(),
+                                   tls.data(), true);
+  if (rc) return rc;
+  for (int c = 0; c < n_cand; c++) {   // the partials are the sums over all shards already: one "shard" to combine
     gaml_result res;
     rc = combine(ctx, partials.data() + (size_t)c * n_sets * GAML_PARTIAL_DOUBLES, 1, tls[c], &res,
                  zeros ? zeros + (size_t)c * 2 * n_sets : nullptr);

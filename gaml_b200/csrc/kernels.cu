@@ -30,7 +30,6 @@ namespace {
 constexpr int kCapLong = 8;        // pacbio placements handled in local memory before the scratch path
 constexpr int kBlock = 256;
 constexpr int kOvfBlock = 128;
-constexpr int kStreamBlocksPerSM = 5;   // paired_stream_kernel: resident blocks per SM the register budget is set for
 
 // ---- small helpers ------------------------------------------------------------------------
 __device__ __forceinline__ int4 ldg4(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
@@ -96,18 +95,14 @@ __device__ __forceinline__ void acc_add_q(Acc& a, long long q) {
   a.hi += (q >> 63) + (long long)(nlo < (unsigned long long)q);
   a.lo = nlo;
 }
-__device__ __forceinline__ void acc_add(Acc& a, double t) {
-  if (fabs(t) < kFixLimit) acc_add_q(a, __double2ll_rn(t * kFixScale));
-  else if (t == -INFINITY) a.neginf++;
+__device__ __forceinline__ void acc_count_odd(Acc& a, double lg) {
+  if (lg == -INFINITY) a.neginf++;
   else a.bad++;
 }
-// Removes a term that an EARLIER evaluation added (same value, same total length -> the same rounded integer): the
-// running total of a paired set is then updated in O(touched reads) instead of re-summed over all reads. The counters
-// wrap modulo 2^32 here and are sign-extended when they reach the 64-bit accumulators.
-__device__ __forceinline__ void acc_sub(Acc& a, double t) {
-  if (fabs(t) < kFixLimit) acc_add_q(a, -__double2ll_rn(t * kFixScale));
-  else if (t == -INFINITY) a.neginf--;
-  else a.bad--;
+// PacBio terms are log values already (logdouble): rounded once to 2^-40 and added.
+__device__ __forceinline__ void acc_add_log(Acc& a, double t) {
+  if (fabs(t) < kFixLimit) acc_add_q(a, __double2ll_rn(t * kFixScale));
+  else acc_count_odd(a, t);
 }
 
 // Block-wide exact sum -> per-set global accumulators {limb0..3 (32-bit limbs in u64), floored, neginf, bad}.
@@ -170,9 +165,16 @@ struct PublishArgs {
   uint32_t* done;
   uint32_t epoch;
   int32_t state_add;
+  long long ql;        // FIX(log 2L): subtracted once per read whose term is a logarithm of its value (0 for PacBio sets)
+  long long n_reads;
+  unsigned long long* const* peer_bufs;   // multi-GPU: every rank's exchange buffer (peer memory), or null
+  int32_t peer_world;
+  uint32_t peer_line;
+  double* part_out;
 };
 __device__ __forceinline__ PublishArgs publish_args(const ScoreParams& P, uint32_t* ticket) {
-  return PublishArgs{P.accum, P.state_acc, P.out, P.error_flag, P.ovf_count, P.scratch_cursor, ticket, P.done, P.epoch, P.state_add};
+  return PublishArgs{P.accum, P.state_acc, P.out, P.error_flag, P.ovf_count, P.scratch_cursor, ticket, P.done, P.epoch, P.state_add,
+                     P.ql, (long long)P.n_reads, P.peer_bufs, P.peer_world, P.peer_line, P.part_out};
 }
 
 // Called by the first warp of the completing block. Lane 0 assembles the eight result words; lanes 0..7 then store
@@ -199,10 +201,14 @@ __device__ __noinline__ void publish_set(PublishArgs A) {
       A.state_acc[1] = (unsigned long long)(x >> 64);
       for (int j = 4; j < 7; j++) A.state_acc[j - 2] = a[j];
     }
-    const __int128 v = (__int128)x;
+    // every read contributes exactly one term; those that are neither floored nor non-finite are FIX(LOG p) and still owe
+    // their - FIX(log 2L) (see acc_term): one exact integer product
+    const long long n_log = A.n_reads - (long long)a[4] - (long long)a[5] - (long long)a[6];
+    const __int128 v = (__int128)x - (__int128)n_log * (__int128)A.ql;
+    const unsigned __int128 xv = (unsigned __int128)v;
     const unsigned long long scratch = __ldcg(A.scratch_cursor);   // placements parked in the scratch arena
     w[0] = (unsigned long long)__double_as_longlong((double)(long long)(v >> 40));
-    w[1] = (unsigned long long)__double_as_longlong((double)(unsigned long long)(x & (((unsigned __int128)1 << 40) - 1)));
+    w[1] = (unsigned long long)__double_as_longlong((double)(unsigned long long)(xv & (((unsigned __int128)1 << 40) - 1)));
     w[2] = (unsigned long long)__double_as_longlong((double)a[4]);
     w[3] = (unsigned long long)__double_as_longlong((double)a[5]);
     w[4] = (unsigned long long)__double_as_longlong((double)a[6]);
@@ -220,6 +226,72 @@ __device__ __noinline__ void publish_set(PublishArgs A) {
     if (lane == j) mine = v;
   }
   if (lane < 8) reinterpret_cast<unsigned long long*>(A.out)[lane] = mine;
+  if (A.part_out && lane < 8) reinterpret_cast<unsigned long long*>(A.part_out)[lane] = mine;
+  if (A.peer_bufs) {
+    // the all-gather of a multi-GPU evaluation, fused into the kernel: one 64-byte store per rank over NVLink peer
+    // memory. The line validates itself (epoch + checksum), so no flag, fence or ordering is needed on this side.
+    for (int p = 0; p < A.peer_world; p++) {
+      unsigned long long* dst = A.peer_bufs[p] + (size_t)A.peer_line * kResultStride;
+      if (lane < 8) dst[lane] = mine;
+    }
+    __threadfence_system();
+  }
+}
+
+// Last kernel of a multi-GPU evaluation's chain (one block): waits until the lines of ALL ranks for this evaluation have
+// arrived in this rank's exchange buffer — each thread polls one (rank, set) line until its epoch word and checksum are
+// right — copies them to the host-mapped gather area and then writes one flag line the host spins on. A peer that never
+// publishes (it died, or the ranks fell out of lockstep) is given `timeout_ns`; the flag line then carries status 1.
+__global__ void __launch_bounds__(kResultStride * 32) exchange_gather_kernel(const unsigned long long* lines, int world, int n_sets, int max_sets,
+                                                                              uint32_t epoch, unsigned long long* host_lines,
+                                                                              unsigned long long* host_flag, unsigned long long timeout_ns) {
+  pdl_release();
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  const unsigned long long want = (unsigned long long)__double_as_longlong((double)epoch);
+  const unsigned long long t0 = global_ns();
+  for (int i = threadIdx.x; i < world * n_sets; i += blockDim.x) {
+    const int rk = i / n_sets, st = i % n_sets;
+    const volatile unsigned long long* src = lines + ((size_t)rk * max_sets + st) * kResultStride;
+    unsigned long long w[8];
+    for (;;) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) w[j] = src[j];
+      unsigned long long sum = kResultSeal;
+#pragma unroll
+      for (int j = 0; j < 7; j++) sum ^= w[j];
+      if (w[6] == want && w[7] == sum) break;
+      if (global_ns() - t0 > timeout_ns) {
+        s_fail = 1;
+        break;
+      }
+    }
+    unsigned long long* dst = host_lines + (size_t)i * kResultStride;
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[j] = w[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    unsigned long long w[8] = {(unsigned long long)s_fail, 0, 0, 0, 0, 0, want, kResultSeal};
+    for (int j = 0; j < 7; j++) w[7] ^= w[j];
+    host_flag[threadIdx.x] = w[threadIdx.x];
+  }
+}
+
+// After a collective library's all-reduce of the ranks' lines (sums of doubles: exact, every field is an integer far
+// below 2^53): rebuild one valid line per set — summed partials, this evaluation's epoch, checksum — in host-mapped memory.
+__global__ void reduced_publish_kernel(const double* reduced, int n_sets, uint32_t epoch, unsigned long long* host_lines) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sets) return;
+  unsigned long long w[8];
+  for (int j = 0; j < 6; j++) w[j] = (unsigned long long)__double_as_longlong(reduced[(size_t)s * kResultStride + j]);
+  w[6] = (unsigned long long)__double_as_longlong((double)epoch);
+  w[7] = kResultSeal;
+  for (int j = 0; j < 7; j++) w[7] ^= w[j];
+  __threadfence_system();
+  for (int j = 0; j < 8; j++) host_lines[(size_t)s * kResultStride + j] = w[j];
 }
 
 // Block-level tail of a set's kernels. early = false: called by every block of the set's LAST kernel, the block that
@@ -253,7 +325,6 @@ __device__ __forceinline__ void finish_set_if_complete(const ScoreParams& P) { f
 // Rare paths kept out of line so the compiler cannot if-convert them into the hot loops (ncu showed the IEEE
 // division being issued, predicated off, on every iteration when it was inline).
 __device__ __noinline__ double slow_log(double v) { return log(v); }
-__device__ __noinline__ double slow_div(double p, double d) { return __ddiv_rn(p, d); }
 
 __device__ __forceinline__ double table_log(const double2* __restrict__ tab, double v) {
   const long long ix = __double_as_longlong(v);
@@ -273,20 +344,55 @@ __device__ __forceinline__ double table_log(const double2* __restrict__ tab, dou
   return fma((double)k, 0.693147180559945309417232121458, e.y) + p;
 }
 
-// max(p / (2 total_len), thr), its log, and the floored flag: GetTotalProb, graph.cc:1505-1512.
-// The quotient is formed by Markstein's correction (q = p*y; q' = q + (p - q d) y with y = RN(1/d), two fmas),
-// which is the correctly rounded p/d; as a belt-and-braces guard the comparison that decides `floored` falls
-// back to the IEEE division whenever the quotient is within 2^-48 of the threshold.
-__device__ __forceinline__ double floored_term(const ScoreParams& P, const double2* log_tab, double p, double thr,
-                                               unsigned& floored) {
-  double q = __dmul_rn(p, P.rcp_two_len);
-  q = fma(fma(-q, P.two_len_d, p), P.rcp_two_len, q);
-  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = slow_div(p, P.two_len_d);
-  if (q < thr) { floored++; q = thr; }
-  return table_log(log_tab, q);
+// The per-read log term of GetTotalProb (graph.cc:1495-1537): log max(p / 2L, thr), restated so that nothing in it
+// needs a division or depends on L except one comparison:
+//   floored  <=>  RN(p / 2L) < thr  <=>  p < pstar, pstar = the smallest double whose IEEE quotient by 2L reaches thr
+//                 (found on the host per evaluation and read length: the decision is EXACTLY the reference's);
+//   floored:   FIX(log thr)                 (host table, glibc log of the reference's own threshold)
+//   otherwise: FIX(LOG p) - FIX(log 2L)     (log(p / 2L) = log p - log 2L to ~1e-14 absolute, far inside the 1e-12 per-read
+//                 bar; FIX = rounded once to 2^-40). Only the first part is accumulated here; the block that publishes a
+//                 set subtracts (number of such reads) * FIX(log 2L) from the exact integer sum (publish_set).
+// LOG p depends on the read's value alone, so it can be tabulated next to the pair term (TermEntry), and every kernel —
+// streaming, delta, total, many-placement, batch — forms bit-identical integers for the same value, which is what lets
+// the running total swap a read's old term for its new one.
+__device__ __forceinline__ void acc_term(Acc& a, unsigned& floored, const double2* log_tab, double p, double pstar, long long qthr) {
+  if (p < pstar) {
+    floored++;
+    acc_add_q(a, qthr);
+    return;
+  }
+  const double lg = table_log(log_tab, p);
+  if (fabs(lg) < kFixLimit) acc_add_q(a, __double2ll_rn(lg * kFixScale));
+  else acc_count_odd(a, lg);
 }
-__device__ __forceinline__ double floored_term(const ScoreParams& P, double p, double thr, unsigned& floored) {
-  return floored_term(P, static_cast<const double2*>(P.log_tab), p, thr, floored);
+// Removes a term an EARLIER evaluation added for the same value at the same total length (same pstar): the running total
+// of a paired set is updated in O(touched reads). The counters wrap modulo 2^32 and are sign-extended in block_accumulate.
+__device__ __forceinline__ void acc_term_sub(Acc& a, unsigned& floored, const double2* log_tab, double p, double pstar, long long qthr) {
+  if (p < pstar) {
+    floored--;
+    acc_add_q(a, -qthr);
+    return;
+  }
+  const double lg = table_log(log_tab, p);
+  if (fabs(lg) < kFixLimit) acc_add_q(a, -__double2ll_rn(lg * kFixScale));
+  else if (lg == -INFINITY) a.neginf--;
+  else a.bad--;
+}
+// Floor test and floored term of a read with packed lengths ll (paired) or length ll (single).
+__device__ __forceinline__ void term_consts(const ScoreParams& P, uint32_t len_index, double& pstar, long long& qthr) {
+  pstar = __ldg(P.pstar_tab + len_index);
+  qthr = __ldg(P.qthr_tab + len_index);
+}
+__device__ __forceinline__ void acc_read(const ScoreParams& P, Acc& a, unsigned& floored, double p, uint32_t len_index) {
+  double pstar;
+  long long qthr;
+  term_consts(P, len_index, pstar, qthr);
+  acc_term(a, floored, static_cast<const double2*>(P.log_tab), p, pstar, qthr);
+}
+// the fixed-point logarithm of a value for the term tables: kTermOdd when it is not finite
+__device__ __forceinline__ long long fix_log(const double2* log_tab, double p) {
+  const double lg = table_log(log_tab, p);
+  return fabs(lg) < kFixLimit ? __double2ll_rn(lg * kFixScale) : kTermOdd;
 }
 
 // ---- placement enumeration ----------------------------------------------------------------
@@ -771,7 +877,7 @@ __device__ __forceinline__ void tier2_tiles(const ScoreParams& P, int* s_tile, A
     }
     if (st > 0) {
       P.values[r] = acc;
-      acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+      acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
     } else if (st < 0) {
       push_overflow(P, r);
     }
@@ -789,13 +895,15 @@ __device__ __forceinline__ void tier2_tiles(const ScoreParams& P, int* s_tile, A
 struct Rec8 { uint32_t w; int pos; };
 __device__ __forceinline__ Rec8 rec8(uint32_t a, uint32_t b) { return Rec8{a, (int)b}; }
 
-// One tier-2 read, written like tier1_body: every load that does not depend on another is requested at once (slot words
-// of all records, pow tables, threshold; then the insert pdf of all combinations), filters are predicates, no branches.
+// One tier-2 read, written like the tier-1 bodies: every load that does not depend on another is requested at once (slot
+// words of all records; then, for all record combinations, the pair term and its logarithm from the set's term table —
+// or the probability-table entries and the insert pdf when the set has none), filters are predicates, no branches.
 // Same rules as tier2_read: status 1 = scored (acc), 0 = a live key occurs several times (the multi pass's read),
 // -1 = the enumeration order matters (duplicate placement with a different payload, or three and more pair terms).
+// qv = the fixed-point logarithm of acc when exactly one tabulated term makes up the value (else kTermOdd: take the log).
 template <int N1, int N2>
 __device__ __forceinline__ int tier2_packed_read(const ScoreParams& P, const int4* __restrict__ sa1, const int4* __restrict__ sa2,
-                                                 const Rec8 (&x)[2], const Rec8 (&y)[2], uint32_t ll, double& acc, double& thr) {
+                                                 const Rec8 (&x)[2], const Rec8 (&y)[2], uint32_t ll, double& acc, long long& qv) {
   const int l1 = ll & 0xffff, l2 = ll >> 16;
   int4 ox[2], oy[2];
 #pragma unroll
@@ -803,26 +911,33 @@ __device__ __forceinline__ int tier2_packed_read(const ScoreParams& P, const int
     ox[i] = __ldg(sa1 + (x[i < N1 ? i : 0].w & kPackKeyMask));
     oy[i] = __ldg(sa2 + (y[i < N2 ? i : 0].w & kPackKeyMask));
   }
-  double px[2], py[2];
+  int ex[2], ey[2];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
-    const int ex = (int)((x[i < N1 ? i : 0].w >> kPackKeyBits) & kPackEdMask), ey = (int)((y[i < N2 ? i : 0].w >> kPackKeyBits) & kPackEdMask);
-    px[i] = __dmul_rn(__ldg(P.m[0].pow_mismatch + ex), __ldg(P.m[0].pow_match + (l1 - ex)));
-    py[i] = __dmul_rn(__ldg(P.m[1].pow_mismatch + ey), __ldg(P.m[1].pow_match + (l2 - ey)));
+    ex[i] = (int)((x[i < N1 ? i : 0].w >> kPackKeyBits) & kPackEdMask);
+    ey[i] = (int)((y[i < N2 ? i : 0].w >> kPackKeyBits) & kPackEdMask);
   }
-  thr = __ldg(P.thr_tab + l1 + l2);
+  const TermEntry* __restrict__ tq = P.tq ? static_cast<const TermEntry*>(P.tq) + 1 : nullptr;   // (entry 0: the fast records' "no pair term")
+  double px[2], py[2];
+  if (!tq) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      px[i] = __dmul_rn(__ldg(P.m[0].pow_mismatch + ex[i]), __ldg(P.m[0].pow_match + (l1 - ex[i])));
+      py[i] = __dmul_rn(__ldg(P.m[1].pow_mismatch + ey[i]), __ldg(P.m[1].pow_match + (l2 - ey[i])));
+    }
+  }
   bool lx[2], ly[2], multi = false;
   int wx[2], wy[2], qx[2], qy[2], orx[2], ory[2];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     const uint32_t fx = (uint32_t)ox[i].x, fy = (uint32_t)oy[i].x;
     const bool hx = i < N1, hy = i < N2;
-    const bool ex = hx && (fx & 0x7fffffffu) == P.epoch, ey = hy && (fy & 0x7fffffffu) == P.epoch;
-    multi |= (ex && (fx >> 31)) || (ey && (fy >> 31));
+    const bool vx = hx && (fx & 0x7fffffffu) == P.epoch, vy = hy && (fy & 0x7fffffffu) == P.epoch;
+    multi |= (vx && (fx >> 31)) || (vy && (fy >> 31));
     wx[i] = ox[i].y; wy[i] = oy[i].y;
     qx[i] = wrap_add(x[hx ? i : 0].pos, ox[i].z); qy[i] = wrap_add(y[hy ? i : 0].pos, oy[i].z);
-    lx[i] = ex && qx[i] >= ox[i].w;   // graph.cc:577
-    ly[i] = ey && qy[i] >= oy[i].w;
+    lx[i] = vx && qx[i] >= ox[i].w;   // graph.cc:577
+    ly[i] = vy && qy[i] >= oy[i].w;
     orx[i] = (int)((x[hx ? i : 0].w >> 29) & 1u); ory[i] = (int)((y[hy ? i : 0].w >> 29) & 1u);
   }
   bool order = false;
@@ -840,7 +955,7 @@ __device__ __forceinline__ int tier2_packed_read(const ScoreParams& P, const int
   }
   bool ok[2][2];
   int dist[2][2];
-  int nt = 0;
+  int nt = 0, nok = 0;
 #pragma unroll
   for (int i = 0; i < N1; i++) {
 #pragma unroll
@@ -850,23 +965,82 @@ __device__ __forceinline__ int tier2_packed_read(const ScoreParams& P, const int
       const bool term = lx[i] && ly[j] && wx[i] == wy[j] && orx[i] != ory[j] && orx[i] == (fwd ? 0 : 1);
       nt += term ? 1 : 0;
       ok[i][j] = term && (unsigned)d < (unsigned)P.ins_n;
+      nok += ok[i][j] ? 1 : 0;
       dist[i][j] = ok[i][j] ? d : 0;
     }
   }
   double t[2][2];
+  long long tqv[2][2];
+  if (tq) {
+    const int lim = 1 << P.tq_shift;
+    bool untab = false;   // an edit distance beyond the table: (p1*p2)*ins from the probability tables instead
+    TermEntry e[2][2];
 #pragma unroll
-  for (int i = 0; i < N1; i++) {
+    for (int i = 0; i < N1; i++) {
 #pragma unroll
-    for (int j = 0; j < N2; j++) t[i][j] = __dmul_rn(__dmul_rn(px[i], py[j]), __ldg(P.ins_tab + dist[i][j]));   // (p1*p2)*ins
+      for (int j = 0; j < N2; j++) {
+        const bool fit = ex[i] < lim && ey[j] < lim;
+        untab |= ok[i][j] && !fit;
+        const size_t idx = fit ? (size_t)((ex[i] << P.tq_shift) | ey[j]) * (size_t)P.ins_n + (size_t)dist[i][j] : 0;
+        const int4 w = __ldg(reinterpret_cast<const int4*>(tq + idx));
+        e[i][j].t = __hiloint2double(w.y, w.x);
+        e[i][j].q = (long long)(((unsigned long long)(uint32_t)w.w << 32) | (uint32_t)w.z);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N1; i++) {
+#pragma unroll
+      for (int j = 0; j < N2; j++) { t[i][j] = e[i][j].t; tqv[i][j] = e[i][j].q; }
+    }
+    if (untab) {
+#pragma unroll
+      for (int i = 0; i < N1; i++) {
+#pragma unroll
+        for (int j = 0; j < N2; j++) {
+          if (ok[i][j] && !(ex[i] < lim && ey[j] < lim)) {
+            t[i][j] = __dmul_rn(__dmul_rn(__ldg(P.uni_prob[0] + ex[i]), __ldg(P.uni_prob[1] + ey[j])), __ldg(P.ins_tab + dist[i][j]));
+            tqv[i][j] = kTermOdd;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N1; i++) {
+#pragma unroll
+      for (int j = 0; j < N2; j++) {
+        t[i][j] = __dmul_rn(__dmul_rn(px[i], py[j]), __ldg(P.ins_tab + dist[i][j]));   // (p1*p2)*ins
+        tqv[i][j] = kTermOdd;
+      }
+    }
   }
   // at most two terms survive below: 0 + a + b in any order is the same double, and absent terms are exact zeros
   acc = 0.0;
+  qv = kTermOdd;
 #pragma unroll
   for (int i = 0; i < N1; i++) {
 #pragma unroll
-    for (int j = 0; j < N2; j++) acc = __dadd_rn(acc, ok[i][j] ? t[i][j] : 0.0);
+    for (int j = 0; j < N2; j++) {
+      acc = __dadd_rn(acc, ok[i][j] ? t[i][j] : 0.0);
+      if (ok[i][j] && nok == 1) qv = tqv[i][j];
+    }
   }
   return multi ? 0 : ((order || nt > 2) ? -1 : 1);
+}
+
+// Adds the term of a value whose fixed-point logarithm may be known already (qv != kTermOdd).
+__device__ __forceinline__ void acc_term_known(Acc& a, unsigned& floored, const double2* log_tab, double p, long long qv,
+                                               double pstar, long long qthr) {
+  if (p < pstar) {
+    floored++;
+    acc_add_q(a, qthr);
+  } else if (qv != kTermOdd) {
+    acc_add_q(a, qv);
+  } else {
+    const double lg = table_log(log_tab, p);
+    if (fabs(lg) < kFixLimit) acc_add_q(a, __double2ll_rn(lg * kFixScale));
+    else acc_count_odd(a, lg);
+  }
 }
 
 // Tier-2 phase from the packed entries: tiles of 256 list entries, a block's first tile is its own index.
@@ -887,7 +1061,8 @@ __device__ __forceinline__ void tier2_packed_tiles(const ScoreParams& P, int* s_
     const uint32_t j = (uint32_t)(k - P.class_begin[cls]);
     int r, st;
     uint32_t ll;
-    double acc = 0.0, thr;
+    double acc = 0.0;
+    long long qv = kTermOdd;
     if (cls < 3) {
       const uint32_t n_c = (uint32_t)(P.class_begin[cls + 1] - P.class_begin[cls]);
       const uint4* base = pk + P.t2base[cls];
@@ -896,25 +1071,27 @@ __device__ __forceinline__ void tier2_packed_tiles(const ScoreParams& P, int* s_
       ll = u0.y;
       if (cls == 0) {
         const Rec8 x[2] = {rec8(u0.z, u0.w), rec8(u0.z, u0.w)}, y[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)};
-        st = tier2_packed_read<1, 2>(P, sa1, sa2, x, y, ll, acc, thr);
+        st = tier2_packed_read<1, 2>(P, sa1, sa2, x, y, ll, acc, qv);
       } else if (cls == 1) {
         const Rec8 x[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)}, y[2] = {rec8(u0.z, u0.w), rec8(u0.z, u0.w)};
-        st = tier2_packed_read<2, 1>(P, sa1, sa2, x, y, ll, acc, thr);
+        st = tier2_packed_read<2, 1>(P, sa1, sa2, x, y, ll, acc, qv);
       } else {
         const uint4 u2 = ldg_stream(base + 2 * n_c + j);
         const Rec8 x[2] = {rec8(u1.x, u1.y), rec8(u1.z, u1.w)}, y[2] = {rec8(u2.x, u2.y), rec8(u2.z, u2.w)};
-        st = tier2_packed_read<2, 2>(P, sa1, sa2, x, y, ll, acc, thr);
+        st = tier2_packed_read<2, 2>(P, sa1, sa2, x, y, ll, acc, qv);
       }
     } else {   // (0,2), (2,0): no pair term
       const int4 dsc = ldg4(static_cast<const int4*>(P.cdesc) + k);
       r = dsc.x;
       ll = (uint32_t)dsc.y;
       st = 1;
-      thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
     }
     if (st > 0) {
       P.values[r] = acc;
-      acc_add(sum, floored_term(P, log_tab, acc, thr, floored));
+      double pstar;
+      long long qthr;
+      term_consts(P, (ll & 0xffff) + (ll >> 16), pstar, qthr);
+      acc_term_known(sum, floored, log_tab, acc, qv, pstar, qthr);
     } else if (st < 0) {
       push_overflow(P, r);
     }
@@ -1009,22 +1186,29 @@ __device__ __forceinline__ void rare_tiles(const ScoreParams& P, int* s_tile, Ac
       continue;
     }
     P.values[r] = acc;
-    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
   }
 }
 
 // Tier-1 tile body: kR reads per lane of one warp tile, every step written without branches so that the kR
-// dependent chains (first records -> {slot words, pow tables, threshold} -> insert pdf -> products -> quotient -> log)
-// are issued side by side: one trip per memory level for all of them. The filters of the pair term (liveness, skip rule
-// graph.cc:577, one walk, orientation/order graph.cc:1864-1875, insert-table range) are predicates
-// (a dropped pair is a term of +0.0, which is what the state holds for such a read); the two rare fix-ups (IEEE division
-// next to the floor threshold, libm log for 0/denormal/non-finite) are taken once, after the common work of all kR reads.
-template <bool kCov, bool kPacked, int kR>
+// dependent chains (packed record -> {slot words, term-table entry} -> select -> accumulate) are issued side by side: one
+// trip per memory level for all of them. The filters of the pair term (liveness, skip rule graph.cc:577, one walk,
+// orientation/order graph.cc:1864-1875, insert-table range) are predicates (a dropped pair is a term of +0.0, which is
+// what the state holds for such a read); the rare fix-ups (mates under different keys, an edit distance beyond the term
+// table, a non-finite logarithm) are taken once, after the common work of all kR reads.
+//   kTab: the set has a term table (uniform lengths) and a combined slot table: the pair term AND its fixed-point
+//         logarithm come from ONE 16-byte gather, requested together with the slot words (for mates under the same key
+//         the insert distance is a property of the two records: both share the key's offset in the walk);
+//   else: the term is formed from the probability tables and the insert pdf, the logarithm by table_log.
+template <bool kCov, bool kPacked, bool kTab, int kR>
 __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __restrict__ src1, const uint4* __restrict__ src2,
                                            int lane, const int4* __restrict__ sa1, const int4* __restrict__ sa2,
-                                           const double2* __restrict__ log_tab, int q_first, int n, Acc& sum, unsigned& floored) {
-  // level 1: the records of this lane's kR reads (read q_first + 32 j + lane; reads past the end are clamped to the last
-  // one and masked out below) and the lengths unless the whole set shares them
+                                           const double2* __restrict__ log_tab, int q_first, int n, Acc& sum, unsigned& floored,
+                                           const uint32_t* __restrict__ ridx = nullptr) {
+  static_assert(!kTab || (kPacked && !kCov), "the term table goes with the packed pairs");
+  // level 1: the records of this lane's kR reads (read q_first + 32 j + lane — or, with a list, the reads at those list
+  // positions; positions past the end are clamped to the last one and masked out below) and the lengths unless the whole
+  // set shares them
   int qi[kR];
   bool valid[kR];
 #pragma unroll
@@ -1032,6 +1216,10 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
     const int q = q_first + 32 * j + lane;
     valid[j] = q < n;
     qi[j] = min(q, n - 1);
+  }
+  if (ridx) {
+#pragma unroll
+    for (int j = 0; j < kR; j++) qi[j] = (int)__ldg(ridx + qi[j]);
   }
   uint4 u1[kR], u2[kR];
 #pragma unroll
@@ -1042,7 +1230,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
   int key1[kR], key2[kR], pos1[kR], pos2[kR], e1[kR], e2[kR], xo[kR], yo[kR];
   bool has1[kR], has2[kR], tier2[kR], same[kR];
   uint32_t ll[kR];
-  if (P.lens_uniform) {
+  if (kTab || P.lens_uniform) {
 #pragma unroll
     for (int j = 0; j < kR; j++) ll[j] = P.uniform_ll;
   } else {
@@ -1085,9 +1273,8 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       pos2[j] = rw2.y;
     }
   }
-  // level 2: slot words of both keys, pow tables, floor threshold (L1/L2 resident)
+  // level 2: slot words of both keys (L1/L2 resident) and, with a term table, the entry the records themselves point at
   int4 o1[kR], o2[kR];
-  double pa[kR], pb[kR], thr[kR];
   if (kPacked && P.comb) {
     // one 256-bit gather per read: {mate 1's slot word, the same key's word in mate 2's store}; the few pairs whose mates
     // lie under different keys take mate 2's word from its own table (predicated second gather)
@@ -1099,9 +1286,6 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       o1[j] = make_int4((int)a.x, (int)a.y, (int)a.z, (int)a.w);
       o2[j] = make_int4((int)b.x, (int)b.y, (int)b.z, (int)b.w);
     }
-#pragma unroll
-    for (int j = 0; j < kR; j++)
-      if (!same[j]) o2[j] = __ldg(sa2 + key2[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < kR; j++) {
@@ -1109,23 +1293,26 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
       o2[j] = __ldg(sa2 + key2[j]);
     }
   }
-  if (kPacked && P.uni_prob[0]) {
-    // set-uniform lengths: the alignment probability depends on the edit distance alone (one table entry per mate
-    // instead of two entries and a product) and the threshold is a kernel parameter
-#pragma unroll
-    for (int j = 0; j < kR; j++) {
-      pa[j] = __ldg(P.uni_prob[0] + e1[j]);
-      pb[j] = __ldg(P.uni_prob[1] + e2[j]);
-      thr[j] = P.uni_thr;
-    }
-  } else {
+  const int4* __restrict__ tq = static_cast<const int4*>(P.tq) + 1;   // (entry 0 is the fast records' "no pair term")
+  int4 te[kR];
+  unsigned tix[kR];
+  bool fit[kR];
+  if (kTab) {
+    const int lim = 1 << P.tq_shift;
 #pragma unroll
     for (int j = 0; j < kR; j++) {
       const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
-      pa[j] = __dmul_rn(__ldg(P.m[0].pow_mismatch + e1[j]), __ldg(P.m[0].pow_match + (l1 - e1[j])));
-      pb[j] = __dmul_rn(__ldg(P.m[1].pow_mismatch + e2[j]), __ldg(P.m[1].pow_match + (l2 - e2[j])));
-      thr[j] = __ldg(P.thr_tab + l1 + l2);
+      const bool fwd = pos1[j] < pos2[j];
+      const int d = fwd ? pos2[j] - pos1[j] + l2 : pos1[j] - pos2[j] + l1;
+      fit[j] = e1[j] < lim && e2[j] < lim;
+      tix[j] = (fit[j] && (unsigned)d < (unsigned)P.ins_n) ? (unsigned)((e1[j] << P.tq_shift) | e2[j]) * (unsigned)P.ins_n + (unsigned)d : 0u;
+      te[j] = __ldg(tq + tix[j]);
     }
+  }
+  if (kPacked && P.comb) {
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+      if (!same[j]) o2[j] = __ldg(sa2 + key2[j]);
   }
   bool mine[kR], ok[kR];
   int dist[kR], px[kR], py[kR];
@@ -1145,79 +1332,184 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
     ok[j] = mine[j] && placed && xo[j] != yo[j] && xo[j] == (fwd ? 0 : 1) && (unsigned)d < (unsigned)P.ins_n;
     dist[j] = ok[j] ? d : 0;
   }
-  double acc[kR];
+  // floor test and floored term of each read (a kernel parameter when the whole set shares the lengths)
+  double pstar[kR];
+  long long qthr[kR];
 #pragma unroll
   for (int j = 0; j < kR; j++) {
-    const double ins = __ldg(P.ins_tab + dist[j]);
-    const double t = __dmul_rn(__dmul_rn(pa[j], pb[j]), ins);                        // (p1*p2)*ins, graph.cc:1889
-    const double signed_t = (o1[j].y < P.n_erased) ? __dsub_rn(0.0, t) : __dadd_rn(0.0, t);
-    acc[j] = ok[j] ? signed_t : 0.0;
-    if (kCov) {
-      if (ok[j]) emit_cov(P, o1[j].y, px[j], py[j], (int)(ll[j] >> 16), t);
+    if (kTab || P.lens_uniform) {
+      pstar[j] = P.uni_pstar;
+      qthr[j] = P.uni_qthr;
+    } else {
+      term_consts(P, (ll[j] & 0xffff) + (ll[j] >> 16), pstar[j], qthr[j]);
     }
   }
-  // max(p / (2 total_len), thr): Markstein quotient, IEEE division next to the threshold (floored_term)
-  double q[kR];
-  bool near_thr = false;
-#pragma unroll
-  for (int j = 0; j < kR; j++) {
-    double v = __dmul_rn(acc[j], P.rcp_two_len);
-    v = fma(fma(-v, P.two_len_d, acc[j]), P.rcp_two_len, v);
-    q[j] = v;
-    near_thr |= fabs(v - thr[j]) <= thr[j] * 3.5527136788005009e-15;
-  }
-  if (near_thr) {
-#pragma unroll
-    for (int j = 0; j < kR; j++)
-      if (fabs(q[j] - thr[j]) <= thr[j] * 3.5527136788005009e-15) q[j] = slow_div(acc[j], P.two_len_d);
-  }
-  unsigned fl[kR];
-  double lg[kR];
-  bool special = false;
-#pragma unroll
-  for (int j = 0; j < kR; j++) {
-    fl[j] = q[j] < thr[j] ? 1u : 0u;
-    q[j] = fl[j] ? thr[j] : q[j];
-    // table_log's fast path, computed unconditionally (garbage, not a trap, for 0/denormal/non-finite input)
-    const long long ix = __double_as_longlong(q[j]);
-    special |= (unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull;
-    const long long tmp = ix - 0x3fe6000000000000ll;
-    const int i = (int)((tmp >> 45) & 127);
-    const long long k = tmp >> 52;
-    const double z = __longlong_as_double(ix - (tmp & 0xfff0000000000000ll));
-    const double2 e = log_tab[i];
-    const double r = fma(z, e.x, -1.0);
-    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-    p = fma(r, p, 0.2);
-    p = fma(r, p, -0.25);
-    p = fma(r, p, 1.0 / 3.0);
-    p = fma(r, p, -0.5);
-    p = fma(r * r, p, r);
-    lg[j] = fma((double)k, 0.693147180559945309417232121458, e.y) + p;
-  }
-  if (special) {
+  // the pair term (p1*p2)*ins (graph.cc:1889) and, where known, its fixed-point logarithm
+  double acc[kR];
+  long long qv[kR];
+  if (kTab) {
+    bool again = false, untab = false;
 #pragma unroll
     for (int j = 0; j < kR; j++) {
-      const long long ix = __double_as_longlong(q[j]);
-      if ((unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) lg[j] = slow_log(q[j]);
+      const unsigned want = (unsigned)((e1[j] << P.tq_shift) | e2[j]) * (unsigned)P.ins_n + (unsigned)dist[j];
+      again |= ok[j] && fit[j] && want != tix[j];   // mates under different keys: the distance depends on the walk
+      untab |= ok[j] && !fit[j];
     }
+    if (again) {
+#pragma unroll
+      for (int j = 0; j < kR; j++) {
+        const unsigned want = (unsigned)((e1[j] << P.tq_shift) | e2[j]) * (unsigned)P.ins_n + (unsigned)dist[j];
+        if (ok[j] && fit[j] && want != tix[j]) te[j] = __ldg(tq + want);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      acc[j] = ok[j] ? __hiloint2double(te[j].y, te[j].x) : 0.0;
+      qv[j] = (long long)(((unsigned long long)(uint32_t)te[j].w << 32) | (uint32_t)te[j].z);
+    }
+    if (untab) {
+#pragma unroll
+      for (int j = 0; j < kR; j++) {
+        if (ok[j] && !fit[j]) {
+          acc[j] = __dmul_rn(__dmul_rn(__ldg(P.uni_prob[0] + e1[j]), __ldg(P.uni_prob[1] + e2[j])), __ldg(P.ins_tab + dist[j]));
+          qv[j] = fix_log(log_tab, acc[j]);
+        }
+      }
+    }
+  } else {
+    double pa[kR], pb[kR];
+    if (kPacked && P.uni_prob[0]) {
+      // set-uniform lengths: the alignment probability depends on the edit distance alone (one table entry per mate)
+#pragma unroll
+      for (int j = 0; j < kR; j++) {
+        pa[j] = __ldg(P.uni_prob[0] + e1[j]);
+        pb[j] = __ldg(P.uni_prob[1] + e2[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kR; j++) {
+        const int l1 = ll[j] & 0xffff, l2 = ll[j] >> 16;
+        pa[j] = __dmul_rn(__ldg(P.m[0].pow_mismatch + e1[j]), __ldg(P.m[0].pow_match + (l1 - e1[j])));
+        pb[j] = __dmul_rn(__ldg(P.m[1].pow_mismatch + e2[j]), __ldg(P.m[1].pow_match + (l2 - e2[j])));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const double ins = __ldg(P.ins_tab + dist[j]);
+      const double t = __dmul_rn(__dmul_rn(pa[j], pb[j]), ins);                        // (p1*p2)*ins, graph.cc:1889
+      acc[j] = ok[j] ? t : 0.0;                                                        // a full evaluation only adds: 0 + t
+      if (kCov) {
+        if (ok[j]) emit_cov(P, o1[j].y, px[j], py[j], (int)(ll[j] >> 16), t);
+      }
+    }
+    // table_log's fast path, computed unconditionally (garbage, not a trap, for 0/denormal/non-finite input)
+    bool special = false;
+    double lg[kR];
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+      const long long ix = __double_as_longlong(acc[j]);
+      special |= mine[j] && !(acc[j] < pstar[j]) && (unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull;
+      const long long tmp = ix - 0x3fe6000000000000ll;
+      const int i = (int)((tmp >> 45) & 127);
+      const long long k = tmp >> 52;
+      const double z = __longlong_as_double(ix - (tmp & 0xfff0000000000000ll));
+      const double2 e = log_tab[i];
+      const double r = fma(z, e.x, -1.0);
+      double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+      p = fma(r, p, 0.2);
+      p = fma(r, p, -0.25);
+      p = fma(r, p, 1.0 / 3.0);
+      p = fma(r, p, -0.5);
+      p = fma(r * r, p, r);
+      lg[j] = fma((double)k, 0.693147180559945309417232121458, e.y) + p;
+    }
+    if (special) {
+#pragma unroll
+      for (int j = 0; j < kR; j++) {
+        const long long ix = __double_as_longlong(acc[j]);
+        if (!(acc[j] < pstar[j]) && (unsigned long long)(ix - 0x0010000000000000ll) >= 0x7fe0000000000000ull) lg[j] = slow_log(acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kR; j++) qv[j] = fabs(lg[j]) < kFixLimit ? __double2ll_rn(lg[j] * kFixScale) : kTermOdd;
   }
+  // floor test, state write, exact accumulation
   bool odd = false;   // a term outside the fixed-point range (log 0 = -inf, NaN): counted, not added
 #pragma unroll
   for (int j = 0; j < kR; j++) {
     if (mine[j]) P.values[qi[j]] = acc[j];
-    const bool fin = fabs(lg[j]) < kFixLimit;
+    const bool fl = acc[j] < pstar[j];
+    const long long q = fl ? qthr[j] : qv[j];
+    const bool fin = q != kTermOdd;
     odd |= mine[j] && !fin;
-    acc_add_q(sum, (mine[j] && fin) ? __double2ll_rn(lg[j] * kFixScale) : 0ll);
-    floored += mine[j] ? fl[j] : 0u;
+    acc_add_q(sum, (mine[j] && fin) ? q : 0ll);
+    floored += (mine[j] && fl) ? 1u : 0u;
   }
   if (odd) {
 #pragma unroll
-    for (int j = 0; j < kR; j++) {
-      if (mine[j] && !(fabs(lg[j]) < kFixLimit)) {
-        if (lg[j] == -INFINITY) sum.neginf++; else sum.bad++;
-      }
-    }
+    for (int j = 0; j < kR; j++)
+      if (mine[j] && !(acc[j] < pstar[j]) && qv[j] == kTermOdd) acc_count_odd(sum, table_log(log_tab, acc[j]));
+  }
+}
+
+// Tier-1 tile body over FastPair records (sets with a term table): per read one 16-byte record, one 32-byte gather of the
+// key's two slot words and one 16-byte gather of the term-table entry the record points at — both gathers depend on the
+// record only, so a tile is two memory levels — then liveness and the skip rule (graph.cc:577) as predicates, the select,
+// the state write and the exact accumulation. Everything else about the pair was resolved when the cache was committed.
+template <int kR>
+__device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4* __restrict__ fast, int lane, int q_first, int n, Acc& sum,
+                                           unsigned& floored, const double2* __restrict__ log_tab) {
+  int qi[kR];
+  bool valid[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const int q = q_first + 32 * j + lane;
+    valid[j] = q < n;
+    qi[j] = min(q, n - 1);
+  }
+  uint4 u[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) u[j] = ldg_stream(fast + qi[j]);
+  const uint4* __restrict__ comb = static_cast<const uint4*>(P.comb);
+  const int4* __restrict__ tq = static_cast<const int4*>(P.tq);
+  uint4 a[kR], b[kR];
+  int4 te[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    ldg256(comb + 2 * (u[j].x & 0x3fffffffu), a[j], b[j]);   // {epoch | multi << 31, walk, cur_pos, skip_below} of both mates
+    te[j] = __ldg(tq + u[j].w);
+  }
+  const double pstar = P.uni_pstar;
+  const long long qthr = P.uni_qthr;
+  bool odd = false;
+  double val[kR];
+  long long qv[kR];
+  bool mine[kR];
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    const bool elsewhere = (u[j].x >> 31) != 0u, noterm = ((u[j].x >> 30) & 1u) != 0u;
+    const bool live = !noterm && (a[j].x & 0x7fffffffu) == P.epoch && (b[j].x & 0x7fffffffu) == P.epoch;
+    const bool multi = live && (((a[j].x | b[j].x) >> 31) != 0u);                       // paired_multi_kernel's read
+    mine[j] = valid[j] && !elsewhere && !multi;
+    const bool ok = live && wrap_add((int)u[j].y, (int)a[j].z) >= (int)a[j].w && wrap_add((int)u[j].z, (int)b[j].z) >= (int)b[j].w &&
+                    a[j].y == b[j].y;                                                   // graph.cc:577; one walk
+    val[j] = ok ? __hiloint2double(te[j].y, te[j].x) : 0.0;
+    qv[j] = (long long)(((unsigned long long)(uint32_t)te[j].w << 32) | (uint32_t)te[j].z);
+  }
+#pragma unroll
+  for (int j = 0; j < kR; j++) {
+    if (mine[j]) P.values[qi[j]] = val[j];
+    const bool fl = val[j] < pstar;
+    const long long q = fl ? qthr : qv[j];
+    const bool fin = q != kTermOdd;
+    odd |= mine[j] && !fin;
+    acc_add_q(sum, (mine[j] && fin) ? q : 0ll);
+    floored += (mine[j] && fl) ? 1u : 0u;
+  }
+  if (odd) {   // a value whose logarithm is not finite (0 under a zero threshold): counted, not added
+#pragma unroll
+    for (int j = 0; j < kR; j++)
+      if (mine[j] && !(val[j] < pstar) && qv[j] == kTermOdd) acc_count_odd(sum, table_log(log_tab, val[j]));
   }
 }
 
@@ -1225,7 +1517,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
 // first-record arrays) and then tier 2 (the static list of reads with two records on a mate, from the compact copy) in
 // one launch — both are tile loops over static data drawn from counters, so a block simply moves on to tier-2 tiles when
 // the tier-1 tiles run out, without a kernel boundary (ramp, tail, launch) in between.
-template <bool kCov, bool kPacked, int kBPS, int kR>
+template <bool kCov, bool kPacked, bool kTab, int kBPS, int kR>
 __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const ScoreParams P) {
   tl_begin(P.timeline, kTlTier1);
   const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
@@ -1245,7 +1537,7 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
   constexpr int kRecLines = kTile * 16 / 128;   // 128-byte lines of one record array per tile
   const int n_tiles = (n + kTile - 1) / kTile;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint4* __restrict__ src1 = static_cast<const uint4*>(kPacked ? P.pairs : P.m[0].first);
+  const uint4* __restrict__ src1 = static_cast<const uint4*>(kTab ? P.fast : (kPacked ? P.pairs : P.m[0].first));
   const uint4* __restrict__ src2 = static_cast<const uint4*>(P.m[1].first);
   auto prefetch_tile = [&](int t) {
     if (t >= n_tiles) return;
@@ -1269,11 +1561,25 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
   while (tile < n_tiles) {
     if (threadIdx.x == 0) s_tile[buf] = 2 * (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // the tile after next
     prefetch_tile(next);
-    tier1_body<kCov, kPacked, kR>(P, src1, src2, lane, sa1, sa2, log_tab, tile * kTile + wib * (32 * kR), n, sum, floored);
+    if (kTab) tier1_fast<kR>(P, src1, lane, tile * kTile + wib * (32 * kR), n, sum, floored, log_tab);
+    else tier1_body<kCov, kPacked, false, kR>(P, src1, src2, lane, sa1, sa2, log_tab, tile * kTile + wib * (32 * kR), n, sum, floored);
     __syncthreads();
     tile = next;
     next = s_tile[buf];
     buf ^= 1;
+  }
+  if (kTab && P.n_cross > 0) {
+    // the cross list: tier-1 reads whose mates lie under different keys (the insert distance depends on the walk) or whose
+    // edit distance is beyond the term table — the general body over the packed pairs, read ids from the list
+    const uint4* __restrict__ pairs = static_cast<const uint4*>(P.pairs);
+    constexpr int kXR = 2, kXTile = kXR * kBlock;   // (two reads per lane whatever the fast tiles use: this body is the wide one)
+    const int x_tiles = (P.n_cross + kXTile - 1) / kXTile;
+    __syncthreads();
+    int xt = blockIdx.x, xbuf = 0;
+    for (; xt < x_tiles; __syncthreads(), xt = s_tile[xbuf], xbuf ^= 1) {
+      if (threadIdx.x == 0) s_tile[xbuf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 3, 1u);
+      tier1_body<false, true, kTab, kXR>(P, pairs, src2, lane, sa1, sa2, log_tab, xt * kXTile + wib * (32 * kXR), P.n_cross, sum, floored, P.xlist);
+    }
   }
   tl_end(P.timeline, kTlTier1);
   if (P.n_main > 0) {
@@ -1333,7 +1639,7 @@ __global__ void __launch_bounds__(kOvfBlock) paired_multi_kernel(const ScorePara
     double acc = 0.0;
     if (!paired_read_any(P, r, ll, acc)) continue;
     P.values[r] = acc;
-    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
   }
   if (!P.chain_first) pdl_wait();
   block_accumulate(sum, floored, P.accum);
@@ -1347,6 +1653,7 @@ __global__ void __launch_bounds__(kOvfBlock) paired_delta_kernel(const ScorePara
   tl_begin(P.timeline, kTlDelta);
   pdl_release();
   pdl_wait();
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t total = __ldg(P.touch_prefix + P.n_touch);
@@ -1365,11 +1672,11 @@ __global__ void __launch_bounds__(kOvfBlock) paired_delta_kernel(const ScorePara
       P.values[r] = acc;
       if (P.delta_only) {   // same total length as the running total: swap this read's term in it
         const uint32_t ll = __ldg(P.lens + r);
-        const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
-        unsigned f_old = 0;
-        acc_sub(sum, floored_term(P, old, thr, f_old));
-        acc_add(sum, floored_term(P, acc, thr, floored));
-        floored -= f_old;
+        double pstar;
+        long long qthr;
+        term_consts(P, (ll & 0xffff) + (ll >> 16), pstar, qthr);
+        acc_term_sub(sum, floored, log_tab, old, pstar, qthr);
+        acc_term(sum, floored, log_tab, acc, pstar, qthr);
       }
     } else {
       push_overflow(P, r);
@@ -1394,6 +1701,7 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
     tl_end(P.timeline, kTlOverflow);
     return;
   }
+  const double2* log_tab = static_cast<const double2*>(P.log_tab);
   Acc sum = acc_zero();
   unsigned floored = 0;
   const uint32_t n = min(*P.ovf_count, P.ovf_cap);
@@ -1404,13 +1712,11 @@ __global__ void __launch_bounds__(kOvfBlock) paired_overflow_kernel(const ScoreP
     const uint32_t ll = __ldg(P.lens + r);
     if (paired_read_any(P, r, ll, acc)) P.values[r] = acc;
     if (full_mode) {
-      const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
-      acc_add(sum, floored_term(P, acc, thr, floored));
-      if (full_mode == 2) {   // delta-only evaluation: the read's previous term leaves the running total
-        unsigned f_old = 0;
-        acc_sub(sum, floored_term(P, old, thr, f_old));
-        floored -= f_old;
-      }
+      double pstar;
+      long long qthr;
+      term_consts(P, (ll & 0xffff) + (ll >> 16), pstar, qthr);
+      acc_term(sum, floored, log_tab, acc, pstar, qthr);
+      if (full_mode == 2) acc_term_sub(sum, floored, log_tab, old, pstar, qthr);   // delta-only: the previous term leaves the running total
     }
   }
   if (full_mode) {
@@ -1440,7 +1746,7 @@ __global__ void __launch_bounds__(kBlock) paired_total_kernel(const ScoreParams 
     double nv = 0.0;
     uint32_t nll = 0;
     if (have_next) { nv = P.values[rn]; nll = __ldg(P.lens + rn); }
-    acc_add(sum, floored_term(P, v, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), floored));
+    acc_read(P, sum, floored, v, (ll & 0xffff) + (ll >> 16));
     v = nv; ll = nll; r = rn; have = have_next;
   }
   block_accumulate(sum, floored, P.accum);
@@ -1496,7 +1802,7 @@ __global__ void __launch_bounds__(kBlock) single_full_kernel(const ScoreParams P
       }
     }
     P.values[r] = acc;
-    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
+    acc_read(P, sum, floored, acc, (uint32_t)len);
   }
   block_accumulate(sum, floored, P.accum);
 }
@@ -1511,7 +1817,7 @@ __global__ void __launch_bounds__(kBlock) single_complex_kernel(const ScoreParam
     double acc;
     if (single_read<true>(P, k, len, acc)) {
       P.values[r] = acc;
-      acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
+      acc_read(P, sum, floored, acc, (uint32_t)len);
     } else {
       push_overflow(P, r);
     }
@@ -1540,7 +1846,7 @@ __global__ void __launch_bounds__(kOvfBlock) single_overflow_kernel(const ScoreP
       acc = single_sum(P, a, n1, len);
     }
     P.values[r] = acc;
-    acc_add(sum, floored_term(P, acc, __ldg(P.thr_tab + len), floored));
+    acc_read(P, sum, floored, acc, (uint32_t)len);
   }
   block_accumulate(sum, floored, P.accum);
   finish_set(P);
@@ -1602,7 +1908,7 @@ __global__ void __launch_bounds__(kBlock) pacbio_full_kernel(const ScoreParams P
       for (int x = 0; x < n; x++) acc = lse_add(acc, a[x].logprob);
     }
     P.values[r] = acc;
-    acc_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+    acc_add_log(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
   }
   block_accumulate(sum, floored, P.accum);
 }
@@ -1632,7 +1938,7 @@ __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreP
     const double acc = warp_lse(part);
     if (lane == 0) {
       P.values[r] = acc;
-      acc_add(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
+      acc_add_log(sum, pacbio_floor(P, acc, (int)__ldg(P.lens + r), floored));
     }
   }
   block_accumulate(sum, floored, P.accum);
@@ -1644,30 +1950,121 @@ __global__ void __launch_bounds__(kOvfBlock) pacbio_overflow_kernel(const ScoreP
 //     sum over ALL reads of term(base value, L_c)  +  sum over reads touched by c of [term(new value, L_c) - term(base value, L_c)]
 // with exactly the per-read arithmetic of a normal evaluation; all sums are exact integers, so the result is the
 // double gaml_calc_prob would return for the candidate's walk set — without touching the state.
-__device__ __forceinline__ double floored_term_at(const double2* log_tab, double p, double d, double rcp, double thr,
-                                                  int& floored) {
-  double q = __dmul_rn(p, rcp);
-  q = fma(fma(-q, d, p), rcp, q);
-  if (fabs(q - thr) <= thr * 3.5527136788005009e-15) q = slow_div(p, d);
-  floored = 0;
-  if (q < thr) { floored = 1; q = thr; }
-  return table_log(log_tab, q);
+// First sum, ONE pass over the base state for all the batch's total lengths: the lengths are sorted
+// ascending, so a read's floor test p < pstar(L_j) is monotone in j — it is not floored below k = its first floored
+// index and floored from k on. sum_j = sum over all reads of qthr + sum over reads with k > j of (Q - qthr), i.e. a
+// histogram over k and a suffix sum (batch_prefix_kernel). The two ends of the range (never floored: nearly every placed
+// read; always floored: unplaced reads) are kept in registers, the rest goes through shared-memory bins.
+struct TermAt { long long q; int floored; int odd; };   // odd: 1 = -inf, 2 = nan (q = 0 then)
+__device__ __forceinline__ TermAt term_at(const double2* log_tab, double p, double pstar, long long qthr) {
+  if (p < pstar) return TermAt{qthr, 1, 0};
+  const double lg = table_log(log_tab, p);
+  if (fabs(lg) < kFixLimit) return TermAt{__double2ll_rn(lg * kFixScale), 0, 0};
+  return TermAt{0ll, 0, lg == -INFINITY ? 1 : 2};
 }
 
-// First sum: one pass over the base state per distinct total length (blockIdx.y).
-__global__ void __launch_bounds__(kBlock) batch_base_kernel(const ScoreParams P, const BatchParams B) {
-  const int j = blockIdx.y;
-  const double d = B.two_len_d[j], rcp = B.rcp_two_len[j];
+constexpr int kBatchMaxLen = 1024;   // distinct total lengths one base pass handles (longer batches: several passes)
+__global__ void __launch_bounds__(kBlock) batch_base_kernel(const ScoreParams P, const BatchParams B, int j0, int nb, size_t hist_off) {
+  __shared__ unsigned long long bins[(kBatchMaxLen + 1) * kBatchBin];
+  for (int i = threadIdx.x; i < (nb + 1) * kBatchBin; i += blockDim.x) bins[i] = 0ull;
+  __syncthreads();
   const double2* log_tab = static_cast<const double2*>(P.log_tab);
-  Acc sum = acc_zero();
-  unsigned floored = 0;
+  // registers: [0] bin 0 (floored at every length), [1] bin nb (floored at none); all reads' qthr
+  unsigned long long lo[2] = {0ull, 0ull}, cnt[2] = {0ull, 0ull}, ninf[2] = {0ull, 0ull}, bad[2] = {0ull, 0ull};
+  long long hi[2] = {0ll, 0ll};
+  Acc all_thr = acc_zero();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
     const uint32_t ll = __ldg(P.lens + r);
-    int fl;
-    acc_add(sum, floored_term_at(log_tab, P.values[r], d, rcp, __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16)), fl));
-    floored += fl;
+    const int cls = __ldg(B.len_class + (ll & 0xffff) + (ll >> 16));
+    const double* row = B.pstar + (size_t)cls * B.n_len + j0;
+    const long long qthr = __ldg(B.qthr_cls + cls);
+    const double p = P.values[r];
+    acc_add_q(all_thr, qthr);
+    int k;   // first j (relative to j0) with p < pstar_j; NaN compares false everywhere -> nb, like the per-length test
+    if (!(p < __ldg(row + nb - 1))) k = nb;
+    else if (p < __ldg(row)) k = 0;
+    else {
+      int a = 0, b = nb - 1;   // row[a] <= p < row[b]
+      while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (p < __ldg(row + mid)) b = mid; else a = mid;
+      }
+      k = b;
+    }
+    long long dq = -qthr;
+    int odd = 0;
+    if (k > 0) {   // a logarithm term at some length
+      const double lg = table_log(log_tab, p);
+      if (fabs(lg) < kFixLimit) dq = __double2ll_rn(lg * kFixScale) - qthr;
+      else odd = lg == -INFINITY ? 1 : 2;
+    } else {
+      dq = 0;      // never used: no length index lies below bin 0
+    }
+    if (k == 0 || k == nb) {
+      const int s = k == 0 ? 0 : 1;
+      lo[s] += (unsigned long long)(uint32_t)dq;
+      hi[s] += dq >> 32;
+      cnt[s]++;
+      ninf[s] += odd == 1;
+      bad[s] += odd == 2;
+    } else {
+      unsigned long long* bin = bins + (size_t)k * kBatchBin;
+      atomicAdd(bin, (unsigned long long)(uint32_t)dq);
+      atomicAdd(bin + 1, (unsigned long long)(dq >> 32));
+      atomicAdd(bin + 2, 1ull);
+      if (odd == 1) atomicAdd(bin + 3, 1ull);
+      if (odd == 2) atomicAdd(bin + 4, 1ull);
+    }
   }
-  block_accumulate(sum, floored, B.accum_len + (size_t)j * kAccumStride);
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    unsigned long long* bin = bins + (size_t)(s == 0 ? 0 : nb) * kBatchBin;
+    if (cnt[s]) {
+      atomicAdd(bin, lo[s]);
+      atomicAdd(bin + 1, (unsigned long long)hi[s]);
+      atomicAdd(bin + 2, cnt[s]);
+      if (ninf[s]) atomicAdd(bin + 3, ninf[s]);
+      if (bad[s]) atomicAdd(bin + 4, bad[s]);
+    }
+  }
+  __syncthreads();
+  unsigned long long* out = B.hist + hist_off * kBatchBin;   // chunks of lengths keep their own nb + 1 bins: see launch_batch
+  for (int i = threadIdx.x; i < (nb + 1) * kBatchBin; i += blockDim.x)
+    if (bins[i]) atomicAdd(out + i, bins[i]);
+  // sum of qthr over all reads: the same for every length; accumulated next to the first bin set only
+  if (j0 == 0) block_accumulate(all_thr, 0u, B.accum_len + (size_t)B.n_len * kAccumStride);
+}
+
+// Suffix sums of the histogram: accum_len[j] = {low, high 64 bits of sum_all qthr + sum_{k > j} (Q - qthr), floored = reads
+// with k <= j, -inf / nan terms of the reads with k > j}. One block per chunk of lengths, bins [hist_off, hist_off + nb].
+__global__ void __launch_bounds__(kBatchMaxLen) batch_prefix_kernel(const BatchParams B, int j0, int nb, size_t hist_off) {
+  __shared__ unsigned long long bins[(kBatchMaxLen + 1) * kBatchBin];
+  const unsigned long long* h = B.hist + hist_off * kBatchBin;
+  for (int i = threadIdx.x; i < (nb + 1) * kBatchBin; i += blockDim.x) bins[i] = h[i];
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j >= nb) return;
+  const unsigned long long* base = B.accum_len + (size_t)B.n_len * kAccumStride;   // limbs of sum_all qthr
+  unsigned __int128 x = 0;
+  for (int t = 0; t < 4; t++) x += (unsigned __int128)base[t] << (32 * t);
+  __int128 v = (__int128)x;
+  unsigned long long floored = 0, ninf = 0, bad = 0;
+  for (int k = 0; k <= nb; k++) {
+    const unsigned long long* bin = bins + (size_t)k * kBatchBin;
+    if (k > j) {
+      v += (__int128)bin[0] + ((__int128)(long long)bin[1] << 32);
+      ninf += bin[3];
+      bad += bin[4];
+    } else {
+      floored += bin[2];
+    }
+  }
+  unsigned long long* o = B.accum_len + (size_t)(j0 + j) * kAccumStride;
+  o[0] = (unsigned long long)(unsigned __int128)v;
+  o[1] = (unsigned long long)((unsigned __int128)v >> 64);
+  o[2] = floored;
+  o[3] = ninf;
+  o[4] = bad;
 }
 
 // Second sum: one thread per mate-1 record under a key the candidate touches. The thread whose record is the
@@ -1731,13 +2128,13 @@ __global__ void __launch_bounds__(kBlock) batch_touch_kernel(const ScoreParams P
     }
     if (v1 == v0) continue;   // bit-identical value: identical term
     const uint32_t ll = __ldg(P.lens + r);
-    const double thr = __ldg(P.thr_tab + (ll & 0xffff) + (ll >> 16));
-    const double d = B.two_len_d[cd.len_index], rcp = B.rcp_two_len[cd.len_index];
-    int f0, f1;
-    const double t0 = floored_term_at(log_tab, v0, d, rcp, thr, f0), t1 = floored_term_at(log_tab, v1, d, rcp, thr, f1);
+    const int cls = __ldg(B.len_class + (ll & 0xffff) + (ll >> 16));
+    const double pstar = __ldg(B.pstar + (size_t)cls * B.n_len + cd.len_index);
+    const long long qthr = __ldg(B.qthr_cls + cls);
+    const TermAt t0 = term_at(log_tab, v0, pstar, qthr), t1 = term_at(log_tab, v1, pstar, qthr);
     long long* acc = B.accum_cand + (size_t)c * 4;
-    if (fabs(t0) < kFixLimit && fabs(t1) < kFixLimit) {
-      const long long dq = __double2ll_rn(t1 * kFixScale) - __double2ll_rn(t0 * kFixScale);   // |q| < 2^62: no overflow
+    if (!t0.odd && !t1.odd) {
+      const long long dq = t1.q - t0.q;   // |q| < 2^62: no overflow
       if (dq != 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)(uint32_t)dq);          // low 32 bits
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), (unsigned long long)(dq >> 32));        // high part, signed
@@ -1745,27 +2142,29 @@ __global__ void __launch_bounds__(kBlock) batch_touch_kernel(const ScoreParams P
     } else {
       atomicAdd(reinterpret_cast<unsigned long long*>(acc + 3), 1ull);   // non-finite term: reported as nan
     }
-    if (f1 != f0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)(long long)(f1 - f0));
+    if (t1.floored != t0.floored)
+      atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)(long long)(t1.floored - t0.floored));
   }
 }
 
 // out[c] = {integer part, 2^-40 units, floored, -inf terms, nan terms, flags} like finalize_kernel.
-__global__ void batch_finalize_kernel(const BatchParams B, double* out, const uint32_t* error_flag) {
+__global__ void batch_finalize_kernel(const BatchParams B, double* out, const uint32_t* error_flag, long long n_reads) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= B.n_cand) return;
-  const unsigned long long* a = B.accum_len + (size_t)B.cands[c].len_index * kAccumStride;
-  unsigned __int128 x = 0;
-  for (int j = 0; j < 4; j++) x += (unsigned __int128)a[j] << (32 * j);
+  const int j = B.cands[c].len_index;
+  const unsigned long long* a = B.accum_len + (size_t)j * kAccumStride;
   const long long* dl = B.accum_cand + (size_t)c * 4;
-  __int128 v = (__int128)x + (__int128)dl[0] + ((__int128)dl[1] << 32);
+  const long long floored = (long long)a[2] + dl[2], ninf = (long long)a[3], bad = (long long)a[4] + dl[3];
+  __int128 v = (__int128)(((unsigned __int128)a[1] << 64) | (unsigned __int128)a[0]) + (__int128)dl[0] + ((__int128)dl[1] << 32);
+  v -= (__int128)(n_reads - floored - ninf - bad) * (__int128)B.ql[j];   // the - FIX(log 2L) part of every logarithm term (publish_set)
   const long long ip = (long long)(v >> 40);
   const unsigned long long fr = (unsigned long long)((unsigned __int128)v & (((unsigned __int128)1 << 40) - 1));
   double* o = out + (size_t)c * kOutStride;
   o[0] = (double)ip;
   o[1] = (double)fr;
-  o[2] = (double)((long long)a[4] + dl[2]);
-  o[3] = (double)a[5];
-  o[4] = (double)((long long)a[6] + dl[3]);
+  o[2] = (double)floored;
+  o[3] = (double)ninf;
+  o[4] = (double)bad;
   o[5] = (double)(*error_flag);
 }
 
@@ -2177,12 +2576,24 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 // The streaming kernel's instantiation: penalised sets (coverage events) and sets whose records do not fit PackedPair
 // stream the 16-byte first records; everything else the packed pairs.
 using StreamKernel = void (*)(const ScoreParams);
-StreamKernel stream_kernel(bool cov, bool packed) {
-  // 4 resident blocks of 256 threads (64 registers), two reads per lane and tile. Measured alternatives that were no
-  // faster (profiles/r01_summary.md): 5 blocks at 48 registers (spills), four reads per lane, 128-thread blocks,
-  // warp-drawn tiles (with and without cp.async staging), the gathered tables in shared memory.
-  if (cov) return paired_stream_kernel<true, false, 4, 2>;
-  return packed ? paired_stream_kernel<false, true, 4, 2> : paired_stream_kernel<false, false, 4, 2>;
+// The streaming kernel's instantiation. Penalised sets (coverage events) and sets whose records do not fit PackedPair
+// stream the 16-byte first records; sets of uniform read length with a term table take the tabulated body. The
+// (resident blocks, reads per lane) shape of the tabulated body can be overridden for measurements with
+// GAML_B200_STREAM_SHAPE=<blocks><reads>, e.g. 62 = 6 blocks per SM, two reads per lane.
+StreamKernel stream_kernel(bool cov, bool packed, bool tab) {
+  if (cov) return paired_stream_kernel<true, false, false, 4, 2>;
+  if (!packed) return paired_stream_kernel<false, false, false, 4, 2>;
+  if (!tab) return paired_stream_kernel<false, true, false, 4, 2>;
+  const char* env = getenv("GAML_B200_STREAM_SHAPE");   // (read per launch: a measurement script switches shapes in one process)
+  switch (env ? atoi(env) : 0) {
+    case 42: return paired_stream_kernel<false, true, true, 4, 2>;
+    case 52: return paired_stream_kernel<false, true, true, 5, 2>;
+    case 62: return paired_stream_kernel<false, true, true, 6, 2>;
+    case 44: return paired_stream_kernel<false, true, true, 4, 4>;
+    case 54: return paired_stream_kernel<false, true, true, 5, 4>;
+    case 81: return paired_stream_kernel<false, true, true, 8, 1>;
+    default: return paired_stream_kernel<false, true, true, 4, 4>;
+  }
 }
 
 template <class K>
@@ -2197,8 +2608,8 @@ int score_grid(int which, int n_items, int sm_count) {
   if (which < 0 || which > 5) which = 0;
   if (per_sm[which] == 0) {
     switch (which) {
-      case kGridPairedFull: per_sm[which] = resident_blocks(stream_kernel(false, true), kBlock); break;
-      case kGridPairedComplex: per_sm[which] = resident_blocks(stream_kernel(false, true), kBlock); break;
+      case kGridPairedFull: per_sm[which] = resident_blocks(stream_kernel(false, true, false), kBlock); break;
+      case kGridPairedComplex: per_sm[which] = resident_blocks(stream_kernel(false, true, false), kBlock); break;
       case kGridPairedTotal: per_sm[which] = resident_blocks(paired_total_kernel, kBlock); break;
       case kGridSingleFull: per_sm[which] = resident_blocks(single_full_kernel, kBlock); break;
       case kGridSingleComplex: per_sm[which] = resident_blocks(single_complex_kernel, kBlock); break;
@@ -2300,7 +2711,22 @@ void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_mu
   if (profile) cudaEventRecord(e0, st);
   Q.chain_first = first || profile ? 1 : 0;
   Q.finish_here = profile ? 0 : 1;   // when profiling, e0/e1 bracket the streaming work alone: the last kernel publishes
-  launch_chain(stream_kernel(P.ev_keys != nullptr, P.pairs != nullptr), grid, kBlock, st, dep && !profile, Q);
+  {
+    // one resident wave of the instantiation that runs (its blocks draw tiles from counters)
+    const StreamKernel k = stream_kernel(P.ev_keys != nullptr, P.pairs != nullptr, P.pairs != nullptr && P.comb != nullptr && P.fast != nullptr);
+    static StreamKernel seen[8];
+    static int seen_per_sm[8];
+    static int n_seen = 0;
+    int per_sm = 0;
+    for (int i = 0; i < n_seen; i++)
+      if (seen[i] == k) per_sm = seen_per_sm[i];
+    if (per_sm == 0) {
+      per_sm = resident_blocks(k, kBlock);
+      if (n_seen < 8) { seen[n_seen] = k; seen_per_sm[n_seen++] = per_sm; }
+    }
+    grid = grid_for((size_t)P.n_reads, kBlock, sm_count, per_sm);
+    launch_chain(k, grid, kBlock, st, dep && !profile, Q);
+  }
   if (profile) cudaEventRecord(e1, st);
   launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
 }
@@ -2437,12 +2863,108 @@ cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* ro
 
 void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
                   int sm_count, cudaStream_t st) {
-  if (B.n_len > 0) {
-    const int gx = grid_for((size_t)P.n_reads, kBlock, sm_count, 4);
-    batch_base_kernel<<<dim3(gx, B.n_len), kBlock, 0, st>>>(P, B);
+  // base pass: chunks of at most kBatchMaxLen distinct lengths, each with its own nb + 1 bins
+  const int gx = grid_for((size_t)P.n_reads, kBlock, sm_count, 4);
+  int chunk = 0;
+  for (int j0 = 0; j0 < B.n_len; j0 += kBatchMaxLen, chunk++) {
+    const int nb = B.n_len - j0 < kBatchMaxLen ? B.n_len - j0 : kBatchMaxLen;
+    batch_base_kernel<<<gx, kBlock, 0, st>>>(P, B, j0, nb, (size_t)chunk * (kBatchMaxLen + 1));
+  }
+  chunk = 0;
+  for (int j0 = 0; j0 < B.n_len; j0 += kBatchMaxLen, chunk++) {
+    const int nb = B.n_len - j0 < kBatchMaxLen ? B.n_len - j0 : kBatchMaxLen;
+    batch_prefix_kernel<<<1, kBatchMaxLen, 0, st>>>(B, j0, nb, (size_t)chunk * (kBatchMaxLen + 1));
   }
   if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
-  batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag);
+  batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag, (long long)P.n_reads);
+}
+int batch_hist_bins(int n_len) { return ((n_len + kBatchMaxLen - 1) / kBatchMaxLen) * (kBatchMaxLen + 1); }
+int batch_launches(int n_len, bool touch) { return 2 * ((n_len + kBatchMaxLen - 1) / kBatchMaxLen) + (touch ? 1 : 0) + 1; }
+
+// Term table of a paired set whose pairs all have the same read lengths: entry (e1, e2, d) = the pair term
+// (p1*p2)*ins(d) (graph.cc:1859-1863, 1889, same order of products) and its fixed-point logarithm, by the very functions
+// the kernels use on the fly, so a tabulated term and a recomputed one are the same bits.
+__global__ void build_term_table_kernel(const double* p1, const double* p2, const double* ins, int ins_n, int shift, const double2* log_tab,
+                                        TermEntry* out) {
+  const size_t total = ((size_t)1 << (2 * shift)) * (size_t)ins_n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % (size_t)ins_n);
+    const int ee = (int)(i / (size_t)ins_n);
+    const int e1 = ee >> shift, e2 = ee & ((1 << shift) - 1);
+    const double t = __dmul_rn(__dmul_rn(p1[e1], p2[e2]), ins[d]);
+    out[i + 1] = TermEntry{t, fix_log(log_tab, t)};
+    if (i == 0) out[0] = TermEntry{0.0, kTermOdd};   // entry 0: "no pair term" (FastPair::w of a pair whose static filters fail)
+  }
+}
+void launch_build_term_table(const double* p1, const double* p2, const double* ins, int ins_n, int shift, const void* log_tab, void* out,
+                             int sm_count, cudaStream_t st) {
+  const size_t total = ((size_t)1 << (2 * shift)) * (size_t)ins_n;
+  build_term_table_kernel<<<grid_for(total, 256, sm_count, 8), 256, 0, st>>>(p1, p2, ins, ins_n, shift, static_cast<const double2*>(log_tab),
+                                                                           static_cast<TermEntry*>(out));
+}
+
+// FastPair (16 B per pair, sets with a term table): what tier 1 needs of a pair whose mates both own exactly one record
+// under the SAME key. Both records then share the key's offset in whatever walk holds it, so everything about the pair
+// term except "is the key live, and do both records pass the skip rule" is a property of the two records — orientation
+// / order filter, insert distance, (p1*p2)*ins and its logarithm — and is resolved here, once per cache commit, into an
+// index into the term table:  x = key | noterm << 30 | elsewhere << 31,  y = pos1,  z = pos2,  w = term-table index
+// (0 = the filters drop the pair: a term of +0.0). noterm: a mate without any record. elsewhere: the read is scored by
+// another phase — tier 2 / rare shapes (several records on a mate) or the cross list (mates under different keys, or an
+// edit distance beyond the table: the general body, tier1_body), for which flags[r] = 1 is emitted.
+__global__ void pack_fast_kernel(const uint4* pairs, int n, int shift, int ins_n, uint32_t uniform_ll, uint4* out, uint32_t* flags) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  if (r == n) { flags[r] = 0u; return; }
+  const uint4 pr = pairs[r];
+  const uint32_t key1 = pr.x & kPackKeyMask;
+  const int e1 = (int)((pr.x >> kPackKeyBits) & kPackEdMask), e2 = (int)((pr.y >> kPackKeyBits) & kPackEdMask);
+  const int xo = (int)((pr.x >> 29) & 1u), yo = (int)((pr.y >> 29) & 1u);
+  const bool none = ((pr.x >> 30) & 1u) != 0u || ((pr.y >> 30) & 1u) != 0u;
+  const bool tier2 = (pr.x >> 31) != 0u, same = (pr.y >> 31) != 0u;
+  const int pos1 = (int)pr.z, pos2 = (int)pr.w;
+  const int l1 = (int)(uniform_ll & 0xffff), l2 = (int)(uniform_ll >> 16);
+  const bool fit = e1 < (1 << shift) && e2 < (1 << shift);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t cross = 0u;
+  if (tier2) {
+    v.x = 0x80000000u;
+  } else if (none) {
+    v.x = 0x40000000u;
+  } else if (!same || !fit) {
+    v.x = 0x80000000u;
+    cross = 1u;
+  } else {
+    const bool fwd = pos1 < pos2;
+    const int d = fwd ? pos2 - pos1 + l2 : pos1 - pos2 + l1;   // graph.cc:1866-1875 (both positions move by the same offset)
+    const bool term = xo != yo && xo == (fwd ? 0 : 1) && (unsigned)d < (unsigned)ins_n;
+    v.x = key1;
+    v.y = (uint32_t)pos1;
+    v.z = (uint32_t)pos2;
+    v.w = term ? 1u + (uint32_t)((e1 << shift) | e2) * (uint32_t)ins_n + (uint32_t)d : 0u;
+  }
+  out[r] = v;
+  flags[r] = cross;
+}
+// flags hold their own exclusive scan now: read r is listed iff offs[r + 1] != offs[r]
+__global__ void scatter_flagged_kernel(const uint32_t* offs, int n, uint32_t* list) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t o = offs[r];
+  if (offs[r + 1] != o) list[o] = (uint32_t)r;
+}
+// Builds FastPair[n] and the cross list (read ids, ascending); flags: n + 1 uint32 of scratch; *n_cross_dev = flags + n
+// afterwards (the scan's total).
+cudaError_t build_fast_pairs(const void* pairs, int n, int shift, int ins_n, uint32_t uniform_ll, void* fast, uint32_t* flags, uint32_t* list,
+                             void* temp, size_t temp_bytes, cudaStream_t st, int* launches) {
+  pack_fast_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(static_cast<const uint4*>(pairs), n, shift, ins_n, uniform_ll, static_cast<uint4*>(fast), flags);
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, flags, flags, n + 1, st);
+  if (need > temp_bytes) return cudaErrorMemoryAllocation;
+  cudaError_t err = cub::DeviceScan::ExclusiveSum(temp, need, flags, flags, n + 1, st);
+  if (err != cudaSuccess) return err;
+  scatter_flagged_kernel<<<(n + 255) / 256, 256, 0, st>>>(flags, n, list);
+  (*launches) += 3;
+  return cudaGetLastError();
 }
 
 // Packs the two dense first-record arrays of a paired set into PackedPair; *bad != 0 afterwards when some record does not
@@ -2582,6 +3104,14 @@ cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* pac
   pacbio_cov_sweep_kernel<<<grid_for(2 * (size_t)cap, 256, sm_count, 8), 256, 0, st>>>(pkey_sorted, ikey_sorted, run_max, C.count, cap,
                                                                                        walk_len, step, bad);
   return cudaGetLastError();
+}
+
+void launch_exchange_gather(const unsigned long long* lines, int world, int n_sets, int max_sets, uint32_t epoch,
+                            unsigned long long* host_lines, unsigned long long* host_flag, unsigned long long timeout_ns, cudaStream_t st) {
+  launch_chain(exchange_gather_kernel, 1, kResultStride * 32, st, true, lines, world, n_sets, max_sets, epoch, host_lines, host_flag, timeout_ns);
+}
+void launch_reduced_publish(const double* reduced, int n_sets, uint32_t epoch, unsigned long long* host_lines, cudaStream_t st) {
+  reduced_publish_kernel<<<1, 32, 0, st>>>(reduced, n_sets, epoch, host_lines);
 }
 
 size_t csr_temp_bytes(int n_reads) {

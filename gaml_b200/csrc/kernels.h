@@ -73,6 +73,15 @@ cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* ro
 // Batched candidate evaluation of one paired set: base pass per distinct total length, touched-read pass, finalize.
 void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
                   int sm_count, cudaStream_t st);
+int batch_hist_bins(int n_len);            // bins of BatchParams::hist for n_len distinct total lengths
+int batch_launches(int n_len, bool touch);  // kernels launch_batch issues
+// Term table of a uniform-length paired set: 1 + (1 << shift)^2 * ins_n TermEntry (entry 0 = "no pair term").
+void launch_build_term_table(const double* p1, const double* p2, const double* ins, int ins_n, int shift, const void* log_tab, void* out,
+                             int sm_count, cudaStream_t st);
+// FastPair array + cross list of a paired set with a term table (kernels.cu); flags: n + 1 uint32 of scratch whose last
+// entry holds the number of listed reads afterwards.
+cudaError_t build_fast_pairs(const void* pairs, int n, int shift, int ins_n, uint32_t uniform_ll, void* fast, uint32_t* flags, uint32_t* list,
+                             void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
 // Coverage-gap penalty of one paired set: radix sort of the event keys, then the one-thread-per-event sweep.
 size_t coverage_sort_temp_bytes(unsigned n);
 cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long long* keys_sorted, unsigned n, void* temp,
@@ -84,6 +93,10 @@ cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* pac
                                    size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st);
 // PacBio alignment probability: one thread per alignment over host-prepared row ranges.
 void launch_pacbio_alnprob(const AlnProbParams& A, int sm_count, cudaStream_t st);
+// Multi-GPU result exchange: last kernel of an evaluation's chain (appended to it: recorded like the scoring kernels).
+void launch_exchange_gather(const unsigned long long* lines, int world, int n_sets, int max_sets, uint32_t epoch,
+                            unsigned long long* host_lines, unsigned long long* host_flag, unsigned long long timeout_ns, cudaStream_t st);
+void launch_reduced_publish(const double* reduced, int n_sets, uint32_t epoch, unsigned long long* host_lines, cudaStream_t st);
 size_t csr_temp_bytes(int n_reads);
 
 }  // namespace gaml

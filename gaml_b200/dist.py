@@ -105,3 +105,42 @@ class ResultExchange:
 
     def attach(self, pc) -> None:
         pc.set_result_exchange(self.map, self.rank, self.world)
+
+
+class PeerExchange:
+    """Result exchange over NVLink peer memory (gaml_peer_exchange_*): every rank creates its device buffer, the 64-byte
+    CUDA IPC handles are all-gathered with `torch.distributed` (plumbing), every rank maps the others' buffers. After
+    attach(pc) an evaluation's all-gather is a 64-byte peer store per rank from the publishing block plus the chain's
+    last kernel waiting for the lines in its own buffer."""
+
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+
+    def attach(self, pc) -> None:
+        import torch.distributed as dist
+        handle, _ptr = pc.peer_exchange_create(self.rank, self.world)
+        handles = [None] * self.world
+        if dist.is_initialized() and self.world > 1:
+            dist.all_gather_object(handles, handle)
+        else:
+            handles[0] = handle
+        pc.peer_exchange_open(handles=handles)
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier()   # nobody evaluates before every rank has mapped every buffer
+
+
+class NcclExchange:
+    """Result exchange as one ncclAllReduce(sum, fp64) per evaluation on the library's stream (gaml_nccl_exchange_init)."""
+
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+
+    def attach(self, pc) -> None:
+        import torch.distributed as dist
+        from . import api
+        ids = [api.nccl_unique_id() if self.rank == 0 else None]
+        if dist.is_initialized() and self.world > 1:
+            dist.broadcast_object_list(ids, src=0)
+        pc.nccl_exchange_init(ids[0], self.rank, self.world)
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier()

@@ -26,7 +26,7 @@ enum {
   GAML_ERR_CUDA = -1,          /* CUDA runtime / no device */
   GAML_ERR_ARG = -2,           /* bad argument */
   GAML_ERR_KEY_EXISTS = -3,    /* cache key inserted twice */
-  GAML_ERR_UNSUPPORTED = -4,   /* e.g. penalty_constant != 0 (coverage penalty, SURVEY §8 A8, not on device yet) */
+  GAML_ERR_UNSUPPORTED = -4,   /* e.g. a penalised paired / PacBio set on a read-id shard, a batch over non-paired sets */
   GAML_ERR_CAPACITY = -5,      /* a read needs more placement scratch than configured */
   GAML_ERR_STATE = -6          /* call order (e.g. finalize without a pending evaluation) */
 };
@@ -46,7 +46,7 @@ typedef struct {
   double min_prob_per_base;
   double min_prob_start;
   double weight;
-  double penalty_constant;     /* must be 0 for now (GAML_ERR_UNSUPPORTED otherwise) */
+  double penalty_constant;     /* coverage-gap penalty, scored on the device; 0 = off (the reference's default) */
   double step;
 } gaml_readset_config;
 
@@ -199,6 +199,25 @@ int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len);
 #define GAML_EXCHANGE_MAX_SETS 8
 int gaml_set_result_exchange(gaml_ctx* ctx, void* shared_base, int64_t bytes, int32_t rank, int32_t world);
 int gaml_eval_finish_gathered(gaml_ctx* ctx, double* gathered, int32_t* total_len);
+/* The same exchange over PEER MEMORY (NVLink / NVSwitch) instead of host memory: every rank owns a small device buffer of
+ * result lines; the block that completes a read set stores its 64-byte line into the buffer of EVERY rank (peer stores),
+ * and the last kernel of the evaluation's chain waits until all ranks' lines of this evaluation have arrived in its own
+ * buffer, then hands them to the host in one piece — the all-gather is part of the evaluation's kernels, and the host
+ * waits for one flag in its own pinned memory. gaml_peer_exchange_create allocates this rank's buffer and returns its
+ * cudaIpcMemHandle_t (GAML_IPC_HANDLE_BYTES) for the caller's plumbing to all-gather (and the raw device pointer, for
+ * contexts of the same process); gaml_peer_exchange_open takes all ranks' handles (rank-major) and/or local pointers and
+ * switches the exchange on. gaml_eval_finish_gathered / gaml_calc_prob_gathered then work as above. */
+#define GAML_IPC_HANDLE_BYTES 64
+int gaml_peer_exchange_create(gaml_ctx* ctx, int32_t rank, int32_t world, void* ipc_handle_out, void** buffer_out);
+int gaml_peer_exchange_open(gaml_ctx* ctx, const void* ipc_handles, void* const* local_buffers);
+int gaml_peer_exchange_close(gaml_ctx* ctx);
+/* ... or through NCCL (SURVEY §8e "one ncclAllReduce(sum, fp64)"): the lines are all-reduced on the evaluation's stream
+ * (every field is an integer far below 2^53, so the sums of doubles are exact); gaml_eval_finish_gathered reports the sum
+ * as shard 0's partials and zeros for the others, which gaml_combine_partials adds to the same result. NCCL is bound at
+ * run time (the copy the process has loaded, else libnccl.so.2). unique_id: 128 bytes from gaml_nccl_unique_id on one
+ * rank, handed to all; NULL detaches. */
+int gaml_nccl_unique_id(void* out128);
+int gaml_nccl_exchange_init(gaml_ctx* ctx, const void* unique_id128, int32_t rank, int32_t world);
 /* prepare + launch + finish_gathered in one call (the multi-GPU form of gaml_calc_prob_partial) */
 int gaml_calc_prob_gathered(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks,
                             double* gathered, int32_t* total_len);
@@ -217,6 +236,13 @@ int gaml_calc_prob_batch(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_id
 int gaml_calc_prob_batch_partial(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
                                  const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
                                  double* partials, int32_t* total_lens);
+
+/* The multi-GPU form (read-id shards, one context per GPU, every rank calls it with the same candidates): the shards'
+ * partials of all candidates are summed by ONE all-reduce on the library's stream (needs gaml_nccl_exchange_init) and
+ * combined exactly, so every rank receives the same probs — bit-identical to the unsharded gaml_calc_prob_batch. */
+int gaml_calc_prob_batch_gathered(gaml_ctx* ctx, int32_t n_cand, const int32_t* erased_idx, const int64_t* erased_off,
+                                  const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
+                                  double* probs, int32_t* total_lens, int32_t* zeros);
 
 /* Forget the paired ScoringState (== constructing a fresh ProbCalculator, prob_calculator.h:45-47): the
  * next evaluation re-scores every read from scratch ("full logL"). */

@@ -165,6 +165,53 @@ def test_result_exchange_between_two_contexts_matches_the_unsharded_result(oracl
     whole.close()
 
 
+def test_peer_memory_exchange_between_two_contexts_matches_the_unsharded_result():
+    """The same over peer memory (gaml_peer_exchange_*): each publishing block stores its 64-byte line into the exchange
+    buffer of both "ranks", the last kernel of each chain waits for both lines in its own buffer. Two contexts of one
+    process wire each other's buffers by pointer (IPC handles are for other processes)."""
+    wl = synth.paired_workload(46, 10000, 200_000, n_evals=12, seed=11)
+    whole = api.ProbCalculator.from_workload(wl)
+    ranks = [api.ProbCalculator.from_workload(wl, shard_of=(rk, 2)) for rk in range(2)]
+    ptrs = [pc.peer_exchange_create(rk, 2)[1] for rk, pc in enumerate(ranks)]
+    for pc in ranks:
+        pc.peer_exchange_open(local_ptrs=ptrs)
+    for e, walks in enumerate(wl.evals):
+        ref = whole.calc_prob(walks)
+        for pc in ranks:
+            pc.prepare(walks)
+            pc.launch()
+        outs = []
+        for pc in ranks:
+            g, tl = pc.finish_gathered()
+            assert g.shape[0] == 2
+            outs.append(pc.combine(g, 2, tl))
+        assert outs[0] == outs[1], e
+        assert outs[0] == ref, (e, outs[0], ref)   # exact integer partial sums: bit-identical for any sharding
+    for pc in ranks:
+        pc.peer_exchange_close()
+        pc.close()
+    whole.close()
+
+
+def test_capacity_error_invalidates_the_state_and_the_one_shot_call_recovers(monkeypatch, oracle):
+    """A scratch arena too small for a walk set's many-placement reads: the evaluation reports GAML_ERR_CAPACITY, the
+    incremental state is dropped (the skipped reads' values are stale), the buffer grows, and gaml_calc_prob_partial
+    repeats the evaluation by itself — the caller sees the oracle's results throughout."""
+    wl = workload.read_workload(os.path.join(GOLDEN, "hand_paired.wl"))
+    ref = workload.read_results(os.path.join(GOLDEN, "hand_paired.ref.res"))
+    monkeypatch.setenv("GAML_B200_SCRATCH_ENTRIES", "1")
+    pc = api.ProbCalculator.from_workload(wl)
+    monkeypatch.delenv("GAML_B200_SCRATCH_ENTRIES")
+    # three-phase form: the error surfaces, the next evaluation is a full re-score with a larger arena
+    pc.prepare(wl.evals[0])
+    pc.launch()
+    with pytest.raises(api.GamlError, match="scratch"):
+        pc.finish()
+    check_against(wl, ref, pc=pc)
+    assert pc.stats().last_scratch_placements >= 1
+    pc.close()
+
+
 def test_flat_cache_file_round_trip(tmp_path):
     """gaml_cache_save / gaml_cache_load: a context whose read sets were filled from the flat cache files scores a
     trajectory identically (partials and per-read values bit for bit) to the one the files were written from —
