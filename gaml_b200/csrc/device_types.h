@@ -103,6 +103,7 @@ struct ScoreParams {
   const void* fast;          // with a term table: one FastPair (16 B) per pair for tier 1 (kernels.cu), or null
   const uint32_t* xlist;     //   and the cross list: tier-1 reads the fast records leave to the general body (ascending read ids)
   int32_t n_cross;
+  int32_t n_tier1;           //   and the number of reads tier 1 streams ([0, n_tier1) of the internal order; n_reads without one)
   uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
   int32_t lens_uniform;
   const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)

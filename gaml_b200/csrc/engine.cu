@@ -164,6 +164,11 @@ struct ReadSetState {
   DevBuf d_lens, d_values, d_stamp, d_ins, d_ovf_list, d_complex, d_clens, d_cdesc;
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
   DevBuf d_uni_prob[2];           // paired, uniform lengths: alignment probability by edit distance, per mate (kernels.cu)
+  // internal read order (kernels.cu "internal read order"): fixed at the first commit of a set with fast records
+  bool perm_valid = false;
+  std::vector<uint32_t> h_inv;    // caller's local read id -> internal index (cache inserts, gaml_read_values)
+  std::vector<uint32_t> h_perm;   // internal index -> caller's local read id (gaml_cache_save)
+  int n_fast = 0;                 // reads [0, n_fast) of the internal order are tier 1's
   DevBuf d_fast, d_xlist;         // with a term table: FastPair per pair + the cross list (kernels.cu), valid when fast_ok
   bool fast_ok = false;
   int n_cross = 0;
@@ -327,6 +332,7 @@ struct gaml_ctx {
   std::vector<WalkView> h_refs;
   std::vector<Walk> h_walks;
   bool fast_changes = true;       // GAML_B200_NO_FAST_CHANGES=1: always build the reference's container (tests)
+  bool permute_reads = true;      // GAML_B200_NO_PERMUTE=1: keep the caller's read order on the device (tests, measurements)
   HashCounts prev_counts;         // multiplicity of every walk hash in prev() (kept in step by finish())
   bool have_prev = false;         // prev() holds a finished evaluation's walks
   WalkDiff cur_diff;              // cur() against prev(), from prepare()
@@ -644,10 +650,13 @@ int ensure_pinned(gaml_ctx* ctx, size_t bytes) {
 int commit(gaml_ctx* ctx) {
   for (auto& rsp : ctx->sets) {
     ReadSetState& rs = *rsp;
+   for (int pass = 0; pass < 2; pass++) {   // (a second pass only right after the internal read order has been fixed)
     for (int m = 0; m < rs.n_mates; m++) {
       MateStore& st = rs.mate[m];
       if (!st.dirty) continue;
       const size_t total = st.total_records();
+      if (rs.perm_valid)   // the arena speaks internal read indices
+        for (int4& v : st.pending) v.x = (int)rs.h_inv[(size_t)v.x];
       if (total > 0xfffffff0ull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 alignment records in one mate store");
       CU(st.arena.reserve(std::max<size_t>(total, 1) * 16, st.arena_n * 16, false, ctx->stream));
       if (st.is_long) CU(st.arena_pos.reserve(std::max<size_t>(total, 1) * 8, st.arena_n * 8, false, ctx->stream));
@@ -790,6 +799,39 @@ int commit(gaml_ctx* ctx) {
       ctx->stats.kernel_launches += launches;
       rs.complex_dirty = false;
     }
+    if (pass == 1 || !rs.fast_ok || rs.perm_valid || !ctx->permute_reads) break;
+    {
+      // First commit of a set with fast records: fix the internal read order (fast reads by key and term-table index,
+      // everything else behind them), rewrite the arenas' read field and build everything again in that order.
+      const int n = rs.n_local;
+      DevBuf keys, ids, inv, temp, nf;
+      CU(keys.reserve((size_t)n * 2 * 8, 0, false, ctx->stream));
+      CU(ids.reserve((size_t)n * 2 * 4, 0, false, ctx->stream));
+      CU(inv.reserve((size_t)n * 4, 0, false, ctx->stream));
+      CU(temp.reserve(std::max<size_t>(perm_temp_bytes(n), 256), 0, false, ctx->stream));
+      CU(nf.reserve(256, 0, true, ctx->stream));
+      int launches = 0;
+      CU(build_read_permutation(rs.d_fast.p, n, keys.as<unsigned long long>(), ids.as<uint32_t>(), inv.as<uint32_t>(), nf.as<uint32_t>(),
+                                temp.p, temp.cap, ctx->stream, &launches));
+      rs.h_inv.resize((size_t)n);
+      rs.h_perm.resize((size_t)n);
+      uint32_t n_fast = 0;
+      CU(cudaMemcpyAsync(rs.h_inv.data(), inv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(rs.h_perm.data(), ids.as<uint32_t>() + n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&n_fast, nf.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      for (int m = 0; m < rs.n_mates; m++) {
+        launch_remap_arena(rs.mate[m].arena.p, rs.mate[m].arena_n, inv.as<uint32_t>(), ctx->sm_count, ctx->stream);
+        launches++;
+        rs.mate[m].dirty = true;
+      }
+      CU(cudaStreamSynchronize(ctx->stream));
+      ctx->stats.kernel_launches += launches;
+      rs.n_fast = (int)n_fast;
+      rs.perm_valid = true;
+      rs.has_state = false;      // (no evaluation can have happened on records of this set yet; a state of zeros stays zeros)
+      rs.total_valid = false;
+    }
+   }
   }
   if (ctx->tables_dirty) {
     std::vector<void*> tabs;   // [SlotA* per store][SlotB* per store][combined-table base per store][its key map per store]
@@ -1168,6 +1210,7 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.fast = rs.fast_ok && rs.pairs_ok && rs.comb_ok ? rs.d_fast.p : nullptr;
   P.xlist = rs.d_xlist.as<uint32_t>();
   P.n_cross = rs.fast_ok ? rs.n_cross : 0;
+  P.n_tier1 = rs.perm_valid ? rs.n_fast : rs.n_local;
   P.ins_tab = rs.d_ins.as<double>();
   P.ins_n = rs.ins_n;
   P.pstar_tab = reinterpret_cast<const double*>(blob + sp.pstar_off);
@@ -2060,6 +2103,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   if (const char* s = getenv("GAML_B200_NO_RUNNING_TOTAL")) ctx->running_total = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_GRAPHS")) ctx->use_graphs = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_FAST_CHANGES")) ctx->fast_changes = !(s[0] && s[0] != '0');
+  if (const char* s = getenv("GAML_B200_NO_PERMUTE")) ctx->permute_reads = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -2432,6 +2476,8 @@ int gaml_cache_save(gaml_ctx* ctx, int set, const char* path) {
     if (st.arena_n) {
       CU(cudaMemcpyAsync(host.data(), st.arena.p, st.arena_n * 16, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
+      if (rs.perm_valid)   // the file speaks the caller's read ids
+        for (int4& v : host) v.x = (int)rs.h_perm[(size_t)v.x];
       ok = ok && fwrite(host.data(), 16, st.arena_n, fc.f) == st.arena_n;
       if (st.is_long) {   // {position, position_end} of every record, after the arena
         std::vector<Int2> pos(st.arena_n);
@@ -2975,8 +3021,15 @@ int gaml_read_values(gaml_ctx* ctx, int set, double* out, int64_t n) {
   ReadSetState& rs = *ctx->sets[set];
   if (n != rs.n_local) return fail(ctx, GAML_ERR_ARG, "n must equal the shard's read count");
   cudaSetDevice(ctx->device);
-  if (n > 0) CU(cudaMemcpyAsync(out, rs.d_values.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!rs.perm_valid) {
+    if (n > 0) CU(cudaMemcpyAsync(out, rs.d_values.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GAML_OK;
+  }
+  std::vector<double> tmp((size_t)n);   // the device holds the internal read order
+  if (n > 0) CU(cudaMemcpyAsync(tmp.data(), rs.d_values.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  for (int64_t r = 0; r < n; r++) out[r] = tmp[rs.h_inv[(size_t)r]];
   return GAML_OK;
 }
 

@@ -1457,7 +1457,12 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
 // record only, so a tile is two memory levels — then liveness and the skip rule (graph.cc:577) as predicates, the select,
 // the state write and the exact accumulation. Everything else about the pair was resolved when the cache was committed.
 template <int kR>
-__device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4* __restrict__ fast, int lane, int q_first, int n, Acc& sum,
+__device__ __forceinline__ void tier1_fast_load(const uint4* __restrict__ fast, int lane, int q_first, int n, uint4 (&u)[kR]) {
+#pragma unroll
+  for (int j = 0; j < kR; j++) u[j] = ldg_stream(fast + min(q_first + 32 * j + lane, n - 1));
+}
+template <int kR>
+__device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4 (&u)[kR], int lane, int q_first, int n, Acc& sum,
                                            unsigned& floored, const double2* __restrict__ log_tab) {
   int qi[kR];
   bool valid[kR];
@@ -1467,9 +1472,6 @@ __device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4* __
     valid[j] = q < n;
     qi[j] = min(q, n - 1);
   }
-  uint4 u[kR];
-#pragma unroll
-  for (int j = 0; j < kR; j++) u[j] = ldg_stream(fast + qi[j]);
   const uint4* __restrict__ comb = static_cast<const uint4*>(P.comb);
   const int4* __restrict__ tq = static_cast<const int4*>(P.tq);
   uint4 a[kR], b[kR];
@@ -1535,13 +1537,14 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
   // there. The exact integer accumulators make the result independent of who sums what.
   constexpr int kTile = kR * kBlock;
   constexpr int kRecLines = kTile * 16 / 128;   // 128-byte lines of one record array per tile
-  const int n_tiles = (n + kTile - 1) / kTile;
+  const int n1 = kTab ? P.n_tier1 : n;          // fast records: tier 1 ends with the last fast read of the internal order
+  const int n_tiles = (n1 + kTile - 1) / kTile;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint4* __restrict__ src1 = static_cast<const uint4*>(kTab ? P.fast : (kPacked ? P.pairs : P.m[0].first));
   const uint4* __restrict__ src2 = static_cast<const uint4*>(P.m[1].first);
   auto prefetch_tile = [&](int t) {
     if (t >= n_tiles) return;
-    const int q = min(t * kTile + ((int)threadIdx.x % kRecLines) * 8, n - 1);   // 8 consecutive 16-byte records = one line
+    const int q = min(t * kTile + ((int)threadIdx.x % kRecLines) * 8, n1 - 1);   // 8 consecutive 16-byte records = one line
     if ((int)threadIdx.x < kRecLines) prefetch_l2(src1 + q);
     else if (!kPacked && (int)threadIdx.x < 2 * kRecLines) prefetch_l2(src2 + q);
   };
@@ -1558,15 +1561,32 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
     rare_tiles(P, s_tile, sum, floored);
     __syncthreads();
   }
-  while (tile < n_tiles) {
-    if (threadIdx.x == 0) s_tile[buf] = 2 * (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // the tile after next
-    prefetch_tile(next);
-    if (kTab) tier1_fast<kR>(P, src1, lane, tile * kTile + wib * (32 * kR), n, sum, floored, log_tab);
-    else tier1_body<kCov, kPacked, false, kR>(P, src1, src2, lane, sa1, sa2, log_tab, tile * kTile + wib * (32 * kR), n, sum, floored);
-    __syncthreads();
-    tile = next;
-    next = s_tile[buf];
-    buf ^= 1;
+  if (kTab) {
+    // fast records: the NEXT tile's records are requested into registers before this tile is worked on (a tile is two
+    // memory levels: its records, then the gathers they point at — the first level is always one tile ahead)
+    uint4 u_cur[kR], u_nxt[kR];
+    if (tile < n_tiles) tier1_fast_load<kR>(src1, lane, tile * kTile + wib * (32 * kR), n1, u_cur);
+    while (tile < n_tiles) {
+      if (threadIdx.x == 0) s_tile[buf] = 2 * (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // the tile after next
+      if (next < n_tiles) tier1_fast_load<kR>(src1, lane, next * kTile + wib * (32 * kR), n1, u_nxt);
+      tier1_fast<kR>(P, u_cur, lane, tile * kTile + wib * (32 * kR), n1, sum, floored, log_tab);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kR; j++) u_cur[j] = u_nxt[j];
+      tile = next;
+      next = s_tile[buf];
+      buf ^= 1;
+    }
+  } else {
+    while (tile < n_tiles) {
+      if (threadIdx.x == 0) s_tile[buf] = 2 * (int)gridDim.x + (int)atomicAdd(P.tile_counter, 1u);   // the tile after next
+      prefetch_tile(next);
+      tier1_body<kCov, kPacked, false, kR>(P, src1, src2, lane, sa1, sa2, log_tab, tile * kTile + wib * (32 * kR), n, sum, floored);
+      __syncthreads();
+      tile = next;
+      next = s_tile[buf];
+      buf ^= 1;
+    }
   }
   if (kTab && P.n_cross > 0) {
     // the cross list: tier-1 reads whose mates lie under different keys (the insert distance depends on the walk) or whose
@@ -2592,7 +2612,9 @@ StreamKernel stream_kernel(bool cov, bool packed, bool tab) {
     case 44: return paired_stream_kernel<false, true, true, 4, 4>;
     case 54: return paired_stream_kernel<false, true, true, 5, 4>;
     case 81: return paired_stream_kernel<false, true, true, 8, 1>;
-    default: return paired_stream_kernel<false, true, true, 4, 4>;
+    case 34: return paired_stream_kernel<false, true, true, 3, 4>;
+    case 32: return paired_stream_kernel<false, true, true, 3, 2>;
+    default: return paired_stream_kernel<false, true, true, 4, 2>;
   }
 }
 
@@ -2926,25 +2948,85 @@ __global__ void pack_fast_kernel(const uint4* pairs, int n, int shift, int ins_n
   const bool fit = e1 < (1 << shift) && e2 < (1 << shift);
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   uint32_t cross = 0u;
-  if (tier2) {
-    v.x = 0x80000000u;
-  } else if (none) {
-    v.x = 0x40000000u;
-  } else if (!same || !fit) {
-    v.x = 0x80000000u;
-    cross = 1u;
-  } else {
+  // the term-table index of (first record of mate 1, first record of mate 2) when both lie under one key: the pair term
+  // of a fast read; for the others only a locality hint for the internal order (reads of like keys and terms together)
+  uint32_t tix = 0u;
+  if (!none && same && fit) {
     const bool fwd = pos1 < pos2;
     const int d = fwd ? pos2 - pos1 + l2 : pos1 - pos2 + l1;   // graph.cc:1866-1875 (both positions move by the same offset)
     const bool term = xo != yo && xo == (fwd ? 0 : 1) && (unsigned)d < (unsigned)ins_n;
+    tix = term ? 1u + (uint32_t)((e1 << shift) | e2) * (uint32_t)ins_n + (uint32_t)d : 0u;
+  }
+  if (tier2) {
+    v.x = 0x80000000u | key1;
+    v.w = tix;
+  } else if (none) {
+    v.x = 0x40000000u;
+  } else if (!same || !fit) {
+    v.x = 0x80000000u | key1;
+    cross = 1u;
+  } else {
     v.x = key1;
     v.y = (uint32_t)pos1;
     v.z = (uint32_t)pos2;
-    v.w = term ? 1u + (uint32_t)((e1 << shift) | e2) * (uint32_t)ins_n + (uint32_t)d : 0u;
+    v.w = tix;
   }
   out[r] = v;
   flags[r] = cross;
 }
+// ---- internal read order ------------------------------------------------------------------------------------------
+// Reads are scored in an INTERNAL order fixed at the first cache commit: tier-1 fast reads first, sorted by (key, term-table
+// index), everything else (tier 2, rare shapes, cross list) behind them. A warp's 32 consecutive reads then share their
+// key's slot words and neighbouring term-table entries (a few cache lines per gather instead of ~30 — the L1 tag stage
+// was what bounded tier 1 once the arithmetic was gone), the state is written in whole lines, tier 1 stops at the last
+// fast read, and the delta kernel's reads under one key are neighbours as well. The permutation is applied to the arena's
+// read field; the ABI keeps speaking the caller's read ids (gaml_read_values, gaml_cache_save map back).
+__global__ void perm_keys_kernel(const uint4* fast, int n, unsigned long long* keys, uint32_t* ids) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint4 f = fast[r];
+  const bool elsewhere = (f.x >> 31) != 0u, noterm = ((f.x >> 30) & 1u) != 0u;
+  unsigned long long k;
+  if (elsewhere) k = (1ull << 63) | ((unsigned long long)(f.x & 0x3fffffffu) << 32) | (unsigned long long)f.w;   // tier 2 / cross: by key too
+  else if (noterm) k = (0x3fffffffull << 32) | (unsigned long long)(uint32_t)r; // end of the fast region
+  else k = ((unsigned long long)(f.x & 0x3fffffffu) << 32) | (unsigned long long)f.w;
+  keys[r] = k;
+  ids[r] = (uint32_t)r;
+}
+__global__ void perm_finish_kernel(const unsigned long long* sorted_keys, const uint32_t* sorted_ids, int n, uint32_t* inv, uint32_t* n_fast) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  inv[sorted_ids[i]] = (uint32_t)i;
+  const bool here = (sorted_keys[i] >> 63) != 0ull;
+  const bool before = i > 0 && (sorted_keys[i - 1] >> 63) != 0ull;
+  if (here && !before) *n_fast = (uint32_t)i;   // first read of the "elsewhere" region
+  if (i == n - 1 && !here) *n_fast = (uint32_t)n;
+}
+__global__ void remap_arena_kernel(int4* arena, size_t n, const uint32_t* inv) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    arena[i].x = (int)inv[arena[i].x];
+}
+size_t perm_temp_bytes(int n) {
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, n);
+  return need;
+}
+// keys / ids: 2 x n each (unsorted half, sorted half); inv: n; n_fast: one uint32 on the device.
+cudaError_t build_read_permutation(const void* fast, int n, unsigned long long* keys, uint32_t* ids, uint32_t* inv, uint32_t* n_fast,
+                                   void* temp, size_t temp_bytes, cudaStream_t st, int* launches) {
+  perm_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const uint4*>(fast), n, keys, ids);
+  size_t need = temp_bytes;
+  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, need, (const unsigned long long*)keys, keys + n, (const uint32_t*)ids, ids + n, n, 0, 64, st);
+  if (err != cudaSuccess) return err;
+  perm_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys + n, ids + n, n, inv, n_fast);
+  (*launches) += 3;
+  return cudaGetLastError();
+}
+void launch_remap_arena(void* arena, size_t n_records, const uint32_t* inv, int sm_count, cudaStream_t st) {
+  if (n_records) remap_arena_kernel<<<grid_for(n_records, 256, sm_count, 16), 256, 0, st>>>(static_cast<int4*>(arena), n_records, inv);
+}
+
 // flags hold their own exclusive scan now: read r is listed iff offs[r + 1] != offs[r]
 __global__ void scatter_flagged_kernel(const uint32_t* offs, int n, uint32_t* list) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;

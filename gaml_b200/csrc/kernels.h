@@ -82,6 +82,12 @@ void launch_build_term_table(const double* p1, const double* p2, const double* i
 // entry holds the number of listed reads afterwards.
 cudaError_t build_fast_pairs(const void* pairs, int n, int shift, int ins_n, uint32_t uniform_ll, void* fast, uint32_t* flags, uint32_t* list,
                              void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
+// Internal read order of a paired set with fast records (kernels.cu): sort keys from the FastPair array, radix sort,
+// inverse permutation (caller's local read id -> internal index) and the length of the fast region.
+size_t perm_temp_bytes(int n);
+cudaError_t build_read_permutation(const void* fast, int n, unsigned long long* keys, uint32_t* ids, uint32_t* inv, uint32_t* n_fast,
+                                   void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
+void launch_remap_arena(void* arena, size_t n_records, const uint32_t* inv, int sm_count, cudaStream_t st);
 // Coverage-gap penalty of one paired set: radix sort of the event keys, then the one-thread-per-event sweep.
 size_t coverage_sort_temp_bytes(unsigned n);
 cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long long* keys_sorted, unsigned n, void* temp,

@@ -9,16 +9,21 @@
 // (graph.h:427) — access specifiers do not change object layout, graph.o is the reference's own object file.
 // A maintainer would instead add two accessors to ReadSet; INTEGRATION.md shows that patch.
 //
-// What stays on the host, exactly as the reference does it, is everything that FILLS the cache: the adapter
-// calls the same precompute routines in the same places (graph.cc:1967-1968, 538-542, 605-609), so the same
-// keys are aligned at the same time. It then mirrors keys it has not sent yet to the device and calls
-// gaml_calc_prob. No score is ever computed on the CPU; if the CUDA context cannot be created the program
-// aborts like the reference's asserts do.
+// What stays on the host, exactly as the reference does it, is everything that FILLS the caches: for every walk the
+// adapter has not seen yet it runs the reference's own precompute routines where CalcScoreForPathsNew /
+// GetPositionsOnlyPath / AddPositions / PacbioReadSet::GetReadProbabilities run them (graph.cc:1967-1968, 538-542,
+// 605-609, 2455-2486), so the same keys are aligned in the same order; it then mirrors the keys the device does not hold
+// yet and calls gaml_calc_prob. A walk seen before costs one vector compare (or one hash probe): its keys are all in the
+// cache already — the cache never shrinks — so it can contribute nothing to either step. No score is ever computed on the
+// CPU; if the CUDA context cannot be created the program aborts like the reference's asserts do.
 #ifndef PROB_CALCULATOR_H__
 #define PROB_CALCULATOR_H__
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <unordered_map>
 #include <unordered_set>
 
 #include "gaml_b200.h"
@@ -161,11 +166,18 @@ class ProbCalculator {
       mirrors_.push_back(Mirror{e.second.first, id, 0, true, {}});
       mirrors_.push_back(Mirror{e.second.second, id, 1, true, {}});
     }
-    if (!pacbio_reads.empty()) {
-      fprintf(stderr, "gaml_b200 adapter: PacBio sets need a pre-filled cache (blasr drivers are not mirrored yet)\n");
-      abort();
+    for (auto& e : pacbio_reads) {
+      // logdouble(double) = log (logdouble.hpp:18): the library's pacbio config wants the probabilities themselves
+      gaml_readset_config c = Cfg(GAML_KIND_PACBIO, e.first.penalty_constant, e.first.step, e.first.min_prob_per_base,
+                                  e.first.min_prob_start, e.first.weight, exp(e.second->match_prob_.logval),
+                                  exp(e.second->mismatch_prob_.logval));
+      vector<int32_t> l(e.second->GetNumberOfReads());
+      for (size_t i = 0; i < l.size(); i++) l[i] = e.second->GetReadLen((int)i);
+      int id = gaml_add_readset(ctx_, &c, (int64_t)l.size(), 0, (int64_t)l.size(), l.data(), NULL, -1, -1);
+      Check(id);
+      pb_mirrors_.push_back(PbMirror{e.second, id, {}});
     }
-    n_sets_ = single_reads.size() + paired_reads.size();
+    n_sets_ = single_reads.size() + paired_reads.size() + pacbio_reads.size();
   }
 
   // Window key of node i inside a contig (reference graph.cc:552-561 / 618-627).
@@ -191,38 +203,202 @@ class ProbCalculator {
                             INT32_MIN));
   }
 
-  void FillAndMirrorCaches(const vector<vector<int>>& paths) {
-    // (1) run the reference's own cache-filling calls where CalcScoreForPathsNew / GetPositionsOnlyPath /
-    //     AddPositions run them, so the same keys get aligned (internal min-hash aligner or bowtie2).
-    for (auto& e : paired_reads) {
-      e.second.first->PrecomputeAlignmentForPaths(paths, gr);    // graph.cc:1967
-      e.second.second->PrecomputeAlignmentForPaths(paths, gr);   // graph.cc:1968
+  // ReadSet::PrecomputeAlignmentForPaths (graph.cc:447-493) for the walks not seen before. The reference's loop carries
+  // `last_end` from one walk into the next (it only decides whether the FIRST window of a walk joins the mass
+  // precompute); a seen walk contributes its remembered final value and nothing else — every key it could add is in the
+  // cache since its first evaluation.
+  void PrecomputeNewWalks(ReadSet& rs, const vector<vector<int>>& paths, const vector<char>& is_new, vector<int>& final_end) {
+    unordered_set<vector<int>> subpaths_precomp;
+    int last_end = -1;
+    for (size_t p = 0; p < paths.size(); p++) {
+      const vector<int>& path = paths[p];
+      if (!is_new[p]) {
+        if (final_end[p] != kNoNode) last_end = final_end[p];
+        continue;
+      }
+      for (int i = 0; i < (int)path.size(); i++) {
+        if (path[i] < 0) continue;
+        int cur_seq_len = 0;
+        vector<int> cur_seq(1, path[i]);
+        int cur_end = i;
+        for (int j = i + 1; j < (int)path.size(); j++) {
+          if (path[j] < 0) break;
+          cur_seq_len += gr.nodes[path[j]]->s.length();
+          cur_seq.push_back(path[j]);
+          cur_end = j;
+          if (cur_seq_len > 300) break;
+        }
+        if (rs.aligment_cache_.count(cur_seq) == 0 &&
+            (last_end != cur_end || (cur_seq.size() == 1 && gr.nodes[cur_seq[0]]->s.length() > 150))) {
+          subpaths_precomp.insert(cur_seq);
+          subpaths_precomp.insert(InvertPath(cur_seq));
+        }
+        if (gr.nodes[path[i]]->s.length() > 300) {
+          if (rs.aligment_cache_.count(vector<int>({path[i]})) == 0) {
+            subpaths_precomp.insert(vector<int>({path[i]}));
+            subpaths_precomp.insert(vector<int>({path[i] ^ 1}));
+          }
+        }
+        last_end = cur_end;
+      }
     }
-    for (auto& m : mirrors_) {
-      for (auto& path : paths) {
-        vector<int> ctg;
-        for (size_t i = 0; i <= path.size(); i++) {
-          if (i == path.size() || path[i] < 0) {
-            unordered_set<vector<int>> missing;
-            m.rs->GetSubpathsFromPath(ctg, gr, missing);          // graph.cc:538-542, 605-609
-            if (!missing.empty()) m.rs->PrecomputeAligmentForSubpaths(gr, USetToVector(missing));
-            // (2) mirror every key this contig looks up and the device does not hold yet
-            for (size_t k = 0; k < ctg.size(); k++) {
-              MirrorKey(m, WindowKey(ctg, k));
-              if (m.paired && gr.nodes[ctg[k]]->s.length() > 300) MirrorKey(m, vector<int>(1, ctg[k]));   // graph.cc:563-566
+    if (!subpaths_precomp.empty()) rs.PrecomputeAligmentForSubpaths(gr, USetToVector(subpaths_precomp));
+  }
+
+  static int FinalEnd(const vector<int>& path, const Graph& g) {   // last_end after the reference's loop over this walk
+    int last = kNoNode;
+    for (int i = 0; i < (int)path.size(); i++) {
+      if (path[i] < 0) continue;
+      int cur_seq_len = 0, cur_end = i;
+      for (int j = i + 1; j < (int)path.size(); j++) {
+        if (path[j] < 0) break;
+        cur_seq_len += g.nodes[path[j]]->s.length();
+        cur_end = j;
+        if (cur_seq_len > 300) break;
+      }
+      last = cur_end;
+    }
+    return last;
+  }
+
+  // PacbioReadSet::GetReadProbabilities' cache fill (graph.cc:2438-2486) + mirroring for one NEW normalised walk.
+  void FillAndMirrorPacbio(PbMirror& m, const vector<int>& path) {
+    PacbioReadSet& rs = *m.rs;
+    const size_t n = path.size();
+    if (n == 0) return;
+    vector<int> begin(n), end(n);
+    int off = 0;
+    for (size_t i = 0; i < n; i++) {
+      begin[i] = off;
+      off += path[i] < 0 ? -path[i] : (int)gr.nodes[path[i]]->s.length();
+      end[i] = off;
+    }
+    vector<vector<int>> keys;
+    vector<pair<int, int>> missing;
+    for (size_t i = 0; i < n; i++) {
+      vector<int> sub;
+      for (size_t j = i; j < n; j++) {
+        sub.push_back(path[j]);
+        if (rs.aligment_cache_.count(sub) == 0) missing.push_back(make_pair((int)i, (int)j));
+        keys.push_back(sub);
+        if ((end[j] - begin[i]) - (end[i] - begin[i]) > rs.max_read_len_) break;   // graph.cc:2450
+      }
+    }
+    if (!missing.empty()) {   // merged runs of missing windows go to the aligner, graph.cc:2455-2486
+      int lastmissend = -47, lastmissbegin = -47;
+      sort(missing.begin(), missing.end());
+      for (size_t i = 0; i < missing.size(); i++) {
+        if (missing[i].first > lastmissend) {
+          if (lastmissend != -47) {
+            int tl;
+            rs.GetReadProbabilitiesSlow(gr, vector<int>(path.begin() + lastmissbegin, path.begin() + lastmissend + 1), tl);
+          }
+          lastmissbegin = missing[i].first;
+          lastmissend = missing[i].second;
+        }
+        lastmissend = max(lastmissend, missing[i].second);
+      }
+      if (lastmissend != -47) {
+        int tl;
+        rs.GetReadProbabilitiesSlow(gr, vector<int>(path.begin() + lastmissbegin, path.begin() + lastmissend + 1), tl);
+      }
+    }
+    vector<gaml_pacbio_alignment> recs;
+    for (auto& key : keys) {
+      if (m.sent.count(key)) continue;
+      auto it = rs.aligment_cache_.find(key);
+      if (it == rs.aligment_cache_.end()) continue;   // the reference asserts it is there by now (graph.cc:2497)
+      m.sent.insert(key);
+      recs.resize(it->second.size());
+      for (size_t k = 0; k < recs.size(); k++) {
+        recs[k].position = it->second[k].position;
+        recs[k].position_end = it->second[k].position_end;
+        recs[k].read_id = it->second[k].read_id;
+        recs[k].pad = 0;
+        recs[k].logprob = it->second[k].prob.logval;
+      }
+      Check(gaml_cache_insert_pacbio(ctx_, m.set, key.data(), (int)key.size(), recs.data(), (int64_t)recs.size()));
+    }
+  }
+
+  void FillAndMirrorCaches(const vector<vector<int>>& paths) {
+    // which walks are new to the adapter: same position as in the previous call (one compare), else the set of all
+    // walks ever evaluated (one hash probe)
+    vector<char> is_new(paths.size(), 0);
+    vector<int> final_end(paths.size(), kNoNode);
+    bool any_new = false;
+    for (size_t p = 0; p < paths.size(); p++) {
+      if (p < prev_paths_.size() && prev_paths_[p] == paths[p]) {
+        final_end[p] = prev_final_end_[p];
+        continue;
+      }
+      auto it = seen_.find(paths[p]);
+      if (it != seen_.end()) {
+        final_end[p] = it->second;
+      } else {
+        is_new[p] = 1;
+        any_new = true;
+        final_end[p] = FinalEnd(paths[p], gr);
+      }
+    }
+    if (any_new) {
+      // (1) the reference's own cache-filling calls where CalcScoreForPathsNew / GetPositionsOnlyPath / AddPositions run
+      //     them, so the same keys get aligned (internal min-hash aligner or bowtie2)
+      for (auto& e : paired_reads) {
+        PrecomputeNewWalks(*e.second.first, paths, is_new, final_end);    // graph.cc:1967
+        PrecomputeNewWalks(*e.second.second, paths, is_new, final_end);   // graph.cc:1968
+      }
+      for (auto& m : mirrors_) {
+        for (size_t p = 0; p < paths.size(); p++) {
+          if (!is_new[p]) continue;
+          const vector<int>& path = paths[p];
+          vector<int> ctg;
+          for (size_t i = 0; i <= path.size(); i++) {
+            if (i == path.size() || path[i] < 0) {
+              unordered_set<vector<int>> missing;
+              m.rs->GetSubpathsFromPath(ctg, gr, missing);          // graph.cc:538-542, 605-609
+              if (!missing.empty()) m.rs->PrecomputeAligmentForSubpaths(gr, USetToVector(missing));
+              // (2) mirror every key this contig looks up and the device does not hold yet
+              for (size_t k = 0; k < ctg.size(); k++) {
+                MirrorKey(m, WindowKey(ctg, k));
+                if (m.paired && gr.nodes[ctg[k]]->s.length() > 300) MirrorKey(m, vector<int>(1, ctg[k]));   // graph.cc:563-566
+              }
+              ctg.clear();
+            } else {
+              ctg.push_back(path[i]);
             }
-            ctg.clear();
-          } else {
-            ctg.push_back(path[i]);
           }
         }
       }
+      for (auto& m : pb_mirrors_) {
+        for (size_t p = 0; p < paths.size(); p++) {
+          if (!is_new[p]) continue;
+          vector<int> path = paths[p];
+          gr.NormalizePath(path);                                    // graph.cc:3184
+          FillAndMirrorPacbio(m, path);
+        }
+      }
+      for (size_t p = 0; p < paths.size(); p++)
+        if (is_new[p]) seen_.emplace(paths[p], final_end[p]);
     }
+    prev_paths_ = paths;
+    prev_final_end_.swap(final_end);
   }
+
+  struct PbMirror {
+    PacbioReadSet* rs;
+    int set;
+    unordered_set<vector<int>> sent;
+  };
+  static const int kNoNode = -1000000;   // FinalEnd of a walk without any node: it leaves `last_end` alone
 
   gaml_ctx* ctx_;
   size_t n_sets_ = 0;
   vector<Mirror> mirrors_;
+  vector<PbMirror> pb_mirrors_;
+  unordered_map<vector<int>, int> seen_;   // every walk evaluated so far -> its FinalEnd
+  vector<vector<int>> prev_paths_;
+  vector<int> prev_final_end_;
 };
 
 #endif

@@ -252,6 +252,70 @@ def c2():
     pc.close()
 
 
+# ---- BASELINE config 4 shape: 10 000 walks, 20 000 keys per mate (slot tables far beyond L1), one read-id shard ---------
+@pytest.fixture(scope="module")
+def c4():
+    wl = synth.paired_workload(10000, 10000, 1_200_000, n_evals=22, seed=44)
+    yield wl
+
+
+def test_c4_shape_full_and_incremental_match_oracle(c4, oracle):
+    """Config 4's shape (100 Mbp genome, 10 000 nodes / walks) on a reduced read count: the full evaluation and 21
+    incremental steps against the oracle — totals <= 1e-9, floored counts and total_len exact, per-read values bit-exact."""
+    wl = c4
+    assert len(wl.evals[0]) >= 10000
+    ref = oracle(wl, "c4shape", dump=True)
+    check_against(wl, ref)
+
+
+def test_c4_shape_two_shards_and_internal_order(c4, monkeypatch):
+    """The same trajectory as two read-id shards (exact combine), and with the caller's read order kept on the device
+    (GAML_B200_NO_PERMUTE): partial sums and per-read values must be IDENTICAL to the default context's."""
+    wl = c4
+    whole = api.ProbCalculator.from_workload(wl)
+    monkeypatch.setenv("GAML_B200_NO_PERMUTE", "1")
+    plain = api.ProbCalculator.from_workload(wl)
+    monkeypatch.delenv("GAML_B200_NO_PERMUTE")
+    shards = [api.ProbCalculator.from_workload(wl, shard_of=(r, 2)) for r in range(2)]
+    for e, walks in enumerate(wl.evals[:12]):
+        pw, tw = whole.calc_prob_partial(walks)
+        pp, tp = plain.calc_prob_partial(walks)
+        assert tw == tp and np.array_equal(pw, pp), e
+        parts, tls = zip(*[pc.calc_prob_partial(walks) for pc in shards])
+        assert shards[0].combine(np.stack(parts), 2, tls[0]) == whole.combine(pw[None, :], 1, tw), e
+    assert np.array_equal(whole.read_values(0), plain.read_values(0))
+    assert np.array_equal(whole.read_values(0), np.concatenate([pc.read_values(0) for pc in shards]))
+    for pc in shards + [whole, plain]:
+        pc.close()
+
+
+def test_c4_shape_batch_of_1024_candidates(c4):
+    """BASELINE config 5 on the config-4 shape: 1024 candidate moves in one batch; a sample of them must equal, bit for
+    bit, the sequential evaluation of that candidate's walk set by a fresh context with the same history."""
+    import bench
+    wl = c4
+    history = wl.evals[:6]
+    base = history[-1]
+    pc = api.ProbCalculator.from_workload(wl)
+    for walks in history:
+        last = pc.calc_prob(walks)
+    cands = bench.make_candidates(base, 1024, np.random.default_rng(5))
+    probs, tls, zeros = pc.calc_prob_batch(cands)
+    assert pc.calc_prob(base) == last   # stateless
+    pc.close()
+    assert len(set(int(t) for t in tls)) > 50   # many distinct total lengths: the one-pass base sum is really exercised
+    for i in (0, 1, 17, 300, 511, 777, 1023):
+        erased, added = cands[i]
+        walks = [w for k, w in enumerate(base) if k not in set(erased)] + [list(w) for w in added]
+        ref_pc = api.ProbCalculator.from_workload(wl)
+        for h in history:
+            ref_pc.calc_prob(h)
+        p, z, tl = ref_pc.calc_prob(walks)
+        ref_pc.close()
+        assert probs[i] == p, (i, probs[i], p)
+        assert int(tls[i]) == tl and (int(zeros[i, 0, 0]), int(zeros[i, 0, 1])) == z[0]
+
+
 def test_c2_incremental_state_equals_full_rescore(c2):
     """Walk the scripted trajectory incrementally, then re-score the last walk set from scratch: the
     persistent per-read state may differ from a fresh one only by the reference's own rounding drift."""

@@ -53,14 +53,18 @@ def main():
     results = {}
     for shape in shapes:
         os.environ.pop("GAML_B200_NO_TERM_TABLE", None)
+        os.environ.pop("GAML_B200_NO_PERMUTE", None)
         if shape == "notab":
             os.environ["GAML_B200_NO_TERM_TABLE"] = "1"
             os.environ["GAML_B200_STREAM_SHAPE"] = "0"
+        elif shape.endswith("np"):
+            os.environ["GAML_B200_NO_PERMUTE"] = "1"
+            os.environ["GAML_B200_STREAM_SHAPE"] = shape[:-2]
         else:
             os.environ["GAML_B200_STREAM_SHAPE"] = shape
         if "wl" not in results:
             t0 = time.time()
-            results["wl"] = bench.make_workload(1, 0, 4, kind=kind)
+            results["wl"] = bench.make_workload(1, 0, int(os.environ.get("SWEEP_EVALS", "202")), kind=kind)
             if sort_reads:
                 relabel_by_key(results["wl"][0])
             print(f"workload {kind} generated in {time.time() - t0:.1f}s", flush=True)
