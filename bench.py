@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the c2 workload (debug only; 1.0 = config 2)")
     ap.add_argument("--delta-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in ProbCalculator leg (oracle/_ref/gpu_harness)")
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4shard"],
                     help="auto (default): config 2 on one GPU, one eighth of config 4 per GPU on several")
     ap.add_argument("--batch", type=int, default=1024, help="candidate moves per gaml_calc_prob_batch launch (0 = skip)")
@@ -584,6 +585,75 @@ def main():
         "cache_upload": {"seconds": t_upload, "bytes": int(cache_bytes)},
         "result": {"prob": prob, "total_len": tl_full, "floored": zeros[0][0]},
     }
+
+    # ---- cache growth (SURVEY §7.3 "the arena must support append"): the same trajectory on a context that starts with the
+    #      keys of the first walk set only and is handed each new window when a walk first needs it (what the annealing loop's
+    #      on-demand aligner does, graph.cc:1967-1968) — insert + evaluate timed together ----
+    if rank == 0 and world == 1 and args.delta_steps > 0:
+        from gaml_b200 import synth
+        spec = wl.sets[0]
+        pc2 = api.ProbCalculator(wl.node_len, wl.normalize_map, local_rank)
+        sid2 = pc2.add_readset(spec)
+        have = [set(), set()]
+
+        def missing_keys(walks):
+            out = []
+            for k in synth.short_keys_for_walks(walks, wl.node_len, with_single_node=True):
+                for m in range(2):
+                    if k not in have[m] and k in spec.caches[m]:
+                        have[m].add(k)
+                        out.append((m, k, spec.caches[m][k]))
+            return out
+        for m, k, recs in missing_keys(walks0):
+            pc2.cache_insert(sid2, m, k, recs)
+        pc2.calc_prob_partial_flat(flat0)
+        grow_us, warm_us, new_keys, new_recs = [], [], 0, 0
+        for fw, walks in zip(seq_flat, seq):
+            todo = missing_keys(walks)
+            t0 = time.perf_counter()
+            for m, k, recs in todo:
+                pc2.cache_insert(sid2, m, k, recs)
+            part2, _tl2 = pc2.calc_prob_partial_flat(fw)
+            dt = (time.perf_counter() - t0) * 1e6
+            (grow_us if todo else warm_us).append(dt)
+            new_keys += len(todo)
+            new_recs += sum(len(r) for _, _, r in todo)
+        st2 = pc2.stats()
+        line["append"] = {"evals_inserting_keys": len(grow_us), "us_per_eval_inserting": float(np.median(grow_us)) if grow_us else None,
+                          "mean_us_inserting": float(np.mean(grow_us)) if grow_us else None,
+                          "us_per_eval_warm": float(np.median(warm_us)) if warm_us else None, "keys_inserted": new_keys, "records_inserted": new_recs,
+                          "cache_appends": int(st2.cache_appends), "cache_rebuilds": int(st2.cache_rebuilds),
+                          "same_partials_as_preloaded_context": bool(np.array_equal(part2, pc.calc_prob_partial_flat(seq_flat[-1])[0])) if seq_flat else None,
+                          "note": "gaml_cache_insert of the windows a walk set needs for the first time + gaml_calc_prob_partial, wall clock, median; "
+                                  "the records go to the arena tail, the affected reads' rows are relocated and the reads scored by the appendix phase"}
+        pc2.close()
+
+    # ---- the drop-in boundary: ProbCalculator::CalcProb of integration/prob_calculator.h, driven by the reference's
+    #      cache-injection harness compiled against it (oracle/_ref/gpu_harness), on the same incremental trajectory ----
+    gpu_harness = os.path.join(ROOT, "oracle", "_ref", "gpu_harness")
+    if rank == 0 and world == 1 and not args.no_dropin and os.path.exists(gpu_harness):
+        from gaml_b200 import workload as wlmod
+        n_drop = min(len(wl.evals), 1 + min(args.delta_steps, 100))
+        sub = wlmod.Workload(node_len=wl.node_len, normalize_map=wl.normalize_map, sets=wl.sets, evals=wl.evals[:n_drop])
+        try:
+            with tempfile.TemporaryDirectory() as tmp:
+                wp, rp = os.path.join(tmp, "dropin.wl"), os.path.join(tmp, "dropin.res")
+                wlmod.write_workload(wp, sub)
+                t0 = time.perf_counter()
+                subprocess.run([gpu_harness, wp, rp, "0", "2"], check=True, cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                               timeout=600)
+                log(f"drop-in leg took {time.perf_counter() - t0:.1f}s")
+                res = wlmod.read_results(rp)
+            # second repeat: a fresh ProbCalculator over host caches that are complete — its first call mirrors the cache
+            # (excluded), the following ones are warm incremental CalcProb calls
+            warm = np.array([r.seconds for r in res[n_drop + 1:]]) * 1e6
+            ok = all(abs(a.score - b.score) <= 1e-9 * abs(b.score) for a, b in zip(res[:n_drop], res[n_drop:]))
+            line["dropin"] = {"dropin_us_per_calcprob": float(np.median(warm)), "mean_us": float(warm.mean()), "calls": int(len(warm)),
+                              "c_abi_e2e_us_per_eval": 1e3 * line["incremental"]["e2e_ms_per_eval"], "repeat_scores_agree": bool(ok),
+                              "note": "ProbCalculator::CalcProb(paths, zeros, total_len) of integration/prob_calculator.h (vector<vector<int>> in, "
+                                      "score out), timed inside oracle/_ref/gpu_harness around each call on the incremental trajectory; median"}
+        except Exception as exc:   # the boundary leg never takes the bench line down
+            line["dropin"] = {"error": str(exc)[:200]}
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         # bounded CPU sample on the box's host: the reference's own scorer, 1 core, the whole workload, a few full evaluations

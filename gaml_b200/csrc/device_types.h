@@ -104,6 +104,12 @@ struct ScoreParams {
   const uint32_t* xlist;     //   and the cross list: tier-1 reads the fast records leave to the general body (ascending read ids)
   int32_t n_cross;
   int32_t n_tier1;           //   and the number of reads tier 1 streams ([0, n_tier1) of the internal order; n_reads without one)
+  // reads that gained records since the static lists were built (cache appends, kernels.cu append_rows_kernel): flagged
+  // in `dirty` (and in their packed / fast records), skipped by every list-driven phase and scored from their rows by the
+  // appendix phase instead
+  const uint32_t* dirty;     // per read, or null when no append has happened since the last rebuild
+  const uint32_t* appx_list;
+  int32_t n_appx;
   uint32_t uniform_ll;       // paired: the packed lengths when every pair of the set has the same ones (lens_uniform)
   int32_t lens_uniform;
   const double* ins_tab;     // insert pdf for dist in [0, ins_n), host-computed; 0 beyond (exp underflow)
@@ -146,7 +152,7 @@ struct ScoreParams {
   // chain discipline of the streaming kernels (set per launch)
   int32_t chain_first;       // 1: first kernel after apply_slots in its group: waits at its top; 0: waits at its end
   int32_t finish_here;       // 1: this kernel's last block publishes the set when nothing was listed for the pass after it
-  uint32_t* tile_counter;    // next tile of [0] tier 1, [1] the rare shapes, [2] tier 2, [3] the cross list (zeroed by apply_slots)
+  uint32_t* tile_counter;    // next tile of [0] tier 1, [1] the rare shapes, [2] tier 2, [3] the cross list, then the appendix (zeroed by apply_slots)
   uint32_t* ticket2;         // blocks-finished counter of the set's last kernel (finish_set)
   uint32_t* done;            // set by finish_set_if_complete
   // reduction: exact 128-bit fixed-point sum of the log terms of this set (kAccumStride u64)

@@ -96,13 +96,18 @@ struct WalkFlat {
   std::vector<FlatEntry> e[2];
   std::vector<int> contig_starts;
   int64_t records = 0, records1 = 0;
+  // validity across cache growth: keys are immutable once inserted, so a walk's lookups change only when a window that
+  // was NOT in the cache when they were built is inserted later — gen = the store's key count at build time, missing =
+  // the hashes of the windows that were looked up and not found
+  size_t gen[2] = {0, 0};
+  std::vector<size_t> missing[2];
 };
 struct FlatCache {   // chained hash table keyed by walk content; the caller supplies the (already computed) hash
   struct Node { size_t h; Walk w; WalkFlat f; int next; };
   std::vector<Node> nodes;
   std::vector<int> buckets;
   void clear() { nodes.clear(); buckets.clear(); }
-  const WalkFlat* find(const int* p, int n, size_t h) const {
+  WalkFlat* find(const int* p, int n, size_t h) {
     if (buckets.empty()) return nullptr;
     for (int i = buckets[h & (buckets.size() - 1)]; i >= 0; i = nodes[i].next)
       if (nodes[i].h == h && (int)nodes[i].w.size() == n && (n == 0 || memcmp(nodes[i].w.data(), p, sizeof(int) * (size_t)n) == 0))
@@ -150,6 +155,13 @@ struct MateStore {
   int table_index = -1;               // position in ctx->d_tables
   std::vector<uint32_t> key_stamp;    // group_occurrences scratch: epoch that last saw the key / its SlotUpdate index
   std::vector<int> key_slot, fill_cursor;
+  // cache append (kernels.cu "cache append"): the row array has slack behind the rows of the last full build, rows_tail is
+  // the next free row; h_count = every read's record count (internal read index), kept in step by the host
+  size_t rows_cap = 0, rows_tail = 0;
+  std::vector<uint16_t> h_count;
+  std::vector<size_t> key_hash_log;   // hash of every key, in insertion order (WalkFlat validation)
+  std::vector<const Walk*> key_by_id; // the key's node sequence (points into key_ids: stable)
+  size_t built_keys = 0;              // keys the device tables / key maps know about
   size_t total_records() const { return arena_n + pending.size(); }
 };
 
@@ -165,6 +177,14 @@ struct ReadSetState {
   DevBuf d_pairs;               // paired: PackedPair per pair (kernels.cu), valid when pairs_ok
   DevBuf d_uni_prob[2];           // paired, uniform lengths: alignment probability by edit distance, per mate (kernels.cu)
   // internal read order (kernels.cu "internal read order"): fixed at the first commit of a set with fast records
+  // cache append: reads that gained records since the last full build are flagged (device) and listed for the appendix
+  // phase; base_built = the static lists exist and appends may be applied on top of them
+  bool base_built = false;
+  DevBuf d_dirty, d_appx, d_append_blob;
+  std::vector<uint8_t> h_dirty;
+  int n_appx = 0;
+  std::vector<int32_t> h_p12, h_p21;   // key maps between the mates' stores (same node sequence), -1 = no partner
+  int64_t appends = 0, rebuilds = 0;
   bool perm_valid = false;
   std::vector<uint32_t> h_inv;    // caller's local read id -> internal index (cache inserts, gaml_read_values)
   std::vector<uint32_t> h_perm;   // internal index -> caller's local read id (gaml_cache_save)
@@ -333,6 +353,7 @@ struct gaml_ctx {
   std::vector<Walk> h_walks;
   bool fast_changes = true;       // GAML_B200_NO_FAST_CHANGES=1: always build the reference's container (tests)
   bool permute_reads = true;      // GAML_B200_NO_PERMUTE=1: keep the caller's read order on the device (tests, measurements)
+  bool append_enabled = true;     // GAML_B200_NO_APPEND=1: every cache growth rebuilds the device index (tests, measurements)
   HashCounts prev_counts;         // multiplicity of every walk hash in prev() (kept in step by finish())
   bool have_prev = false;         // prev() holds a finished evaluation's walks
   WalkDiff cur_diff;              // cur() against prev(), from prepare()
@@ -364,10 +385,9 @@ int fail(gaml_ctx* ctx, int code, const std::string& msg) {
 
 // d_flags layout (u64 words, zeroed at the start of every evaluation): [0] scratch cursor | [1] error flag (u32) |
 // [2, 2+n) per-set overflow counters (u32 in u64 slots) | [2+n, 2+2n) tickets of the last streaming kernel |
-// [2+2n, 2+3n) tickets of the last kernel | [2+3n, 2+4n) "published early" marks | [2+4n, 2+6n) tile counters of
-// tier 1 and tier 2 | then per set kAccumStride
-// words of exact accumulators
-size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (6 + kAccumStride); }
+// [2+2n, 2+3n) tickets of the last kernel | [2+3n, 2+4n) "published early" marks | [2+4n, 2+8n) tile counters (eight
+// u32 per set: tier 1, rare shapes, tier 2, cross list, appendix) | then per set kAccumStride words of exact accumulators
+size_t flags_words(size_t n_sets) { return 2 + std::max<size_t>(n_sets, 1) * (8 + kAccumStride); }
 
 double insert_pdf(double d, double mean, double sd) {   // graph.cc:1593-1598, same expression order
   double z = (d - mean) / sd;
@@ -446,6 +466,10 @@ void build_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, Wa
   out.e[0].clear();
   out.e[1].clear();
   out.records = out.records1 = 0;
+  for (int m = 0; m < 2; m++) {
+    out.gen[m] = rs.mate[m].keys.size();
+    out.missing[m].clear();
+  }
   out.contig_starts.assign(1, 0);   // events (0,1) and (cur_len,1) per later contig, graph.cc:1826, 1835
   for (size_t c = 0; c < ctgs.size(); c++) {
     if (c > 0) {
@@ -461,10 +485,15 @@ void build_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const Walk& walk, Wa
         int node_max = 0;
         window_key(ctx, ctg, i, key);
         int kid[2] = {find_key(st, key), -1};
+        if (kid[0] < 0) out.missing[m].push_back(hash_nodes(key.data(), (int)key.size()));
         if (ctx->node_len[ctg[i]] > kWindowLen) {
           if (key.size() == 1) kid[1] = -1;   // window key IS the single-node key: the second lookup re-visits
                                               // the same list at the same offset, a no-op under the de-dup rule
-          else { Walk one(1, ctg[i]); kid[1] = find_key(st, one); }
+          else {
+            Walk one(1, ctg[i]);
+            kid[1] = find_key(st, one);
+            if (kid[1] < 0) out.missing[m].push_back(hash_nodes(one.data(), 1));
+          }
         }
         for (int t = 0; t < 2; t++) {
           if (kid[t] < 0) continue;
@@ -493,7 +522,20 @@ size_t hash_walk(const Walk& w) { return WalkHash()(w); }
 
 const WalkFlat& cached_walk_flat(const gaml_ctx* ctx, ReadSetState& rs, const WalkView& v) {
   FlatCache& fc = rs.flat_cache;
-  if (const WalkFlat* f = fc.find(v.p, v.n, v.h)) return *f;
+  if (WalkFlat* f = fc.find(v.p, v.n, v.h)) {
+    bool stale = false;
+    for (int m = 0; m < 2; m++) {
+      const MateStore& st = rs.mate[m];
+      if (f->gen[m] == st.keys.size()) continue;
+      if (!f->missing[m].empty())
+        for (size_t g = f->gen[m]; g < st.key_hash_log.size() && !stale; g++)
+          stale = std::find(f->missing[m].begin(), f->missing[m].end(), st.key_hash_log[g]) != f->missing[m].end();
+      f->gen[m] = st.keys.size();
+    }
+    if (!stale) return *f;
+    build_walk_flat(ctx, rs, Walk(v.p, v.p + v.n), *f);   // a window this walk looks up has been inserted since
+    return *f;
+  }
   if (fc.nodes.size() >= (1u << 17)) fc.clear();   // bound the memory of a very long annealing run
   const Walk walk(v.p, v.p + v.n);
   WalkFlat& f = fc.insert(walk, v.h);
@@ -646,10 +688,150 @@ int ensure_pinned(gaml_ctx* ctx, size_t bytes) {
   return GAML_OK;
 }
 
+// Cache append (SURVEY §7.3 "the arena must support append"; kernels.cu "cache append"): keys inserted since the last
+// full build — typically the windows of one new join, a few hundred records — are applied in O(new records): records to
+// the arena tail, one relocated row block per read that gained records, the read flagged for the appendix phase, the
+// new keys added to the key maps. Returns 1 = applied, 0 = not applicable (the caller rebuilds), < 0 = error.
+int try_append(gaml_ctx* ctx, ReadSetState& rs) {
+  if (!ctx->append_enabled || rs.cfg.kind != GAML_KIND_PAIRED || rs.n_mates != 2 || !rs.base_built || !rs.pairs_ok || rs.penalty) return 0;
+  cudaStream_t st_ = ctx->stream;
+  struct MatePlan {
+    std::vector<int4> new_rows;             // {key, pos, edor, seq}, grouped by read
+    std::vector<AppendGroupHost> groups;
+    size_t tail_after = 0;
+  } plan[2];
+  size_t newly_dirty = 0;
+  std::vector<uint32_t> dirty_now;
+  for (int m = 0; m < 2; m++) {
+    MateStore& st = rs.mate[m];
+    plan[m].tail_after = st.rows_tail;
+    if (!st.dirty || st.pending.empty()) continue;
+    if (st.total_records() > 0xfffffff0ull) return 0;
+    const size_t n = st.pending.size();
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    auto read_of = [&](uint32_t i) { return rs.perm_valid ? rs.h_inv[(size_t)st.pending[i].x] : (uint32_t)st.pending[i].x; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return read_of(a) < read_of(b); });
+    plan[m].new_rows.resize(n);
+    size_t tail = st.rows_tail;
+    for (size_t i = 0; i < n;) {
+      const uint32_t r = read_of(order[i]);
+      size_t j = i;
+      for (; j < n && read_of(order[j]) == r; j++) {
+        const int4& a = st.pending[order[j]];   // {read, pos, edor, key}
+        plan[m].new_rows[j] = make_int4(a.w, a.y, a.z, (int)(uint32_t)(st.arena_n + order[j]));
+      }
+      const size_t cnt_old = st.h_count[r], need = cnt_old + (j - i);
+      if (need >= 0x3fff || cnt_old == 0xffff) return 0;
+      plan[m].groups.push_back(AppendGroupHost{r, (uint32_t)i, (uint32_t)(j - i), (uint32_t)tail});
+      tail += need;
+      if (!rs.h_dirty[r]) {
+        rs.h_dirty[r] = 2;   // provisional: counted once over both mates, confirmed or rolled back below
+        dirty_now.push_back(r);
+        newly_dirty++;
+      }
+      i = j;
+    }
+    plan[m].tail_after = tail;
+  }
+  const size_t limit = std::max<size_t>(4096, (size_t)rs.n_local / 16);
+  const bool fits = plan[0].tail_after <= rs.mate[0].rows_cap && plan[1].tail_after <= rs.mate[1].rows_cap &&
+                    (size_t)rs.n_appx + newly_dirty <= limit;
+  if (!fits) {
+    for (uint32_t r : dirty_now) rs.h_dirty[r] = 0;
+    return 0;
+  }
+  for (uint32_t r : dirty_now) rs.h_dirty[r] = 1;
+  // ---- apply ----
+  int launches = 0;
+  for (int m = 0; m < 2; m++) {
+    MateStore& st = rs.mate[m];
+    if (!st.dirty) continue;
+    const size_t total = st.total_records();
+    if (!st.pending.empty()) {
+      if (rs.perm_valid)
+        for (int4& v : st.pending) v.x = (int)rs.h_inv[(size_t)v.x];
+      CU(st.arena.reserve(total * 16, st.arena_n * 16, false, st_));
+      CU(cudaMemcpyAsync(st.arena.as<char>() + st.arena_n * 16, st.pending.data(), st.pending.size() * 16, cudaMemcpyHostToDevice, st_));
+      const size_t rows_bytes = plan[m].new_rows.size() * 16, grp_bytes = plan[m].groups.size() * sizeof(AppendGroupHost);
+      CU(rs.d_append_blob.reserve(2 * (rows_bytes + grp_bytes + 64), 0, false, st_));
+      char* blob = rs.d_append_blob.as<char>() + (size_t)m * (rs.d_append_blob.cap / 2);
+      CU(cudaMemcpyAsync(blob, plan[m].new_rows.data(), rows_bytes, cudaMemcpyHostToDevice, st_));
+      CU(cudaMemcpyAsync(blob + rows_bytes, plan[m].groups.data(), grp_bytes, cudaMemcpyHostToDevice, st_));
+      launch_append_rows(blob + rows_bytes, (int)plan[m].groups.size(), blob, st.rows.p, st.first.p, rs.d_dirty.as<uint32_t>(), rs.d_pairs.p,
+                         rs.fast_ok ? rs.d_fast.p : nullptr, st_);
+      launches++;
+      for (const AppendGroupHost& g : plan[m].groups) st.h_count[g.read] = (uint16_t)(st.h_count[g.read] + g.n_new);
+      st.rows_tail = plan[m].tail_after;
+      st.arena_n = total;
+      CU(cudaStreamSynchronize(st_));   // pending / plan vectors are pageable host memory about to be released
+      st.pending.clear();
+    }
+    const size_t old_slots = st.slots_a.cap;
+    CU(st.slots_a.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotA), 0, true, st_));
+    CU(st.slots_b.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotB), 0, true, st_));
+    if (st.slots_a.cap != old_slots) ctx->tables_dirty = true;
+    st.dirty = false;
+  }
+  if (!dirty_now.empty()) {
+    CU(rs.d_appx.reserve(((size_t)rs.n_appx + dirty_now.size()) * 4, (size_t)rs.n_appx * 4, false, st_));
+    CU(cudaMemcpyAsync(rs.d_appx.as<uint32_t>() + rs.n_appx, dirty_now.data(), dirty_now.size() * 4, cudaMemcpyHostToDevice, st_));
+    CU(cudaStreamSynchronize(st_));
+    rs.n_appx += (int)dirty_now.size();
+  }
+  // ---- key maps between the mates' stores and the combined slot table: the new keys only ----
+  {
+    MateStore &s1 = rs.mate[0], &s2 = rs.mate[1];
+    const size_t k1 = s1.keys.size(), k2 = s2.keys.size();
+    const size_t old1 = rs.h_p12.size(), old2 = rs.h_p21.size();
+    rs.h_p12.resize(std::max<size_t>(k1, 1), -1);
+    rs.h_p21.resize(std::max<size_t>(k2, 1), -1);
+    for (size_t k = s1.built_keys; k < k1; k++) {
+      auto it = s2.key_ids.find(*s1.key_by_id[k]);
+      if (it != s2.key_ids.end()) { rs.h_p12[k] = it->second; rs.h_p21[(size_t)it->second] = (int32_t)k; }
+    }
+    for (size_t k = s2.built_keys; k < k2; k++) {
+      auto it = s1.key_ids.find(*s2.key_by_id[k]);
+      if (it != s1.key_ids.end()) { rs.h_p21[k] = it->second; rs.h_p12[(size_t)it->second] = (int32_t)k; }
+    }
+    const void* old_comb = rs.d_comb.p;
+    const void* old_p21 = rs.d_partner21.p;
+    CU(rs.d_partner12.reserve(rs.h_p12.size() * 4, old1 * 4, false, st_));
+    CU(rs.d_partner21.reserve(rs.h_p21.size() * 4, old2 * 4, false, st_));
+    // (a new key of one store may be the partner of an OLD key of the other: re-send the maps from the first touched entry)
+    size_t lo1 = std::min(old1, s1.built_keys), lo2 = std::min(old2, s2.built_keys);
+    for (size_t k = s2.built_keys; k < k2; k++)
+      if (rs.h_p21[k] >= 0) lo1 = std::min(lo1, (size_t)rs.h_p21[k]);
+    for (size_t k = s1.built_keys; k < k1; k++)
+      if (rs.h_p12[k] >= 0) lo2 = std::min(lo2, (size_t)rs.h_p12[k]);
+    if (lo1 < rs.h_p12.size())
+      CU(cudaMemcpyAsync(rs.d_partner12.as<int32_t>() + lo1, rs.h_p12.data() + lo1, (rs.h_p12.size() - lo1) * 4, cudaMemcpyHostToDevice, st_));
+    if (lo2 < rs.h_p21.size())
+      CU(cudaMemcpyAsync(rs.d_partner21.as<int32_t>() + lo2, rs.h_p21.data() + lo2, (rs.h_p21.size() - lo2) * 4, cudaMemcpyHostToDevice, st_));
+    CU(rs.d_comb.reserve(rs.h_p12.size() * 2 * sizeof(SlotA), 0, true, st_));   // per-evaluation contents: nothing to keep
+    CU(cudaStreamSynchronize(st_));
+    if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21) ctx->tables_dirty = true;
+    s1.built_keys = k1;
+    s2.built_keys = k2;
+  }
+  ctx->stats.kernel_launches += launches;
+  rs.appends++;
+  return 1;
+}
+
 // Upload staged cache inserts and rebuild the read-major CSR of every dirty store.
 int commit(gaml_ctx* ctx) {
   for (auto& rsp : ctx->sets) {
     ReadSetState& rs = *rsp;
+    bool any_dirty = false;
+    for (int m = 0; m < rs.n_mates; m++) any_dirty |= rs.mate[m].dirty;
+    if (any_dirty) {
+      const int ar = try_append(ctx, rs);
+      if (ar < 0) return ar;
+      if (ar == 1) continue;
+      for (int m = 0; m < rs.n_mates; m++) rs.mate[m].dirty = true;   // full rebuild of the set: both mates' lists and the shared ones
+      rs.rebuilds++;
+    }
    for (int pass = 0; pass < 2; pass++) {   // (a second pass only right after the internal read order has been fixed)
     for (int m = 0; m < rs.n_mates; m++) {
       MateStore& st = rs.mate[m];
@@ -673,7 +855,10 @@ int commit(gaml_ctx* ctx) {
         st.pending_pos.clear();
         st.pending_pos.shrink_to_fit();
       }
-      CU(st.rows.reserve(std::max<size_t>(total, 1) * 16, 0, false, ctx->stream));
+      st.rows_cap = st.is_long ? std::max<size_t>(total, 1) : total + std::max<size_t>(total / 4, (size_t)1 << 16);   // slack for appends
+      st.rows_tail = total;
+      CU(st.rows.reserve(st.rows_cap * 16, 0, false, ctx->stream));
+      st.rows_cap = std::max(st.rows_cap, st.rows.cap / 16);
       if (!st.is_long) CU(st.first.reserve(std::max<size_t>(rs.n_local, 1) * 16, 0, false, ctx->stream));
       CU(st.rowptr.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
       CU(st.cursor.reserve(((size_t)rs.n_local + 1) * 4, 0, false, ctx->stream));
@@ -689,7 +874,7 @@ int commit(gaml_ctx* ctx) {
       ctx->stats.kernel_launches += launches;
       st.dirty = false;
       rs.complex_dirty = true;
-      rs.flat_cache.clear();   // key ids / record counts / max positions changed
+      // (the per-walk lookup cache stays: keys are immutable, cached_walk_flat re-checks the windows a walk missed)
     }
     if (rs.complex_dirty && rs.cfg.kind != GAML_KIND_PACBIO) {
       // static tier-2 list: reads that own more than one record on some mate
@@ -732,7 +917,12 @@ int commit(gaml_ctx* ctx) {
         // key maps between the two mates' stores (same node sequence) and the combined slot table
         {
           MateStore &s1 = rs.mate[0], &s2 = rs.mate[1];
-          std::vector<int32_t> p12(std::max<size_t>(s1.keys.size(), 1), -1), p21(std::max<size_t>(s2.keys.size(), 1), -1);
+          std::vector<int32_t>& p12 = rs.h_p12;
+          std::vector<int32_t>& p21 = rs.h_p21;
+          p12.assign(std::max<size_t>(s1.keys.size(), 1), -1);
+          p21.assign(std::max<size_t>(s2.keys.size(), 1), -1);
+          s1.built_keys = s1.keys.size();
+          s2.built_keys = s2.keys.size();
           for (const auto& kv : s1.key_ids) {
             auto it = s2.key_ids.find(kv.first);
             if (it != s2.key_ids.end()) {
@@ -747,7 +937,7 @@ int commit(gaml_ctx* ctx) {
           CU(cudaMemcpyAsync(rs.d_partner12.p, p12.data(), p12.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
           CU(cudaMemcpyAsync(rs.d_partner21.p, p21.data(), p21.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
           CU(rs.d_comb.reserve(p12.size() * 2 * sizeof(SlotA), 0, true, ctx->stream));
-          CU(cudaStreamSynchronize(ctx->stream));   // p12 / p21 are locals
+          CU(cudaStreamSynchronize(ctx->stream));
           if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21 || !rs.comb_ok) ctx->tables_dirty = true;
           rs.comb_ok = true;
         }
@@ -798,6 +988,25 @@ int commit(gaml_ctx* ctx) {
       }
       ctx->stats.kernel_launches += launches;
       rs.complex_dirty = false;
+      // the state appends build on: every read's record count per mate on the host, no read dirty, an empty appendix
+      rs.base_built = false;
+      if (rs.cfg.kind == GAML_KIND_PAIRED && rs.n_mates == 2 && rs.n_local > 0 && rs.pairs_ok) {
+        DevBuf counts;
+        CU(counts.reserve((size_t)rs.n_local * 2, 0, false, ctx->stream));
+        for (int m = 0; m < 2; m++) {
+          MateStore& st = rs.mate[m];
+          launch_extract_counts(st.first.p, st.rowptr.as<uint32_t>(), rs.n_local, counts.as<uint16_t>(), ctx->stream);
+          st.h_count.resize((size_t)rs.n_local);
+          CU(cudaMemcpyAsync(st.h_count.data(), counts.p, (size_t)rs.n_local * 2, cudaMemcpyDeviceToHost, ctx->stream));
+          CU(cudaStreamSynchronize(ctx->stream));
+          ctx->stats.kernel_launches++;
+        }
+        CU(rs.d_dirty.reserve((size_t)rs.n_local * 4, 0, false, ctx->stream));
+        CU(cudaMemsetAsync(rs.d_dirty.p, 0, (size_t)rs.n_local * 4, ctx->stream));
+        rs.h_dirty.assign((size_t)rs.n_local, 0);
+        rs.n_appx = 0;
+        rs.base_built = true;
+      }
     }
     if (pass == 1 || !rs.fast_ok || rs.perm_valid || !ctx->permute_reads) break;
     {
@@ -1211,6 +1420,9 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.xlist = rs.d_xlist.as<uint32_t>();
   P.n_cross = rs.fast_ok ? rs.n_cross : 0;
   P.n_tier1 = rs.perm_valid ? rs.n_fast : rs.n_local;
+  P.dirty = rs.n_appx > 0 ? rs.d_dirty.as<uint32_t>() : nullptr;
+  P.appx_list = rs.d_appx.as<uint32_t>();
+  P.n_appx = rs.n_appx;
   P.ins_tab = rs.d_ins.as<double>();
   P.ins_n = rs.ins_n;
   P.pstar_tab = reinterpret_cast<const double*>(blob + sp.pstar_off);
@@ -1254,8 +1466,8 @@ ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   P.ticket = reinterpret_cast<uint32_t*>(fl + 2 + ns + s);
   P.ticket2 = reinterpret_cast<uint32_t*>(fl + 2 + 2 * ns + s);
   P.done = reinterpret_cast<uint32_t*>(fl + 2 + 3 * ns + s);
-  P.tile_counter = reinterpret_cast<uint32_t*>(fl + 2 + 4 * ns + 2 * s);
-  P.accum = fl + 2 + 6 * ns + s * kAccumStride;
+  P.tile_counter = reinterpret_cast<uint32_t*>(fl + 2 + 4 * ns + 4 * s);
+  P.accum = fl + 2 + 8 * ns + s * kAccumStride;
   P.chain_first = 1;
   P.finish_here = 0;
   P.out = ctx->exch_dev ? ctx->exch_dev + exch_line(ctx, ctx->exch_rank, s) * kResultStride : ctx->d_out_mapped + s * kResultStride;
@@ -2104,6 +2316,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   if (const char* s = getenv("GAML_B200_NO_GRAPHS")) ctx->use_graphs = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_FAST_CHANGES")) ctx->fast_changes = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_PERMUTE")) ctx->permute_reads = !(s[0] && s[0] != '0');
+  if (const char* s = getenv("GAML_B200_NO_APPEND")) ctx->append_enabled = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -2390,7 +2603,9 @@ int gaml_cache_insert(gaml_ctx* ctx, int set, int mate, const int32_t* key, int3
     km.any = n_records > 0;
     km.max_pos = n_records > 0 ? mx : 0;
   }
-  st->key_ids.emplace(std::move(k), (int)st->keys.size());
+  st->key_hash_log.push_back(hash_nodes(k.data(), (int)k.size()));
+  auto ins = st->key_ids.emplace(std::move(k), (int)st->keys.size());
+  st->key_by_id.push_back(&ins.first->first);
   st->keys.push_back(km);
   st->dirty = true;
   return GAML_OK;
@@ -2566,6 +2781,12 @@ int gaml_cache_load(gaml_ctx* ctx, int set, const char* path) {
     MateStore& st = rs.mate[m];
     st.key_ids = std::move(tmp[m].key_ids);
     st.keys = std::move(tmp[m].keys);
+    st.key_hash_log.assign(st.keys.size(), 0);
+    st.key_by_id.assign(st.keys.size(), nullptr);
+    for (const auto& kv : st.key_ids) {
+      st.key_hash_log[(size_t)kv.second] = hash_nodes(kv.first.data(), (int)kv.first.size());
+      st.key_by_id[(size_t)kv.second] = &kv.first;
+    }
     st.pending = std::move(tmp[m].pending);
     st.pending_pos = std::move(tmp[m].pending_pos);
     st.dirty = true;
@@ -3072,6 +3293,11 @@ int gaml_get_stats(gaml_ctx* ctx, gaml_stats* out) {
     ctx->stats.last_device_ms = ms;
     ctx->stats.last_score_kernel_ms = ms2;
     ctx->timing_pending = false;
+  }
+  ctx->stats.cache_appends = ctx->stats.cache_rebuilds = 0;
+  for (auto& rs : ctx->sets) {
+    ctx->stats.cache_appends += rs->appends;
+    ctx->stats.cache_rebuilds += rs->rebuilds;
   }
   *out = ctx->stats;
   return GAML_OK;

@@ -875,6 +875,7 @@ __device__ __forceinline__ void tier2_tiles(const ScoreParams& P, int* s_tile, A
       case 2: st = tier2_read<2, 2>(P, rows1, rows2, P.cbase[0][2] + 2 * j, P.cbase[1][2] + 2 * j, ll, acc); break;
       default: st = 1; acc = 0.0; break;   // (0,2), (2,0): no pair term
     }
+    if (P.dirty && __ldg(P.dirty + r)) continue;   // gained records since the list was built: the appendix phase's read
     if (st > 0) {
       P.values[r] = acc;
       acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
@@ -1086,6 +1087,7 @@ __device__ __forceinline__ void tier2_packed_tiles(const ScoreParams& P, int* s_
       ll = (uint32_t)dsc.y;
       st = 1;
     }
+    if (P.dirty && __ldg(P.dirty + r)) continue;   // gained records since the list was built: the appendix phase's read
     if (st > 0) {
       P.values[r] = acc;
       double pstar;
@@ -1176,6 +1178,7 @@ __device__ __forceinline__ void rare_tiles(const ScoreParams& P, int* s_tile, Ac
     const uint32_t e1 = __ldg(P.m[0].cptr + k + 1), e2 = __ldg(P.m[1].cptr + k + 1);
     const int r = dsc.x;
     const uint32_t ll = (uint32_t)dsc.y;
+    if (P.dirty && __ldg(P.dirty + r)) continue;   // gained records since the list was built: the appendix phase's read
     TwoLive x, y;
     two_live_scan(P, 0, rows1, (uint32_t)dsc.z, e1 - (uint32_t)dsc.z, x);
     two_live_scan(P, 1, rows2, (uint32_t)dsc.w, e2 - (uint32_t)dsc.w, y);
@@ -1220,6 +1223,8 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
   if (ridx) {
 #pragma unroll
     for (int j = 0; j < kR; j++) qi[j] = (int)__ldg(ridx + qi[j]);
+    if (P.dirty) {   // (a dirty read's packed pair carries the "elsewhere" flag: masked out below like a tier-2 read)
+    }
   }
   uint4 u1[kR], u2[kR];
 #pragma unroll
@@ -1515,6 +1520,27 @@ __device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4 (&u
   }
 }
 
+__device__ __forceinline__ bool paired_read_any(const ScoreParams& P, int r, uint32_t ll, double& acc);
+// Appendix phase of the streaming kernel: the reads that gained records since the static lists were built, scored from
+// their (relocated) rows by the general ordered path. A read under a key that occurs several times is claimed through its
+// stamp by whichever of this phase and the multi pass reaches it first — both score it the same way.
+__device__ __forceinline__ void appendix_tiles(const ScoreParams& P, int* s_tile, Acc& sum, unsigned& floored) {
+  const int n_tiles = (P.n_appx + kBlock - 1) / kBlock;
+  int tile = blockIdx.x, buf = 0;
+  for (; tile < n_tiles; __syncthreads(), tile = s_tile[buf], buf ^= 1) {
+    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 4, 1u);
+    const int k = tile * kBlock + (int)threadIdx.x;
+    if (k >= P.n_appx) continue;
+    const int r = (int)__ldg(P.appx_list + k);
+    if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;   // the multi pass has it
+    const uint32_t ll = __ldg(P.lens + r);
+    double acc = 0.0;
+    if (!paired_read_any(P, r, ll, acc)) continue;   // (scratch exhausted: error flag set)
+    P.values[r] = acc;
+    acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
+  }
+}
+
 // FULL, the streaming kernel: tier 1 (every read with at most one record per mate, straight from the dense
 // first-record arrays) and then tier 2 (the static list of reads with two records on a mate, from the compact copy) in
 // one launch — both are tile loops over static data drawn from counters, so a block simply moves on to tier-2 tiles when
@@ -1608,6 +1634,10 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
     if (!kCov && P.t2pack) tier2_packed_tiles(P, s_tile, sum, floored);
     else tier2_tiles(P, s_tile, sum, floored);
     tl_end(P.timeline, kTlTier2);
+  }
+  if (P.n_appx > 0) {
+    __syncthreads();   // s_tile is shared with the phases before
+    appendix_tiles(P, s_tile, sum, floored);
   }
   if (!P.chain_first) pdl_wait();
   block_accumulate(sum, floored, P.accum);
@@ -2582,6 +2612,45 @@ __global__ void compact_copy_kernel(const uint32_t* list, int n_complex, const u
   for (uint32_t i = 0; i < n; i++) crows[d + i] = rows[b + i];
 }
 
+// ---- cache append: new records of reads that are scored already -------------------------------------------------------
+// A key inserted after the device index was built (the annealing loop aligns a new join's window on demand, graph.cc:
+// 1967-1968) brings a few hundred records. Instead of rebuilding the read-major index over all records, each read that
+// gains records gets its row block RELOCATED to the tail of the row array with the new rows appended (they are the
+// highest arena indices, i.e. last in reference list order), its first-record word is updated, and the read is flagged:
+// in `dirty`, and in its packed / fast pair record ("elsewhere") so that the list-driven phases leave it to the appendix
+// phase. One thread per affected read; the host supplies exact destinations (it keeps every read's record count).
+struct AppendGroup { uint32_t read; uint32_t new_begin; uint32_t n_new; uint32_t dst; };   // dst: new row block's first row
+__global__ void append_rows_kernel(const AppendGroup* groups, int n_groups, const int4* new_rows, int4* rows, int4* first,
+                                   uint32_t* dirty, uint4* pairs, uint4* fast) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const AppendGroup ag = groups[g];
+  int4 f = first[ag.read];
+  const uint32_t cnt_old = f.x < 0 ? 0u : (uint32_t)((f.z >> 16) & 0x3fff);
+  const uint32_t base_old = (uint32_t)f.w;
+  for (uint32_t i = 0; i < cnt_old; i++) rows[ag.dst + i] = rows[base_old + i];
+  for (uint32_t i = 0; i < ag.n_new; i++) rows[ag.dst + cnt_old + i] = new_rows[ag.new_begin + i];
+  if (cnt_old == 0) {
+    const int4 r0 = new_rows[ag.new_begin];   // {key, pos, edor, seq}
+    f.x = r0.x;
+    f.y = r0.y;
+    f.z = r0.z & 0x4000ffff;
+  }
+  f.z = (f.z & 0x4000ffff) | (int)((cnt_old + ag.n_new) << 16);
+  f.w = (int)ag.dst;
+  first[ag.read] = f;
+  dirty[ag.read] = 1u;
+  if (pairs) pairs[ag.read].x |= 0x80000000u;   // PackedPair: "tier 2" = not tier 1's
+  if (fast) fast[ag.read].x |= 0x80000000u;     // FastPair: "elsewhere"
+}
+// per-read record counts of a store after a full build (the host keeps them up to date across appends)
+__global__ void extract_counts_kernel(const int4* first, const uint32_t* rowptr, int n, uint16_t* out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t c = rowptr[r + 1] - rowptr[r];
+  out[r] = (uint16_t)(c < 0xffffu ? c : 0xffffu);
+  (void)first;
+}
 int grid_for(size_t n, int block, int sm_count, int per_sm) {
   size_t need = (n + block - 1) / block;
   size_t cap = (size_t)sm_count * per_sm;
@@ -2589,6 +2658,17 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 }
 
 }  // namespace
+
+void launch_append_rows(const void* groups, int n_groups, const void* new_rows, void* rows, void* first, uint32_t* dirty, void* pairs,
+                        void* fast, cudaStream_t st) {
+  if (n_groups > 0)
+    append_rows_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(static_cast<const AppendGroup*>(groups), n_groups, static_cast<const int4*>(new_rows),
+                                                               static_cast<int4*>(rows), static_cast<int4*>(first), dirty,
+                                                               static_cast<uint4*>(pairs), static_cast<uint4*>(fast));
+}
+void launch_extract_counts(const void* first, const uint32_t* rowptr, int n, uint16_t* out, cudaStream_t st) {
+  if (n > 0) extract_counts_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first), rowptr, n, out);
+}
 
 // ---- launch wrappers ------------------------------------------------------------------------
 // Grids are sized to exactly one resident wave (SM count x blocks that fit per SM for that kernel) so the

@@ -82,6 +82,11 @@ void launch_build_term_table(const double* p1, const double* p2, const double* i
 // entry holds the number of listed reads afterwards.
 cudaError_t build_fast_pairs(const void* pairs, int n, int shift, int ins_n, uint32_t uniform_ll, void* fast, uint32_t* flags, uint32_t* list,
                              void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
+// Cache append (kernels.cu "cache append"): AppendGroup = {read, first new row, new rows, destination row} per affected read.
+struct AppendGroupHost { uint32_t read, new_begin, n_new, dst; };
+void launch_append_rows(const void* groups, int n_groups, const void* new_rows, void* rows, void* first, uint32_t* dirty, void* pairs,
+                        void* fast, cudaStream_t st);
+void launch_extract_counts(const void* first, const uint32_t* rowptr, int n, uint16_t* out, cudaStream_t st);
 // Internal read order of a paired set with fast records (kernels.cu): sort keys from the FastPair array, radix sort,
 // inverse permutation (caller's local read id -> internal index) and the length of the fast region.
 size_t perm_temp_bytes(int n);

@@ -104,6 +104,9 @@ typedef struct {
                                       walk list (walk_set.h) instead of the reference's container */
   int64_t delta_only_evals;        /* paired-set evaluations that updated the running total in O(touched reads): incremental,
                                       total length unchanged, so no O(R) pass (GetTotalProb's sum is kept exactly on the device) */
+  int64_t cache_appends;           /* cache growths applied in O(new records): rows of the affected reads relocated, reads handed to
+                                      the appendix phase */
+  int64_t cache_rebuilds;          /* cache growths that rebuilt a read set's device index (first build, appendix full, no slack) */
 } gaml_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -108,6 +108,13 @@ class ProbCalculator {
     unordered_set<vector<int>> sent;
   };
 
+  struct PbMirror {
+    PacbioReadSet* rs;
+    int set;
+    unordered_set<vector<int>> sent;
+  };
+  static const int kNoNode = -1000000;   // FinalEnd of a walk without any node: it leaves `last_end` alone
+
   void Check(int rc) {
     if (rc < 0) {
       fprintf(stderr, "gaml_b200: %s\n", gaml_last_error(ctx_));
@@ -384,13 +391,6 @@ class ProbCalculator {
     prev_paths_ = paths;
     prev_final_end_.swap(final_end);
   }
-
-  struct PbMirror {
-    PacbioReadSet* rs;
-    int set;
-    unordered_set<vector<int>> sent;
-  };
-  static const int kNoNode = -1000000;   // FinalEnd of a walk without any node: it leaves `last_end` alone
 
   gaml_ctx* ctx_;
   size_t n_sets_ = 0;

@@ -46,8 +46,14 @@ if [ -f "$LIBDIR/libgaml_b200.so" ]; then
   g++ "${GFLAGS[@]}" -c "$REF/gaml.cc" -o gaml_gpu.o &
   g++ "${GFLAGS[@]}" -c "$REF/moves.cc" -o moves_gpu.o &
   wait
+  # gpu_harness: the SAME cache-injection harness as ref_harness, compiled against the drop-in adapter instead of the
+  # reference's prob_calculator.h — every read-set kind (PacBio included) through ProbCalculator::CalcProb over the CUDA
+  # library, and the per-call cost of the drop-in boundary (bench.py's dropin leg).
+  g++ "${GFLAGS[@]}" -c "$HERE/ref_harness.cc" -o gpu_harness.o &
+  wait
   g++ -o gaml_gpu gaml_gpu.o moves_gpu.o graph.o input_output.o graph_from_assembly.o \
       -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200' 2>/dev/null
-  echo "build_ref: built $OUT/gaml_gpu (reference annealing loop + moves over the CUDA ProbCalculator)"
+  g++ -o gpu_harness gpu_harness.o graph.o -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200'
+  echo "build_ref: built $OUT/gaml_gpu (reference annealing loop + moves over the CUDA ProbCalculator) and $OUT/gpu_harness"
 fi
 echo "build_ref: built $OUT/gaml_ref and $OUT/ref_harness"

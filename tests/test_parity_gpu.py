@@ -112,7 +112,53 @@ def test_cache_grows_during_annealing(oracle):
         prob, zeros, tl = pc.calc_prob(walks)
         assert zeros == ref[e].zeros and tl == ref[e].total_len
         assert np.array_equal(pc.read_values(0), ref[e].per_read[0]), e
+    # a full re-score on top of the grown cache sees the appended records too (fresh state: equal up to the incremental
+    # state's own rounding drift)
+    v_inc = pc.read_values(0)
+    pc.reset_state()
+    full = pc.calc_prob(wl.evals[-1])
+    assert pc.stats().last_was_full == 1 and full[1:] == (zeros, tl) and abs(full[0] - prob) <= REL_TOTAL * abs(prob)
+    v_full = pc.read_values(0)
+    nz = v_full != 0
+    assert np.array_equal(nz, v_inc != 0) or np.all(np.abs(v_inc[~nz]) < 1e-25)
+    assert np.all(np.abs(v_inc[nz] - v_full[nz]) <= 1e-9 * np.abs(v_full[nz]))
+    st = pc.stats()
+    assert st.cache_appends >= 5 and st.cache_rebuilds <= 3, (st.cache_appends, st.cache_rebuilds)   # growth is applied in place
     pc.close()
+
+
+def test_cache_growth_by_append_equals_rebuilding(monkeypatch):
+    """The same growing cache with appends switched off (every growth rebuilds the device index): identical partial sums
+    and per-read values at every step, for incremental and for full evaluations."""
+    wl = synth.paired_workload(46, 10000, 200_000, n_evals=40, seed=13)
+    spec = wl.sets[0]
+    pcs = []
+    for no_append in (False, True):
+        if no_append:
+            monkeypatch.setenv("GAML_B200_NO_APPEND", "1")
+        pc = api.ProbCalculator(wl.node_len, wl.normalize_map)
+        pc.add_readset(spec)
+        pcs.append(pc)
+    monkeypatch.delenv("GAML_B200_NO_APPEND")
+    inserted = [set(), set()]
+    for e, walks in enumerate(wl.evals):
+        need = synth.short_keys_for_walks(walks, wl.node_len, with_single_node=True)
+        for m in range(2):
+            for k in need:
+                if k not in inserted[m] and k in spec.caches[m]:
+                    for pc in pcs:
+                        pc.cache_insert(0, m, k, spec.caches[m][k])
+                    inserted[m].add(k)
+        if e % 7 == 6:
+            for pc in pcs:
+                pc.reset_state()
+        a, b = [pc.calc_prob_partial(walks) for pc in pcs]
+        assert a[1] == b[1] and np.array_equal(a[0], b[0]), (e, a, b)
+        if e % 5 == 0:
+            assert np.array_equal(pcs[0].read_values(0), pcs[1].read_values(0)), e
+    assert pcs[0].stats().cache_appends >= 10 and pcs[1].stats().cache_appends == 0
+    for pc in pcs:
+        pc.close()
 
 
 def test_two_shards_on_one_gpu_combine_to_the_unsharded_result(oracle):
@@ -420,6 +466,25 @@ def test_reference_annealing_driver_over_cuda_is_identical(tmp_path):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("IDENTICAL TRAJECTORY") == 2, out.stdout
+
+
+@pytest.mark.parametrize("name", ["synth_mixed", "hand_pacbio", "synth_pacbio_penalty", "synth_paired", "synth_single"])
+def test_dropin_prob_calculator_scores_every_read_set_kind(name, tmp_path):
+    """oracle/_ref/gpu_harness = the reference's cache-injection harness compiled against integration/prob_calculator.h
+    (the drop-in ProbCalculator over the CUDA library) instead of the reference's header: single, paired AND PacBio sets
+    through ProbCalculator::CalcProb must reproduce the reference's own results (the committed goldens)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "gpu_harness")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gpu_harness not prebuilt")
+    res = str(tmp_path / "dropin.res")
+    out = subprocess.run([exe, os.path.join(GOLDEN, name + ".wl"), res, "0"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = workload.read_results(res)
+    ref = workload.read_results(os.path.join(GOLDEN, name + ".ref.res"))
+    assert len(got) == len(ref)
+    for e, (g, r) in enumerate(zip(got, ref)):
+        assert g.total_len == r.total_len and g.zeros == r.zeros, (e, g.zeros, r.zeros)
+        assert abs(g.score - r.score) <= REL_TOTAL * abs(r.score), (e, g.score, r.score)
 
 
 # ---- batched candidate evaluation (BASELINE config 5) ---------------------------------------------
