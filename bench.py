@@ -11,13 +11,13 @@ prob_calculator.h:63-109).
          sharded by read id: N = 8 is the whole of config 4, N = 2 / 4 the same genome at a quarter / half of the coverage
          (weak scaling: the per-GPU shard is fixed).
 Every rank scores its shard; the ranks' 64-byte result lines are exchanged by the evaluation's own kernels over NVLink
-peer memory (--exchange peer, default), a host shared-memory segment (host) or one ncclAllReduce (nccl), and every rank
-combines them exactly.
+peer memory (--exchange peer), a host shared-memory segment the kernels write into (host, the default: the fastest end to
+end in the A/B on the 8-GPU box, profiles/r02_exchange_ab.md) or one ncclAllReduce (nccl), and every rank combines them exactly.
 
 One JSON line on stdout (rank 0). `value` is device time with all inputs resident in HBM — CUDA events around each
-evaluation's kernel chain on the library's stream, which for N > 1 ends with the kernel that has received every rank's
-line, i.e. the exchange is INSIDE the timed region; L2 flushed between steps, all ranks released together after the
-flush. `e2e` is the same metric through gaml_calc_prob_partial / gaml_calc_prob_gathered with host buffers in and out,
+evaluation's kernel chain on the library's stream (with --exchange peer the chain ends with the kernel that has received
+every rank's line); `value_incl_exchange` is the wall clock from the chain's submission until the rank holds every rank's
+result line; L2 flushed between steps, all ranks released together after the flush. `e2e` is the same metric through gaml_calc_prob_partial / gaml_calc_prob_gathered with host buffers in and out,
 wall clock. `roofline` is the dominant kernel of this rank against the measured HBM copy peak. The incremental (delta)
 evaluations of the annealing loop are reported beside it as `sa_iters_per_s`.
 """
@@ -317,8 +317,9 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4shard"],
                     help="auto (default): config 2 on one GPU, one eighth of config 4 per GPU on several")
     ap.add_argument("--batch", type=int, default=1024, help="candidate moves per gaml_calc_prob_batch launch (0 = skip)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "host", "nccl"],
-                    help="how the ranks' result lines meet (N > 1): NVLink peer memory, host shared memory, ncclAllReduce")
+    ap.add_argument("--exchange", default="host", choices=["peer", "host", "nccl"],
+                    help="how the ranks' result lines meet (N > 1): host shared memory written by the kernels (default: the fastest end to "
+                         "end on the 8-GPU box, profiles/r02_exchange_ab.md), NVLink peer memory, ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gaml_b200" else args.warmup
 
@@ -416,10 +417,12 @@ def main():
         pc.prepare(walks0)
         flush_l2()
         rendezvous()
+        t0 = time.perf_counter()
         pc.launch()
         g, tl = finish_all()
+        wall = time.perf_counter() - t0
         st = pc.stats()
-        return st.last_device_ms, st.last_score_kernel_ms, g, tl
+        return st.last_device_ms, st.last_score_kernel_ms, g, tl, wall
 
     def eval_all_ranks(fw):
         """One evaluation through the C ABI, all ranks' partials combined: (prob, zeros, total_len)."""
@@ -449,10 +452,11 @@ def main():
     gc.disable()              # no collector pauses inside the timed loops (every rank waits for the slowest one)
     if rank == 0:             # one nvidia-smi poller per job, not per rank
         sampler.start()
-    dev_ms = 0.0
+    dev_ms, wall_ms = 0.0, 0.0
     for _ in range(args.steps):
-        d, _k, g_full, tl = full_step_device()
-        dev_ms += max_over_ranks(d) if world > 1 else d   # per step: the slowest rank's chain (they end together anyway)
+        d, _k, g_full, tl, wall = full_step_device()
+        dev_ms += max_over_ranks(d) if world > 1 else d   # per step: the slowest rank's chain
+        wall_ms += 1e3 * max_over_ranks(wall)             # launch -> every rank's result line received, slowest rank
     barrier()
     st = pc.stats()
     launches = st.kernel_launches - launches0
@@ -555,6 +559,9 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "alignments_per_step": int(a_total),
+        "value_incl_exchange": {"value": a_total * args.steps / (wall_ms * 1e-3), "unit": "alignments/s", "ms_per_step": wall_ms / args.steps,
+                                "note": "inputs resident as for `value`; wall clock from the kernel chain's submission until THIS rank holds every rank's "
+                                        "result line (N > 1) / its own (N = 1), max over ranks: device time + launch + the exchange"},
         "measurement": {"l2": "flushed between steps (256 MiB write, then read back so L2 holds clean foreign lines)",
                         "timing": "CUDA events around each evaluation's kernel chain (nodes of its CUDA graph on the library stream); N > 1: all ranks "
                                   "released together after their flush, the chain ends with the exchange's gather kernel, per step the max over ranks",

@@ -290,12 +290,24 @@ struct gaml_ctx {
   DevBuf d_tables;                // SlotA* per store, then SlotB* per store
   bool tables_dirty = true;
   DevBuf d_blob;                  // per-evaluation staging (updates, occurrences, touch ranges, set_begin)
+  // A FULL evaluation's staging blob is a function of the walk list and the cache alone (the epoch is a kernel parameter).
+  // It is kept on the device in its own buffer: a full re-score of the walk list that was evaluated last — a fresh
+  // ScoringState over unchanged walks, gaml_reset_state — needs no flattening and no upload at all.
+  DevBuf d_full_blob;
+  char* blob_dev = nullptr;       // the blob of the pending evaluation (d_blob or d_full_blob)
+  bool full_blob_valid = false;
+  uint64_t list_gen = 0, cache_gen = 0, full_list_gen = 0, full_cache_gen = 0;
+  std::vector<SetPlan> full_plan;
+  int full_n_updates = 0;
+  size_t full_upd_off = 0, full_blob_bytes = 0;
+  int64_t full_blob_reuses = 0;
   void* h_blob = nullptr;         // pinned
   size_t h_blob_cap = 0;
   DevBuf d_flags, d_scratch, d_csr_temp, d_logtab;
   DevBuf d_batch_blob, d_batch_acc, d_batch_out;   // gaml_calc_prob_batch
   DevBuf d_aln[8];                                  // gaml_pacbio_alignment_logprob
   std::vector<double> h_batch_out;
+  std::vector<char> h_append;                       // staging of a cache append's rows and groups
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
   std::vector<double> h_res;      // validated copy of h_out taken by finish()
@@ -753,18 +765,21 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
         for (int4& v : st.pending) v.x = (int)rs.h_inv[(size_t)v.x];
       CU(st.arena.reserve(total * 16, st.arena_n * 16, false, st_));
       CU(cudaMemcpyAsync(st.arena.as<char>() + st.arena_n * 16, st.pending.data(), st.pending.size() * 16, cudaMemcpyHostToDevice, st_));
+      // (copies from pageable host memory return once the source has been staged: the vectors may be reused right away)
       const size_t rows_bytes = plan[m].new_rows.size() * 16, grp_bytes = plan[m].groups.size() * sizeof(AppendGroupHost);
+      std::vector<char>& hb = ctx->h_append;   // one staging copy per mate: [new rows | groups]
+      hb.resize(rows_bytes + grp_bytes);
+      memcpy(hb.data(), plan[m].new_rows.data(), rows_bytes);
+      memcpy(hb.data() + rows_bytes, plan[m].groups.data(), grp_bytes);
       CU(rs.d_append_blob.reserve(2 * (rows_bytes + grp_bytes + 64), 0, false, st_));
       char* blob = rs.d_append_blob.as<char>() + (size_t)m * (rs.d_append_blob.cap / 2);
-      CU(cudaMemcpyAsync(blob, plan[m].new_rows.data(), rows_bytes, cudaMemcpyHostToDevice, st_));
-      CU(cudaMemcpyAsync(blob + rows_bytes, plan[m].groups.data(), grp_bytes, cudaMemcpyHostToDevice, st_));
+      CU(cudaMemcpyAsync(blob, hb.data(), hb.size(), cudaMemcpyHostToDevice, st_));
       launch_append_rows(blob + rows_bytes, (int)plan[m].groups.size(), blob, st.rows.p, st.first.p, rs.d_dirty.as<uint32_t>(), rs.d_pairs.p,
                          rs.fast_ok ? rs.d_fast.p : nullptr, st_);
       launches++;
       for (const AppendGroupHost& g : plan[m].groups) st.h_count[g.read] = (uint16_t)(st.h_count[g.read] + g.n_new);
       st.rows_tail = plan[m].tail_after;
       st.arena_n = total;
-      CU(cudaStreamSynchronize(st_));   // pending / plan vectors are pageable host memory about to be released
       st.pending.clear();
     }
     const size_t old_slots = st.slots_a.cap;
@@ -776,7 +791,6 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
   if (!dirty_now.empty()) {
     CU(rs.d_appx.reserve(((size_t)rs.n_appx + dirty_now.size()) * 4, (size_t)rs.n_appx * 4, false, st_));
     CU(cudaMemcpyAsync(rs.d_appx.as<uint32_t>() + rs.n_appx, dirty_now.data(), dirty_now.size() * 4, cudaMemcpyHostToDevice, st_));
-    CU(cudaStreamSynchronize(st_));
     rs.n_appx += (int)dirty_now.size();
   }
   // ---- key maps between the mates' stores and the combined slot table: the new keys only ----
@@ -809,7 +823,6 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
     if (lo2 < rs.h_p21.size())
       CU(cudaMemcpyAsync(rs.d_partner21.as<int32_t>() + lo2, rs.h_p21.data() + lo2, (rs.h_p21.size() - lo2) * 4, cudaMemcpyHostToDevice, st_));
     CU(rs.d_comb.reserve(rs.h_p12.size() * 2 * sizeof(SlotA), 0, true, st_));   // per-evaluation contents: nothing to keep
-    CU(cudaStreamSynchronize(st_));
     if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21) ctx->tables_dirty = true;
     s1.built_keys = k1;
     s2.built_keys = k2;
@@ -821,16 +834,19 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
 
 // Upload staged cache inserts and rebuild the read-major CSR of every dirty store.
 int commit(gaml_ctx* ctx) {
+  bool rebuilt = false;
   for (auto& rsp : ctx->sets) {
     ReadSetState& rs = *rsp;
     bool any_dirty = false;
     for (int m = 0; m < rs.n_mates; m++) any_dirty |= rs.mate[m].dirty;
     if (any_dirty) {
+      ctx->cache_gen++;
       const int ar = try_append(ctx, rs);
       if (ar < 0) return ar;
       if (ar == 1) continue;
       for (int m = 0; m < rs.n_mates; m++) rs.mate[m].dirty = true;   // full rebuild of the set: both mates' lists and the shared ones
       rs.rebuilds++;
+      rebuilt = true;
     }
    for (int pass = 0; pass < 2; pass++) {   // (a second pass only right after the internal read order has been fixed)
     for (int m = 0; m < rs.n_mates; m++) {
@@ -1072,7 +1088,7 @@ int commit(gaml_ctx* ctx) {
       CU(cudaMemcpyAsync(ctx->d_tables.p, tabs.data(), tabs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
     ctx->tables_dirty = false;
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (rebuilt) CU(cudaStreamSynchronize(ctx->stream));   // (appends and table uploads are ordered on the stream: nothing to wait for)
   return GAML_OK;
 }
 
@@ -1115,6 +1131,39 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->cur_total_len = total_len;
   int rc = commit(ctx);
   if (rc != GAML_OK) return rc;
+  const bool list_same = old_set && diff.valid && diff.old_changed.empty() && diff.new_changed.empty() && ws.n == old_set->n;
+  if (!list_same) ctx->list_gen++;
+  bool all_full = true;
+  for (auto& rsp : ctx->sets) all_full &= !(rsp->cfg.kind == GAML_KIND_PAIRED && rsp->has_state);
+  if (all_full && ctx->full_blob_valid && ctx->full_list_gen == ctx->list_gen && ctx->full_cache_gen == ctx->cache_gen &&
+      ctx->full_plan.size() == ctx->sets.size()) {
+    // the same walks, the same cache, every paired set from scratch: the blob of the last such evaluation is still on the device
+    ctx->plan = ctx->full_plan;
+    ctx->n_updates = ctx->full_n_updates;
+    ctx->upd_off = ctx->full_upd_off;
+    ctx->blob_bytes = ctx->full_blob_bytes;
+    ctx->blob_dev = ctx->d_full_blob.as<char>();
+    for (size_t s = 0; s < ctx->sets.size(); s++) {
+      ReadSetState& rt = *ctx->sets[s];
+      if (rt.cfg.kind == GAML_KIND_PACBIO) continue;
+      const int two_len = two_len_of(ctx->plan[s].total_len);
+      if (!rt.pstar_valid || rt.pstar_two_len != two_len) {
+        rt.h_pstar.assign(rt.h_thr.size(), 0.0);
+        for (int li : rt.len_classes) rt.h_pstar[li] = floor_pstar(rt.h_thr[li], (double)two_len);
+        rt.pstar_two_len = two_len;
+        rt.pstar_valid = true;
+      }
+    }
+    CU(ctx->d_flags.reserve(flags_words(ctx->sets.size()) * sizeof(unsigned long long), 0, true, ctx->stream));
+    for (auto& rsp : ctx->sets) CU(rsp->d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));
+    CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
+    ctx->stats.last_h2d_bytes = 0;
+    ctx->full_blob_reuses++;
+    ctx->epoch++;
+    ctx->prepared = true;
+    ctx->launched = false;
+    return GAML_OK;
+  }
   // host-side generation of the per-key stamp tables (group_occurrences). The device epoch (slot liveness, result lines)
   // advances only at the end, once this function can no longer fail: the ranks of a multi-GPU job stay in step even when
   // one of them rejects a walk set.
@@ -1354,7 +1403,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   }
   ctx->n_updates = (int)updates.size();
 
-  CU(ctx->d_blob.reserve(std::max<size_t>(off, 256), 0, false, ctx->stream));
+  DevBuf& dst_blob = all_full ? ctx->d_full_blob : ctx->d_blob;
+  CU(dst_blob.reserve(std::max<size_t>(off, (size_t)1 << 18), 0, false, ctx->stream));   // (generous: growing a device buffer frees the old
+                                                                                         //  one, which waits for the whole device)
+  ctx->blob_dev = dst_blob.as<char>();
   CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, ctx->stream));
   CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
   if (ctx->h_out_cap < (n_sets + 1) * kResultStride) {
@@ -1370,8 +1422,17 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     ctx->h_out_cap = cap;
   }
   for (auto& rsp : ctx->sets) CU(rsp->d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));   // grows after a capacity error
-  CU(cudaMemcpyAsync(ctx->d_blob.p, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->blob_dev, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.last_h2d_bytes = (int64_t)off;
+  ctx->full_blob_valid = all_full;
+  if (all_full) {
+    ctx->full_plan = ctx->plan;
+    ctx->full_n_updates = ctx->n_updates;
+    ctx->full_upd_off = ctx->upd_off;
+    ctx->full_blob_bytes = ctx->blob_bytes;
+    ctx->full_list_gen = ctx->list_gen;
+    ctx->full_cache_gen = ctx->cache_gen;
+  }
   ctx->epoch++;
   ctx->prepared = true;
   ctx->launched = false;
@@ -1392,7 +1453,7 @@ bool nccl_lines(const gaml_ctx* ctx) { return ctx->nccl_on && !ctx->peer_on && !
 ScoreParams make_params(gaml_ctx* ctx, size_t s) {
   ReadSetState& rs = *ctx->sets[s];
   const SetPlan& sp = ctx->plan[s];
-  char* blob = ctx->d_blob.as<char>();
+  char* blob = ctx->blob_dev;
   ScoreParams P{};
   for (int m = 0; m < rs.n_mates; m++) {
     MateStore& st = rs.mate[m];
@@ -1631,7 +1692,7 @@ int launch(gaml_ctx* ctx) {
     CU(ctx->d_timeline.reserve(kTimelineWords * 8, 0, true, st));
     CU(cudaMemsetAsync(ctx->d_timeline.p, 0, kTimelineWords * 8, st));
   }
-  char* blob = ctx->d_blob.as<char>();
+  char* blob = ctx->blob_dev;
   int launches = 0;
   bool any_penalty = false;
   for (auto& rs : ctx->sets) any_penalty |= rs->penalty || rs->pb_penalty;
@@ -2387,6 +2448,8 @@ int gaml_set_graph(gaml_ctx* ctx, int32_t n_nodes, const int32_t* node_len, cons
     if (node_len[i] < 0) return fail(ctx, GAML_ERR_ARG, "negative node length");
   }
   ctx->have_prev = false;   // lengths and lookups of remembered walks refer to the old graph
+  ctx->full_blob_valid = false;
+  ctx->cache_gen++;
   for (auto& rs : ctx->sets) {
     rs->flat_cache.clear();
     rs->has_state = false;

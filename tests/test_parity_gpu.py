@@ -223,8 +223,11 @@ def test_peer_memory_exchange_between_two_contexts_matches_the_unsharded_result(
         pc.peer_exchange_open(local_ptrs=ptrs)
     for e, walks in enumerate(wl.evals):
         ref = whole.calc_prob(walks)
+        # (two "ranks" on ONE GPU: both are prepared before either is launched — a launched rank's last kernel waits for the
+        #  other's line, and anything in a prepare that waits for the whole device, e.g. growing a buffer, would wait for it)
         for pc in ranks:
             pc.prepare(walks)
+        for pc in ranks:
             pc.launch()
         outs = []
         for pc in ranks:

@@ -1,34 +1,22 @@
-import os, sys, subprocess, tempfile
+import os, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
-from gaml_b200 import api, synth, workload
-wl = synth.paired_workload(12, 2500, 4000, n_evals=30, seed=31)
-with tempfile.TemporaryDirectory() as tmp:
-    wp, rp = os.path.join(tmp, "a.wl"), os.path.join(tmp, "a.res")
-    workload.write_workload(wp, wl)
-    subprocess.run([os.path.abspath("oracle/gaml_oracle"), wp, rp, "1"], check=True, cwd=tmp, stderr=subprocess.DEVNULL)
-    ref = workload.read_results(rp)
-spec = wl.sets[0]
-for mode in ("append", "noappend", "append_noperm"):
-    os.environ.pop("GAML_B200_NO_APPEND", None); os.environ.pop("GAML_B200_NO_PERMUTE", None)
-    if mode == "noappend": os.environ["GAML_B200_NO_APPEND"] = "1"
-    if mode == "append_noperm": os.environ["GAML_B200_NO_PERMUTE"] = "1"
-    pc = api.ProbCalculator(wl.node_len, wl.normalize_map)
-    sid = pc.add_readset(spec)
-    inserted = [set(), set()]
-    for e, walks in enumerate(wl.evals):
-        need = synth.short_keys_for_walks(walks, wl.node_len, with_single_node=True)
-        nk = 0
-        for m in range(2):
-            for k in need:
-                if k not in inserted[m] and k in spec.caches[m]:
-                    pc.cache_insert(sid, m, k, spec.caches[m][k]); inserted[m].add(k); nk += 1
-        prob, zeros, tl = pc.calc_prob(walks)
-        v = pc.read_values(0)
-        bad = np.nonzero(v != ref[e].per_read[0])[0]
-        st = pc.stats()
-        print(mode, e, 'newkeys', nk, 'full' if st.last_was_full else 'delta', 'bad', len(bad), bad[:5], 'zeros', zeros == ref[e].zeros, 'app', st.cache_appends, 'reb', st.cache_rebuilds)
-        if len(bad):
-            r = bad[0]; print('   read', r, v[r], ref[e].per_read[0][r])
-            break
-    pc.close()
+from gaml_b200 import api, synth
+wl = synth.paired_workload(46, 10000, 200_000, n_evals=6, seed=11)
+whole = api.ProbCalculator.from_workload(wl)
+ranks = [api.ProbCalculator.from_workload(wl, shard_of=(rk, 2)) for rk in range(2)]
+ptrs = [pc.peer_exchange_create(rk, 2)[1] for rk, pc in enumerate(ranks)]
+for pc in ranks:
+    pc.peer_exchange_open(local_ptrs=ptrs)
+for e, walks in enumerate(wl.evals):
+    ref = whole.calc_prob(walks)
+    for rk, pc in enumerate(ranks):
+        t0 = time.time(); pc.prepare(walks); t1 = time.time(); pc.launch(); t2 = time.time()
+        print(e, 'rank', rk, 'prepare %.3f ms launch %.3f ms' % ((t1-t0)*1e3, (t2-t1)*1e3), flush=True)
+    for rk, pc in enumerate(ranks):
+        t0 = time.time()
+        try:
+            g, tl = pc.finish_gathered()
+            print(e, 'rank', rk, 'finish %.3f ms' % ((time.time()-t0)*1e3), pc.combine(g, 2, tl) == ref, flush=True)
+        except Exception as ex:
+            print(e, 'rank', rk, 'finish FAILED after %.3f ms' % ((time.time()-t0)*1e3), ex, flush=True)
