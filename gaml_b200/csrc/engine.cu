@@ -822,7 +822,7 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
       CU(cudaMemcpyAsync(rs.d_partner12.as<int32_t>() + lo1, rs.h_p12.data() + lo1, (rs.h_p12.size() - lo1) * 4, cudaMemcpyHostToDevice, st_));
     if (lo2 < rs.h_p21.size())
       CU(cudaMemcpyAsync(rs.d_partner21.as<int32_t>() + lo2, rs.h_p21.data() + lo2, (rs.h_p21.size() - lo2) * 4, cudaMemcpyHostToDevice, st_));
-    CU(rs.d_comb.reserve(rs.h_p12.size() * 2 * sizeof(SlotA), 0, true, st_));   // per-evaluation contents: nothing to keep
+    CU(rs.d_comb.reserve(rs.h_p12.size() * 4 * sizeof(SlotA), 0, true, st_));   // per-evaluation contents: nothing to keep
     if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21) ctx->tables_dirty = true;
     s1.built_keys = k1;
     s2.built_keys = k2;
@@ -952,7 +952,7 @@ int commit(gaml_ctx* ctx) {
           CU(rs.d_partner21.reserve(p21.size() * 4, 0, false, ctx->stream));
           CU(cudaMemcpyAsync(rs.d_partner12.p, p12.data(), p12.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
           CU(cudaMemcpyAsync(rs.d_partner21.p, p21.data(), p21.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-          CU(rs.d_comb.reserve(p12.size() * 2 * sizeof(SlotA), 0, true, ctx->stream));
+          CU(rs.d_comb.reserve(p12.size() * 4 * sizeof(SlotA), 0, true, ctx->stream));
           CU(cudaStreamSynchronize(ctx->stream));
           if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21 || !rs.comb_ok) ctx->tables_dirty = true;
           rs.comb_ok = true;
@@ -1734,8 +1734,7 @@ int launch(gaml_ctx* ctx) {
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
       if (sp.full) {
         const uint32_t n_multi = (uint32_t)sp.multi_records;
-        launch_paired_full(P, sp.grid, sp.cgrid, n_multi, og, ctx->sm_count, st, chained, profile, rs.ev0, rs.ev1);
-        launches += 2 + (n_multi > 0);
+        launches += launch_paired_full(P, sp.grid, sp.cgrid, n_multi, og, ctx->sm_count, st, chained, profile, rs.ev0, rs.ev1);
         any_full = true;
         // 16 B per live record + packed lengths (4) + probs write (8) per pair (no probs read: fused)
         bytes += 16 * sp.records + 12 * (int64_t)rs.n_local;
@@ -3113,7 +3112,21 @@ int gaml_peer_exchange_open(gaml_ctx* ctx, const void* ipc_handles, void* const*
     if (p == ctx->peer_rank) {
       ctx->peer_ptrs[p] = ctx->d_peer_lines.p;
     } else if (local_buffers && local_buffers[p]) {
-      ctx->peer_ptrs[p] = local_buffers[p];   // another context of this process (IPC handles cannot be opened by their creator)
+      // another context of this process, on ANOTHER GPU (IPC handles cannot be opened by their creator; a kernel that
+      // waits for a line must not share its GPU with the kernel that writes it)
+      cudaPointerAttributes attr{};
+      CU(cudaPointerGetAttributes(&attr, local_buffers[p]));
+      if (attr.device == ctx->device) {
+        peer_exchange_release(ctx);
+        return fail(ctx, GAML_ERR_ARG, "peer exchange: two ranks on one GPU (their kernels would wait on one another)");
+      }
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(attr.device, 0);
+      if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (pe != cudaSuccess) {
+        peer_exchange_release(ctx);
+        return fail(ctx, GAML_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+      }
+      ctx->peer_ptrs[p] = local_buffers[p];
     } else if (ipc_handles) {
       cudaIpcMemHandle_t h;
       memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)p * GAML_IPC_HANDLE_BYTES, sizeof(h));

@@ -1287,7 +1287,7 @@ __device__ __forceinline__ void tier1_body(const ScoreParams& P, const uint4* __
 #pragma unroll
     for (int j = 0; j < kR; j++) {
       uint4 a, b;
-      ldg256(comb + 2 * key1[j], a, b);
+      ldg256(comb + 4 * key1[j], a, b);
       o1[j] = make_int4((int)a.x, (int)a.y, (int)a.z, (int)a.w);
       o2[j] = make_int4((int)b.x, (int)b.y, (int)b.z, (int)b.w);
     }
@@ -1483,7 +1483,7 @@ __device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4 (&u
   int4 te[kR];
 #pragma unroll
   for (int j = 0; j < kR; j++) {
-    ldg256(comb + 2 * (u[j].x & 0x3fffffffu), a[j], b[j]);   // {epoch | multi << 31, walk, cur_pos, skip_below} of both mates
+    ldg256(comb + 4 * (u[j].x & 0x3fffffffu), a[j], b[j]);   // {epoch | multi << 31, walk, cur_pos, skip_below} of both mates
     te[j] = __ldg(tq + u[j].w);
   }
   const double pstar = P.uni_pstar;
@@ -1520,34 +1520,16 @@ __device__ __forceinline__ void tier1_fast(const ScoreParams& P, const uint4 (&u
   }
 }
 
-__device__ __forceinline__ bool paired_read_any(const ScoreParams& P, int r, uint32_t ll, double& acc);
-// Appendix phase of the streaming kernel: the reads that gained records since the static lists were built, scored from
-// their (relocated) rows by the general ordered path. A read under a key that occurs several times is claimed through its
-// stamp by whichever of this phase and the multi pass reaches it first — both score it the same way.
-__device__ __forceinline__ void appendix_tiles(const ScoreParams& P, int* s_tile, Acc& sum, unsigned& floored) {
-  const int n_tiles = (P.n_appx + kBlock - 1) / kBlock;
-  int tile = blockIdx.x, buf = 0;
-  for (; tile < n_tiles; __syncthreads(), tile = s_tile[buf], buf ^= 1) {
-    if (threadIdx.x == 0) s_tile[buf] = (int)gridDim.x + (int)atomicAdd(P.tile_counter + 4, 1u);
-    const int k = tile * kBlock + (int)threadIdx.x;
-    if (k >= P.n_appx) continue;
-    const int r = (int)__ldg(P.appx_list + k);
-    if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;   // the multi pass has it
-    const uint32_t ll = __ldg(P.lens + r);
-    double acc = 0.0;
-    if (!paired_read_any(P, r, ll, acc)) continue;   // (scratch exhausted: error flag set)
-    P.values[r] = acc;
-    acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
-  }
-}
-
 // FULL, the streaming kernel: tier 1 (every read with at most one record per mate, straight from the dense
 // first-record arrays) and then tier 2 (the static list of reads with two records on a mate, from the compact copy) in
 // one launch — both are tile loops over static data drawn from counters, so a block simply moves on to tier-2 tiles when
 // the tier-1 tiles run out, without a kernel boundary (ramp, tail, launch) in between.
-template <bool kCov, bool kPacked, bool kTab, int kBPS, int kR>
+// kPhase: 0 = every phase in one launch; sets with fast records run TWO launches back to back in the chain — 1 = tier 1
+// over the fast records alone (a light body: twice the resident warps of the fused kernel, and tier 1 is bound by memory
+// latency), 2 = everything else (rare shapes, cross list, tier 2, appendix).
+template <bool kCov, bool kPacked, bool kTab, int kBPS, int kR, int kPhase = 0>
 __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const ScoreParams P) {
-  tl_begin(P.timeline, kTlTier1);
+  tl_begin(P.timeline, kPhase == 2 ? kTlTier2 : kTlTier1);
   const int4* sa1 = reinterpret_cast<const int4*>(P.m[0].slots_a);
   const int4* sa2 = reinterpret_cast<const int4*>(P.m[1].slots_a);
   const double2* log_tab = static_cast<const double2*>(P.log_tab);
@@ -1576,18 +1558,20 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
   };
   static_assert(2 * kRecLines <= kBlock, "one prefetch per thread");
   int tile = blockIdx.x, next = (int)blockIdx.x + (int)gridDim.x, buf = 0;
-  prefetch_tile(tile);   // static data: may be requested before the wait below
+  if (kPhase != 2) prefetch_tile(tile);   // static data: may be requested before the wait below
   // First kernel after apply_slots (no multi pass before it): wait here, release after. Otherwise the multi pass did
   // that, every block of this kernel starts after apply_slots completed, and the wait moves to the end.
   if (P.chain_first) pdl_wait();
   pdl_release();   // AFTER the wait: the next streaming kernel starts without a wait of its own, see tier 2
   // The rare-shape tiles go first: their long dependent chains overlap with everything after them instead of forming
   // the kernel's tail.
-  if (P.n_complex > P.n_main) {
+  if (kPhase != 1 && P.n_complex > P.n_main) {
     rare_tiles(P, s_tile, sum, floored);
     __syncthreads();
   }
-  if (kTab) {
+  if (kPhase == 2) {
+    // (tier 1 runs in the launch before this one)
+  } else if (kTab) {
     // fast records: the NEXT tile's records are requested into registers before this tile is worked on (a tile is two
     // memory levels: its records, then the gathers they point at — the first level is always one tile ahead)
     uint4 u_cur[kR], u_nxt[kR];
@@ -1614,7 +1598,7 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
       buf ^= 1;
     }
   }
-  if (kTab && P.n_cross > 0) {
+  if (kPhase != 1 && kTab && P.n_cross > 0) {
     // the cross list: tier-1 reads whose mates lie under different keys (the insert distance depends on the walk) or whose
     // edit distance is beyond the term table — the general body over the packed pairs, read ids from the list
     const uint4* __restrict__ pairs = static_cast<const uint4*>(P.pairs);
@@ -1627,18 +1611,14 @@ __global__ void __launch_bounds__(kBlock, kBPS) paired_stream_kernel(const Score
       tier1_body<false, true, kTab, kXR>(P, pairs, src2, lane, sa1, sa2, log_tab, xt * kXTile + wib * (32 * kXR), P.n_cross, sum, floored, P.xlist);
     }
   }
-  tl_end(P.timeline, kTlTier1);
-  if (P.n_main > 0) {
+  if (kPhase != 2) tl_end(P.timeline, kTlTier1);
+  if (kPhase != 1 && P.n_main > 0) {
     __syncthreads();   // s_tile is shared with the rare-shape phase
-    tl_begin(P.timeline, kTlTier2);
+    if (kPhase == 0) tl_begin(P.timeline, kTlTier2);
     if (!kCov && P.t2pack) tier2_packed_tiles(P, s_tile, sum, floored);
     else tier2_tiles(P, s_tile, sum, floored);
-    tl_end(P.timeline, kTlTier2);
   }
-  if (P.n_appx > 0) {
-    __syncthreads();   // s_tile is shared with the phases before
-    appendix_tiles(P, s_tile, sum, floored);
-  }
+  if (kPhase != 1) tl_end(P.timeline, kTlTier2);
   if (!P.chain_first) pdl_wait();
   block_accumulate(sum, floored, P.accum);
   if (P.finish_here) finish_set_if_complete(P);
@@ -1674,7 +1654,7 @@ __global__ void __launch_bounds__(kOvfBlock) paired_multi_kernel(const ScorePara
   pdl_release();
   Acc sum = acc_zero();
   unsigned floored = 0;
-  const uint32_t total = __ldg(P.mtouch_prefix + P.n_mtouch);
+  const uint32_t total = P.n_mtouch > 0 ? __ldg(P.mtouch_prefix + P.n_mtouch) : 0u;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
     int lo = 0, hi = P.n_mtouch;   // largest t with prefix[t] <= q
     while (hi - lo > 1) {
@@ -1691,10 +1671,56 @@ __global__ void __launch_bounds__(kOvfBlock) paired_multi_kernel(const ScorePara
     P.values[r] = acc;
     acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
   }
+  // the appendix: reads that gained records since the static lists were built (cache appends), scored from their
+  // (relocated) rows by the same general path; one under a repeated key may have been claimed by the loop above
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n_appx; k += gridDim.x * blockDim.x) {
+    const int r = (int)__ldg(P.appx_list + k);
+    if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;
+    const uint32_t ll = __ldg(P.lens + r);
+    double acc = 0.0;
+    if (!paired_read_any(P, r, ll, acc)) continue;
+    P.values[r] = acc;
+    acc_read(P, sum, floored, acc, (ll & 0xffff) + (ll >> 16));
+  }
   if (!P.chain_first) pdl_wait();
   block_accumulate(sum, floored, P.accum);
   if (P.finish_here) finish_set_if_complete(P);
   tl_end(P.timeline, kTlDelta);
+}
+
+// Replay of a touched FAST read (one record per mate, both under one key, term resolved at commit — FastPair): its pair
+// term T is a property of the two records, so the subtract/add sequence of graph.cc:1936-1950 is "T leaves for every
+// erased walk that holds the key and passes the skip rule, T enters for every added one", in enumeration order. Everything
+// comes from the 64-byte combined slot entry of the key (both words of both mates), at most one further occurrence per
+// mate and the term-table entry: three memory levels instead of the general path's six. Covers keys that occur at most
+// twice in the evaluation, in different walks (the normal case: once in the erased walk, once in the added one).
+// Returns false when the general path has to take the read.
+__device__ __forceinline__ bool delta_fast(const ScoreParams& P, int r, double& acc) {
+  const uint4 f = __ldg(static_cast<const uint4*>(P.fast) + r);
+  if ((f.x >> 31) != 0u) return false;          // scored by the list-driven phases: several records / different keys
+  if (((f.x >> 30) & 1u) != 0u) return true;    // a mate without any record: no pair term, the value stands
+  const uint4* __restrict__ comb = static_cast<const uint4*>(P.comb) + 4 * (size_t)(f.x & 0x3fffffffu);
+  uint4 a1, a2, b1, b2;
+  ldg256(comb, a1, a2);
+  ldg256(comb + 2, b1, b2);
+  const int4 te = __ldg(static_cast<const int4*>(P.tq) + f.w);
+  const bool live1 = (a1.x & 0x7fffffffu) == P.epoch, live2 = (a2.x & 0x7fffffffu) == P.epoch;
+  if (!live1 || !live2) return !live1 && !live2 ? true : false;   // (both stores hold the key or neither does)
+  const int n1 = (int)b1.y, n2 = (int)b2.y;
+  if (n1 != n2 || n1 > 2) return false;
+  int4 o1 = make_int4((int)a1.y, 0, (int)a1.z, (int)a1.w), o2 = make_int4((int)a2.y, 0, (int)a2.z, (int)a2.w);   // {walk, -, cur_pos, skip_below}
+  int4 p1 = o1, p2 = o2;
+  if (n1 == 2) {
+    p1 = ldg4(P.m[0].occ + b1.z + 1);   // {walk, seg, cur_pos, skip_below}
+    p2 = ldg4(P.m[1].occ + b2.z + 1);
+    if (p1.x == o1.x || p1.x != p2.x) return false;   // the key twice in ONE walk: distances between the occurrences matter
+  }
+  if (o1.x != o2.x) return false;
+  const double t = __hiloint2double(te.y, te.x);
+  const int pos1 = (int)f.y, pos2 = (int)f.z;
+  if (wrap_add(pos1, o1.z) >= o1.w && wrap_add(pos2, o2.z) >= o2.w) acc = o1.x < P.n_erased ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  if (n1 == 2 && wrap_add(pos1, p1.z) >= p1.w && wrap_add(pos2, p2.z) >= p2.w) acc = p1.x < P.n_erased ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  return true;
 }
 
 // DELTA discovery + update: one thread per mate-1 record under a key of an erased/added walk; the first
@@ -1706,19 +1732,40 @@ __global__ void __launch_bounds__(kOvfBlock) paired_delta_kernel(const ScorePara
   const double2* log_tab = static_cast<const double2*>(P.log_tab);
   Acc sum = acc_zero();
   unsigned floored = 0;
-  const uint32_t total = __ldg(P.touch_prefix + P.n_touch);
+  // the touched keys' range table in shared memory: every thread searches it
+  constexpr int kTouchShared = 1024;
+  __shared__ uint32_t s_prefix[kTouchShared + 1];
+  __shared__ uint32_t s_begin[kTouchShared];
+  const bool in_shared = P.n_touch <= kTouchShared;
+  if (in_shared) {
+    for (int t = threadIdx.x; t <= P.n_touch; t += blockDim.x) {
+      s_prefix[t] = __ldg(P.touch_prefix + t);
+      if (t < P.n_touch) s_begin[t] = P.touch[t].begin;
+    }
+    __syncthreads();
+  }
+  const uint32_t total = in_shared ? s_prefix[P.n_touch] : __ldg(P.touch_prefix + P.n_touch);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int lo = 0, hi = P.n_touch;   // largest t with prefix[t] <= i
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(P.touch_prefix + mid) <= i) lo = mid; else hi = mid;
+    uint32_t at;
+    if (in_shared) {
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_prefix[mid] <= i) lo = mid; else hi = mid;
+      }
+      at = s_begin[lo] + (i - s_prefix[lo]);
+    } else {
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(P.touch_prefix + mid) <= i) lo = mid; else hi = mid;
+      }
+      at = P.touch[lo].begin + (i - __ldg(P.touch_prefix + lo));
     }
-    const TouchRange tr = P.touch[lo];
-    const int r = ldg4(P.arena1 + tr.begin + (i - __ldg(P.touch_prefix + lo))).x;
+    const int r = ldg4(P.arena1 + at).x;
     if (atomicExch(P.stamp + r, P.epoch) == P.epoch) continue;
     const double old = P.values[r];
     double acc = old;
-    if (paired_read_ordered(P, r, acc)) {
+    if ((P.fast && P.tq && !P.ev_keys && delta_fast(P, r, acc)) || paired_read_ordered(P, r, acc)) {
       P.values[r] = acc;
       if (P.delta_only) {   // same total length as the running total: swap this read's term in it
         const uint32_t ll = __ldg(P.lens + r);
@@ -2497,7 +2544,15 @@ __global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* t
   if (cb) {
     const int32_t* mp = kInline ? T.cm[u.store] : comb_map[u.store];
     const int idx = mp ? mp[u.key] : u.key;
-    if (idx >= 0) cb[2 * idx] = a;
+    if (idx >= 0) {   // 64-byte entry per mate-1 key: {first word mate 1, first word mate 2, second word mate 1, second word mate 2}
+      cb[4 * idx] = a;
+      SlotA bw;
+      bw.epoch_flag = (uint32_t)b.seg;
+      bw.walk = b.n_occ;
+      bw.cur_pos = b.occ_begin;
+      bw.skip_below = 0;
+      cb[4 * idx + 2] = bw;
+    }
   }
   tl_end(timeline, kTlApply);
 }
@@ -2688,15 +2743,30 @@ StreamKernel stream_kernel(bool cov, bool packed, bool tab) {
   switch (env ? atoi(env) : 0) {
     case 42: return paired_stream_kernel<false, true, true, 4, 2>;
     case 52: return paired_stream_kernel<false, true, true, 5, 2>;
-    case 62: return paired_stream_kernel<false, true, true, 6, 2>;
     case 44: return paired_stream_kernel<false, true, true, 4, 4>;
-    case 54: return paired_stream_kernel<false, true, true, 5, 4>;
-    case 81: return paired_stream_kernel<false, true, true, 8, 1>;
-    case 34: return paired_stream_kernel<false, true, true, 3, 4>;
     case 32: return paired_stream_kernel<false, true, true, 3, 2>;
+    case 2: return nullptr;   // two launches: stream_kernel_tier1 + stream_kernel_rest
+    // measured (profiles/r02_summary.md): one fused launch at 4 blocks x 2 reads beats every two-launch shape — tier 1 is
+    // bound by DRAM, and MORE resident warps make it slower, not faster
     default: return paired_stream_kernel<false, true, true, 4, 2>;
   }
 }
+// The two-launch form of a set with fast records: tier 1 alone (shape from GAML_B200_TIER1_SHAPE=<blocks><reads>), then the rest.
+StreamKernel stream_kernel_tier1() {
+  const char* env = getenv("GAML_B200_TIER1_SHAPE");
+  switch (env ? atoi(env) : 0) {
+    case 81: return paired_stream_kernel<false, true, true, 8, 1, 1>;
+    case 61: return paired_stream_kernel<false, true, true, 6, 1, 1>;
+    case 62: return paired_stream_kernel<false, true, true, 6, 2, 1>;
+    case 52: return paired_stream_kernel<false, true, true, 5, 2, 1>;
+    case 42: return paired_stream_kernel<false, true, true, 4, 2, 1>;
+    case 44: return paired_stream_kernel<false, true, true, 4, 4, 1>;
+    case 34: return paired_stream_kernel<false, true, true, 3, 4, 1>;
+    case 82: return paired_stream_kernel<false, true, true, 8, 2, 1>;
+    default: return paired_stream_kernel<false, true, true, 6, 2, 1>;
+  }
+}
+StreamKernel stream_kernel_rest() { return paired_stream_kernel<false, true, true, 4, 2, 2>; }
 
 template <class K>
 int resident_blocks(K kernel, int block) {
@@ -2788,8 +2858,9 @@ void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB
 // kernel(s) of the set are bracketed by e0/e1 (the roofline timing); an event between two kernels makes the second
 // wait for the first in the ordinary way, so profiling costs the overlap at those two boundaries.
 // Tier 1 and tier 2 touch disjoint reads and only meet in the (commutative, integer) accumulators.
-void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_multi_items, int ovf_grid, int sm_count,
-                        cudaStream_t st, bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1) {
+int launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_multi_items, int ovf_grid, int sm_count,
+                       cudaStream_t st, bool chained, bool profile, cudaEvent_t e0, cudaEvent_t e1) {
+  int n_launched = 0;
   // chain: [multi pass] -> streaming kernel (tier 1 + tier 2) -> many-placement pass. Only two kernels of a chain are in
   // flight at a time (kernel n+2 starts when kernel n has completed), so the multi pass — a small grid of
   // register-hungry blocks with a long dependent chain, needing apply_slots only — goes FIRST and runs underneath the
@@ -2800,13 +2871,15 @@ void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_mu
   ScoreParams Q = P;
   bool dep = chained && !profile;
   bool first = true;
-  if (n_multi_items > 0) {
+  if (n_multi_items > 0 || P.n_appx > 0) {
     Q.chain_first = 1;
     Q.finish_here = 0;
+    if (n_multi_items < (uint32_t)P.n_appx) n_multi_items = (uint32_t)P.n_appx;   // (grid sizing only)
     // at most ONE resident wave: the streaming kernel behind it is released only when every block of this grid has
     // started, so blocks queuing for a second wave would hold it back for the duration of the first
     static const int per_sm = resident_blocks(paired_multi_kernel, kOvfBlock);
     launch_chain(paired_multi_kernel, grid_for(n_multi_items, kOvfBlock, sm_count, per_sm), kOvfBlock, st, dep, Q);
+    n_launched++;
     dep = true;
     first = false;
   }
@@ -2815,22 +2888,38 @@ void launch_paired_full(const ScoreParams& P, int grid, int cgrid, uint32_t n_mu
   Q.finish_here = profile ? 0 : 1;   // when profiling, e0/e1 bracket the streaming work alone: the last kernel publishes
   {
     // one resident wave of the instantiation that runs (its blocks draw tiles from counters)
-    const StreamKernel k = stream_kernel(P.ev_keys != nullptr, P.pairs != nullptr, P.pairs != nullptr && P.comb != nullptr && P.fast != nullptr);
-    static StreamKernel seen[8];
-    static int seen_per_sm[8];
+    static StreamKernel seen[16];
+    static int seen_per_sm[16];
     static int n_seen = 0;
-    int per_sm = 0;
-    for (int i = 0; i < n_seen; i++)
-      if (seen[i] == k) per_sm = seen_per_sm[i];
-    if (per_sm == 0) {
-      per_sm = resident_blocks(k, kBlock);
-      if (n_seen < 8) { seen[n_seen] = k; seen_per_sm[n_seen++] = per_sm; }
+    auto blocks_per_sm = [&](StreamKernel k) {
+      for (int i = 0; i < n_seen; i++)
+        if (seen[i] == k) return seen_per_sm[i];
+      const int v = resident_blocks(k, kBlock);
+      if (n_seen < 16) { seen[n_seen] = k; seen_per_sm[n_seen++] = v; }
+      return v;
+    };
+    const bool tab = P.pairs != nullptr && P.comb != nullptr && P.fast != nullptr;
+    const StreamKernel k = stream_kernel(P.ev_keys != nullptr, P.pairs != nullptr, tab);
+    if (k) {
+      grid = grid_for((size_t)P.n_reads, kBlock, sm_count, blocks_per_sm(k));
+      launch_chain(k, grid, kBlock, st, dep && !profile, Q);
+      n_launched++;
+    } else {
+      // fast records: tier 1 in a launch of its own, everything else in the next one (which waits for it at its end)
+      ScoreParams Q1 = Q;
+      Q1.finish_here = 0;
+      const StreamKernel k1 = stream_kernel_tier1(), k2 = stream_kernel_rest();
+      launch_chain(k1, grid_for((size_t)std::max(P.n_tier1, 1), kBlock, sm_count, blocks_per_sm(k1)), kBlock, st, dep && !profile, Q1);
+      ScoreParams Q2 = Q;
+      Q2.chain_first = 0;
+      const int items = std::max(std::max(P.n_main, P.n_complex - P.n_main), std::max(P.n_cross / 2, P.n_appx));
+      launch_chain(k2, grid_for((size_t)std::max(items, 1), kBlock, sm_count, blocks_per_sm(k2)), kBlock, st, true, Q2);
+      n_launched += 2;
     }
-    grid = grid_for((size_t)P.n_reads, kBlock, sm_count, per_sm);
-    launch_chain(k, grid, kBlock, st, dep && !profile, Q);
   }
   if (profile) cudaEventRecord(e1, st);
   launch_chain(paired_overflow_kernel, ovf_grid, kOvfBlock, st, !profile, P, 1);
+  return n_launched + 1;
 }
 
 void launch_paired_delta(const ScoreParams& P, uint32_t n_touch_records, int grid_total, int ovf_grid, int sm_count,

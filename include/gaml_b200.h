@@ -209,7 +209,8 @@ int gaml_eval_finish_gathered(gaml_ctx* ctx, double* gathered, int32_t* total_le
  * waits for one flag in its own pinned memory. gaml_peer_exchange_create allocates this rank's buffer and returns its
  * cudaIpcMemHandle_t (GAML_IPC_HANDLE_BYTES) for the caller's plumbing to all-gather (and the raw device pointer, for
  * contexts of the same process); gaml_peer_exchange_open takes all ranks' handles (rank-major) and/or local pointers and
- * switches the exchange on. gaml_eval_finish_gathered / gaml_calc_prob_gathered then work as above. */
+ * switches the exchange on. gaml_eval_finish_gathered / gaml_calc_prob_gathered then work as above. Every rank needs its OWN
+ * GPU: a kernel that waits for a line must never share a GPU with the kernel that writes it (refused with GAML_ERR_ARG). */
 #define GAML_IPC_HANDLE_BYTES 64
 int gaml_peer_exchange_create(gaml_ctx* ctx, int32_t rank, int32_t world, void* ipc_handle_out, void** buffer_out);
 int gaml_peer_exchange_open(gaml_ctx* ctx, const void* ipc_handles, void* const* local_buffers);

@@ -211,20 +211,23 @@ def test_result_exchange_between_two_contexts_matches_the_unsharded_result(oracl
     whole.close()
 
 
-def test_peer_memory_exchange_between_two_contexts_matches_the_unsharded_result():
+def test_peer_memory_exchange_between_two_gpus_matches_the_unsharded_result():
     """The same over peer memory (gaml_peer_exchange_*): each publishing block stores its 64-byte line into the exchange
-    buffer of both "ranks", the last kernel of each chain waits for both lines in its own buffer. Two contexts of one
-    process wire each other's buffers by pointer (IPC handles are for other processes)."""
+    buffer of both ranks over NVLink, the last kernel of each chain waits for both lines in its own buffer. Needs TWO
+    GPUs (one context each, wired by pointer — IPC handles are for other processes): a kernel that waits for a line
+    another kernel writes must never share its GPU with that kernel (B200_PROFILING.md), so on a one-GPU box this is
+    covered by `bench.py --gpus N --exchange peer` instead (profiles/r02_exchange_ab.md)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs: kernels that wait on one another must not share a GPU")
     wl = synth.paired_workload(46, 10000, 200_000, n_evals=12, seed=11)
     whole = api.ProbCalculator.from_workload(wl)
-    ranks = [api.ProbCalculator.from_workload(wl, shard_of=(rk, 2)) for rk in range(2)]
+    ranks = [api.ProbCalculator.from_workload(wl, device=rk, shard_of=(rk, 2)) for rk in range(2)]
     ptrs = [pc.peer_exchange_create(rk, 2)[1] for rk, pc in enumerate(ranks)]
     for pc in ranks:
         pc.peer_exchange_open(local_ptrs=ptrs)
     for e, walks in enumerate(wl.evals):
         ref = whole.calc_prob(walks)
-        # (two "ranks" on ONE GPU: both are prepared before either is launched — a launched rank's last kernel waits for the
-        #  other's line, and anything in a prepare that waits for the whole device, e.g. growing a buffer, would wait for it)
         for pc in ranks:
             pc.prepare(walks)
         for pc in ranks:

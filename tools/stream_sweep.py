@@ -54,7 +54,12 @@ def main():
     for shape in shapes:
         os.environ.pop("GAML_B200_NO_TERM_TABLE", None)
         os.environ.pop("GAML_B200_NO_PERMUTE", None)
-        if shape == "notab":
+        os.environ.pop("GAML_B200_TIER1_SHAPE", None)
+        os.environ.pop("GAML_B200_STREAM_SHAPE", None)
+        if shape.startswith("t"):   # two launches: tier 1 alone in this shape, then the rest
+            os.environ["GAML_B200_TIER1_SHAPE"] = shape[1:]
+            os.environ["GAML_B200_STREAM_SHAPE"] = "2"
+        elif shape == "notab":
             os.environ["GAML_B200_NO_TERM_TABLE"] = "1"
             os.environ["GAML_B200_STREAM_SHAPE"] = "0"
         elif shape.endswith("np"):
