@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -83,6 +84,7 @@ class ProbCalculator {
     zeros.clear();
     for (size_t s = 0; s < n_sets_; s++) zeros.push_back(make_pair(z[2 * s], z[2 * s + 1]));
     total_len = res.total_len;
+    had_calc_ = true;
     return res.prob;
   }
   double CalcProb(vector<vector<int>>& paths, int& total_len) {
@@ -92,6 +94,60 @@ class ProbCalculator {
   double CalcProb(vector<vector<int>>& paths) {
     int tl;
     return CalcProb(paths, tl);
+  }
+
+  // NOT in the reference: scores every candidate walk set against the CURRENT state (the walk set of the last CalcProb)
+  // in one device batch (gaml_calc_prob_batch) and changes no state. scores[c] is the double a CalcProb(candidates[c])
+  // issued right now would return. The moves that try several alternatives one CalcProb at a time (LocalChange2
+  // moves.cc:107-113, FixGapLength 715-726, FixRepForNode2 1158-1305) submit them here when built with
+  // oracle/build_ref.sh's moves.cc patch (target gaml_gpu_batched, GamlBatchReplay below). With single or PacBio sets
+  // configured — they keep no incremental state to evaluate candidates against — the candidates are scored one by one.
+  vector<double> CalcProbBatch(vector<vector<vector<int>>>& candidates) {
+    vector<double> scores(candidates.size(), 0.0);
+    if (candidates.empty()) return scores;
+    if (!ctx_) Init();
+    if (!single_reads.empty() || !pacbio_reads.empty() || paired_reads.empty() || prev_paths_.empty() || !had_calc_) {
+      for (size_t c = 0; c < candidates.size(); c++) scores[c] = CalcProb(candidates[c]);
+      return scores;
+    }
+    const vector<vector<int>> base = prev_paths_;   // FillAndMirrorCaches moves prev_paths_ along
+    const vector<int> base_final_end = prev_final_end_;
+    vector<int32_t> erased_idx, added_nodes;
+    vector<int64_t> erased_off(1, 0), added_walk_off(1, 0), cand_added_off(1, 0);
+    for (size_t c = 0; c < candidates.size(); c++) {
+      const vector<vector<int>>& cand = candidates[c];
+      FillAndMirrorCaches(cand);   // aligns and mirrors the windows of walks seen for the first time
+      // multiset difference against the base walk list: equal walks at the front and at the back drop out at once
+      size_t lo = 0;
+      while (lo < base.size() && lo < cand.size() && base[lo] == cand[lo]) lo++;
+      size_t hb = base.size(), hc = cand.size();
+      while (hb > lo && hc > lo && base[hb - 1] == cand[hc - 1]) { hb--; hc--; }
+      unordered_map<vector<int>, int> need;
+      for (size_t i = lo; i < hc; i++) need[cand[i]]++;
+      for (size_t i = lo; i < hb; i++) {
+        auto it = need.find(base[i]);
+        if (it != need.end() && it->second > 0) it->second--;
+        else erased_idx.push_back((int32_t)i);
+      }
+      unordered_map<vector<int>, int> have;
+      for (size_t i = lo; i < hb; i++) have[base[i]]++;
+      for (size_t i = lo; i < hc; i++) {
+        auto it = have.find(cand[i]);
+        if (it != have.end() && it->second > 0) { it->second--; continue; }
+        added_nodes.insert(added_nodes.end(), cand[i].begin(), cand[i].end());
+        added_walk_off.push_back((int64_t)added_nodes.size());
+      }
+      erased_off.push_back((int64_t)erased_idx.size());
+      cand_added_off.push_back((int64_t)added_walk_off.size() - 1);
+    }
+    prev_paths_ = base;   // the state did not move
+    prev_final_end_ = base_final_end;
+    if (erased_idx.empty()) erased_idx.push_back(0);
+    if (added_nodes.empty()) added_nodes.push_back(0);
+    vector<int32_t> tls(candidates.size());
+    Check(gaml_calc_prob_batch(ctx_, (int32_t)candidates.size(), erased_idx.data(), erased_off.data(), added_nodes.data(),
+                               added_walk_off.data(), cand_added_off.data(), scores.data(), tls.data(), NULL));
+    return scores;
   }
 
   vector<pair<SingleReadConfig, ReadSet*>> single_reads;
@@ -399,6 +455,36 @@ class ProbCalculator {
   unordered_map<vector<int>, int> seen_;   // every walk evaluated so far -> its FinalEnd
   vector<vector<int>> prev_paths_;
   vector<int> prev_final_end_;
+  bool had_calc_ = false;
+};
+
+// Two-pass replay for a move that scores a LIST of alternatives and acts on them in order (first improvement wins,
+// similar scores are remembered, ...): pass 0 runs the move's own loop unchanged except that Score() records the
+// candidate and answers NaN — every comparison the loops make on a score is false for NaN, so pass 0 has no effect
+// besides building the candidates; End() scores them in ONE batch; pass 1 runs the loop again with the real scores, in
+// the same order. oracle/build_ref.sh wraps the loops of moves.cc with it (in the compiler's input stream).
+struct GamlBatchReplay {
+  explicit GamlBatchReplay(ProbCalculator& pc) : pc_(pc), pass_(0), next_(0) {}
+  void Begin(int pass) {
+    pass_ = pass;
+    next_ = 0;
+    if (pass == 0) sets_.clear();
+  }
+  double Score(vector<vector<int>>& paths) {
+    if (pass_ == 0) {
+      sets_.push_back(paths);
+      return std::numeric_limits<double>::quiet_NaN();
+    }
+    return scores_[next_++];
+  }
+  void End() {
+    if (pass_ == 0) scores_ = pc_.CalcProbBatch(sets_);
+  }
+  ProbCalculator& pc_;
+  int pass_;
+  size_t next_;
+  vector<vector<vector<int>>> sets_;
+  vector<double> scores_;
 };
 
 #endif

@@ -54,6 +54,35 @@ if [ -f "$LIBDIR/libgaml_b200.so" ]; then
   g++ -o gaml_gpu gaml_gpu.o moves_gpu.o graph.o input_output.o graph_from_assembly.o \
       -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200' 2>/dev/null
   g++ -o gpu_harness gpu_harness.o graph.o -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200'
+  # gaml_gpu_batched: the same program with the three places where moves.cc scores a LIST of alternatives
+  # one CalcProb at a time rewritten — in the compiler's input stream, like the graph.cc:1478 line — to hand the whole
+  # list to ProbCalculator::CalcProbBatch (one device batch) through GamlBatchReplay (integration/prob_calculator.h):
+  #   LocalChange2     moves.cc:108-113   the two sampled extensions of each step
+  #   FixGapLength     moves.cc:717-720   the two interior points of the ternary search
+  #   FixRepForNode2   moves.cc:1158-1305 the three candidate loops (pairs of positions, doubles, palindromes)
+  sed -e '108i\    GamlBatchReplay gb(prob_calc); for (int gb_ph = 0; gb_ph < 2; gb_ph++) { gb.Begin(gb_ph); scores.clear();' \
+      -e '110s/prob_calc.CalcProb(new_paths)/gb.Score(new_paths)/' \
+      -e '113a\    gb.End(); }' \
+      -e '717i\  double mid1_p = 0, mid2_p = 0; { GamlBatchReplay gb(prob_calc); for (int gb_ph = 0; gb_ph < 2; gb_ph++) { gb.Begin(gb_ph);' \
+      -e '718s/double mid1_p = prob_calc.CalcProb(paths)/mid1_p = gb.Score(paths)/' \
+      -e '720s/double mid2_p = prob_calc.CalcProb(paths)/mid2_p = gb.Score(paths)/' \
+      -e '720a\  gb.End(); } }' \
+      -e '1157a\  GamlBatchReplay gb(prob_calc);' \
+      -e '1158i\  for (int gb_ph = 0; gb_ph < 2; gb_ph++) { gb.Begin(gb_ph);' \
+      -e '1189s/prob_calc.CalcProb(paths2)/gb.Score(paths2)/' \
+      -e '1204a\  gb.End(); }' \
+      -e '1205i\  for (int gb_ph = 0; gb_ph < 2; gb_ph++) { gb.Begin(gb_ph);' \
+      -e '1264s/prob_calc.CalcProb(paths2)/gb.Score(paths2)/' \
+      -e '1281a\  gb.End(); }' \
+      -e '1282i\  for (int gb_ph = 0; gb_ph < 2; gb_ph++) { gb.Begin(gb_ph);' \
+      -e '1290s/prob_calc.CalcProb(paths2)/gb.Score(paths2)/' \
+      -e '1305a\  gb.End(); }' \
+      "$REF/moves.cc" > moves_batched.ii.cc
+  if [ "$(grep -c 'gb.Score' moves_batched.ii.cc)" != "6" ]; then echo "build_ref: moves.cc patch did not apply (reference changed?)" >&2; exit 1; fi
+  g++ "${GFLAGS[@]}" -I"$REF" -c moves_batched.ii.cc -o moves_gpu_batched.o
+  rm -f moves_batched.ii.cc
+  g++ -o gaml_gpu_batched gaml_gpu.o moves_gpu_batched.o graph.o input_output.o graph_from_assembly.o \
+      -L"$LIBDIR" -lgaml_b200 '-Wl,-rpath,$ORIGIN/../../gaml_b200' 2>/dev/null
   echo "build_ref: built $OUT/gaml_gpu (reference annealing loop + moves over the CUDA ProbCalculator) and $OUT/gpu_harness"
 fi
 echo "build_ref: built $OUT/gaml_ref and $OUT/ref_harness"

@@ -20,6 +20,15 @@ for kind in single paired; do
   python -c "print('%.2f' % ($t1 - $t0))" > "$D/ref.time"; python -c "print('%.2f' % ($t2 - $t1))" > "$D/gpu.time"
   python "$ROOT/tools/compare_traces.py" "$D/ref.log" "$D/gpu.log" | tee "$OUT/$kind.compare.txt" || rc=1
   echo "$kind: reference $(cat $D/ref.time)s, cuda $(cat $D/gpu.time)s for $ITERS iterations (wall, includes the one-off CPU alignment of new keys)" | tee -a "$OUT/$kind.compare.txt"
+  if [ -x "$ROOT/oracle/_ref/gaml_gpu_batched" ]; then
+    # the same driver with the moves' candidate lists scored in device batches (oracle/build_ref.sh, gaml_gpu_batched)
+    t3=$(date +%s.%N)
+    ( cd "$D" && stdbuf -oL "$ROOT/oracle/_ref/gaml_gpu_batched" gaml.cfg > batched.log 2>&1 ) || { echo "gaml_gpu_batched failed ($kind)"; tail -5 "$D/batched.log"; rc=1; }
+    t4=$(date +%s.%N)
+    python "$ROOT/tools/compare_traces.py" "$D/ref.log" "$D/batched.log" | tee "$OUT/$kind.batched.compare.txt" || rc=1
+    python -c "print('$kind: cuda with batched moves %.2f s for $ITERS iterations' % ($t4 - $t3))" | tee -a "$OUT/$kind.batched.compare.txt"
+    cp "$D/batched.log" "$OUT/$kind.batched.log"
+  fi
   grep -c "^itnum" "$D/gpu.log" > /dev/null
   cp "$D/ref.log" "$OUT/$kind.ref.log"; cp "$D/gpu.log" "$OUT/$kind.gpu.log"
 done
