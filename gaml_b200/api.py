@@ -58,7 +58,8 @@ EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_s
            "gaml_get_stats", "gaml_set_profiling", "gaml_read_timeline", "gaml_set_result_exchange",
            "gaml_eval_finish_gathered", "gaml_calc_prob_gathered", "gaml_cache_save", "gaml_cache_load",
            "gaml_pacbio_alignment_logprob", "gaml_peer_exchange_create", "gaml_peer_exchange_open", "gaml_peer_exchange_close",
-           "gaml_nccl_unique_id", "gaml_nccl_exchange_init", "gaml_calc_prob_batch_gathered"]
+           "gaml_nccl_unique_id", "gaml_nccl_exchange_init", "gaml_calc_prob_batch_gathered",
+           "gaml_penalty_export", "gaml_penalty_import"]
 
 _lib = None
 
@@ -110,6 +111,8 @@ def load_library() -> C.CDLL:
     lib.gaml_calc_prob_gathered.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double),
                                             C.POINTER(C.c_int32)]
     lib.gaml_calc_prob_batch_gathered.argtypes = [vp, C.c_int32, i32p, i64p, i32p, i64p, i64p, dp, i32p, i32p]
+    lib.gaml_penalty_export.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_int64)]
+    lib.gaml_penalty_import.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int64]
     lib.gaml_peer_exchange_create.argtypes = [vp, C.c_int32, C.c_int32, vp, C.POINTER(vp)]
     lib.gaml_peer_exchange_open.argtypes = [vp, vp, C.POINTER(vp)]
     lib.gaml_peer_exchange_close.argtypes = [vp]
@@ -439,6 +442,22 @@ class ProbCalculator:
         self._check(self.lib.gaml_nccl_exchange_init(self.h, unique_id, rank, world))
         if unique_id is not None:
             self._gather_buffers(world)
+
+    def penalty_export(self, set_id: int) -> np.ndarray:
+        """gaml_penalty_export: this shard's coverage events of the last evaluation (uint64 words)."""
+        n = C.c_int64(0)
+        rc = self.lib.gaml_penalty_export(self.h, set_id, None, 0, C.byref(n))
+        if rc < 0 and n.value == 0:
+            self._check(rc)
+        out = np.zeros(max(n.value, 1), dtype=np.uint64)
+        self._check(self.lib.gaml_penalty_export(self.h, set_id, out.ctypes.data_as(C.POINTER(C.c_uint64)), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def penalty_import(self, set_id: int, all_events: np.ndarray) -> None:
+        """gaml_penalty_import: the concatenation of every shard's events (this shard's included)."""
+        a = np.ascontiguousarray(all_events, dtype=np.uint64)
+        p = a.ctypes.data_as(C.POINTER(C.c_uint64)) if len(a) else None
+        self._check(self.lib.gaml_penalty_import(self.h, set_id, p, len(a)))
 
     def clear_result_exchange(self) -> None:
         if getattr(self, "_exch_keep", None) is not None:

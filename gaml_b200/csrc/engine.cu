@@ -226,6 +226,12 @@ struct ReadSetState {
   FlatCache flat_cache;         // per distinct walk: its lookups in this set (cleared when the set's cache grows)
   int bad_bases = 0;            // ScoringState::bad_bases (graph.h:614)
   bool penalty = false;         // paired set with penalty_constant != 0: coverage events are collected
+  // a penalised set on a read-id shard: a walk's coverage events live on all shards, so an evaluation leaves this
+  // shard's events on the device (no sweep), the caller gathers every shard's (gaml_penalty_export), hands the union
+  // back (gaml_penalty_import: sort + sweep + bad_bases bookkeeping) and only then combines the partials
+  bool sharded = false;
+  bool penalty_pending = false;
+  std::vector<unsigned long long> h_type1;   // the host's contig-start events of the pending evaluation (paired)
   DevBuf d_cov_thr, d_ev, d_ev_sorted, d_ev_temp, d_bad;
   // PacBio coverage penalty (graph.cc:3197-3250)
   bool pb_penalty = false;
@@ -1399,6 +1405,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       }
       csb[cov_cs[s].size()] = k;
       *reinterpret_cast<uint32_t*>(hb + sp.evcount_off) = (uint32_t)k;
+      ctx->sets[s]->h_type1.assign(keys, keys + k);
     }
   }
   ctx->n_updates = (int)updates.size();
@@ -1744,7 +1751,9 @@ int launch(gaml_ctx* ctx) {
         // touched records (+ the O(R) pass when the total length changed: probs read (8) + packed lengths (4) per pair)
         bytes += 16 * sp.records + (sp.delta_only ? 0 : 12 * (int64_t)rs.n_local);
       }
-      if (rs.penalty) {
+      if (rs.penalty && rs.sharded) {
+        chained = false;   // the sweep waits for every shard's events: gaml_penalty_import
+      } else if (rs.penalty) {
         CU(launch_coverage(rs.d_ev.as<unsigned long long>(), rs.d_ev_sorted.as<unsigned long long>(), sp.ev_cap, rs.d_ev_temp.p,
                            rs.d_ev_temp.cap, reinterpret_cast<const int*>(blob + sp.csbegin_off),
                            reinterpret_cast<const int*>(blob + sp.cs_off), rs.cfg.step,
@@ -1775,7 +1784,7 @@ int launch(gaml_ctx* ctx) {
         CU(rs.d_bad.reserve(256, 0, true, st));
         PbCovParams C{};
         C.seeds = blob + sp.pb_seeds_off;
-        C.n_seed = (int)rs.h_pb_seeds.size();
+        C.n_seed = rs.sharded ? 0 : (int)rs.h_pb_seeds.size();   // (a shard emits its own alignments' intervals only)
         C.occ = blob + sp.pb_occ_off;
         C.occ_prefix = reinterpret_cast<const uint32_t*>(blob + sp.pb_prefix_off);
         C.n_occ = (int)rs.h_pb_occ.size();
@@ -1792,8 +1801,8 @@ int launch(gaml_ctx* ctx) {
         C.error_flag = P.error_flag;
         CU(launch_pacbio_coverage(C, rs.d_pb_packed.as<unsigned long long>(), rs.d_pb_runmax.as<unsigned long long>(),
                                   rs.d_pb_temp.p, rs.d_pb_temp.cap, reinterpret_cast<const int*>(blob + sp.pb_len_off),
-                                  rs.cfg.step, rs.d_bad.as<int>(), ctx->sm_count, st));
-        launches += 6;
+                                  rs.cfg.step, rs.d_bad.as<int>(), ctx->sm_count, st, rs.sharded ? 1 : 0));
+        launches += rs.sharded ? 1 : 6;
         chained = false;
       }
       bytes += 16 * sp.records + 16 * (int64_t)rs.n_local;
@@ -1889,6 +1898,11 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
   bool need_sync = false;
   for (size_t s = 0; s < n_sets; s++) {
     ReadSetState& rs = *ctx->sets[s];
+    if ((rs.pb_penalty || rs.penalty) && rs.sharded) {   // swept later, over all shards' events (gaml_penalty_import)
+      rs.penalty_pending = true;
+      need_sync = true;
+      continue;
+    }
     if (rs.pb_penalty) {   // one int: this evaluation's bad bases over all walks (a local in CalcScoreForPacbio)
       rs.h_bad.assign(1, 0);
       CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1968,9 +1982,9 @@ int finish(gaml_ctx* ctx, double* partials, int32_t* total_len, double* gathered
     flags |= (uint32_t)(f & 15);
     ovf += (uint32_t)((f >> 4) & 0xffffff);
     scratch_placements = std::max<int64_t>(scratch_placements, (int64_t)(f >> 28));
-    if (rs.pb_penalty) rs.bad_bases = rs.h_bad[0];
+    if (rs.pb_penalty && !rs.sharded) rs.bad_bases = rs.h_bad[0];
     if (rs.cfg.kind == GAML_KIND_PAIRED) {
-      if (rs.penalty) {   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
+      if (rs.penalty && !rs.sharded) {   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
         if (ctx->plan[s].full) rs.bad_bases = 0;
         for (int w = 0; w < ctx->plan[s].n_cov_walks; w++)
           rs.bad_bases += w < ctx->plan[s].n_erased ? -rs.h_bad[w] : rs.h_bad[w];
@@ -2083,6 +2097,10 @@ int combine_raw(const double* gathered, int n_shards, int n_sets, const int32_t*
 
 int combine(gaml_ctx* ctx, const double* gathered, int n_shards, int total_len, gaml_result* result, int32_t* zeros) {
   const size_t n_sets = ctx->sets.size();
+  for (auto& rs : ctx->sets)
+    if (rs->penalty_pending)
+      return fail(ctx, GAML_ERR_STATE, "a penalised read set on a read-id shard: gather the shards' coverage events "
+                                       "(gaml_penalty_export) and hand them to gaml_penalty_import before combining");
   std::vector<int32_t> kinds(n_sets);
   std::vector<int64_t> counts(n_sets);
   std::vector<double> weights(n_sets), pen(n_sets);
@@ -2464,9 +2482,6 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   if (!cfg || n_reads_total < 0 || shard_lo < 0 || shard_hi < shard_lo || shard_hi > n_reads_total)
     return fail(ctx, GAML_ERR_ARG, "bad read set shape");
   if (cfg->kind < 0 || cfg->kind > 2) return fail(ctx, GAML_ERR_ARG, "bad read set kind");
-  if (cfg->penalty_constant != 0.0 && cfg->kind != GAML_KIND_SINGLE && (shard_lo != 0 || shard_hi != n_reads_total))
-    return fail(ctx, GAML_ERR_UNSUPPORTED, "penalty_constant != 0 on a sharded paired / pacbio set: a walk's coverage events live "
-                                           "on all shards (SURVEY §8e)");
   if (cfg->penalty_constant != 0.0 && cfg->kind == GAML_KIND_PACBIO && !(cfg->match_prob > 0.0 && cfg->mismatch_prob > 0.0))
     return fail(ctx, GAML_ERR_ARG, "a pacbio set with penalty_constant != 0 needs match_prob and mismatch_prob (GetMinReadProb, graph.h:478)");
   // single sets: the reference's sweep never counts a gap (graph.cc:1710-1733: last_event_type is never >= 3), so
@@ -2485,6 +2500,7 @@ int gaml_add_readset(gaml_ctx* ctx, const gaml_readset_config* cfg, int64_t n_re
   rs.lo = shard_lo;
   rs.hi = shard_hi;
   rs.n_local = (int)n_local;
+  rs.sharded = shard_lo != 0 || shard_hi != n_reads_total;
   rs.n_mates = paired ? 2 : 1;
   const int32_t* lens[2] = {read_len1, read_len2};
   const int32_t maxes[2] = {max_read_len1, max_read_len2};
@@ -3299,6 +3315,132 @@ int gaml_calc_prob_batch_gathered(gaml_ctx* ctx, int32_t n_cand, const int32_t* 
     probs[c] = res.prob;
     if (total_lens) total_lens[c] = tls[c];
   }
+  return GAML_OK;
+}
+
+// ---- coverage penalty of a read set on a read-id shard --------------------------------------------
+// Paired sets: one 64-bit event key per covered position (walk << 33 | position << 1 | 1, kernels.cu cov_key).
+// PacBio sets: two words per interval {(walk << 32 | start), end}.
+int gaml_penalty_export(gaml_ctx* ctx, int set, uint64_t* out, int64_t cap, int64_t* n_out) {
+  if (check_ctx(ctx) || !n_out) return GAML_ERR_ARG;
+  if (set < 0 || set >= (int)ctx->sets.size()) return fail(ctx, GAML_ERR_ARG, "no such read set");
+  ReadSetState& rs = *ctx->sets[set];
+  if (!rs.penalty_pending) return fail(ctx, GAML_ERR_STATE, "no pending coverage events: the set is not a penalised shard, or no evaluation has finished");
+  cudaSetDevice(ctx->device);
+  const SetPlan& sp = ctx->plan[set];
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (rs.penalty) {
+    uint32_t count = 0;
+    const size_t ns = std::max<size_t>(ctx->sets.size(), 1);
+    const unsigned long long* accum = ctx->d_flags.as<unsigned long long>() + 2 + 8 * ns + (size_t)set * kAccumStride;
+    CU(cudaMemcpy(&count, accum + 7, 4, cudaMemcpyDeviceToHost));
+    if (count > sp.ev_cap) return fail(ctx, GAML_ERR_CAPACITY, "coverage-event buffer exhausted");
+    const int64_t n = (int64_t)count - sp.n_type1;   // the host's contig-start events lead the buffer: every rank has them
+    *n_out = n;
+    if (n > cap) return fail(ctx, GAML_ERR_CAPACITY, "gaml_penalty_export: output buffer too small (n_out holds the count)");
+    if (n > 0) CU(cudaMemcpy(out, rs.d_ev.as<unsigned long long>() + sp.n_type1, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return GAML_OK;
+  }
+  uint32_t count = 0;
+  CU(cudaMemcpy(&count, rs.d_pb_count.p, 4, cudaMemcpyDeviceToHost));
+  if (count > sp.pb_cap) return fail(ctx, GAML_ERR_CAPACITY, "coverage-interval buffer exhausted");
+  *n_out = 2 * (int64_t)count;
+  if (2 * (int64_t)count > cap) return fail(ctx, GAML_ERR_CAPACITY, "gaml_penalty_export: output buffer too small (n_out holds the count)");
+  std::vector<unsigned long long> ik(count);
+  std::vector<int32_t> ie(count);
+  if (count) {
+    CU(cudaMemcpy(ik.data(), rs.d_pb_ikey.p, (size_t)count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ie.data(), rs.d_pb_iend.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
+  }
+  for (uint32_t i = 0; i < count; i++) {
+    out[2 * (size_t)i] = ik[i];
+    out[2 * (size_t)i + 1] = (uint64_t)(uint32_t)ie[i];
+  }
+  return GAML_OK;
+}
+
+int gaml_penalty_import(gaml_ctx* ctx, int set, const uint64_t* all, int64_t n_all) {
+  if (check_ctx(ctx) || n_all < 0 || (n_all > 0 && !all)) return GAML_ERR_ARG;
+  if (set < 0 || set >= (int)ctx->sets.size()) return fail(ctx, GAML_ERR_ARG, "no such read set");
+  ReadSetState& rs = *ctx->sets[set];
+  if (!rs.penalty_pending) return fail(ctx, GAML_ERR_STATE, "no pending coverage events for this read set");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const SetPlan& sp = ctx->plan[set];
+  char* blob = ctx->blob_dev;
+  if (rs.penalty) {
+    // [contig starts | every shard's covered positions | padding] -> sort -> one thread per event (graph.cc:1893-1919)
+    const uint64_t total = (uint64_t)rs.h_type1.size() + (uint64_t)n_all;
+    if (total > 0x7fffffffull) return fail(ctx, GAML_ERR_CAPACITY, "too many coverage events");
+    const uint32_t cap = (uint32_t)total + 16;
+    std::vector<unsigned long long> keys(cap, ~0ull);
+    std::copy(rs.h_type1.begin(), rs.h_type1.end(), keys.begin());
+    if (n_all) memcpy(keys.data() + rs.h_type1.size(), all, (size_t)n_all * 8);
+    CU(rs.d_ev.reserve((size_t)cap * 8, 0, false, st));
+    CU(rs.d_ev_sorted.reserve((size_t)cap * 8, 0, false, st));
+    CU(rs.d_ev_temp.reserve(std::max<size_t>(coverage_sort_temp_bytes(cap), 256), 0, false, st));
+    CU(rs.d_bad.reserve(std::max<size_t>(sp.n_cov_walks, 1) * 4, 0, false, st));
+    CU(cudaMemcpyAsync(rs.d_ev.p, keys.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(rs.d_bad.p, 0, std::max<size_t>(sp.n_cov_walks, 1) * 4, st));
+    CU(launch_coverage(rs.d_ev.as<unsigned long long>(), rs.d_ev_sorted.as<unsigned long long>(), cap, rs.d_ev_temp.p, rs.d_ev_temp.cap,
+                       reinterpret_cast<const int*>(blob + sp.csbegin_off), reinterpret_cast<const int*>(blob + sp.cs_off), rs.cfg.step,
+                       rs.cfg.insert_mean + 5 * rs.cfg.insert_std, rs.d_bad.as<int>(), ctx->sm_count, st));
+    ctx->stats.kernel_launches += 3;
+    rs.h_bad.assign(std::max(sp.n_cov_walks, 1), 0);
+    if (sp.n_cov_walks) CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, (size_t)sp.n_cov_walks * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (sp.full) rs.bad_bases = 0;   // EraseFromScoringState / AddToScoringState, graph.cc:1938, 1946
+    for (int w = 0; w < sp.n_cov_walks; w++) rs.bad_bases += w < sp.n_erased ? -rs.h_bad[w] : rs.h_bad[w];
+    rs.penalty_pending = false;
+    return GAML_OK;
+  }
+  // PacBio: the union of the shards' alignment intervals + the artificial and per-node intervals of every walk
+  if (n_all & 1) return fail(ctx, GAML_ERR_ARG, "PacBio intervals come as pairs of words");
+  const size_t n_int = (size_t)n_all / 2 + rs.h_pb_seeds.size();
+  if (n_int > 0x3ffffff0ull) return fail(ctx, GAML_ERR_CAPACITY, "too many PacBio coverage intervals");
+  const uint32_t cap = (uint32_t)n_int + 16;
+  std::vector<unsigned long long> ikey(cap, ~0ull), pkey(2 * (size_t)cap, ~0ull);
+  std::vector<int32_t> iend(cap, -1);
+  size_t k = 0;
+  auto put = [&](unsigned long long key, int32_t end) {
+    ikey[k] = key;
+    iend[k] = end;
+    pkey[2 * k] = key;
+    pkey[2 * k + 1] = (key & 0xffffffff00000000ull) | (unsigned long long)((uint32_t)end ^ 0x80000000u);
+    k++;
+  };
+  for (const int4& sd : rs.h_pb_seeds)   // {walk, start, end, -}
+    put(((unsigned long long)(uint32_t)sd.x << 32) | (unsigned long long)((uint32_t)sd.y ^ 0x80000000u), sd.z);
+  for (int64_t i = 0; i < n_all; i += 2) put(all[i], (int32_t)(uint32_t)all[i + 1]);
+  CU(rs.d_pb_ikey.reserve((size_t)cap * 2 * 8, 0, false, st));
+  CU(rs.d_pb_iend.reserve((size_t)cap * 2 * 4, 0, false, st));
+  CU(rs.d_pb_pkey.reserve((size_t)cap * 4 * 8, 0, false, st));
+  CU(rs.d_pb_packed.reserve((size_t)cap * 8, 0, false, st));
+  CU(rs.d_pb_runmax.reserve((size_t)cap * 8, 0, false, st));
+  CU(rs.d_pb_temp.reserve(std::max<size_t>(pacbio_coverage_temp_bytes(cap), 256), 0, false, st));
+  CU(rs.d_pb_count.reserve(256, 0, true, st));
+  CU(rs.d_bad.reserve(256, 0, true, st));
+  const uint32_t count = (uint32_t)n_int;
+  CU(cudaMemcpyAsync(rs.d_pb_ikey.p, ikey.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs.d_pb_iend.p, iend.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs.d_pb_pkey.p, pkey.data(), (size_t)cap * 2 * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs.d_pb_count.p, &count, 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(rs.d_bad.p, 0, 4, st));
+  PbCovParams C{};
+  C.ikey = rs.d_pb_ikey.as<unsigned long long>();
+  C.iend = rs.d_pb_iend.as<int32_t>();
+  C.pkey = rs.d_pb_pkey.as<unsigned long long>();
+  C.count = rs.d_pb_count.as<uint32_t>();
+  C.cap = cap;
+  CU(launch_pacbio_coverage(C, rs.d_pb_packed.as<unsigned long long>(), rs.d_pb_runmax.as<unsigned long long>(), rs.d_pb_temp.p,
+                            rs.d_pb_temp.cap, reinterpret_cast<const int*>(blob + sp.pb_len_off), rs.cfg.step, rs.d_bad.as<int>(),
+                            ctx->sm_count, st, 2));
+  ctx->stats.kernel_launches += 5;
+  rs.h_bad.assign(1, 0);
+  CU(cudaMemcpyAsync(rs.h_bad.data(), rs.d_bad.p, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  rs.bad_bases = rs.h_bad[0];
+  rs.penalty_pending = false;
   return GAML_OK;
 }
 

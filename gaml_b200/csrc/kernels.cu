@@ -3329,15 +3329,21 @@ size_t pacbio_coverage_temp_bytes(uint32_t cap) {
 
 // ikey/iend/pkey hold 2 x their capacity (unsorted half, sorted half); unused slots are padded with all-ones keys, which
 // sort behind every real (walk, position). bad is one int.
+// phase 0: everything; 1: emit only (a read-id shard's own intervals, left in ikey / iend for gaml_penalty_export);
+// 2: sort + sweep only (ikey / iend / pkey / count hold the union of all shards' intervals: gaml_penalty_import)
 cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* packed, unsigned long long* run_max, void* temp,
-                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st) {
+                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st, int phase) {
   const uint32_t cap = C.cap;
-  cudaError_t err = cudaMemsetAsync(C.ikey, 0xff, (size_t)cap * 2 * 8, st);
-  if (err == cudaSuccess) err = cudaMemsetAsync(C.pkey, 0xff, (size_t)cap * 4 * 8, st);
-  if (err == cudaSuccess) err = cudaMemsetAsync(C.count, 0, 4, st);
-  if (err == cudaSuccess) err = cudaMemsetAsync(bad, 0, 4, st);
-  if (err != cudaSuccess) return err;
-  pacbio_cov_emit_kernel<<<grid_for(cap, 256, sm_count, 8), 256, 0, st>>>(C);
+  cudaError_t err = cudaSuccess;
+  if (phase != 2) {
+    err = cudaMemsetAsync(C.ikey, 0xff, (size_t)cap * 2 * 8, st);
+    if (err == cudaSuccess) err = cudaMemsetAsync(C.pkey, 0xff, (size_t)cap * 4 * 8, st);
+    if (err == cudaSuccess) err = cudaMemsetAsync(C.count, 0, 4, st);
+    if (err == cudaSuccess) err = cudaMemsetAsync(bad, 0, 4, st);
+    if (err != cudaSuccess) return err;
+    pacbio_cov_emit_kernel<<<grid_for(cap, 256, sm_count, 8), 256, 0, st>>>(C);
+    if (phase == 1) return cudaGetLastError();
+  }
   unsigned long long* ikey_sorted = C.ikey + cap;
   int* iend_sorted = C.iend + cap;
   unsigned long long* pkey_sorted = C.pkey + 2 * (size_t)cap;

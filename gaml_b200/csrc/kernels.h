@@ -101,7 +101,8 @@ cudaError_t launch_coverage(const unsigned long long* keys_in, unsigned long lon
 // PacBio coverage penalty of one set: emit intervals, sort by (walk, start), running max of ends, sort positions, sweep.
 size_t pacbio_coverage_temp_bytes(uint32_t cap);
 cudaError_t launch_pacbio_coverage(const PbCovParams& C, unsigned long long* packed, unsigned long long* run_max, void* temp,
-                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st);
+                                   size_t temp_bytes, const int* walk_len, double step, int* bad, int sm_count, cudaStream_t st,
+                                   int phase = 0);   // 1: emit only, 2: sort + sweep only (read-id shards, kernels.cu)
 // PacBio alignment probability: one thread per alignment over host-prepared row ranges.
 void launch_pacbio_alnprob(const AlnProbParams& A, int sm_count, cudaStream_t st);
 // Multi-GPU result exchange: last kernel of an evaluation's chain (appended to it: recorded like the scoring kernels).

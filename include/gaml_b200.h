@@ -248,6 +248,16 @@ int gaml_calc_prob_batch_gathered(gaml_ctx* ctx, int32_t n_cand, const int32_t* 
                                   const int32_t* added_nodes, const int64_t* added_walk_off, const int64_t* cand_added_off,
                                   double* probs, int32_t* total_lens, int32_t* zeros);
 
+/* Coverage-gap penalty (penalty_constant != 0) of a paired or PacBio set on a READ-ID SHARD: the sweep of
+ * graph.cc:1893-1919 / 3197-3250 runs over a walk's events from ALL reads, so after gaml_eval_finish[_gathered] every rank
+ * (1) takes its shard's events with gaml_penalty_export (paired: one 64-bit key per covered position; PacBio: two words per
+ * alignment interval; n_out = words written, or needed when cap is too small), (2) all-gathers them with whatever it has
+ * (MPI, torch.distributed, ...), (3) hands the concatenation of all shards' events, its own included, to
+ * gaml_penalty_import, which sorts and sweeps them on the device and updates the set's bad_bases — the same integer on
+ * every rank — and only then (4) calls gaml_combine_partials (refused with GAML_ERR_STATE while events are pending). */
+int gaml_penalty_export(gaml_ctx* ctx, int set, uint64_t* out, int64_t cap, int64_t* n_out);
+int gaml_penalty_import(gaml_ctx* ctx, int set, const uint64_t* all, int64_t n_all);
+
 /* Forget the paired ScoringState (== constructing a fresh ProbCalculator, prob_calculator.h:45-47): the
  * next evaluation re-scores every read from scratch ("full logL"). */
 int gaml_reset_state(gaml_ctx* ctx);

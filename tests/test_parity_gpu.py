@@ -82,10 +82,6 @@ def test_error_behaviour():
     bad["read_id"] = 10 ** 6
     with pytest.raises(api.GamlError, match="read_id"):
         pc.cache_insert(0, 0, (6, 4), bad)
-    pb = workload.read_workload(os.path.join(GOLDEN, "hand_pacbio.wl")).sets[0]
-    pb.penalty_constant = 0.1          # a coverage penalty needs all reads of a walk: refused on a read-id shard
-    with pytest.raises(api.GamlError, match="penalty_constant"):
-        pc.add_readset(pb, shard=(0, max(pb.n_reads // 2, 1)))
     # the context is still usable after rejected calls
     prob, _, _ = pc.calc_prob(wl.evals[0])
     ref = workload.read_results(os.path.join(GOLDEN, "hand_paired.ref.res"))
@@ -594,6 +590,34 @@ def test_pacbio_coverage_penalty_matches_oracle(seed, oracle):
     pc.close()
     wl.sets[-1].penalty_constant = pen
     assert any(abs(a - r.score) > 1e-6 for a, r in zip(plain, ref))
+
+
+@pytest.mark.parametrize("name", ["synth_paired_penalty", "synth_pacbio_penalty"])
+def test_coverage_penalty_on_read_id_shards_matches_reference_golden(name):
+    """A penalised set split over read-id shards: a walk's coverage events live on all shards, so each
+    evaluation the shards' events are gathered (gaml_penalty_export), the union is swept on every shard
+    (gaml_penalty_import) and the partials combined — against the reference's own results for the unsharded set."""
+    wl = workload.read_workload(os.path.join(GOLDEN, name + ".wl"))
+    ref = workload.read_results(os.path.join(GOLDEN, name + ".ref.res"))
+    n_shards = 3
+    shards = [api.ProbCalculator.from_workload(wl, shard_of=(r, n_shards)) for r in range(n_shards)]
+    pen_sets = [s for s, spec in enumerate(wl.sets) if spec.penalty_constant != 0 and spec.kind != 0]
+    assert pen_sets
+    for e, walks in enumerate(wl.evals):
+        parts, tls = zip(*[pc.calc_prob_partial(walks) for pc in shards])
+        with pytest.raises(api.GamlError, match="gaml_penalty_import"):
+            shards[0].combine(np.stack(parts), n_shards, tls[0])     # events still pending
+        for s in pen_sets:
+            union = np.concatenate([pc.penalty_export(s) for pc in shards])
+            for pc in shards:
+                pc.penalty_import(s, union)
+        outs = [pc.combine(np.stack(parts), n_shards, tls[0]) for pc in shards]
+        assert outs[0] == outs[1] == outs[2], e
+        prob, zeros, tl = outs[0]
+        assert tl == ref[e].total_len and zeros == ref[e].zeros, e
+        assert abs(prob - ref[e].score) <= REL_TOTAL * abs(ref[e].score), (e, prob, ref[e].score)
+    for pc in shards:
+        pc.close()
 
 
 def test_single_set_penalty_is_a_no_op_like_the_reference(oracle):
