@@ -543,7 +543,10 @@ def main():
             batch_probs = run_batch()
         barrier()
         batch_s = max_over_ranks(time.perf_counter() - t0) / 3
+        stb = pc.stats()
         batch_info = {"candidates_per_launch": args.batch, "ms_per_batch": 1e3 * batch_s, "candidates_per_s": args.batch / batch_s,
+                      "device_ms_per_batch": stb.last_device_ms, "library_call_ms": stb.last_prepare_host_us * 1e-3,
+                      "touched_mate1_records": int(stb.last_records_gathered),
                       "mix": "40% extend / 30% interchange / 30% disconnect on the walk set reached after the incremental run",
                       "kernel_launches_per_batch": int((pc.stats().kernel_launches - launches_b0) / 3),
                       "best_candidate_prob": float(max(batch_probs)),

@@ -65,11 +65,13 @@ struct PlcLong {
 struct TouchRange { uint32_t begin; uint32_t count; };   // arena range of one touched mate-1 key
 
 constexpr int kAccumStride = 8;   // per set, u64: four 32-bit limbs of the exact 128-bit sum, floored, -inf terms, nan terms, spare
+constexpr int kBatchSlice = 4096;   // touched records of one candidate a block of the batch touch kernel takes
 constexpr int kBatchBin = 5;      // batch base pass, per bin, u64: low / high 32-bit lanes of sum(Q - qthr), reads, -inf, nan
 constexpr int kOutStride = 6;     // per set, f64: integer part, 2^-40 units, floored, -inf terms, nan terms, flags
 constexpr unsigned long long kResultSeal = 0x5eed5eed5eed5eedull;   // word 7 = seal ^ xor of words 0..6
 constexpr int kResultStride = 8;  // per set in the host-mapped result buffer (one 64-byte line): the kOutStride values,
                                   // the epoch of the evaluation that wrote them (the host's completion flag), a checksum
+struct Int2 { int32_t x, y; };
 struct Double2 { double x, y; };  // {1/c, -log(1/c)} entries of the log table
 // One entry of a uniform-length paired set's term table: the pair term (p1*p2)*ins for (edit 1, edit 2, insert distance)
 // and its fixed-point logarithm (kTermOdd when the logarithm is not finite).
@@ -184,7 +186,6 @@ struct ScoreParams {
 };
 
 // ---- PacBio coverage penalty (graph.cc:3197-3250) -----------------------------------------------------------------
-struct Int2 { int32_t x, y; };
 struct PbCovParams {
   const void* seeds;            // int4 {walk, start, end, -}: the artificial interval and one interval per node of every walk
   int32_t n_seed;
@@ -233,7 +234,8 @@ struct BatchCand {             // one candidate move, one paired read set
   int32_t key_count[2];
   int32_t n_erased;            // walk ordinals < n_erased are subtracted
   int32_t len_index;           // index of this candidate's total length among the batch's distinct values
-  int32_t pad[2];
+  int32_t range_begin;         // this candidate's slice of the batch's touched-key ranges
+  int32_t range_count;
 };
 struct BatchParams {
   const BatchCand* cands;
@@ -245,6 +247,9 @@ struct BatchParams {
   const TouchRange* ranges;    // mate-1 arena ranges of the touched keys, all candidates back to back
   const uint32_t* range_prefix;// n_ranges + 1 prefix sums of the range lengths
   const int32_t* range_cand;   // owning candidate of each range
+  const int32_t* partner12;    // mate-1 key id -> the same node sequence's key id in mate 2's store (-1: none), or null
+  const Int2* blocks;          // touched-record pass: {candidate, first record of the slice} per block (kBatchSlice records each)
+  int32_t n_blocks;
   int32_t n_ranges;
   // The batch's distinct total lengths, ASCENDING (so that a read's floor test pstar grows with the index), for every
   // length class (distinct len1+len2) of the set: pstar[cls * n_len + j]; len_class maps len1+len2 -> cls.

@@ -2124,6 +2124,8 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
                             double* partials, int32_t* total_lens, bool reduce_over_ranks = false) {
   if (n_cand <= 0 || !erased_off || !cand_added_off || !added_walk_off || !partials)
     return fail(ctx, GAML_ERR_ARG, "bad batch arguments");
+  const auto t_batch0 = std::chrono::steady_clock::now();
+  double batch_device_ms = 0.0;
   if (ctx->prepared || ctx->launched) return fail(ctx, GAML_ERR_STATE, "an evaluation is pending");
   const size_t n_sets = ctx->sets.size();
   if (n_sets == 0) return fail(ctx, GAML_ERR_STATE, "no read sets");
@@ -2138,27 +2140,47 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
   if (rc != GAML_OK) return rc;
   const WalkSet& base_set = ctx->prev();   // old_paths of every set
   const int n_base = base_set.n;
-  std::vector<Walk> base(n_base);
-  for (int i = 0; i < n_base; i++) base[i] = base_set.walk(i);
-  // rank of every base walk in the iteration order of the reference's multiset (GetChanges, graph.cc:1747-1763):
-  // erasing the kept walks leaves the others in place, so a candidate's erased walks come out in rank order
-  std::vector<int> rank(n_base, 0);
+  // Rank of every base walk in the iteration order of the reference's multiset (GetChanges, graph.cc:1747-1763): erasing
+  // the kept walks leaves the others in place, so a candidate's erased walks come out in rank order. With no equal walks
+  // in the base set the order is the container's rule (walk_set.h): buckets by the index of their first element,
+  // descending, then index descending — found from the cached bucket numbers in one pass; with equal walks the
+  // container itself is built.
+  std::vector<int64_t> rank((size_t)n_base, 0);
   {
-    std::unordered_multiset<Walk, WalkHash> idx(base.begin(), base.begin() + n_base);
-    std::unordered_map<Walk, std::vector<int>, WalkHash> where;
-    for (int i = n_base - 1; i >= 0; i--) where[base[i]].push_back(i);
-    int k = 0;
-    for (const Walk& w : idx) {
-      std::vector<int>& v = where[w];
-      rank[v.back()] = k++;
-      v.pop_back();
+    bool unique = ctx->prev_counts.valid && base_set.bkt_count == bucket_count_for((size_t)std::max(n_base, 1)) &&
+                  (int)base_set.bkt.size() == n_base;
+    if (unique)
+      for (int i = 0; i < n_base && unique; i++) unique = ctx->prev_counts.get(base_set.hash[i]) == 1;
+    if (unique) {
+      std::vector<int> first(base_set.bkt_count, -1);
+      for (int i = 0; i < n_base; i++)
+        if (first[base_set.bkt[i]] < 0) first[base_set.bkt[i]] = i;
+      // ascending rank = earlier in the iteration: larger first-of-bucket first, then larger index first
+      for (int i = 0; i < n_base; i++) rank[i] = -((int64_t)first[base_set.bkt[i]] * ((int64_t)n_base + 1) + (int64_t)i);
+    } else {
+      std::vector<Walk> base((size_t)n_base);
+      for (int i = 0; i < n_base; i++) base[i] = base_set.walk(i);
+      std::unordered_multiset<Walk, WalkHash> idx(base.begin(), base.begin() + n_base);
+      std::unordered_map<Walk, std::vector<int>, WalkHash> where;
+      for (int i = n_base - 1; i >= 0; i--) where[base[i]].push_back(i);
+      int64_t k = 0;
+      for (const Walk& w : idx) {
+        std::vector<int>& v = where[w];
+        rank[v.back()] = k++;
+        v.pop_back();
+      }
     }
   }
   long long base_len = 0;
   std::vector<int> base_walk_len(n_base);
   for (int i = 0; i < n_base; i++) {
-    base_walk_len[i] = walk_length(ctx, base[i]);
-    base_len += base_walk_len[i];
+    int t = 0;
+    for (int64_t k = base_set.offs[i]; k < base_set.offs[i + 1]; k++) {
+      const int x = base_set.nodes[(size_t)k];
+      t += x < 0 ? -x : ctx->node_len[x];
+    }
+    base_walk_len[i] = t;
+    base_len += t;
   }
   // distinct total lengths, ascending (the base pass relies on the floor test growing with the index)
   std::vector<int> cand_len(n_cand);
@@ -2223,7 +2245,6 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
       BatchCand& cd = cands[c];
       cd.n_erased = (int)cand_erased[c].size();
       cd.len_index = cand_len_index[c];
-      cd.pad[0] = cd.pad[1] = 0;
       for (int m = 0; m < 2; m++) {
         std::vector<std::pair<int, Occ>>& items = obs[m].items;
         std::stable_sort(items.begin(), items.end(),
@@ -2242,6 +2263,7 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
         }
         cd.key_count[m] = (int)keys[m].size() - cd.key_begin[m];
       }
+      cd.range_begin = (int32_t)ranges.size();
       // each touched mate-1 key once (a key of an erased walk often reappears in the added walk)
       std::sort(touch.begin(), touch.end(), [](const TouchRange& a, const TouchRange& b) { return a.begin < b.begin; });
       for (size_t t = 0; t < touch.size(); t++) {
@@ -2252,6 +2274,7 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
         if (touch_total > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 touched records in one batch");
         range_prefix.push_back((uint32_t)touch_total);
       }
+      cd.range_count = (int32_t)ranges.size() - cd.range_begin;
     }
     // ---- blob ----
     auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -2268,6 +2291,13 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     const size_t o_ranges = place(ranges.size() * sizeof(TouchRange));
     const size_t o_prefix = place(range_prefix.size() * 4);
     const size_t o_rcand = place(range_cand.size() * 4);
+    // the touched-record pass: one block per slice of kBatchSlice records of a candidate
+    std::vector<Int2> blocks;
+    for (int c = 0; c < n_cand; c++) {
+      const uint32_t tot = range_prefix[(size_t)cands[c].range_begin + cands[c].range_count] - range_prefix[(size_t)cands[c].range_begin];
+      for (uint32_t at = 0; at < tot; at += (uint32_t)kBatchSlice) blocks.push_back(Int2{c, (int32_t)at});
+    }
+    const size_t o_blocks = place(blocks.size() * sizeof(Int2));
     // floor tests: per length class of the set (distinct len1 + len2) and distinct total length
     std::vector<int32_t> len_class(std::max<size_t>(rs.h_thr.size(), 1), 0);
     std::vector<long long> qthr_cls(std::max<size_t>(rs.len_classes.size(), 1), 0);
@@ -2294,6 +2324,7 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     put(o_ranges, ranges.data(), ranges.size() * sizeof(TouchRange));
     put(o_prefix, range_prefix.data(), range_prefix.size() * 4);
     put(o_rcand, range_cand.data(), range_cand.size() * 4);
+    put(o_blocks, blocks.data(), blocks.size() * sizeof(Int2));
     put(o_pstar, pstar.data(), pstar.size() * 8);
     put(o_qcls, qthr_cls.data(), qthr_cls.size() * 8);
     put(o_lcls, len_class.data(), len_class.size() * 4);
@@ -2324,6 +2355,9 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     B.ranges = reinterpret_cast<const TouchRange*>(db + o_ranges);
     B.range_prefix = reinterpret_cast<const uint32_t*>(db + o_prefix);
     B.range_cand = reinterpret_cast<const int32_t*>(db + o_rcand);
+    B.partner12 = rs.comb_ok ? rs.d_partner12.as<int32_t>() : nullptr;
+    B.blocks = reinterpret_cast<const Int2*>(db + o_blocks);
+    B.n_blocks = (int)blocks.size();
     B.n_ranges = (int)ranges.size();
     B.pstar = reinterpret_cast<const double*>(db + o_pstar);
     B.qthr_cls = reinterpret_cast<const long long*>(db + o_qcls);
@@ -2333,8 +2367,10 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     B.accum_len = ctx->d_batch_acc.as<unsigned long long>();
     B.accum_cand = reinterpret_cast<long long*>(B.accum_len + ((size_t)n_len + 1) * kAccumStride);
     B.hist = B.accum_len + ((size_t)n_len + 1) * kAccumStride + (size_t)n_cand * 4;
+    CU(cudaEventRecord(ctx->ev[1], st));
     launch_batch(P, B, (uint32_t)touch_total, ctx->d_batch_out.as<double>(),
                  reinterpret_cast<const uint32_t*>(ctx->d_flags.as<unsigned long long>() + 1), ctx->sm_count, st);
+    CU(cudaEventRecord(ctx->ev[2], st));
     CU(cudaGetLastError());
     ctx->stats.kernel_launches += batch_launches(n_len, touch_total > 0);
     if (reduce_over_ranks) {
@@ -2345,12 +2381,21 @@ int calc_prob_batch_partial(gaml_ctx* ctx, int n_cand, const int32_t* erased_idx
     }
     CU(cudaMemcpyAsync(ctx->h_batch_out.data(), ctx->d_batch_out.p, (size_t)n_cand * kOutStride * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) batch_device_ms += ms;
+    }
+    ctx->stats.last_records_gathered = (int64_t)touch_total;
     for (int c = 0; c < n_cand; c++) {
       const double* o = ctx->h_batch_out.data() + (size_t)c * kOutStride;
       if (((uint64_t)o[5]) & 2) return fail(ctx, GAML_ERR_CAPACITY, "placement scratch exhausted (GAML_B200_SCRATCH_ENTRIES)");
       for (int k = 0; k < GAML_PARTIAL_DOUBLES; k++) partials[((size_t)c * n_sets + s) * GAML_PARTIAL_DOUBLES + k] = o[k];
     }
   }
+  // (measurement: the batch kernels' device time, and the whole call's wall time, in the fields of a normal evaluation)
+  ctx->stats.last_device_ms = batch_device_ms;
+  ctx->stats.last_prepare_host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_batch0).count();
+  ctx->timing_pending = false;
   return GAML_OK;
 }
 

@@ -418,13 +418,13 @@ struct CandLookup {
 };
 template <class F>
 __device__ __forceinline__ void visit_row(const MateView&, const CandLookup& lk, const int4& rw, int idx, F&& f) {
-  int lo = 0, hi = lk.n;
+  int lo = 0, hi = lk.n;   // (plain loads: the tables may sit in shared memory — batch_touch_kernel stages them)
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (__ldg(lk.keys + mid) < rw.x) lo = mid + 1; else hi = mid;
+    if (lk.keys[mid] < rw.x) lo = mid + 1; else hi = mid;
   }
-  if (lo >= lk.n || __ldg(lk.keys + lo) != rw.x) return;
-  const int4 a = __ldg(lk.a + lo), b = __ldg(lk.b + lo);
+  if (lo >= lk.n || lk.keys[lo] != rw.x) return;
+  const int4 a = lk.a[lo], b = lk.b[lo];
   f(make_int4(a.y, b.x, a.z, a.w), rw, idx);
   for (int t = 1; t < b.y; t++) f(ldg4(lk.occ + b.z + t), rw, idx);
 }
@@ -590,17 +590,17 @@ __device__ __forceinline__ unsigned order_few(Few& t) {
 }
 
 __device__ __forceinline__ void one_pair(const ScoreParams& P, int xw, int xp, int xe, int yw, int yp, int ye, int l1,
-                                         int l2, double p1, double& acc) {
+                                         int l2, double p1, double& acc, int n_erased) {
   if (xw != yw) return;
   double t;
-  if (pair_term(P, xw, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < P.n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
+  if (pair_term(P, xw, xp, xe, yp, ye, l1, l2, p1, t)) acc = (xw < n_erased) ? __dsub_rn(acc, t) : __dadd_rn(acc, t);
 }
 
 // Per-read paired update for reads with <= kFew live placements per mate. For lists sorted in enumeration
 // order the plain x-major / y-minor loop with a same-walk filter IS the reference's order: walks ascend with
 // x, erased walks (subtract) precede added ones (add). Returns false if the read needs the scratch path.
 template <bool kCompact = false, class E0 = uint32_t, class E1 = uint32_t>
-__device__ __forceinline__ bool paired_read_with(const ScoreParams& P, const E0& lk0, const E1& lk1, int r, double& acc) {
+__device__ __forceinline__ bool paired_read_with(const ScoreParams& P, const E0& lk0, const E1& lk1, int r, double& acc, int n_erased) {
   Few a, b;
   const uint32_t ll = __ldg((kCompact ? P.clens : P.lens) + r);   // r is the list index k in the compact variant
   scan_two<kCompact>(P.m[0], lk0, r, a);
@@ -616,14 +616,14 @@ __device__ __forceinline__ bool paired_read_with(const ScoreParams& P, const E0&
     const double p1 = align_prob(P.m[0], a.edor[x], l1);
 #pragma unroll
     for (int y = 0; y < kFew; y++)
-      if ((vb >> y) & 1u) one_pair(P, a.walk[x], a.pos[x], a.edor[x], b.walk[y], b.pos[y], b.edor[y], l1, l2, p1, acc);
+      if ((vb >> y) & 1u) one_pair(P, a.walk[x], a.pos[x], a.edor[x], b.walk[y], b.pos[y], b.edor[y], l1, l2, p1, acc, n_erased);
   }
   return true;
 }
 
 template <bool kCompact = false>
 __device__ __forceinline__ bool paired_read(const ScoreParams& P, int r, double& acc) {
-  return paired_read_with<kCompact>(P, P.epoch, P.epoch, r, acc);
+  return paired_read_with<kCompact>(P, P.epoch, P.epoch, r, acc, P.n_erased);
 }
 
 // Level-batched form of paired_read for the shapes the ordered paths mostly see (incremental evaluations, where a
@@ -711,7 +711,7 @@ __device__ __forceinline__ int paired_read_fast(const ScoreParams& P, int r, dou
 #pragma unroll
     for (int y = 0; y < kFew; y++)
       if ((vb >> y) & 1u)
-        one_pair(P, t[0].walk[x], t[0].pos[x], t[0].edor[x], t[1].walk[y], t[1].pos[y], t[1].edor[y], l1, l2, p1, acc);
+        one_pair(P, t[0].walk[x], t[0].pos[x], t[0].edor[x], t[1].walk[y], t[1].pos[y], t[1].edor[y], l1, l2, p1, acc, P.n_erased);
   }
   return 1;
 }
@@ -744,7 +744,7 @@ __device__ int gather_short(const MateView& mv, const E& epoch, int r, Plc* out)
   return n;
 }
 
-__device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int n2, int l1, int l2, double acc) {
+__device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int n2, int l1, int l2, double acc, int n_erased) {
   sort_by_ord(a, n1);
   sort_by_ord(b, n2);
   // per-walk de-dup (lists are walk-major after the sort)
@@ -765,7 +765,7 @@ __device__ double apply_pairs(const ScoreParams& P, Plc* a, int n1, Plc* b, int 
   }
   for (int x = 0; x < m1; x++) {
     const double p1 = align_prob(P.m[0], a[x].edor, l1);
-    for (int y = 0; y < m2; y++) one_pair(P, a[x].walk, a[x].pos, a[x].edor, b[y].walk, b[y].pos, b[y].edor, l1, l2, p1, acc);
+    for (int y = 0; y < m2; y++) one_pair(P, a[x].walk, a[x].pos, a[x].edor, b[y].walk, b[y].pos, b[y].edor, l1, l2, p1, acc, n_erased);
   }
   return acc;
 }
@@ -1639,7 +1639,7 @@ __device__ __forceinline__ bool paired_read_any(const ScoreParams& P, int r, uin
   Plc* b = a + n1;
   gather_short(P.m[0], P.epoch, r, a);
   gather_short(P.m[1], P.epoch, r, b);
-  acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc);
+  acc = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, acc, P.n_erased);
   return true;
 }
 
@@ -2164,84 +2164,192 @@ __global__ void __launch_bounds__(kBatchMaxLen) batch_prefix_kernel(const BatchP
   o[4] = bad;
 }
 
-// Second sum: one thread per mate-1 record under a key the candidate touches. The thread whose record is the
-// FIRST such record of its read (smallest arena index) owns the read for this candidate — no claim words, so
-// different candidates can share a read in the same launch.
+// Second sum: a block per candidate (per kBatchSlice-record slice of a large one) over the mate-1 records under the keys the candidate touches. The candidate's own
+// tables — touched ranges, sorted key ids and slot words of both mates — are staged in shared memory once, so a record
+// costs its arena word, the read's FastPair, its value and one term-table entry; the thread whose record is the FIRST
+// touched record of its read owns the read (no claim words: different candidates share reads in the same launch), and a
+// fast read has only the one. The candidate's sums are reduced in the block and stored, no global atomics.
+constexpr int kCandKeys = 192;     // keys per mate staged in shared memory (more: looked up in global memory)
+constexpr int kCandRanges = 256;
 __global__ void __launch_bounds__(kBlock) batch_touch_kernel(const ScoreParams P, const BatchParams B) {
-  const uint32_t total = __ldg(B.range_prefix + B.n_ranges);
+  if ((int)blockIdx.x >= B.n_blocks) return;
+  const Int2 blk = B.blocks[blockIdx.x];   // {candidate, first record of this block's slice}
+  const int c = blk.x;
+  const BatchCand cd = B.cands[c];
   const double2* log_tab = static_cast<const double2*>(P.log_tab);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int lo = 0, hi = B.n_ranges;   // largest t with prefix[t] <= i
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(B.range_prefix + mid) <= i) lo = mid; else hi = mid;
-    }
-    const int c = __ldg(B.range_cand + lo);
-    const BatchCand cd = B.cands[c];
-    const uint32_t ai = B.ranges[lo].begin + (i - __ldg(B.range_prefix + lo));
-    const int r = ldg4(P.arena1 + ai).x;
-    CandLookup lk0{B.keys[0] + cd.key_begin[0], cd.key_count[0], static_cast<const int4*>(B.slot_a[0]) + cd.key_begin[0],
-                   static_cast<const int4*>(B.slot_b[0]) + cd.key_begin[0], B.occ[0]};
-    CandLookup lk1{B.keys[1] + cd.key_begin[1], cd.key_count[1], static_cast<const int4*>(B.slot_a[1]) + cd.key_begin[1],
-                   static_cast<const int4*>(B.slot_b[1]) + cd.key_begin[1], B.occ[1]};
-    {   // ownership: is there an earlier record of this read under a key of this candidate?
-      const MateView& mv = P.m[0];
-      const int4 f = ldg4(static_cast<const int4*>(mv.first) + r);
-      int cnt = (f.z >> 16) & 0x3fff;
-      const uint32_t base = (uint32_t)f.w;
-      if (cnt == 0x3fff) cnt = (int)(__ldg(mv.rowptr + r + 1) - base);
-      const RowShort* rows = static_cast<const RowShort*>(mv.rows);
-      bool owner = true;
-      for (int k = 0; k < cnt; k++) {
-        const int4 rw = ldg4(rows + base + k);
-        if ((uint32_t)rw.w >= ai) break;   // rows are in arena order
-        int l2 = 0, h2 = lk0.n;
-        while (l2 < h2) {
-          const int mid = (l2 + h2) >> 1;
-          if (__ldg(lk0.keys + mid) < rw.x) l2 = mid + 1; else h2 = mid;
-        }
-        if (l2 < lk0.n && __ldg(lk0.keys + l2) == rw.x) { owner = false; break; }
+  __shared__ int s_keys[2][kCandKeys];
+  __shared__ int4 s_a[2][kCandKeys], s_b[2][kCandKeys];
+  __shared__ uint32_t s_prefix[kCandRanges + 1], s_begin[kCandRanges];
+  __shared__ long long s_acc[4];
+  const bool keys_in_shared = cd.key_count[0] <= kCandKeys && cd.key_count[1] <= kCandKeys;
+  const bool ranges_in_shared = cd.range_count <= kCandRanges;
+  if (threadIdx.x < 4) s_acc[threadIdx.x] = 0;
+  if (keys_in_shared) {
+    for (int m = 0; m < 2; m++)
+      for (int k = threadIdx.x; k < cd.key_count[m]; k += blockDim.x) {
+        s_keys[m][k] = __ldg(B.keys[m] + cd.key_begin[m] + k);
+        s_a[m][k] = __ldg(static_cast<const int4*>(B.slot_a[m]) + cd.key_begin[m] + k);
+        s_b[m][k] = __ldg(static_cast<const int4*>(B.slot_b[m]) + cd.key_begin[m] + k);
       }
-      if (!owner) continue;
+  }
+  const uint32_t p0 = __ldg(B.range_prefix + cd.range_begin);
+  if (ranges_in_shared)
+    for (int t = threadIdx.x; t <= cd.range_count; t += blockDim.x) {
+      s_prefix[t] = __ldg(B.range_prefix + cd.range_begin + t) - p0;
+      if (t < cd.range_count) s_begin[t] = B.ranges[cd.range_begin + t].begin;
     }
-    const double v0 = P.values[r];
-    double v1 = v0;
-    ScoreParams Q = P;   // the replay reads n_erased from the params
-    Q.n_erased = cd.n_erased;
-    if (!paired_read_with(Q, lk0, lk1, r, v1)) {
-      // many-placement read: same replay from a scratch allocation, inline (rare)
-      const int n1 = gather_short(P.m[0], lk0, r, nullptr), n2 = gather_short(P.m[1], lk1, r, nullptr);
-      const unsigned long long at = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
-      if (at + n1 + n2 > P.scratch_cap) {
-        atomicOr(P.error_flag, 2u);
-        continue;
-      }
-      Plc* a = P.scratch + at;
-      Plc* b = a + n1;
-      gather_short(P.m[0], lk0, r, a);
-      gather_short(P.m[1], lk1, r, b);
-      const uint32_t ll = __ldg(P.lens + r);
-      v1 = apply_pairs(Q, a, n1, b, n2, ll & 0xffff, ll >> 16, v0);
+  __syncthreads();
+  const uint32_t cand_total = __ldg(B.range_prefix + cd.range_begin + cd.range_count) - p0;
+  const uint32_t slice_begin = (uint32_t)blk.y, total = min(cand_total, slice_begin + (uint32_t)kBatchSlice);
+  CandLookup lk0{B.keys[0] + cd.key_begin[0], cd.key_count[0], static_cast<const int4*>(B.slot_a[0]) + cd.key_begin[0],
+                 static_cast<const int4*>(B.slot_b[0]) + cd.key_begin[0], B.occ[0]};
+  CandLookup lk1{B.keys[1] + cd.key_begin[1], cd.key_count[1], static_cast<const int4*>(B.slot_a[1]) + cd.key_begin[1],
+                 static_cast<const int4*>(B.slot_b[1]) + cd.key_begin[1], B.occ[1]};
+  if (keys_in_shared) {   // the general replay searches the staged copies too
+    lk0.keys = s_keys[0]; lk0.a = s_a[0]; lk0.b = s_b[0];
+    lk1.keys = s_keys[1]; lk1.a = s_a[1]; lk1.b = s_b[1];
+  }
+  auto find_key = [&](int m, int key) {   // index of `key` among the candidate's keys of mate m, or -1
+    const int n = cd.key_count[m];
+    int l = 0, h = n;
+    if (keys_in_shared) {
+      while (l < h) { const int mid = (l + h) >> 1; if (s_keys[m][mid] < key) l = mid + 1; else h = mid; }
+      return (l < n && s_keys[m][l] == key) ? l : -1;
     }
-    if (v1 == v0) continue;   // bit-identical value: identical term
+    const int* keys = B.keys[m] + cd.key_begin[m];
+    while (l < h) { const int mid = (l + h) >> 1; if (__ldg(keys + mid) < key) l = mid + 1; else h = mid; }
+    return (l < n && __ldg(keys + l) == key) ? l : -1;
+  };
+  long long sum_lo = 0, sum_hi = 0, d_floored = 0, n_bad = 0;
+  auto locate = [&](uint32_t i, uint32_t& ai) {   // i-th touched record of the candidate -> arena index
+    int lo = 0, hi = cd.range_count;   // largest t with prefix[t] <= i
+    if (ranges_in_shared) {
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= i) lo = mid; else hi = mid; }
+      ai = s_begin[lo] + (i - s_prefix[lo]);
+    } else {
+      const uint32_t* pre = B.range_prefix + cd.range_begin;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(pre + mid) - p0 <= i) lo = mid; else hi = mid; }
+      ai = B.ranges[cd.range_begin + lo].begin + (i - (__ldg(pre + lo) - p0));
+    }
+  };
+  auto account = [&](int r, double v0, double v1) {   // the read's term at the candidate's total length: new - old
+    if (v1 == v0) return;   // bit-identical value: identical term
     const uint32_t ll = __ldg(P.lens + r);
     const int cls = __ldg(B.len_class + (ll & 0xffff) + (ll >> 16));
     const double pstar = __ldg(B.pstar + (size_t)cls * B.n_len + cd.len_index);
     const long long qthr = __ldg(B.qthr_cls + cls);
     const TermAt t0 = term_at(log_tab, v0, pstar, qthr), t1 = term_at(log_tab, v1, pstar, qthr);
-    long long* acc = B.accum_cand + (size_t)c * 4;
     if (!t0.odd && !t1.odd) {
       const long long dq = t1.q - t0.q;   // |q| < 2^62: no overflow
-      if (dq != 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)(uint32_t)dq);          // low 32 bits
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), (unsigned long long)(dq >> 32));        // high part, signed
-      }
+      sum_lo += (long long)(uint32_t)dq;   // low 32 bits
+      sum_hi += dq >> 32;                  // high part, signed
     } else {
-      atomicAdd(reinterpret_cast<unsigned long long*>(acc + 3), 1ull);   // non-finite term: reported as nan
+      n_bad++;   // non-finite term: reported as nan
     }
-    if (t1.floored != t0.floored)
-      atomicAdd(reinterpret_cast<unsigned long long*>(acc + 2), (unsigned long long)(long long)(t1.floored - t0.floored));
+    d_floored += t1.floored - t0.floored;
+  };
+  // Chunks of the candidate's records, two passes each: (A) every record — fast reads are finished on the spot, the others
+  // are queued; (B) the queue, densely: the general replay is ~10x a fast read's work, and taken lane by lane inside pass A
+  // it would make every warp pay for it on every trip.
+  constexpr int kChunk = 2048;
+  __shared__ uint32_t s_queue[kChunk];
+  __shared__ int s_qn;
+  const bool fast_path = P.fast && P.tq && B.partner12;
+  for (uint32_t chunk = slice_begin; chunk < total; chunk += kChunk) {
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    const uint32_t chunk_end = min(total, chunk + (uint32_t)kChunk);
+    for (uint32_t i = chunk + threadIdx.x; i < chunk_end; i += blockDim.x) {
+      uint32_t ai;
+      locate(i, ai);
+      const int r = ldg4(P.arena1 + ai).x;
+      bool done = false;
+      if (fast_path) {
+        // a FAST read (one record per mate under one key, term resolved at commit — FastPair): its only mate-1 record is
+        // the one this thread holds, and the replay is "T leaves / enters per occurrence of the key in the candidate's
+        // erased / added walks" exactly like delta_fast, from the candidate's own key tables
+        const uint4 f = __ldg(static_cast<const uint4*>(P.fast) + r);
+        if ((f.x >> 31) == 0u) {
+          if (((f.x >> 30) & 1u) != 0u) continue;   // a mate without any record: no pair term, nothing changes
+          const int k1 = (int)(f.x & 0x3fffffffu), k2 = __ldg(B.partner12 + k1);
+          const int i1 = find_key(0, k1), i2 = k2 >= 0 ? find_key(1, k2) : -1;
+          if (i1 < 0 || i2 < 0) continue;   // the key is not in this candidate's walks for one of the mates: no pair term changes
+          const int4 a1 = lk0.a[i1], b1 = lk0.b[i1], a2 = lk1.a[i2], b2 = lk1.b[i2];
+          if (b1.y == b2.y && b1.y <= 2) {
+            int4 o1 = make_int4(a1.y, 0, a1.z, a1.w), o2 = make_int4(a2.y, 0, a2.z, a2.w);   // {walk, -, cur_pos, skip_below}
+            int4 q1 = o1, q2 = o2;
+            bool ok = o1.x == o2.x;
+            if (b1.y == 2) {
+              q1 = ldg4(lk0.occ + b1.z + 1);
+              q2 = ldg4(lk1.occ + b2.z + 1);
+              ok = ok && q1.x != o1.x && q1.x == q2.x;   // (the key twice in ONE walk: the general path)
+            }
+            if (ok) {
+              const int4 te = __ldg(static_cast<const int4*>(P.tq) + f.w);
+              const double t = __hiloint2double(te.y, te.x);
+              const int pos1 = (int)f.y, pos2 = (int)f.z;
+              const double v0 = P.values[r];
+              double v1 = v0;
+              if (wrap_add(pos1, o1.z) >= o1.w && wrap_add(pos2, o2.z) >= o2.w) v1 = o1.x < cd.n_erased ? __dsub_rn(v1, t) : __dadd_rn(v1, t);
+              if (b1.y == 2 && wrap_add(pos1, q1.z) >= q1.w && wrap_add(pos2, q2.z) >= q2.w)
+                v1 = q1.x < cd.n_erased ? __dsub_rn(v1, t) : __dadd_rn(v1, t);
+              account(r, v0, v1);
+              done = true;
+            }
+          }
+        }
+      }
+      if (!done) s_queue[atomicAdd(&s_qn, 1)] = i;
+    }
+    __syncthreads();
+    const int qn = s_qn;
+    for (int q = threadIdx.x; q < qn; q += blockDim.x) {
+      uint32_t ai;
+      locate(s_queue[q], ai);
+      const int r = ldg4(P.arena1 + ai).x;
+      {   // ownership: is there an earlier record of this read under a key of this candidate?
+        const MateView& mv = P.m[0];
+        const int4 f = ldg4(static_cast<const int4*>(mv.first) + r);
+        int cnt = (f.z >> 16) & 0x3fff;
+        const uint32_t base = (uint32_t)f.w;
+        if (cnt == 0x3fff) cnt = (int)(__ldg(mv.rowptr + r + 1) - base);
+        const RowShort* rows = static_cast<const RowShort*>(mv.rows);
+        bool owner = true;
+        for (int k = 0; k < cnt; k++) {
+          const int4 rw = ldg4(rows + base + k);
+          if ((uint32_t)rw.w >= ai) break;   // rows are in arena order
+          if (find_key(0, rw.x) >= 0) { owner = false; break; }
+        }
+        if (!owner) continue;
+      }
+      const double v0 = P.values[r];
+      double v1 = v0;
+      if (!paired_read_with(P, lk0, lk1, r, v1, cd.n_erased)) {
+        // many-placement read: same replay from a scratch allocation, inline (rare)
+        const int n1 = gather_short(P.m[0], lk0, r, nullptr), n2 = gather_short(P.m[1], lk1, r, nullptr);
+        const unsigned long long at = atomicAdd(P.scratch_cursor, (unsigned long long)(n1 + n2));
+        if (at + n1 + n2 > P.scratch_cap) {
+          atomicOr(P.error_flag, 2u);
+          continue;
+        }
+        Plc* a = P.scratch + at;
+        Plc* b = a + n1;
+        gather_short(P.m[0], lk0, r, a);
+        gather_short(P.m[1], lk1, r, b);
+        const uint32_t ll = __ldg(P.lens + r);
+        v1 = apply_pairs(P, a, n1, b, n2, ll & 0xffff, ll >> 16, v0, cd.n_erased);
+      }
+      account(r, v0, v1);
+    }
+    __syncthreads();
   }
+  if (sum_lo) atomicAdd(reinterpret_cast<unsigned long long*>(&s_acc[0]), (unsigned long long)sum_lo);
+  if (sum_hi) atomicAdd(reinterpret_cast<unsigned long long*>(&s_acc[1]), (unsigned long long)sum_hi);
+  if (d_floored) atomicAdd(reinterpret_cast<unsigned long long*>(&s_acc[2]), (unsigned long long)d_floored);
+  if (n_bad) atomicAdd(reinterpret_cast<unsigned long long*>(&s_acc[3]), (unsigned long long)n_bad);
+  __syncthreads();
+  if (threadIdx.x < 4 && s_acc[threadIdx.x])   // (a candidate with many touched records is spread over several blocks)
+    atomicAdd(reinterpret_cast<unsigned long long*>(B.accum_cand + (size_t)c * 4 + threadIdx.x), (unsigned long long)s_acc[threadIdx.x]);
 }
 
 // out[c] = {integer part, 2^-40 units, floored, -inf terms, nan terms, flags} like finalize_kernel.
@@ -3054,6 +3162,12 @@ cudaError_t compact_copy(const uint32_t* list, int n_complex, const uint32_t* ro
 
 void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_records, double* out, const uint32_t* error_flag,
                   int sm_count, cudaStream_t st) {
+  // GAML_B200_BATCH_TIMING=1 (measurement aid): per-kernel device times of the batch on stderr
+  static const bool timing = getenv("GAML_B200_BATCH_TIMING") != nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (timing)
+    for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], st);
   // base pass: chunks of at most kBatchMaxLen distinct lengths, each with its own nb + 1 bins
   const int gx = grid_for((size_t)P.n_reads, kBlock, sm_count, 4);
   int chunk = 0;
@@ -3061,13 +3175,25 @@ void launch_batch(const ScoreParams& P, const BatchParams& B, uint32_t n_touch_r
     const int nb = B.n_len - j0 < kBatchMaxLen ? B.n_len - j0 : kBatchMaxLen;
     batch_base_kernel<<<gx, kBlock, 0, st>>>(P, B, j0, nb, (size_t)chunk * (kBatchMaxLen + 1));
   }
+  if (timing) cudaEventRecord(ev[1], st);
   chunk = 0;
   for (int j0 = 0; j0 < B.n_len; j0 += kBatchMaxLen, chunk++) {
     const int nb = B.n_len - j0 < kBatchMaxLen ? B.n_len - j0 : kBatchMaxLen;
     batch_prefix_kernel<<<1, kBatchMaxLen, 0, st>>>(B, j0, nb, (size_t)chunk * (kBatchMaxLen + 1));
   }
-  if (n_touch_records > 0) batch_touch_kernel<<<grid_for(n_touch_records, kBlock, sm_count, 8), kBlock, 0, st>>>(P, B);
+  if (timing) cudaEventRecord(ev[2], st);
+  if (n_touch_records > 0 && B.n_blocks > 0) batch_touch_kernel<<<B.n_blocks, kBlock, 0, st>>>(P, B);   // a block per slice of a candidate's records
+  if (timing) cudaEventRecord(ev[3], st);
   batch_finalize_kernel<<<(B.n_cand + 127) / 128, 128, 0, st>>>(B, out, error_flag, (long long)P.n_reads);
+  if (timing) {
+    cudaEventRecord(ev[4], st);
+    cudaEventSynchronize(ev[4]);
+    float t[4];
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+    fprintf(stderr, "[gaml_b200 batch] n_len %d: base %.3f ms, prefix %.3f ms, touch %.3f ms (%u records), finalize %.3f ms\n", B.n_len, t[0], t[1],
+            t[2], n_touch_records, t[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
 }
 int batch_hist_bins(int n_len) { return ((n_len + kBatchMaxLen - 1) / kBatchMaxLen) * (kBatchMaxLen + 1); }
 int batch_launches(int n_len, bool touch) { return 2 * ((n_len + kBatchMaxLen - 1) / kBatchMaxLen) + (touch ? 1 : 0) + 1; }
