@@ -3,7 +3,7 @@
 //
 // A scalar CPU restatement of the GAML assembly-likelihood hot path, written from the behaviour of
 // the reference (usamec/GAML) and pinned against the reference's own compiled code (oracle/_ref,
-// see tests/test_oracle_vs_ref.py and tests/golden/). Each routine cites the reference lines it
+// see tests/test_oracle.py and tests/golden/). Each routine cites the reference lines it
 // restates. Same CLI and file formats as oracle/ref_harness.cc:
 //
 //   gaml_oracle <workload GAMLWL1> <results GAMLRS1> [dump=0|1] [repeat=1]
