@@ -432,13 +432,18 @@ def main():
         part, tl = pc.calc_prob_partial_flat(fw)
         return pc.combine(part[None, :], 1, tl)   # the C ABI's walk layout: host int32 ids + int64 offsets (what a C++ caller holds)
 
-    def full_step_e2e():
+    # e2e alternates between the start walk set and the one a single annealing move later: every step is a full evaluation of
+    # a walk list that differs from the one evaluated before it, so the library flattens it and uploads its slot tables
+    # each time (an unchanged list would find its tables on the device already: reported separately as e2e_same_walks)
+    flat_alt = api.FlatWalks(wl.evals[1]) if len(wl.evals) > 1 else flat0
+
+    def full_step_e2e(fw=None):
         """(wall seconds of the C-ABI call incl. the exchange + combine, result); reset, L2 flush and the rendezvous are outside."""
         pc.reset_state()
         flush_l2()
         rendezvous()
         t0 = time.perf_counter()
-        res = eval_all_ranks(flat0)
+        res = eval_all_ranks(fw if fw is not None else flat0)
         return time.perf_counter() - t0, res
 
     # ---- value: device-resident inputs, CUDA events, L2 flushed between steps ----
@@ -484,18 +489,31 @@ def main():
     a_total = sum_over_ranks(float(a_local))
 
     # ---- e2e: host walks in, host result out, wall clock, exchange included ----
-    for _ in range(args.warmup):
-        full_step_e2e()
+    for k in range(args.warmup + (args.warmup & 1)):
+        full_step_e2e(flat_alt if k & 1 else flat0)
     barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        dt, (prob, zeros, tl_full) = full_step_e2e()
+    e2e_s, e2e_aln, h2d, prep_full_us = 0.0, 0.0, 0, 0.0
+    for k in range(args.steps):
+        dt, (prob_k, zeros_k, tl_k) = full_step_e2e(flat_alt if k & 1 else flat0)
         e2e_s += max_over_ranks(dt)
+        st = pc.stats()
+        e2e_aln += float(st.last_records_gathered)
+        h2d = max(h2d, int(st.last_h2d_bytes))
+        prep_full_us += st.last_prepare_host_us / args.steps
+        if not k & 1:
+            prob, zeros, tl_full = prob_k, zeros_k, tl_k
+    barrier()
+    e2e_aln = sum_over_ranks(e2e_aln)
+    d2h = pc.stats().last_d2h_bytes
+    # the same walk set over and over (what `value` evaluates): its slot tables are on the device already
+    same_s = 0.0
+    full_step_e2e(flat0)
+    for _ in range(max(args.steps // 2, 1)):
+        dt, _res = full_step_e2e(flat0)
+        same_s += max_over_ranks(dt)
+    same_steps = max(args.steps // 2, 1)
     barrier()
     clocks = sampler.stop()
-    st = pc.stats()
-    h2d, d2h = st.last_h2d_bytes, st.last_d2h_bytes
-    prep_full_us = st.last_prepare_host_us
 
     # ---- incremental evaluations of the annealing loop (delta kernel + O(R) pass), ranks in lockstep ----
     pc.reset_state()
@@ -505,10 +523,18 @@ def main():
     barrier()
     only0 = pc.stats().delta_only_evals
     t0 = time.perf_counter()
-    for nodes_offs in seq_flat:
+    slow_evals = []
+    for k_eval, nodes_offs in enumerate(seq_flat):
+        t_e = time.perf_counter()
         eval_all_ranks(nodes_offs)
+        if time.perf_counter() - t_e > 1e-3:
+            s_ = pc.stats()
+            slow_evals.append((k_eval, round((time.perf_counter() - t_e) * 1e3, 2), round(s_.last_prepare_host_us), round(s_.last_launch_host_us),
+                               round(s_.last_finish_host_us), int(s_.last_was_full)))
     barrier()
     delta_s = max_over_ranks(time.perf_counter() - t0)
+    if slow_evals:
+        log(f"[rank {rank}] incremental evaluations over 1 ms (index, ms, prepare/launch/finish us, full): {slow_evals[:8]}")
     delta_only = pc.stats().delta_only_evals - only0
     # the same trajectory once more, untimed, reading the library's per-evaluation device time and counters
     pc.reset_state()
@@ -574,11 +600,15 @@ def main():
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps, "kernel_ms_median": ker_list[len(ker_list) // 2], "kernel_ms_min": ker_list[0], "kernel_ms_max": ker_list[-1],
                      "timing": f"CUDA events around the streaming kernel (rare shapes + tier 1 + tier 2, one launch) on the library stream, {args.steps} extra "
                                "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
-        "e2e": {"value": a_total * args.steps / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": e2e_aln / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps, "host_prepare_us": prep_full_us,
                 "note": "gaml_calc_prob_partial (N=1) / gaml_calc_prob_gathered (N>1, the exchange included) + exact combine: host walk arrays in, "
-                        "score out, wall clock per step (max over ranks), L2 flushed between steps, ranks released together after the flush; "
-                        "the alignment cache is resident state like the reference's aligment_cache_"},
+                        "score out, wall clock per step (max over ranks), L2 flushed between steps, ranks released together after the flush; the "
+                        "steps alternate between two walk sets one annealing move apart, so every step flattens its walks and uploads their slot "
+                        "tables (h2d_bytes_per_step); the alignment cache is resident state like the reference's aligment_cache_"},
+        "e2e_same_walks": {"value": a_total * same_steps / same_s, "unit": "alignments/s", "ms_per_step": 1e3 * same_s / same_steps,
+                           "note": "the same call on the walk set evaluated last (a fresh ScoringState over unchanged walks): the set's slot tables "
+                                   "are still on the device, nothing is flattened or uploaded"},
         "gpu_launches": int(launches),
         "device_timeline_us": timeline,
         "ordered_paths_per_full_eval": full_overflow_reads,

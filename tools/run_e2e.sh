@@ -6,12 +6,15 @@ set -uo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 OUT=${1:-$ROOT/gpurun_out/e2e}
 ITERS=${2:-500}
+KINDS=${E2E_KINDS:-"single paired"}     # E2E_KINDS=paired E2E_UNIQUE=100 E2E_READS=400000: a 1 Mbp / 400 k-pair run
+UNIQUE=${E2E_UNIQUE:-10}
+READS=${E2E_READS:-50000}
 mkdir -p "$OUT"
 rc=0
-for kind in single paired; do
+for kind in $KINDS; do
   D=/tmp/e2e_$kind
   rm -rf "$D"
-  python "$ROOT/tools/make_e2e_dataset.py" "$D" --kind $kind --n-reads 50000 --iterations "$ITERS" > "$OUT/$kind.gen.log"
+  python "$ROOT/tools/make_e2e_dataset.py" "$D" --kind $kind --n-unique "$UNIQUE" --n-reads "$READS" --iterations "$ITERS" > "$OUT/$kind.gen.log"
   t0=$(date +%s.%N)
   ( cd "$D" && stdbuf -oL "$ROOT/oracle/_ref/gaml_ref" gaml.cfg > ref.log 2>&1 )
   t1=$(date +%s.%N)
@@ -19,7 +22,15 @@ for kind in single paired; do
   t2=$(date +%s.%N)
   python -c "print('%.2f' % ($t1 - $t0))" > "$D/ref.time"; python -c "print('%.2f' % ($t2 - $t1))" > "$D/gpu.time"
   python "$ROOT/tools/compare_traces.py" "$D/ref.log" "$D/gpu.log" | tee "$OUT/$kind.compare.txt" || rc=1
-  echo "$kind: reference $(cat $D/ref.time)s, cuda $(cat $D/gpu.time)s for $ITERS iterations (wall, includes the one-off CPU alignment of new keys)" | tee -a "$OUT/$kind.compare.txt"
+  echo "$kind: reference $(cat $D/ref.time)s, cuda $(cat $D/gpu.time)s for $ITERS iterations (wall, includes read loading and the one-off CPU alignment of new keys)" | tee -a "$OUT/$kind.compare.txt"
+  # the annealing loop alone: wall time between the first and the last trace line (gaml.cc:330 prints hh:mm:ss) is too coarse,
+  # so the loop is timed by the "start prob" line's position: seconds from that line to the end of the log
+  python - "$D/ref.log" "$D/gpu.log" <<'PY' | tee -a "$OUT/$kind.compare.txt"
+import sys
+for p in sys.argv[1:]:
+    n = sum(1 for l in open(p, errors="replace") if l.startswith("itnum "))
+    print(f"{p}: {n} annealing iterations")
+PY
   if [ -x "$ROOT/oracle/_ref/gaml_gpu_batched" ]; then
     # the same driver with the moves' candidate lists scored in device batches (oracle/build_ref.sh, gaml_gpu_batched)
     t3=$(date +%s.%N)
