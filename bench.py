@@ -236,7 +236,9 @@ def reference_arm(args):
     n_procs = max(1, min(cores, 64))
     kind = workload_kind(args, world)
     # the job's workload is `world` shards; the CPU scores shard 0 of it as the bounded sample (a rate, not a total)
-    wl, _ = make_workload(world, 0, 1, scale=args.scale, kind=kind)
+    wl, (lo, hi) = make_workload(world, 0, 1, scale=args.scale, kind=kind)
+    assert lo == 0
+    wl.sets[0].n_reads = hi - lo     # rank 0's shard holds reads [0, hi): read ids and the length arrays are already local
     with tempfile.TemporaryDirectory() as tmp:
         per_step, aligns, kind_cpu = run_cpu(wl, n_procs, args.steps + args.warmup, tmp)
     timed = per_step[args.warmup:]
@@ -435,7 +437,10 @@ def main():
     # e2e alternates between the start walk set and the one a single annealing move later: every step is a full evaluation of
     # a walk list that differs from the one evaluated before it, so the library flattens it and uploads its slot tables
     # each time (an unchanged list would find its tables on the device already: reported separately as e2e_same_walks)
-    flat_alt = api.FlatWalks(wl.evals[1]) if len(wl.evals) > 1 else flat0
+    alt = next((w for w in wl.evals[1:] if w != walks0), None)   # (a scripted move can be a no-op: take the first list that differs)
+    if alt is None:
+        raise RuntimeError("the workload's trajectory never leaves the start walks: e2e needs a second walk set")
+    flat_alt = api.FlatWalks(alt)
 
     def full_step_e2e(fw=None):
         """(wall seconds of the C-ABI call incl. the exchange + combine, result); reset, L2 flush and the rendezvous are outside."""

@@ -1,16 +1,17 @@
 #!/bin/bash
-# N=8 exchange A/B on the whole of config 4 (run with gpurun --gpus 8)
 mkdir -p gpurun_out
-for ex in peer host nccl; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 --exchange $ex --delta-steps 100 --batch 1024 > gpurun_out/bench_n8_$ex.json 2> gpurun_out/bench_n8_$ex.err
-  echo "exchange $ex rc=$?"
-  grep -v "^\[W\|^W1\|^\*\*\*\|Setting OMP" gpurun_out/bench_n8_$ex.err | tail -3
-  python - <<PY
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
+echo "n8 rc=$?"
+grep -v "^\[W\|^W1\|^\*\*\*\|Setting OMP" gpurun_out/r02_bench_n8.err | tail -4
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29532 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > gpurun_out/r02_bench_n8_reference.json 2>/dev/null
+echo "n8 ref rc=$?"
+python - <<'PY'
 import json
-try:
-    d=json.load(open('gpurun_out/bench_n8_$ex.json'))
-    print('$ex', 'value', d['value'], 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'kernel_ms', d['roofline']['kernel_ms'], 'e2e_ms', d['e2e']['ms_per_step'], 'prep_us', d['e2e']['host_prepare_us'], 'inc_e2e_ms', d['incremental']['e2e_ms_per_eval'], 'inc_dev_ms', d['incremental']['device_ms_per_eval'], 'inc_prep', d['incremental']['host_prepare_us_per_eval'], 'batch_ms', d['batch']['ms_per_batch'], 'prob', d['result'])
-except Exception as e:
-    print('$ex failed', e)
+for f in ('r02_bench_n8','r02_bench_n8_reference'):
+    d=json.load(open(f'gpurun_out/{f}.json'))
+    for k in ('value','ms_per_step','value_incl_exchange','e2e','e2e_same_walks','sa_iters_per_s','incremental','batch','config'):
+        v=d.get(k)
+        if isinstance(v,dict): v={kk:vv for kk,vv in v.items() if kk not in ('note','mix')}
+        print(f, k, str(v)[:330])
+    if d.get('roofline'): print(f, 'frac', d['roofline']['frac'], d['roofline']['kernel_ms'])
 PY
-done
