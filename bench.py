@@ -437,10 +437,15 @@ def main():
     # e2e alternates between the start walk set and the one a single annealing move later: every step is a full evaluation of
     # a walk list that differs from the one evaluated before it, so the library flattens it and uploads its slot tables
     # each time (an unchanged list would find its tables on the device already: reported separately as e2e_same_walks)
-    alt = next((w for w in wl.evals[1:] if w != walks0), None)   # (a scripted move can be a no-op: take the first list that differs)
-    if alt is None:
+    alts = []
+    for w in wl.evals[1:]:   # (a scripted move can be a no-op: take lists that differ from the start list and from each other)
+        if w != walks0 and all(w != a for a in alts):
+            alts.append(w)
+        if len(alts) == 3:
+            break
+    if not alts:
         raise RuntimeError("the workload's trajectory never leaves the start walks: e2e needs a second walk set")
-    flat_alt = api.FlatWalks(alt)
+    e2e_cycle = [flat0] + [api.FlatWalks(a) for a in alts]
 
     def full_step_e2e(fw=None):
         """(wall seconds of the C-ABI call incl. the exchange + combine, result); reset, L2 flush and the rendezvous are outside."""
@@ -494,19 +499,27 @@ def main():
     a_total = sum_over_ranks(float(a_local))
 
     # ---- e2e: host walks in, host result out, wall clock, exchange included ----
-    for k in range(args.warmup + (args.warmup & 1)):
-        full_step_e2e(flat_alt if k & 1 else flat0)
+    n_cyc = len(e2e_cycle)
+    for k in range(-(-args.warmup // n_cyc) * n_cyc):
+        full_step_e2e(e2e_cycle[k % n_cyc])
     barrier()
-    e2e_s, e2e_aln, h2d, prep_full_us = 0.0, 0.0, 0, 0.0
+    e2e_s, e2e_aln, h2d, h2d_max, prep_full_us = 0.0, 0.0, 0, 0, 0.0
+    st0 = pc.stats()
     for k in range(args.steps):
-        dt, (prob_k, zeros_k, tl_k) = full_step_e2e(flat_alt if k & 1 else flat0)
+        dt, (prob_k, zeros_k, tl_k) = full_step_e2e(e2e_cycle[k % n_cyc])
         e2e_s += max_over_ranks(dt)
         st = pc.stats()
         e2e_aln += float(st.last_records_gathered)
-        h2d = max(h2d, int(st.last_h2d_bytes))
+        h2d += int(st.last_h2d_bytes)
+        h2d_max = max(h2d_max, int(st.last_h2d_bytes))
         prep_full_us += st.last_prepare_host_us / args.steps
-        if not k & 1:
+        if k % n_cyc == 0:
             prob, zeros, tl_full = prob_k, zeros_k, tl_k
+    st1 = pc.stats()
+    e2e_how = {"walk_lists_cycled": n_cyc, "patched": int(st1.full_patch_evals - st0.full_patch_evals),
+               "tables_resident": int(st1.full_reuse_evals - st0.full_reuse_evals),
+               "all_walks_flattened": args.steps - int(st1.full_patch_evals - st0.full_patch_evals) - int(st1.full_reuse_evals - st0.full_reuse_evals)}
+    h2d = h2d // max(args.steps, 1)
     barrier()
     e2e_aln = sum_over_ranks(e2e_aln)
     d2h = pc.stats().last_d2h_bytes
@@ -517,6 +530,20 @@ def main():
         dt, _res = full_step_e2e(flat0)
         same_s += max_over_ranks(dt)
     same_steps = max(args.steps // 2, 1)
+    barrier()
+    # a list unrelated to the one on the device (the start list reversed, alternating with the start list): no alignment
+    # between consecutive lists, every walk is flattened and all slot updates are uploaded
+    flat_rev = api.FlatWalks(list(reversed(walks0)))
+    cold_s, cold_h2d, cold_steps = 0.0, 0, max(args.steps // 4, 2)
+    for k in range(cold_steps + 2):
+        dt, _res = full_step_e2e(flat0 if k & 1 else flat_rev)
+        if k >= 2:
+            cold_s += max_over_ranks(dt)
+            cold_h2d = max(cold_h2d, int(pc.stats().last_h2d_bytes))
+    cold_info = {"value": a_total * cold_steps / cold_s, "unit": "alignments/s", "ms_per_step": 1e3 * cold_s / cold_steps,
+                 "h2d_bytes_per_step": cold_h2d,
+                 "note": "the start list and its reverse in turn: consecutive lists do not align, all walks are flattened on the host"}
+    full_step_e2e(flat0)
     barrier()
     clocks = sampler.stop()
 
@@ -605,12 +632,16 @@ def main():
                      "algorithmic_bytes_per_launch": int(bytes_local), "kernel_ms": ker_ms / args.steps, "kernel_ms_median": ker_list[len(ker_list) // 2], "kernel_ms_min": ker_list[0], "kernel_ms_max": ker_list[-1],
                      "timing": f"CUDA events around the streaming kernel (rare shapes + tier 1 + tier 2, one launch) on the library stream, {args.steps} extra "
                                "steps after the timed region with gaml_set_profiling 2, L2 flushed between steps"},
-        "e2e": {"value": e2e_aln / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": e2e_aln / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "h2d_bytes_max": int(h2d_max), "full_evaluations": e2e_how,
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps, "host_prepare_us": prep_full_us,
                 "note": "gaml_calc_prob_partial (N=1) / gaml_calc_prob_gathered (N>1, the exchange included) + exact combine: host walk arrays in, "
                         "score out, wall clock per step (max over ranks), L2 flushed between steps, ranks released together after the flush; the "
-                        "steps alternate between two walk sets one annealing move apart, so every step flattens its walks and uploads their slot "
-                        "tables (h2d_bytes_per_step); the alignment cache is resident state like the reference's aligment_cache_"},
+                        "steps cycle through walk lists one to three annealing moves apart, so every step's list differs from the one evaluated before "
+                        "it; the library keeps the slot tables of one BASE list on the device and builds + uploads only the updates of the "
+                        "keys the changed walks look up (h2d_bytes_per_step = mean, full_evaluations = how each step was prepared); a list "
+                        "unrelated to the resident one flattens every walk: e2e_cold_list; the alignment cache is resident state like the "
+                        "reference's aligment_cache_"},
+        "e2e_cold_list": cold_info,
         "e2e_same_walks": {"value": a_total * same_steps / same_s, "unit": "alignments/s", "ms_per_step": 1e3 * same_s / same_steps,
                            "note": "the same call on the walk set evaluated last (a fresh ScoringState over unchanged walks): the set's slot tables "
                                    "are still on the device, nothing is flattened or uploaded"},

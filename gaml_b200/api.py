@@ -47,7 +47,7 @@ class Stats(C.Structure):
                 ("last_launch_host_us", C.c_double), ("last_finish_host_us", C.c_double),
                 ("last_scratch_placements", C.c_int64), ("last_multi_items", C.c_int64),
                 ("fast_change_evals", C.c_int64), ("delta_only_evals", C.c_int64), ("cache_appends", C.c_int64),
-                ("cache_rebuilds", C.c_int64)]
+                ("cache_rebuilds", C.c_int64), ("full_reuse_evals", C.c_int64), ("full_patch_evals", C.c_int64)]
 
 
 EXPORTS = ["gaml_ctx_create", "gaml_ctx_destroy", "gaml_last_error", "gaml_ctx_stream", "gaml_set_graph",

@@ -133,10 +133,10 @@ struct FlatCache {   // chained hash table keyed by walk content; the caller sup
 // Per-store accumulation of the occurrences of one evaluation.
 struct OccBuilder {
   std::vector<std::pair<int, Occ>> items;   // (key id, occurrence) in enumeration order
-  int next_seg = 0;
+  uint32_t next_seg = 0;                    // (the kernels order placements by seg as an unsigned number)
   void reset() { items.clear(); next_seg = 0; }
   void add(int key, int walk, int cur_pos, int skip_below) {
-    items.push_back({key, Occ{walk, next_seg++, cur_pos, skip_below}});
+    items.push_back({key, Occ{walk, (int)next_seg++, cur_pos, skip_below}});
   }
 };
 
@@ -155,6 +155,7 @@ struct MateStore {
   int table_index = -1;               // position in ctx->d_tables
   std::vector<uint32_t> key_stamp;    // group_occurrences scratch: epoch that last saw the key / its SlotUpdate index
   std::vector<int> key_slot, fill_cursor;
+  std::vector<int> base_slot;         // patched full evaluations: the key's SlotUpdate index in the resident base blob, -1 = none
   // cache append (kernels.cu "cache append"): the row array has slack behind the rows of the last full build, rows_tail is
   // the next free row; h_count = every read's record count (internal read index), kept in step by the host
   size_t rows_cap = 0, rows_tail = 0;
@@ -307,6 +308,29 @@ struct gaml_ctx {
   int full_n_updates = 0;
   size_t full_upd_off = 0, full_blob_bytes = 0;
   int64_t full_blob_reuses = 0;
+  // Patched full evaluation: a full re-score of a walk list a few walks away from the BASE list (the one the resident
+  // blob was built for) uploads only the slot updates of the keys those walks look up. Walks carry order-preserving labels
+  // with gaps ((base index + 1) << base_g; a walk that is not in the base list gets a label between its neighbours'), and
+  // a lookup's enumeration number is label << base_s | index inside the walk, so patched lists keep the reference's
+  // placement order without renumbering the resident entries. track[i] follows wsets[i].
+  struct ListTrack {
+    bool valid = false;
+    uint64_t base_gen = 0;
+    std::vector<uint32_t> label;   // per walk of the list
+    std::vector<int> removed;      // base walks that are not in the list (ascending base index)
+    int n_added = 0;               // walks of the list that are not base walks
+  };
+  ListTrack track[2];
+  bool patch_enabled = true;       // GAML_B200_NO_FULL_PATCH=1: every full evaluation of a changed list flattens all walks (tests)
+  bool base_valid = false;
+  uint64_t base_gen = 0;
+  int base_g = 3, base_s = 0;
+  WalkSet base_ws;                 // nodes / offs / hash of the base list
+  std::vector<SlotUpdate> full_updates;
+  std::vector<std::vector<Occ>> full_occs;
+  std::vector<std::vector<std::pair<int, int>>> base_mkeys;   // per set: (mate, key) of the base's keys with several occurrences
+  size_t patch_upd_off = 0, patch_skip_off = 0;               // the pending evaluation's patch inside d_full_blob
+  int n_patch = 0, n_skip = 0;
   void* h_blob = nullptr;         // pinned
   size_t h_blob_cap = 0;
   DevBuf d_flags, d_scratch, d_csr_temp, d_logtab;
@@ -657,7 +681,8 @@ void flatten_pacbio(const gaml_ctx* ctx, ReadSetState& rs, const Walk* walks, in
 // keys that occur several times (repeat nodes), their occurrences contiguous in enumeration order in the Occ array
 // — the kernels read occ[occ_begin + t] only for t >= 1, so single-occurrence keys need no Occ entry.
 // Counting pass over a per-key stamp table, no sort.
-void group_occurrences(OccBuilder& ob, MateStore& st, uint32_t epoch, std::vector<SlotUpdate>& updates, std::vector<Occ>& occ) {
+void group_occurrences(OccBuilder& ob, MateStore& st, uint32_t epoch, std::vector<SlotUpdate>& updates, std::vector<Occ>& occ,
+                       bool record_base = false) {
   occ.clear();
   if (st.key_stamp.size() < st.keys.size()) {
     st.key_stamp.resize(st.keys.size(), 0u);
@@ -669,6 +694,7 @@ void group_occurrences(OccBuilder& ob, MateStore& st, uint32_t epoch, std::vecto
     if (st.key_stamp[k] != epoch) {
       st.key_stamp[k] = epoch;
       st.key_slot[k] = (int)updates.size();
+      if (record_base) st.base_slot[k] = (int)updates.size();
       SlotUpdate u;
       u.key = k;
       u.n_occ = 1;
@@ -1098,6 +1124,300 @@ int commit(gaml_ctx* ctx) {
   return GAML_OK;
 }
 
+// ---- patched full evaluation ------------------------------------------------------------------------------------------
+constexpr int kMaxPatchWalks = 64;
+constexpr size_t kPatchReserve = (size_t)1 << 18;   // room behind the base blob in d_full_blob
+bool patch_debug() {
+  static const bool on = getenv("GAML_B200_PATCH_DEBUG") != nullptr;
+  return on;
+}
+#define PATCH_NO(why)                                                          \
+  do {                                                                         \
+    if (patch_debug()) fprintf(stderr, "[gaml_b200] full patch: %s\n", why);   \
+    return false;                                                              \
+  } while (0)
+
+// Labels of the new list from the previous list's (equal walks keep theirs, run by run) along load_walks' alignment.
+// A walk that left the list is noted when it was a base walk; a walk that entered it gets its base label back when it
+// equals a missing base walk and the label fits between its neighbours', else a label in the gap between them.
+bool derive_track(gaml_ctx* ctx, const WalkSet& old, const WalkSet& ws, const WalkDiff& d, const gaml_ctx::ListTrack& tp,
+                  gaml_ctx::ListTrack& tc) {
+  const int g = ctx->base_g;
+  const uint32_t gmask = (1u << g) - 1u;
+  if ((int)tp.label.size() != old.n) PATCH_NO("label array out of step");
+  tc.label.resize((size_t)ws.n);
+  tc.removed = tp.removed;
+  tc.n_added = tp.n_added;
+  size_t io = 0, in = 0;
+  int x = 0, y = 0;
+  while (x < old.n || y < ws.n) {
+    const int nx = io < d.old_changed.size() ? d.old_changed[io] : old.n;
+    const int ny = in < d.new_changed.size() ? d.new_changed[in] : ws.n;
+    const int r = std::min(nx - x, ny - y);
+    if (r < 0) PATCH_NO("negative run");
+    if (r > 0) {
+      memcpy(tc.label.data() + y, tp.label.data() + x, sizeof(uint32_t) * (size_t)r);
+      x += r;
+      y += r;
+    }
+    bool moved = r > 0;
+    if (x == nx && x < old.n) {
+      const uint32_t lab = tp.label[x];
+      if ((lab & gmask) == 0) tc.removed.insert(std::upper_bound(tc.removed.begin(), tc.removed.end(), (int)(lab >> g) - 1), (int)(lab >> g) - 1);
+      else tc.n_added--;
+      x++;
+      io++;
+      moved = true;
+    }
+    if (y == ny && y < ws.n) {
+      tc.label[y] = 0xffffffffu;   // assigned below, once its right neighbour's label is known
+      y++;
+      in++;
+      moved = true;
+    }
+    if (!moved) PATCH_NO("no alignment");   // (lists of different length with nothing left to skip: not an alignment)
+  }
+  const uint32_t label_max = ctx->base_s >= 32 ? 0u : (uint32_t)((1ull << (32 - ctx->base_s)) - 1ull);
+  for (size_t k = 0; k < d.new_changed.size(); k++) {
+    const int yy = d.new_changed[k];
+    const uint32_t left = yy > 0 ? tc.label[yy - 1] : 0u;
+    int y2 = yy + 1;
+    while (y2 < ws.n && tc.label[y2] == 0xffffffffu) y2++;
+    const bool at_end = y2 >= ws.n;   // nothing labelled to the right: walks appended to the list count upwards
+    const uint32_t right = at_end ? label_max : tc.label[y2];
+    if (right <= left + 1) PATCH_NO("no label left in the gap");   // no label left in this gap: the next full evaluation renumbers
+    uint32_t lab = 0;
+    for (size_t q = 0; q < tc.removed.size(); q++) {
+      const int b = tc.removed[q];
+      const uint32_t bl = (uint32_t)(b + 1) << g;
+      if (bl <= left || bl >= right) continue;
+      if (ctx->base_ws.hash[b] != ws.hash[yy] || !same_walk(ctx->base_ws.view(b), ws.view(yy))) continue;
+      lab = bl;
+      tc.removed.erase(tc.removed.begin() + (long)q);
+      break;
+    }
+    if (!lab) {
+      lab = at_end ? left + 1 : left + (right - left) / 2;
+      if ((lab & gmask) == 0) {   // multiples of 2^g are the base walks' labels
+        if (lab + 1 < right) lab++;
+        else if (lab - 1 > left) lab--;
+        else PATCH_NO("gap holds only a base label");
+      }
+      tc.n_added++;
+    }
+    tc.label[yy] = lab;
+  }
+  if ((int)tc.removed.size() > kMaxPatchWalks || tc.n_added > kMaxPatchWalks) PATCH_NO("too far from the base list");
+  tc.base_gen = tp.base_gen;
+  return true;
+}
+
+// Prepares a full evaluation of cur() as the resident base blob plus a patch. Returns 1 = prepared, 0 = not applicable
+// (the caller flattens every walk), < 0 = error.
+int prepare_full_patch(gaml_ctx* ctx, int total_len) {
+  const gaml_ctx::ListTrack& tc = ctx->track[ctx->cur_set];
+  const WalkSet& ws = ctx->cur();
+  const int g = ctx->base_g, S = ctx->base_s;
+  const uint32_t gmask = (1u << g) - 1u;
+  std::vector<int> added;
+  for (int y = 0; y < ws.n; y++)
+    if (tc.label[(size_t)y] & gmask) added.push_back(y);
+  std::vector<uint32_t> gone;   // labels of the missing base walks, ascending
+  for (int b : tc.removed) gone.push_back((uint32_t)(b + 1) << g);
+  auto is_gone = [&](int walk) { return std::binary_search(gone.begin(), gone.end(), (uint32_t)walk); };
+  if (++ctx->stamp_gen == 0) {
+    for (MateStore* st : ctx->stores) std::fill(st->key_stamp.begin(), st->key_stamp.end(), 0u);
+    ctx->stamp_gen = 1;
+  }
+  const uint32_t stamp = ctx->stamp_gen;
+  const size_t n_sets = ctx->sets.size(), n_stores = ctx->stores.size();
+  ctx->plan = ctx->full_plan;
+  std::vector<int32_t> skip;
+  std::vector<SlotUpdate> pupd;
+  std::vector<std::vector<Occ>> pocc(n_stores);
+  std::vector<std::vector<TouchRange>> pmt(n_sets);
+  std::vector<char> mt_changed(n_sets, 0);
+  struct AddOcc { int key; Occ o; };
+  std::vector<Occ> tmp;
+  for (size_t s = 0; s < n_sets; s++) {
+    ReadSetState& rs = *ctx->sets[s];
+    SetPlan& sp = ctx->plan[s];
+    std::vector<AddOcc> adds[2];
+    std::vector<int> akeys[2];
+    auto touch_key = [&](int m, int k) {
+      MateStore& st = rs.mate[m];
+      if (st.key_stamp.size() < st.keys.size()) {
+        st.key_stamp.resize(st.keys.size(), 0u);
+        st.key_slot.resize(st.keys.size(), 0);
+      }
+      if (st.key_stamp[k] == stamp) return;
+      st.key_stamp[k] = stamp;
+      akeys[m].push_back(k);
+    };
+    for (int b : tc.removed) {
+      const WalkFlat& f = cached_walk_flat(ctx, rs, ctx->base_ws.view(b));
+      sp.records -= f.records;
+      sp.records1 -= f.records1;
+      for (int m = 0; m < 2; m++)
+        for (const FlatEntry& e : f.e[m]) touch_key(m, e.key);
+    }
+    for (int y : added) {
+      const WalkFlat& f = cached_walk_flat(ctx, rs, ws.view(y));
+      sp.records += f.records;
+      sp.records1 += f.records1;
+      const uint32_t lab = tc.label[(size_t)y];
+      for (int m = 0; m < 2; m++) {
+        if (f.e[m].size() >= ((size_t)1 << S)) return 0;   // more lookups than a label's enumeration range holds
+        uint32_t seg = lab << S;
+        for (const FlatEntry& e : f.e[m]) {
+          adds[m].push_back(AddOcc{e.key, Occ{(int)lab, (int)seg++, e.cur, e.skip}});
+          touch_key(m, e.key);
+        }
+      }
+    }
+    std::vector<std::pair<int, int>> new_multi;   // (mate, key)
+    for (int m = 0; m < 2; m++) {
+      MateStore& st = rs.mate[m];
+      std::stable_sort(adds[m].begin(), adds[m].end(), [](const AddOcc& a, const AddOcc& b) { return a.key < b.key; });
+      for (int k : akeys[m]) {
+        tmp.clear();
+        const int bi = (size_t)k < st.base_slot.size() ? st.base_slot[k] : -1;
+        bool base_multi = false;
+        if (bi >= 0) {
+          skip.push_back(bi);
+          const SlotUpdate& bu = ctx->full_updates[(size_t)bi];
+          base_multi = bu.n_occ > 1;
+          if (bu.n_occ == 1) {
+            if (!is_gone(bu.first.walk)) tmp.push_back(bu.first);
+          } else {
+            const std::vector<Occ>& fo = ctx->full_occs[st.table_index];
+            for (int t = 0; t < bu.n_occ; t++)
+              if (!is_gone(fo[(size_t)bu.occ_begin + t].walk)) tmp.push_back(fo[(size_t)bu.occ_begin + t]);
+          }
+        }
+        auto lo = std::lower_bound(adds[m].begin(), adds[m].end(), k, [](const AddOcc& a, int key) { return a.key < key; });
+        for (; lo != adds[m].end() && lo->key == k; ++lo) tmp.push_back(lo->o);
+        std::sort(tmp.begin(), tmp.end(), [](const Occ& a, const Occ& b) { return (uint32_t)a.seg < (uint32_t)b.seg; });
+        if (base_multi || tmp.size() > 1) mt_changed[s] = 1;
+        if (tmp.empty()) continue;   // the key is not live in this evaluation: its slot keeps a stale epoch
+        SlotUpdate u;
+        u.key = k;
+        u.n_occ = (int)tmp.size();
+        u.occ_begin = 0;
+        u.store = st.table_index;
+        u.first = tmp[0];
+        if (tmp.size() > 1) {
+          u.occ_begin = (int)pocc[st.table_index].size();   // rebased below, once the patch has its place in the blob
+          pocc[st.table_index].insert(pocc[st.table_index].end(), tmp.begin(), tmp.end());
+          new_multi.push_back({m, k});
+        }
+        pupd.push_back(u);
+      }
+    }
+    if (mt_changed[s]) {
+      sp.multi_records = 0;
+      for (int m = 0; m < 2; m++) {
+        const MateStore& st = rs.mate[m];
+        auto push = [&](int k) {
+          const KeyMeta& km = st.keys[k];
+          if (!km.count) return;
+          pmt[s].push_back(TouchRange{km.arena_off, km.count});
+          sp.multi_records += km.count;
+        };
+        for (const std::pair<int, int>& mk : ctx->base_mkeys[s])
+          if (mk.first == m && st.key_stamp[mk.second] != stamp) push(mk.second);
+        for (const std::pair<int, int>& mk : new_multi)
+          if (mk.first == m) push(mk.second);
+        if (m == 0) sp.n_mtouch1 = (int)pmt[s].size();
+      }
+      sp.n_mtouch = (int)pmt[s].size();
+    }
+    sp.total_len = total_len;
+    sp.full = true;
+    sp.delta_only = false;
+  }
+  std::sort(skip.begin(), skip.end());
+
+  // ---- the patch's place behind the base blob ----
+  auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  const size_t p0 = align16(ctx->full_blob_bytes);
+  size_t off = p0;
+  ctx->patch_skip_off = off;
+  off = align16(off + skip.size() * sizeof(int32_t));
+  ctx->patch_upd_off = off;
+  off = align16(off + pupd.size() * sizeof(SlotUpdate));
+  std::vector<size_t> pocc_off(n_stores);
+  for (size_t i = 0; i < n_stores; i++) {
+    pocc_off[i] = off;
+    off = align16(off + pocc[i].size() * sizeof(Occ));
+  }
+  for (size_t s = 0; s < n_sets; s++) {
+    SetPlan& sp = ctx->plan[s];
+    ReadSetState& rs = *ctx->sets[s];
+    if (mt_changed[s]) {
+      sp.mtouch_off = off;
+      off = align16(off + pmt[s].size() * sizeof(TouchRange));
+      sp.mprefix_off = off;
+      off = align16(off + (pmt[s].size() + 1) * sizeof(uint32_t));
+    }
+    sp.pstar_off = off;
+    off = align16(off + std::max<size_t>(rs.h_thr.size(), 1) * sizeof(double));
+  }
+  if (off > ctx->d_full_blob.cap) return 0;
+  // occurrence lists of the patch are addressed relative to the base's per-store arrays (same buffer)
+  for (SlotUpdate& u : pupd)
+    if (u.n_occ > 1) {
+      size_t base_occ = 0;
+      for (size_t s = 0; s < n_sets; s++)
+        for (int m = 0; m < 2; m++)
+          if (ctx->sets[s]->mate[m].table_index == u.store) base_occ = ctx->plan[s].occ_off[m];
+      u.occ_begin += (int)((pocc_off[(size_t)u.store] - base_occ) / sizeof(Occ));
+    }
+  const size_t bytes = off - p0;
+  int rc = ensure_pinned(ctx, bytes);
+  if (rc != GAML_OK) return rc;
+  char* hb = static_cast<char*>(ctx->h_blob) - p0;   // (offsets below are blob offsets)
+  if (!skip.empty()) memcpy(hb + ctx->patch_skip_off, skip.data(), skip.size() * sizeof(int32_t));
+  if (!pupd.empty()) memcpy(hb + ctx->patch_upd_off, pupd.data(), pupd.size() * sizeof(SlotUpdate));
+  for (size_t i = 0; i < n_stores; i++)
+    if (!pocc[i].empty()) memcpy(hb + pocc_off[i], pocc[i].data(), pocc[i].size() * sizeof(Occ));
+  for (size_t s = 0; s < n_sets; s++) {
+    SetPlan& sp = ctx->plan[s];
+    ReadSetState& rt = *ctx->sets[s];
+    if (mt_changed[s]) {
+      if (!pmt[s].empty()) memcpy(hb + sp.mtouch_off, pmt[s].data(), pmt[s].size() * sizeof(TouchRange));
+      uint32_t* mpre = reinterpret_cast<uint32_t*>(hb + sp.mprefix_off);
+      uint64_t macc = 0;
+      for (size_t t = 0; t < pmt[s].size(); t++) {
+        mpre[t] = (uint32_t)macc;
+        macc += pmt[s][t].count;
+      }
+      if (macc > 0xffffffffull) return fail(ctx, GAML_ERR_CAPACITY, "more than 2^32 records under repeated keys in one evaluation");
+      mpre[pmt[s].size()] = (uint32_t)macc;
+    }
+    const int two_len = two_len_of(sp.total_len);
+    if (!rt.pstar_valid || rt.pstar_two_len != two_len) {
+      rt.h_pstar.assign(rt.h_thr.size(), 0.0);
+      for (int li : rt.len_classes) rt.h_pstar[li] = floor_pstar(rt.h_thr[li], (double)two_len);
+      rt.pstar_two_len = two_len;
+      rt.pstar_valid = true;
+    }
+    if (!rt.h_pstar.empty()) memcpy(hb + sp.pstar_off, rt.h_pstar.data(), rt.h_pstar.size() * sizeof(double));
+  }
+  ctx->n_updates = ctx->full_n_updates;
+  ctx->upd_off = ctx->full_upd_off;
+  ctx->n_patch = (int)pupd.size();
+  ctx->n_skip = (int)skip.size();
+  ctx->blob_bytes = off;
+  ctx->blob_dev = ctx->d_full_blob.as<char>();
+  CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, ctx->stream));
+  for (auto& rsp : ctx->sets) CU(rsp->d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));
+  CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
+  if (bytes) CU(cudaMemcpyAsync(ctx->blob_dev + p0, ctx->h_blob, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stats.last_h2d_bytes = (int64_t)bytes;
+  return 1;
+}
+
 int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walks) {
   if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
@@ -1141,6 +1461,19 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   if (!list_same) ctx->list_gen++;
   bool all_full = true;
   for (auto& rsp : ctx->sets) all_full &= !(rsp->cfg.kind == GAML_KIND_PAIRED && rsp->has_state);
+  ctx->n_patch = ctx->n_skip = 0;
+  // labels of this list relative to the resident base blob's list (patched full evaluation): followed through every
+  // evaluation, full or incremental, for as long as the lists align and stay within a few walks of the base
+  if (ctx->full_cache_gen != ctx->cache_gen || !ctx->full_blob_valid) ctx->base_valid = false;
+  gaml_ctx::ListTrack& track = ctx->track[ctx->cur_set];
+  track.valid = false;
+  if (ctx->base_valid && old_set && diff.valid) {
+    const gaml_ctx::ListTrack& tp = ctx->track[ctx->cur_set ^ 1];
+    if (tp.valid && tp.base_gen == ctx->base_gen) track.valid = derive_track(ctx, *old_set, ws, diff, tp, track);
+    else if (patch_debug()) fprintf(stderr, "[gaml_b200] full patch: previous list not tracked (valid %d)\n", (int)tp.valid);
+  } else if (patch_debug()) {
+    fprintf(stderr, "[gaml_b200] full patch: no tracking (base %d, prev %d, diff %d)\n", (int)ctx->base_valid, old_set != nullptr, (int)diff.valid);
+  }
   if (all_full && ctx->full_blob_valid && ctx->full_list_gen == ctx->list_gen && ctx->full_cache_gen == ctx->cache_gen &&
       ctx->full_plan.size() == ctx->sets.size()) {
     // the same walks, the same cache, every paired set from scratch: the blob of the last such evaluation is still on the device
@@ -1165,11 +1498,45 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     CU(ctx->d_scratch.reserve(ctx->scratch_entries * sizeof(Plc), 0, false, ctx->stream));
     ctx->stats.last_h2d_bytes = 0;
     ctx->full_blob_reuses++;
+    ctx->stats.full_reuse_evals++;
     ctx->epoch++;
     ctx->prepared = true;
     ctx->launched = false;
     return GAML_OK;
   }
+  if (all_full && ctx->patch_enabled && ctx->base_valid && track.valid && track.base_gen == ctx->base_gen &&
+      ctx->full_plan.size() == ctx->sets.size()) {
+    // a full evaluation of a list a few walks away from the base list: the resident blob + the updates of those walks' keys
+    rc = prepare_full_patch(ctx, total_len);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      ctx->stats.full_patch_evals++;
+      ctx->epoch++;
+      ctx->prepared = true;
+      ctx->launched = false;
+      return GAML_OK;
+    }
+    ctx->n_patch = ctx->n_skip = 0;
+  }
+  const size_t n_sets = ctx->sets.size();
+  // Full evaluations of paired sets number their walks with gaps (labels) when the context allows patched re-scores later.
+  bool spaced = all_full && ctx->patch_enabled && n_sets > 0 && ws.n > 0;
+  for (auto& rsp : ctx->sets) spaced &= rsp->cfg.kind == GAML_KIND_PAIRED && !rsp->penalty && rsp->n_mates == 2;
+  int lab_g = 3, lab_s = 0;
+  if (spaced) {
+    int bits = 0;
+    while (((uint64_t)(ws.n + 2) << lab_g) >> bits) bits++;
+    if (32 - (bits + 1) >= 12) bits++;   // (room for walks appended behind the base list's labels)
+    lab_s = std::min(32 - bits, 20);
+    if (lab_s < 6) spaced = false;
+  }
+  bool seg_overflow = false;
+  std::vector<SlotUpdate>& updates = ctx->h_updates;
+  std::vector<std::vector<Occ>>& occs = ctx->h_occs;
+  std::vector<std::vector<TouchRange>>& touches = ctx->h_touches;
+  std::vector<std::vector<TouchRange>>& mtouches = ctx->h_mtouches;
+  std::vector<std::vector<std::vector<int>>> cov_cs;   // per penalty set: contig starts of every touched walk
+ for (;;) {   // (a second round only when a walk has more lookups than a label's enumeration range: dense numbers then)
   // host-side generation of the per-key stamp tables (group_occurrences). The device epoch (slot liveness, result lines)
   // advances only at the end, once this function can no longer fail: the ranks of a multi-GPU job stay in step even when
   // one of them rejects a walk set.
@@ -1178,22 +1545,22 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     ctx->stamp_gen = 1;
   }
 
-  const size_t n_sets = ctx->sets.size();
   ctx->plan.assign(n_sets, SetPlan());
-  std::vector<SlotUpdate>& updates = ctx->h_updates;
-  std::vector<std::vector<Occ>>& occs = ctx->h_occs;
-  std::vector<std::vector<TouchRange>>& touches = ctx->h_touches;
   updates.clear();
   occs.resize(ctx->stores.size());
   ctx->h_ob.resize(ctx->stores.size());
   touches.resize(n_sets);
   for (auto& t : touches) t.clear();
-  std::vector<std::vector<TouchRange>>& mtouches = ctx->h_mtouches;
   mtouches.resize(n_sets);
   for (auto& t : mtouches) t.clear();
   for (auto& o : ctx->h_ob) o.reset();
   ctx->h_walks.clear();
-  std::vector<std::vector<std::vector<int>>> cov_cs(n_sets);   // per penalty set: contig starts of every touched walk
+  cov_cs.assign(n_sets, {});
+  seg_overflow = false;
+  if (spaced) {
+    ctx->base_mkeys.assign(n_sets, {});
+    for (MateStore* st : ctx->stores) st->base_slot.assign(st->keys.size(), -1);
+  }
 
   // GetChanges (graph.cc:1745-1764) is the same for every paired set with state (they all follow the last evaluated
   // walks). Fast path: the difference is confined to the region where the new walk list departs from the previous one
@@ -1229,7 +1596,15 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       std::vector<int> cs;
       if (sp.full) {
         for (int i = 0; i < ws.n; i++) {
-          flatten_paired_walk(ctx, rs, ws.view(i), ord++, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          int lab = ord++;
+          uint32_t seg0 = 0;
+          if (spaced) {
+            lab = (i + 1) << lab_g;
+            seg0 = (uint32_t)lab << lab_s;
+            ob[0]->next_seg = ob[1]->next_seg = seg0;
+          }
+          flatten_paired_walk(ctx, rs, ws.view(i), lab, ob, sp, tp, rs.penalty ? &cs : nullptr);
+          if (spaced && (ob[0]->next_seg - seg0 >= (1u << lab_s) || ob[1]->next_seg - seg0 >= (1u << lab_s))) seg_overflow = true;
           if (rs.penalty) cov_cs[s].push_back(cs);
         }
       } else {
@@ -1249,12 +1624,13 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       }
       const size_t u0 = updates.size();
       for (int m = 0; m < 2; m++)
-        group_occurrences(*ob[m], rs.mate[m], ctx->stamp_gen, updates, occs[rs.mate[m].table_index]);
+        group_occurrences(*ob[m], rs.mate[m], ctx->stamp_gen, updates, occs[rs.mate[m].table_index], spaced);
       if (sp.full) {   // records under keys that occur several times: enumerated by the multi pass, mate 1's ranges first
         std::vector<TouchRange>& mt = mtouches[s];
         for (int m = 0; m < 2; m++) {
           for (size_t u = u0; u < updates.size(); u++) {
             if (updates[u].n_occ < 2 || updates[u].store != rs.mate[m].table_index) continue;
+            if (spaced) ctx->base_mkeys[s].push_back({m, updates[u].key});
             const KeyMeta& km = rs.mate[m].keys[updates[u].key];
             if (km.count) {
               mt.push_back(TouchRange{km.arena_off, km.count});
@@ -1280,6 +1656,10 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       sp.cgrid = rs.cfg.kind == GAML_KIND_SINGLE && rs.n_complex > 0 ? score_grid(kGridSingleComplex, rs.n_complex, ctx->sm_count) : 0;
     }
   }
+
+  if (!(spaced && seg_overflow)) break;
+  spaced = false;
+ }
 
   // ---- pack the staging blob: [updates][occ per store][touch + prefix per set][set_begin] -----
   auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -1411,7 +1791,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->n_updates = (int)updates.size();
 
   DevBuf& dst_blob = all_full ? ctx->d_full_blob : ctx->d_blob;
-  CU(dst_blob.reserve(std::max<size_t>(off, (size_t)1 << 18), 0, false, ctx->stream));   // (generous: growing a device buffer frees the old
+  CU(dst_blob.reserve(std::max<size_t>(off + (all_full ? kPatchReserve : 0), (size_t)1 << 18), 0, false, ctx->stream));   // (generous: growing a device buffer frees the old
                                                                                          //  one, which waits for the whole device)
   ctx->blob_dev = dst_blob.as<char>();
   CU(ctx->d_flags.reserve(flags_words(n_sets) * sizeof(unsigned long long), 0, true, ctx->stream));
@@ -1431,14 +1811,32 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   for (auto& rsp : ctx->sets) CU(rsp->d_ovf_list.reserve((size_t)ctx->ovf_cap * 4, 0, false, ctx->stream));   // grows after a capacity error
   CU(cudaMemcpyAsync(ctx->blob_dev, ctx->h_blob, off, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.last_h2d_bytes = (int64_t)off;
-  ctx->full_blob_valid = all_full;
-  if (all_full) {
+  if (all_full) {   // (an incremental evaluation stages into d_blob: the resident full blob stays as it is)
+    ctx->full_blob_valid = true;
     ctx->full_plan = ctx->plan;
     ctx->full_n_updates = ctx->n_updates;
     ctx->full_upd_off = ctx->upd_off;
     ctx->full_blob_bytes = ctx->blob_bytes;
     ctx->full_list_gen = ctx->list_gen;
     ctx->full_cache_gen = ctx->cache_gen;
+    ctx->base_valid = spaced;
+    if (spaced) {   // this list is the base of later patched evaluations: keep its walks and its updates on the host
+      ctx->base_gen++;
+      ctx->base_g = lab_g;
+      ctx->base_s = lab_s;
+      ctx->base_ws.n = ws.n;
+      ctx->base_ws.nodes = ws.nodes;
+      ctx->base_ws.offs = ws.offs;
+      ctx->base_ws.hash = ws.hash;
+      ctx->full_updates.swap(updates);
+      ctx->full_occs.swap(occs);
+      track.valid = true;
+      track.base_gen = ctx->base_gen;
+      track.removed.clear();
+      track.n_added = 0;
+      track.label.resize((size_t)ws.n);
+      for (int i = 0; i < ws.n; i++) track.label[(size_t)i] = (uint32_t)(i + 1) << lab_g;
+    }
   }
   ctx->epoch++;
   ctx->prepared = true;
@@ -1708,7 +2106,9 @@ int launch(gaml_ctx* ctx) {
   struct RecorderGuard { ~RecorderGuard() { set_launch_recorder(nullptr); } } recorder_guard;
   if (record) set_launch_recorder(&chain);
   else if (ctx->timed) CU(cudaEventRecord(ctx->ev[0], st));
-  launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates, ctx->d_tables.as<SlotA*>(),
+  launch_apply_slots(reinterpret_cast<const SlotUpdate*>(blob + ctx->upd_off), ctx->n_updates,
+                     reinterpret_cast<const SlotUpdate*>(blob + ctx->patch_upd_off), ctx->n_patch,
+                     reinterpret_cast<const int32_t*>(blob + ctx->patch_skip_off), ctx->n_skip, ctx->d_tables.as<SlotA*>(),
                      ctx->d_tables.as<SlotB*>() + ctx->stores.size(), ctx->d_tables.as<SlotA*>() + 2 * ctx->stores.size(),
                      ctx->d_tables.as<const int32_t*>() + 3 * ctx->stores.size(),
                      ctx->stores.size() <= (size_t)kInlineStores ? &ctx->h_tables : nullptr, ctx->epoch, ctx->d_flags.as<unsigned long long>(),
@@ -2440,6 +2840,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
   if (const char* s = getenv("GAML_B200_NO_FAST_CHANGES")) ctx->fast_changes = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_PERMUTE")) ctx->permute_reads = !(s[0] && s[0] != '0');
   if (const char* s = getenv("GAML_B200_NO_APPEND")) ctx->append_enabled = !(s[0] && s[0] != '0');
+  if (const char* s = getenv("GAML_B200_NO_FULL_PATCH")) ctx->patch_enabled = !(s[0] && s[0] != '0');
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;

@@ -2623,19 +2623,35 @@ __global__ void __launch_bounds__(128) pacbio_alnprob_kernel(const AlnProbParams
 // key id that holds, side by side, the word of that key in mate 1's store and the word of the same key (same node
 // sequence) in mate 2's store (base + 1, index through the mate-2 -> mate-1 key map): tier 1 of the streaming kernel
 // fetches both with one 256-bit gather for the pairs whose mates lie under the same key (nearly all of them).
+// A patched full evaluation (engine.cu "patched full evaluation") applies the resident updates of the base walk list
+// and, behind them, the few updates of the keys whose occurrences differ from the base's; the base entries of those keys
+// (indices in the ascending list `skip`) are left out, so every key is written by exactly one thread and a key that lost
+// its last occurrence simply keeps a stale epoch.
 template <bool kInline>
-__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+__global__ void apply_slots_kernel(const SlotUpdate* upd, int n, const SlotUpdate* patch, int n_patch, const int32_t* skip, int n_skip,
+                                   SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
                                    const int32_t* const* comb_map, const StoreTables T, uint32_t epoch, unsigned long long* flags,
                                    int n_flag_words, unsigned long long* timeline) {
   pdl_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   tl_begin(timeline, kTlApply);
   if (i < n_flag_words) flags[i] = 0ull;   // scratch cursor, error flag, overflow counters, tickets, accumulators
-  if (i >= n) {
+  if (i >= n + n_patch) {
     tl_end(timeline, kTlApply);
     return;
   }
-  const SlotUpdate u = upd[i];
+  if (i < n && n_skip > 0) {
+    int lo = 0, hi = n_skip;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(skip + mid) < i) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_skip && __ldg(skip + lo) == i) {
+      tl_end(timeline, kTlApply);
+      return;
+    }
+  }
+  const SlotUpdate u = i < n ? upd[i] : patch[i - n];
   SlotA a;
   a.epoch_flag = epoch | (u.n_occ > 1 ? 0x80000000u : 0u);
   a.walk = u.first.walk;
@@ -2949,16 +2965,17 @@ void launch_chain(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st
   issue_launch(pl, st);
 }
 
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+void launch_apply_slots(const SlotUpdate* upd, int n, const SlotUpdate* patch, int n_patch, const int32_t* skip, int n_skip,
+                        SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
                         const int32_t* const* comb_map, const StoreTables* inline_tabs, uint32_t epoch, unsigned long long* flags,
                         int n_flag_words, unsigned long long* timeline, cudaStream_t st) {
-  const int m = n > n_flag_words ? n : n_flag_words;
+  const int m = n + n_patch > n_flag_words ? n + n_patch : n_flag_words;
   if (inline_tabs)
-    launch_chain(apply_slots_kernel<true>, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, comb_base, comb_map, *inline_tabs,
-                 epoch, flags, n_flag_words, timeline);
+    launch_chain(apply_slots_kernel<true>, (m + 255) / 256, 256, st, false, upd, n, patch, n_patch, skip, n_skip, tab_a, tab_b, comb_base,
+                 comb_map, *inline_tabs, epoch, flags, n_flag_words, timeline);
   else
-    launch_chain(apply_slots_kernel<false>, (m + 255) / 256, 256, st, false, upd, n, tab_a, tab_b, comb_base, comb_map, StoreTables{},
-                 epoch, flags, n_flag_words, timeline);
+    launch_chain(apply_slots_kernel<false>, (m + 255) / 256, 256, st, false, upd, n, patch, n_patch, skip, n_skip, tab_a, tab_b, comb_base,
+                 comb_map, StoreTables{}, epoch, flags, n_flag_words, timeline);
 }
 
 // Every wrapper below appends its kernels to the evaluation's chain. `chained` = the operation before it on `st` is a

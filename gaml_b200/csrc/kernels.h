@@ -39,7 +39,8 @@ struct StoreTables {
   SlotA* cb[kInlineStores];
   const int32_t* cm[kInlineStores];
 };
-void launch_apply_slots(const SlotUpdate* upd, int n, SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
+void launch_apply_slots(const SlotUpdate* upd, int n, const SlotUpdate* patch, int n_patch, const int32_t* skip, int n_skip,
+                        SlotA* const* tab_a, SlotB* const* tab_b, SlotA* const* comb_base,
                         const int32_t* const* comb_map, const StoreTables* inline_tabs, uint32_t epoch, unsigned long long* flags,
                         int n_flag_words, unsigned long long* timeline, cudaStream_t st);
 constexpr int kTimelineWords = 12;   // profiling level 2: {start, end} ns of apply, tier 1, tier 2, many-placement, delta, total

@@ -107,6 +107,9 @@ typedef struct {
   int64_t cache_appends;           /* cache growths applied in O(new records): rows of the affected reads relocated, reads handed to
                                       the appendix phase */
   int64_t cache_rebuilds;          /* cache growths that rebuilt a read set's device index (first build, appendix full, no slack) */
+  int64_t full_reuse_evals;        /* full evaluations of the walk list evaluated last: slot tables already on the device, no upload */
+  int64_t full_patch_evals;        /* full evaluations of a list a few walks away from the resident one: only the slot updates of
+                                      those walks' keys were built and uploaded (O(changed walks) host work) */
 } gaml_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -337,6 +337,50 @@ def test_c4_shape_two_shards_and_internal_order(c4, monkeypatch):
         pc.close()
 
 
+def _patched_equals_flattened(wl, monkeypatch, script, min_patched):
+    """Two contexts over the same workload, one with patched full evaluations (default), one that flattens every walk
+    of every full evaluation (GAML_B200_NO_FULL_PATCH): partial sums and per-read values must be IDENTICAL at every step.
+    script = [(index into wl.evals or an explicit walk list, fresh ScoringState?)]."""
+    patched = api.ProbCalculator.from_workload(wl)
+    monkeypatch.setenv("GAML_B200_NO_FULL_PATCH", "1")
+    plain = api.ProbCalculator.from_workload(wl)
+    monkeypatch.delenv("GAML_B200_NO_FULL_PATCH")
+    for step, (k, fresh) in enumerate(script):
+        walks = wl.evals[k] if isinstance(k, int) else k
+        if fresh:
+            patched.reset_state()
+            plain.reset_state()
+        pa, ta = patched.calc_prob_partial(walks)
+        pb, tb = plain.calc_prob_partial(walks)
+        assert ta == tb and np.array_equal(pa, pb), (step, pa, pb)
+        assert np.array_equal(patched.read_values(0), plain.read_values(0)), step
+    assert patched.stats().full_patch_evals >= min_patched, patched.stats().full_patch_evals
+    assert plain.stats().full_patch_evals == 0
+    patched.close()
+    plain.close()
+
+
+def test_c4_shape_full_evaluation_of_a_changed_list_uploads_only_its_patch(c4, monkeypatch):
+    """A full evaluation (fresh ScoringState) of a walk list a few moves away from the list whose slot tables are on the
+    device flattens and uploads only the changed walks' keys (engine.cu "patched full evaluation") — at 10 000 walks the
+    difference between O(changed) and O(all walks) host work. Checked against the same library flattening everything:
+    joins, splits, there and back, after incremental drift, after a reordered list (renumbering), repeated lists."""
+    wl = c4
+    rev = list(reversed(wl.evals[0]))
+    script = [(0, True), (2, True), (0, True), (3, True), (4, False), (5, False), (6, True), (6, True), (1, True), (9, False),
+              (0, True), (rev, True), (2, True), (12, True), (rev, True), (0, True), (21, True), (20, True)]
+    _patched_equals_flattened(wl, monkeypatch, script, min_patched=8)
+
+
+def test_patched_full_evaluation_with_repeat_keys(monkeypatch):
+    """The same on a small repeat-rich graph: keys that occur several times (their occurrence lists are merged from the
+    base's and the patch's, and the multi pass gets a new range list) and reads with placements on several walks (the
+    order of the placements across walks must survive the labels with gaps)."""
+    wl = synth.paired_workload(14, 2500, 6000, n_evals=26, seed=77)
+    script = [(0, True)] + [(k, True) for k in range(1, 26)] + [(0, True), (13, True), (14, False), (15, False), (3, True), (25, True)]
+    _patched_equals_flattened(wl, monkeypatch, script, min_patched=10)
+
+
 def test_c4_shape_batch_of_1024_candidates(c4):
     """BASELINE config 5 on the config-4 shape: 1024 candidate moves in one batch; a sample of them must equal, bit for
     bit, the sequential evaluation of that candidate's walk set by a fresh context with the same history."""
