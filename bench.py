@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the c2 workload (debug only; 1.0 = config 2)")
     ap.add_argument("--delta-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C3 legs")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in ProbCalculator leg (oracle/_ref/gpu_harness)")
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4shard"],
                     help="auto (default): config 2 on one GPU, one eighth of config 4 per GPU on several")
@@ -730,6 +731,44 @@ def main():
                                       "score out), timed inside oracle/_ref/gpu_harness around each call on the incremental trajectory; median"}
         except Exception as exc:   # the boundary leg never takes the bench line down
             line["dropin"] = {"error": str(exc)[:200]}
+
+    # ---- the other single-GPU configurations of BASELINE.json (C1: single-end reads, C3: paired + PacBio), full evaluations
+    #      through the C ABI with host walk arrays (the parity tests score the same workloads against the oracle) ----
+    if rank == 0 and world == 1 and not args.no_other_configs and kind == "c2":
+        from gaml_b200 import synth
+        others = {}
+        specs = (("c1", "C1: 100 kbp genome, 50 k single-end 100 bp reads", lambda: synth.single_workload(10, 10000, 50_000, n_evals=4, seed=7)),
+                 ("c3", "C3: config 2's 2 M read pairs (weight 1.0) + 46 k PacBio-like 10 kbp reads (weight 0.5)",
+                  lambda: synth.mixed_workload(460, 10000, int(2_000_000 * args.scale), int(46_000 * args.scale), n_evals=4, seed=42, pacbio_len=10000)))
+        for name, desc, make in specs:
+            try:
+                t0 = time.perf_counter()
+                wlo = make()
+                pco = api.ProbCalculator.from_workload(wlo, device=local_rank)
+                fws = [api.FlatWalks(w) for w in wlo.evals]
+                pco.set_profiling(1)
+                for fw in fws:                      # warm-up: every list once (graphs, buffers)
+                    pco.reset_state()
+                    pco.calc_prob_partial_flat(fw)
+                n_o, wall_o, dev_o, rec_o = max(args.steps, 4), 0.0, 0.0, 0
+                for k in range(n_o):
+                    pco.reset_state()
+                    flush_l2()
+                    t1 = time.perf_counter()
+                    pco.calc_prob_partial_flat(fws[k % len(fws)])
+                    wall_o += time.perf_counter() - t1
+                    sto = pco.stats()
+                    dev_o += sto.last_device_ms
+                    rec_o += int(sto.last_records_gathered)
+                others[name] = {"workload": desc, "alignments_per_eval": rec_o // n_o, "e2e_ms_per_eval": 1e3 * wall_o / n_o,
+                                "device_ms_per_eval": dev_o / n_o, "e2e_alignments_per_s": rec_o / wall_o,
+                                "read_sets": [int(sp.kind) for sp in wlo.sets], "setup_s": round(time.perf_counter() - t0 - wall_o, 1)}
+                pco.close()
+            except Exception as exc:
+                others[name] = {"error": str(exc)[:200]}
+        others["note"] = ("full evaluations (fresh ScoringState) cycling through the workload's walk lists, gaml_calc_prob_partial with host "
+                          "walk arrays, wall clock, L2 flushed between evaluations; read_sets: 0 single, 1 paired, 2 PacBio")
+        line["other_configs"] = others
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         # bounded CPU sample on the box's host: the reference's own scorer, 1 core, the whole workload, a few full evaluations

@@ -1418,7 +1418,32 @@ int prepare_full_patch(gaml_ctx* ctx, int total_len) {
   return 1;
 }
 
+// GAML_B200_PREP_TIMING=1: mean host microseconds of prepare()'s phases, printed to stderr every 100 evaluations
+struct PrepTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  static constexpr int kPhases = 8;
+  static double acc[kPhases];
+  static long calls;
+  PrepTimer() : on(getenv("GAML_B200_PREP_TIMING") != nullptr) { if (on) t = std::chrono::steady_clock::now(); }
+  void lap(int phase) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    acc[phase] += std::chrono::duration<double, std::micro>(n - t).count();
+    t = n;
+  }
+  void done() {
+    if (!on || ++calls % 100) return;
+    fprintf(stderr, "[gaml_b200] prepare us/call: load %.1f len+commit %.1f track %.1f patch/reuse %.1f flatten %.1f pack %.1f enqueue %.1f\n",
+            acc[0] / 100, acc[1] / 100, acc[2] / 100, acc[3] / 100, acc[4] / 100, acc[5] / 100, acc[6] / 100);
+    for (double& a : acc) a = 0;
+  }
+};
+double PrepTimer::acc[PrepTimer::kPhases] = {0};
+long PrepTimer::calls = 0;
+
 int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walks) {
+  PrepTimer pt;
   if (n_walks < 0 || (n_walks > 0 && (!nodes || !offs))) return fail(ctx, GAML_ERR_ARG, "bad walk arrays");
   if (ctx->node_len.empty()) return fail(ctx, GAML_ERR_STATE, "gaml_set_graph has not been called");
   // an evaluation in flight updates the read state and the walk bookkeeping when it is finished: preparing another one
@@ -1431,6 +1456,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   const WalkSet* old_set = ctx->have_prev ? &ctx->prev() : nullptr;
   WalkDiff& diff = ctx->cur_diff;
   load_walks(ws, old_set, nodes, offs, n_walks, diff);   // aligns with the previous list, hashes only the walks that changed
+  pt.lap(0);
   const int n_nodes = (int)ctx->node_len.size();
   // node ids and GetTotalLen (graph.cc:1966, int arithmetic like the reference): over the changed walks when the rest is
   // the previous evaluation's, else over all of them
@@ -1462,6 +1488,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   bool all_full = true;
   for (auto& rsp : ctx->sets) all_full &= !(rsp->cfg.kind == GAML_KIND_PAIRED && rsp->has_state);
   ctx->n_patch = ctx->n_skip = 0;
+  pt.lap(1);
   // labels of this list relative to the resident base blob's list (patched full evaluation): followed through every
   // evaluation, full or incremental, for as long as the lists align and stay within a few walks of the base
   if (ctx->full_cache_gen != ctx->cache_gen || !ctx->full_blob_valid) ctx->base_valid = false;
@@ -1474,6 +1501,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   } else if (patch_debug()) {
     fprintf(stderr, "[gaml_b200] full patch: no tracking (base %d, prev %d, diff %d)\n", (int)ctx->base_valid, old_set != nullptr, (int)diff.valid);
   }
+  pt.lap(2);
   if (all_full && ctx->full_blob_valid && ctx->full_list_gen == ctx->list_gen && ctx->full_cache_gen == ctx->cache_gen &&
       ctx->full_plan.size() == ctx->sets.size()) {
     // the same walks, the same cache, every paired set from scratch: the blob of the last such evaluation is still on the device
@@ -1502,6 +1530,8 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
     ctx->epoch++;
     ctx->prepared = true;
     ctx->launched = false;
+    pt.lap(3);
+    pt.done();
     return GAML_OK;
   }
   if (all_full && ctx->patch_enabled && ctx->base_valid && track.valid && track.base_gen == ctx->base_gen &&
@@ -1514,6 +1544,8 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
       ctx->epoch++;
       ctx->prepared = true;
       ctx->launched = false;
+      pt.lap(3);
+      pt.done();
       return GAML_OK;
     }
     ctx->n_patch = ctx->n_skip = 0;
@@ -1660,6 +1692,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   if (!(spaced && seg_overflow)) break;
   spaced = false;
  }
+  pt.lap(4);
 
   // ---- pack the staging blob: [updates][occ per store][touch + prefix per set][set_begin] -----
   auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
@@ -1790,6 +1823,7 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   }
   ctx->n_updates = (int)updates.size();
 
+  pt.lap(5);
   DevBuf& dst_blob = all_full ? ctx->d_full_blob : ctx->d_blob;
   CU(dst_blob.reserve(std::max<size_t>(off + (all_full ? kPatchReserve : 0), (size_t)1 << 18), 0, false, ctx->stream));   // (generous: growing a device buffer frees the old
                                                                                          //  one, which waits for the whole device)
@@ -1841,6 +1875,8 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   ctx->epoch++;
   ctx->prepared = true;
   ctx->launched = false;
+  pt.lap(6);
+  pt.done();
   return GAML_OK;
 }
 
