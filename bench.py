@@ -726,7 +726,14 @@ def main():
             warm = np.array([r.seconds for r in res[n_drop + 1:]]) * 1e6
             ok = all(abs(a.score - b.score) <= 1e-9 * abs(b.score) for a, b in zip(res[:n_drop], res[n_drop:]))
             line["dropin"] = {"dropin_us_per_calcprob": float(np.median(warm)), "mean_us": float(warm.mean()), "calls": int(len(warm)),
-                              "c_abi_e2e_us_per_eval": 1e3 * line["incremental"]["e2e_ms_per_eval"], "repeat_scores_agree": bool(ok),
+                              "p10_us": float(np.percentile(warm, 10)), "p90_us": float(np.percentile(warm, 90)),
+                              "c_abi_e2e_us_per_eval": 1e3 * line["incremental"]["e2e_ms_per_eval"],
+                              "c_abi_us_per_eval_inserting_keys": (line.get("append") or {}).get("us_per_eval_inserting"),
+                              "repeat_scores_agree": bool(ok),
+                              "what_is_compared": "the harness's ProbCalculator starts with an empty device cache, so most of its calls also "
+                                                  "upload the windows of the move's new walks (a cache append) - the C-ABI figure for that is "
+                                                  "c_abi_us_per_eval_inserting_keys; calls whose walks need no new window are the p10 and compare "
+                                                  "with c_abi_e2e_us_per_eval",
                               "note": "ProbCalculator::CalcProb(paths, zeros, total_len) of integration/prob_calculator.h (vector<vector<int>> in, "
                                       "score out), timed inside oracle/_ref/gpu_harness around each call on the incremental trajectory; median"}
         except Exception as exc:   # the boundary leg never takes the bench line down

@@ -13,7 +13,7 @@
 // adapter has not seen yet it runs the reference's own precompute routines where CalcScoreForPathsNew /
 // GetPositionsOnlyPath / AddPositions / PacbioReadSet::GetReadProbabilities run them (graph.cc:1967-1968, 538-542,
 // 605-609, 2455-2486), so the same keys are aligned in the same order; it then mirrors the keys the device does not hold
-// yet and calls gaml_calc_prob. A walk seen before costs one vector compare (or one hash probe): its keys are all in the
+// yet and calls gaml_calc_prob. A walk seen before costs a share of a block compare (or one hash probe): its keys are all in the
 // cache already — the cache never shrinks — so it can contribute nothing to either step. No score is ever computed on the
 // CPU; if the CUDA context cannot be created the program aborts like the reference's asserts do.
 #ifndef PROB_CALCULATOR_H__
@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <unordered_map>
 #include <unordered_set>
@@ -70,21 +71,20 @@ class ProbCalculator {
 
   double CalcProb(vector<vector<int>>& paths, vector<pair<int, int>>& zeros, int& total_len) {
     if (!ctx_) Init();   // lazy: gaml.cc constructs the calculator before PrepareReads fills the read sets
-    FillAndMirrorCaches(paths);
-    vector<int32_t> nodes;
-    vector<int64_t> offs(1, 0);
-    for (auto& p : paths) {
-      nodes.insert(nodes.end(), p.begin(), p.end());
-      offs.push_back((int64_t)nodes.size());
-    }
-    if (nodes.empty()) nodes.push_back(0);
-    vector<int32_t> z(2 * (n_sets_ ? n_sets_ : 1));
+    // ONE pass over the caller's vector-of-vectors: the flat arrays the C ABI takes. Everything else the adapter does per
+    // call (which walks are new, FinalEnd bookkeeping) works on these arrays against the previous call's.
+    Flatten(paths, cur_);
+    FillAndMirrorCaches(paths, cur_, prev_, prev_final_end_, cur_final_end_, NULL);
+    z_.assign(2 * (n_sets_ ? n_sets_ : 1), 0);
     gaml_result res;
-    Check(gaml_calc_prob(ctx_, nodes.data(), offs.data(), (int)paths.size(), &res, z.data()));
+    Check(gaml_calc_prob(ctx_, cur_.nodes.data(), cur_.offs.data(), (int)paths.size(), &res, z_.data()));
     zeros.clear();
-    for (size_t s = 0; s < n_sets_; s++) zeros.push_back(make_pair(z[2 * s], z[2 * s + 1]));
+    for (size_t s = 0; s < n_sets_; s++) zeros.push_back(make_pair(z_[2 * s], z_[2 * s + 1]));
     total_len = res.total_len;
     had_calc_ = true;
+    cur_.swap(prev_);   // the evaluated walks become the list the next call is compared with (no copy)
+    prev_final_end_.swap(cur_final_end_);
+    have_prev_ = true;
     return res.prob;
   }
   double CalcProb(vector<vector<int>>& paths, int& total_len) {
@@ -106,42 +106,49 @@ class ProbCalculator {
     vector<double> scores(candidates.size(), 0.0);
     if (candidates.empty()) return scores;
     if (!ctx_) Init();
-    if (!single_reads.empty() || !pacbio_reads.empty() || paired_reads.empty() || prev_paths_.empty() || !had_calc_) {
+    if (!single_reads.empty() || !pacbio_reads.empty() || paired_reads.empty() || !have_prev_ || prev_.n() == 0 || !had_calc_) {
       for (size_t c = 0; c < candidates.size(); c++) scores[c] = CalcProb(candidates[c]);
       return scores;
     }
-    const vector<vector<int>> base = prev_paths_;   // FillAndMirrorCaches moves prev_paths_ along
-    const vector<int> base_final_end = prev_final_end_;
     vector<int32_t> erased_idx, added_nodes;
     vector<int64_t> erased_off(1, 0), added_walk_off(1, 0), cand_added_off(1, 0);
+    FlatPaths cand;
+    vector<int> fe, match;
+    vector<int> un_base, un_cand;   // walks without an equal partner at the aligned position
     for (size_t c = 0; c < candidates.size(); c++) {
-      const vector<vector<int>>& cand = candidates[c];
-      FillAndMirrorCaches(cand);   // aligns and mirrors the windows of walks seen for the first time
-      // multiset difference against the base walk list: equal walks at the front and at the back drop out at once
-      size_t lo = 0;
-      while (lo < base.size() && lo < cand.size() && base[lo] == cand[lo]) lo++;
-      size_t hb = base.size(), hc = cand.size();
-      while (hb > lo && hc > lo && base[hb - 1] == cand[hc - 1]) { hb--; hc--; }
-      unordered_map<vector<int>, int> need;
-      for (size_t i = lo; i < hc; i++) need[cand[i]]++;
-      for (size_t i = lo; i < hb; i++) {
-        auto it = need.find(base[i]);
-        if (it != need.end() && it->second > 0) it->second--;
-        else erased_idx.push_back((int32_t)i);
+      Flatten(candidates[c], cand);
+      // aligns the candidate with the CURRENT walk list (which stays what it is) and mirrors the windows of walks seen
+      // for the first time
+      FillAndMirrorCaches(candidates[c], cand, prev_, prev_final_end_, fe, &match);
+      // multiset difference against the current list: aligned equal walks drop out; what is left on either side (a
+      // handful of walks) is matched by content
+      un_cand.clear();
+      un_base.clear();
+      {
+        size_t x = 0;   // base walks between two matched ones are unmatched
+        for (size_t y = 0; y < match.size(); y++) {
+          if (match[y] < 0) { un_cand.push_back((int)y); continue; }
+          for (; x < (size_t)match[y]; x++) un_base.push_back((int)x);
+          x = (size_t)match[y] + 1;
+        }
+        for (; x < prev_.n(); x++) un_base.push_back((int)x);
       }
-      unordered_map<vector<int>, int> have;
-      for (size_t i = lo; i < hb; i++) have[base[i]]++;
-      for (size_t i = lo; i < hc; i++) {
-        auto it = have.find(cand[i]);
-        if (it != have.end() && it->second > 0) { it->second--; continue; }
-        added_nodes.insert(added_nodes.end(), cand[i].begin(), cand[i].end());
+      vector<char> cand_taken(un_cand.size(), 0);
+      for (size_t i = 0; i < un_base.size(); i++) {
+        bool kept = false;
+        for (size_t j = 0; j < un_cand.size() && !kept; j++)
+          if (!cand_taken[j] && SameWalk(prev_, (size_t)un_base[i], cand, (size_t)un_cand[j])) { cand_taken[j] = 1; kept = true; }
+        if (!kept) erased_idx.push_back((int32_t)un_base[i]);
+      }
+      for (size_t j = 0; j < un_cand.size(); j++) {
+        if (cand_taken[j]) continue;
+        const size_t y = (size_t)un_cand[j];
+        added_nodes.insert(added_nodes.end(), cand.nodes.begin() + cand.offs[y], cand.nodes.begin() + cand.offs[y + 1]);
         added_walk_off.push_back((int64_t)added_nodes.size());
       }
       erased_off.push_back((int64_t)erased_idx.size());
       cand_added_off.push_back((int64_t)added_walk_off.size() - 1);
     }
-    prev_paths_ = base;   // the state did not move
-    prev_final_end_ = base_final_end;
     if (erased_idx.empty()) erased_idx.push_back(0);
     if (added_nodes.empty()) added_nodes.push_back(0);
     vector<int32_t> tls(candidates.size());
@@ -384,15 +391,86 @@ class ProbCalculator {
     }
   }
 
-  void FillAndMirrorCaches(const vector<vector<int>>& paths) {
-    // which walks are new to the adapter: same position as in the previous call (one compare), else the set of all
-    // walks ever evaluated (one hash probe)
-    vector<char> is_new(paths.size(), 0);
-    vector<int> final_end(paths.size(), kNoNode);
+  // The C ABI's walk layout (and the adapter's memory of the previous call).
+  struct FlatPaths {
+    vector<int32_t> nodes;
+    vector<int64_t> offs;   // n + 1
+    size_t n() const { return offs.empty() ? 0 : offs.size() - 1; }
+    void swap(FlatPaths& o) { nodes.swap(o.nodes); offs.swap(o.offs); }
+  };
+  static void Flatten(const vector<vector<int>>& paths, FlatPaths& f) {
+    size_t total = 0;
+    for (size_t p = 0; p < paths.size(); p++) total += paths[p].size();
+    f.nodes.resize(total ? total : 1);
+    f.offs.resize(paths.size() + 1);
+    int32_t* out = f.nodes.data();
+    size_t at = 0;
+    f.offs[0] = 0;
+    for (size_t p = 0; p < paths.size(); p++) {
+      const vector<int>& w = paths[p];
+      if (!w.empty()) memcpy(out + at, w.data(), w.size() * sizeof(int32_t));
+      at += w.size();
+      f.offs[p + 1] = (int64_t)at;
+    }
+  }
+  static bool SameWalk(const FlatPaths& a, size_t x, const FlatPaths& b, size_t y) {
+    const int64_t la = a.offs[x + 1] - a.offs[x], lb = b.offs[y + 1] - b.offs[y];
+    return la == lb && (la == 0 || memcmp(a.nodes.data() + a.offs[x], b.nodes.data() + b.offs[y], (size_t)la * sizeof(int32_t)) == 0);
+  }
+  // match[y] = index of the equal walk of `old` that new walk y is aligned with, or -1: two cursors, runs of equal walks
+  // compared in blocks on the flat arrays, resynchronisation within a few walks after an edited / removed / inserted
+  // walk (indices shift when a move erases a walk: comparing position by position would miss everything behind it).
+  static void Align(const FlatPaths& old, const FlatPaths& cur, vector<int>& match) {
+    const size_t no = old.n(), nc = cur.n();
+    match.assign(nc, -1);
+    size_t x = 0, y = 0;
+    const size_t kBlock = 128;
+    while (x < no && y < nc) {
+      if (x + kBlock <= no && y + kBlock <= nc) {   // a whole block of equal walks: same boundaries (shifted), same nodes
+        const int64_t shift = cur.offs[y] - old.offs[x];
+        int64_t diff = 0;
+        for (size_t i = 1; i <= kBlock; i++) diff |= (cur.offs[y + i] - old.offs[x + i]) ^ shift;
+        if (diff == 0 && memcmp(cur.nodes.data() + cur.offs[y], old.nodes.data() + old.offs[x],
+                                (size_t)(cur.offs[y + kBlock] - cur.offs[y]) * sizeof(int32_t)) == 0) {
+          for (size_t i = 0; i < kBlock; i++) match[y + i] = (int)(x + i);
+          x += kBlock;
+          y += kBlock;
+          continue;
+        }
+      }
+      if (SameWalk(old, x, cur, y)) {
+        match[y++] = (int)x++;
+        continue;
+      }
+      size_t bdx = 0, bdy = 0;
+      bool found = false;
+      for (size_t dist = 1; dist <= 6 && !found; dist++)
+        for (size_t dx = 0; dx <= dist && !found; dx++) {
+          const size_t dy = dist - dx;
+          if (x + dx < no && y + dy < nc && SameWalk(old, x + dx, cur, y + dy)) { bdx = dx; bdy = dy; found = true; }
+        }
+      if (!found) break;   // everything from here on counts as unmatched
+      x += bdx;
+      y += bdy;
+    }
+  }
+
+  // `paths` = the caller's walks, `cur` = the same flattened, `old` / `old_final_end` = the list to compare with.
+  // Fills final_end (per walk of `cur`) and, when asked, the alignment.
+  void FillAndMirrorCaches(const vector<vector<int>>& paths, const FlatPaths& cur, const FlatPaths& old,
+                           const vector<int>& old_final_end, vector<int>& final_end, vector<int>* match_out) {
+    // which walks are new to the adapter: aligned with an equal walk of the previous list (block compares on the flat
+    // arrays), else the set of all walks ever evaluated (one hash probe)
+    vector<int>& match = match_out ? *match_out : match_;
+    if (have_prev_) Align(old, cur, match);
+    else match.assign(paths.size(), -1);
+    is_new_.assign(paths.size(), 0);
+    vector<char>& is_new = is_new_;
+    final_end.resize(paths.size());
     bool any_new = false;
     for (size_t p = 0; p < paths.size(); p++) {
-      if (p < prev_paths_.size() && prev_paths_[p] == paths[p]) {
-        final_end[p] = prev_final_end_[p];
+      if (match[p] >= 0) {
+        final_end[p] = old_final_end[(size_t)match[p]];
         continue;
       }
       auto it = seen_.find(paths[p]);
@@ -444,8 +522,6 @@ class ProbCalculator {
       for (size_t p = 0; p < paths.size(); p++)
         if (is_new[p]) seen_.emplace(paths[p], final_end[p]);
     }
-    prev_paths_ = paths;
-    prev_final_end_.swap(final_end);
   }
 
   gaml_ctx* ctx_;
@@ -453,8 +529,12 @@ class ProbCalculator {
   vector<Mirror> mirrors_;
   vector<PbMirror> pb_mirrors_;
   unordered_map<vector<int>, int> seen_;   // every walk evaluated so far -> its FinalEnd
-  vector<vector<int>> prev_paths_;
-  vector<int> prev_final_end_;
+  FlatPaths cur_, prev_;                   // this call's walks / the last evaluated ones, in the C ABI's layout
+  vector<int> prev_final_end_, cur_final_end_;
+  vector<int> match_;
+  vector<char> is_new_;
+  vector<int32_t> z_;
+  bool have_prev_ = false;
   bool had_calc_ = false;
 };
 
