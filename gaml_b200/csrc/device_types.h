@@ -106,7 +106,7 @@ struct ScoreParams {
   const uint32_t* xlist;     //   and the cross list: tier-1 reads the fast records leave to the general body (ascending read ids)
   int32_t n_cross;
   int32_t n_tier1;           //   and the number of reads tier 1 streams ([0, n_tier1) of the internal order; n_reads without one)
-  // reads that gained records since the static lists were built (cache appends, kernels.cu append_rows_kernel): flagged
+  // reads that gained records since the static lists were built (cache appends, kernels.cu append_apply_kernel): flagged
   // in `dirty` (and in their packed / fast records), skipped by every list-driven phase and scored from their rows by the
   // appendix phase instead
   const uint32_t* dirty;     // per read, or null when no append has happened since the last rebuild

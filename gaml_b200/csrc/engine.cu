@@ -337,7 +337,10 @@ struct gaml_ctx {
   DevBuf d_batch_blob, d_batch_acc, d_batch_out;   // gaml_calc_prob_batch
   DevBuf d_aln[8];                                  // gaml_pacbio_alignment_logprob
   std::vector<double> h_batch_out;
-  std::vector<char> h_append;                       // staging of a cache append's rows and groups
+  void* h_append_pinned = nullptr;                  // pinned staging of a cache append (arena records, rows, groups, lists, key-map patches)
+  size_t h_append_cap = 0;
+  cudaEvent_t ev_append = nullptr;                  // recorded behind the append's copy: the staging is reused only after it
+  bool append_copy_pending = false;
   double* h_out = nullptr;        // pinned + mapped: kResultStride doubles per set, written by the last kernel of each set
   double* d_out_mapped = nullptr; // device-side address of h_out
   std::vector<double> h_res;      // validated copy of h_out taken by finish()
@@ -752,18 +755,26 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
     if (!st.dirty || st.pending.empty()) continue;
     if (st.total_records() > 0xfffffff0ull) return 0;
     const size_t n = st.pending.size();
-    std::vector<uint32_t> order(n);
-    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    auto read_of = [&](uint32_t i) { return rs.perm_valid ? rs.h_inv[(size_t)st.pending[i].x] : (uint32_t)st.pending[i].x; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return read_of(a) < read_of(b); });
+    // group the new records by read, arena order inside a group. Grouping by the CALLER's read id is the same grouping
+    // (the internal order is a bijection) and needs no lookups while sorting; one key's records usually arrive in
+    // ascending read order already.
+    std::vector<uint64_t> order(n);
+    bool sorted = true;
+    for (size_t i = 0; i < n; i++) {
+      order[i] = ((uint64_t)(uint32_t)st.pending[i].x << 32) | (uint64_t)i;
+      sorted &= i == 0 || order[i - 1] < order[i];
+    }
+    if (!sorted) std::sort(order.begin(), order.end());
     plan[m].new_rows.resize(n);
     size_t tail = st.rows_tail;
     for (size_t i = 0; i < n;) {
-      const uint32_t r = read_of(order[i]);
+      const uint32_t caller_read = (uint32_t)(order[i] >> 32);
+      const uint32_t r = rs.perm_valid ? rs.h_inv[(size_t)caller_read] : caller_read;
       size_t j = i;
-      for (; j < n && read_of(order[j]) == r; j++) {
-        const int4& a = st.pending[order[j]];   // {read, pos, edor, key}
-        plan[m].new_rows[j] = make_int4(a.w, a.y, a.z, (int)(uint32_t)(st.arena_n + order[j]));
+      for (; j < n && (uint32_t)(order[j] >> 32) == caller_read; j++) {
+        const uint32_t src = (uint32_t)order[j];
+        const int4& a = st.pending[src];   // {read, pos, edor, key}
+        plan[m].new_rows[j] = make_int4(a.w, a.y, a.z, (int)(uint32_t)(st.arena_n + src));
       }
       const size_t cnt_old = st.h_count[r], need = cnt_old + (j - i);
       if (need >= 0x3fff || cnt_old == 0xffff) return 0;
@@ -786,78 +797,142 @@ int try_append(gaml_ctx* ctx, ReadSetState& rs) {
     return 0;
   }
   for (uint32_t r : dirty_now) rs.h_dirty[r] = 1;
-  // ---- apply ----
-  int launches = 0;
+  // ---- key maps between the mates' stores (and the combined slot table): entries that change, as (index, value) patches ----
+  std::vector<int2> p12_patch, p21_patch;
+  size_t old1 = 0, old2 = 0;
+  {
+    MateStore &s1 = rs.mate[0], &s2 = rs.mate[1];
+    const size_t k1 = s1.keys.size(), k2 = s2.keys.size();
+    old1 = rs.h_p12.size();
+    old2 = rs.h_p21.size();
+    rs.h_p12.resize(std::max<size_t>(k1, 1), -1);
+    rs.h_p21.resize(std::max<size_t>(k2, 1), -1);
+    for (size_t k = s1.built_keys; k < k1; k++) {
+      auto it = s2.key_ids.find(*s1.key_by_id[k]);
+      if (it != s2.key_ids.end()) {
+        rs.h_p12[k] = it->second;
+        rs.h_p21[(size_t)it->second] = (int32_t)k;
+        if ((size_t)it->second < std::min(old2, s2.built_keys)) p21_patch.push_back(make_int2(it->second, (int)k));   // an OLD key of the other store
+      }
+    }
+    for (size_t k = s2.built_keys; k < k2; k++) {
+      auto it = s1.key_ids.find(*s2.key_by_id[k]);
+      if (it != s1.key_ids.end()) {
+        rs.h_p21[k] = it->second;
+        rs.h_p12[(size_t)it->second] = (int32_t)k;
+        if ((size_t)it->second < std::min(old1, s1.built_keys)) p12_patch.push_back(make_int2(it->second, (int)k));
+      }
+    }
+    for (size_t k = std::min(old1, s1.built_keys); k < rs.h_p12.size(); k++) p12_patch.push_back(make_int2((int)k, rs.h_p12[k]));
+    for (size_t k = std::min(old2, s2.built_keys); k < rs.h_p21.size(); k++) p21_patch.push_back(make_int2((int)k, rs.h_p21[k]));
+  }
+  // ---- ONE staged blob (pinned), ONE copy, ONE launch ----
+  auto align16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+  size_t off = 0, arena_off[2], rows_off[2], grp_off[2];
   for (int m = 0; m < 2; m++) {
     MateStore& st = rs.mate[m];
-    if (!st.dirty) continue;
-    const size_t total = st.total_records();
-    if (!st.pending.empty()) {
+    const bool has = st.dirty && !st.pending.empty();
+    arena_off[m] = off;
+    off = align16(off + (has ? st.pending.size() * 16 : 0));
+    rows_off[m] = off;
+    off = align16(off + (has ? plan[m].new_rows.size() * 16 : 0));
+    grp_off[m] = off;
+    off = align16(off + (has ? plan[m].groups.size() * sizeof(AppendGroupHost) : 0));
+  }
+  const size_t appx_off = off;
+  off = align16(off + dirty_now.size() * 4);
+  const size_t p12_off = off;
+  off = align16(off + p12_patch.size() * sizeof(int2));
+  const size_t p21_off = off;
+  off = align16(off + p21_patch.size() * sizeof(int2));
+  const size_t blob_bytes = off;
+  if (ctx->append_copy_pending) {   // the previous append's copy reads the pinned staging
+    CU(cudaEventSynchronize(ctx->ev_append));
+    ctx->append_copy_pending = false;
+  }
+  if (blob_bytes > ctx->h_append_cap) {
+    if (ctx->h_append_pinned) cudaFreeHost(ctx->h_append_pinned);
+    ctx->h_append_pinned = nullptr;
+    ctx->h_append_cap = 0;
+    const size_t cap = std::max<size_t>(blob_bytes * 2, (size_t)1 << 18);
+    CU(cudaMallocHost(&ctx->h_append_pinned, cap));
+    ctx->h_append_cap = cap;
+  }
+  char* hb = static_cast<char*>(ctx->h_append_pinned);
+  CU(rs.d_append_blob.reserve(std::max<size_t>(blob_bytes, (size_t)1 << 18), 0, false, st_));
+  char* db = rs.d_append_blob.as<char>();
+  AppendJob J{};
+  for (int m = 0; m < 2; m++) {
+    MateStore& st = rs.mate[m];
+    const bool has = st.dirty && !st.pending.empty();
+    AppendMate& am = J.m[m];
+    if (has) {
+      const size_t total = st.total_records();
       if (rs.perm_valid)
         for (int4& v : st.pending) v.x = (int)rs.h_inv[(size_t)v.x];
       CU(st.arena.reserve(total * 16, st.arena_n * 16, false, st_));
-      CU(cudaMemcpyAsync(st.arena.as<char>() + st.arena_n * 16, st.pending.data(), st.pending.size() * 16, cudaMemcpyHostToDevice, st_));
-      // (copies from pageable host memory return once the source has been staged: the vectors may be reused right away)
-      const size_t rows_bytes = plan[m].new_rows.size() * 16, grp_bytes = plan[m].groups.size() * sizeof(AppendGroupHost);
-      std::vector<char>& hb = ctx->h_append;   // one staging copy per mate: [new rows | groups]
-      hb.resize(rows_bytes + grp_bytes);
-      memcpy(hb.data(), plan[m].new_rows.data(), rows_bytes);
-      memcpy(hb.data() + rows_bytes, plan[m].groups.data(), grp_bytes);
-      CU(rs.d_append_blob.reserve(2 * (rows_bytes + grp_bytes + 64), 0, false, st_));
-      char* blob = rs.d_append_blob.as<char>() + (size_t)m * (rs.d_append_blob.cap / 2);
-      CU(cudaMemcpyAsync(blob, hb.data(), hb.size(), cudaMemcpyHostToDevice, st_));
-      launch_append_rows(blob + rows_bytes, (int)plan[m].groups.size(), blob, st.rows.p, st.first.p, rs.d_dirty.as<uint32_t>(), rs.d_pairs.p,
-                         rs.fast_ok ? rs.d_fast.p : nullptr, st_);
-      launches++;
+      memcpy(hb + arena_off[m], st.pending.data(), st.pending.size() * 16);
+      memcpy(hb + rows_off[m], plan[m].new_rows.data(), plan[m].new_rows.size() * 16);
+      memcpy(hb + grp_off[m], plan[m].groups.data(), plan[m].groups.size() * sizeof(AppendGroupHost));
+      am.arena_src = db + arena_off[m];
+      am.arena_dst = st.arena.as<char>() + st.arena_n * 16;
+      am.n_rec = (uint32_t)st.pending.size();
+      am.groups = db + grp_off[m];
+      am.n_groups = (int)plan[m].groups.size();
+      am.new_rows = db + rows_off[m];
+      am.rows = st.rows.p;
+      am.first = st.first.p;
       for (const AppendGroupHost& g : plan[m].groups) st.h_count[g.read] = (uint16_t)(st.h_count[g.read] + g.n_new);
       st.rows_tail = plan[m].tail_after;
       st.arena_n = total;
       st.pending.clear();
     }
-    const size_t old_slots = st.slots_a.cap;
-    CU(st.slots_a.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotA), 0, true, st_));
-    CU(st.slots_b.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotB), 0, true, st_));
-    if (st.slots_a.cap != old_slots) ctx->tables_dirty = true;
-    st.dirty = false;
+    if (st.dirty) {
+      const size_t old_slots = st.slots_a.cap;
+      CU(st.slots_a.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotA), 0, true, st_));
+      CU(st.slots_b.reserve(std::max<size_t>(st.keys.size(), 1) * sizeof(SlotB), 0, true, st_));
+      if (st.slots_a.cap != old_slots) ctx->tables_dirty = true;
+      st.dirty = false;
+    }
   }
+  J.dirty = rs.d_dirty.as<uint32_t>();
+  J.pairs = rs.d_pairs.p;
+  J.fast = rs.fast_ok ? rs.d_fast.p : nullptr;
   if (!dirty_now.empty()) {
     CU(rs.d_appx.reserve(((size_t)rs.n_appx + dirty_now.size()) * 4, (size_t)rs.n_appx * 4, false, st_));
-    CU(cudaMemcpyAsync(rs.d_appx.as<uint32_t>() + rs.n_appx, dirty_now.data(), dirty_now.size() * 4, cudaMemcpyHostToDevice, st_));
+    memcpy(hb + appx_off, dirty_now.data(), dirty_now.size() * 4);
+    J.appx_src = reinterpret_cast<const uint32_t*>(db + appx_off);
+    J.appx_dst = rs.d_appx.as<uint32_t>() + rs.n_appx;
+    J.n_appx_new = (int)dirty_now.size();
     rs.n_appx += (int)dirty_now.size();
   }
-  // ---- key maps between the mates' stores and the combined slot table: the new keys only ----
   {
     MateStore &s1 = rs.mate[0], &s2 = rs.mate[1];
-    const size_t k1 = s1.keys.size(), k2 = s2.keys.size();
-    const size_t old1 = rs.h_p12.size(), old2 = rs.h_p21.size();
-    rs.h_p12.resize(std::max<size_t>(k1, 1), -1);
-    rs.h_p21.resize(std::max<size_t>(k2, 1), -1);
-    for (size_t k = s1.built_keys; k < k1; k++) {
-      auto it = s2.key_ids.find(*s1.key_by_id[k]);
-      if (it != s2.key_ids.end()) { rs.h_p12[k] = it->second; rs.h_p21[(size_t)it->second] = (int32_t)k; }
-    }
-    for (size_t k = s2.built_keys; k < k2; k++) {
-      auto it = s1.key_ids.find(*s2.key_by_id[k]);
-      if (it != s1.key_ids.end()) { rs.h_p21[k] = it->second; rs.h_p12[(size_t)it->second] = (int32_t)k; }
-    }
     const void* old_comb = rs.d_comb.p;
     const void* old_p21 = rs.d_partner21.p;
     CU(rs.d_partner12.reserve(rs.h_p12.size() * 4, old1 * 4, false, st_));
     CU(rs.d_partner21.reserve(rs.h_p21.size() * 4, old2 * 4, false, st_));
-    // (a new key of one store may be the partner of an OLD key of the other: re-send the maps from the first touched entry)
-    size_t lo1 = std::min(old1, s1.built_keys), lo2 = std::min(old2, s2.built_keys);
-    for (size_t k = s2.built_keys; k < k2; k++)
-      if (rs.h_p21[k] >= 0) lo1 = std::min(lo1, (size_t)rs.h_p21[k]);
-    for (size_t k = s1.built_keys; k < k1; k++)
-      if (rs.h_p12[k] >= 0) lo2 = std::min(lo2, (size_t)rs.h_p12[k]);
-    if (lo1 < rs.h_p12.size())
-      CU(cudaMemcpyAsync(rs.d_partner12.as<int32_t>() + lo1, rs.h_p12.data() + lo1, (rs.h_p12.size() - lo1) * 4, cudaMemcpyHostToDevice, st_));
-    if (lo2 < rs.h_p21.size())
-      CU(cudaMemcpyAsync(rs.d_partner21.as<int32_t>() + lo2, rs.h_p21.data() + lo2, (rs.h_p21.size() - lo2) * 4, cudaMemcpyHostToDevice, st_));
+    if (!p12_patch.empty()) memcpy(hb + p12_off, p12_patch.data(), p12_patch.size() * sizeof(int2));
+    if (!p21_patch.empty()) memcpy(hb + p21_off, p21_patch.data(), p21_patch.size() * sizeof(int2));
+    J.p12_patch = reinterpret_cast<const int2*>(db + p12_off);
+    J.n_p12 = (int)p12_patch.size();
+    J.p12 = rs.d_partner12.as<int32_t>();
+    J.p21_patch = reinterpret_cast<const int2*>(db + p21_off);
+    J.n_p21 = (int)p21_patch.size();
+    J.p21 = rs.d_partner21.as<int32_t>();
     CU(rs.d_comb.reserve(rs.h_p12.size() * 4 * sizeof(SlotA), 0, true, st_));   // per-evaluation contents: nothing to keep
     if (rs.d_comb.p != old_comb || rs.d_partner21.p != old_p21) ctx->tables_dirty = true;
-    s1.built_keys = k1;
-    s2.built_keys = k2;
+    s1.built_keys = s1.keys.size();
+    s2.built_keys = s2.keys.size();
+  }
+  int launches = 0;
+  if (blob_bytes) {
+    CU(cudaMemcpyAsync(db, hb, blob_bytes, cudaMemcpyHostToDevice, st_));
+    CU(cudaEventRecord(ctx->ev_append, st_));
+    ctx->append_copy_pending = true;
+    launch_append_apply(J, st_);
+    CU(cudaGetLastError());
+    launches++;
   }
   ctx->stats.kernel_launches += launches;
   rs.appends++;
@@ -2883,6 +2958,7 @@ int gaml_ctx_create(int device, gaml_ctx** out) {
     return GAML_ERR_CUDA;
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&ctx->ev_append, cudaEventDisableTiming);
   {
     // log table for table_log (kernels.cu): interval i of z in [0.6875, 1.375) -> {invc = RN(1/centre), -log(invc)}
     // with the logarithm of the ROUNDED reciprocal taken in long double, so log z = log1p(z*invc - 1) + logc exactly.
@@ -2923,6 +2999,8 @@ void gaml_ctx_destroy(gaml_ctx* ctx) {
     if (NcclApi* api = nccl_api(nullptr)) api->comm_destroy(ctx->nccl_comm);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_append) cudaEventDestroy(ctx->ev_append);
+  if (ctx->h_append_pinned) cudaFreeHost(ctx->h_append_pinned);
   cudaStream_t st = ctx->stream;
   for (auto& g : ctx->graphs) {
     if (g.second.exec) cudaGraphExecDestroy(g.second.exec);

@@ -2799,28 +2799,53 @@ __global__ void compact_copy_kernel(const uint32_t* list, int n_complex, const u
 // in `dirty`, and in its packed / fast pair record ("elsewhere") so that the list-driven phases leave it to the appendix
 // phase. One thread per affected read; the host supplies exact destinations (it keeps every read's record count).
 struct AppendGroup { uint32_t read; uint32_t new_begin; uint32_t n_new; uint32_t dst; };   // dst: new row block's first row
-__global__ void append_rows_kernel(const AppendGroup* groups, int n_groups, const int4* new_rows, int4* rows, int4* first,
-                                   uint32_t* dirty, uint4* pairs, uint4* fast) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  const AppendGroup ag = groups[g];
-  int4 f = first[ag.read];
-  const uint32_t cnt_old = f.x < 0 ? 0u : (uint32_t)((f.z >> 16) & 0x3fff);
-  const uint32_t base_old = (uint32_t)f.w;
-  for (uint32_t i = 0; i < cnt_old; i++) rows[ag.dst + i] = rows[base_old + i];
-  for (uint32_t i = 0; i < ag.n_new; i++) rows[ag.dst + cnt_old + i] = new_rows[ag.new_begin + i];
-  if (cnt_old == 0) {
-    const int4 r0 = new_rows[ag.new_begin];   // {key, pos, edor, seq}
-    f.x = r0.x;
-    f.y = r0.y;
-    f.z = r0.z & 0x4000ffff;
+// The whole of one cache append in ONE launch over one staged blob: both mates' new arena records to the arena tails,
+// both mates' relocated row blocks, the newly flagged reads onto the appendix list, the key-map entries that changed.
+// One thread per item of the concatenated index space; the parts touch disjoint memory.
+__global__ void append_apply_kernel(const AppendJob J) {
+  const uint32_t n_a0 = J.m[0].n_rec, n_a1 = J.m[1].n_rec, n_g0 = (uint32_t)J.m[0].n_groups, n_g1 = (uint32_t)J.m[1].n_groups;
+  const uint32_t total = n_a0 + n_a1 + n_g0 + n_g1 + (uint32_t)J.n_appx_new + (uint32_t)J.n_p12 + (uint32_t)J.n_p21;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t k = i;
+    if (k < n_a0) { static_cast<int4*>(J.m[0].arena_dst)[k] = static_cast<const int4*>(J.m[0].arena_src)[k]; continue; }
+    k -= n_a0;
+    if (k < n_a1) { static_cast<int4*>(J.m[1].arena_dst)[k] = static_cast<const int4*>(J.m[1].arena_src)[k]; continue; }
+    k -= n_a1;
+    if (k < n_g0 + n_g1) {
+      const int m = k < n_g0 ? 0 : 1;
+      if (m) k -= n_g0;
+      const AppendGroup ag = static_cast<const AppendGroup*>(J.m[m].groups)[k];
+      const int4* new_rows = static_cast<const int4*>(J.m[m].new_rows);
+      int4* rows = static_cast<int4*>(J.m[m].rows);
+      int4* first = static_cast<int4*>(J.m[m].first);
+      int4 f = first[ag.read];
+      const uint32_t cnt_old = f.x < 0 ? 0u : (uint32_t)((f.z >> 16) & 0x3fff);
+      const uint32_t base_old = (uint32_t)f.w;
+      for (uint32_t t = 0; t < cnt_old; t++) rows[ag.dst + t] = rows[base_old + t];
+      for (uint32_t t = 0; t < ag.n_new; t++) rows[ag.dst + cnt_old + t] = new_rows[ag.new_begin + t];
+      if (cnt_old == 0) {
+        const int4 r0 = new_rows[ag.new_begin];   // {key, pos, edor, seq}
+        f.x = r0.x;
+        f.y = r0.y;
+        f.z = r0.z & 0x4000ffff;
+      }
+      f.z = (f.z & 0x4000ffff) | (int)((cnt_old + ag.n_new) << 16);
+      f.w = (int)ag.dst;
+      first[ag.read] = f;
+      J.dirty[ag.read] = 1u;
+      // (a read that gained records on both mates is flagged by two threads: both write the same bit)
+      if (J.pairs) atomicOr(&static_cast<uint4*>(J.pairs)[ag.read].x, 0x80000000u);   // PackedPair: "tier 2" = not tier 1's
+      if (J.fast) atomicOr(&static_cast<uint4*>(J.fast)[ag.read].x, 0x80000000u);     // FastPair: "elsewhere"
+      continue;
+    }
+    k -= n_g0 + n_g1;
+    if (k < (uint32_t)J.n_appx_new) { J.appx_dst[k] = J.appx_src[k]; continue; }
+    k -= (uint32_t)J.n_appx_new;
+    if (k < (uint32_t)J.n_p12) { const int2 p = J.p12_patch[k]; J.p12[p.x] = p.y; continue; }
+    k -= (uint32_t)J.n_p12;
+    const int2 p = J.p21_patch[k];
+    J.p21[p.x] = p.y;
   }
-  f.z = (f.z & 0x4000ffff) | (int)((cnt_old + ag.n_new) << 16);
-  f.w = (int)ag.dst;
-  first[ag.read] = f;
-  dirty[ag.read] = 1u;
-  if (pairs) pairs[ag.read].x |= 0x80000000u;   // PackedPair: "tier 2" = not tier 1's
-  if (fast) fast[ag.read].x |= 0x80000000u;     // FastPair: "elsewhere"
 }
 // per-read record counts of a store after a full build (the host keeps them up to date across appends)
 __global__ void extract_counts_kernel(const int4* first, const uint32_t* rowptr, int n, uint16_t* out) {
@@ -2838,12 +2863,12 @@ int grid_for(size_t n, int block, int sm_count, int per_sm) {
 
 }  // namespace
 
-void launch_append_rows(const void* groups, int n_groups, const void* new_rows, void* rows, void* first, uint32_t* dirty, void* pairs,
-                        void* fast, cudaStream_t st) {
-  if (n_groups > 0)
-    append_rows_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(static_cast<const AppendGroup*>(groups), n_groups, static_cast<const int4*>(new_rows),
-                                                               static_cast<int4*>(rows), static_cast<int4*>(first), dirty,
-                                                               static_cast<uint4*>(pairs), static_cast<uint4*>(fast));
+void launch_append_apply(const AppendJob& J, cudaStream_t st) {
+  const size_t total = (size_t)J.m[0].n_rec + J.m[1].n_rec + (size_t)J.m[0].n_groups + (size_t)J.m[1].n_groups + (size_t)J.n_appx_new +
+                       (size_t)J.n_p12 + (size_t)J.n_p21;
+  if (total == 0) return;
+  const size_t blocks = (total + 127) / 128;
+  append_apply_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 128, 0, st>>>(J);
 }
 void launch_extract_counts(const void* first, const uint32_t* rowptr, int n, uint16_t* out, cudaStream_t st) {
   if (n > 0) extract_counts_kernel<<<(n + 255) / 256, 256, 0, st>>>(static_cast<const int4*>(first), rowptr, n, out);

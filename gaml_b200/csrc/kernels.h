@@ -85,8 +85,20 @@ cudaError_t build_fast_pairs(const void* pairs, int n, int shift, int ins_n, uin
                              void* temp, size_t temp_bytes, cudaStream_t st, int* launches);
 // Cache append (kernels.cu "cache append"): AppendGroup = {read, first new row, new rows, destination row} per affected read.
 struct AppendGroupHost { uint32_t read, new_begin, n_new, dst; };
-void launch_append_rows(const void* groups, int n_groups, const void* new_rows, void* rows, void* first, uint32_t* dirty, void* pairs,
-                        void* fast, cudaStream_t st);
+// One cache append of a paired set (append_apply_kernel): per mate the staged arena records and their place at the arena
+// tail, the groups + new rows of the reads that gained records; the reads newly on the appendix list; key-map patches.
+struct AppendMate {
+  const void* arena_src; void* arena_dst; uint32_t n_rec;
+  const void* groups; int n_groups; const void* new_rows; void* rows; void* first;
+};
+struct AppendJob {
+  AppendMate m[2];
+  uint32_t* dirty; void* pairs; void* fast;
+  const uint32_t* appx_src; uint32_t* appx_dst; int n_appx_new;
+  const int2* p12_patch; int n_p12; int32_t* p12;
+  const int2* p21_patch; int n_p21; int32_t* p21;
+};
+void launch_append_apply(const AppendJob& J, cudaStream_t st);
 void launch_extract_counts(const void* first, const uint32_t* rowptr, int n, uint16_t* out, cudaStream_t st);
 // Internal read order of a paired set with fast records (kernels.cu): sort keys from the FastPair array, radix sort,
 // inverse permutation (caller's local read id -> internal index) and the length of the fast region.
