@@ -400,11 +400,20 @@ def main():
         flush_sink.copy_(flush_view.sum())   # ... then read it back so L2 is left holding CLEAN foreign lines
         torch.cuda.synchronize()
 
+    sync_t = torch.zeros(1, dtype=torch.int64, device=dev) if world > 1 else None
+
     def rendezvous():
-        """All ranks leave together AFTER their own flush: a step's clock never contains another rank's flush."""
+        """All ranks leave together AFTER their own flush: a step's clock never contains another rank's flush. A barrier
+        alone releases the ranks tens of microseconds apart (more than the exchange costs), so rank 0 then names an instant
+        0.3 ms ahead on the node's monotonic clock and every rank spins until it."""
         if world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+            if rank == 0:
+                sync_t[0] = time.monotonic_ns() + 300_000
+            dist.broadcast(sync_t, 0)
+            t_start = int(sync_t.item())
+            while time.monotonic_ns() < t_start:
+                pass
 
     def finish_all():
         if world > 1:

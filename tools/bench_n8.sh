@@ -1,4 +1,5 @@
 #!/bin/bash
+# the whole of BASELINE config 4 on 8 GPUs, both arms (what the driver runs at N=8); results into gpurun_out/
 mkdir -p gpurun_out
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
 echo "n8 rc=$?"
