@@ -313,14 +313,7 @@ struct gaml_ctx {
   // with gaps ((base index + 1) << base_g; a walk that is not in the base list gets a label between its neighbours'), and
   // a lookup's enumeration number is label << base_s | index inside the walk, so patched lists keep the reference's
   // placement order without renumbering the resident entries. track[i] follows wsets[i].
-  struct ListTrack {
-    bool valid = false;
-    uint64_t base_gen = 0;
-    std::vector<uint32_t> label;   // per walk of the list
-    std::vector<int> removed;      // base walks that are not in the list (ascending base index)
-    int n_added = 0;               // walks of the list that are not base walks
-  };
-  ListTrack track[2];
+  gaml::ListTrack track[2];          // labels of wsets[i] (walk_set.h)
   bool patch_enabled = true;       // GAML_B200_NO_FULL_PATCH=1: every full evaluation of a changed list flattens all walks (tests)
   bool base_valid = false;
   uint64_t base_gen = 0;
@@ -1206,91 +1199,11 @@ bool patch_debug() {
   static const bool on = getenv("GAML_B200_PATCH_DEBUG") != nullptr;
   return on;
 }
-#define PATCH_NO(why)                                                          \
-  do {                                                                         \
-    if (patch_debug()) fprintf(stderr, "[gaml_b200] full patch: %s\n", why);   \
-    return false;                                                              \
-  } while (0)
-
-// Labels of the new list from the previous list's (equal walks keep theirs, run by run) along load_walks' alignment.
-// A walk that left the list is noted when it was a base walk; a walk that entered it gets its base label back when it
-// equals a missing base walk and the label fits between its neighbours', else a label in the gap between them.
-bool derive_track(gaml_ctx* ctx, const WalkSet& old, const WalkSet& ws, const WalkDiff& d, const gaml_ctx::ListTrack& tp,
-                  gaml_ctx::ListTrack& tc) {
-  const int g = ctx->base_g;
-  const uint32_t gmask = (1u << g) - 1u;
-  if ((int)tp.label.size() != old.n) PATCH_NO("label array out of step");
-  tc.label.resize((size_t)ws.n);
-  tc.removed = tp.removed;
-  tc.n_added = tp.n_added;
-  size_t io = 0, in = 0;
-  int x = 0, y = 0;
-  while (x < old.n || y < ws.n) {
-    const int nx = io < d.old_changed.size() ? d.old_changed[io] : old.n;
-    const int ny = in < d.new_changed.size() ? d.new_changed[in] : ws.n;
-    const int r = std::min(nx - x, ny - y);
-    if (r < 0) PATCH_NO("negative run");
-    if (r > 0) {
-      memcpy(tc.label.data() + y, tp.label.data() + x, sizeof(uint32_t) * (size_t)r);
-      x += r;
-      y += r;
-    }
-    bool moved = r > 0;
-    if (x == nx && x < old.n) {
-      const uint32_t lab = tp.label[x];
-      if ((lab & gmask) == 0) tc.removed.insert(std::upper_bound(tc.removed.begin(), tc.removed.end(), (int)(lab >> g) - 1), (int)(lab >> g) - 1);
-      else tc.n_added--;
-      x++;
-      io++;
-      moved = true;
-    }
-    if (y == ny && y < ws.n) {
-      tc.label[y] = 0xffffffffu;   // assigned below, once its right neighbour's label is known
-      y++;
-      in++;
-      moved = true;
-    }
-    if (!moved) PATCH_NO("no alignment");   // (lists of different length with nothing left to skip: not an alignment)
-  }
-  const uint32_t label_max = ctx->base_s >= 32 ? 0u : (uint32_t)((1ull << (32 - ctx->base_s)) - 1ull);
-  for (size_t k = 0; k < d.new_changed.size(); k++) {
-    const int yy = d.new_changed[k];
-    const uint32_t left = yy > 0 ? tc.label[yy - 1] : 0u;
-    int y2 = yy + 1;
-    while (y2 < ws.n && tc.label[y2] == 0xffffffffu) y2++;
-    const bool at_end = y2 >= ws.n;   // nothing labelled to the right: walks appended to the list count upwards
-    const uint32_t right = at_end ? label_max : tc.label[y2];
-    if (right <= left + 1) PATCH_NO("no label left in the gap");   // no label left in this gap: the next full evaluation renumbers
-    uint32_t lab = 0;
-    for (size_t q = 0; q < tc.removed.size(); q++) {
-      const int b = tc.removed[q];
-      const uint32_t bl = (uint32_t)(b + 1) << g;
-      if (bl <= left || bl >= right) continue;
-      if (ctx->base_ws.hash[b] != ws.hash[yy] || !same_walk(ctx->base_ws.view(b), ws.view(yy))) continue;
-      lab = bl;
-      tc.removed.erase(tc.removed.begin() + (long)q);
-      break;
-    }
-    if (!lab) {
-      lab = at_end ? left + 1 : left + (right - left) / 2;
-      if ((lab & gmask) == 0) {   // multiples of 2^g are the base walks' labels
-        if (lab + 1 < right) lab++;
-        else if (lab - 1 > left) lab--;
-        else PATCH_NO("gap holds only a base label");
-      }
-      tc.n_added++;
-    }
-    tc.label[yy] = lab;
-  }
-  if ((int)tc.removed.size() > kMaxPatchWalks || tc.n_added > kMaxPatchWalks) PATCH_NO("too far from the base list");
-  tc.base_gen = tp.base_gen;
-  return true;
-}
 
 // Prepares a full evaluation of cur() as the resident base blob plus a patch. Returns 1 = prepared, 0 = not applicable
 // (the caller flattens every walk), < 0 = error.
 int prepare_full_patch(gaml_ctx* ctx, int total_len) {
-  const gaml_ctx::ListTrack& tc = ctx->track[ctx->cur_set];
+  const ListTrack& tc = ctx->track[ctx->cur_set];
   const WalkSet& ws = ctx->cur();
   const int g = ctx->base_g, S = ctx->base_s;
   const uint32_t gmask = (1u << g) - 1u;
@@ -1567,11 +1480,15 @@ int prepare(gaml_ctx* ctx, const int32_t* nodes, const int64_t* offs, int n_walk
   // labels of this list relative to the resident base blob's list (patched full evaluation): followed through every
   // evaluation, full or incremental, for as long as the lists align and stay within a few walks of the base
   if (ctx->full_cache_gen != ctx->cache_gen || !ctx->full_blob_valid) ctx->base_valid = false;
-  gaml_ctx::ListTrack& track = ctx->track[ctx->cur_set];
+  ListTrack& track = ctx->track[ctx->cur_set];
   track.valid = false;
   if (ctx->base_valid && old_set && diff.valid) {
-    const gaml_ctx::ListTrack& tp = ctx->track[ctx->cur_set ^ 1];
-    if (tp.valid && tp.base_gen == ctx->base_gen) track.valid = derive_track(ctx, *old_set, ws, diff, tp, track);
+    const ListTrack& tp = ctx->track[ctx->cur_set ^ 1];
+    if (tp.valid && tp.base_gen == ctx->base_gen) {
+      const char* why = nullptr;
+      track.valid = derive_track(ctx->base_ws, ctx->base_g, ctx->base_s, kMaxPatchWalks, *old_set, ws, diff, tp, track, &why);
+      if (!track.valid && patch_debug()) fprintf(stderr, "[gaml_b200] full patch: %s\n", why ? why : "?");
+    }
     else if (patch_debug()) fprintf(stderr, "[gaml_b200] full patch: previous list not tracked (valid %d)\n", (int)tp.valid);
   } else if (patch_debug()) {
     fprintf(stderr, "[gaml_b200] full patch: no tracking (base %d, prev %d, diff %d)\n", (int)ctx->base_valid, old_set != nullptr, (int)diff.valid);

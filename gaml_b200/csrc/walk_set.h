@@ -316,4 +316,99 @@ inline bool get_changes_fast(const WalkSet& old, const WalkSet& cur, const WalkD
   return true;
 }
 
+// ---- walk labels for patched full evaluations (engine.cu "patched full evaluation") ---------------------------------
+// The slot tables of ONE base walk list stay on the device. Every walk of a later list carries a label that orders it
+// among the base walks without renumbering them: base walk b has label (b + 1) << g; a walk that is not in the base list
+// gets a label strictly between its neighbours' (appended walks count upwards), never a multiple of 2^g. Labels are
+// followed from list to list along load_walks' alignment.
+struct ListTrack {
+  bool valid = false;
+  uint64_t base_gen = 0;
+  std::vector<uint32_t> label;   // per walk of the list, strictly increasing
+  std::vector<int> removed;      // base walks that are not in the list (ascending base index)
+  int n_added = 0;               // walks of the list that are not base walks
+};
+
+// Labels of the new list `ws` from the previous list's (`old`, labels in tp) along the diff d: equal walks keep theirs,
+// run by run. A walk that left the list is noted when it was a base walk; a walk that entered it gets its base label back
+// when it equals a missing base walk and that label fits between its neighbours', else a label in the gap between them.
+// false (reason in *why) = the next full evaluation renumbers: a gap is used up, the lists do not align, or the list has
+// drifted more than max_walks walks away from the base. g / s: label spacing and the enumeration bits below a label
+// (labels stay below 2^(32 - s)).
+inline bool derive_track(const WalkSet& base, int g, int s, int max_walks, const WalkSet& old, const WalkSet& ws, const WalkDiff& d,
+                         const ListTrack& tp, ListTrack& tc, const char** why = nullptr) {
+  auto no = [&](const char* reason) {
+    if (why) *why = reason;
+    return false;
+  };
+  const uint32_t gmask = (1u << g) - 1u;
+  if (!d.valid) return no("no alignment with the previous list");
+  if ((int)tp.label.size() != old.n) return no("label array out of step");
+  tc.label.resize((size_t)ws.n);
+  tc.removed = tp.removed;
+  tc.n_added = tp.n_added;
+  size_t io = 0, in = 0;
+  int x = 0, y = 0;
+  while (x < old.n || y < ws.n) {
+    const int nx = io < d.old_changed.size() ? d.old_changed[io] : old.n;
+    const int ny = in < d.new_changed.size() ? d.new_changed[in] : ws.n;
+    const int r = std::min(nx - x, ny - y);
+    if (r < 0) return no("negative run");
+    if (r > 0) {
+      memcpy(tc.label.data() + y, tp.label.data() + x, sizeof(uint32_t) * (size_t)r);
+      x += r;
+      y += r;
+    }
+    bool moved = r > 0;
+    if (x == nx && x < old.n) {
+      const uint32_t lab = tp.label[x];
+      if ((lab & gmask) == 0) tc.removed.insert(std::upper_bound(tc.removed.begin(), tc.removed.end(), (int)(lab >> g) - 1), (int)(lab >> g) - 1);
+      else tc.n_added--;
+      x++;
+      io++;
+      moved = true;
+    }
+    if (y == ny && y < ws.n) {
+      tc.label[y] = 0xffffffffu;   // assigned below, once its right neighbour's label is known
+      y++;
+      in++;
+      moved = true;
+    }
+    if (!moved) return no("lists of different length with nothing left to skip");
+  }
+  const uint32_t label_max = s >= 32 ? 0u : (uint32_t)((1ull << (32 - s)) - 1ull);
+  for (size_t k = 0; k < d.new_changed.size(); k++) {
+    const int yy = d.new_changed[k];
+    const uint32_t left = yy > 0 ? tc.label[yy - 1] : 0u;
+    int y2 = yy + 1;
+    while (y2 < ws.n && tc.label[y2] == 0xffffffffu) y2++;
+    const bool at_end = y2 >= ws.n;   // nothing labelled to the right: walks appended to the list count upwards
+    const uint32_t right = at_end ? label_max : tc.label[y2];
+    if (right <= left + 1) return no("no label left in the gap");
+    uint32_t lab = 0;
+    for (size_t q = 0; q < tc.removed.size(); q++) {
+      const int b = tc.removed[q];
+      const uint32_t bl = (uint32_t)(b + 1) << g;
+      if (bl <= left || bl >= right) continue;
+      if (base.hash[b] != ws.hash[yy] || !same_walk(base.view(b), ws.view(yy))) continue;
+      lab = bl;
+      tc.removed.erase(tc.removed.begin() + (long)q);
+      break;
+    }
+    if (!lab) {
+      lab = at_end ? left + 1 : left + (right - left) / 2;
+      if ((lab & gmask) == 0) {   // multiples of 2^g are the base walks' labels
+        if (lab + 1 < right) lab++;
+        else if (lab - 1 > left) lab--;
+        else return no("the gap holds only a base label");
+      }
+      tc.n_added++;
+    }
+    tc.label[yy] = lab;
+  }
+  if ((int)tc.removed.size() > max_walks || tc.n_added > max_walks) return no("too far from the base list");
+  tc.base_gen = tp.base_gen;
+  return true;
+}
+
 }  // namespace gaml

@@ -1,6 +1,7 @@
 // CPU unit test: get_changes_fast (diff + container-order replica, gaml_b200/csrc/walk_set.h) must return exactly what
 // the reference's algorithm on the real std::unordered_multiset returns (get_changes_reference), over random annealing
 // style trajectories: joins, splits, tail swaps, flips, duplicates, insertions and deletions at any position.
+// Second part: the walk labels of patched full evaluations (derive_track).
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -19,6 +20,107 @@ static void flatten(const std::vector<Walk>& ws) {
     g_offs.push_back((int64_t)g_nodes.size());
   }
   if (g_nodes.empty()) g_nodes.push_back(0);
+}
+
+// Walk labels of patched full evaluations (derive_track): over random annealing-style trajectories the labels must stay
+// strictly increasing, a walk carrying a base label must BE that base walk, `removed` must list exactly the base walks
+// that carry no label in the list, and going back to the base list must restore the base labels.
+static int test_labels() {
+  std::mt19937_64 rng(777);
+  long tracked = 0, renumbered = 0, back_home = 0;
+  for (int trial = 0; trial < 200; trial++) {
+    const int alphabet = 50 + (int)(rng() % 5000);
+    const int n0 = 2 + (int)(rng() % 600);
+    std::vector<Walk> base;
+    for (int i = 0; i < n0; i++) {
+      Walk w(1 + rng() % 3);
+      for (int& x : w) x = (int)(rng() % alphabet);
+      base.push_back(w);
+    }
+    const int g = 3;
+    int bits = 0;
+    while (((uint64_t)(n0 + 2) << g) >> bits) bits++;
+    if (32 - (bits + 1) >= 12) bits++;
+    const int s = std::min(32 - bits, 20);
+    WalkSet sets[2], base_ws;
+    ListTrack tracks[2];
+    int which = 0;
+    WalkDiff d;
+    flatten(base);
+    load_walks(sets[which], nullptr, g_nodes.data(), g_offs.data(), (int)base.size(), d);
+    base_ws = sets[which];
+    auto rebase = [&](const WalkSet& ws, ListTrack& t) {
+      base_ws = ws;
+      t.valid = true;
+      t.base_gen++;
+      t.removed.clear();
+      t.n_added = 0;
+      t.label.resize((size_t)ws.n);
+      for (int i = 0; i < ws.n; i++) t.label[(size_t)i] = (uint32_t)(i + 1) << g;
+    };
+    rebase(sets[which], tracks[which]);
+    std::vector<Walk> cur = base, home = base;
+    for (int step = 0; step < 80; step++) {
+      std::vector<Walk> nw = cur;
+      const int kind = (int)(rng() % 7);
+      auto pick = [&]() { return (size_t)(rng() % nw.size()); };
+      if (kind == 0 && nw.size() >= 2) {            // join (replace one, erase the other)
+        size_t i = pick(), j = pick();
+        if (i != j) { nw[i].insert(nw[i].end(), nw[j].begin(), nw[j].end()); nw.erase(nw.begin() + (long)j); }
+      } else if (kind == 1) {                       // split: second part appended
+        size_t i = pick();
+        if (nw[i].size() >= 2) { Walk tail(nw[i].begin() + 1, nw[i].end()); nw[i].resize(1); nw.push_back(tail); }
+      } else if (kind == 2) {                       // edit in place
+        size_t i = pick();
+        nw[i].push_back((int)(rng() % alphabet));
+      } else if (kind == 3) {                       // insert in the middle
+        nw.insert(nw.begin() + (long)(rng() % (nw.size() + 1)), Walk(1, (int)(rng() % alphabet)));
+      } else if (kind == 4 && nw.size() >= 2) {     // erase
+        nw.erase(nw.begin() + (long)pick());
+      } else if (kind == 5) {                       // back to the base list
+        nw = home;
+      }                                             // kind 6: the same list again
+      if (nw.empty()) nw.push_back(Walk(1, 0));
+      flatten(nw);
+      WalkSet& nxt = sets[which ^ 1];
+      load_walks(nxt, &sets[which], g_nodes.data(), g_offs.data(), (int)nw.size(), d);
+      ListTrack& tc = tracks[which ^ 1];
+      const ListTrack& tp = tracks[which];
+      tc.valid = tp.valid && d.valid && derive_track(base_ws, g, s, 64, sets[which], nxt, d, tp, tc);
+      if (tc.valid) {
+        tracked++;
+        const uint32_t gmask = (1u << g) - 1u, label_max = (uint32_t)((1ull << (32 - s)) - 1ull);
+        std::vector<char> present((size_t)base_ws.n, 0);
+        int added = 0;
+        for (int i = 0; i < nxt.n; i++) {
+          const uint32_t lab = tc.label[(size_t)i];
+          if (i > 0 && tc.label[(size_t)i - 1] >= lab) { printf("FAIL: labels not increasing (trial %d step %d)\n", trial, step); return 1; }
+          if (lab == 0 || lab > label_max) { printf("FAIL: label out of range\n"); return 1; }
+          if ((lab & gmask) == 0) {
+            const int b = (int)(lab >> g) - 1;
+            if (b < 0 || b >= base_ws.n || !same_walk(base_ws.view(b), nxt.view(i))) { printf("FAIL: base label on another walk\n"); return 1; }
+            present[(size_t)b] = 1;
+          } else {
+            added++;
+          }
+        }
+        if (added != tc.n_added) { printf("FAIL: n_added %d != %d\n", tc.n_added, added); return 1; }
+        std::vector<int> gone;
+        for (int b = 0; b < base_ws.n; b++)
+          if (!present[(size_t)b]) gone.push_back(b);
+        if (gone != tc.removed) { printf("FAIL: removed list (trial %d step %d)\n", trial, step); return 1; }
+        if (nw == home && tc.n_added == 0 && tc.removed.empty()) back_home++;
+      } else {
+        renumbered++;
+        rebase(nxt, tc);   // what a full evaluation does when the labels cannot be kept
+        home = nw;
+      }
+      which ^= 1;
+      cur.swap(nw);
+    }
+  }
+  printf("OK labels: %ld lists tracked, %ld renumbered, %ld returns to the base list recognised\n", tracked, renumbered, back_home);
+  return tracked > 5 * renumbered && back_home > 100 ? 0 : 1;
 }
 
 int main() {
@@ -125,5 +227,6 @@ int main() {
   }
   printf("OK: %ld evaluations, fast path %ld (%.0f%%), %ld with two or more erased walks\n", checked, fast_used,
          100.0 * (double)fast_used / (double)checked, multi_erased);
-  return fast_used * 2 > checked ? 0 : 1;
+  if (fast_used * 2 <= checked) return 1;
+  return test_labels();
 }
