@@ -28,6 +28,7 @@
 #include <unordered_map>
 #include <unordered_set>
 
+#include "flat_paths.h"
 #include "gaml_b200.h"
 #include "graph.h"
 #include "utility.h"
@@ -73,7 +74,7 @@ class ProbCalculator {
     if (!ctx_) Init();   // lazy: gaml.cc constructs the calculator before PrepareReads fills the read sets
     // ONE pass over the caller's vector-of-vectors: the flat arrays the C ABI takes. Everything else the adapter does per
     // call (which walks are new, FinalEnd bookkeeping) works on these arrays against the previous call's.
-    Flatten(paths, cur_);
+    gaml_flat::Flatten(paths, cur_);
     FillAndMirrorCaches(paths, cur_, prev_, prev_final_end_, cur_final_end_, NULL);
     z_.assign(2 * (n_sets_ ? n_sets_ : 1), 0);
     gaml_result res;
@@ -112,40 +113,17 @@ class ProbCalculator {
     }
     vector<int32_t> erased_idx, added_nodes;
     vector<int64_t> erased_off(1, 0), added_walk_off(1, 0), cand_added_off(1, 0);
-    FlatPaths cand;
+    gaml_flat::FlatPaths cand;
     vector<int> fe, match;
     vector<int> un_base, un_cand;   // walks without an equal partner at the aligned position
     for (size_t c = 0; c < candidates.size(); c++) {
-      Flatten(candidates[c], cand);
+      gaml_flat::Flatten(candidates[c], cand);
       // aligns the candidate with the CURRENT walk list (which stays what it is) and mirrors the windows of walks seen
       // for the first time
       FillAndMirrorCaches(candidates[c], cand, prev_, prev_final_end_, fe, &match);
       // multiset difference against the current list: aligned equal walks drop out; what is left on either side (a
       // handful of walks) is matched by content
-      un_cand.clear();
-      un_base.clear();
-      {
-        size_t x = 0;   // base walks between two matched ones are unmatched
-        for (size_t y = 0; y < match.size(); y++) {
-          if (match[y] < 0) { un_cand.push_back((int)y); continue; }
-          for (; x < (size_t)match[y]; x++) un_base.push_back((int)x);
-          x = (size_t)match[y] + 1;
-        }
-        for (; x < prev_.n(); x++) un_base.push_back((int)x);
-      }
-      vector<char> cand_taken(un_cand.size(), 0);
-      for (size_t i = 0; i < un_base.size(); i++) {
-        bool kept = false;
-        for (size_t j = 0; j < un_cand.size() && !kept; j++)
-          if (!cand_taken[j] && SameWalk(prev_, (size_t)un_base[i], cand, (size_t)un_cand[j])) { cand_taken[j] = 1; kept = true; }
-        if (!kept) erased_idx.push_back((int32_t)un_base[i]);
-      }
-      for (size_t j = 0; j < un_cand.size(); j++) {
-        if (cand_taken[j]) continue;
-        const size_t y = (size_t)un_cand[j];
-        added_nodes.insert(added_nodes.end(), cand.nodes.begin() + cand.offs[y], cand.nodes.begin() + cand.offs[y + 1]);
-        added_walk_off.push_back((int64_t)added_nodes.size());
-      }
+      gaml_flat::Difference(prev_, cand, match, un_base, un_cand, erased_idx, added_nodes, added_walk_off);
       erased_off.push_back((int64_t)erased_idx.size());
       cand_added_off.push_back((int64_t)added_walk_off.size() - 1);
     }
@@ -164,6 +142,7 @@ class ProbCalculator {
   Graph& gr;
 
  private:
+  typedef gaml_flat::FlatPaths FlatPaths;
   struct Mirror {   // one ReadSet <-> one (set, mate) store of the library
     ReadSet* rs;
     int set, mate;
@@ -391,70 +370,6 @@ class ProbCalculator {
     }
   }
 
-  // The C ABI's walk layout (and the adapter's memory of the previous call).
-  struct FlatPaths {
-    vector<int32_t> nodes;
-    vector<int64_t> offs;   // n + 1
-    size_t n() const { return offs.empty() ? 0 : offs.size() - 1; }
-    void swap(FlatPaths& o) { nodes.swap(o.nodes); offs.swap(o.offs); }
-  };
-  static void Flatten(const vector<vector<int>>& paths, FlatPaths& f) {
-    size_t total = 0;
-    for (size_t p = 0; p < paths.size(); p++) total += paths[p].size();
-    f.nodes.resize(total ? total : 1);
-    f.offs.resize(paths.size() + 1);
-    int32_t* out = f.nodes.data();
-    size_t at = 0;
-    f.offs[0] = 0;
-    for (size_t p = 0; p < paths.size(); p++) {
-      const vector<int>& w = paths[p];
-      if (!w.empty()) memcpy(out + at, w.data(), w.size() * sizeof(int32_t));
-      at += w.size();
-      f.offs[p + 1] = (int64_t)at;
-    }
-  }
-  static bool SameWalk(const FlatPaths& a, size_t x, const FlatPaths& b, size_t y) {
-    const int64_t la = a.offs[x + 1] - a.offs[x], lb = b.offs[y + 1] - b.offs[y];
-    return la == lb && (la == 0 || memcmp(a.nodes.data() + a.offs[x], b.nodes.data() + b.offs[y], (size_t)la * sizeof(int32_t)) == 0);
-  }
-  // match[y] = index of the equal walk of `old` that new walk y is aligned with, or -1: two cursors, runs of equal walks
-  // compared in blocks on the flat arrays, resynchronisation within a few walks after an edited / removed / inserted
-  // walk (indices shift when a move erases a walk: comparing position by position would miss everything behind it).
-  static void Align(const FlatPaths& old, const FlatPaths& cur, vector<int>& match) {
-    const size_t no = old.n(), nc = cur.n();
-    match.assign(nc, -1);
-    size_t x = 0, y = 0;
-    const size_t kBlock = 128;
-    while (x < no && y < nc) {
-      if (x + kBlock <= no && y + kBlock <= nc) {   // a whole block of equal walks: same boundaries (shifted), same nodes
-        const int64_t shift = cur.offs[y] - old.offs[x];
-        int64_t diff = 0;
-        for (size_t i = 1; i <= kBlock; i++) diff |= (cur.offs[y + i] - old.offs[x + i]) ^ shift;
-        if (diff == 0 && memcmp(cur.nodes.data() + cur.offs[y], old.nodes.data() + old.offs[x],
-                                (size_t)(cur.offs[y + kBlock] - cur.offs[y]) * sizeof(int32_t)) == 0) {
-          for (size_t i = 0; i < kBlock; i++) match[y + i] = (int)(x + i);
-          x += kBlock;
-          y += kBlock;
-          continue;
-        }
-      }
-      if (SameWalk(old, x, cur, y)) {
-        match[y++] = (int)x++;
-        continue;
-      }
-      size_t bdx = 0, bdy = 0;
-      bool found = false;
-      for (size_t dist = 1; dist <= 6 && !found; dist++)
-        for (size_t dx = 0; dx <= dist && !found; dx++) {
-          const size_t dy = dist - dx;
-          if (x + dx < no && y + dy < nc && SameWalk(old, x + dx, cur, y + dy)) { bdx = dx; bdy = dy; found = true; }
-        }
-      if (!found) break;   // everything from here on counts as unmatched
-      x += bdx;
-      y += bdy;
-    }
-  }
-
   // `paths` = the caller's walks, `cur` = the same flattened, `old` / `old_final_end` = the list to compare with.
   // Fills final_end (per walk of `cur`) and, when asked, the alignment.
   void FillAndMirrorCaches(const vector<vector<int>>& paths, const FlatPaths& cur, const FlatPaths& old,
@@ -462,7 +377,7 @@ class ProbCalculator {
     // which walks are new to the adapter: aligned with an equal walk of the previous list (block compares on the flat
     // arrays), else the set of all walks ever evaluated (one hash probe)
     vector<int>& match = match_out ? *match_out : match_;
-    if (have_prev_) Align(old, cur, match);
+    if (have_prev_) gaml_flat::Align(old, cur, match);
     else match.assign(paths.size(), -1);
     is_new_.assign(paths.size(), 0);
     vector<char>& is_new = is_new_;

@@ -169,3 +169,14 @@ def test_fast_get_changes_equals_the_reference_container():
     out = subprocess.run([entry.CHANGES_TEST_BIN], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("OK"), out.stdout
+
+
+def test_dropin_list_bookkeeping():
+    """tests/cpp/test_flat_paths.cc: the drop-in ProbCalculator's flat walk lists (integration/flat_paths.h) — alignment with
+    the previous call's list and the multiset difference handed to gaml_calc_prob_batch — over 12 000 random candidate
+    lists (CPU only)."""
+    import __graft_entry__ as entry
+    entry.build()
+    out = subprocess.run([entry.FLAT_TEST_BIN], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK"), out.stdout
