@@ -143,7 +143,11 @@ int gaml_cache_insert_pacbio(gaml_ctx* ctx, int set, const int32_t* key, int32_t
                              const gaml_pacbio_alignment* records, int64_t n_records);
 /* 1 if the key is present (aligment_cache_.count(key)), 0 if not, <0 on error. */
 int gaml_cache_contains(gaml_ctx* ctx, int set, int mate, const int32_t* key, int32_t key_len);
-/* Uploads staged inserts and rebuilds the per-read CSR on the device (also done lazily by CalcProb). */
+/* Uploads staged inserts (also done lazily by CalcProb). The first commit of a set builds its device index (read-major
+ * rows, packed pair records, term table, internal read order); later ones — the annealing loop inserts the windows of a
+ * new join — are applied in O(new records): records appended to the arena, the affected reads' rows relocated, the reads
+ * handed to an appendix phase (gaml_stats.cache_appends); the index is rebuilt only when the appendix or the row slack
+ * is full (gaml_stats.cache_rebuilds). */
 int gaml_cache_commit(gaml_ctx* ctx);
 
 /* PacBio alignment probability on the device (PacbioReadSet::AligmentProbability, graph.cc:2175-2297; the value
@@ -187,8 +191,11 @@ int gaml_combine_partials_raw(const double* gathered, int32_t n_shards, int32_t 
                               const int64_t* n_reads_total, const double* weights, int32_t total_len,
                               gaml_result* result, int32_t* zeros);
 
-/* Three-phase form of gaml_calc_prob_partial for measurement: prepare = host flattening + H2D of the
- * per-evaluation tables; launch = the kernels (asynchronous, on gaml_ctx_stream); finish = D2H + sync. */
+/* Three-phase form of gaml_calc_prob_partial for measurement: prepare = host side (the walk list is diffed against the
+ * previous evaluation's, the lookups of the CHANGED walks are flattened, the per-evaluation tables go to the device with
+ * one copy; a full evaluation of a list a few walks away from the one whose tables are resident uploads only a patch,
+ * gaml_stats.full_patch_evals); launch = the kernels (one CUDA-graph submission on gaml_ctx_stream); finish = wait for the
+ * 64-byte result line the last block writes into host-mapped memory. GAML_ERR_STATE if an evaluation is still in flight. */
 int gaml_eval_prepare(gaml_ctx* ctx, const int32_t* walk_nodes, const int64_t* walk_offsets, int32_t n_walks);
 int gaml_eval_launch(gaml_ctx* ctx);
 int gaml_eval_finish(gaml_ctx* ctx, double* partials, int32_t* total_len);
